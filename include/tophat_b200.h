@@ -1,0 +1,226 @@
+/*
+ * tophat_b200.h -- C ABI of libtophat_b200.so
+ *
+ * The drop-in boundary of the B200-native splice-junction hot path.  The reference (TopHat 2.1.2)
+ * exposes this path only as two executables (segment_juncs, long_spanning_reads) driven by
+ * tophat.py; our replacements of those executables are thin C++ hosts that do argv/BAM/FASTA/text
+ * I/O and call the entry points below for every per-read computation.  Each entry point names the
+ * reference function(s) it replaces (paths relative to the reference tree, src/...).
+ *
+ * Conventions
+ *   - plain C, POD structs, pointers + sizes only; no C++/torch types cross the boundary;
+ *   - every function returns 0 on success and a negative THB_E* code on failure; the message is
+ *     available from thb_last_error(); the library never calls exit();
+ *   - the caller owns every host buffer it passes in; the context owns all device memory;
+ *   - one context per process per device; a context is not re-entrant;
+ *   - there is NO CPU fallback: without a usable sm_100 device thb_create() fails.
+ *
+ * Coordinates are the reference's: 0-based, `left` inclusive, `right` as BowtieHit::right()
+ * (bwt_map.h:213-243, one past the last aligned reference base).  Reference ids are 1-based in
+ * SAM-header order (bwt_map.h:608-674); id 0 is "none".
+ */
+#ifndef TOPHAT_B200_H
+#define TOPHAT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THB_OK              0
+#define THB_ENODEVICE      -1   /* no CUDA device / wrong architecture            */
+#define THB_ECUDA          -2   /* a CUDA runtime call failed                     */
+#define THB_EINVAL         -3   /* malformed argument / batch                     */
+#define THB_ENOMEM         -4   /* host or device allocation failed               */
+#define THB_EUNSUPPORTED   -5   /* parameter combination outside the GPU path     */
+#define THB_ESTATE         -6   /* call sequence error (e.g. no reference loaded) */
+#define THB_ENCCL          -7   /* NCCL failure                                   */
+
+typedef struct thb_ctx thb_ctx;
+
+/* ---- option globals consumed on the hot path (common.cpp:79-180, parsed at common.cpp:459-721) */
+typedef struct thb_params {
+  int32_t segment_length;             /* --segment-length            (common.cpp:121) 25      */
+  int32_t segment_mismatches;         /* --segment-mismatches        (common.cpp:122) 2       */
+  int32_t min_segment_intron_length;  /* --min-segment-intron        (common.cpp:115) 50      */
+  int32_t max_segment_intron_length;  /* --max-segment-intron        (common.cpp:116) 500000  */
+  int32_t max_insertion_length;       /* --max-insertion-length      (common.cpp:98)  3       */
+  int32_t max_deletion_length;        /* --max-deletion-length       (common.cpp:99)  3       */
+  int32_t max_seg_multihits;          /* --max-seg-multihits         (common.cpp:135) 40      */
+  int32_t inner_dist_mean;            /* --inner-dist-mean           (common.cpp:101) 200     */
+  int32_t inner_dist_std_dev;         /* --inner-dist-std-dev        (common.cpp:102) 20      */
+  int32_t bowtie2;                    /* 0 with --bowtie1            (common.cpp:79)  1       */
+  int32_t library_type;               /* eLIBRARY_TYPE (common.h): 0 none, 1 fr-unstranded,
+                                         2 fr-firststrand, 3 fr-secondstrand, 4.. ff-*        */
+  int32_t fusion_search;              /* --fusion-search             (common.cpp:171) 0       */
+  int32_t fusion_anchor_length;       /* --fusion-anchor-length      (common.cpp:172) 20      */
+  int32_t fusion_min_dist;            /* --fusion-min-dist           (common.cpp:173) 10000000*/
+  /* long_spanning_reads only */
+  int32_t max_report_intron_length;   /* --max-report-intron         (common.cpp:107) 500000  */
+  int32_t min_report_intron_length;   /* --min-report-intron         (common.cpp:106) 50      */
+  int32_t min_anchor_len;             /* --min-anchor                (common.cpp:105) 8       */
+  int32_t read_mismatches;            /* --read-mismatches           (common.cpp:123) 2       */
+  int32_t read_gap_length;            /* --read-gap-length           (common.cpp:124) 2       */
+  int32_t read_edit_dist;             /* --read-edit-dist            (common.cpp:125) 2       */
+  int32_t bowtie2_max_penalty;        /* (common.cpp:87) 6 */
+  int32_t bowtie2_min_penalty;        /* (common.cpp:88) 2 */
+  int32_t bowtie2_penalty_for_N;      /* (common.cpp:89) 1 */
+  int32_t bowtie2_read_gap_open;      /* (common.cpp:90) 5 */
+  int32_t bowtie2_read_gap_cont;      /* (common.cpp:91) 3 */
+  int32_t bowtie2_ref_gap_open;       /* (common.cpp:92) 5 */
+  int32_t bowtie2_ref_gap_cont;       /* (common.cpp:93) 3 */
+  int32_t reserved[5];
+} thb_params;
+
+/* Fills *p with the reference binaries' defaults (common.cpp:79-180). */
+void thb_params_default(thb_params* p);
+
+/* ---- device context ---------------------------------------------------------------------------*/
+
+/* Creates a context on CUDA device `device` (must be compute capability 10.x). */
+int  thb_create(int device, thb_ctx** out);
+void thb_destroy(thb_ctx* ctx);
+const char* thb_last_error(const thb_ctx* ctx);   /* ctx may be NULL: last creation error */
+const char* thb_version(void);
+
+/* ---- reference genome image ---------------------------------------------------------------------
+ * Replaces RefSequenceTable + get_seqs (bwt_map.h:579-788; segment_juncs.cpp:64-88): the genome
+ * as bit planes instead of seqan::String<Dna5,Packed<>>.
+ *
+ * Global base coordinate g = contig_start[id-1] + pos.  contig_start[] are multiples of 64 and
+ * leave >= 64 bases of zero padding after every contig.  For every 64-base block b:
+ *   planes[2*b+0] bit j = low  bit of the 2-bit code of base 64*b+j   (A=0 C=1 G=2 T=3)
+ *   planes[2*b+1] bit j = high bit
+ *   nmask[b]      bit j = 1 if the FASTA byte was not one of ACGTUacgtu (SeqAn Dna5 'N',
+ *                         alphabet_residue_tabs.h:107-140); such bases carry code 0 in `planes`,
+ *                         which is exactly the Dna5->Dna conversion (`& 3`) the junction scan and
+ *                         insertion search apply (segment_juncs.cpp:2157, 2499).
+ */
+typedef struct thb_ref_image {
+  uint32_t        n_contigs;
+  const uint64_t* contig_start;   /* [n_contigs] global coordinate of base 0 of each contig    */
+  const uint32_t* contig_len;     /* [n_contigs] 0 = id known from the SAM header, no sequence */
+  uint64_t        n_blocks;       /* number of 64-base blocks                                  */
+  const uint64_t* planes;         /* [2*n_blocks]                                              */
+  const uint64_t* nmask;          /* [n_blocks]                                                */
+} thb_ref_image;
+
+int thb_ref_upload(thb_ctx* ctx, const thb_ref_image* img);
+
+/* Host helper: packs `len` FASTA bytes of one contig (no newlines) into planes/nmask at global
+ * coordinate `gstart` (multiple of 64).  Buffers must be zero-initialised by the caller.       */
+void thb_pack_bases(const char* seq, uint64_t len, uint64_t gstart, uint64_t* planes, uint64_t* nmask);
+
+/* ---- segment_juncs batch ------------------------------------------------------------------------
+ * One thb_bundle = one call of find_insertions_and_deletions / find_fusions / find_gaps for one
+ * read, i.e. the `hits_for_read` vector that look_for_hit_group / process_next_hit_group
+ * (segment_juncs.cpp:3823-4123) assemble, plus the partner hit group find_gaps looks up
+ * (segment_juncs.cpp:3322-3344).  Bundles are stored in the reference's processing order.
+ */
+typedef struct thb_hit {          /* the BowtieHit fields the path reads (bwt_map.h:78-536)      */
+  uint32_t ref_id;                /* ref_id()                                                    */
+  int32_t  left;                  /* left()                                                      */
+  int32_t  right;                 /* right()                                                     */
+  uint8_t  read_len;              /* read_len()                                                  */
+  uint8_t  edit_dist;             /* edit_dist()                                                 */
+  uint8_t  flags;                 /* THB_HIT_*                                                   */
+  uint8_t  reserved;
+} thb_hit;                        /* 16 bytes */
+
+#define THB_HIT_ANTISENSE  0x01   /* antisense_align() */
+#define THB_HIT_END        0x02   /* end()             */
+
+typedef struct thb_bundle {
+  uint32_t read_id;               /* insert_id                                                   */
+  uint32_t hit_begin;             /* first hit of segment 0 in hits[]; segments follow in order  */
+  uint32_t partner_begin;         /* first partner hit in partner_hits[]                         */
+  uint16_t n_partner;             /* partner group size; 0 <=> !has_partner                      */
+  uint8_t  read_len;              /* bases in the read                                           */
+  uint8_t  flags;                 /* THB_BUNDLE_*                                                */
+} thb_bundle;                     /* 16 bytes */
+
+#define THB_BUNDLE_INDELS        0x01  /* run find_insertions_and_deletions (2807-2942)          */
+#define THB_BUNDLE_GAPS          0x02  /* run find_gaps (3293-3650)                              */
+#define THB_BUNDLE_FUSIONS       0x04  /* run find_fusions (2976-3291)                           */
+#define THB_BUNDLE_FUSIONS_LAST  0x08  /* find_fusions sees the bundle as mutated by find_gaps
+                                          (different-group branch, 4005-4033)                    */
+#define THB_BUNDLE_RIGHT_MATE    0x10  /* eREAD read_side == READ_RIGHT (segments.h:12-17)       */
+
+typedef struct thb_segjuncs_batch {
+  uint32_t          n_bundles;
+  uint32_t          n_segs;        /* number of segment files (hits_for_read.size())             */
+  uint32_t          read_words;    /* 64-bit words per bit plane of a read = ceil(maxlen/64)     */
+  uint32_t          reserved;
+  const thb_bundle* bundles;       /* [n_bundles]                                                */
+  const uint16_t*   seg_count;     /* [n_bundles*n_segs] hits per segment                        */
+  const uint64_t*   reads;         /* [n_bundles*3*read_words]: plane0 | plane1 | planeN words;
+                                      bit j of word w = base 64*w+j; planeN set for every read
+                                      byte outside ACGT (such bases have code 0)                 */
+  uint64_t          n_hits;
+  const thb_hit*    hits;          /* [n_hits]                                                   */
+  uint64_t          n_partner_hits;
+  const thb_hit*    partner_hits;  /* [n_partner_hits]                                           */
+  uint64_t          order_base;    /* added to the bundle index to form the insertion
+                                      first-wins priority (insertions.h:52-67): lower wins       */
+} thb_segjuncs_batch;
+
+/* Host helper: packs an ASCII read into the three planes (read_words words each). */
+void thb_pack_read(const char* seq, uint32_t len, uint32_t read_words, uint64_t* out3planes);
+
+/* Result records.  Same value types and orderings as junctions.h:27-80, deletions.h:26,
+ * insertions.h:31-74, fusions.h:24-116.                                                         */
+typedef struct thb_junction { uint32_t ref_id; uint32_t left; uint32_t right; uint32_t antisense; } thb_junction;
+typedef struct thb_insertion { uint32_t ref_id; uint32_t left; uint32_t len; char seq[20]; } thb_insertion;
+typedef struct thb_fusion { uint32_t ref_id1; uint32_t ref_id2; uint32_t left; uint32_t right;
+                            uint32_t dir; uint32_t count; uint32_t edit_dist; uint32_t reserved; } thb_fusion;
+
+typedef struct thb_segjuncs_results {
+  uint64_t            n_junctions;  const thb_junction*  junctions;   /* Junction order          */
+  uint64_t            n_deletions;  const thb_junction*  deletions;   /* as Deletion(ref,l,r)    */
+  uint64_t            n_insertions; const thb_insertion* insertions;  /* (ref,left,len) order    */
+  uint64_t            n_fusions;    const thb_fusion*    fusions;     /* Fusion order            */
+} thb_segjuncs_results;
+
+/* Clears the accumulated junction / deletion / insertion / fusion sets of the context. */
+int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* params);
+
+/* Processes one batch whose arrays live in HOST memory (copied to the device inside the call).
+ * Replaces, for every bundle, find_insertions_and_deletions -> detect_small_{deletion,insertion}
+ * -> simpleSplitAlignment (2807-2942, 2554-2627, 2470-2541, 2390-2456), find_gaps (3293-3650)
+ * with map_read_to_contig (2946-2973) and juncs_from_ref_segs<RecordSegmentJuncs> for GT-AG,
+ * GC-AG, AT-AC (2051-2377, 1669-1696), and find_fusions/detect_fusion (2976-3291, 2629-2805). */
+int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* host_batch);
+
+/* Same, for a batch whose arrays already live in DEVICE memory of ctx's device.               */
+int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* device_batch);
+
+/* Sorts and de-duplicates the accumulated sets (the std::set semantics of 4907-4922, insertion
+ * first-wins, the max_seg_juncs cap of 58/1692-1693) and returns host pointers owned by ctx,
+ * valid until the next thb_segjuncs_begin / thb_destroy.                                       */
+int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out);
+
+/* Multi-GPU exchange (replaces the per-thread set union at 4911-4922): all-gathers the
+ * de-duplicated junction/deletion/insertion/fusion sets of every rank over NCCL and merges them,
+ * after which thb_segjuncs_finish returns the union on every rank.  `nccl_unique_id` is the 128
+ * byte ncclUniqueId obtained on rank 0 via thb_nccl_unique_id and distributed by the caller.   */
+int thb_nccl_unique_id(void* out128);
+int thb_comm_init(thb_ctx* ctx, const void* nccl_unique_id128, int rank, int world);
+int thb_segjuncs_allgather(thb_ctx* ctx);
+
+/* Kernel timing of the last submit (CUDA events on the context's stream), milliseconds.        */
+typedef struct thb_timing {
+  float h2d_ms; float scan_kernel_ms; float finish_ms; float total_ms;
+  uint64_t n_windows; uint64_t n_indel_tasks; uint64_t n_rescue_tasks; uint64_t n_juncs_emitted;
+  uint64_t algorithmic_bytes; uint32_t kernel_launches; uint32_t reserved;
+} thb_timing;
+int thb_last_timing(thb_ctx* ctx, thb_timing* out);
+
+/* Raw access for the measurement harness: CUDA stream of the context (cudaStream_t as void*). */
+void* thb_stream(thb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPHAT_B200_H */

@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for oracle/segjuncs_oracle.c and runner for the
+reference's own CPU binaries built into oracle/_ref/ by oracle/Makefile.ref.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  Nothing under tophat_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from typing import Dict, List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from tophat_b200 import capi, synth  # noqa: E402  (struct mirrors only; no product compute)
+
+BUILD_DIR = os.path.join(_HERE, "_build")
+ORACLE_SO = os.path.join(BUILD_DIR, "liboracle.so")
+REF_DIR = os.path.join(_HERE, "_ref")
+
+
+def build_oracle(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, "segjuncs_oracle.c")]
+    join_src = os.path.join(_HERE, "join_oracle.c")
+    if os.path.exists(join_src):
+        srcs.append(join_src)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    newest = max(os.path.getmtime(s) for s in srcs + [os.path.join(_ROOT, "include", "tophat_b200.h")])
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < newest:
+        cmd = ["gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-Wall", "-Wno-unused-function",
+               "-o", ORACLE_SO] + srcs
+        subprocess.run(cmd, check=True)
+    return ORACLE_SO
+
+
+def build_reference() -> bool:
+    """Builds oracle/_ref when the reference tree is present (this container only)."""
+    if not os.path.isdir("/root/reference/src"):
+        return have_reference()
+    subprocess.run(["make", "-s", "-f", os.path.join("oracle", "Makefile.ref"), "-j8"], cwd=_ROOT, check=True)
+    return have_reference()
+
+
+def have_reference() -> bool:
+    return all(os.path.exists(os.path.join(REF_DIR, p)) for p in
+               ("segment_juncs", "long_spanning_reads", "prep_reads", "fix_map_ordering", "juncs_db"))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_results_new.restype = C.c_void_p
+        L.orc_results_free.argtypes = [C.c_void_p]
+        L.orc_segjuncs_batch.argtypes = [C.POINTER(capi.Params), C.POINTER(capi.RefImageC), C.POINTER(capi.BatchC), C.c_void_p]
+        L.orc_segjuncs_finish.argtypes = [C.c_void_p]
+        for n in ("orc_n_juncs", "orc_n_dels", "orc_n_ins", "orc_n_fus"):
+            getattr(L, n).argtypes = [C.c_void_p]
+            getattr(L, n).restype = C.c_size_t
+        for n in ("orc_get_juncs", "orc_get_dels", "orc_get_ins", "orc_get_fus", "orc_get_counters"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+            getattr(L, n).restype = None
+        _lib = L
+    return _lib
+
+
+class Counters:
+    def __init__(self, a):
+        self.n_windows, self.n_indel_tasks, self.n_rescue_tasks, self.n_fusion_tasks, self.n_juncs_emitted = [int(x) for x in a]
+
+
+def segjuncs(params: capi.Params, ref: synth.RefImage, batches: List[synth.PackedBatch]):
+    """Runs the CPU restatement over the batches in order; returns (SegJuncsResults, Counters)."""
+    L = lib()
+    res = L.orc_results_new()
+    try:
+        img = capi.ref_image_c(ref)
+        for b in batches:
+            bc = capi.batch_c(b)
+            rc = L.orc_segjuncs_batch(C.byref(params), C.byref(img), C.byref(bc), res)
+            if rc != 0:
+                raise RuntimeError("oracle failed: %d" % rc)
+        L.orc_segjuncs_finish(res)
+        j = np.zeros(L.orc_n_juncs(res), dtype=synth.JUNCTION_DTYPE)
+        d = np.zeros(L.orc_n_dels(res), dtype=synth.JUNCTION_DTYPE)
+        i = np.zeros(L.orc_n_ins(res), dtype=synth.INSERTION_DTYPE)
+        f = np.zeros(L.orc_n_fus(res), dtype=synth.FUSION_DTYPE)
+        if j.size: L.orc_get_juncs(res, j.ctypes.data)
+        if d.size: L.orc_get_dels(res, d.ctypes.data)
+        if i.size: L.orc_get_ins(res, i.ctypes.data)
+        if f.size: L.orc_get_fus(res, f.ctypes.data)
+        cnt = np.zeros(5, dtype=np.uint64)
+        L.orc_get_counters(res, cnt.ctypes.data)
+        return capi.SegJuncsResults(j, d, i, f), Counters(cnt)
+    finally:
+        L.orc_results_free(res)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own binaries
+
+
+def tophat_common_opts(inner_mean: int = 50, inner_sd: int = 20, extra: Optional[List[str]] = None) -> List[str]:
+    """The option block tophat.py passes to every stage binary (TopHatParams.cmd, tophat.py:824-900)."""
+    o = ["--min-anchor", "8", "--splice-mismatches", "0", "--min-report-intron", "50",
+         "--max-report-intron", "500000", "--min-isoform-fraction", "0.15", "--output-dir", "./",
+         "--max-multihits", "20", "--max-seg-multihits", "40", "--segment-length", "25",
+         "--segment-mismatches", "2", "--min-closure-exon", "100", "--min-closure-intron", "50",
+         "--max-closure-intron", "5000", "--min-coverage-intron", "50", "--max-coverage-intron", "20000",
+         "--min-segment-intron", "50", "--max-segment-intron", "500000", "--read-mismatches", "2",
+         "--read-gap-length", "2", "--read-edit-dist", "2", "--read-realign-edit-dist", "3",
+         "--max-insertion-length", "3", "--max-deletion-length", "3", "-z", "gzip",
+         "--inner-dist-mean", str(inner_mean), "--inner-dist-std-dev", str(inner_sd),
+         "--no-closure-search", "--no-coverage-search", "--no-microexon-search"]
+    return o + (extra or [])
+
+
+def make_bams(files: Dict[str, str], outdir: str, nseg: int) -> Dict[str, str]:
+    """FASTQ/SAM text -> BAM via the reference's prep_reads / fix_map_ordering (oracle/_ref)."""
+    hdr = files["header"]
+    out = {}
+    for side in ("left", "right"):
+        kept = os.path.join(outdir, side + "_kept_reads.bam")
+        subprocess.run([os.path.join(REF_DIR, "prep_reads"), "--sam-header", hdr, "--outfile", kept,
+                        "--index-outfile", kept + ".index", "--aux-outfile", os.path.join(outdir, side + ".info"),
+                        files[side + "_fq"]], check=True, stderr=subprocess.DEVNULL)
+        out[side + "_reads"] = kept
+        for key, name in [("mapped", side + "_kept_reads.mapped.bam")] + \
+                         [("seg%d" % (k + 1), "%s_kept_reads_seg%d.bam" % (side, k + 1)) for k in range(nseg)]:
+            bam = os.path.join(outdir, name)
+            subprocess.run([os.path.join(REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile",
+                            bam + ".index", files["%s_%s_sam" % (side, key)], bam], check=True,
+                           stderr=subprocess.DEVNULL)
+            out["%s_%s" % (side, key)] = bam
+    return out
+
+
+def run_segment_juncs(binary: str, files: Dict[str, str], bams: Dict[str, str], outdir: str, nseg: int,
+                      opts: Optional[List[str]] = None, paired: bool = True, threads: int = 1,
+                      env: Optional[dict] = None, tag: str = "") -> Dict[str, str]:
+    outs = {k: os.path.join(outdir, "segment%s.%s" % (tag, k)) for k in ("juncs", "insertions", "deletions", "fusions")}
+    cmd = [binary] + (opts if opts is not None else tophat_common_opts()) + \
+          ["-p%d" % threads, "--sam-header", files["header"], "--ium-reads", "", files["fasta"],
+           outs["juncs"], outs["insertions"], outs["deletions"], outs["fusions"],
+           bams["left_reads"], bams["left_mapped"], ",".join(bams["left_seg%d" % (k + 1)] for k in range(nseg))]
+    if paired:
+        cmd += [bams["right_reads"], bams["right_mapped"], ",".join(bams["right_seg%d" % (k + 1)] for k in range(nseg))]
+    log = os.path.join(outdir, "segment_juncs%s.log" % tag)
+    with open(log, "w") as lf:
+        subprocess.run(cmd, check=True, stderr=lf, env=env)
+    outs["log"] = log
+    return outs
+
+
+def parse_juncs(path: str, names: List[str]) -> np.ndarray:
+    idx = {n: i + 1 for i, n in enumerate(names)}
+    rows = []
+    with open(path) as f:
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            rows.append((idx[t[0]], int(t[1]) & 0xFFFFFFFF, int(t[2]) & 0xFFFFFFFF, 1 if t[3] == "-" else 0))
+    return np.array(rows, dtype=synth.JUNCTION_DTYPE) if rows else np.zeros(0, dtype=synth.JUNCTION_DTYPE)
+
+
+def format_juncs(j: np.ndarray, names: List[str]) -> str:
+    """segment.juncs text exactly as the driver writes it (segment_juncs.cpp:5041-5046)."""
+    return "".join("%s\t%d\t%d\t%c\n" % (names[int(r["ref_id"]) - 1], np.int32(r["left"]), np.int32(r["right"]),
+                                         "-" if r["antisense"] else "+") for r in j)
+
+
+def format_deletions(d: np.ndarray, names: List[str]) -> str:
+    """segment.deletions text (segment_juncs.cpp:5070-5074)."""
+    return "".join("%s\t%d\t%d\n" % (names[int(r["ref_id"]) - 1], np.int32(r["left"]) + 1, np.int32(r["right"])) for r in d)
+
+
+def format_insertions(i: np.ndarray, names: List[str]) -> str:
+    """segment.insertions text (segment_juncs.cpp:5085-5090)."""
+    return "".join("%s\t%d\t%d\t%s\n" % (names[int(r["ref_id"]) - 1], np.int32(r["left"]), np.int32(r["left"]),
+                                         r["seq"].decode()) for r in i)

@@ -1,0 +1,221 @@
+"""ctypes mirror of include/tophat_b200.h and loader of libtophat_b200.so.
+
+This is the Python face of the C ABI: the same structs, the same entry points, the same error
+behaviour (negative return code -> ThbError carrying thb_last_error()).  There is no CPU fallback:
+if the shared library was not built, or no sm_100 device is usable, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import synth
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtophat_b200.so")
+
+
+class ThbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "segment_length", "segment_mismatches", "min_segment_intron_length", "max_segment_intron_length",
+        "max_insertion_length", "max_deletion_length", "max_seg_multihits", "inner_dist_mean",
+        "inner_dist_std_dev", "bowtie2", "library_type", "fusion_search", "fusion_anchor_length",
+        "fusion_min_dist", "max_report_intron_length", "min_report_intron_length", "min_anchor_len",
+        "read_mismatches", "read_gap_length", "read_edit_dist", "bowtie2_max_penalty", "bowtie2_min_penalty",
+        "bowtie2_penalty_for_N", "bowtie2_read_gap_open", "bowtie2_read_gap_cont", "bowtie2_ref_gap_open",
+        "bowtie2_ref_gap_cont")] + [("reserved", C.c_int32 * 5)]
+
+
+def default_params(**over) -> Params:
+    """The reference binaries' defaults (common.cpp:79-180)."""
+    p = Params()
+    d = dict(segment_length=25, segment_mismatches=2, min_segment_intron_length=50,
+             max_segment_intron_length=500000, max_insertion_length=3, max_deletion_length=3,
+             max_seg_multihits=40, inner_dist_mean=200, inner_dist_std_dev=20, bowtie2=1, library_type=0,
+             fusion_search=0, fusion_anchor_length=20, fusion_min_dist=10000000,
+             max_report_intron_length=500000, min_report_intron_length=50, min_anchor_len=8,
+             read_mismatches=2, read_gap_length=2, read_edit_dist=2, bowtie2_max_penalty=6,
+             bowtie2_min_penalty=2, bowtie2_penalty_for_N=1, bowtie2_read_gap_open=5, bowtie2_read_gap_cont=3,
+             bowtie2_ref_gap_open=5, bowtie2_ref_gap_cont=3)
+    d.update(over)
+    for k, v in d.items():
+        setattr(p, k, int(v))
+    return p
+
+
+class RefImageC(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("contig_start", C.c_void_p), ("contig_len", C.c_void_p),
+                ("n_blocks", C.c_uint64), ("planes", C.c_void_p), ("nmask", C.c_void_p)]
+
+
+class BatchC(C.Structure):
+    _fields_ = [("n_bundles", C.c_uint32), ("n_segs", C.c_uint32), ("read_words", C.c_uint32),
+                ("reserved", C.c_uint32), ("bundles", C.c_void_p), ("seg_count", C.c_void_p),
+                ("reads", C.c_void_p), ("n_hits", C.c_uint64), ("hits", C.c_void_p),
+                ("n_partner_hits", C.c_uint64), ("partner_hits", C.c_void_p), ("order_base", C.c_uint64)]
+
+
+class ResultsC(C.Structure):
+    _fields_ = [("n_junctions", C.c_uint64), ("junctions", C.c_void_p),
+                ("n_deletions", C.c_uint64), ("deletions", C.c_void_p),
+                ("n_insertions", C.c_uint64), ("insertions", C.c_void_p),
+                ("n_fusions", C.c_uint64), ("fusions", C.c_void_p)]
+
+
+class TimingC(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("scan_kernel_ms", C.c_float), ("finish_ms", C.c_float),
+                ("total_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
+                ("n_rescue_tasks", C.c_uint64), ("n_juncs_emitted", C.c_uint64),
+                ("algorithmic_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def ref_image_c(ref: synth.RefImage) -> RefImageC:
+    """Borrowed-pointer view; `ref` must outlive the struct."""
+    r = RefImageC()
+    r.n_contigs = len(ref.names)
+    r.contig_start = ref.contig_start.ctypes.data
+    r.contig_len = ref.contig_len.ctypes.data
+    r.n_blocks = ref.n_blocks
+    r.planes = ref.planes.ctypes.data
+    r.nmask = ref.nmask.ctypes.data
+    return r
+
+
+def batch_c(b: synth.PackedBatch) -> BatchC:
+    """Borrowed-pointer view of host numpy arrays; `b` must outlive the struct."""
+    s = BatchC()
+    s.n_bundles = b.n_bundles
+    s.n_segs = b.n_segs
+    s.read_words = b.read_words
+    s.bundles = b.bundles.ctypes.data
+    s.seg_count = b.seg_count.ctypes.data
+    s.reads = b.reads.ctypes.data
+    s.n_hits = b.hits.shape[0]
+    s.hits = b.hits.ctypes.data
+    s.n_partner_hits = b.partner_hits.shape[0]
+    s.partner_hits = b.partner_hits.ctypes.data
+    s.order_base = b.order_base
+    return s
+
+
+def _copy_records(ptr: Optional[int], n: int, dtype: np.dtype) -> np.ndarray:
+    if not n:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class SegJuncsResults:
+    def __init__(self, juncs, dels, ins, fus):
+        self.junctions, self.deletions, self.insertions, self.fusions = juncs, dels, ins, fus
+
+    @classmethod
+    def from_c(cls, r: ResultsC) -> "SegJuncsResults":
+        return cls(_copy_records(r.junctions, r.n_junctions, synth.JUNCTION_DTYPE),
+                   _copy_records(r.deletions, r.n_deletions, synth.JUNCTION_DTYPE),
+                   _copy_records(r.insertions, r.n_insertions, synth.INSERTION_DTYPE),
+                   _copy_records(r.fusions, r.n_fusions, synth.FUSION_DTYPE))
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Loads libtophat_b200.so; raises ThbError (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ThbError("libtophat_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+    lib = C.CDLL(p)
+    lib.thb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.thb_destroy.argtypes = [C.c_void_p]
+    lib.thb_destroy.restype = None
+    lib.thb_last_error.argtypes = [C.c_void_p]
+    lib.thb_last_error.restype = C.c_char_p
+    lib.thb_version.restype = C.c_char_p
+    lib.thb_params_default.argtypes = [C.POINTER(Params)]
+    lib.thb_params_default.restype = None
+    lib.thb_ref_upload.argtypes = [C.c_void_p, C.POINTER(RefImageC)]
+    lib.thb_segjuncs_begin.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.thb_segjuncs_submit.argtypes = [C.c_void_p, C.POINTER(BatchC)]
+    lib.thb_segjuncs_submit_device.argtypes = [C.c_void_p, C.POINTER(BatchC)]
+    lib.thb_segjuncs_finish.argtypes = [C.c_void_p, C.POINTER(ResultsC)]
+    lib.thb_last_timing.argtypes = [C.c_void_p, C.POINTER(TimingC)]
+    lib.thb_stream.argtypes = [C.c_void_p]
+    lib.thb_stream.restype = C.c_void_p
+    lib.thb_pack_bases.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.thb_pack_bases.restype = None
+    lib.thb_pack_read.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.thb_pack_read.restype = None
+    lib.thb_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.thb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.thb_segjuncs_allgather.argtypes = [C.c_void_p]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class Context:
+    """One device context (thb_ctx).  Mirrors the call sequence of the host binaries."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.thb_create(device, C.byref(h))
+        if rc != 0:
+            msg = self.lib.thb_last_error(None)
+            raise ThbError("thb_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.h = h
+        self._keep = []
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.thb_last_error(self.h)
+            raise ThbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.thb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ref_upload(self, ref: synth.RefImage) -> None:
+        img = ref_image_c(ref)
+        self._check(self.lib.thb_ref_upload(self.h, C.byref(img)), "thb_ref_upload")
+
+    def segjuncs_begin(self, params: Params) -> None:
+        self._check(self.lib.thb_segjuncs_begin(self.h, C.byref(params)), "thb_segjuncs_begin")
+
+    def segjuncs_submit(self, batch: synth.PackedBatch) -> None:
+        b = batch_c(batch)
+        self._check(self.lib.thb_segjuncs_submit(self.h, C.byref(b)), "thb_segjuncs_submit")
+
+    def segjuncs_submit_device(self, b: BatchC) -> None:
+        self._check(self.lib.thb_segjuncs_submit_device(self.h, C.byref(b)), "thb_segjuncs_submit_device")
+
+    def segjuncs_finish(self) -> SegJuncsResults:
+        r = ResultsC()
+        self._check(self.lib.thb_segjuncs_finish(self.h, C.byref(r)), "thb_segjuncs_finish")
+        return SegJuncsResults.from_c(r)
+
+    def timing(self) -> TimingC:
+        t = TimingC()
+        self._check(self.lib.thb_last_timing(self.h, C.byref(t)), "thb_last_timing")
+        return t
+
+    def stream(self) -> int:
+        return int(self.lib.thb_stream(self.h) or 0)
