@@ -1,0 +1,643 @@
+// thb_api.cu -- implementation of the C ABI declared in include/tophat_b200.h.
+//
+// Owns the device context: reference image, result sets, staging buffers, streams.  The host
+// batch path (thb_segjuncs_submit) is a two-stream, double-buffered pipeline: chunk c+1 is copied
+// host->device on the copy stream while the scan kernel of chunk c runs on the compute stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include "../../include/tophat_b200.h"
+#include "segjuncs_kernel.cuh"
+
+using namespace thb;
+
+namespace {
+
+char g_create_error[512] = "";
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Staging { DevBuf bundles, seg_count, reads, hits, partner; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; };
+
+// dynamically bound NCCL (the library is only needed for the multi-GPU exchange)
+struct NcclUid { char b[128]; };          // ncclUniqueId is passed BY VALUE to ncclCommInitRank
+struct Nccl {
+  typedef NcclUid Uid;
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct thb_ctx {
+  int device = 0;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+  std::string err;
+  // reference
+  DevBuf d_planes, d_nmask, d_cstart, d_clen;
+  std::vector<uint64_t> h_cstart; std::vector<uint32_t> h_clen;
+  RefView ref{}; bool have_ref = false;
+  // parameters
+  thb_params params{}; SegParams sp{}; bool begun = false;
+  // result sets
+  DevBuf d_juncs, d_dels; uint64_t cap_juncs = 0, cap_dels = 0;
+  DevBuf d_ins; uint64_t cap_ins = 0;
+  DevBuf d_scalars;                 // [0..7] counters (u64), then ins_count(u64), then flags (u32 x4)
+  unsigned long long* d_counters = nullptr; unsigned long long* d_ins_count = nullptr;
+  unsigned int* d_ovf_juncs = nullptr; unsigned int* d_ovf_dels = nullptr; unsigned int* d_err = nullptr;
+  DevBuf d_keys, d_keys_sorted, d_cub_tmp, d_decoded, d_count;
+  Staging stage[2];
+  // host results
+  std::vector<thb_junction> h_juncs, h_dels; std::vector<thb_insertion> h_ins; std::vector<thb_fusion> h_fus;
+  std::vector<InsRec> h_insrec;
+  // accounting
+  thb_timing timing{}; uint64_t n_bundles_total = 0, n_hits_total = 0, n_partner_total = 0;
+  uint64_t n_ins_out = 0, n_del_out = 0;
+  // nccl
+  Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
+};
+
+namespace {
+
+int fail(thb_ctx* c, int code, const char* fmt, ...)
+{
+  char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (c) c->err = buf; else snprintf(g_create_error, sizeof g_create_error, "%s", buf);
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, THB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+HashSet make_set(DevBuf& b, uint64_t cap, unsigned int* ovf) { HashSet h; h.slots = (uint64_t*)b.p; h.mask = cap - 1; h.overflow = ovf; return h; }
+
+int grid_for(uint64_t n, int block) {
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint64_t g = (n + block - 1) / block; uint64_t cap = (uint64_t)sms * 16;
+  if (g > cap) g = cap; if (g < 1) g = 1; return (int)g;
+}
+
+int alloc_set(thb_ctx* ctx, DevBuf& b, uint64_t cap)
+{
+  CU(b.reserve(cap * sizeof(uint64_t)));
+  hs_clear_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((uint64_t*)b.p, cap);
+  CU(cudaGetLastError());
+  return THB_OK;
+}
+
+// doubles a hash set, re-inserting its content
+int grow_set(thb_ctx* ctx, DevBuf& b, uint64_t& cap, unsigned int* ovf)
+{
+  DevBuf nb; uint64_t ncap = cap * 2;
+  CU(nb.reserve(ncap * sizeof(uint64_t)));
+  hs_clear_kernel<<<grid_for(ncap, 256), 256, 0, ctx->compute>>>((uint64_t*)nb.p, ncap);
+  CU(cudaMemsetAsync(ovf, 0, sizeof(unsigned int), ctx->compute));
+  HashSet dst; dst.slots = (uint64_t*)nb.p; dst.mask = ncap - 1; dst.overflow = ovf;
+  hs_rehash_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)b.p, cap, dst);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->compute));
+  b.release(); b = nb; cap = ncap;
+  return THB_OK;
+}
+
+SegOutputs outputs(thb_ctx* ctx)
+{
+  SegOutputs o;
+  o.juncs = make_set(ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs);
+  o.dels = make_set(ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels);
+  o.ins = (InsRec*)ctx->d_ins.p; o.ins_count = ctx->d_ins_count; o.ins_cap = ctx->cap_ins;
+  o.counters = ctx->d_counters; o.err = ctx->d_err;
+  return o;
+}
+
+struct Flags { unsigned int ovf_juncs, ovf_dels, err, pad; };
+
+int read_state(thb_ctx* ctx, Flags* f, unsigned long long* ins_count)
+{
+  CU(cudaMemcpyAsync(f, ctx->d_ovf_juncs, sizeof(Flags), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaMemcpyAsync(ins_count, ctx->d_ins_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  return THB_OK;
+}
+
+int launch_scan(thb_ctx* ctx, const BatchView& bv)
+{
+  if (bv.n_bundles == 0) return THB_OK;
+  const int block = 256;
+  segjuncs_kernel<<<grid_for(bv.n_bundles, block), block, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, outputs(ctx));
+  CU(cudaGetLastError());
+  ctx->timing.kernel_launches++;
+  return THB_OK;
+}
+
+int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
+{
+  if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
+  if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  if (b->n_segs < 1 || b->n_segs > (uint32_t)MAX_SEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, MAX_SEGS);
+  if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4] (reads up to 255 bp)", b->read_words);
+  if (b->n_bundles && (!b->bundles || !b->seg_count || !b->reads)) return fail(ctx, THB_EINVAL, "null batch array");
+  if (b->n_hits && !b->hits) return fail(ctx, THB_EINVAL, "null hits array");
+  if (b->n_partner_hits && !b->partner_hits) return fail(ctx, THB_EINVAL, "null partner_hits array");
+  return THB_OK;
+}
+
+// After a scan: grow any structure that overflowed and report whether the scan must be repeated
+// (set inserts are idempotent; the insertion buffer is rolled back to `ins_before`).
+int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* redo)
+{
+  Flags f; unsigned long long ins_now; *redo = false;
+  int rc = read_state(ctx, &f, &ins_now); if (rc) return rc;
+  const unsigned long long ins_before = *ins_before_p;      // valid only after the sync above
+  if (f.err & 2u) return fail(ctx, THB_EUNSUPPORTED, "more than %d rescued mate-anchor hits for one read in --bowtie1 mode", RES_MAX);
+  if (f.ovf_juncs) { rc = grow_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs); if (rc) return rc; *redo = true; }
+  if (f.ovf_dels) { rc = grow_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels); if (rc) return rc; *redo = true; }
+  if ((f.err & 1u) || ins_now > ctx->cap_ins) {
+    uint64_t ncap = std::max<uint64_t>(ctx->cap_ins * 2, ins_now + 1024);
+    DevBuf nb; CU(nb.reserve(ncap * sizeof(InsRec)));
+    CU(cudaMemcpyAsync(nb.p, ctx->d_ins.p, (size_t)std::min<uint64_t>(ins_before, ctx->cap_ins) * sizeof(InsRec), cudaMemcpyDeviceToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    ctx->d_ins.release(); ctx->d_ins = nb; ctx->cap_ins = ncap; *redo = true;
+  }
+  if (*redo) {
+    CU(cudaMemcpyAsync(ctx->d_ins_count, &ins_before, sizeof ins_before, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+  }
+  return THB_OK;
+}
+
+uint64_t algorithmic_bytes(const thb_ctx* ctx, const unsigned long long* cnt)
+{
+  // SURVEY.md section 8(d), B_segjuncs, evaluated on the actual task counts of the run.
+  const uint64_t per_read = 16 + 40;
+  return ctx->n_bundles_total * per_read + 16ull * (ctx->n_hits_total + ctx->n_partner_total) +
+         cnt[0] * (32ull + 64ull) + 16ull * cnt[3] +               // windows + junction records
+         cnt[1] * (32ull + 64ull) + 16ull * (ctx->n_ins_out + ctx->n_del_out) +
+         cnt[2] * (32ull + 128ull);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* thb_version(void) { return "tophat_b200 0.1 (sm_100a)"; }
+
+void thb_params_default(thb_params* p)
+{
+  memset(p, 0, sizeof *p);
+  p->segment_length = 25; p->segment_mismatches = 2; p->min_segment_intron_length = 50;
+  p->max_segment_intron_length = 500000; p->max_insertion_length = 3; p->max_deletion_length = 3;
+  p->max_seg_multihits = 40; p->inner_dist_mean = 200; p->inner_dist_std_dev = 20; p->bowtie2 = 1;
+  p->library_type = 0; p->fusion_search = 0; p->fusion_anchor_length = 20; p->fusion_min_dist = 10000000;
+  p->max_report_intron_length = 500000; p->min_report_intron_length = 50; p->min_anchor_len = 8;
+  p->read_mismatches = 2; p->read_gap_length = 2; p->read_edit_dist = 2;
+  p->bowtie2_max_penalty = 6; p->bowtie2_min_penalty = 2; p->bowtie2_penalty_for_N = 1;
+  p->bowtie2_read_gap_open = 5; p->bowtie2_read_gap_cont = 3; p->bowtie2_ref_gap_open = 5; p->bowtie2_ref_gap_cont = 3;
+}
+
+const char* thb_last_error(const thb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error; }
+
+int thb_create(int device, thb_ctx** out)
+{
+  thb_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, THB_EINVAL, "null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(nullptr, THB_ENODEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, THB_ENODEVICE, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp prop; e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, THB_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, THB_ENODEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, THB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  ctx = new thb_ctx(); ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t ee) { int rc = fail(nullptr, THB_ECUDA, "%s: %s", what, cudaGetErrorString(ee)); delete ctx; return rc; };
+  if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b); cudaEventCreate(&ctx->ev_c); cudaEventCreate(&ctx->ev_d);
+  for (auto& s : ctx->stage) { cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming); }
+  if ((e = ctx->d_scalars.reserve(256)) != cudaSuccess) return bail("cudaMalloc", e);
+  ctx->d_counters = (unsigned long long*)ctx->d_scalars.p;
+  ctx->d_ins_count = ctx->d_counters + 8;
+  ctx->d_ovf_juncs = (unsigned int*)(ctx->d_counters + 9);
+  ctx->d_ovf_dels = ctx->d_ovf_juncs + 1; ctx->d_err = ctx->d_ovf_juncs + 2;
+  cudaMemset(ctx->d_scalars.p, 0, 256);
+  thb_params_default(&ctx->params);
+  *out = ctx;
+  return THB_OK;
+}
+
+void thb_destroy(thb_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+  for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
+                     &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count }) b->release();
+  for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
+  cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
+  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
+  delete ctx;
+}
+
+void* thb_stream(thb_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
+
+void thb_pack_bases(const char* seq, uint64_t len, uint64_t gstart, uint64_t* planes, uint64_t* nmask)
+{
+  for (uint64_t i = 0; i < len; ++i) {
+    const uint64_t g = gstart + i, b = g >> 6; const unsigned j = (unsigned)(g & 63);
+    unsigned c; bool isn = false;
+    switch (seq[i]) { case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break; case 'G': case 'g': c = 2; break;
+                      case 'T': case 't': case 'U': case 'u': c = 3; break; default: c = 0; isn = true; }
+    if (c & 1) planes[2 * b] |= 1ull << j;
+    if (c & 2) planes[2 * b + 1] |= 1ull << j;
+    if (isn) nmask[b] |= 1ull << j;
+  }
+}
+
+void thb_pack_read(const char* seq, uint32_t len, uint32_t read_words, uint64_t* out)
+{
+  memset(out, 0, sizeof(uint64_t) * 3 * read_words);
+  for (uint32_t i = 0; i < len && i < read_words * 64; ++i) {
+    const uint32_t w = i >> 6, j = i & 63; unsigned c; bool isn = false;
+    switch (seq[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 0; isn = true; }
+    if (c & 1) out[w] |= 1ull << j;
+    if (c & 2) out[read_words + w] |= 1ull << j;
+    if (isn) out[2 * read_words + w] |= 1ull << j;
+  }
+}
+
+int thb_ref_upload(thb_ctx* ctx, const thb_ref_image* img)
+{
+  if (!ctx || !img) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (img->n_contigs == 0 || !img->contig_start || !img->contig_len || !img->planes || !img->nmask)
+    return fail(ctx, THB_EINVAL, "incomplete reference image");
+  for (uint32_t i = 0; i < img->n_contigs; ++i) {
+    if (img->contig_start[i] & 63) return fail(ctx, THB_EINVAL, "contig_start[%u] is not a multiple of 64", i);
+    const uint64_t end = img->contig_start[i] + img->contig_len[i] + 64;
+    if (end > img->n_blocks * 64) return fail(ctx, THB_EINVAL, "contig %u overruns the image (needs 64 bases of padding)", i);
+    if (i && img->contig_start[i] < img->contig_start[i - 1] + img->contig_len[i - 1] + 64) return fail(ctx, THB_EINVAL, "contigs %u/%u overlap or lack padding", i - 1, i);
+  }
+  if (img->n_blocks * 64 >= (1ull << 39)) return fail(ctx, THB_EUNSUPPORTED, "reference larger than 2^39 bases");
+  CU(ctx->d_planes.reserve((img->n_blocks + 2) * 16)); CU(ctx->d_nmask.reserve((img->n_blocks + 2) * 8));
+  CU(ctx->d_cstart.reserve(img->n_contigs * 8)); CU(ctx->d_clen.reserve(img->n_contigs * 4));
+  CU(cudaMemsetAsync(ctx->d_planes.p, 0, (img->n_blocks + 2) * 16, ctx->compute));
+  CU(cudaMemsetAsync(ctx->d_nmask.p, 0, (img->n_blocks + 2) * 8, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->d_planes.p, img->planes, img->n_blocks * 16, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->d_nmask.p, img->nmask, img->n_blocks * 8, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->d_cstart.p, img->contig_start, img->n_contigs * 8, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->d_clen.p, img->contig_len, img->n_contigs * 4, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->h_cstart.assign(img->contig_start, img->contig_start + img->n_contigs);
+  ctx->h_clen.assign(img->contig_len, img->contig_len + img->n_contigs);
+  ctx->ref.planes = (const ulonglong2*)ctx->d_planes.p; ctx->ref.nmask = (const uint64_t*)ctx->d_nmask.p;
+  ctx->ref.contig_start = (const uint64_t*)ctx->d_cstart.p; ctx->ref.contig_len = (const uint32_t*)ctx->d_clen.p;
+  ctx->ref.n_contigs = img->n_contigs; ctx->have_ref = true;
+  return THB_OK;
+}
+
+int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
+{
+  if (!ctx || !p) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (p->segment_length < 4 || p->segment_length > 32)
+    return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside the GPU path's [4,32] (two segments must fit one 64-bit plane word)", p->segment_length);
+  if (p->max_segment_intron_length + p->segment_length + 64 >= (1 << KEY_LEN_BITS))
+    return fail(ctx, THB_EUNSUPPORTED, "--max-segment-intron %d too large for the 24-bit span field", p->max_segment_intron_length);
+  if (p->max_insertion_length > 20 || p->max_deletion_length > 1000)
+    return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 20 / --max-deletion-length > 1000 not supported");
+  if (p->fusion_search) return fail(ctx, THB_EUNSUPPORTED, "--fusion-search is not implemented on the GPU path yet");
+  if (p->inner_dist_mean + p->inner_dist_std_dev + std::max(0, p->inner_dist_std_dev - p->inner_dist_mean) > 100000)
+    return fail(ctx, THB_EUNSUPPORTED, "mate flank longer than 100000 bases");
+  ctx->params = *p;
+  SegParams& s = ctx->sp;
+  s.seglen = p->segment_length; s.segmm = p->segment_mismatches; s.min_intron = p->min_segment_intron_length;
+  s.max_intron = p->max_segment_intron_length; s.max_ins = p->max_insertion_length; s.max_del = p->max_deletion_length;
+  s.max_multihits = p->max_seg_multihits; s.inner_mean = p->inner_dist_mean; s.inner_sd = p->inner_dist_std_dev;
+  s.bowtie2 = p->bowtie2; s.library_type = p->library_type;
+  if (ctx->cap_juncs == 0) ctx->cap_juncs = 1ull << 21;
+  if (ctx->cap_dels == 0) ctx->cap_dels = 1ull << 18;
+  if (ctx->cap_ins == 0) ctx->cap_ins = 1ull << 18;
+  int rc;
+  if ((rc = alloc_set(ctx, ctx->d_juncs, ctx->cap_juncs))) return rc;
+  if ((rc = alloc_set(ctx, ctx->d_dels, ctx->cap_dels))) return rc;
+  CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec)));
+  CU(cudaMemsetAsync(ctx->d_scalars.p, 0, 256, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->h_juncs.clear(); ctx->h_dels.clear(); ctx->h_ins.clear(); ctx->h_fus.clear();
+  memset(&ctx->timing, 0, sizeof ctx->timing);
+  ctx->n_bundles_total = ctx->n_hits_total = ctx->n_partner_total = 0; ctx->n_ins_out = ctx->n_del_out = 0;
+  ctx->begun = true;
+  return THB_OK;
+}
+
+int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* b)
+{
+  if (!ctx || !b) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = validate_batch(ctx, b); if (rc) return rc;
+  BatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
+  bv.partner = b->partner_hits; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
+  bv.order_base = b->order_base;
+  unsigned long long ins_before = 0;
+  CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  float ms_total = 0.f;
+  for (int attempt = 0; attempt < 24; ++attempt) {
+    unsigned long long cnt0[4];
+    CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+    rc = launch_scan(ctx, bv); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+    bool redo = false;
+    rc = check_and_grow(ctx, &ins_before, &redo); if (rc) return rc;
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    if (!redo) { ms_total = ms; break; }
+    // roll the task counters back so that a repeated scan is not double counted
+    CU(cudaMemcpyAsync(ctx->d_counters, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+  }
+  ctx->timing.scan_kernel_ms += ms_total; ctx->timing.total_ms += ms_total;
+  ctx->n_bundles_total += b->n_bundles; ctx->n_hits_total += b->n_hits; ctx->n_partner_total += b->n_partner_hits;
+  return THB_OK;
+}
+
+int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
+{
+  if (!ctx || !b) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = validate_batch(ctx, b); if (rc) return rc;
+  if (b->n_bundles == 0) return THB_OK;
+  const uint32_t CH = 1u << 20;                         // bundles per pipeline chunk
+  const size_t rdw = (size_t)3 * b->read_words;
+  unsigned long long ins_before_all = 0;
+  CU(cudaMemcpyAsync(&ins_before_all, ctx->d_ins_count, sizeof ins_before_all, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaEventRecord(ctx->ev_c, ctx->compute));
+  float kernel_ms = 0.f;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+  const uint32_t nchunks = (b->n_bundles + CH - 1) / CH;
+  struct Range { uint32_t b0, nb; uint64_t h0, h1, p0, p1; };
+  auto range_of = [&](uint32_t c, Range* r) -> bool {
+    r->b0 = c * CH; const uint32_t b1 = std::min<uint32_t>(b->n_bundles, r->b0 + CH); r->nb = b1 - r->b0;
+    r->h0 = b->bundles[r->b0].hit_begin; r->h1 = (b1 < b->n_bundles) ? b->bundles[b1].hit_begin : b->n_hits;
+    r->p0 = b->bundles[r->b0].partner_begin; r->p1 = (b1 < b->n_bundles) ? b->bundles[b1].partner_begin : b->n_partner_hits;
+    return !(r->h1 < r->h0 || r->h1 > b->n_hits || r->p1 < r->p0 || r->p1 > b->n_partner_hits);
+  };
+  // host -> device copy of chunk c into staging buffer c&1 on the copy stream
+  auto enqueue_copy = [&](uint32_t c) -> int {
+    Staging& s = ctx->stage[c & 1]; Range r;
+    if (!range_of(c, &r)) return fail(ctx, THB_EINVAL, "hit_begin / partner_begin not monotonic near bundle %u", c * CH);
+    if (s.used) CU(cudaStreamWaitEvent(ctx->copy, s.consumed, 0));
+    CU(s.bundles.reserve((size_t)r.nb * sizeof(thb_bundle))); CU(s.seg_count.reserve((size_t)r.nb * b->n_segs * 2));
+    CU(s.reads.reserve((size_t)r.nb * rdw * 8)); CU(s.hits.reserve((size_t)(r.h1 - r.h0 + 1) * sizeof(thb_hit)));
+    CU(s.partner.reserve((size_t)(r.p1 - r.p0 + 1) * sizeof(thb_hit)));
+    CU(cudaMemcpyAsync(s.bundles.p, b->bundles + r.b0, (size_t)r.nb * sizeof(thb_bundle), cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaMemcpyAsync(s.seg_count.p, b->seg_count + (size_t)r.b0 * b->n_segs, (size_t)r.nb * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaMemcpyAsync(s.reads.p, b->reads + (size_t)r.b0 * rdw, (size_t)r.nb * rdw * 8, cudaMemcpyHostToDevice, ctx->copy));
+    if (r.h1 > r.h0) CU(cudaMemcpyAsync(s.hits.p, b->hits + r.h0, (size_t)(r.h1 - r.h0) * sizeof(thb_hit), cudaMemcpyHostToDevice, ctx->copy));
+    if (r.p1 > r.p0) CU(cudaMemcpyAsync(s.partner.p, b->partner_hits + r.p0, (size_t)(r.p1 - r.p0) * sizeof(thb_hit), cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaEventRecord(s.copied, ctx->copy));
+    return THB_OK;
+  };
+  rc = enqueue_copy(0); if (rc) return rc;
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    Staging& s = ctx->stage[c & 1]; Range r; range_of(c, &r);
+    CU(cudaStreamWaitEvent(ctx->compute, s.copied, 0));
+    BatchView bv; bv.bundles = (const thb_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p;
+    bv.reads = (const uint64_t*)s.reads.p; bv.hits = (const thb_hit*)s.hits.p - r.h0; bv.partner = (const thb_hit*)s.partner.p - r.p0;
+    bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.order_base = b->order_base + r.b0;
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); kev.push_back({e0, e1});
+    unsigned long long ins_before = 0;
+    CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
+    for (int attempt = 0; attempt < 24; ++attempt) {
+      unsigned long long cnt0[4];
+      CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
+      CU(cudaEventRecord(e0, ctx->compute));
+      rc = launch_scan(ctx, bv); if (rc) return rc;
+      CU(cudaEventRecord(e1, ctx->compute));
+      // the next chunk's copy (other staging buffer, whose kernel already completed) overlaps this scan
+      if (attempt == 0 && c + 1 < nchunks) { rc = enqueue_copy(c + 1); if (rc) return rc; }
+      bool redo = false;
+      rc = check_and_grow(ctx, &ins_before, &redo); if (rc) return rc;      // synchronises the compute stream
+      if (!redo) break;
+      CU(cudaMemcpyAsync(ctx->d_counters, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, ctx->compute));
+      CU(cudaStreamSynchronize(ctx->compute));
+    }
+    CU(cudaEventRecord(s.consumed, ctx->compute)); s.used = true;
+  }
+  CU(cudaEventRecord(ctx->ev_d, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  for (auto& pr : kev) { float ms = 0.f; cudaEventElapsedTime(&ms, pr.first, pr.second); kernel_ms += ms; cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  float tot = 0.f; CU(cudaEventElapsedTime(&tot, ctx->ev_c, ctx->ev_d));
+  ctx->timing.scan_kernel_ms += kernel_ms; ctx->timing.total_ms += tot; ctx->timing.h2d_ms += std::max(0.f, tot - kernel_ms);
+  ctx->n_bundles_total += b->n_bundles; ctx->n_hits_total += b->n_hits; ctx->n_partner_total += b->n_partner_hits;
+  (void)ins_before_all;
+  return THB_OK;
+}
+
+static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, std::vector<thb_junction>& out, uint64_t limit)
+{
+  CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8)); CU(ctx->d_count.reserve(64));
+  CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
+  hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, (unsigned long long*)ctx->d_count.p);
+  CU(cudaGetLastError());
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  out.clear();
+  if (n == 0) return THB_OK;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute);
+  CU(ctx->d_cub_tmp.reserve(tmp + 16));
+  CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute));
+  if (n > limit) n = limit;       // std::set capped at max_seg_juncs by erasing the largest (1692-1693)
+  CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
+  decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_keys_sorted.p, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
+  CU(cudaGetLastError());
+  out.resize(n);
+  CU(cudaMemcpyAsync(out.data(), ctx->d_decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  return THB_OK;
+}
+
+int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
+{
+  if (!ctx || !out) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  int rc;
+  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull))) return rc;
+  // insertions: first inserted wins among equal (ref, left, length) -- insertions.h:52-67
+  unsigned long long nins = 0;
+  CU(cudaMemcpyAsync(&nins, ctx->d_ins_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->h_insrec.resize(nins);
+  if (nins) { CU(cudaMemcpyAsync(ctx->h_insrec.data(), ctx->d_ins.p, nins * sizeof(InsRec), cudaMemcpyDeviceToHost, ctx->compute)); CU(cudaStreamSynchronize(ctx->compute)); }
+  std::sort(ctx->h_insrec.begin(), ctx->h_insrec.end(), [](const InsRec& a, const InsRec& b) { return a.key != b.key ? a.key < b.key : a.order < b.order; });
+  ctx->h_ins.clear();
+  for (size_t i = 0; i < ctx->h_insrec.size(); ++i) {
+    const InsRec& r = ctx->h_insrec[i];
+    if (i && ctx->h_insrec[i - 1].key == r.key) continue;
+    const uint64_t gl1 = r.key >> 8; const uint32_t len = (uint32_t)(r.key & 0xff);
+    size_t c = std::upper_bound(ctx->h_cstart.begin(), ctx->h_cstart.end(), gl1) - ctx->h_cstart.begin() - 1;
+    thb_insertion o; memset(&o, 0, sizeof o);
+    o.ref_id = (uint32_t)c + 1; o.left = (uint32_t)(gl1 - ctx->h_cstart[c]) - 1u; o.len = len;
+    for (uint32_t k = 0; k < len && k < 19; ++k) o.seq[k] = "ACGTN"[(r.seq >> (3 * k)) & 7];
+    ctx->h_ins.push_back(o);
+  }
+  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  float ms = 0.f; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  ctx->timing.finish_ms = ms;
+  unsigned long long cnt[8];
+  CU(cudaMemcpy(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
+  ctx->n_ins_out = nins; ctx->n_del_out = ctx->h_dels.size();
+  ctx->timing.n_windows = cnt[0]; ctx->timing.n_indel_tasks = cnt[1]; ctx->timing.n_rescue_tasks = cnt[2]; ctx->timing.n_juncs_emitted = cnt[3];
+  ctx->timing.algorithmic_bytes = algorithmic_bytes(ctx, cnt);
+  out->n_junctions = ctx->h_juncs.size(); out->junctions = ctx->h_juncs.data();
+  out->n_deletions = ctx->h_dels.size(); out->deletions = ctx->h_dels.data();
+  out->n_insertions = ctx->h_ins.size(); out->insertions = ctx->h_ins.data();
+  out->n_fusions = ctx->h_fus.size(); out->fusions = ctx->h_fus.data();
+  return THB_OK;
+}
+
+int thb_last_timing(thb_ctx* ctx, thb_timing* out)
+{
+  if (!ctx || !out) return THB_EINVAL;
+  *out = ctx->timing;
+  return THB_OK;
+}
+
+// ---- multi-GPU exchange -------------------------------------------------------------------------
+static int nccl_bind(thb_ctx* ctx, Nccl& n)
+{
+  if (n.h) return THB_OK;
+  const char* names[] = { "libnccl.so.2", "libnccl.so" };
+  for (const char* nm : names) { n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.h) break; }
+  if (!n.h) return fail(ctx, THB_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  n.GetUniqueId = (int (*)(void*))dlsym(n.h, "ncclGetUniqueId");
+  *(void**)(&n.CommInitRank) = dlsym(n.h, "ncclCommInitRank");
+  *(void**)(&n.AllGather) = dlsym(n.h, "ncclAllGather");
+  n.CommDestroy = (int (*)(void*))dlsym(n.h, "ncclCommDestroy");
+  n.GetErrorString = (const char* (*)(int))dlsym(n.h, "ncclGetErrorString");
+  if (!n.GetUniqueId || !n.CommInitRank || !n.AllGather) return fail(ctx, THB_ENCCL, "libnccl lacks required symbols");
+  return THB_OK;
+}
+
+int thb_nccl_unique_id(void* out128)
+{
+  static Nccl n; int rc = nccl_bind(nullptr, n); if (rc) return rc;
+  return n.GetUniqueId(out128) == 0 ? THB_OK : THB_ENCCL;
+}
+
+int thb_comm_init(thb_ctx* ctx, const void* uid, int rank, int world)
+{
+  if (!ctx || !uid) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = nccl_bind(ctx, ctx->nccl); if (rc) return rc;
+  Nccl::Uid u; memcpy(u.b, uid, 128);
+  int e = ctx->nccl.CommInitRank(&ctx->comm, world, u, rank);
+  if (e != 0) return fail(ctx, THB_ENCCL, "ncclCommInitRank: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(e) : "?");
+  ctx->rank = rank; ctx->world = world;
+  return THB_OK;
+}
+
+// all-gather one hash set: every rank compacts its keys, pads to the global maximum, exchanges, and
+// inserts everything it received.
+static int allgather_set(thb_ctx* ctx, DevBuf& set, uint64_t& cap, unsigned int* ovf)
+{
+  const int W = ctx->world;
+  CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_count.reserve(8 * (size_t)(W + 1)));
+  unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
+  CU(cudaMemsetAsync(d_cnt, 0, 8, ctx->compute));
+  hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, d_cnt);
+  CU(cudaGetLastError());
+  // ncclUint64 = 5
+  if (ctx->nccl.AllGather(d_cnt, d_cnt + 1, 1, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
+  std::vector<unsigned long long> counts(W + 1);
+  CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * (size_t)(W + 1), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  unsigned long long mx = 0, total = 0; for (int r = 0; r < W; ++r) { mx = std::max(mx, counts[1 + r]); total += counts[1 + r]; }
+  if (mx == 0) return THB_OK;
+  DevBuf send, recv; CU(send.reserve(mx * 8)); CU(recv.reserve(mx * 8 * W));
+  CU(cudaMemsetAsync(send.p, 0xff, mx * 8, ctx->compute));                     // pad with HS_EMPTY
+  CU(cudaMemcpyAsync(send.p, ctx->d_keys.p, counts[0] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  if (ctx->nccl.AllGather(send.p, recv.p, mx, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(keys)");
+  while (cap < 2 * total) { int rc = grow_set(ctx, set, cap, ovf); if (rc) return rc; }
+  HashSet dst; dst.slots = (uint64_t*)set.p; dst.mask = cap - 1; dst.overflow = ovf;
+  hs_insert_list_kernel<<<grid_for(mx * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)recv.p, mx * W, dst);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->compute));
+  send.release(); recv.release();
+  return THB_OK;
+}
+
+int thb_segjuncs_allgather(thb_ctx* ctx)
+{
+  if (!ctx) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->comm) return fail(ctx, THB_ESTATE, "thb_comm_init not called");
+  int rc;
+  if ((rc = allgather_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs))) return rc;
+  if ((rc = allgather_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels))) return rc;
+  // insertion records: gather the append buffers (4 x u64 per record)
+  const int W = ctx->world;
+  CU(ctx->d_count.reserve(8 * (size_t)(W + 1)));
+  unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
+  CU(cudaMemcpyAsync(d_cnt, ctx->d_ins_count, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  if (ctx->nccl.AllGather(d_cnt, d_cnt + 1, 1, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(ins counts)");
+  std::vector<unsigned long long> counts(W + 1);
+  CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * (size_t)(W + 1), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  unsigned long long mx = 0, total = 0; for (int r = 0; r < W; ++r) { mx = std::max(mx, counts[1 + r]); total += counts[1 + r]; }
+  if (mx) {
+    DevBuf send, recv; CU(send.reserve(mx * sizeof(InsRec))); CU(recv.reserve(mx * sizeof(InsRec) * W));
+    CU(cudaMemsetAsync(send.p, 0xff, mx * sizeof(InsRec), ctx->compute));
+    CU(cudaMemcpyAsync(send.p, ctx->d_ins.p, counts[0] * sizeof(InsRec), cudaMemcpyDeviceToDevice, ctx->compute));
+    if (ctx->nccl.AllGather(send.p, recv.p, mx * 4, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(ins)");
+    std::vector<InsRec> all(mx * W);
+    CU(cudaMemcpyAsync(all.data(), recv.p, all.size() * sizeof(InsRec), cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    std::vector<InsRec> keep; keep.reserve(total);
+    for (const InsRec& r : all) if (r.key != ~0ull) keep.push_back(r);
+    if (keep.size() > ctx->cap_ins) { ctx->d_ins.release(); ctx->cap_ins = keep.size() + 1024; CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec))); }
+    unsigned long long n = keep.size();
+    CU(cudaMemcpyAsync(ctx->d_ins.p, keep.data(), n * sizeof(InsRec), cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaMemcpyAsync(ctx->d_ins_count, &n, 8, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    send.release(); recv.release();
+  }
+  return THB_OK;
+}
+
+}  // extern "C"
