@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- measurement of the splice-junction hot path on B200 (contract: task statement + DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+
+One "step" = one pass of the hot path (thb_segjuncs_begin -> submit(left mates) -> submit(right mates)
+-> [N>1: NCCL all-gather of the discovered sets] -> thb_segjuncs_finish) over one batch of synthetic
+2x101 bp read pairs.  Workload at N=1: BASELINE.json configs[1] (10 M pairs, chr20-sized reference).  For
+N>1 every rank runs the same number of pairs (its own shard of reads, same reference): weak scaling.
+
+  value  : reads (mates) per second, whole job, inputs resident in HBM (CUDA events on the library's stream)
+  e2e    : same metric through the C ABI with HOST (pinned) buffers: H2D copies + D2H results inside the timing
+  roofline : scan kernel, algorithmic bytes (SURVEY.md §8d formula on the actual task counts) / CUDA-event time
+  cpu_baseline : the reference's own segment_juncs binary (oracle/_ref) on a bounded sample, same box
+
+`--impl reference` times the reference CPU binary only (rank 0 alone under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+CHR20 = 64_444_167
+METRIC = "spliced reads processed/s (segment_juncs junction+indel discovery), 2x101bp"
+UNIT = "reads/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload
+
+
+def make_workload(pairs: int, rank: int, workers: int):
+    from tophat_b200 import synth
+    chunk = 500_000 if pairs >= 500_000 else max(1000, pairs)
+    nchunks = (pairs + chunk - 1) // chunk
+    cfg = synth.SynthConfig(contig_lens=(CHR20,), n_pairs=pairs, seed=20240611, chunk=chunk,
+                            chunk_seed_base=rank * nchunks)
+    t = time.time()
+    wl = synth.generate(cfg, workers=workers)
+    log("[bench] rank %d: generated %d pairs in %.1f s (%d workers)" % (rank, pairs, time.time() - t, workers))
+    return wl
+
+
+def pack(wl):
+    from tophat_b200 import synth
+    t = time.time()
+    bl = synth.pack_side(wl.left, wl.right, False)
+    br = synth.pack_side(wl.right, wl.left, True, order_base=bl.n_bundles)
+    log("[bench] packed %d + %d bundles in %.1f s" % (bl.n_bundles, br.n_bundles, time.time() - t))
+    return [bl, br]
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref binaries; the only place besides tests/ that executes oracle/)
+
+
+class ReferenceArm:
+    """Prepares BAM/FASTA inputs for a sample of the workload and times the reference's segment_juncs."""
+
+    def __init__(self, wl, sample_pairs: int, threads: int):
+        from tophat_b200 import synth
+        from oracle import pyoracle
+        self.py = pyoracle
+        if not pyoracle.have_reference():
+            raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference exists)")
+        self.sample_pairs = min(sample_pairs, wl.cfg.n_pairs)
+        self.threads = threads
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        self.dir = tempfile.mkdtemp(prefix="thb_ref_", dir=base)
+        t = time.time()
+        sub = synth.subset(wl, self.sample_pairs)
+        self.nseg = len(sub.left.seg_hits)
+        self.files = synth.write_pipeline_files(sub, self.dir)
+        self.bams = pyoracle.make_bams(self.files, self.dir, self.nseg)
+        # a 1-pair input measures the fixed start-up (FASTA load of the same reference)
+        tiny = synth.subset(wl, 1)
+        self.tdir = os.path.join(self.dir, "tiny"); os.makedirs(self.tdir)
+        tf = synth.write_pipeline_files(tiny, self.tdir)
+        tf["fasta"] = self.files["fasta"]; tf["header"] = self.files["header"]
+        self.tfiles, self.tbams = tf, pyoracle.make_bams(tf, self.tdir, self.nseg)
+        log("[bench] reference arm inputs for %d pairs ready in %.1f s" % (self.sample_pairs, time.time() - t))
+
+    def _run(self, files, bams, outdir, threads):
+        opts = self.py.tophat_common_opts(50, 20)
+        t = time.perf_counter()
+        outs = self.py.run_segment_juncs(os.path.join(self.py.REF_DIR, "segment_juncs"), files, bams, outdir, self.nseg,
+                                         opts=opts, threads=threads)
+        return time.perf_counter() - t, outs
+
+    def startup(self) -> float:
+        return min(self._run(self.tfiles, self.tbams, self.tdir, 1)[0] for _ in range(2))
+
+    def step(self) -> float:
+        return self._run(self.files, self.bams, self.dir, self.threads)[0]
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def usable_threads(sample_pairs: int) -> int:
+    # -p N is honoured only when every .index side file has >= N entries (utils.cpp:75-79); an entry is written
+    # every >= 1000 records, the sparsest stream (*.mapped.bam of one side) holds ~0.25 records per pair
+    n = os.cpu_count() or 1
+    return max(1, min(n, sample_pairs // 8000))
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    wl = make_workload(args.ref_pairs, 0, max(1, (os.cpu_count() or 1)))
+    threads = usable_threads(args.ref_pairs)
+    arm = ReferenceArm(wl, args.ref_pairs, threads)
+    try:
+        st = arm.startup()
+        for _ in range(args.warmup):
+            arm.step()
+        times = [arm.step() for _ in range(args.steps)]
+    finally:
+        arm.close()
+    reads = 2 * arm.sample_pairs
+    per = sum(times) / len(times)
+    work = max(per - st, 1e-6)
+    val = reads / work
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args.ref_pairs, 1, note="bounded sample of the GPU arm's workload; value excludes the "
+                                      "%.2f s fixed start-up (FASTA load) measured on a 1-pair input" % st),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": "%d pairs (%d reads), oracle/_ref/segment_juncs -p%d, wall %.2f s/step incl. %.2f s start-up"
+                                       % (arm.sample_pairs, reads, threads, per, st)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(pairs: int, world: int, note: str = ""):
+    c = {"workload": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, "
+                     "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
+         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stage": "segment_juncs (junction / indel discovery)",
+         "l2": "inputs (>1 GB per step at the default size) exceed the 126 MB L2; no explicit flush",
+         "parallelism": "read-shard x%d%s" % (world, " + NCCL all-gather of the junction/indel sets" if world > 1 else "")}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index; self.proc = None; self.path = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        fd, self.path = tempfile.mkstemp(prefix="thb_clk_", suffix=".csv"); os.close(fd)
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+        if not rows and shutil.which("nvidia-smi"):
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True).stdout
+            rows = [l.strip().split(", ") for l in out.splitlines() if l.strip()]
+        sm, mx, reasons = [], 0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+
+
+def run_gpu_arm(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    from tophat_b200 import capi
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    workers = max(1, (os.cpu_count() or 1) // world)
+    wl = make_workload(args.pairs, rank, workers)
+    batches = pack(wl)
+    n_reads = 2 * args.pairs
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    ctx = capi.Context(local_rank)
+    ctx.ref_upload(wl.ref)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ctx.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    # device-resident copies (value) and pinned host copies (e2e)
+    fields = ("bundles", "seg_count", "reads", "hits", "partner_hits")
+    dev, dev_structs, pinned = [], [], []
+    for b in batches:
+        t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k)).view(np.uint8).reshape(-1)) for k in fields}
+        d = {k: v.cuda() for k, v in t.items()}
+        dev.append(d)
+        bc = capi.batch_c(b)
+        bc.bundles, bc.seg_count, bc.reads = d["bundles"].data_ptr(), d["seg_count"].data_ptr(), d["reads"].data_ptr()
+        bc.hits, bc.partner_hits = d["hits"].data_ptr(), d["partner_hits"].data_ptr()
+        dev_structs.append(bc)
+        pt = {k: v.pin_memory() for k, v in t.items()}
+        pinned.append(pt)
+    torch.cuda.synchronize()
+
+    def pinned_struct(i):
+        bc = capi.batch_c(batches[i]); pt = pinned[i]
+        bc.bundles, bc.seg_count, bc.reads = pt["bundles"].data_ptr(), pt["seg_count"].data_ptr(), pt["reads"].data_ptr()
+        bc.hits, bc.partner_hits = pt["hits"].data_ptr(), pt["partner_hits"].data_ptr()
+        return bc
+    host_structs = [pinned_struct(i) for i in range(len(batches))]
+    h2d_bytes = sum(b.nbytes() for b in batches)
+
+    import ctypes as C
+
+    def step(device_resident: bool):
+        ctx.segjuncs_begin(P)
+        for i in range(len(batches)):
+            if device_resident:
+                ctx.segjuncs_submit_device(dev_structs[i])
+            else:
+                ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(host_structs[i])), "thb_segjuncs_submit")
+        if world > 1:
+            ctx.segjuncs_allgather()
+        res = ctx.segjuncs_finish()
+        return res, ctx.timing()
+
+    def timed(device_resident: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            res, tm = step(device_resident)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scan_ms, alg, launches = 0.0, 0, 0
+        e0.record(stream)
+        for _ in range(steps):
+            res, tm = step(device_resident)
+            scan_ms += tm.scan_kernel_ms; alg += tm.algorithmic_bytes; launches += tm.total_launches
+            scan_launches = tm.kernel_launches
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, scan_ms, alg, launches, scan_launches, res, tm
+
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
+    ms, scan_ms, alg, launches, scan_launches, res, tm = timed(True, args.steps, args.warmup)
+    ms_e2e, _, _, _, _, res_h, _ = timed(False, args.steps, args.warmup)
+    clocks = clk.stop() if rank == 0 else None
+    d2h_bytes = int(res_h.junctions.nbytes + res_h.deletions.nbytes + res_h.insertions.nbytes + res_h.fusions.nbytes)
+
+    # the two arms must agree with each other (same sets from device-resident and host submission)
+    assert res.junctions.shape == res_h.junctions.shape and (res.junctions == res_h.junctions).all()
+
+    total_reads = n_reads * world
+    per_step = ms / args.steps
+    value = total_reads / (per_step * 1e-3)
+    e2e_val = total_reads / (ms_e2e / args.steps * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks, peak_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        scan_per_launch_ms = scan_ms / max(1, args.steps * scan_launches)
+        achieved = (alg / max(1, args.steps * scan_launches)) / (scan_per_launch_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("segjuncs_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": workload_config(args.pairs, world),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": ms_e2e / args.steps, "api": "thb_segjuncs_begin/submit(host, pinned)/finish"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "segjuncs_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
+                             "frac": achieved / peaks, "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg / max(1, args.steps * scan_launches),
+                             "kernel_ms_per_launch": scan_per_launch_ms, "launches_per_step": scan_launches},
+                "clocks": clocks,
+                "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
+                            "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
+                            "indel_tasks": int(tm.n_indel_tasks), "rescue_tasks": int(tm.n_rescue_tasks)}}
+    ctx.close()
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                threads = usable_threads(args.ref_pairs)
+                arm = ReferenceArm(wl, args.ref_pairs, threads)
+                try:
+                    st = arm.startup(); arm.step(); wall = arm.step()
+                finally:
+                    arm.close()
+                reads = 2 * arm.sample_pairs
+                line["cpu_baseline"] = {"value": reads / max(wall - st, 1e-6), "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": "first %d pairs (%d reads) of the same workload; oracle/_ref/segment_juncs -p%d; wall %.2f s "
+                                                  "of which %.2f s fixed start-up (FASTA load, excluded)" % (arm.sample_pairs, reads, threads, wall, st)}
+            except Exception as e:  # the baseline leg must never hide the GPU result
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("THB_BENCH_PAIRS", 10_000_000)), help="read pairs per GPU")
+    ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 200_000)),
+                    help="pairs in the bounded sample the reference CPU binary is timed on")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -213,9 +213,16 @@ int thb_segjuncs_allgather(thb_ctx* ctx);
 typedef struct thb_timing {
   float h2d_ms; float scan_kernel_ms; float finish_ms; float total_ms;
   uint64_t n_windows; uint64_t n_indel_tasks; uint64_t n_rescue_tasks; uint64_t n_juncs_emitted;
-  uint64_t algorithmic_bytes; uint32_t kernel_launches; uint32_t reserved;
+  uint64_t algorithmic_bytes;
+  uint32_t kernel_launches;   /* launches of the scan kernel                                       */
+  uint32_t total_launches;    /* every kernel of this library since thb_segjuncs_begin (valid after finish) */
 } thb_timing;
 int thb_last_timing(thb_ctx* ctx, thb_timing* out);
+
+/* Page-locked host memory for batch arrays (full-speed, asynchronous host->device copies).
+ * Returns NULL on failure. */
+void* thb_alloc_pinned(size_t bytes);
+void  thb_free_pinned(void* p);
 
 /* Raw access for the measurement harness: CUDA stream of the context (cudaStream_t as void*). */
 void* thb_stream(thb_ctx* ctx);

@@ -68,7 +68,7 @@ def lib() -> C.CDLL:
         for n in ("orc_n_juncs", "orc_n_dels", "orc_n_ins", "orc_n_fus"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = C.c_size_t
-        for n in ("orc_get_juncs", "orc_get_dels", "orc_get_ins", "orc_get_fus", "orc_get_counters"):
+        for n in ("orc_get_juncs", "orc_get_dels", "orc_get_ins", "orc_get_fus", "orc_get_counters", "orc_get_ins_order"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
             getattr(L, n).restype = None
         _lib = L
@@ -102,7 +102,10 @@ def segjuncs(params: capi.Params, ref: synth.RefImage, batches: List[synth.Packe
         if f.size: L.orc_get_fus(res, f.ctypes.data)
         cnt = np.zeros(5, dtype=np.uint64)
         L.orc_get_counters(res, cnt.ctypes.data)
-        return capi.SegJuncsResults(j, d, i, f), Counters(cnt)
+        out = capi.SegJuncsResults(j, d, i, f)
+        out.insertion_order = np.zeros(i.size, dtype=np.uint64)
+        if i.size: L.orc_get_ins_order(res, out.insertion_order.ctypes.data)
+        return out, Counters(cnt)
     finally:
         L.orc_results_free(res)
 

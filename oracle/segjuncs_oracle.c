@@ -636,6 +636,9 @@ int orc_segjuncs_batch(const thb_params* P, const thb_ref_image* img, const thb_
   for (uint32_t bi = 0; bi < b->n_bundles; ++bi) {
     const thb_bundle* bu = &b->bundles[bi];
     unpack_read(b, bi, bu->read_len, read);
+    /* insertion priority = global processing position of the bundle (first inserted wins,
+     * insertions.h:52-67); order_base lets a sharded run reproduce the single-process order */
+    out->order = (b->order_base + bi) << 12;
     uint32_t off = bu->hit_begin;
     for (uint32_t s = 0; s < b->n_segs; ++s) {
       H[s].n = 0;
@@ -691,5 +694,6 @@ void orc_get_juncs(const orc_results* r, thb_junction* out) { for (size_t i = 0;
 void orc_get_dels(const orc_results* r, thb_junction* out) { for (size_t i = 0; i < r->n_dels; ++i) { out[i].ref_id = r->dels[i].ref_id; out[i].left = r->dels[i].left; out[i].right = r->dels[i].right; out[i].antisense = 0; } }
 void orc_get_ins(const orc_results* r, thb_insertion* out) { for (size_t i = 0; i < r->n_ins; ++i) { memset(&out[i], 0, sizeof out[i]); out[i].ref_id = r->ins[i].ref_id; out[i].left = r->ins[i].left; out[i].len = r->ins[i].len; memcpy(out[i].seq, r->ins[i].seq, sizeof out[i].seq); } }
 void orc_get_fus(const orc_results* r, thb_fusion* out) { for (size_t i = 0; i < r->n_fus; ++i) { out[i].ref_id1 = r->fus[i].ref1; out[i].ref_id2 = r->fus[i].ref2; out[i].left = r->fus[i].left; out[i].right = r->fus[i].right; out[i].dir = r->fus[i].dir; out[i].count = r->fus[i].count; out[i].edit_dist = r->fus[i].edit_dist; out[i].reserved = 0; } }
+void orc_get_ins_order(const orc_results* r, uint64_t* out) { for (size_t i = 0; i < r->n_ins; ++i) out[i] = r->ins[i].order; }
 void orc_get_counters(const orc_results* r, uint64_t* out5)
 { out5[0] = r->n_windows; out5[1] = r->n_indel_tasks; out5[2] = r->n_rescue_tasks; out5[3] = r->n_fusion_tasks; out5[4] = r->n_juncs_emitted; }

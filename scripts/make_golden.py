@@ -1,0 +1,45 @@
+"""Generates tests/golden/*: outputs of the reference's OWN segment_juncs binary (oracle/_ref, built
+from /root/reference/src by oracle/Makefile.ref) on seeded synthetic workloads.
+
+Run in the build container (needs oracle/_ref):   python scripts/make_golden.py
+The workloads are re-generated deterministically by the tests from the JSON config stored beside
+each output (tophat_b200/synth.py, seeded PCG64), so only the small text outputs are committed.
+"""
+import json, os, shutil, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tophat_b200 import synth
+from oracle import pyoracle
+
+CASES = {
+    # name: (SynthConfig kwargs, inner_dist_mean, inner_dist_std_dev, extra options)
+    "splice_2contig": (dict(contig_lens=(400_000, 150_000), n_pairs=3000, seed=101), 50, 20, []),
+    "indel_heavy": (dict(contig_lens=(300_000,), n_pairs=2500, seed=102, indel_prob=0.5), 50, 20, []),
+    "wide_flank": (dict(contig_lens=(500_000,), n_pairs=2000, seed=103, indel_prob=0.1, n_rate=0.004), 200, 20, []),
+    "firststrand": (dict(contig_lens=(300_000, 100_000), n_pairs=2000, seed=104), 50, 20, ["--library-type", "fr-firststrand"]),
+}
+
+
+def main():
+    assert pyoracle.build_reference(), "oracle/_ref missing and /root/reference not available"
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, im, isd, extra) in CASES.items():
+        out = os.path.join(gdir, name)
+        os.makedirs(out, exist_ok=True)
+        wl = synth.generate(synth.SynthConfig(**kw))
+        with tempfile.TemporaryDirectory() as td:
+            files = synth.write_pipeline_files(wl, td)
+            nseg = len(wl.left.seg_hits)
+            bams = pyoracle.make_bams(files, td, nseg)
+            outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg,
+                                              opts=pyoracle.tophat_common_opts(im, isd, extra))
+            for k in ("juncs", "insertions", "deletions"):
+                shutil.copy(outs[k], os.path.join(out, "segment." + k))
+        with open(os.path.join(out, "config.json"), "w") as f:
+            json.dump(dict(synth=kw, inner_dist_mean=im, inner_dist_std_dev=isd, extra=extra,
+                           generator="scripts/make_golden.py", binary="oracle/_ref/segment_juncs (TopHat 2.1.2, -p1)"), f, indent=1)
+        print(name, {k: sum(1 for _ in open(os.path.join(out, "segment." + k))) for k in ("juncs", "insertions", "deletions")})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""Shared helpers of the parity tests (test infrastructure; may import oracle/)."""
+import json
+import os
+
+import numpy as np
+
+from tophat_b200 import capi, synth
+from oracle import pyoracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+LIBTYPE = {"fr-unstranded": 1, "fr-firststrand": 2, "fr-secondstrand": 3}
+
+
+def golden_cases():
+    return sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "config.json")))
+
+
+def load_golden(name):
+    d = os.path.join(GOLDEN, name)
+    cfg = json.load(open(os.path.join(d, "config.json")))
+    kw = dict(cfg["synth"])
+    kw["contig_lens"] = tuple(kw["contig_lens"])
+    wl = synth.generate(synth.SynthConfig(**kw))
+    over = dict(inner_dist_mean=cfg["inner_dist_mean"], inner_dist_std_dev=cfg["inner_dist_std_dev"])
+    ex = cfg.get("extra", [])
+    if "--library-type" in ex:
+        over["library_type"] = LIBTYPE[ex[ex.index("--library-type") + 1]]
+    P = capi.default_params(**over)
+    texts = {k: open(os.path.join(d, "segment." + k)).read() for k in ("juncs", "insertions", "deletions")}
+    return wl, P, texts
+
+
+def pack_both(wl, fusion_search=False):
+    bl = synth.pack_side(wl.left, wl.right, False, fusion_search)
+    br = synth.pack_side(wl.right, wl.left, True, fusion_search, order_base=bl.n_bundles)
+    return [bl, br]
+
+
+def as_text(res, names):
+    return {"juncs": pyoracle.format_juncs(res.junctions, names),
+            "insertions": pyoracle.format_insertions(res.insertions, names),
+            "deletions": pyoracle.format_deletions(res.deletions, names)}
+
+
+def assert_same_results(got, want, what=""):
+    for name in ("junctions", "deletions", "insertions", "fusions"):
+        a, b = getattr(got, name), getattr(want, name)
+        assert a.shape == b.shape, "%s %s: %d vs %d records" % (what, name, len(a), len(b))
+        assert (a == b).all(), "%s %s differ" % (what, name)
+
+
+def gpu_segjuncs(P, ref, batches, ctx=None):
+    own = ctx is None
+    if own:
+        ctx = capi.Context(0)
+        ctx.ref_upload(ref)
+    ctx.segjuncs_begin(P)
+    for b in batches:
+        ctx.segjuncs_submit(b)
+    got = ctx.segjuncs_finish()
+    t = ctx.timing()
+    if own:
+        ctx.close()
+    return got, t
+
+
+# ---- hand-built bundles for known-answer tests -----------------------------
+
+def manual_workload(contigs, reads):
+    """contigs: list of (name, ascii bytes); reads: list of dict(seq=ascii, hits=[[(ref_id,left,len,edit,anti)]*]*nseg,
+    partner=[(ref_id,left,len,edit,anti)], flags=int).  Returns (RefImage, PackedBatch)."""
+    ref = synth.build_ref_image([n for n, _ in contigs], [synth.codes_from_ascii(s) for _, s in contigs])
+    nseg = len(reads[0]["hits"])
+    L = max(len(r["seq"]) for r in reads)
+    rw = (L + 63) // 64
+    bundles = np.zeros(len(reads), dtype=synth.BUNDLE_DTYPE)
+    seg_count = np.zeros((len(reads), nseg), dtype="<u2")
+    rd = np.zeros((len(reads), 3 * rw), dtype="<u8")
+    hits, partner = [], []
+    for i, r in enumerate(reads):
+        codes = synth.codes_from_ascii(r["seq"])
+        padded = np.zeros((1, L), dtype=np.uint8)
+        padded[0, :len(codes)] = codes
+        rd[i] = synth.pack_reads(padded, rw)[0]
+        bundles[i]["read_id"] = i + 1
+        bundles[i]["hit_begin"] = len(hits)
+        bundles[i]["partner_begin"] = len(partner)
+        bundles[i]["read_len"] = len(codes)
+        bundles[i]["flags"] = r.get("flags", synth.B_INDELS | synth.B_GAPS)
+        for s, hs in enumerate(r["hits"]):
+            seg_count[i, s] = len(hs)
+            for (rid, left, ln, ed, anti) in hs:
+                hits.append((rid, left, left + ln, ln, ed, (synth.HIT_ANTISENSE if anti else 0) | (synth.HIT_END if s == nseg - 1 else 0), 0))
+        ph = r.get("partner", [])
+        bundles[i]["n_partner"] = len(ph)
+        for (rid, left, ln, ed, anti) in ph:
+            partner.append((rid, left, left + ln, ln, ed, (synth.HIT_ANTISENSE if anti else 0) | synth.HIT_END, 0))
+    H = np.array(hits, dtype=synth.HIT_DTYPE) if hits else np.zeros(0, dtype=synth.HIT_DTYPE)
+    PH = np.array(partner, dtype=synth.HIT_DTYPE) if partner else np.zeros(0, dtype=synth.HIT_DTYPE)
+    return ref, synth.PackedBatch(nseg, rw, bundles, np.ascontiguousarray(seg_count), np.ascontiguousarray(rd), H, PH, 0)

@@ -73,7 +73,7 @@ class TimingC(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("scan_kernel_ms", C.c_float), ("finish_ms", C.c_float),
                 ("total_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
                 ("n_rescue_tasks", C.c_uint64), ("n_juncs_emitted", C.c_uint64),
-                ("algorithmic_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("algorithmic_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("total_launches", C.c_uint32)]
 
 
 def ref_image_c(ref: synth.RefImage) -> RefImageC:
@@ -156,6 +156,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_pack_bases.restype = None
     lib.thb_pack_read.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.thb_pack_read.restype = None
+    lib.thb_alloc_pinned.argtypes = [C.c_size_t]
+    lib.thb_alloc_pinned.restype = C.c_void_p
+    lib.thb_free_pinned.argtypes = [C.c_void_p]
+    lib.thb_free_pinned.restype = None
     lib.thb_nccl_unique_id.argtypes = [C.c_void_p]
     lib.thb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.thb_segjuncs_allgather.argtypes = [C.c_void_p]
@@ -219,3 +223,18 @@ class Context:
 
     def stream(self) -> int:
         return int(self.lib.thb_stream(self.h) or 0)
+
+    # ---- multi-GPU exchange (NCCL)
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.thb_nccl_unique_id(buf)
+        if rc != 0:
+            raise ThbError("thb_nccl_unique_id failed (%d)" % rc)
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int) -> None:
+        buf = C.create_string_buffer(uid, 128)
+        self._check(self.lib.thb_comm_init(self.h, buf, rank, world), "thb_comm_init")
+
+    def segjuncs_allgather(self) -> None:
+        self._check(self.lib.thb_segjuncs_allgather(self.h), "thb_segjuncs_allgather")

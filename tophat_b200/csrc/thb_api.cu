@@ -77,6 +77,7 @@ struct thb_ctx {
   // accounting
   thb_timing timing{}; uint64_t n_bundles_total = 0, n_hits_total = 0, n_partner_total = 0;
   uint64_t n_ins_out = 0, n_del_out = 0;
+  uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
 };
@@ -103,7 +104,7 @@ int alloc_set(thb_ctx* ctx, DevBuf& b, uint64_t cap)
 {
   CU(b.reserve(cap * sizeof(uint64_t)));
   hs_clear_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((uint64_t*)b.p, cap);
-  CU(cudaGetLastError());
+  CU(cudaGetLastError()); ctx->own_launches++;
   return THB_OK;
 }
 
@@ -112,7 +113,7 @@ int grow_set(thb_ctx* ctx, DevBuf& b, uint64_t& cap, unsigned int* ovf)
 {
   DevBuf nb; uint64_t ncap = cap * 2;
   CU(nb.reserve(ncap * sizeof(uint64_t)));
-  hs_clear_kernel<<<grid_for(ncap, 256), 256, 0, ctx->compute>>>((uint64_t*)nb.p, ncap);
+  hs_clear_kernel<<<grid_for(ncap, 256), 256, 0, ctx->compute>>>((uint64_t*)nb.p, ncap); ctx->own_launches += 2;
   CU(cudaMemsetAsync(ovf, 0, sizeof(unsigned int), ctx->compute));
   HashSet dst; dst.slots = (uint64_t*)nb.p; dst.mask = ncap - 1; dst.overflow = ovf;
   hs_rehash_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)b.p, cap, dst);
@@ -148,7 +149,7 @@ int launch_scan(thb_ctx* ctx, const BatchView& bv)
   const int block = 256;
   segjuncs_kernel<<<grid_for(bv.n_bundles, block), block, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, outputs(ctx));
   CU(cudaGetLastError());
-  ctx->timing.kernel_launches++;
+  ctx->timing.kernel_launches++; ctx->own_launches++;
   return THB_OK;
 }
 
@@ -268,6 +269,14 @@ void thb_destroy(thb_ctx* ctx)
 
 void* thb_stream(thb_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
 
+void* thb_alloc_pinned(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void thb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 void thb_pack_bases(const char* seq, uint64_t len, uint64_t gstart, uint64_t* planes, uint64_t* nmask)
 {
   for (uint64_t i = 0; i < len; ++i) {
@@ -353,6 +362,7 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   CU(cudaStreamSynchronize(ctx->compute));
   ctx->h_juncs.clear(); ctx->h_dels.clear(); ctx->h_ins.clear(); ctx->h_fus.clear();
   memset(&ctx->timing, 0, sizeof ctx->timing);
+  ctx->own_launches = 2;            // the two hs_clear launches above
   ctx->n_bundles_total = ctx->n_hits_total = ctx->n_partner_total = 0; ctx->n_ins_out = ctx->n_del_out = 0;
   ctx->begun = true;
   return THB_OK;
@@ -468,7 +478,7 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, std::vector<thb_j
   CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8)); CU(ctx->d_count.reserve(64));
   CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
   hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, (unsigned long long*)ctx->d_count.p);
-  CU(cudaGetLastError());
+  CU(cudaGetLastError()); ctx->own_launches++;
   unsigned long long n = 0;
   CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
@@ -481,7 +491,7 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, std::vector<thb_j
   if (n > limit) n = limit;       // std::set capped at max_seg_juncs by erasing the largest (1692-1693)
   CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
   decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_keys_sorted.p, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
-  CU(cudaGetLastError());
+  CU(cudaGetLastError()); ctx->own_launches++;
   out.resize(n);
   CU(cudaMemcpyAsync(out.data(), ctx->d_decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
@@ -524,6 +534,7 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   ctx->n_ins_out = nins; ctx->n_del_out = ctx->h_dels.size();
   ctx->timing.n_windows = cnt[0]; ctx->timing.n_indel_tasks = cnt[1]; ctx->timing.n_rescue_tasks = cnt[2]; ctx->timing.n_juncs_emitted = cnt[3];
   ctx->timing.algorithmic_bytes = algorithmic_bytes(ctx, cnt);
+  ctx->timing.total_launches = ctx->own_launches;
   out->n_junctions = ctx->h_juncs.size(); out->junctions = ctx->h_juncs.data();
   out->n_deletions = ctx->h_dels.size(); out->deletions = ctx->h_dels.data();
   out->n_insertions = ctx->h_ins.size(); out->insertions = ctx->h_ins.data();
@@ -581,7 +592,7 @@ static int allgather_set(thb_ctx* ctx, DevBuf& set, uint64_t& cap, unsigned int*
   unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
   CU(cudaMemsetAsync(d_cnt, 0, 8, ctx->compute));
   hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, d_cnt);
-  CU(cudaGetLastError());
+  CU(cudaGetLastError()); ctx->own_launches++;
   // ncclUint64 = 5
   if (ctx->nccl.AllGather(d_cnt, d_cnt + 1, 1, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
   std::vector<unsigned long long> counts(W + 1);
@@ -596,7 +607,7 @@ static int allgather_set(thb_ctx* ctx, DevBuf& set, uint64_t& cap, unsigned int*
   while (cap < 2 * total) { int rc = grow_set(ctx, set, cap, ovf); if (rc) return rc; }
   HashSet dst; dst.slots = (uint64_t*)set.p; dst.mask = cap - 1; dst.overflow = ovf;
   hs_insert_list_kernel<<<grid_for(mx * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)recv.p, mx * W, dst);
-  CU(cudaGetLastError());
+  CU(cudaGetLastError()); ctx->own_launches++;
   CU(cudaStreamSynchronize(ctx->compute));
   send.release(); recv.release();
   return THB_OK;

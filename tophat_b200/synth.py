@@ -156,6 +156,7 @@ class SynthConfig:
     intron_max: int = 400_000
     fusion_frac: float = 0.0           # fraction of fragments that are chimeric (config 5 style)
     chunk: int = 500_000
+    chunk_seed_base: int = 0           # added to the chunk index in the RNG stream id (per-rank shards)
 
 
 @dataclasses.dataclass
@@ -360,7 +361,95 @@ def _place(ref_codes, space: _ExonSpace, codes_fwd: np.ndarray, emap: np.ndarray
     return (g1, r1, l1, m1), (g2, r2, l2, m2)
 
 
-def generate(cfg: SynthConfig) -> Workload:
+_GEN_STATE = {}
+
+
+def _gen_chunk(ci: int):
+    """One chunk of fragments (independent RNG stream per chunk so chunks can run in any process)."""
+    st = _GEN_STATE
+    cfg, contigs, space, exonic = st["cfg"], st["contigs"], st["space"], st["exonic"]
+    rng = np.random.default_rng(np.random.SeedSequence([cfg.seed, cfg.chunk_seed_base + ci + 1]))
+    L = cfg.read_len
+    offs, lens = segment_layout(L, cfg.segment_length)
+    nseg = offs.shape[0]
+    done = ci * cfg.chunk
+    n = min(cfg.chunk, cfg.n_pairs - done)
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[]) for s in ("left", "right")}
+    a0, b0, plus = _sample_mates(rng, cfg, space, contigs, n)
+    for which, x0 in (("A", a0), ("B", b0)):
+        codes_fwd, emap = _make_read_fwd(rng, cfg, space, exonic, x0)
+        # A is sequenced forward, B reverse-complemented (fr library); fragment strand decides
+        # which one is mate 1.
+        rev = which == "B"
+        # per-row side assignment: plus fragments: A=left,B=right ; minus: B=left, A=right
+        is_left = plus if which == "A" else ~plus
+        # whole-read contiguous mapping (the *.mapped.bam stream): <= 2 mismatches end to end
+        (g1, r1, l1, m1), _ = _place(contigs, space, codes_fwd, emap, 0, L, 2)
+        mapped = g1 & (emap[:, L - 1] - emap[:, 0] == L - 1)
+        # re-check contiguity on the genome: first-anchor placement must also fit the last base
+        rid_last, g_last, _ = space.to_genome(np.maximum(emap[:, L - 1], 0))
+        mapped &= (rid_last == r1) & (g_last == l1 + L - 1)
+        read_codes = revcomp_codes(codes_fwd) if rev else codes_fwd
+        for side, selmask in (("left", is_left), ("right", ~is_left)):
+            sel = np.nonzero(selmask)[0]
+            if sel.size == 0:
+                continue
+            base = done  # read index within side == pair index
+            A = acc[side]
+            A["reads"].append((sel + base, read_codes[sel]))
+            mh = np.zeros(int(mapped[sel].sum()), dtype=SEGHIT_DTYPE)
+            ms = sel[mapped[sel]]
+            mh["read_idx"] = ms + base
+            mh["ref_id"] = r1[ms]; mh["left"] = l1[ms]; mh["right"] = l1[ms] + L
+            mh["read_len"] = L; mh["edit_dist"] = m1[ms]
+            mh["flags"] = (HIT_ANTISENSE if rev else 0) | HIT_END
+            A["mapped"].append(mh)
+            A["unm"].append((sel + base, ~mapped[sel]))
+        # segment hits for reads that did not map end to end
+        for k in range(nseg):
+            # segment k of the *sequenced* read covers, in forward orientation:
+            lo = int(L - offs[k] - lens[k]) if rev else int(offs[k])
+            ln = int(lens[k])
+            for (g, r, l, m) in _place(contigs, space, codes_fwd, emap, lo, ln, 2):
+                keep = g & ~mapped
+                rows = np.nonzero(keep)[0]
+                if rows.size == 0:
+                    continue
+                sh = np.zeros(rows.size, dtype=SEGHIT_DTYPE)
+                sh["read_idx"] = rows + done
+                sh["ref_id"] = r[rows]; sh["left"] = l[rows]; sh["right"] = l[rows] + ln
+                sh["read_len"] = ln; sh["edit_dist"] = m[rows]
+                sh["flags"] = (HIT_ANTISENSE if rev else 0) | (HIT_END if k == nseg - 1 else 0)
+                for side, selmask in (("left", is_left), ("right", ~is_left)):
+                    part = sh[selmask[rows]]
+                    if part.size:
+                        acc[side]["seg"][k].append(part)
+            # decoy multihits at random positions
+            if cfg.decoy_rate > 0:
+                nd = rng.poisson(cfg.decoy_rate, size=n)
+                nd[mapped] = 0
+                rows = np.repeat(np.arange(n), nd)
+                if rows.size:
+                    dh = np.zeros(rows.size, dtype=SEGHIT_DTYPE)
+                    cidx = rng.integers(0, len(contigs), size=rows.size)
+                    clen = np.asarray([c.shape[0] for c in contigs])[cidx]
+                    dh["read_idx"] = rows + done
+                    dh["ref_id"] = cidx + 1
+                    dl = (rng.random(rows.size) * (clen - 1400)).astype(np.int64) + 700
+                    dh["left"] = dl; dh["right"] = dl + int(lens[k])
+                    dh["read_len"] = int(lens[k]); dh["edit_dist"] = rng.integers(0, 3, size=rows.size)
+                    dh["flags"] = (rng.integers(0, 2, size=rows.size) * HIT_ANTISENSE).astype(np.uint8) | \
+                        (HIT_END if k == nseg - 1 else 0)
+                    for side, selmask in (("left", is_left), ("right", ~is_left)):
+                        part = dh[selmask[rows]]
+                        if part.size:
+                            acc[side]["seg"][k].append(part)
+    return acc
+
+
+def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
+    """Reference + reads + analytic hits.  Chunks of cfg.chunk fragments carry their own RNG stream
+    (seed, chunk index), so the result does not depend on `workers` (fork-based process pool)."""
     rng = np.random.default_rng(np.random.PCG64(cfg.seed))
     names, contigs, exons_pc, anns = [], [], [], []
     for ci, n in enumerate(cfg.contig_lens):
@@ -382,81 +471,22 @@ def generate(cfg: SynthConfig) -> Workload:
     offs, lens = segment_layout(L, cfg.segment_length)
     nseg = offs.shape[0]
 
-    sides = {"left": None, "right": None}
-    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[]) for s in sides}
-    done = 0
-    while done < cfg.n_pairs:
-        n = min(cfg.chunk, cfg.n_pairs - done)
-        a0, b0, plus = _sample_mates(rng, cfg, space, contigs, n)
-        for which, x0 in (("A", a0), ("B", b0)):
-            codes_fwd, emap = _make_read_fwd(rng, cfg, space, exonic, x0)
-            # A is sequenced forward, B reverse-complemented (fr library); fragment strand decides
-            # which one is mate 1.
-            rev = which == "B"
-            # per-row side assignment: plus fragments: A=left,B=right ; minus: B=left, A=right
-            is_left = plus if which == "A" else ~plus
-            # whole-read contiguous mapping (the *.mapped.bam stream): <= 2 mismatches end to end
-            (g1, r1, l1, m1), _ = _place(contigs, space, codes_fwd, emap, 0, L, 2)
-            mapped = g1 & (emap[:, L - 1] - emap[:, 0] == L - 1)
-            # re-check contiguity on the genome: first-anchor placement must also fit the last base
-            rid_last, g_last, _ = space.to_genome(np.maximum(emap[:, L - 1], 0))
-            mapped &= (rid_last == r1) & (g_last == l1 + L - 1)
-            read_codes = revcomp_codes(codes_fwd) if rev else codes_fwd
-            for side, selmask in (("left", is_left), ("right", ~is_left)):
-                sel = np.nonzero(selmask)[0]
-                if sel.size == 0:
-                    continue
-                base = done  # read index within side == pair index
-                A = acc[side]
-                A["reads"].append((sel + base, read_codes[sel]))
-                mh = np.zeros(int(mapped[sel].sum()), dtype=SEGHIT_DTYPE)
-                ms = sel[mapped[sel]]
-                mh["read_idx"] = ms + base
-                mh["ref_id"] = r1[ms]; mh["left"] = l1[ms]; mh["right"] = l1[ms] + L
-                mh["read_len"] = L; mh["edit_dist"] = m1[ms]
-                mh["flags"] = (HIT_ANTISENSE if rev else 0) | HIT_END
-                A["mapped"].append(mh)
-                A["unm"].append((sel + base, ~mapped[sel]))
-            # segment hits for reads that did not map end to end
+    _GEN_STATE.update(cfg=cfg, contigs=contigs, space=space, exonic=exonic)
+    nchunks = (cfg.n_pairs + cfg.chunk - 1) // cfg.chunk
+    if workers > 1 and nchunks > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, nchunks)) as pool:
+            chunk_accs = pool.map(_gen_chunk, range(nchunks), chunksize=1)
+    else:
+        chunk_accs = [_gen_chunk(c) for c in range(nchunks)]
+    _GEN_STATE.clear()
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[]) for s in ("left", "right")}
+    for ca in chunk_accs:
+        for s in acc:
+            acc[s]["reads"] += ca[s]["reads"]; acc[s]["mapped"] += ca[s]["mapped"]; acc[s]["unm"] += ca[s]["unm"]
             for k in range(nseg):
-                # segment k of the *sequenced* read covers, in forward orientation:
-                lo = int(L - offs[k] - lens[k]) if rev else int(offs[k])
-                ln = int(lens[k])
-                for (g, r, l, m) in _place(contigs, space, codes_fwd, emap, lo, ln, 2):
-                    keep = g & ~mapped
-                    rows = np.nonzero(keep)[0]
-                    if rows.size == 0:
-                        continue
-                    sh = np.zeros(rows.size, dtype=SEGHIT_DTYPE)
-                    sh["read_idx"] = rows + done
-                    sh["ref_id"] = r[rows]; sh["left"] = l[rows]; sh["right"] = l[rows] + ln
-                    sh["read_len"] = ln; sh["edit_dist"] = m[rows]
-                    sh["flags"] = (HIT_ANTISENSE if rev else 0) | (HIT_END if k == nseg - 1 else 0)
-                    for side, selmask in (("left", is_left), ("right", ~is_left)):
-                        part = sh[selmask[rows]]
-                        if part.size:
-                            acc[side]["seg"][k].append(part)
-                # decoy multihits at random positions
-                if cfg.decoy_rate > 0:
-                    nd = rng.poisson(cfg.decoy_rate, size=n)
-                    nd[mapped] = 0
-                    rows = np.repeat(np.arange(n), nd)
-                    if rows.size:
-                        dh = np.zeros(rows.size, dtype=SEGHIT_DTYPE)
-                        cidx = rng.integers(0, len(contigs), size=rows.size)
-                        clen = np.asarray([c.shape[0] for c in contigs])[cidx]
-                        dh["read_idx"] = rows + done
-                        dh["ref_id"] = cidx + 1
-                        dl = (rng.random(rows.size) * (clen - 1400)).astype(np.int64) + 700
-                        dh["left"] = dl; dh["right"] = dl + int(lens[k])
-                        dh["read_len"] = int(lens[k]); dh["edit_dist"] = rng.integers(0, 3, size=rows.size)
-                        dh["flags"] = (rng.integers(0, 2, size=rows.size) * HIT_ANTISENSE).astype(np.uint8) | \
-                            (HIT_END if k == nseg - 1 else 0)
-                        for side, selmask in (("left", is_left), ("right", ~is_left)):
-                            part = dh[selmask[rows]]
-                            if part.size:
-                                acc[side]["seg"][k].append(part)
-        done += n
+                acc[s]["seg"][k] += ca[s]["seg"][k]
+    del chunk_accs
 
     def finish(side: str) -> SideData:
         A = acc[side]
@@ -468,8 +498,11 @@ def generate(cfg: SynthConfig) -> Workload:
             unm[idx] = u
         # prep_reads drops reads with >= 10% N or > 90% of one base (prep_reads.cpp:255-269): such
         # reads are never mapped, so they contribute no hits to any stream.
-        frac = np.stack([(reads == c).sum(axis=1) for c in range(5)], axis=1) / float(L)
-        qc_fail = (frac[:, :4] > 0.9).any(axis=1) | (frac[:, 4] >= 0.1)
+        qc_fail = np.zeros(cfg.n_pairs, dtype=bool)
+        for lo in range(0, cfg.n_pairs, 1 << 20):
+            blk = reads[lo:lo + (1 << 20)]
+            frac = np.stack([(blk == c).sum(axis=1) for c in range(5)], axis=1) / float(L)
+            qc_fail[lo:lo + (1 << 20)] = (frac[:, :4] > 0.9).any(axis=1) | (frac[:, 4] >= 0.1)
         seg_hits = []
         for k in range(nseg):
             h = np.concatenate(A["seg"][k]) if A["seg"][k] else np.zeros(0, dtype=SEGHIT_DTYPE)
@@ -483,6 +516,15 @@ def generate(cfg: SynthConfig) -> Workload:
 
     introns = np.concatenate(anns) if anns else np.zeros(0)
     return Workload(cfg, ref, finish("left"), finish("right"), introns)
+
+
+def subset(wl: Workload, n_pairs: int) -> Workload:
+    """The first n_pairs fragments of a workload (same reference): a bounded sample for the CPU baseline."""
+    def cut(sd: SideData) -> SideData:
+        return SideData(sd.reads[:n_pairs], sd.ids[:n_pairs], [h[h["read_idx"] < n_pairs] for h in sd.seg_hits],
+                        sd.mapped_hits[sd.mapped_hits["read_idx"] < n_pairs], sd.unmapped[:n_pairs])
+    cfg = dataclasses.replace(wl.cfg, n_pairs=n_pairs)
+    return Workload(cfg, wl.ref, cut(wl.left), cut(wl.right), wl.introns)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -663,9 +705,11 @@ def write_hits_sam(path: str, wl: Workload, side: SideData, hits: np.ndarray, se
             fwd = revcomp_codes(sub) if anti else sub
             codes = wl.ref.codes[rid - 1]
             left = int(h["left"])
-            refb = codes[left:left + fwd.shape[0]]
-            md, nm = _md_and_nm(fwd, refb)
             nm = int(h["edit_dist"])     # decoys carry a synthetic edit distance
+            if nm == 0:
+                md = str(fwd.shape[0])
+            else:
+                md, _ = _md_and_nm(fwd, codes[left:left + fwd.shape[0]])
             f.write("%s\t%d\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:UU\n" % (
                 qn, 16 if anti else 0, wl.ref.names[rid - 1], left + 1, fwd.shape[0],
                 CODE2CHAR[fwd].tobytes().decode(), "I" * fwd.shape[0], -6 * nm, nm, nm, md))
