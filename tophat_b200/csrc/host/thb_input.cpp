@@ -1,0 +1,315 @@
+#include "thb_input.hpp"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <zlib.h>
+
+namespace thbhost {
+
+// ---- RefTable -----------------------------------------------------------------------------------------
+uint32_t RefTable::get_id(const std::string& name)
+{
+  auto it = by_name_.find(name);
+  if (it != by_name_.end()) return it->second;
+  names_.push_back(name);
+  const uint32_t id = (uint32_t)names_.size();
+  by_name_.emplace(name, id);
+  return id;
+}
+uint32_t RefTable::find(const std::string& name) const { auto it = by_name_.find(name); return it == by_name_.end() ? 0 : it->second; }
+
+bool RefTable::load_sam_header(const std::string& path, std::string* err)
+{
+  std::ifstream in(path.c_str());
+  if (!in.good()) { *err = "Failed to open SAM header file " + path; return false; }
+  std::string line;
+  while (std::getline(in, line)) {
+    if (line.compare(0, 3, "@SQ") != 0) continue;
+    size_t p = 0;
+    while ((p = line.find('\t', p)) != std::string::npos) {
+      ++p;
+      if (line.compare(p, 3, "SN:") == 0) {
+        size_t e = line.find_first_of("\t\r\n", p);
+        get_id(line.substr(p + 3, e == std::string::npos ? std::string::npos : e - p - 3));
+        break;
+      }
+    }
+  }
+  return true;
+}
+
+// ---- Genome ---------------------------------------------------------------------------------------------
+thb_ref_image Genome::image() const
+{
+  thb_ref_image img; img.n_contigs = (uint32_t)contig_len.size(); img.contig_start = contig_start.data();
+  img.contig_len = contig_len.data(); img.n_blocks = n_blocks; img.planes = planes.data(); img.nmask = nmask.data();
+  return img;
+}
+
+bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int threads, std::string* err)
+{
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { *err = "cannot open " + path + " for reading"; return false; }
+  std::map<uint32_t, std::string> seqs;          // id -> bases (no line breaks)
+  std::vector<char> buf(1 << 22);
+  std::string name, seq, header; bool in_header = false, have_record = false, at_line_start = true;
+  auto flush = [&]() {
+    if (!have_record) return;
+    if (log && !name.empty()) fprintf(stderr, "\tLoading %s...", name.c_str());
+    if (log && !seq.empty()) fprintf(stderr, " done (%ld bases).\n", (long)seq.size());
+    const uint32_t id = rt.get_id(name);
+    seqs[id].swap(seq); seq.clear();
+  };
+  size_t n;
+  while ((n = fread(buf.data(), 1, buf.size(), f)) > 0) {
+    size_t i = 0;
+    while (i < n) {
+      if (in_header) {
+        const char* nl = (const char*)memchr(buf.data() + i, '\n', n - i);
+        const size_t e = nl ? (size_t)(nl - buf.data()) : n;
+        header.append(buf.data() + i, e - i);
+        i = e;
+        if (nl) { in_header = false; at_line_start = true; ++i;
+          size_t cut = header.find_first_of(" \t\r"); name = cut == std::string::npos ? header : header.substr(0, cut); header.clear(); }
+        continue;
+      }
+      if (at_line_start && buf[i] == '>') { flush(); have_record = true; in_header = true; ++i; continue; }
+      if (!have_record) { have_record = true; name.clear(); }     // sequence before any header: empty name
+      const char* nl = (const char*)memchr(buf.data() + i, '\n', n - i);
+      const size_t e = nl ? (size_t)(nl - buf.data()) : n;
+      size_t e2 = e; if (e2 > i && buf[e2 - 1] == '\r') --e2;
+      // strip any embedded CR (rare); everything else is a base
+      for (size_t k = i; k < e2; ++k) if (buf[k] == '\r') { seq.append(buf.data() + i, k - i); i = k + 1; }
+      if (e2 > i) seq.append(buf.data() + i, e2 - i);
+      i = e; at_line_start = false;
+      if (nl) { at_line_start = true; ++i; }
+    }
+  }
+  fclose(f);
+  if (in_header) { size_t cut = header.find_first_of(" \t\r"); name = cut == std::string::npos ? header : header.substr(0, cut); }
+  flush();
+  const uint32_t nc = rt.size();
+  g.contig_start.assign(nc, 0); g.contig_len.assign(nc, 0);
+  uint64_t gpos = 0;
+  for (uint32_t id = 1; id <= nc; ++id) {
+    auto it = seqs.find(id);
+    const uint64_t len = it == seqs.end() ? 0 : it->second.size();
+    if (len > 0xffffffffull) { *err = "contig longer than 2^32 bases"; return false; }
+    g.contig_start[id - 1] = gpos; g.contig_len[id - 1] = (uint32_t)len;
+    gpos += ((len + 63) / 64 + 1) * 64;
+  }
+  g.n_blocks = gpos / 64 + 1;
+  g.planes.assign(2 * g.n_blocks, 0); g.nmask.assign(g.n_blocks, 0);
+  // pack 64-aligned slices in parallel (slices never share a plane word)
+  struct Job { uint32_t id; uint64_t off, len; };
+  std::vector<Job> jobs; const uint64_t SL = 1ull << 22;
+  for (auto& kv : seqs) for (uint64_t o = 0; o < kv.second.size(); o += SL) jobs.push_back({kv.first, o, std::min<uint64_t>(SL, kv.second.size() - o)});
+  std::atomic<size_t> nexti(0);
+  auto work = [&]() { for (;;) { size_t j = nexti.fetch_add(1); if (j >= jobs.size()) break; const Job& jb = jobs[j];
+      thb_pack_bases(seqs[jb.id].data() + jb.off, jb.len, g.contig_start[jb.id - 1] + jb.off, g.planes.data(), g.nmask.data()); } };
+  std::vector<std::thread> th; const int nt = std::max(1, std::min<int>(threads, (int)jobs.size()));
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work(); for (auto& t : th) t.join();
+  return true;
+}
+
+// ---- HitStream ------------------------------------------------------------------------------------------
+HitStream::HitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, int max_report_intron)
+  : path_(path), rt_(rt), rt_mutex_(rt_mutex), max_report_intron_(max_report_intron), q_(4)
+{
+  th_ = std::thread([this] { produce(); });
+}
+HitStream::~HitStream() { q_.stop(); if (th_.joinable()) th_.join(); }
+
+void HitStream::produce()
+{
+  BamReader br;
+  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  std::vector<uint32_t> tid2ref(br.header().target_name.size(), 0);
+  { std::lock_guard<std::mutex> l(rt_mutex_);
+    for (size_t i = 0; i < tid2ref.size(); ++i) tid2ref[i] = rt_.get_id(br.header().target_name[i]); }
+  uint32_t star_id = 0;
+  const size_t CH = 1 << 16;
+  std::vector<HitRec> chunk; chunk.reserve(CH);
+  BamRecord r;
+  while (br.next(r)) {
+    // qname "<id>|<offset>:<seg>:<nsegs>" (bwt_map.cpp:1126-1143)
+    bool end = true;
+    const char* pipe = strrchr(r.qname, '|');
+    if (pipe && strchr(pipe + 1, ':')) {
+      unsigned so = 0, sn = 0, ns = 0;
+      sscanf(pipe + 1, "%u:%u:%u", &so, &sn, &ns);
+      end = (sn + 1 == ns);
+    }
+    HitRec hr; memset(&hr, 0, sizeof hr);
+    hr.id = (uint32_t)atoi(r.qname);          // atoi stops at '|' (ReadTable::get_id, bwt_map.h:546-552)
+    if (r.tid < 0) {                          // unmapped record -> hit on "*" (1145-1156)
+      if (!star_id) { std::lock_guard<std::mutex> l(rt_mutex_); star_id = rt_.get_id("*"); }
+      hr.h.ref_id = star_id; hr.h.flags = end ? THB_HIT_END : 0;
+      chunk.push_back(hr);
+    } else {
+      if (r.aux_str("XF")) continue;          // fusion-pass records never reach this stage's inputs
+      int64_t nm = 0; r.aux_int("NM", &nm);
+      unsigned char mism = (unsigned char)nm; // the reference keeps it in an unsigned char (1182-1188)
+      int64_t right = r.pos; unsigned rlen = 0, gaps = 0; bool bad = false;
+      for (int i = 0; i < r.n_cigar && !bad; ++i) {
+        const uint32_t c = r.cigar_at(i); const int len = (int)(c >> 4); const int op = (int)(c & 15);
+        if (len <= 0) { bad = true; break; }
+        switch (op) {
+          case 0: right += len; rlen += len; break;                          // M
+          case 1: rlen += len; gaps += len; mism -= (unsigned char)len; break; // I
+          case 2: right += len; gaps += len; mism -= (unsigned char)len; break; // D
+          case 3: if (len > max_report_intron_) bad = true; right += len; break; // N
+          case 4: rlen += len; break;                                        // S
+          case 5: case 6: break;                                             // H, P
+          default: bad = true;                                               // invalid CIGAR operation
+        }
+      }
+      if (bad) continue;
+      if (r.mtid >= 0 && r.mtid != r.tid) continue;                          // 1409-1416
+      hr.h.ref_id = (size_t)r.tid < tid2ref.size() ? tid2ref[r.tid] : 0;
+      hr.h.left = r.pos; hr.h.right = (int32_t)right; hr.h.read_len = (uint8_t)std::min(rlen, 255u);
+      hr.h.edit_dist = (uint8_t)(mism + gaps);
+      hr.h.flags = (uint8_t)(((r.flag & 0x10) ? THB_HIT_ANTISENSE : 0) | (end ? THB_HIT_END : 0));
+      chunk.push_back(hr);
+    }
+    if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<HitRec>(); chunk.reserve(CH); }
+  }
+  if (!br.error().empty()) err_ = br.error();
+  if (!chunk.empty()) q_.push(std::move(chunk));
+  q_.finish();
+}
+
+bool HitStream::ensure()
+{
+  while (pos_ >= cur_.size()) {
+    if (end_) return false;
+    cur_.clear(); pos_ = 0;
+    if (!q_.pop(cur_)) { end_ = true; return false; }
+  }
+  return true;
+}
+
+uint32_t HitStream::next_group_id()
+{
+  // records with id 0 terminate grouping in the reference (insert_id 0 == "no hit"); skip them
+  while (ensure()) { if (cur_[pos_].id != 0) return cur_[pos_].id; ++pos_; }
+  return 0;
+}
+void HitStream::next_group(std::vector<thb_hit>& out)
+{
+  const uint32_t id = next_group_id();
+  if (!id) return;
+  while (ensure() && cur_[pos_].id == id) { out.push_back(cur_[pos_].h); ++pos_; ++n_records_; }
+}
+void HitStream::skip_group()
+{
+  const uint32_t id = next_group_id();
+  if (!id) return;
+  while (ensure() && cur_[pos_].id == id) { ++pos_; ++n_records_; }
+}
+
+// ---- ReadStream -----------------------------------------------------------------------------------------
+void pack_read_ascii(const char* s, uint32_t len, ReadRec& r)
+{
+  memset(r.planes, 0, sizeof r.planes);
+  r.len = len;
+  for (uint32_t i = 0; i < len && i < 256; ++i) {
+    unsigned c; bool isn = false;
+    switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 0; isn = true; }
+    const uint32_t w = i >> 6, j = i & 63;
+    if (c & 1) r.planes[w] |= 1ull << j;
+    if (c & 2) r.planes[4 + w] |= 1ull << j;
+    if (isn) r.planes[8 + w] |= 1ull << j;
+  }
+}
+
+ReadStream::ReadStream(const std::string& path) : path_(path), q_(4)
+{
+  const bool bam = path.size() >= 4 && path.compare(path.size() - 4, 4, ".bam") == 0;
+  th_ = std::thread([this, bam] { if (bam) produce_bam(); else produce_fastx(); });
+}
+ReadStream::~ReadStream() { q_.stop(); if (th_.joinable()) th_.join(); }
+
+void ReadStream::produce_bam()
+{
+  BamReader br;
+  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  // 4-bit BAM base codes "=ACMGRSVTWYHKDBN": A=1 C=2 G=4 T=8, everything else is treated as N
+  static const int8_t code[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};
+  const size_t CH = 1 << 15;
+  std::vector<ReadRec> chunk; chunk.reserve(CH);
+  BamRecord r;
+  while (br.next(r)) {
+    if (r.flag & 0x200) continue;                    // BAM_FQCFAIL reads are skipped (reads.cpp:552)
+    ReadRec rr; memset(&rr, 0, sizeof rr);
+    rr.id = (uint32_t)atol(r.qname);
+    if (r.l_seq > 255) { err_ = path_ + ": read longer than 255 bases"; break; }
+    rr.len = (uint32_t)r.l_seq;
+    for (int i = 0; i < r.l_seq; ++i) {
+      const int v = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 15; const int c = code[v];
+      const int w = i >> 6, j = i & 63;
+      if (c < 0) rr.planes[8 + w] |= 1ull << j;
+      else { if (c & 1) rr.planes[w] |= 1ull << j; if (c & 2) rr.planes[4 + w] |= 1ull << j; }
+    }
+    chunk.push_back(rr);
+    if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<ReadRec>(); chunk.reserve(CH); }
+  }
+  if (!br.error().empty() && err_.empty()) err_ = br.error();
+  if (!chunk.empty()) q_.push(std::move(chunk));
+  q_.finish();
+}
+
+void ReadStream::produce_fastx()
+{
+  gzFile f = gzopen(path_.c_str(), "rb");
+  if (!f) { err_ = "cannot open " + path_ + " for reading"; q_.finish(); return; }
+  gzbuffer(f, 1 << 20);
+  const size_t CH = 1 << 15;
+  std::vector<ReadRec> chunk; chunk.reserve(CH);
+  std::vector<char> line(1 << 16);
+  auto getl = [&](std::string& s) -> bool { s.clear(); if (!gzgets(f, line.data(), (int)line.size())) return false; s = line.data();
+    while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); return true; };
+  std::string l, seq, plus, qual;
+  while (getl(l)) {
+    if (l.empty()) continue;
+    const bool fq = l[0] == '@';
+    if (!fq && l[0] != '>') continue;
+    if (!getl(seq)) break;
+    if (fq) { getl(plus); getl(qual); }
+    ReadRec rr; rr.id = (uint32_t)atol(l.c_str() + 1);
+    if (seq.size() > 255) { err_ = path_ + ": read longer than 255 bases"; break; }
+    for (char& c : seq) c = (char)toupper((unsigned char)c);
+    pack_read_ascii(seq.data(), (uint32_t)seq.size(), rr);
+    chunk.push_back(rr);
+    if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<ReadRec>(); chunk.reserve(CH); }
+  }
+  gzclose(f);
+  if (!chunk.empty()) q_.push(std::move(chunk));
+  q_.finish();
+}
+
+bool ReadStream::ensure()
+{
+  while (pos_ >= cur_.size()) {
+    if (end_) return false;
+    cur_.clear(); pos_ = 0;
+    if (!q_.pop(cur_)) { end_ = true; return false; }
+  }
+  return true;
+}
+
+const ReadRec* ReadStream::get(uint32_t id)
+{
+  while (ensure()) {
+    const ReadRec& r = cur_[pos_];
+    if (r.id == id) return &r;             // not consumed: the same read may be requested again
+    if (r.id > id) return nullptr;
+    ++pos_;
+  }
+  return nullptr;
+}
+
+}  // namespace thbhost
