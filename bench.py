@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 import numpy as np
 
 CHR20 = 64_444_167
+KERNELS = ("bundle", "hit", "rescue", "rescued_windows", "window_scan", "indel")
 METRIC = "spliced reads processed/s (segment_juncs junction+indel discovery), 2x101bp"
 UNIT = "reads/s"
 
@@ -277,11 +278,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scan_ms, alg, launches = 0.0, 0, 0
+        kms = {k: 0.0 for k in KERNELS}
         e0.record(stream)
         for _ in range(steps):
             res, tm = step(device_resident)
             scan_ms += tm.scan_kernel_ms; alg += tm.algorithmic_bytes; launches += tm.total_launches
             scan_launches = tm.kernel_launches
+            for k in KERNELS:
+                kms[k] += getattr(tm, k + "_ms")
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -291,13 +295,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, scan_ms, alg, launches, scan_launches, res, tm
+        return ms, scan_ms, alg, launches, scan_launches, res, tm, kms
 
     clk = ClockSampler(local_rank)
     if rank == 0:
         clk.start()
-    ms, scan_ms, alg, launches, scan_launches, res, tm = timed(True, args.steps, args.warmup)
-    ms_e2e, _, _, _, _, res_h, _ = timed(False, args.steps, args.warmup)
+    ms, scan_ms, alg, launches, scan_launches, res, tm, kms = timed(True, args.steps, args.warmup)
+    ms_e2e, _, _, _, _, res_h, _, _ = timed(False, args.steps, args.warmup)
     clocks = clk.stop() if rank == 0 else None
     d2h_bytes = int(res_h.junctions.nbytes + res_h.deletions.nbytes + res_h.insertions.nbytes + res_h.fusions.nbytes)
 
@@ -317,13 +321,29 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             peaks, peak_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-        scan_per_launch_ms = scan_ms / max(1, args.steps * scan_launches)
-        achieved = (alg / max(1, args.steps * scan_launches)) / (scan_per_launch_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        # Per-kernel split of SURVEY.md 8(d)'s B_segjuncs, on this run's actual task counts:
+        #   bundle      : 16 (bundle header) per bundle + 16 per partner hit
+        #   hit         : 40 (read) per bundle + 16 per segment hit
+        #   window_scan : 32 (descriptor) + 64 (two reference sectors) per window + 16 per emitted junction record
+        #   rescue      : 32 + 128 per mate-anchor task;  indel: 32 + 64 per task + 16 per record
+        n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
+        n_hh = sum(int(b.hits.shape[0]) for b in batches)
+        kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh, "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted),
+                  "rescue": 160 * int(tm.n_rescue_tasks), "rescued_windows": 0,
+                  "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions))}
+        dom = max(KERNELS, key=lambda k: kms[k])
+        n_launch = max(1, args.steps * scan_launches)
+        dom_ms = kms[dom] / n_launch
+        dom_bytes = kbytes[dom] / max(1, scan_launches)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        phase_ms = scan_ms / n_launch
+        phase_bytes = alg / n_launch
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("segjuncs_kernel_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = next((v for k, v in tj.items() if k.startswith(dom + "_kernel")), None)
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -332,10 +352,17 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps, "api": "thb_segjuncs_begin/submit(host, pinned)/finish"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "segjuncs_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
                              "frac": achieved / peaks, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg / max(1, args.steps * scan_launches),
-                             "kernel_ms_per_launch": scan_per_launch_ms, "launches_per_step": scan_launches},
+                             "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
+                             "launches_per_step": scan_launches,
+                             "per_kernel_ms_per_launch": {k: kms[k] / n_launch for k in KERNELS},
+                             "per_kernel_gbs": {k: (kbytes[k] / max(1, scan_launches)) / (kms[k] / n_launch * 1e-3) / 1e9 if kms[k] > 0 else 0.0
+                                                for k in KERNELS},
+                             "phase": {"kernels": "bundle+hit+rescue+rescued_windows+window_scan+indel", "ms_per_launch": phase_ms,
+                                       "algorithmic_bytes_per_launch": phase_bytes,
+                                       "achieved": phase_bytes / (phase_ms * 1e-3) / 1e9 if phase_ms > 0 else 0.0,
+                                       "frac": (phase_bytes / (phase_ms * 1e-3) / 1e9 / peaks) if phase_ms > 0 else 0.0}},
                 "clocks": clocks,
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),

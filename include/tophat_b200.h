@@ -209,9 +209,73 @@ int thb_nccl_unique_id(void* out128);
 int thb_comm_init(thb_ctx* ctx, const void* nccl_unique_id128, int rank, int world);
 int thb_segjuncs_allgather(thb_ctx* ctx);
 
+/* ---- long_spanning_reads: segment-chain join -----------------------------------------------------------
+ * One thb_join_bundle = one call of join_segments_for_read (long_spanning_reads.cpp:2612-2667): the read plus,
+ * per segment, the hit group JoinSegmentsWorker assembled for it (contiguous hits from the segment BAM followed
+ * by the hits against juncs_db contigs converted to genomic coordinates, 2706-2765 / 87-163).  The host keeps
+ * the worker's stream rules (every segment must have a hit, the last one must carry the end flag, 2768-2785);
+ * the kernel runs the chain DFS (2222-2610), merge_chain (805-2038) and the edit-distance consistency check
+ * (bwt_map.cpp:2349-2465) and returns every valid merged alignment.  Sorting / de-duplicating a read's
+ * alignments (2805-2807), the read-level filters (2810-2813) and the SAM fields are the caller's.              */
+#define THB_JHIT_MAX_OPS    9
+#define THB_JOINED_MAX_OPS  27
+#define THB_JHIT_ANTISENSE_SPLICE 0x04    /* antisense_splice() (with THB_HIT_ANTISENSE / THB_HIT_END)        */
+/* CIGAR ops are packed as length << 4 | CigarOpCode (bwt_map.h:36-55: MATCH 1, INS 3, DEL 5, REF_SKIP 11,
+ * SOFT_CLIP 13, PAD 15; lower-case fusion-side codes never occur without --fusion-search).                    */
+typedef struct thb_jhit {          /* BowtieHit of one segment (BAMHitFactory / SplicedBAMHitFactory)           */
+  uint32_t ref_id;
+  int32_t  left;
+  uint8_t  n_ops, flags, mismatches, splice_mms;
+  uint32_t ops[THB_JHIT_MAX_OPS];
+} thb_jhit;                        /* 48 bytes */
+
+typedef struct thb_join_bundle {
+  uint32_t read_id;
+  uint32_t hit_begin;              /* first hit of segment 0; segments follow in order                         */
+  uint16_t read_len;
+  uint8_t  n_segs;                 /* segments of THIS read (all non-empty)                                    */
+  uint8_t  reserved;
+  uint32_t reserved2;
+} thb_join_bundle;                 /* 16 bytes */
+
+typedef struct thb_join_batch {
+  uint32_t               n_bundles;
+  uint32_t               n_segs;       /* row stride of seg_count (maximum segments per read)                  */
+  uint32_t               read_words;
+  uint32_t               reserved;
+  const thb_join_bundle* bundles;
+  const uint16_t*        seg_count;    /* [n_bundles * n_segs]                                                  */
+  const uint64_t*        reads;        /* [n_bundles * 3 * read_words], as in thb_segjuncs_batch                */
+  uint64_t               n_hits;
+  const thb_jhit*        hits;
+} thb_join_batch;
+
+typedef struct thb_joined {        /* the BowtieHit merge_chain returns                                         */
+  uint32_t bundle;                 /* index of the read in the submitted batch                                  */
+  uint32_t ref_id;
+  int32_t  left;
+  uint8_t  n_ops, flags, mismatches, edit_dist;
+  uint8_t  splice_mms, reserved8[3];
+  uint32_t ops[THB_JOINED_MAX_OPS];
+} thb_joined;                      /* 128 bytes */
+
+/* Uploads the junction set (junction files + deletions as Junction(ref, left - 1, right), 2895-2944) and the
+ * insertion set (2952-2980).  Arrays must be sorted and unique in the reference's set orders.                */
+int thb_join_begin(thb_ctx* ctx, const thb_params* params, const thb_junction* juncs, uint64_t n_juncs,
+                   const thb_insertion* insertions, uint64_t n_insertions);
+/* Joins one batch (host arrays); *out / *n_out receive the merged alignments of this batch, grouped by nothing
+ * in particular (use .bundle), owned by ctx and valid until the next join call.                              */
+int thb_join_submit(thb_ctx* ctx, const thb_join_batch* host_batch, const thb_joined** out, uint64_t* n_out);
+typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; uint32_t launches; uint32_t reserved;
+                                 uint64_t n_chains, n_closures, n_joined, algorithmic_bytes; } thb_join_timing;
+int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out);
+
 /* Kernel timing of the last submit (CUDA events on the context's stream), milliseconds.        */
 typedef struct thb_timing {
-  float h2d_ms; float scan_kernel_ms; float finish_ms; float total_ms;
+  float h2d_ms;
+  float scan_kernel_ms;         /* sum of the five scan-phase kernels below                              */
+  float finish_ms; float total_ms;
+  float bundle_ms, hit_ms, rescue_ms, rescued_windows_ms, window_scan_ms, indel_ms;   /* per kernel, CUDA events */
   uint64_t n_windows; uint64_t n_indel_tasks; uint64_t n_rescue_tasks; uint64_t n_juncs_emitted;
   uint64_t algorithmic_bytes;
   uint32_t kernel_launches;   /* launches of the scan kernel                                       */

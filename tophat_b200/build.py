@@ -59,7 +59,7 @@ def build_host_binaries(force: bool = False) -> list:
             continue
         exe = os.path.join(BIN_DIR, prog)
         if force or _newer(exe, _csrc_files() + [LIB]):
-            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unused-function", "-I", os.path.join(ROOT, "include"), "-I", host,
+            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unused-function", "-Wno-misleading-indentation", "-I", os.path.join(ROOT, "include"), "-I", host,
                    "-o", exe, main] + common + ["-L", HERE, "-ltophat_b200", "-Wl,-rpath,$ORIGIN/..", "-lz", "-lpthread"]
             subprocess.run(cmd, check=True)
         outs.append(exe)

@@ -71,7 +71,8 @@ class ResultsC(C.Structure):
 
 class TimingC(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("scan_kernel_ms", C.c_float), ("finish_ms", C.c_float),
-                ("total_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
+                ("total_ms", C.c_float), ("bundle_ms", C.c_float), ("hit_ms", C.c_float), ("rescue_ms", C.c_float),
+                ("rescued_windows_ms", C.c_float), ("window_scan_ms", C.c_float), ("indel_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
                 ("n_rescue_tasks", C.c_uint64), ("n_juncs_emitted", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("total_launches", C.c_uint32)]
 

@@ -1,0 +1,297 @@
+// long_spanning_reads -- drop-in replacement of the reference stage binary (src/long_spanning_reads.cpp main/driver,
+// 2870-3329): same argv, same inputs, BAM output with the same records.  The host merges the id-sorted segment
+// streams the way JoinSegmentsWorker does (2706-2785, look_right_for_hit_group 87-163), packs per-read bundles, runs
+// the chain join on the GPU through libtophat_b200.so, and then does what is left of the worker loop: sort + unique
+// of a read's alignments (2805-2807), the read-level filters (2810-2813), bowtie_sam_extra (bwt_map.cpp:2467-2648) and
+// print_bamhit (1888-2093).  There is no CPU fallback for the join itself.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+#include "tophat_b200.h"
+#include "thb_options.hpp"
+#include "thb_input.hpp"
+#include "thb_join_input.hpp"
+#include "thb_bamwrite.hpp"
+
+using namespace thbhost;
+
+static void print_usage()
+{
+  fprintf(stderr, "Usage:   long_spanning_reads <reads.fa/.fq> <possible_juncs1,...,possible_juncsN> <possible_insertions1,...,possible_insertionsN> "
+                  "<possible_deletions1,...,possible_deletionsN> <seg1.bwtout,...,segN.bwtout> [spliced_seg1.bwtout,...,spliced_segN.bwtout]\n");
+}
+[[noreturn]] static void die(const char* fmt, const std::string& a = "") { fprintf(stderr, fmt, a.c_str()); fputc('\n', stderr); exit(1); }
+
+// CigarOpCode (bwt_map.h:36-55) -> BAM op code / SAM letter
+static int bam_op(int code) { switch (code) { case 1: return 0; case 3: return 1; case 5: return 2; case 11: return 3; case 13: return 4; case 14: return 5; case 15: return 6; default: return 0; } }
+
+struct Joined {
+  uint32_t ref_id; int32_t left; bool anti, asplice; uint8_t mism, edit, smm; std::vector<uint32_t> ops;   // ops: len << 4 | CigarOpCode
+};
+// BowtieHit::operator< (bwt_map.h:180-207) within one read
+static bool joined_less(const Joined& a, const Joined& b)
+{
+  if (a.ref_id != b.ref_id) return a.ref_id < b.ref_id;
+  if (a.left != b.left) return a.left < b.left;
+  if (a.anti != b.anti) return a.anti < b.anti;
+  if (a.mism != b.mism) return a.mism < b.mism;
+  if (a.edit != b.edit) return a.edit < b.edit;
+  if (a.ops != b.ops) {
+    if (a.ops.size() != b.ops.size()) return a.ops.size() < b.ops.size();
+    for (size_t i = 0; i < a.ops.size(); ++i) if (a.ops[i] != b.ops[i]) {
+      const uint32_t ac = a.ops[i] & 15, bc = b.ops[i] & 15;
+      return ac < bc || (ac == bc && (a.ops[i] >> 4) < (b.ops[i] >> 4));
+    }
+  }
+  return false;
+}
+// BowtieHit::operator== (167-178)
+static bool joined_equal(const Joined& a, const Joined& b)
+{ return a.ref_id == b.ref_id && a.anti == b.anti && a.left == b.left && a.asplice == b.asplice && a.edit == b.edit && a.ops == b.ops; }
+
+struct GenomeView {
+  const Genome* g;
+  char base(uint32_t ref_id, int64_t pos) const {      // Dna5 character
+    const uint64_t gl = g->contig_start[ref_id - 1] + (uint64_t)pos; const uint64_t b = gl >> 6; const unsigned j = (unsigned)(gl & 63);
+    if ((g->nmask[b] >> j) & 1) return 'N';
+    return "ACGT"[((g->planes[2 * b] >> j) & 1) | (((g->planes[2 * b + 1] >> j) & 1) << 1)];
+  }
+};
+
+static void reverse_complement(std::string& s)
+{
+  std::reverse(s.begin(), s.end());
+  for (char& c : s) switch (c) { case 'A': c = 'T'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; case 'T': c = 'A'; break; default: c = 'N'; }
+}
+
+int main(int argc, char** argv)
+{
+  fprintf(stderr, "long_spanning_reads v%s (%s)\n", "2.1.2", "tophat_b200");
+  fprintf(stderr, "--------------------------------------------\n");
+  Options o;
+  if (parse_options(argc, argv, o, print_usage)) return 1;
+  const std::vector<std::string>& a = o.positional;
+  if (a.size() < 8) { print_usage(); return 1; }
+  const std::string ref_fname = a[0], reads_fname = a[1];
+  const std::vector<std::string> juncs_files = split_list(a[2]), ins_files = split_list(a[3]), del_files = split_list(a[4]);
+  const std::string bam_out = a[6];
+  const std::vector<std::string> seg_files = split_list(a[7]);
+  std::vector<std::string> spl_files; if (a.size() >= 9) spl_files = split_list(a[8]);
+  if (seg_files.empty()) { fprintf(stderr, "No hits to process, exiting\n"); return 0; }          // 2883-2887
+  if (o.color) die("Error: colorspace reads are outside the GPU path");
+  if (o.p.fusion_search) die("Error: --fusion-search is not implemented on the GPU join path yet");
+  if (seg_files.size() > 12) die("Error: more than 12 segments per read are not supported by the GPU path");
+
+  thb_ctx* ctx = nullptr;
+  const char* dev_env = getenv("TOPHAT_GPU_DEVICE");
+  if (thb_create(dev_env ? atoi(dev_env) : 0, &ctx) != THB_OK) die("Error: %s", thb_last_error(nullptr));
+  auto t0 = std::chrono::steady_clock::now();
+  RefTable rt; std::string err;
+  if (!o.sam_header.empty() && !rt.load_sam_header(o.sam_header, &err)) die("%s", err);
+  fprintf(stderr, "Loading reference sequences...\n");
+  Genome g;
+  if (!load_fasta(ref_fname, rt, g, false, 8, &err)) die("Error: %s", err);
+  fprintf(stderr, "        reference sequences loaded.\n");
+
+  // junctions + deletions -> std::set<Junction>; insertions -> std::set<Insertion> (2895-2980)
+  struct JL { bool operator()(const thb_junction& x, const thb_junction& y) const {
+    if (x.ref_id != y.ref_id) return x.ref_id < y.ref_id; if (x.left != y.left) return x.left < y.left;
+    if (x.right != y.right) return x.right < y.right; return x.antisense < y.antisense; } };
+  struct IL { bool operator()(const thb_insertion& x, const thb_insertion& y) const {
+    if (x.ref_id != y.ref_id) return x.ref_id < y.ref_id; if (x.left != y.left) return x.left < y.left; return x.len < y.len; } };
+  std::set<thb_junction, JL> jset; std::set<thb_insertion, IL> iset;
+  fprintf(stderr, "Loading junctions...");
+  for (const std::string& f : juncs_files) {
+    FILE* fp = fopen(f.c_str(), "r"); if (!fp) die("Error: cannot open %s for reading", f);
+    char buf[2048];
+    while (fgets(buf, sizeof buf, fp)) { char name[256]; int l, r; char orient;
+      if (sscanf(buf, "%255s %d %d %c", name, &l, &r, &orient) != 4) continue;
+      thb_junction j; j.ref_id = rt.get_id(name); j.left = (uint32_t)l; j.right = (uint32_t)r; j.antisense = orient == '-'; jset.insert(j); }
+    fclose(fp);
+  }
+  fprintf(stderr, "done\nLoading deletions...");
+  for (const std::string& f : del_files) {
+    FILE* fp = fopen(f.c_str(), "r"); if (!fp) continue;
+    char buf[2048];
+    while (fgets(buf, sizeof buf, fp)) { char* nl = strrchr(buf, '\n'); if (nl) *nl = 0;
+      char* t1 = strchr(buf, '\t'); if (!t1) die("Error: malformed deletion coordinate record"); *t1++ = 0;
+      char* t2 = strchr(t1, '\t'); if (!t2) die("Error: malformed deletion coordinate record"); *t2++ = 0;
+      char* t3 = strchr(t2, '\t'); if (t3) *t3 = 0;
+      thb_junction j; j.ref_id = rt.get_id(buf); j.left = (uint32_t)atoi(t1) - 1u; j.right = (uint32_t)atoi(t2); j.antisense = 0; jset.insert(j); }
+    fclose(fp);
+  }
+  fprintf(stderr, "done\nLoading insertions...");
+  for (const std::string& f : ins_files) {
+    FILE* fp = fopen(f.c_str(), "r"); if (!fp) continue;
+    char buf[2048];
+    while (fgets(buf, sizeof buf, fp)) { char* nl = strrchr(buf, '\n'); if (nl) *nl = 0;
+      char* t1 = strchr(buf, '\t'); if (!t1) die("Error: malformed insertion coordinate record"); *t1++ = 0;
+      char* t2 = strchr(t1, '\t'); if (!t2) die("Error: malformed insertion coordinate record"); *t2++ = 0;
+      char* t3 = strchr(t2, '\t'); if (!t3) die("Error: malformed insertion coordinate record"); *t3++ = 0;
+      char* t4 = strchr(t3, '\t'); if (t4) *t4 = 0;
+      thb_insertion in; memset(&in, 0, sizeof in); in.ref_id = rt.get_id(buf); in.left = (uint32_t)atoi(t1); in.len = (uint32_t)strlen(t3);
+      if (in.len > 19) die("Error: insertion longer than 19 bases is not supported by the GPU path");
+      memcpy(in.seq, t3, in.len); iset.insert(in); }
+    fclose(fp);
+  }
+  fprintf(stderr, "done\n");
+  // contigs named only by the junction files must exist in the genome image before it is uploaded
+  if (g.contig_len.size() < rt.size()) {
+    Genome g2 = g; const size_t old = g.contig_len.size(); uint64_t gpos = (g.n_blocks ? (g.n_blocks - 1) * 64 : 0);
+    for (size_t i = old; i < rt.size(); ++i) { g2.contig_start.push_back(gpos); g2.contig_len.push_back(0); gpos += 64; }
+    g2.n_blocks = gpos / 64 + 1; g2.planes.resize(2 * g2.n_blocks, 0); g2.nmask.resize(g2.n_blocks, 0); g = g2;
+  }
+  std::vector<thb_junction> jv(jset.begin(), jset.end()); std::vector<thb_insertion> iv(iset.begin(), iset.end());
+
+  std::mutex rtm;
+  std::vector<std::unique_ptr<JoinHitStream>> contig, spliced;
+  for (auto& f : seg_files) contig.emplace_back(new JoinHitStream(f, rt, rtm, false, o.p.max_report_intron_length, o.p.min_anchor_len));
+  for (auto& f : spl_files) spliced.emplace_back(new JoinHitStream(f, rt, rtm, true, o.p.max_report_intron_length, o.p.min_anchor_len));
+  FullReadStream reads(reads_fname);
+  // spliced streams may name contigs unknown so far: make sure every id has a (possibly empty) slot before upload
+  // (ids created later belong to sequence-less contigs and can never pass the consistency check)
+  { thb_ref_image img = g.image(); if (thb_ref_upload(ctx, &img) != THB_OK) die("Error: thb_ref_upload: %s", thb_last_error(ctx)); }
+  if (thb_join_begin(ctx, &o.p, jv.data(), jv.size(), iv.data(), iv.size()) != THB_OK) die("Error: thb_join_begin: %s", thb_last_error(ctx));
+  auto t1 = std::chrono::steady_clock::now();
+
+  BamWriter bw;
+  if (!bw.open(bam_out, o.sam_header, bam_out + ".index", &err)) die("Error: %s", err);
+  std::vector<int> ref2tid;
+  const GenomeView gv{&g};
+  const size_t nseg = seg_files.size();
+
+  struct Pending { uint32_t id; FullRead read; };
+  std::vector<thb_join_bundle> bundles; std::vector<uint16_t> segc; std::vector<uint64_t> rplanes; std::vector<thb_jhit> hits; std::vector<Pending> pend;
+  uint64_t n_reads = 0, n_out = 0;
+  auto flush = [&]() {
+    if (bundles.empty()) return;
+    // reads of one batch share read_words = 4 (reads up to 255 bases)
+    thb_join_batch jb; memset(&jb, 0, sizeof jb);
+    jb.n_bundles = (uint32_t)bundles.size(); jb.n_segs = (uint32_t)nseg; jb.read_words = 4; jb.bundles = bundles.data(); jb.seg_count = segc.data();
+    jb.reads = rplanes.data(); jb.n_hits = hits.size(); jb.hits = hits.data();
+    const thb_joined* out = nullptr; uint64_t no = 0;
+    if (thb_join_submit(ctx, &jb, &out, &no) != THB_OK) die("Error: thb_join_submit: %s", thb_last_error(ctx));
+    std::vector<std::vector<Joined>> per(bundles.size());
+    for (uint64_t i = 0; i < no; ++i) {
+      const thb_joined& j = out[i]; Joined J; J.ref_id = j.ref_id; J.left = j.left; J.anti = (j.flags & THB_HIT_ANTISENSE) != 0;
+      J.asplice = (j.flags & THB_JHIT_ANTISENSE_SPLICE) != 0; J.mism = j.mismatches; J.edit = j.edit_dist; J.smm = j.splice_mms;
+      J.ops.assign(j.ops, j.ops + j.n_ops); per[j.bundle].push_back(std::move(J));
+    }
+    std::vector<uint8_t> aux; std::vector<uint32_t> bcig; std::string MD;
+    for (size_t b = 0; b < bundles.size(); ++b) {
+      std::vector<Joined>& v = per[b];
+      std::sort(v.begin(), v.end(), joined_less);
+      v.erase(std::unique(v.begin(), v.end(), joined_equal), v.end());
+      const FullRead& rd = pend[b].read;
+      for (const Joined& J : v) {
+        int gap = 0, rlen = 0; bool has_splice = false;
+        for (uint32_t op : J.ops) { const int c = (int)(op & 15), l = (int)(op >> 4); if (c == 3 || c == 5) gap += l; if (c == 1 || c == 3 || c == 13) rlen += l; if (c == 11) has_splice = true; }
+        if ((int)J.mism > o.p.read_mismatches || gap > o.p.read_gap_length || (int)J.edit > o.p.read_edit_dist) continue;   // 2810-2813
+        // the hit's own sequence / qualities (merge_chain 1959-1979): forward-genome orientation
+        std::string hseq = rd.seq, hqual = rd.qual;
+        if (J.anti) { reverse_complement(hseq); std::reverse(hqual.begin(), hqual.end()); }
+        // bowtie_sam_extra (bwt_map.cpp:2467-2648)
+        aux.clear(); MD.clear();
+        if (J.ref_id >= 1 && J.ref_id <= g.contig_len.size() && g.contig_len[J.ref_id - 1] > 0) {
+          long pos_ref = J.left; size_t pos_seq = 0; int pos_mm = 0, mm = 0, gap_opens = 0, gap_conts = 0, AS = 0;
+          for (uint32_t op : J.ops) {
+            const int c = (int)(op & 15), l = (int)(op >> 4);
+            if (c == 1) {
+              for (int k = 0; k < l; ++k, ++pos_seq) {
+                const char rn = gv.base(J.ref_id, pos_ref + k); const char sc = pos_seq < hseq.size() ? hseq[pos_seq] : 'N';
+                if (sc != rn) {
+                  ++mm;
+                  if (pos_seq < hqual.size()) {
+                    if (sc == 'N' || rn == 'N') AS -= o.p.bowtie2_penalty_for_N;
+                    else { const float pen = o.p.bowtie2_min_penalty + (o.p.bowtie2_max_penalty - o.p.bowtie2_min_penalty) * std::min((int)(hqual[pos_seq] - '!'), 40) / 40.0f; AS -= (int)pen; }
+                  }
+                  MD += std::to_string(pos_mm); MD.push_back(rn); pos_mm = 0;
+                } else { if (rn == 'N') AS -= o.p.bowtie2_penalty_for_N; ++pos_mm; }
+              }
+              pos_ref += l;
+            } else if (c == 3) { pos_seq += (size_t)l; AS -= o.p.bowtie2_read_gap_open; AS -= o.p.bowtie2_read_gap_cont * l; gap_opens += 1; gap_conts += l; }
+            else if (c == 5) {
+              AS -= o.p.bowtie2_ref_gap_open; AS -= o.p.bowtie2_ref_gap_cont * l; gap_opens += 1; gap_conts += l;
+              MD += std::to_string(pos_mm); MD.push_back('^'); for (int k = 0; k < l; ++k) MD.push_back(gv.base(J.ref_id, pos_ref + k));
+              pos_ref += l; pos_mm = 0;
+            } else if (c == 11) pos_ref += l;
+          }
+          MD += std::to_string(pos_mm);
+          BamWriter::aux_int(aux, "AS", AS); BamWriter::aux_int(aux, "XM", mm); BamWriter::aux_int(aux, "XO", gap_opens);
+          BamWriter::aux_int(aux, "XG", gap_conts); BamWriter::aux_str(aux, "MD", MD);
+        }
+        // print_bamhit (bwt_map.cpp:1888-2093): read sequence cut to the hit's read length, rc for antisense hits
+        std::string seq = rd.seq, quals = rd.qual; seq.resize((size_t)rlen, '\0'); quals.resize((size_t)rlen, '\0');
+        if (J.anti) { reverse_complement(seq); std::reverse(quals.begin(), quals.end()); }
+        BamWriter::aux_int(aux, "NM", (int)J.mism + gap);
+        if (has_splice) BamWriter::aux_char(aux, "XS", J.asplice ? '-' : '+');
+        bcig.clear(); for (uint32_t op : J.ops) bcig.push_back(((op >> 4) << 4) | (uint32_t)bam_op((int)(op & 15)));
+        if (ref2tid.size() < rt.size() + 1) { ref2tid.assign(rt.size() + 1, -2); }
+        int& tid = ref2tid[J.ref_id]; if (tid == -2) tid = bw.target_id(rt.name(J.ref_id));
+        bw.write(rd.name, pend[b].id, J.anti ? 0x10 : 0, tid, J.left, 255, bcig, seq, quals, aux);
+        ++n_out;
+      }
+    }
+    bundles.clear(); segc.clear(); rplanes.clear(); hits.clear(); pend.clear();
+  };
+
+  // JoinSegmentsWorker::operator() (2671-2845)
+  const size_t BATCH = 1u << 20;
+  std::vector<std::vector<thb_jhit>> seg_hits(nseg);
+  for (;;) {
+    const uint32_t cid = contig[0]->next_group_id();
+    const uint32_t sid = spliced.empty() ? 0 : spliced[0]->next_group_id();
+    if (!cid && !sid) break;
+    const uint32_t id = (cid && (!sid || cid <= sid)) ? cid : sid;
+    for (auto& v : seg_hits) v.clear();
+    if (cid == id) contig[0]->next_group(seg_hits[0]);
+    if (sid == id) spliced[0]->next_group(seg_hits[0]);
+    // look_right_for_hit_group (87-163): stop at the first segment without contiguous or spliced hits
+    for (size_t s = 1; s < nseg; ++s) {
+      uint32_t gidc; while ((gidc = contig[s]->next_group_id()) != 0 && gidc < id) contig[s]->skip_group();
+      if (gidc == id) contig[s]->next_group(seg_hits[s]);
+      if (s < spliced.size()) { uint32_t gids; while ((gids = spliced[s]->next_group_id()) != 0 && gids < id) spliced[s]->skip_group();
+                                if (gids == id) spliced[s]->next_group(seg_hits[s]); }
+      if (seg_hits[s].empty()) break;
+    }
+    int last_non_empty = (int)nseg - 1;
+    while (last_non_empty >= 0 && seg_hits[last_non_empty].empty()) --last_non_empty;
+    if (last_non_empty < 0) continue;
+    if (!(seg_hits[last_non_empty][0].flags & THB_HIT_END)) continue;                                    // 2777-2785
+    const FullRead* rd = reads.get(id);
+    if (!rd) { if (!reads.ok()) die("Error: %s", reads.error()); fprintf(stderr, "Error: could not get read # %d from stream\n", (int)id); exit(1); }
+    if (rd->seq.size() > 255) die("Error: reads longer than 255 bases are not supported");
+    thb_join_bundle bu; memset(&bu, 0, sizeof bu);
+    bu.read_id = id; bu.hit_begin = (uint32_t)hits.size(); bu.read_len = (uint16_t)rd->seq.size(); bu.n_segs = (uint8_t)(last_non_empty + 1);
+    for (size_t s = 0; s < nseg; ++s) {
+      const size_t c = (int)s <= last_non_empty ? seg_hits[s].size() : 0;
+      if (c > 65535) die("Error: more than 65535 hits for one segment of one read");
+      segc.push_back((uint16_t)c);
+      if ((int)s <= last_non_empty) hits.insert(hits.end(), seg_hits[s].begin(), seg_hits[s].end());
+    }
+    ReadRec rr; pack_read_ascii(rd->seq.data(), (uint32_t)rd->seq.size(), rr);
+    rplanes.insert(rplanes.end(), rr.planes, rr.planes + 12);
+    bundles.push_back(bu); pend.push_back(Pending{id, *rd}); ++n_reads;
+    if (bundles.size() >= BATCH) flush();
+  }
+  flush();
+  for (auto& h : contig) if (!h->ok()) die("Error: %s", h->error());
+  for (auto& h : spliced) if (!h->ok()) die("Error: %s", h->error());
+  if (!reads.ok()) die("Error: %s", reads.error());
+  if (!bw.close(&err)) die("Error: %s", err);
+  auto t2 = std::chrono::steady_clock::now();
+  if (getenv("TOPHAT_GPU_STATS")) {
+    thb_join_timing tm; thb_join_last_timing(ctx, &tm);
+    auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    fprintf(stderr, "{\"gpu_stats\": {\"reads\": %llu, \"records\": %llu, \"ref_load_s\": %.3f, \"join_s\": %.3f, \"kernel_ms\": %.3f, \"chains\": %llu, \"closures\": %llu}}\n",
+            (unsigned long long)n_reads, (unsigned long long)n_out, sec(t0, t1), sec(t1, t2), tm.kernel_ms, (unsigned long long)tm.n_chains, (unsigned long long)tm.n_closures);
+  }
+  thb_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,147 @@
+#include "thb_bamwrite.hpp"
+#include <zlib.h>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace thbhost {
+
+namespace {
+const size_t BLOCK_DATA = 0xff00;        // uncompressed payload per BGZF block (samtools uses 64 KiB - slack)
+int reg2bin(int beg, int end)
+{
+  --end;
+  if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+  if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+  if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+  if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+  if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+  return 0;
+}
+}  // namespace
+
+BamWriter::~BamWriter() { std::string e; close(&e); }
+
+bool BamWriter::open(const std::string& path, const std::string& header_sam_path, const std::string& index_path, std::string* err)
+{
+  f_ = fopen(path.c_str(), "wb");
+  if (!f_) { *err = "cannot open " + path + " for writing"; return false; }
+  if (!index_path.empty()) fidx_ = fopen(index_path.c_str(), "w");
+  std::string text; std::vector<uint32_t> tlen;
+  { std::ifstream in(header_sam_path.c_str()); if (!in.good()) { *err = "Failed to open SAM header file " + header_sam_path; return false; }
+    std::stringstream ss; ss << in.rdbuf(); text = ss.str(); }
+  { std::istringstream ls(text); std::string line;
+    while (std::getline(ls, line)) {
+      if (line.compare(0, 3, "@SQ") != 0) continue;
+      std::string sn; uint32_t ln = 0; size_t p = 0;
+      while ((p = line.find('\t', p)) != std::string::npos) { ++p; size_t e = line.find_first_of("\t\r\n", p);
+        const std::string fld = line.substr(p, e == std::string::npos ? std::string::npos : e - p);
+        if (fld.compare(0, 3, "SN:") == 0) sn = fld.substr(3); else if (fld.compare(0, 3, "LN:") == 0) ln = (uint32_t)strtoul(fld.c_str() + 3, nullptr, 10); }
+      tnames_.push_back(sn); tlen.push_back(ln);
+    } }
+  put("BAM\1", 4);
+  const int32_t l_text = (int32_t)text.size(); put(&l_text, 4); put(text.data(), text.size());
+  const int32_t n_ref = (int32_t)tnames_.size(); put(&n_ref, 4);
+  for (size_t i = 0; i < tnames_.size(); ++i) { const int32_t l = (int32_t)tnames_[i].size() + 1; put(&l, 4); put(tnames_[i].c_str(), (size_t)l); put(&tlen[i], 4); }
+  flush_block();
+  return true;
+}
+
+int BamWriter::target_id(const std::string& name) const
+{ for (size_t i = 0; i < tnames_.size(); ++i) if (tnames_[i] == name) return (int)i; return -1; }
+
+void BamWriter::put(const void* p, size_t n)
+{
+  const uint8_t* s = (const uint8_t*)p;
+  while (n) { const size_t room = BLOCK_DATA - blk_.size(); const size_t k = n < room ? n : room; blk_.insert(blk_.end(), s, s + k); s += k; n -= k;
+    if (blk_.size() >= BLOCK_DATA) flush_block(); }
+}
+
+void BamWriter::flush_block()
+{
+  if (blk_.empty() || !f_) return;
+  uint8_t out[70000];
+  z_stream zs; memset(&zs, 0, sizeof zs);
+  deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+  zs.next_in = blk_.data(); zs.avail_in = (uInt)blk_.size(); zs.next_out = out + 18; zs.avail_out = sizeof(out) - 18 - 8;
+  const int rc = deflate(&zs, Z_FINISH); const size_t clen = zs.total_out; deflateEnd(&zs);
+  if (rc != Z_STREAM_END) { fail_ = true; return; }
+  const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  memcpy(out, hdr, 16);
+  const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1); memcpy(out + 16, &bsize, 2);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), blk_.data(), (uInt)blk_.size()), isize = (uint32_t)blk_.size();
+  memcpy(out + 18 + clen, &crc, 4); memcpy(out + 18 + clen + 4, &isize, 4);
+  const size_t total = clen + 26;
+  if (fwrite(out, 1, total, f_) != total) fail_ = true;
+  file_off_ += total; blk_.clear();
+}
+
+void BamWriter::write(const std::string& qname, uint32_t read_id, int flag, int tid, int pos0, int mapq, const std::vector<uint32_t>& cigar,
+                      const std::string& seq, const std::string& qual, const std::vector<uint8_t>& aux)
+{
+  // side index: an entry every >= 1000 records, at a read-id boundary (common.h:577-611)
+  int64_t pre_pos = 0; bool write_index = false;
+  if (fidx_ && read_id) {
+    if (idxcount_ >= 1000 && (long)read_id != idx_last_id_) { pre_pos = tell(); write_index = true; }
+    idx_last_id_ = (long)read_id; idxcount_++;
+  }
+  int end = pos0; for (uint32_t c : cigar) { const int op = (int)(c & 15); if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += (int)(c >> 4); }
+  if (end == pos0) end = pos0 + 1;
+  const int32_t l_seq = (int32_t)seq.size();
+  const int32_t block_size = 32 + (int32_t)qname.size() + 1 + 4 * (int32_t)cigar.size() + (l_seq + 1) / 2 + l_seq + (int32_t)aux.size();
+  std::vector<uint8_t> rec; rec.reserve((size_t)block_size + 4);
+  auto p32 = [&](int32_t v) { const uint8_t* b = (const uint8_t*)&v; rec.insert(rec.end(), b, b + 4); };
+  p32(block_size); p32(tid); p32(pos0);
+  const uint32_t bin_mq_nl = ((uint32_t)reg2bin(pos0, end) << 16) | ((uint32_t)mapq << 8) | (uint32_t)(qname.size() + 1);
+  p32((int32_t)bin_mq_nl); p32((int32_t)(((uint32_t)flag << 16) | (uint32_t)cigar.size()));
+  p32(l_seq); p32(-1); p32(-1); p32(0);
+  rec.insert(rec.end(), qname.begin(), qname.end()); rec.push_back(0);
+  for (uint32_t c : cigar) p32((int32_t)c);
+  static const uint8_t code[256] = {0};
+  (void)code;
+  auto nt = [](char c) -> uint8_t { switch (c) { case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': return 3; case 'G': case 'g': return 4;
+    case 'R': return 5; case 'S': return 6; case 'V': return 7; case 'T': case 't': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
+    case 'D': return 13; case 'B': return 14; default: return 15; } };
+  for (int i = 0; i < l_seq; i += 2) rec.push_back((uint8_t)((nt(seq[i]) << 4) | (i + 1 < l_seq ? nt(seq[i + 1]) : 0)));
+  for (int i = 0; i < l_seq; ++i) rec.push_back((uint8_t)(i < (int)qual.size() ? qual[i] - 33 : 0xff));
+  rec.insert(rec.end(), aux.begin(), aux.end());
+  // samtools' bgzf_write flushes the current block first when a record does not fit in it
+  if (blk_.size() + rec.size() > BLOCK_DATA && !blk_.empty() && rec.size() <= BLOCK_DATA) flush_block();
+  put(rec.data(), rec.size());
+  wcount_++;
+  if (write_index) { fprintf(fidx_, "%ld\t%ld\n", (long)read_id, (long)pre_pos); idxcount_ = 0; }
+}
+
+bool BamWriter::close(std::string* err)
+{
+  if (!f_) return !fail_;
+  flush_block();
+  static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (fwrite(eof_block, 1, 28, f_) != 28) fail_ = true;
+  if (fclose(f_) != 0) fail_ = true;
+  f_ = nullptr;
+  if (fidx_) { fclose(fidx_); fidx_ = nullptr; }
+  if (fail_ && err) *err = "error writing BAM output";
+  return !fail_;
+}
+
+void BamWriter::aux_int(std::vector<uint8_t>& a, const char tag[2], long long x)
+{
+  a.push_back((uint8_t)tag[0]); a.push_back((uint8_t)tag[1]);
+  auto putn = [&](char t, const void* p, int n) { a.push_back((uint8_t)t); const uint8_t* b = (const uint8_t*)p; a.insert(a.end(), b, b + n); };
+  if (x < 0) {
+    if (x >= -127) { const int8_t v = (int8_t)x; putn('c', &v, 1); }
+    else if (x >= -32767) { const int16_t v = (int16_t)x; putn('s', &v, 2); }
+    else { const int32_t v = (int32_t)x; putn('i', &v, 4); }
+  } else {
+    if (x <= 255) { const uint8_t v = (uint8_t)x; putn('C', &v, 1); }
+    else if (x <= 65535) { const uint16_t v = (uint16_t)x; putn('S', &v, 2); }
+    else { const uint32_t v = (uint32_t)x; putn('I', &v, 4); }
+  }
+}
+void BamWriter::aux_char(std::vector<uint8_t>& a, const char tag[2], char c)
+{ a.push_back((uint8_t)tag[0]); a.push_back((uint8_t)tag[1]); a.push_back('A'); a.push_back((uint8_t)c); }
+void BamWriter::aux_str(std::vector<uint8_t>& a, const char tag[2], const std::string& s)
+{ a.push_back((uint8_t)tag[0]); a.push_back((uint8_t)tag[1]); a.push_back('Z'); a.insert(a.end(), s.begin(), s.end()); a.push_back(0); }
+
+}  // namespace thbhost

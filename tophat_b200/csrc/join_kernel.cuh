@@ -1,0 +1,457 @@
+// join_kernel.cuh -- long_spanning_reads' per-read arithmetic as one sm_100a kernel (thread = read).
+//
+// Replaces, for --fusion-search off and base-space reads, the reference's
+//   join_segments_for_read   long_spanning_reads.cpp:2612-2667   (multihit guard, one DFS per first-segment hit)
+//   dfs_seg_hits             2222-2610   (chain enumeration, 10,000-leaf budget per first-segment hit)
+//   merge_segment_chain      2101-2220   (chain orientation, valid_hit 2045-2099)
+//   merge_chain              805-2038    (gap closure by junction / deletion / insertion look-up with the +-4 bp
+//                                         boundary adjustment, CIGAR stitching)
+//   BowtieHit::check_editdist_consistency   bwt_map.cpp:2349-2465
+// The junction / insertion sets are sorted device arrays searched with the std::set bounds the reference uses.
+// Sorting + de-duplicating a read's joined hits, the read-level filters and the SAM fields stay on the host.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/tophat_b200.h"
+#include "bitplanes.cuh"
+
+namespace thb {
+
+constexpr int JMAXOPS = THB_JOINED_MAX_OPS;
+constexpr int JMAXSEGS = 12;
+// CigarOpCode values (bwt_map.h:36-55); ops are packed as length << 4 | opcode
+enum { OP_MATCH = 1, OP_mATCH = 2, OP_INS = 3, OP_iNS = 4, OP_DEL = 5, OP_dEL = 6, OP_REF_SKIP = 11, OP_rEF_SKIP = 12,
+       OP_SOFT_CLIP = 13, OP_HARD_CLIP = 14, OP_PAD = 15 };
+__host__ __device__ __forceinline__ uint32_t mkop(int code, uint32_t len) { return (len << 4) | (uint32_t)code; }
+__host__ __device__ __forceinline__ int opc(uint32_t o) { return (int)(o & 15u); }
+__host__ __device__ __forceinline__ uint32_t opl(uint32_t o) { return o >> 4; }
+
+struct JoinParams {
+  int max_ins, max_del, min_report_intron, max_report_intron, fusion_min_dist, max_seg_multihits, bowtie2, seglen;
+};
+
+struct JoinSets {
+  const thb_junction* juncs; uint32_t n_juncs;        // Junction order (junctions.h:39-57)
+  const thb_insertion* ins; uint32_t n_ins;           // (refid, left, length) order (insertions.h:52-67)
+};
+
+struct JoinBatchView {
+  const thb_join_bundle* bundles; const uint16_t* seg_count; const uint64_t* reads; const thb_jhit* hits;
+  uint32_t n_bundles, n_segs, read_words;
+};
+
+struct JoinOut {
+  thb_joined* rec; unsigned long long cap; unsigned long long* count; unsigned int* overflow;
+  unsigned long long* counters;      // [0] chains merged (leaves) [1] closures looked up [2] joined hits emitted
+};
+
+// working hit of merge_chain
+struct WHit {
+  uint32_t ref; int left; int n; uint32_t ops[JMAXOPS];
+  bool anti, asplice; uint8_t mism, smm; int seq_pos, seq_len;
+};
+
+__device__ __forceinline__ int cig_right(int left, const uint32_t* ops, int n)
+{ int r = left; for (int i = 0; i < n; ++i) { const int c = opc(ops[i]); if (c == OP_MATCH || c == OP_REF_SKIP || c == OP_DEL) r += (int)opl(ops[i]); } return r; }
+__device__ __forceinline__ int cig_read_len(const uint32_t* ops, int n)
+{ int r = 0; for (int i = 0; i < n; ++i) { const int c = opc(ops[i]); if (c == OP_MATCH || c == OP_INS || c == OP_SOFT_CLIP) r += (int)opl(ops[i]); } return r; }
+__device__ __forceinline__ bool cig_spliced(const uint32_t* ops, int n)
+{ for (int i = 0; i < n; ++i) if (opc(ops[i]) == OP_REF_SKIP) return true; return false; }
+__device__ __forceinline__ int cig_gap_length(const uint32_t* ops, int n)
+{ int r = 0; for (int i = 0; i < n; ++i) { const int c = opc(ops[i]); if (c == OP_INS || c == OP_DEL) r += (int)opl(ops[i]); } return r; }
+
+// Dna5 code of global base g: 0..3, 4 = N
+__device__ __forceinline__ int ref_code5(const RefView& r, uint64_t g)
+{
+  const uint64_t b = g >> 6; const int j = (int)(g & 63);
+  if ((__ldg(r.nmask + b) >> j) & 1ull) return 4;
+  const ulonglong2 w = __ldg(r.planes + b);
+  return (int)((w.x >> j) & 1ull) | ((int)((w.y >> j) & 1ull) << 1);
+}
+// code of base i of the oriented read R (planes with stride 4 words): 0..3, 4 = N
+__device__ __forceinline__ int read_code5(const uint64_t* R, int i)
+{
+  const int w = i >> 6, j = i & 63;
+  if ((R[8 + w] >> j) & 1ull) return 4;
+  return (int)((R[w] >> j) & 1ull) | ((int)((R[4 + w] >> j) & 1ull) << 1);
+}
+
+// std::set<Junction>::lower_bound / upper_bound on the sorted array
+__device__ __forceinline__ bool junc_less(const thb_junction& a, uint32_t ref, uint32_t left, uint32_t right, uint32_t anti)
+{
+  if (a.ref_id != ref) return a.ref_id < ref;
+  if (a.left != left) return a.left < left;
+  if (a.right != right) return a.right < right;
+  return a.antisense < anti;
+}
+__device__ __forceinline__ bool junc_greater(const thb_junction& a, uint32_t ref, uint32_t left, uint32_t right, uint32_t anti)
+{
+  if (a.ref_id != ref) return a.ref_id > ref;
+  if (a.left != left) return a.left > left;
+  if (a.right != right) return a.right > right;
+  return a.antisense > anti;
+}
+__device__ __forceinline__ uint32_t junc_lower_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t right, uint32_t anti)
+{ uint32_t lo = 0, hi = S.n_juncs; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_less(S.juncs[mid], ref, left, right, anti)) lo = mid + 1; else hi = mid; } return lo; }
+__device__ __forceinline__ uint32_t junc_upper_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t right, uint32_t anti)
+{ uint32_t lo = 0, hi = S.n_juncs; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_greater(S.juncs[mid], ref, left, right, anti)) hi = mid; else lo = mid + 1; } return lo; }
+// std::set<Insertion>::upper_bound(Insertion(ref, left, <string of length len>))
+__device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t len)
+{
+  uint32_t lo = 0, hi = S.n_ins;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1; const thb_insertion& a = S.ins[mid];
+    bool greater;
+    if (a.ref_id != ref) greater = a.ref_id > ref; else if (a.left != left) greater = a.left > left; else greater = a.len > len;
+    if (greater) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void load_whit(WHit& w, const thb_jhit* h, int seq_pos, int seq_len)
+{
+  const uint4* p = reinterpret_cast<const uint4*>(h);
+  const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  w.ref = a.x; w.left = (int)a.y;
+  w.n = (int)(a.z & 0xffu); const uint32_t fl = (a.z >> 8) & 0xffu; w.mism = (uint8_t)((a.z >> 16) & 0xffu); w.smm = (uint8_t)(a.z >> 24);
+  w.anti = (fl & THB_HIT_ANTISENSE) != 0; w.asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
+  w.ops[0] = a.w; w.ops[1] = b.x; w.ops[2] = b.y; w.ops[3] = b.z; w.ops[4] = b.w; w.ops[5] = c.x; w.ops[6] = c.y; w.ops[7] = c.z; w.ops[8] = c.w;
+  if (w.n > THB_JHIT_MAX_OPS) w.n = THB_JHIT_MAX_OPS;
+  w.seq_pos = seq_pos; w.seq_len = seq_len;
+}
+
+// the few fields of a segment hit the DFS needs
+struct LiteHit { uint32_t ref; int left, right; bool anti; };
+__device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
+{
+  const uint4* p = reinterpret_cast<const uint4*>(h);
+  const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  uint32_t ops[9] = { a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w };
+  int n = (int)(a.z & 0xffu); if (n > THB_JHIT_MAX_OPS) n = THB_JHIT_MAX_OPS;
+  LiteHit l; l.ref = a.x; l.left = (int)a.y; l.anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0;
+  int r = l.left;
+  #pragma unroll
+  for (int i = 0; i < 9; ++i) if (i < n) { const int cc = opc(ops[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(ops[i]); }
+  l.right = r;
+  return l;
+}
+
+// dfs_seg_hits' pair test with --fusion-search off (2250-2558): same contig, same strand, and the genomic gap between
+// the (strand-ordered) pair within [-max_insertion_length, max_report_intron_length].
+__device__ __forceinline__ bool chain_compatible(const JoinParams& P, const LiteHit& prev, const LiteHit& curr)
+{
+  if (prev.ref != curr.ref || prev.anti != curr.anti) return false;     // would need a fusion (dir != FUSION_NOTHING, 2402)
+  int dist;
+  if (prev.anti) dist = prev.left - curr.right;                         // pair swapped for antisense hits (2355-2361)
+  else {
+    dist = curr.left - prev.right;                                      // 2366-2379
+  }
+  return dist <= P.max_report_intron && dist >= -P.max_ins;             // 2554-2556
+}
+
+// valid_hit 2045-2099
+__device__ __forceinline__ bool valid_cigar(const JoinParams& P, const uint32_t* ops, int n)
+{
+  for (int i = 1; i < n; ++i) {
+    const int c = opc(ops[i]), p = opc(ops[i - 1]);
+    if (c != OP_MATCH && p != OP_MATCH) return false;
+    if (c == OP_INS && (int)opl(ops[i]) > P.max_ins) return false;
+    if (c == OP_DEL && (int)opl(ops[i]) > P.max_del) return false;
+    if (c == OP_REF_SKIP && (int64_t)opl(ops[i]) < (int64_t)P.min_report_intron) return false;
+  }
+  return opc(ops[0]) == OP_MATCH && opc(ops[n - 1]) == OP_MATCH;
+}
+
+// BowtieHit::check_editdist_consistency (bwt_map.cpp:2349-2465) for a single-contig hit whose sequence is R
+__device__ __forceinline__ bool editdist_consistent(const RefView& ref, uint32_t ref_id, int left, const uint32_t* ops, int n,
+                                                    const uint64_t* R, int read_words4, uint8_t mismatches)
+{
+  if (!(ref_id >= 1 && ref_id <= ref.n_contigs)) return false;
+  const int64_t len = (int64_t)__ldg(ref.contig_len + ref_id - 1);
+  if (len <= 0) return false;
+  const uint64_t cs = __ldg(ref.contig_start + ref_id - 1);
+  int64_t pos_ref = left; int pos_seq = 0; unsigned mm = 0, nmm = 0;
+  for (int i = 0; i < n; ++i) {
+    const int c = opc(ops[i]); const int l = (int)opl(ops[i]);
+    if (c == OP_MATCH) {
+      if (pos_ref < 0 || pos_ref + l > len) return false;               // the reference would read outside the contig
+      for (int o = 0; o < l; o += 64) {
+        const int m = min(64, l - o);
+        const P3 g = ref_fetch3(ref, cs + (uint64_t)(pos_ref + o), m);
+        P3 r; r.p0 = plane_slice(R, 4, pos_seq + o, m); r.p1 = plane_slice(R + 4, 4, pos_seq + o, m); r.pn = plane_slice(R + 8, 4, pos_seq + o, m);
+        mm += (unsigned)__popcll((g.p0 ^ r.p0) | (g.p1 ^ r.p1) | (g.pn ^ r.pn));
+        nmm += (unsigned)__popcll(g.pn & r.pn);
+      }
+      pos_ref += l; pos_seq += l;
+    } else if (c == OP_INS) pos_seq += l;
+    else if (c == OP_DEL || c == OP_REF_SKIP) pos_ref += l;
+  }
+  (void)read_words4;
+  return mm == (unsigned)mismatches || mm + nmm == (unsigned)mismatches;
+}
+
+__device__ __forceinline__ bool cig_push(uint32_t* ops, int& n, uint32_t op)
+{ if (n >= JMAXOPS) return false; ops[n++] = op; return true; }
+
+// merge_chain (805-2038), fusion_dir == FUSION_NOTHING, base space.  `chain[e]` are the hits in genomic order, R the
+// read in the chain's orientation, seq_len[e] the read bases of element e.  Returns false where the reference
+// returns an empty BowtieHit.
+__device__ bool merge_chain(const RefView& ref, const JoinParams& P, const JoinSets& S, const uint64_t* R,
+                            const thb_jhit* const* chain, const int* seq_len, int n, thb_joined& out, unsigned& n_closures)
+{
+  // first pass (843-897): more than one gap that only a fusion could explain -> give up
+  {
+    int num_fusions = 0;
+    LiteHit prev = load_lite(chain[0]);
+    for (int e = 1; e < n; ++e) {
+      const LiteHit curr = load_lite(chain[e]);
+      if (prev.ref != curr.ref) ++num_fusions;
+      else {
+        const int gap = curr.left - prev.right;
+        const int hi = min(P.max_report_intron, P.fusion_min_dist);
+        if (gap < -P.max_ins || (gap > P.max_del && (gap < P.min_report_intron || gap > hi))) ++num_fusions;
+      }
+      if (num_fusions >= 2) return false;
+      prev = curr;
+    }
+  }
+  if (!(chain[0]->ref_id >= 1 && chain[0]->ref_id <= ref.n_contigs)) return false;
+  const uint64_t cs = __ldg(ref.contig_start + chain[0]->ref_id - 1);
+  const int64_t clen = (int64_t)__ldg(ref.contig_len + chain[0]->ref_id - 1);
+
+  // accumulators of the final pass (1888-1945), filled as blocks are finalised
+  uint32_t LC[JMAXOPS]; int nLC = 0; int num_mm = 0, num_smm = 0; bool saw_as = false, saw_s = false;
+  int old_read_length = 0;
+  auto finalize = [&](const WHit& h) -> bool {
+    num_mm += h.mism; num_smm += h.smm;
+    if (cig_spliced(h.ops, h.n)) {
+      if (h.asplice) { if (saw_s) return false; saw_as = true; } else { if (saw_as) return false; saw_s = true; }
+    }
+    int b = 0;
+    if (nLC > 0 && opc(LC[nLC - 1]) == opc(h.ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(h.ops[0])); b = 1; }
+    for (; b < h.n; ++b) if (!cig_push(LC, nLC, h.ops[b])) return false;
+    return true;
+  };
+
+  WHit prev; load_whit(prev, chain[0], 0, seq_len[0]);
+  const int left0 = prev.left; const uint32_t ref0 = prev.ref;
+  old_read_length += cig_read_len(prev.ops, prev.n);
+  bool antisense = prev.anti;
+  for (int e = 1; e < n; ++e) {
+    WHit curr; load_whit(curr, chain[e], prev.seq_pos + prev.seq_len, seq_len[e]);
+    old_read_length += cig_read_len(curr.ops, curr.n);
+    antisense = prev.anti;
+    if (!(opc(prev.ops[prev.n - 1]) == OP_MATCH || opc(curr.ops[0]) == OP_MATCH)) return false;          // 930-934
+    const bool ps = cig_spliced(prev.ops, prev.n), csp = cig_spliced(curr.ops, curr.n);
+    if (ps && csp && prev.asplice != curr.asplice) return false;                                          // 942-949
+    bool found = false;
+    bool antisense_closure = ps ? prev.asplice : curr.asplice;
+    int mismatch = 0;
+    const int prml = (int)opl(prev.ops[prev.n - 1]), clml = (int)opl(curr.ops[0]);
+    const int pright = cig_right(prev.left, prev.ops, prev.n);
+    const int dist = curr.left - pright;
+    const bool same_strand = prev.anti == curr.anti;
+    uint32_t NC[JMAXOPS]; int nNC = 0;
+    if (curr.ref != prev.ref) return false;
+    if (dist < 0 && dist >= -P.max_ins && same_strand) {
+      // ---- insertion closure (1010-1306)
+      const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(curr.left + 4);
+      uint32_t it = ins_upper_bound(S, prev.ref, lbnd, 0u);
+      const uint32_t ub = ins_upper_bound(S, prev.ref, rbnd, (uint32_t)P.max_ins);
+      n_closures++;
+      int best_itpr = 0; uint32_t best_len = 0;
+      for (; it != ub && it < S.n_ins; ++it) {
+        const thb_insertion& I = S.ins[it];
+        if ((int)I.len != pright - curr.left) continue;
+        const int itpr = pright - (int)I.left - 1;               // insert_to_prev_right
+        const int clti = (int)I.left - curr.left + 1;            // curr_left_to_insert
+        if (itpr > prml || clti > clml) continue;
+        int this_ref_mm = 0, ins_mm = 0; const int ilen = (int)I.len;
+        auto ins_code = [&](int k) -> int { const char ch = I.seq[k]; return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; };
+        if (itpr > 0) {
+          // referenceSequence = ref[I.left + 1, prev.right); old/new segment = last itpr bases of prev's sequence
+          const int64_t g0 = (int64_t)I.left + 1; const int s0 = prev.seq_pos + prev.seq_len - itpr;
+          if (g0 < 0 || g0 + itpr > clen) return false;
+          for (int ri = 0; ri < itpr; ++ri) {
+            const int rc = ref_code5(ref, cs + (uint64_t)(g0 + ri)), sc = read_code5(R, s0 + ri);
+            if (rc == 4 || rc != sc) ++this_ref_mm;
+            if (ri < ilen) { const int ic = ins_code(ri); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
+            else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + ri - ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
+          }
+        }
+        if (clti > 0) {
+          // referenceSequence = ref[curr.left, I.left + 1); old/new segment = first clti bases of curr's sequence
+          const int64_t g0 = curr.left; const int s0 = curr.seq_pos;
+          if (g0 < 0 || g0 + clti > clen) return false;
+          for (int ri = 0; ri < clti; ++ri) {
+            const int sp = clti - ri - 1, ip = ilen - ri - 1;
+            const int rc = ref_code5(ref, cs + (uint64_t)(g0 + sp)), sc = read_code5(R, s0 + sp);
+            if (rc == 4 || rc != sc) ++this_ref_mm;
+            if (ri < ilen) { const int ic = ins_code(ip); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
+            else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + sp + ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
+          }
+        }
+        if (found) return false;                                  // a second same-length candidate rejects the chain (1246-1250)
+        if (ins_mm == 0) { mismatch = -this_ref_mm; found = true; best_itpr = itpr; best_len = I.len; }
+      }
+      if (!found) return false;
+      // new cigar (1262-1290); lengths are uint32 in the reference, the arithmetic wraps the same way
+      for (int k = 0; k < prev.n; ++k) NC[nNC++] = prev.ops[k];
+      { const uint32_t bl = opl(NC[nNC - 1]) - (uint32_t)best_itpr; if ((bl & 0x0fffffffu) == 0) --nNC; else NC[nNC - 1] = mkop(opc(NC[nNC - 1]), bl & 0x0fffffffu); }
+      if (!cig_push(NC, nNC, mkop(OP_INS, best_len))) return false;
+      { const uint32_t fl = (opl(curr.ops[0]) + (uint32_t)(best_itpr - (int)best_len)) & 0x0fffffffu;
+        int c0 = 1; if (fl > 0) { c0 = 0; }
+        for (int k = c0; k < curr.n; ++k) if (!cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), fl) : curr.ops[k])) return false; }
+    } else if (dist > 0 && dist <= P.max_report_intron && same_strand) {
+      // ---- junction / deletion closure (1311-1591)
+      const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(curr.left + 4);
+      uint32_t it = junc_upper_bound(S, prev.ref, lbnd, rbnd - 8u, 1u);
+      const uint32_t ub = junc_lower_bound(S, prev.ref, lbnd + 8u, rbnd, 0u);
+      n_closures++;
+      int new_diff = 0xff, best_dtl = 0; uint32_t best_glen = 0; bool best_anti = false;
+      for (; it != ub && it < S.n_juncs; ++it) {
+        const thb_junction J = S.juncs[it];
+        const int dtl = (int)(J.left - (uint32_t)pright + 1u), dtr = (int)(J.right - (uint32_t)curr.left);
+        if (!(abs(dtl) <= 4 && abs(dtr) <= 4 && dtl == dtr)) continue;
+        if (dtl > clml || -dtl > prml) continue;                  // enough matched bases on either side (1343-1348)
+        int new_mm = 0, old_mm = 0;
+        if (dtl > 0) {
+          if ((int64_t)pright + dtl > clen || (int64_t)curr.left + dtl > clen) return false;
+          for (int i = 0; i < dtl; ++i) {
+            const int sc = read_code5(R, curr.seq_pos + i);
+            if (sc != ref_code5(ref, cs + (uint64_t)(pright + i))) ++new_mm;
+            if (sc != ref_code5(ref, cs + (uint64_t)(curr.left + i))) ++old_mm;
+          }
+        } else if (dtl < 0) {
+          const int ad = -dtl;
+          if ((int64_t)J.right + ad > clen) return false;
+          for (int i = 0; i < ad; ++i) {
+            const int sc = read_code5(R, prev.seq_pos + prev.seq_len - (ad - i));
+            if (sc != ref_code5(ref, cs + (uint64_t)J.right + (uint64_t)i)) ++new_mm;
+            if (sc != ref_code5(ref, cs + (uint64_t)J.left + 1u + (uint64_t)i)) ++old_mm;
+          }
+        }
+        const int temp = new_mm - old_mm;
+        if (temp >= new_diff || new_mm >= 2) continue;            // first strictly better candidate in Junction order (1497-1512)
+        new_diff = temp; best_dtl = dtl; best_glen = J.right - J.left - 1u; best_anti = J.antisense != 0; found = true;
+      }
+      if (!found) return false;
+      mismatch = new_diff;
+      for (int k = 0; k < prev.n; ++k) NC[nNC++] = prev.ops[k];
+      { const int nlb = prml + best_dtl; if (nlb > 0) NC[nNC - 1] = mkop(opc(NC[nNC - 1]), (uint32_t)nlb); else --nNC; }
+      if (best_glen <= (uint32_t)P.max_del) { if (!cig_push(NC, nNC, mkop(OP_DEL, best_glen))) return false; }
+      else { if (!cig_push(NC, nNC, mkop(OP_REF_SKIP, best_glen))) return false; antisense_closure = best_anti; }
+      { const int nrf = clml - best_dtl;
+        for (int k = nrf > 0 ? 0 : 1; k < curr.n; ++k) if (!cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), (uint32_t)nrf) : curr.ops[k])) return false; }
+    } else if (!(dist == 0 && same_strand)) {
+      return false;                                               // only a fusion could close this gap (1592-1819)
+    }
+    if (found) {
+      // merged_hit (1822-1838); _mismatches / _edit_dist are unsigned chars in the reference
+      const int mm = (int)prev.mism + (int)curr.mism + mismatch;
+      prev.n = nNC; for (int k = 0; k < nNC; ++k) prev.ops[k] = NC[k];
+      prev.asplice = antisense_closure; prev.anti = antisense; prev.mism = (uint8_t)mm; prev.smm = (uint8_t)(prev.smm + curr.smm);
+      prev.seq_len += curr.seq_len;
+      if (nNC == 0) return false;
+    } else {
+      if (!finalize(prev)) return false;
+      prev = curr;
+    }
+  }
+  if (!finalize(prev)) return false;
+  // new_hit (1947-1957) + final checks (2023-2035)
+  if (nLC == 0) return false;
+  const uint8_t mism = (uint8_t)num_mm;
+  const uint8_t edit = (uint8_t)(num_mm + cig_gap_length(LC, nLC));
+  if (cig_read_len(LC, nLC) != old_read_length) return false;
+  if (!editdist_consistent(ref, ref0, left0, LC, nLC, R, 4, mism)) return false;
+  out.ref_id = ref0; out.left = left0; out.n_ops = (uint8_t)nLC;
+  out.flags = (uint8_t)((antisense ? THB_HIT_ANTISENSE : 0) | (saw_as ? THB_JHIT_ANTISENSE_SPLICE : 0));
+  out.mismatches = mism; out.edit_dist = edit; out.splice_mms = (uint8_t)num_smm;
+  for (int k = 0; k < nLC; ++k) out.ops[k] = LC[k];
+  return true;
+}
+
+__device__ __forceinline__ void emit_joined(const JoinOut& o, const thb_joined& j)
+{
+  const unsigned long long slot = atomicAdd(o.count, 1ull);
+  if (slot >= o.cap) { atomicOr(o.overflow, 1u); return; }
+  o.rec[slot] = j;
+}
+
+// join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610) for one read
+__device__ void join_read(const RefView& ref, const JoinParams& P, const JoinSets& S, const JoinBatchView& bv, const JoinOut& o,
+                          uint32_t bi, unsigned& n_leaves, unsigned& n_closures, unsigned& n_emit)
+{
+  const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
+  const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
+  if (n < 1 || n > JMAXSEGS) return;
+  uint32_t off[JMAXSEGS]; int cnt[JMAXSEGS];
+  { uint32_t a = hdr.y;
+    for (int s = 0; s < n; ++s) { cnt[s] = (int)__ldg(bv.seg_count + (size_t)bi * bv.n_segs + s); off[s] = a; a += (uint32_t)cnt[s]; } }
+  if (P.bowtie2) for (int s = 0; s < n; ++s) if (cnt[s] > P.max_seg_multihits) return;      // 2624-2632
+  // the read in both orientations, stride-4 planes
+  uint64_t Rf[12], Rr[12];
+  { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
+    for (int k = 0; k < 12; ++k) { Rf[k] = 0; Rr[k] = 0; }
+    for (int pl = 0; pl < 3; ++pl) for (int w = 0; w < rw && w < 4; ++w) Rf[pl * 4 + w] = __ldg(rd + pl * rw + w);
+    // reverse complement of the whole read (non-ACGT stays N, reads.cpp:191-207)
+    for (int i = 0; i < read_len; ++i) {
+      const int c = read_code5(Rf, read_len - 1 - i); const int w = i >> 6, j = i & 63;
+      if (c == 4) Rr[8 + w] |= 1ull << j; else { const int d = 3 - c; if (d & 1) Rr[w] |= 1ull << j; if (d & 2) Rr[4 + w] |= 1ull << j; }
+    } }
+  int seglen_of[JMAXSEGS];
+  for (int s = 0; s < n; ++s) seglen_of[s] = (s == n - 1) ? read_len - s * P.seglen : P.seglen;
+
+  int sel[JMAXSEGS], it[JMAXSEGS];
+  const thb_jhit* chain[JMAXSEGS]; int clen[JMAXSEGS];
+  auto leaf = [&]() {
+    ++n_leaves;
+    thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0;
+    bool ok;
+    if (n == 1) {                                                  // merge_segment_chain, single hit (2196-2213)
+      WHit w; load_whit(w, bv.hits + off[0] + sel[0], 0, read_len);
+      ok = w.n > 0 && valid_cigar(P, w.ops, w.n);
+      if (ok) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
+                j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
+                for (int k = 0; k < w.n; ++k) j.ops[k] = w.ops[k]; }
+    } else {
+      const bool anti = (bv.hits[off[0] + sel[0]].flags & THB_HIT_ANTISENSE) != 0;     // chain orientation (2117-2121)
+      for (int e = 0; e < n; ++e) { const int s = anti ? n - 1 - e : e; chain[e] = bv.hits + off[s] + sel[s]; clen[e] = seglen_of[s]; }
+      ok = merge_chain(ref, P, S, anti ? Rr : Rf, chain, clen, n, j, n_closures);
+      if (ok) ok = valid_cigar(P, j.ops, j.n_ops);
+    }
+    if (ok) { emit_joined(o, j); ++n_emit; }
+  };
+  for (int i0 = 0; i0 < cnt[0]; ++i0) {
+    sel[0] = i0;
+    int num_try = 10000;                                           // 2647
+    if (n == 1) { --num_try; leaf(); continue; }
+    int lvl = 1; it[1] = 0;
+    LiteHit top[JMAXSEGS]; top[0] = load_lite(bv.hits + off[0] + i0);
+    while (lvl >= 1) {
+      if (it[lvl] >= cnt[lvl]) { --lvl; if (lvl >= 1) ++it[lvl]; continue; }
+      const LiteHit cand = load_lite(bv.hits + off[lvl] + it[lvl]);
+      if (!chain_compatible(P, top[lvl - 1], cand)) { ++it[lvl]; continue; }
+      sel[lvl] = it[lvl]; top[lvl] = cand;
+      if (lvl == n - 1) { --num_try; leaf(); if (num_try <= 0) break; ++it[lvl]; }
+      else { ++lvl; it[lvl] = 0; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+chain_join_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, JoinOut o)
+{
+  unsigned n_leaves = 0, n_closures = 0, n_emit = 0;
+  const unsigned lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < bv.n_bundles; base += gridDim.x * blockDim.x) {
+    if (base + lane < bv.n_bundles) join_read(ref, P, S, bv, o, base + lane, n_leaves, n_closures, n_emit);
+    __syncwarp();
+  }
+  for (int k = 16; k > 0; k >>= 1) { n_leaves += __shfl_xor_sync(0xffffffffu, n_leaves, k); n_closures += __shfl_xor_sync(0xffffffffu, n_closures, k); n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k); }
+  if (lane == 0) { if (n_leaves) atomicAdd(o.counters + 0, (unsigned long long)n_leaves); if (n_closures) atomicAdd(o.counters + 1, (unsigned long long)n_closures);
+                   if (n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit); }
+}
+
+}  // namespace thb

@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "../../include/tophat_b200.h"
 #include "segjuncs_kernel.cuh"
+#include "join_kernel.cuh"
 
 using namespace thb;
 
@@ -70,6 +71,13 @@ struct thb_ctx {
   unsigned long long* d_counters = nullptr; unsigned long long* d_ins_count = nullptr;
   unsigned int* d_ovf_juncs = nullptr; unsigned int* d_ovf_dels = nullptr; unsigned int* d_err = nullptr;
   DevBuf d_keys, d_keys_sorted, d_cub_tmp, d_decoded, d_count;
+  // task queues of the scan phase
+  DevBuf q_win, q_indel, q_rescue, q_rescue_out, q_rbundle, q_bstate, q_owner;
+  uint64_t cap_win = 0, cap_indel = 0;
+  unsigned long long* d_qcounts = nullptr; unsigned int* d_qovf = nullptr;
+  cudaEvent_t kev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool kev_pending = false;
+  int sms = 148;
   Staging stage[2];
   // host results
   std::vector<thb_junction> h_juncs, h_dels; std::vector<thb_insertion> h_ins; std::vector<thb_fusion> h_fus;
@@ -78,6 +86,9 @@ struct thb_ctx {
   thb_timing timing{}; uint64_t n_bundles_total = 0, n_hits_total = 0, n_partner_total = 0;
   uint64_t n_ins_out = 0, n_del_out = 0;
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
+  // long_spanning_reads join
+  DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out; uint64_t j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
+  JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{};
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
 };
@@ -133,7 +144,7 @@ SegOutputs outputs(thb_ctx* ctx)
   return o;
 }
 
-struct Flags { unsigned int ovf_juncs, ovf_dels, err, pad; };
+struct Flags { unsigned int ovf_juncs, ovf_dels, err, qovf; };
 
 int read_state(thb_ctx* ctx, Flags* f, unsigned long long* ins_count)
 {
@@ -143,21 +154,68 @@ int read_state(thb_ctx* ctx, Flags* f, unsigned long long* ins_count)
   return THB_OK;
 }
 
-int launch_scan(thb_ctx* ctx, const BatchView& bv)
+// The scan phase of one bundle range: K1 enumerate -> K2 rescue -> K3 rescued windows -> K4 window scan -> K5 indel.
+// `n_partner` = partner hits present in this launch (upper bound of the rescue queue).
+template <int NSMAX>
+void launch_phase(thb_ctx* ctx, const BatchView& bv, const Queues& q, const SegOutputs& o, uint64_t n_hits)
+{
+  const int g_b = grid_for(bv.n_bundles, 256), g_h = grid_for(n_hits, 256), g_t = ctx->sms * 8;
+  uint32_t* bstate = (uint32_t*)ctx->q_bstate.p; uint32_t* owner = (uint32_t*)ctx->q_owner.p;
+  cudaEventRecord(ctx->kev[0], ctx->compute);
+  bundle_kernel<NSMAX><<<g_b, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner);
+  cudaEventRecord(ctx->kev[1], ctx->compute);
+  if (n_hits) hit_kernel<NSMAX><<<g_h, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, n_hits, o);
+  cudaEventRecord(ctx->kev[2], ctx->compute);
+  rescue_kernel<<<g_t, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q);
+  cudaEventRecord(ctx->kev[3], ctx->compute);
+  rescued_windows_kernel<NSMAX><<<g_t, 128, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, o);
+  cudaEventRecord(ctx->kev[4], ctx->compute);
+  window_scan_kernel<<<g_t, 256, 0, ctx->compute>>>(ctx->ref, q, o);
+  cudaEventRecord(ctx->kev[5], ctx->compute);
+  indel_kernel<<<g_t, 256, 0, ctx->compute>>>(ctx->ref, q, o);
+  cudaEventRecord(ctx->kev[6], ctx->compute);
+}
+
+int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t n_hits)
 {
   if (bv.n_bundles == 0) return THB_OK;
-  const int block = 256;
-  segjuncs_kernel<<<grid_for(bv.n_bundles, block), block, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, outputs(ctx));
+  ctx->cap_win = std::max<uint64_t>(ctx->cap_win, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+  ctx->cap_indel = std::max<uint64_t>(ctx->cap_indel, std::max<uint64_t>(bv.n_bundles / 2, 1u << 16));
+  CU(ctx->q_win.reserve(ctx->cap_win * sizeof(WindowTask))); CU(ctx->q_indel.reserve(ctx->cap_indel * sizeof(IndelTask)));
+  CU(ctx->q_rescue.reserve((n_partner + 1) * sizeof(uint2))); CU(ctx->q_rescue_out.reserve((n_partner + 1) * sizeof(int2)));
+  CU(ctx->q_rbundle.reserve((size_t)bv.n_bundles * sizeof(uint32_t)));
+  CU(ctx->q_bstate.reserve((size_t)bv.n_bundles * sizeof(uint32_t))); CU(ctx->q_owner.reserve((size_t)(n_hits + 1) * sizeof(uint32_t)));
+  Queues q;
+  q.win = (WindowTask*)ctx->q_win.p; q.cap_win = ctx->cap_win; q.indel = (IndelTask*)ctx->q_indel.p; q.cap_indel = ctx->cap_indel;
+  q.rescue = (uint2*)ctx->q_rescue.p; q.rescue_out = (int2*)ctx->q_rescue_out.p; q.rbundle = (uint32_t*)ctx->q_rbundle.p;
+  q.counts = ctx->d_qcounts; q.overflow = ctx->d_qovf;
+  CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
+  const SegOutputs o = outputs(ctx);
+  if (bv.n_segs <= 4) launch_phase<4>(ctx, bv, q, o, n_hits);
+  else if (bv.n_segs <= 8) launch_phase<8>(ctx, bv, q, o, n_hits);
+  else launch_phase<14>(ctx, bv, q, o, n_hits);
   CU(cudaGetLastError());
-  ctx->timing.kernel_launches++; ctx->own_launches++;
+  ctx->kev_pending = true;
+  ctx->timing.kernel_launches++; ctx->own_launches += 6;
   return THB_OK;
+}
+
+// adds the per-kernel CUDA-event times of the last launch_scan (the stream must be idle)
+void collect_kernel_times(thb_ctx* ctx, float* total)
+{
+  *total = 0.f;
+  if (!ctx->kev_pending) return;
+  ctx->kev_pending = false;
+  float* dst[6] = { &ctx->timing.bundle_ms, &ctx->timing.hit_ms, &ctx->timing.rescue_ms, &ctx->timing.rescued_windows_ms, &ctx->timing.window_scan_ms, &ctx->timing.indel_ms };
+  for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]) == cudaSuccess) { *dst[k] += ms; *total += ms; } }
 }
 
 int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
 {
   if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
   if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
-  if (b->n_segs < 1 || b->n_segs > (uint32_t)MAX_SEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, MAX_SEGS);
+  if (b->n_segs < 1 || b->n_segs > 14u) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,14]", b->n_segs);
+  if (b->n_bundles >= (1u << 28)) return fail(ctx, THB_EUNSUPPORTED, "more than 2^28 bundles in one batch");
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4] (reads up to 255 bp)", b->read_words);
   if (b->n_bundles && (!b->bundles || !b->seg_count || !b->reads)) return fail(ctx, THB_EINVAL, "null batch array");
   if (b->n_hits && !b->hits) return fail(ctx, THB_EINVAL, "null hits array");
@@ -172,7 +230,9 @@ int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* r
   Flags f; unsigned long long ins_now; *redo = false;
   int rc = read_state(ctx, &f, &ins_now); if (rc) return rc;
   const unsigned long long ins_before = *ins_before_p;      // valid only after the sync above
-  if (f.err & 2u) return fail(ctx, THB_EUNSUPPORTED, "more than %d rescued mate-anchor hits for one read in --bowtie1 mode", RES_MAX);
+  if (f.err & 2u) return fail(ctx, THB_EUNSUPPORTED, "more than %d rescued mate-anchor hits for one read (raise RES_MAX)", RES_MAX);
+  if (f.qovf & 1u) { ctx->cap_win *= 2; *redo = true; }
+  if (f.qovf & 2u) { ctx->cap_indel *= 2; *redo = true; }
   if (f.ovf_juncs) { rc = grow_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs); if (rc) return rc; *redo = true; }
   if (f.ovf_dels) { rc = grow_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels); if (rc) return rc; *redo = true; }
   if ((f.err & 1u) || ins_now > ctx->cap_ins) {
@@ -184,7 +244,7 @@ int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* r
   }
   if (*redo) {
     CU(cudaMemcpyAsync(ctx->d_ins_count, &ins_before, sizeof ins_before, cudaMemcpyHostToDevice, ctx->compute));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->compute));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(unsigned int), ctx->compute));   // err + queue overflow flags
     CU(cudaStreamSynchronize(ctx->compute));
   }
   return THB_OK;
@@ -246,7 +306,10 @@ int thb_create(int device, thb_ctx** out)
   ctx->d_counters = (unsigned long long*)ctx->d_scalars.p;
   ctx->d_ins_count = ctx->d_counters + 8;
   ctx->d_ovf_juncs = (unsigned int*)(ctx->d_counters + 9);
-  ctx->d_ovf_dels = ctx->d_ovf_juncs + 1; ctx->d_err = ctx->d_ovf_juncs + 2;
+  ctx->d_ovf_dels = ctx->d_ovf_juncs + 1; ctx->d_err = ctx->d_ovf_juncs + 2; ctx->d_qovf = ctx->d_ovf_juncs + 3;
+  ctx->d_qcounts = ctx->d_counters + 12;
+  for (auto& e : ctx->kev) cudaEventCreate(&e);
+  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
   cudaMemset(ctx->d_scalars.p, 0, 256);
   thb_params_default(&ctx->params);
   *out = ctx;
@@ -260,7 +323,10 @@ void thb_destroy(thb_ctx* ctx)
   cudaDeviceSynchronize();
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
-                     &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count }) b->release();
+                     &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
+                     &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner,
+                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out }) b->release();
+  for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
@@ -376,24 +442,24 @@ int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* b)
   BatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
   bv.partner = b->partner_hits; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
   bv.order_base = b->order_base;
+  bv.partner_base = 0; bv.hit_base = 0;
   unsigned long long ins_before = 0;
   CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  float ms_total = 0.f;
-  for (int attempt = 0; attempt < 24; ++attempt) {
+  float ms_total = 0.f; bool done = false;
+  for (int attempt = 0; attempt < 24 && !done; ++attempt) {
     unsigned long long cnt0[4];
     CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
-    CU(cudaEventRecord(ctx->ev_a, ctx->compute));
-    rc = launch_scan(ctx, bv); if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+    rc = launch_scan(ctx, bv, b->n_partner_hits, b->n_hits); if (rc) return rc;
     bool redo = false;
     rc = check_and_grow(ctx, &ins_before, &redo); if (rc) return rc;
-    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
-    if (!redo) { ms_total = ms; break; }
+    if (!redo) { collect_kernel_times(ctx, &ms_total); done = true; break; }
+    ctx->kev_pending = false;
     // roll the task counters back so that a repeated scan is not double counted
     CU(cudaMemcpyAsync(ctx->d_counters, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
   }
+  if (!done) return fail(ctx, THB_ENOMEM, "result structures still overflow after 24 growth attempts");
   ctx->timing.scan_kernel_ms += ms_total; ctx->timing.total_ms += ms_total;
   ctx->n_bundles_total += b->n_bundles; ctx->n_hits_total += b->n_hits; ctx->n_partner_total += b->n_partner_hits;
   return THB_OK;
@@ -412,7 +478,6 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
   float kernel_ms = 0.f;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
   const uint32_t nchunks = (b->n_bundles + CH - 1) / CH;
   struct Range { uint32_t b0, nb; uint64_t h0, h1, p0, p1; };
   auto range_of = [&](uint32_t c, Range* r) -> bool {
@@ -444,28 +509,28 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
     BatchView bv; bv.bundles = (const thb_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p;
     bv.reads = (const uint64_t*)s.reads.p; bv.hits = (const thb_hit*)s.hits.p - r.h0; bv.partner = (const thb_hit*)s.partner.p - r.p0;
     bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.order_base = b->order_base + r.b0;
-    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); kev.push_back({e0, e1});
+    bv.partner_base = r.p0; bv.hit_base = r.h0;
     unsigned long long ins_before = 0;
     CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
+    bool done = false;
     for (int attempt = 0; attempt < 24; ++attempt) {
       unsigned long long cnt0[4];
       CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
-      CU(cudaEventRecord(e0, ctx->compute));
-      rc = launch_scan(ctx, bv); if (rc) return rc;
-      CU(cudaEventRecord(e1, ctx->compute));
+      rc = launch_scan(ctx, bv, r.p1 - r.p0, r.h1 - r.h0); if (rc) return rc;
       // the next chunk's copy (other staging buffer, whose kernel already completed) overlaps this scan
       if (attempt == 0 && c + 1 < nchunks) { rc = enqueue_copy(c + 1); if (rc) return rc; }
       bool redo = false;
       rc = check_and_grow(ctx, &ins_before, &redo); if (rc) return rc;      // synchronises the compute stream
-      if (!redo) break;
+      if (!redo) { float ms = 0.f; collect_kernel_times(ctx, &ms); kernel_ms += ms; done = true; break; }
+      ctx->kev_pending = false;
       CU(cudaMemcpyAsync(ctx->d_counters, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, ctx->compute));
       CU(cudaStreamSynchronize(ctx->compute));
     }
+    if (!done) return fail(ctx, THB_ENOMEM, "result structures still overflow after 24 growth attempts");
     CU(cudaEventRecord(s.consumed, ctx->compute)); s.used = true;
   }
   CU(cudaEventRecord(ctx->ev_d, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  for (auto& pr : kev) { float ms = 0.f; cudaEventElapsedTime(&ms, pr.first, pr.second); kernel_ms += ms; cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   float tot = 0.f; CU(cudaEventElapsedTime(&tot, ctx->ev_c, ctx->ev_d));
   ctx->timing.scan_kernel_ms += kernel_ms; ctx->timing.total_ms += tot; ctx->timing.h2d_ms += std::max(0.f, tot - kernel_ms);
   ctx->n_bundles_total += b->n_bundles; ctx->n_hits_total += b->n_hits; ctx->n_partner_total += b->n_partner_hits;
@@ -546,6 +611,107 @@ int thb_last_timing(thb_ctx* ctx, thb_timing* out)
 {
   if (!ctx || !out) return THB_EINVAL;
   *out = ctx->timing;
+  return THB_OK;
+}
+
+
+// ---- long_spanning_reads join -------------------------------------------------------------------------
+int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs, uint64_t n_juncs, const thb_insertion* ins, uint64_t n_ins)
+{
+  if (!ctx || !p) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
+  if (p->fusion_search) return fail(ctx, THB_EUNSUPPORTED, "--fusion-search is not implemented on the GPU join path yet");
+  if (p->segment_length < 4 || p->segment_length > 255) return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside [4,255]", p->segment_length);
+  if (p->max_insertion_length > 19) return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 not supported");
+  if ((n_juncs && !juncs) || (n_ins && !ins) || n_juncs >= (1ull << 31) || n_ins >= (1ull << 31)) return fail(ctx, THB_EINVAL, "bad junction / insertion set");
+  for (uint64_t i = 1; i < n_juncs; ++i) {
+    const thb_junction &a = juncs[i - 1], &b = juncs[i];
+    const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.right != b.right ? a.right < b.right : a.antisense < b.antisense;
+    if (!lt) return fail(ctx, THB_EINVAL, "junction set not sorted / unique at %llu", (unsigned long long)i);
+  }
+  for (uint64_t i = 1; i < n_ins; ++i) {
+    const thb_insertion &a = ins[i - 1], &b = ins[i];
+    const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.len < b.len;
+    if (!lt) return fail(ctx, THB_EINVAL, "insertion set not sorted / unique at %llu", (unsigned long long)i);
+  }
+  CU(ctx->j_juncs.reserve((n_juncs + 1) * sizeof(thb_junction))); CU(ctx->j_ins.reserve((n_ins + 1) * sizeof(thb_insertion)));
+  if (n_juncs) CU(cudaMemcpyAsync(ctx->j_juncs.p, juncs, n_juncs * sizeof(thb_junction), cudaMemcpyHostToDevice, ctx->compute));
+  if (n_ins) CU(cudaMemcpyAsync(ctx->j_ins.p, ins, n_ins * sizeof(thb_insertion), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->j_n_juncs = n_juncs; ctx->j_n_ins = n_ins;
+  JoinParams& j = ctx->jp;
+  j.max_ins = p->max_insertion_length; j.max_del = p->max_deletion_length; j.min_report_intron = p->min_report_intron_length;
+  j.max_report_intron = p->max_report_intron_length; j.fusion_min_dist = p->fusion_min_dist; j.max_seg_multihits = p->max_seg_multihits;
+  j.bowtie2 = p->bowtie2; j.seglen = p->segment_length;
+  ctx->params = *p; ctx->join_begun = true;
+  memset(&ctx->jtiming, 0, sizeof ctx->jtiming);
+  return THB_OK;
+}
+
+int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** out, uint64_t* n_out)
+{
+  if (!ctx || !b || !out || !n_out) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->join_begun) return fail(ctx, THB_ESTATE, "thb_join_begin not called");
+  *out = nullptr; *n_out = 0;
+  if (b->n_bundles == 0) return THB_OK;
+  if (b->n_segs < 1 || b->n_segs > (uint32_t)JMAXSEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, JMAXSEGS);
+  if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4]", b->read_words);
+  if (!b->bundles || !b->seg_count || !b->reads || (b->n_hits && !b->hits)) return fail(ctx, THB_EINVAL, "null batch array");
+  const size_t rdw = (size_t)3 * b->read_words;
+  CU(ctx->j_bundles.reserve((size_t)b->n_bundles * sizeof(thb_join_bundle))); CU(ctx->j_segc.reserve((size_t)b->n_bundles * b->n_segs * 2));
+  CU(ctx->j_reads.reserve((size_t)b->n_bundles * rdw * 8)); CU(ctx->j_hits.reserve((size_t)(b->n_hits + 1) * sizeof(thb_jhit)));
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_bundles.p, b->bundles, (size_t)b->n_bundles * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_segc.p, b->seg_count, (size_t)b->n_bundles * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_reads.p, b->reads, (size_t)b->n_bundles * rdw * 8, cudaMemcpyHostToDevice, ctx->compute));
+  if (b->n_hits) CU(cudaMemcpyAsync(ctx->j_hits.p, b->hits, (size_t)b->n_hits * sizeof(thb_jhit), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+  ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * b->n_bundles, 1u << 16));
+  JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
+  JoinBatchView bv; bv.bundles = (const thb_join_bundle*)ctx->j_bundles.p; bv.seg_count = (const uint16_t*)ctx->j_segc.p; bv.reads = (const uint64_t*)ctx->j_reads.p;
+  bv.hits = (const thb_jhit*)ctx->j_hits.p; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
+  unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f;
+  for (int attempt = 0; attempt < 24; ++attempt) {
+    CU(ctx->j_out.reserve(ctx->j_cap_out * sizeof(thb_joined)));
+    CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
+    CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
+    CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
+    JoinOut o; o.rec = (thb_joined*)ctx->j_out.p; o.cap = ctx->j_cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
+    CU(cudaEventRecord(ctx->kev[0], ctx->compute));
+    chain_join_kernel<<<grid_for(b->n_bundles, 128), 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, o);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->kev[1], ctx->compute));
+    ctx->jtiming.launches++;
+    unsigned int ovf = 0;
+    CU(cudaMemcpyAsync(&n, ctx->d_qcounts, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (!ovf && n <= ctx->j_cap_out) { CU(cudaEventElapsedTime(&kms, ctx->kev[0], ctx->kev[1])); break; }
+    ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out * 2, n + 1024);
+    if (attempt == 23) return fail(ctx, THB_ENOMEM, "joined-hit buffer still overflows");
+  }
+  ctx->h_joined.resize(n);
+  CU(cudaEventRecord(ctx->ev_c, ctx->compute));
+  if (n) CU(cudaMemcpyAsync(ctx->h_joined.data(), ctx->j_out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaEventRecord(ctx->ev_d, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  float h2d = 0.f, d2h = 0.f; cudaEventElapsedTime(&h2d, ctx->ev_a, ctx->ev_b); cudaEventElapsedTime(&d2h, ctx->ev_c, ctx->ev_d);
+  thb_join_timing& t = ctx->jtiming;
+  t.h2d_ms += h2d; t.kernel_ms += kms; t.d2h_ms += d2h; t.n_chains += cnt[0]; t.n_closures += cnt[1]; t.n_joined += cnt[2];
+  // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 48 per segment hit, per closure
+  // 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain, 128 per output record
+  t.algorithmic_bytes += 56ull * b->n_bundles + 48ull * b->n_hits + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
+  *out = ctx->h_joined.data(); *n_out = n;
+  return THB_OK;
+}
+
+int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out)
+{
+  if (!ctx || !out) return THB_EINVAL;
+  *out = ctx->jtiming;
   return THB_OK;
 }
 
