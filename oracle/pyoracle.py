@@ -191,3 +191,85 @@ def format_insertions(i: np.ndarray, names: List[str]) -> str:
     """segment.insertions text (segment_juncs.cpp:5085-5090)."""
     return "".join("%s\t%d\t%d\t%s\n" % (names[int(r["ref_id"]) - 1], np.int32(r["left"]), np.int32(r["left"]),
                                          r["seq"].decode()) for r in i)
+
+
+# ---------------------------------------------------------------------------------------------
+# long_spanning_reads: junction index + spliced segment hits + the reference binary
+
+
+def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: str, nseg: int, max_seg_len: int = 26) -> Dict[str, str]:
+    """juncs_db (reference binary) on the segment_juncs outputs, then synthetic segment hits against its contigs,
+    turned into id-sorted BAMs by the reference's fix_map_ordering (tophat.py:3686-3741)."""
+    fa = os.path.join(outdir, "segment_juncs.fa")
+    with open(fa, "w") as f:
+        subprocess.run([os.path.join(REF_DIR, "juncs_db"), "3", str(max_seg_len), outs["juncs"], outs["insertions"], outs["deletions"],
+                        "/dev/null", files["fasta"]], check=True, stdout=f, stderr=subprocess.DEVNULL)
+    contigs = synth.parse_juncs_db_fasta(fa)
+    hdr = os.path.join(outdir, "segment_juncs.hdr.sam")
+    synth.write_contig_header(hdr, contigs)
+    j = {"juncs_fa": fa, "juncs_header": hdr, "n_contigs": len(contigs)}
+    for sname, side in (("left", wl.left), ("right", wl.right)):
+        per_seg = synth.spliced_segment_hits(wl, side, contigs)
+        for k in range(nseg):
+            sam = os.path.join(outdir, "%s_seg%d.to_spliced.sam" % (sname, k + 1))
+            synth.write_spliced_sam(sam, wl.cfg, k, per_seg[k])
+            bam = os.path.join(outdir, "%s_kept_reads_seg%d.to_spliced.bam" % (sname, k + 1))
+            subprocess.run([os.path.join(REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile", bam + ".index", sam, bam],
+                           check=True, stderr=subprocess.DEVNULL)
+            j["%s_spl%d" % (sname, k + 1)] = bam
+        j["%s_n_spliced" % sname] = sum(len(x) for x in per_seg)
+    return j
+
+
+def run_long_spanning_reads(binary: str, files: Dict[str, str], bams: Dict[str, str], jin: Dict[str, str], outs: Dict[str, str], outdir: str,
+                            nseg: int, side: str = "left", opts: Optional[List[str]] = None, tag: str = "", env: Optional[dict] = None,
+                            with_spliced: bool = True) -> str:
+    out_bam = os.path.join(outdir, "%s_candidates%s.bam" % (side, tag))
+    cmd = [binary] + (opts if opts is not None else tophat_common_opts()) + \
+          ["-p1", "--sam-header", files["header"], "--bowtie2-max-penalty", "6", "--bowtie2-min-penalty", "2", "--bowtie2-penalty-for-N", "1",
+           "--bowtie2-read-gap-open", "5", "--bowtie2-read-gap-cont", "3", "--bowtie2-ref-gap-open", "5", "--bowtie2-ref-gap-cont", "3",
+           files["fasta"], bams[side + "_reads"], outs["juncs"], outs["insertions"], outs["deletions"], "/dev/null", out_bam,
+           ",".join(bams["%s_seg%d" % (side, k + 1)] for k in range(nseg))]
+    if with_spliced:
+        cmd.append(",".join(jin["%s_spl%d" % (side, k + 1)] for k in range(nseg)))
+    with open(os.path.join(outdir, "long_spanning_reads%s.%s.log" % (tag, side)), "w") as lf:
+        subprocess.run(cmd, check=True, stderr=lf, env=env)
+    return out_bam
+
+
+def read_bam(path: str):
+    """Decoded BAM records (BGZF is multi-member gzip): (qname, flag, tid, pos, mapq, cigar, seq, qual, mtid, mpos, tlen, aux dict)."""
+    import gzip
+    import struct
+    data = gzip.open(path, "rb").read()
+    assert data[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    off = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, off)[0]; off += 4
+    refs = []
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", data, off)[0]; off += 4
+        refs.append(data[off:off + ln - 1].decode()); off += ln + 4
+    recs = []
+    while off < len(data):
+        bs = struct.unpack_from("<i", data, off)[0]; p = off + 4; off = p + bs
+        tid, pos, l_qn, mapq, _bin, n_cig, flag, l_seq, mtid, mpos, tlen = struct.unpack_from("<iiBBHHHiiii", data, p)
+        q = p + 32
+        qname = data[q:q + l_qn - 1].decode(); q += l_qn
+        cig = "".join("%d%s" % (c >> 4, "MIDNSHP=X"[c & 15]) for c in struct.unpack_from("<%dI" % n_cig, data, q)); q += 4 * n_cig
+        sb = data[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
+        seq = "".join("=ACMGRSVTWYHKDBN"[(sb[i >> 1] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq))
+        qual = bytes(data[q:q + l_seq]); q += l_seq
+        aux = {}
+        while q < off:
+            tag = data[q:q + 2].decode(); t = chr(data[q + 2]); q += 3
+            if t == "A": aux[tag] = chr(data[q]); q += 1
+            elif t in "cCsSiI":
+                fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}[t]
+                aux[tag] = struct.unpack_from(fmt, data, q)[0]; q += struct.calcsize(fmt)
+            elif t == "Z":
+                e = data.index(b"\x00", q); aux[tag] = data[q:e].decode(); q = e + 1
+            else:
+                raise ValueError("aux type %s" % t)
+        recs.append((qname, flag, refs[tid] if tid >= 0 else "*", pos, mapq, cig, seq, qual, mtid, mpos, tlen, aux))
+    return refs, recs

@@ -1,0 +1,55 @@
+"""Drop-in boundary test of long_spanning_reads: our executable (C++ host + chain-join kernel) against the reference's
+own binary on identical inputs -- segment BAMs, junction-index segment BAMs built from the reference's juncs_db output,
+and the segment.juncs/insertions/deletions of segment_juncs.  BAM byte identity is not meaningful (zlib); the decoded
+records must be identical, in the same order."""
+import os
+import tempfile
+
+import pytest
+
+from tophat_b200 import build, synth
+from oracle import pyoracle
+
+OUR_BIN = os.path.join(build.BIN_DIR, "long_spanning_reads")
+
+
+def test_host_binary_builds():
+    build.build_library()
+    outs = build.build_host_binaries()
+    assert OUR_BIN in outs and os.access(OUR_BIN, os.X_OK)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("kw,spliced", [
+    (dict(contig_lens=(300_000, 120_000), n_pairs=3000, seed=401), True),
+    (dict(contig_lens=(300_000,), n_pairs=3000, seed=402, indel_prob=0.5), True),
+    (dict(contig_lens=(250_000,), n_pairs=2500, seed=403, indel_prob=0.2, decoy_rate=2.0, sub_rate=0.01), True),
+    (dict(contig_lens=(250_000,), n_pairs=2000, seed=404), False),
+    (dict(contig_lens=(250_000,), n_pairs=2000, seed=405, read_len=75, indel_prob=0.3), True),
+    (dict(contig_lens=(250_000,), n_pairs=1500, seed=406, read_len=150, indel_prob=0.3, n_rate=0.004), True),
+])
+def test_cli_matches_reference_binary(kw, spliced):
+    build.build_all()
+    with tempfile.TemporaryDirectory() as td:
+        wl = synth.generate(synth.SynthConfig(keep_truth=True, **kw))
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg)
+        jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg, max_seg_len=int(max(synth.segment_layout(wl.cfg.read_len, wl.cfg.segment_length)[1])))
+        total = 0
+        for side in ("left", "right"):
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=side, tag=".ref", with_spliced=spliced)
+            our_bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, bams, jin, outs, td, nseg, side=side, tag=".b200", with_spliced=spliced)
+            refs_a, a = pyoracle.read_bam(our_bam)
+            refs_b, b = pyoracle.read_bam(ref_bam)
+            assert refs_a == refs_b
+            assert len(a) == len(b), "%s: %d records vs %d in the reference output" % (side, len(a), len(b))
+            for x, y in zip(a, b):
+                assert x == y, "record differs:\n ours %r\n ref  %r" % (x, y)
+            total += len(b)
+        assert total > 200
+        if spliced:
+            assert jin["left_n_spliced"] + jin["right_n_spliced"] > 100

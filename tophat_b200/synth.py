@@ -157,6 +157,7 @@ class SynthConfig:
     fusion_frac: float = 0.0           # fraction of fragments that are chimeric (config 5 style)
     chunk: int = 500_000
     chunk_seed_base: int = 0           # added to the chunk index in the RNG stream id (per-rank shards)
+    keep_truth: bool = False           # keep the per-base genomic origin of every read (needed to place spliced segment hits)
 
 
 @dataclasses.dataclass
@@ -167,6 +168,8 @@ class SideData:
     seg_hits: List[np.ndarray]          # per segment: structured array (read_idx + HIT fields)
     mapped_hits: np.ndarray             # full-read hits (the *.mapped.bam stream)
     unmapped: np.ndarray                # bool (n,): read went to segment mapping
+    truth: Optional[dict] = None        # keep_truth: fwd (n,L) codes in genome orientation, gpos (n,L) genomic position of
+                                        # every base (-1 = inserted), ref_id (n,), rev (n,) read is the reverse complement of fwd
 
 
 SEGHIT_DTYPE = np.dtype([("read_idx", "<u4"), ("ref_id", "<u4"), ("left", "<i4"), ("right", "<i4"),
@@ -374,7 +377,7 @@ def _gen_chunk(ci: int):
     nseg = offs.shape[0]
     done = ci * cfg.chunk
     n = min(cfg.chunk, cfg.n_pairs - done)
-    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[]) for s in ("left", "right")}
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[]) for s in ("left", "right")}
     a0, b0, plus = _sample_mates(rng, cfg, space, contigs, n)
     for which, x0 in (("A", a0), ("B", b0)):
         codes_fwd, emap = _make_read_fwd(rng, cfg, space, exonic, x0)
@@ -405,6 +408,11 @@ def _gen_chunk(ci: int):
             mh["flags"] = (HIT_ANTISENSE if rev else 0) | HIT_END
             A["mapped"].append(mh)
             A["unm"].append((sel + base, ~mapped[sel]))
+            if cfg.keep_truth:
+                ok = emap[sel] >= 0
+                rid_t, gpos_t, _ = space.to_genome(np.where(ok, emap[sel], 0))
+                gpos_t = np.where(ok, gpos_t, -1)
+                A["truth"].append((sel + base, codes_fwd[sel], gpos_t, rid_t[:, 0], np.full(sel.size, rev)))
         # segment hits for reads that did not map end to end
         for k in range(nseg):
             # segment k of the *sequenced* read covers, in forward orientation:
@@ -480,10 +488,11 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
     else:
         chunk_accs = [_gen_chunk(c) for c in range(nchunks)]
     _GEN_STATE.clear()
-    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[]) for s in ("left", "right")}
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[]) for s in ("left", "right")}
     for ca in chunk_accs:
         for s in acc:
             acc[s]["reads"] += ca[s]["reads"]; acc[s]["mapped"] += ca[s]["mapped"]; acc[s]["unm"] += ca[s]["unm"]
+            acc[s]["truth"] += ca[s]["truth"]
             for k in range(nseg):
                 acc[s]["seg"][k] += ca[s]["seg"][k]
     del chunk_accs
@@ -512,7 +521,13 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
         mh = np.concatenate(A["mapped"]) if A["mapped"] else np.zeros(0, dtype=SEGHIT_DTYPE)
         mh = mh[~qc_fail[mh["read_idx"]]]
         mh = mh[np.argsort(mh["read_idx"], kind="stable")]
-        return SideData(reads, np.arange(1, cfg.n_pairs + 1, dtype="<u4"), seg_hits, mh, unm)
+        truth = None
+        if cfg.keep_truth:
+            truth = dict(fwd=np.zeros((cfg.n_pairs, L), np.uint8), gpos=np.full((cfg.n_pairs, L), -1, np.int64),
+                         ref_id=np.zeros(cfg.n_pairs, np.int64), rev=np.zeros(cfg.n_pairs, bool), qc_fail=qc_fail)
+            for idx, f, gp, rid, rv in A["truth"]:
+                truth["fwd"][idx] = f; truth["gpos"][idx] = gp; truth["ref_id"][idx] = rid; truth["rev"][idx] = rv
+        return SideData(reads, np.arange(1, cfg.n_pairs + 1, dtype="<u4"), seg_hits, mh, unm, truth)
 
     introns = np.concatenate(anns) if anns else np.zeros(0)
     return Workload(cfg, ref, finish("left"), finish("right"), introns)
@@ -521,8 +536,9 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
 def subset(wl: Workload, n_pairs: int) -> Workload:
     """The first n_pairs fragments of a workload (same reference): a bounded sample for the CPU baseline."""
     def cut(sd: SideData) -> SideData:
+        tr = None if sd.truth is None else {k: v[:n_pairs] for k, v in sd.truth.items()}
         return SideData(sd.reads[:n_pairs], sd.ids[:n_pairs], [h[h["read_idx"] < n_pairs] for h in sd.seg_hits],
-                        sd.mapped_hits[sd.mapped_hits["read_idx"] < n_pairs], sd.unmapped[:n_pairs])
+                        sd.mapped_hits[sd.mapped_hits["read_idx"] < n_pairs], sd.unmapped[:n_pairs], tr)
     cfg = dataclasses.replace(wl.cfg, n_pairs=n_pairs)
     return Workload(cfg, wl.ref, cut(wl.left), cut(wl.right), wl.introns)
 
@@ -730,3 +746,109 @@ def write_pipeline_files(wl: Workload, outdir: str) -> Dict[str, str]:
             p[key] = os.path.join(outdir, "%s_seg%d.sam" % (sname, k + 1))
             write_hits_sam(p[key], wl, side, side.seg_hits[k], k)
     return p
+
+
+# ---------------------------------------------------------------------------------------------
+# long_spanning_reads inputs: segment hits against the juncs_db contigs
+
+
+def parse_juncs_db_fasta(path: str):
+    """juncs_db output (juncs_db.cpp:109-149): >ref|left_start|L-R|right_end|<type>|<strand>  ->  list of
+    (name, ref, left_start, L, R, type, seq)."""
+    out = []
+    name = None
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                name = line[1:]
+            elif name is not None:
+                t = name.split("|")
+                if len(t) >= 6 and "-" in t[-4]:
+                    lr = t[-4].split("-")
+                    try:
+                        out.append((name, "|".join(t[:-5]), int(t[-5]), int(lr[0]), int(lr[1]) if lr[1].isdigit() else lr[1], t[-2], line))
+                    except ValueError:
+                        pass
+                name = None
+    return out
+
+
+def spliced_segment_hits(wl: Workload, side: SideData, contigs, max_mm: int = 2):
+    """For every segment of every unmapped read that crosses exactly one junction for which juncs_db made an intron
+    contig, the ungapped placement on that contig (what bowtie reports against the junction index), kept when it has
+    <= max_mm mismatches.  Returns per segment a list of dict(read_idx, contig, pos0, anti, fwd codes, nm, md)."""
+    assert side.truth is not None, "generate the workload with keep_truth=True"
+    cfg = wl.cfg
+    L = cfg.read_len
+    offs, lens = segment_layout(L, cfg.segment_length)
+    nseg = offs.shape[0]
+    key = {}
+    for (name, ref, left_start, jl, jr, typ, seq) in contigs:
+        if typ in ("ins", "del", "fus") or not isinstance(jr, int):
+            continue
+        key[(ref, jl, jr)] = (name, left_start, seq)
+    names = wl.ref.names
+    tr = side.truth
+    out = [[] for _ in range(nseg)]
+    cand = np.nonzero(side.unmapped & ~tr["qc_fail"])[0]
+    gpos = tr["gpos"]; fwd = tr["fwd"]
+    for ri in cand:
+        g = gpos[ri]
+        jumps = np.nonzero((g[1:] - g[:-1] > 1) & (g[1:] >= 0) & (g[:-1] >= 0))[0]
+        if jumps.size == 0:
+            continue
+        rev = bool(tr["rev"][ri])
+        ref = names[int(tr["ref_id"][ri]) - 1]
+        for k in range(nseg):
+            lo = int(L - offs[k] - lens[k]) if rev else int(offs[k]); ln = int(lens[k])
+            inside = jumps[(jumps >= lo) & (jumps < lo + ln - 1)]
+            if inside.size != 1:
+                continue
+            j = int(inside[0])
+            if (g[lo:lo + ln] < 0).any():
+                continue
+            ent = key.get((ref, int(g[j]), int(g[j + 1])))
+            if ent is None:
+                continue
+            name, left_start, cseq = ent
+            x = j - lo + 1                                   # bases on the left exon
+            pos0 = (int(g[j]) - left_start + 1) - x
+            if pos0 < 0 or pos0 + ln > len(cseq):
+                continue
+            cc = codes_from_ascii(cseq[pos0:pos0 + ln].encode())
+            seg = fwd[ri, lo:lo + ln]
+            mm = (seg != cc) | (seg > 3) | (cc > 3)
+            nm = int(mm.sum())
+            if nm > max_mm:
+                continue
+            md, run = [], 0
+            for q in range(ln):
+                if mm[q]:
+                    md.append(str(run)); md.append(chr(CODE2CHAR[min(int(cc[q]), 4)])); run = 0
+                else:
+                    run += 1
+            md.append(str(run))
+            out[k].append(dict(read_idx=int(ri), contig=name, pos0=pos0, anti=rev, fwd=seg, nm=nm, md="".join(md)))
+    return out
+
+
+def write_spliced_sam(path: str, cfg: SynthConfig, seg_index: int, hits) -> None:
+    offs, lens = segment_layout(cfg.read_len, cfg.segment_length)
+    nseg = offs.shape[0]
+    with open(path, "w") as f:
+        for h in sorted(hits, key=lambda d: d["read_idx"]):
+            o = int(offs[seg_index])
+            qn = "%d|%d:%d:%d" % (h["read_idx"] + 1, o, seg_index, nseg)
+            ln = h["fwd"].shape[0]
+            f.write("%s\t%d\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:UU\n" % (
+                qn, 16 if h["anti"] else 0, h["contig"], h["pos0"] + 1, ln, CODE2CHAR[h["fwd"]].tobytes().decode(), "I" * ln,
+                -6 * h["nm"], h["nm"], h["nm"], h["md"]))
+
+
+def write_contig_header(path: str, contigs) -> None:
+    with open(path, "w") as f:
+        f.write("@HD\tVN:1.0\tSO:unsorted\n")
+        for c in contigs:
+            f.write("@SQ\tSN:%s\tLN:%d\n" % (c[0], len(c[6])))
+        f.write("@PG\tID:TopHat\tVN:2.1.2\n")
