@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
 
-One "step" = one pass of the hot path (thb_segjuncs_begin -> submit(left mates) -> submit(right mates)
--> [N>1: NCCL all-gather of the discovered sets] -> thb_segjuncs_finish) over one batch of synthetic
-2x101 bp read pairs.  Workload at N=1: BASELINE.json configs[1] (10 M pairs, chr20-sized reference).  For
+One "step" = one pass of the hot path over one batch of synthetic 2x101 bp read pairs:
+  stage 1 segment_juncs       thb_segjuncs_begin -> submit(left mates) -> submit(right mates) -> [N>1: NCCL all-gather
+                              of the discovered sets] -> thb_segjuncs_finish
+  stage 2 long_spanning_reads thb_join_begin(junction / indel sets) -> join(left mates) -> join(right mates)  Workload at N=1: BASELINE.json configs[1] (10 M pairs, chr20-sized reference).  For
 N>1 every rank runs the same number of pairs (its own shard of reads, same reference): weak scaling.
 
   value  : reads (mates) per second, whole job, inputs resident in HBM (CUDA events on the library's stream)
@@ -34,7 +35,7 @@ import numpy as np
 
 CHR20 = 64_444_167
 KERNELS = ("bundle", "hit", "rescue", "rescued_windows", "window_scan", "indel")
-METRIC = "spliced reads processed/s (segment_juncs junction+indel discovery), 2x101bp"
+METRIC = "spliced reads aligned/s (segment_juncs + long_spanning_reads), 2x101bp"
 UNIT = "reads/s"
 
 
@@ -46,12 +47,12 @@ def log(*a):
 # workload
 
 
-def make_workload(pairs: int, rank: int, workers: int):
+def make_workload(pairs: int, rank: int, workers: int, keep_candidates: bool = False, keep_truth: bool = False):
     from tophat_b200 import synth
     chunk = 500_000 if pairs >= 500_000 else max(1000, pairs)
     nchunks = (pairs + chunk - 1) // chunk
     cfg = synth.SynthConfig(contig_lens=(CHR20,), n_pairs=pairs, seed=20240611, chunk=chunk,
-                            chunk_seed_base=rank * nchunks)
+                            chunk_seed_base=rank * nchunks, keep_candidates=keep_candidates, keep_truth=keep_truth)
     t = time.time()
     wl = synth.generate(cfg, workers=workers)
     log("[bench] rank %d: generated %d pairs in %.1f s (%d workers)" % (rank, pairs, time.time() - t, workers))
@@ -72,7 +73,9 @@ def pack(wl):
 
 
 class ReferenceArm:
-    """Prepares BAM/FASTA inputs for a sample of the workload and times the reference's segment_juncs."""
+    """Prepares BAM/FASTA inputs for a sample workload (generated with keep_truth) and times the reference's own
+    segment_juncs followed by long_spanning_reads for both mates (juncs_db + the junction-index segment mapping that
+    tophat.py runs in between are set-up, not timed, exactly as they are outside the GPU arm's timed region)."""
 
     def __init__(self, wl, sample_pairs: int, threads: int):
         from tophat_b200 import synth
@@ -85,30 +88,36 @@ class ReferenceArm:
         base = "/dev/shm" if os.path.isdir("/dev/shm") else None
         self.dir = tempfile.mkdtemp(prefix="thb_ref_", dir=base)
         t = time.time()
-        sub = synth.subset(wl, self.sample_pairs)
+        sub = synth.subset(wl, self.sample_pairs) if self.sample_pairs < wl.cfg.n_pairs else wl
         self.nseg = len(sub.left.seg_hits)
         self.files = synth.write_pipeline_files(sub, self.dir)
         self.bams = pyoracle.make_bams(self.files, self.dir, self.nseg)
-        # a 1-pair input measures the fixed start-up (FASTA load of the same reference)
+        self.opts = pyoracle.tophat_common_opts(50, 20)
+        self.sj = os.path.join(pyoracle.REF_DIR, "segment_juncs"); self.lsr = os.path.join(pyoracle.REF_DIR, "long_spanning_reads")
+        self.outs = pyoracle.run_segment_juncs(self.sj, self.files, self.bams, self.dir, self.nseg, opts=self.opts, threads=threads)
+        self.jin = pyoracle.make_join_inputs(sub, self.files, self.outs, self.dir, self.nseg, fast=True)
+        # a 1-pair input measures the fixed start-up (FASTA load of the same reference) of every binary run
         tiny = synth.subset(wl, 1)
         self.tdir = os.path.join(self.dir, "tiny"); os.makedirs(self.tdir)
         tf = synth.write_pipeline_files(tiny, self.tdir)
         tf["fasta"] = self.files["fasta"]; tf["header"] = self.files["header"]
         self.tfiles, self.tbams = tf, pyoracle.make_bams(tf, self.tdir, self.nseg)
+        self.touts = pyoracle.run_segment_juncs(self.sj, self.tfiles, self.tbams, self.tdir, self.nseg, opts=self.opts)
+        self.tjin = pyoracle.make_join_inputs(tiny, self.tfiles, self.touts, self.tdir, self.nseg, fast=True)
         log("[bench] reference arm inputs for %d pairs ready in %.1f s" % (self.sample_pairs, time.time() - t))
 
-    def _run(self, files, bams, outdir, threads):
-        opts = self.py.tophat_common_opts(50, 20)
+    def _run(self, files, bams, jin, outdir, threads):
         t = time.perf_counter()
-        outs = self.py.run_segment_juncs(os.path.join(self.py.REF_DIR, "segment_juncs"), files, bams, outdir, self.nseg,
-                                         opts=opts, threads=threads)
-        return time.perf_counter() - t, outs
+        outs = self.py.run_segment_juncs(self.sj, files, bams, outdir, self.nseg, opts=self.opts, threads=threads)
+        for side in ("left", "right"):
+            self.py.run_long_spanning_reads(self.lsr, files, bams, jin, outs, outdir, self.nseg, side=side, opts=self.opts, threads=threads)
+        return time.perf_counter() - t
 
     def startup(self) -> float:
-        return min(self._run(self.tfiles, self.tbams, self.tdir, 1)[0] for _ in range(2))
+        return min(self._run(self.tfiles, self.tbams, self.tjin, self.tdir, 1) for _ in range(2))
 
     def step(self) -> float:
-        return self._run(self.files, self.bams, self.dir, self.threads)[0]
+        return self._run(self.files, self.bams, self.jin, self.dir, self.threads)
 
     def close(self):
         shutil.rmtree(self.dir, ignore_errors=True)
@@ -124,7 +133,7 @@ def usable_threads(sample_pairs: int) -> int:
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
-    wl = make_workload(args.ref_pairs, 0, max(1, (os.cpu_count() or 1)))
+    wl = make_workload(args.ref_pairs, 0, max(1, (os.cpu_count() or 1)), keep_truth=True)
     threads = usable_threads(args.ref_pairs)
     arm = ReferenceArm(wl, args.ref_pairs, threads)
     try:
@@ -144,7 +153,7 @@ def run_reference_arm(args, rank: int, world: int):
             "config": workload_config(args.ref_pairs, 1, note="bounded sample of the GPU arm's workload; value excludes the "
                                       "%.2f s fixed start-up (FASTA load) measured on a 1-pair input" % st),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": "%d pairs (%d reads), oracle/_ref/segment_juncs -p%d, wall %.2f s/step incl. %.2f s start-up"
+                             "sample": "%d pairs (%d reads), oracle/_ref segment_juncs + long_spanning_reads (left, right) -p%d, wall %.2f s/step incl. %.2f s start-up"
                                        % (arm.sample_pairs, reads, threads, per, st)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -154,7 +163,7 @@ def run_reference_arm(args, rank: int, world: int):
 def workload_config(pairs: int, world: int, note: str = ""):
     c = {"workload": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, "
                      "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
-         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stage": "segment_juncs (junction / indel discovery)",
+         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)",
          "l2": "inputs (>1 GB per step at the default size) exceed the 126 MB L2; no explicit flush",
          "parallelism": "read-shard x%d%s" % (world, " + NCCL all-gather of the junction/indel sets" if world > 1 else "")}
     if note:
@@ -212,14 +221,15 @@ class ClockSampler:
 
 
 def run_gpu_arm(args, rank: int, local_rank: int, world: int):
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from tophat_b200 import capi
+    from tophat_b200 import capi, synth
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     workers = max(1, (os.cpu_count() or 1) // world)
-    wl = make_workload(args.pairs, rank, workers)
+    wl = make_workload(args.pairs, rank, workers, keep_candidates=True)
     batches = pack(wl)
     n_reads = 2 * args.pairs
     P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
@@ -233,59 +243,77 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
-    # device-resident copies (value) and pinned host copies (e2e)
-    fields = ("bundles", "seg_count", "reads", "hits", "partner_hits")
-    dev, dev_structs, pinned = [], [], []
-    for b in batches:
-        t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k)).view(np.uint8).reshape(-1)) for k in fields}
-        d = {k: v.cuda() for k, v in t.items()}
-        dev.append(d)
-        bc = capi.batch_c(b)
-        bc.bundles, bc.seg_count, bc.reads = d["bundles"].data_ptr(), d["seg_count"].data_ptr(), d["reads"].data_ptr()
-        bc.hits, bc.partner_hits = d["hits"].data_ptr(), d["partner_hits"].data_ptr()
-        dev_structs.append(bc)
-        pt = {k: v.pin_memory() for k, v in t.items()}
-        pinned.append(pt)
-    torch.cuda.synchronize()
+    def stage(batch_list, fields, to_struct):
+        """device-resident copies (value) and pinned host copies (e2e) of packed batches + their C structs"""
+        keep, dev_s, host_s = [], [], []
+        for b in batch_list:
+            t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k)).view(np.uint8).reshape(-1)) for k in fields}
+            d = {k: v.cuda() for k, v in t.items()}
+            pt = {k: v.pin_memory() for k, v in t.items()}
+            keep.append((d, pt))
+            for src, dst in ((d, dev_s), (pt, host_s)):
+                bc = to_struct(b)
+                for k in fields:
+                    setattr(bc, k, src[k].data_ptr())
+                dst.append(bc)
+        torch.cuda.synchronize()
+        return keep, dev_s, host_s
 
-    def pinned_struct(i):
-        bc = capi.batch_c(batches[i]); pt = pinned[i]
-        bc.bundles, bc.seg_count, bc.reads = pt["bundles"].data_ptr(), pt["seg_count"].data_ptr(), pt["reads"].data_ptr()
-        bc.hits, bc.partner_hits = pt["hits"].data_ptr(), pt["partner_hits"].data_ptr()
-        return bc
-    host_structs = [pinned_struct(i) for i in range(len(batches))]
-    h2d_bytes = sum(b.nbytes() for b in batches)
+    sj_fields = ("bundles", "seg_count", "reads", "hits", "partner_hits")
+    sj_keep, sj_dev, sj_host = stage(batches, sj_fields, capi.batch_c)
 
-    import ctypes as C
-
-    def step(device_resident: bool):
+    def segjuncs_pass(device_resident: bool):
         ctx.segjuncs_begin(P)
         for i in range(len(batches)):
             if device_resident:
-                ctx.segjuncs_submit_device(dev_structs[i])
+                ctx.segjuncs_submit_device(sj_dev[i])
             else:
-                ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(host_structs[i])), "thb_segjuncs_submit")
+                ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit")
         if world > 1:
             ctx.segjuncs_allgather()
         res = ctx.segjuncs_finish()
         return res, ctx.timing()
 
+    # stage 2 inputs: the junction-index segment hits depend on the junction set stage 1 finds (tophat.py:3686-3741 runs
+    # juncs_db + bowtie in between); they are derived once from a set-up pass and reused by every timed step
+    t0 = time.time()
+    res0, _ = segjuncs_pass(True)
+    jsets = capi.join_sets_from_results(res0)
+    jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
+    log("[bench] rank %d: join batches %d + %d reads, %d segment hits (%.1f s)" % (
+        rank, jbatches[0].n_bundles, jbatches[1].n_bundles, sum(int(b.hits.shape[0]) for b in jbatches), time.time() - t0))
+    j_fields = ("bundles", "seg_count", "reads", "hits")
+    j_keep, j_dev, j_host = stage(jbatches, j_fields, capi.join_batch_c)
+    h2d_bytes = sum(b.nbytes() for b in batches) + sum(b.nbytes() for b in jbatches) + int(jsets[0].nbytes + jsets[1].nbytes)
+
+    def step(device_resident: bool):
+        res, tm = segjuncs_pass(device_resident)
+        ctx.join_begin(P, jsets[0], jsets[1])
+        n_joined, d2h = 0, 0
+        for i in range(len(jbatches)):
+            if device_resident:
+                n_joined += ctx.join_submit_device(j_dev[i])
+            else:
+                out = C.c_void_p(); n = C.c_uint64()
+                ctx._check(ctx.lib.thb_join_submit(ctx.h, C.byref(j_host[i]), C.byref(out), C.byref(n)), "thb_join_submit")
+                n_joined += int(n.value); d2h += int(n.value) * 128
+        return res, tm, ctx.join_timing(), n_joined, d2h
+
     def timed(device_resident: bool, steps: int, warmup: int):
         for _ in range(warmup):
-            res, tm = step(device_resident)
+            step(device_resident)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        scan_ms, alg, launches = 0.0, 0, 0
-        kms = {k: 0.0 for k in KERNELS}
+        acc = dict(scan_ms=0.0, alg=0, launches=0, join_ms=0.0, join_alg=0, join_launches=0, kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
         for _ in range(steps):
-            res, tm = step(device_resident)
-            scan_ms += tm.scan_kernel_ms; alg += tm.algorithmic_bytes; launches += tm.total_launches
-            scan_launches = tm.kernel_launches
+            res, tm, jt, n_joined, d2h = step(device_resident)
+            acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
+            acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
             for k in KERNELS:
-                kms[k] += getattr(tm, k + "_ms")
+                acc["kms"][k] += getattr(tm, k + "_ms")
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -295,23 +323,26 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, scan_ms, alg, launches, scan_launches, res, tm, kms
+        acc.update(ms=ms, res=res, tm=tm, jt=jt, n_joined=n_joined, d2h=d2h, scan_launches=tm.kernel_launches)
+        return acc
 
     clk = ClockSampler(local_rank)
     if rank == 0:
         clk.start()
-    ms, scan_ms, alg, launches, scan_launches, res, tm, kms = timed(True, args.steps, args.warmup)
-    ms_e2e, _, _, _, _, res_h, _, _ = timed(False, args.steps, args.warmup)
+    A = timed(True, args.steps, args.warmup)
+    E = timed(False, args.steps, args.warmup)
     clocks = clk.stop() if rank == 0 else None
-    d2h_bytes = int(res_h.junctions.nbytes + res_h.deletions.nbytes + res_h.insertions.nbytes + res_h.fusions.nbytes)
+    res, res_h, tm = A["res"], E["res"], A["tm"]
+    d2h_bytes = int(res_h.junctions.nbytes + res_h.deletions.nbytes + res_h.insertions.nbytes + res_h.fusions.nbytes) + E["d2h"]
 
-    # the two arms must agree with each other (same sets from device-resident and host submission)
+    # the two arms must agree with each other (same sets / same number of alignments from device-resident and host submission)
     assert res.junctions.shape == res_h.junctions.shape and (res.junctions == res_h.junctions).all()
+    assert A["n_joined"] == E["n_joined"]
 
     total_reads = n_reads * world
-    per_step = ms / args.steps
+    per_step = A["ms"] / args.steps
     value = total_reads / (per_step * 1e-3)
-    e2e_val = total_reads / (ms_e2e / args.steps * 1e-3)
+    e2e_val = total_reads / (E["ms"] / args.steps * 1e-3)
 
     line = None
     if rank == 0:
@@ -321,23 +352,26 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             peaks, peak_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-        # Per-kernel split of SURVEY.md 8(d)'s B_segjuncs, on this run's actual task counts:
+        # Per-kernel split of SURVEY.md 8(d)'s B_segjuncs / B_join, on this run's actual task counts:
         #   bundle      : 16 (bundle header) per bundle + 16 per partner hit
         #   hit         : 40 (read) per bundle + 16 per segment hit
         #   window_scan : 32 (descriptor) + 64 (two reference sectors) per window + 16 per emitted junction record
         #   rescue      : 32 + 128 per mate-anchor task;  indel: 32 + 64 per task + 16 per record
+        #   chain_join  : 56 per read + 48 per segment hit + 128 per closure + 96 per merged chain + 128 per output record
         n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
         n_hh = sum(int(b.hits.shape[0]) for b in batches)
-        kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh, "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted),
-                  "rescue": 160 * int(tm.n_rescue_tasks), "rescued_windows": 0,
-                  "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions))}
-        dom = max(KERNELS, key=lambda k: kms[k])
-        n_launch = max(1, args.steps * scan_launches)
-        dom_ms = kms[dom] / n_launch
-        dom_bytes = kbytes[dom] / max(1, scan_launches)
+        steps = args.steps
+        kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh,
+                  "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
+                  "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions)),
+                  "chain_join": A["join_alg"] / steps}
+        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_join"] = A["join_ms"] / steps
+        klaunch = {k: A["scan_launches"] for k in KERNELS}; klaunch["chain_join"] = max(1, A["join_launches"] // steps)
+        allk = KERNELS + ("chain_join",)
+        dom = max(allk, key=lambda k: kms[k])
+        dom_ms = kms[dom] / klaunch[dom]; dom_bytes = kbytes[dom] / klaunch[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        phase_ms = scan_ms / n_launch
-        phase_bytes = alg / n_launch
+        tot_ms = sum(kms.values()); tot_bytes = A["alg"] / steps + A["join_alg"] / steps
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -350,38 +384,41 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(args.pairs, world),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": ms_e2e / args.steps, "api": "thb_segjuncs_begin/submit(host, pinned)/finish"},
-                "gpu_launches": int(launches),
+                        "ms_per_step": E["ms"] / args.steps,
+                        "api": "thb_segjuncs_begin/submit(host, pinned)/finish + thb_join_begin/submit(host, pinned)"},
+                "gpu_launches": int(A["launches"]),
                 "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
                              "frac": achieved / peaks, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
-                             "launches_per_step": scan_launches,
-                             "per_kernel_ms_per_launch": {k: kms[k] / n_launch for k in KERNELS},
-                             "per_kernel_gbs": {k: (kbytes[k] / max(1, scan_launches)) / (kms[k] / n_launch * 1e-3) / 1e9 if kms[k] > 0 else 0.0
-                                                for k in KERNELS},
-                             "phase": {"kernels": "bundle+hit+rescue+rescued_windows+window_scan+indel", "ms_per_launch": phase_ms,
-                                       "algorithmic_bytes_per_launch": phase_bytes,
-                                       "achieved": phase_bytes / (phase_ms * 1e-3) / 1e9 if phase_ms > 0 else 0.0,
-                                       "frac": (phase_bytes / (phase_ms * 1e-3) / 1e9 / peaks) if phase_ms > 0 else 0.0}},
+                             "launches_per_step": klaunch[dom],
+                             "per_kernel_ms_per_step": kms,
+                             "per_kernel_gbs": {k: (kbytes[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0) for k in allk},
+                             "all_kernels": {"ms_per_step": tot_ms, "algorithmic_bytes_per_step": tot_bytes,
+                                             "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
+                                             "frac": (tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks) if tot_ms > 0 else 0.0}},
                 "clocks": clocks,
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
-                            "indel_tasks": int(tm.n_indel_tasks), "rescue_tasks": int(tm.n_rescue_tasks)}}
+                            "indel_tasks": int(tm.n_indel_tasks), "rescue_tasks": int(tm.n_rescue_tasks),
+                            "join_reads": int(sum(b.n_bundles for b in jbatches)), "joined_alignments": int(A["n_joined"]),
+                            "join_chains": int(A["jt"].n_chains), "join_closures": int(A["jt"].n_closures)}}
     ctx.close()
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 threads = usable_threads(args.ref_pairs)
-                arm = ReferenceArm(wl, args.ref_pairs, threads)
+                swl = make_workload(args.ref_pairs, 0, os.cpu_count() or 1, keep_truth=True)
+                arm = ReferenceArm(swl, args.ref_pairs, threads)
                 try:
                     st = arm.startup(); arm.step(); wall = arm.step()
                 finally:
                     arm.close()
                 reads = 2 * arm.sample_pairs
                 line["cpu_baseline"] = {"value": reads / max(wall - st, 1e-6), "unit": UNIT, "cores": threads, "kind": "reference",
-                                        "sample": "first %d pairs (%d reads) of the same workload; oracle/_ref/segment_juncs -p%d; wall %.2f s "
-                                                  "of which %.2f s fixed start-up (FASTA load, excluded)" % (arm.sample_pairs, reads, threads, wall, st)}
+                                        "sample": "%d pairs (%d reads) from the same generator and reference; oracle/_ref segment_juncs + "
+                                                  "long_spanning_reads (left, right) -p%d; wall %.2f s of which %.2f s fixed start-up "
+                                                  "(FASTA loads, excluded)" % (arm.sample_pairs, reads, threads, wall, st)}
             except Exception as e:  # the baseline leg must never hide the GPU result
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
@@ -395,7 +432,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("THB_BENCH_PAIRS", 10_000_000)), help="read pairs per GPU")
-    ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 200_000)),
+    ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 100_000)),
                     help="pairs in the bounded sample the reference CPU binary is timed on")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

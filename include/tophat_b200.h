@@ -266,6 +266,10 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* params, const thb_junction* j
 /* Joins one batch (host arrays); *out / *n_out receive the merged alignments of this batch, grouped by nothing
  * in particular (use .bundle), owned by ctx and valid until the next join call.                              */
 int thb_join_submit(thb_ctx* ctx, const thb_join_batch* host_batch, const thb_joined** out, uint64_t* n_out);
+/* Same for a batch whose arrays already live in device memory; the merged alignments stay on the device until
+ * thb_join_fetch copies them to the host (same lifetime as above).                                          */
+int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* device_batch, uint64_t* n_out);
+int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out);
 typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; uint32_t launches; uint32_t reserved;
                                  uint64_t n_chains, n_closures, n_joined, algorithmic_bytes; } thb_join_timing;
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out);

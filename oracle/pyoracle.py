@@ -197,7 +197,7 @@ def format_insertions(i: np.ndarray, names: List[str]) -> str:
 # long_spanning_reads: junction index + spliced segment hits + the reference binary
 
 
-def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: str, nseg: int, max_seg_len: int = 26) -> Dict[str, str]:
+def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: str, nseg: int, max_seg_len: int = 26, fast: bool = False) -> Dict[str, str]:
     """juncs_db (reference binary) on the segment_juncs outputs, then synthetic segment hits against its contigs,
     turned into id-sorted BAMs by the reference's fix_map_ordering (tophat.py:3686-3741)."""
     fa = os.path.join(outdir, "segment_juncs.fa")
@@ -208,8 +208,9 @@ def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: st
     hdr = os.path.join(outdir, "segment_juncs.hdr.sam")
     synth.write_contig_header(hdr, contigs)
     j = {"juncs_fa": fa, "juncs_header": hdr, "n_contigs": len(contigs)}
+    junctions = parse_juncs(outs["juncs"], wl.ref.names)
     for sname, side in (("left", wl.left), ("right", wl.right)):
-        per_seg = synth.spliced_segment_hits(wl, side, contigs)
+        per_seg = synth.spliced_hits_for_sam(wl, side, junctions, contigs) if fast else synth.spliced_segment_hits(wl, side, contigs)
         for k in range(nseg):
             sam = os.path.join(outdir, "%s_seg%d.to_spliced.sam" % (sname, k + 1))
             synth.write_spliced_sam(sam, wl.cfg, k, per_seg[k])
@@ -223,10 +224,10 @@ def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: st
 
 def run_long_spanning_reads(binary: str, files: Dict[str, str], bams: Dict[str, str], jin: Dict[str, str], outs: Dict[str, str], outdir: str,
                             nseg: int, side: str = "left", opts: Optional[List[str]] = None, tag: str = "", env: Optional[dict] = None,
-                            with_spliced: bool = True) -> str:
+                            with_spliced: bool = True, threads: int = 1) -> str:
     out_bam = os.path.join(outdir, "%s_candidates%s.bam" % (side, tag))
     cmd = [binary] + (opts if opts is not None else tophat_common_opts()) + \
-          ["-p1", "--sam-header", files["header"], "--bowtie2-max-penalty", "6", "--bowtie2-min-penalty", "2", "--bowtie2-penalty-for-N", "1",
+          ["-p%d" % threads, "--sam-header", files["header"], "--bowtie2-max-penalty", "6", "--bowtie2-min-penalty", "2", "--bowtie2-penalty-for-N", "1",
            "--bowtie2-read-gap-open", "5", "--bowtie2-read-gap-cont", "3", "--bowtie2-ref-gap-open", "5", "--bowtie2-ref-gap-cont", "3",
            files["fasta"], bams[side + "_reads"], outs["juncs"], outs["insertions"], outs["deletions"], "/dev/null", out_bam,
            ",".join(bams["%s_seg%d" % (side, k + 1)] for k in range(nseg))]

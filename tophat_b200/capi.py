@@ -62,6 +62,24 @@ class BatchC(C.Structure):
                 ("n_partner_hits", C.c_uint64), ("partner_hits", C.c_void_p), ("order_base", C.c_uint64)]
 
 
+class JoinBatchC(C.Structure):
+    _fields_ = [("n_bundles", C.c_uint32), ("n_segs", C.c_uint32), ("read_words", C.c_uint32), ("reserved", C.c_uint32),
+                ("bundles", C.c_void_p), ("seg_count", C.c_void_p), ("reads", C.c_void_p), ("n_hits", C.c_uint64), ("hits", C.c_void_p)]
+
+
+class JoinTimingC(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_chains", C.c_uint64), ("n_closures", C.c_uint64), ("n_joined", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
+
+
+def join_batch_c(b: "synth.PackedJoinBatch") -> JoinBatchC:
+    s = JoinBatchC()
+    s.n_bundles = b.n_bundles; s.n_segs = b.n_segs; s.read_words = b.read_words
+    s.bundles = b.bundles.ctypes.data; s.seg_count = b.seg_count.ctypes.data; s.reads = b.reads.ctypes.data
+    s.n_hits = b.hits.shape[0]; s.hits = b.hits.ctypes.data
+    return s
+
+
 class ResultsC(C.Structure):
     _fields_ = [("n_junctions", C.c_uint64), ("junctions", C.c_void_p),
                 ("n_deletions", C.c_uint64), ("deletions", C.c_void_p),
@@ -157,6 +175,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_pack_bases.restype = None
     lib.thb_pack_read.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.thb_pack_read.restype = None
+    lib.thb_join_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.thb_join_submit.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.thb_join_submit_device.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_uint64)]
+    lib.thb_join_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.thb_join_last_timing.argtypes = [C.c_void_p, C.POINTER(JoinTimingC)]
     lib.thb_alloc_pinned.argtypes = [C.c_size_t]
     lib.thb_alloc_pinned.restype = C.c_void_p
     lib.thb_free_pinned.argtypes = [C.c_void_p]
@@ -239,3 +262,48 @@ class Context:
 
     def segjuncs_allgather(self) -> None:
         self._check(self.lib.thb_segjuncs_allgather(self.h), "thb_segjuncs_allgather")
+
+    # ---- long_spanning_reads join
+    def join_begin(self, params: Params, junctions: np.ndarray, insertions: np.ndarray) -> None:
+        """junctions: JUNCTION_DTYPE sorted unique (incl. deletions as (ref, left-1, right)); insertions: INSERTION_DTYPE sorted."""
+        self._jkeep = (np.ascontiguousarray(junctions), np.ascontiguousarray(insertions))
+        j, i = self._jkeep
+        self._check(self.lib.thb_join_begin(self.h, C.byref(params), j.ctypes.data if j.size else None, j.shape[0],
+                                            i.ctypes.data if i.size else None, i.shape[0]), "thb_join_begin")
+
+    def join_submit(self, batch) -> np.ndarray:
+        b = batch if isinstance(batch, JoinBatchC) else join_batch_c(batch)
+        out = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.thb_join_submit(self.h, C.byref(b), C.byref(out), C.byref(n)), "thb_join_submit")
+        return _copy_records(out.value, n.value, synth.JOINED_DTYPE)
+
+    def join_submit_device(self, b: JoinBatchC) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.thb_join_submit_device(self.h, C.byref(b), C.byref(n)), "thb_join_submit_device")
+        return int(n.value)
+
+    def join_fetch(self) -> np.ndarray:
+        out = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.thb_join_fetch(self.h, C.byref(out), C.byref(n)), "thb_join_fetch")
+        return _copy_records(out.value, n.value, synth.JOINED_DTYPE)
+
+    def join_timing(self) -> JoinTimingC:
+        t = JoinTimingC()
+        self._check(self.lib.thb_join_last_timing(self.h, C.byref(t)), "thb_join_last_timing")
+        return t
+
+
+def join_sets_from_results(res: "SegJuncsResults"):
+    """The std::set<Junction> long_spanning_reads builds from segment.juncs + segment.deletions (deletions enter as
+    Junction(ref, left - 1 + 1 - 1 ... ) i.e. exactly the Deletion record: long_spanning_reads.cpp:2916-2944) and the insertion set."""
+    j = np.concatenate([res.junctions, res.deletions]) if res.deletions.size else res.junctions.copy()
+    if res.deletions.size:
+        j[len(res.junctions):]["antisense"] = 0
+    order = np.lexsort((j["antisense"], j["right"], j["left"], j["ref_id"]))
+    j = j[order]
+    if j.size:
+        keep = np.ones(j.size, bool)
+        keep[1:] = ~((j["ref_id"][1:] == j["ref_id"][:-1]) & (j["left"][1:] == j["left"][:-1]) & (j["right"][1:] == j["right"][:-1]) &
+                     (j["antisense"][1:] == j["antisense"][:-1]))
+        j = j[keep]
+    return np.ascontiguousarray(j), np.ascontiguousarray(res.insertions)

@@ -48,6 +48,8 @@ struct Nccl {
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -72,6 +74,7 @@ struct thb_ctx {
   unsigned int* d_ovf_juncs = nullptr; unsigned int* d_ovf_dels = nullptr; unsigned int* d_err = nullptr;
   DevBuf d_keys, d_keys_sorted, d_cub_tmp, d_decoded, d_count;
   // task queues of the scan phase
+  DevBuf ag_send, ag_recv;
   DevBuf q_win, q_indel, q_rescue, q_rescue_out, q_rbundle, q_bstate, q_owner;
   uint64_t cap_win = 0, cap_indel = 0;
   unsigned long long* d_qcounts = nullptr; unsigned int* d_qovf = nullptr;
@@ -88,7 +91,7 @@ struct thb_ctx {
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // long_spanning_reads join
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out; uint64_t j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
-  JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{};
+  JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
 };
@@ -324,7 +327,7 @@ void thb_destroy(thb_ctx* ctx)
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
-                     &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner,
+                     &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
                      &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
@@ -649,29 +652,20 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   return THB_OK;
 }
 
-int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** out, uint64_t* n_out)
+static int join_validate(thb_ctx* ctx, const thb_join_batch* b)
 {
-  if (!ctx || !b || !out || !n_out) return THB_EINVAL;
-  CU(cudaSetDevice(ctx->device));
   if (!ctx->join_begun) return fail(ctx, THB_ESTATE, "thb_join_begin not called");
-  *out = nullptr; *n_out = 0;
-  if (b->n_bundles == 0) return THB_OK;
   if (b->n_segs < 1 || b->n_segs > (uint32_t)JMAXSEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, JMAXSEGS);
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4]", b->read_words);
   if (!b->bundles || !b->seg_count || !b->reads || (b->n_hits && !b->hits)) return fail(ctx, THB_EINVAL, "null batch array");
-  const size_t rdw = (size_t)3 * b->read_words;
-  CU(ctx->j_bundles.reserve((size_t)b->n_bundles * sizeof(thb_join_bundle))); CU(ctx->j_segc.reserve((size_t)b->n_bundles * b->n_segs * 2));
-  CU(ctx->j_reads.reserve((size_t)b->n_bundles * rdw * 8)); CU(ctx->j_hits.reserve((size_t)(b->n_hits + 1) * sizeof(thb_jhit)));
-  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_bundles.p, b->bundles, (size_t)b->n_bundles * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_segc.p, b->seg_count, (size_t)b->n_bundles * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_reads.p, b->reads, (size_t)b->n_bundles * rdw * 8, cudaMemcpyHostToDevice, ctx->compute));
-  if (b->n_hits) CU(cudaMemcpyAsync(ctx->j_hits.p, b->hits, (size_t)b->n_hits * sizeof(thb_jhit), cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
-  ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * b->n_bundles, 1u << 16));
+  return THB_OK;
+}
+
+// launches the chain join over device-resident arrays; results stay in ctx->j_out, *n receives their number
+static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsigned long long* n_res)
+{
+  ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
-  JoinBatchView bv; bv.bundles = (const thb_join_bundle*)ctx->j_bundles.p; bv.seg_count = (const uint16_t*)ctx->j_segc.p; bv.reads = (const uint64_t*)ctx->j_reads.p;
-  bv.hits = (const thb_jhit*)ctx->j_hits.p; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
   unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f;
   for (int attempt = 0; attempt < 24; ++attempt) {
     CU(ctx->j_out.reserve(ctx->j_cap_out * sizeof(thb_joined)));
@@ -680,7 +674,7 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
     CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
     JoinOut o; o.rec = (thb_joined*)ctx->j_out.p; o.cap = ctx->j_cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
     CU(cudaEventRecord(ctx->kev[0], ctx->compute));
-    chain_join_kernel<<<grid_for(b->n_bundles, 128), 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, o);
+    chain_join_kernel<<<grid_for(bv.n_bundles, 128), 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[1], ctx->compute));
     ctx->jtiming.launches++;
@@ -693,19 +687,68 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
     ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out * 2, n + 1024);
     if (attempt == 23) return fail(ctx, THB_ENOMEM, "joined-hit buffer still overflows");
   }
+  thb_join_timing& t = ctx->jtiming;
+  t.kernel_ms += kms; t.n_chains += cnt[0]; t.n_closures += cnt[1]; t.n_joined += cnt[2];
+  // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 48 per segment hit, per closure
+  // 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain, 128 per output record
+  t.algorithmic_bytes += 56ull * bv.n_bundles + 48ull * n_hits + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
+  ctx->j_last_n = n;
+  *n_res = n;
+  return THB_OK;
+}
+
+int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out)
+{
+  if (!ctx || !out || !n_out) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  const unsigned long long n = ctx->j_last_n;
   ctx->h_joined.resize(n);
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
   if (n) CU(cudaMemcpyAsync(ctx->h_joined.data(), ctx->j_out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaEventRecord(ctx->ev_d, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  float h2d = 0.f, d2h = 0.f; cudaEventElapsedTime(&h2d, ctx->ev_a, ctx->ev_b); cudaEventElapsedTime(&d2h, ctx->ev_c, ctx->ev_d);
-  thb_join_timing& t = ctx->jtiming;
-  t.h2d_ms += h2d; t.kernel_ms += kms; t.d2h_ms += d2h; t.n_chains += cnt[0]; t.n_closures += cnt[1]; t.n_joined += cnt[2];
-  // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 48 per segment hit, per closure
-  // 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain, 128 per output record
-  t.algorithmic_bytes += 56ull * b->n_bundles + 48ull * b->n_hits + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
+  float d2h = 0.f; cudaEventElapsedTime(&d2h, ctx->ev_c, ctx->ev_d); ctx->jtiming.d2h_ms += d2h;
   *out = ctx->h_joined.data(); *n_out = n;
   return THB_OK;
+}
+
+int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* b, uint64_t* n_out)
+{
+  if (!ctx || !b || !n_out) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  *n_out = 0; ctx->j_last_n = 0;
+  int rc = join_validate(ctx, b); if (rc) return rc;
+  if (b->n_bundles == 0) return THB_OK;
+  JoinBatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
+  bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
+  unsigned long long n = 0;
+  rc = join_run(ctx, bv, b->n_hits, &n); if (rc) return rc;
+  *n_out = n;
+  return THB_OK;
+}
+
+int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** out, uint64_t* n_out)
+{
+  if (!ctx || !b || !out || !n_out) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  *out = nullptr; *n_out = 0; ctx->j_last_n = 0;
+  int rc = join_validate(ctx, b); if (rc) return rc;
+  if (b->n_bundles == 0) return THB_OK;
+  const size_t rdw = (size_t)3 * b->read_words;
+  CU(ctx->j_bundles.reserve((size_t)b->n_bundles * sizeof(thb_join_bundle))); CU(ctx->j_segc.reserve((size_t)b->n_bundles * b->n_segs * 2));
+  CU(ctx->j_reads.reserve((size_t)b->n_bundles * rdw * 8)); CU(ctx->j_hits.reserve((size_t)(b->n_hits + 1) * sizeof(thb_jhit)));
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_bundles.p, b->bundles, (size_t)b->n_bundles * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_segc.p, b->seg_count, (size_t)b->n_bundles * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->j_reads.p, b->reads, (size_t)b->n_bundles * rdw * 8, cudaMemcpyHostToDevice, ctx->compute));
+  if (b->n_hits) CU(cudaMemcpyAsync(ctx->j_hits.p, b->hits, (size_t)b->n_hits * sizeof(thb_jhit), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+  JoinBatchView bv; bv.bundles = (const thb_join_bundle*)ctx->j_bundles.p; bv.seg_count = (const uint16_t*)ctx->j_segc.p; bv.reads = (const uint64_t*)ctx->j_reads.p;
+  bv.hits = (const thb_jhit*)ctx->j_hits.p; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
+  unsigned long long n = 0;
+  rc = join_run(ctx, bv, b->n_hits, &n); if (rc) return rc;
+  float h2d = 0.f; cudaEventElapsedTime(&h2d, ctx->ev_a, ctx->ev_b); ctx->jtiming.h2d_ms += h2d;
+  return thb_join_fetch(ctx, out, n_out);
 }
 
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out)
@@ -726,6 +769,8 @@ static int nccl_bind(thb_ctx* ctx, Nccl& n)
   *(void**)(&n.CommInitRank) = dlsym(n.h, "ncclCommInitRank");
   *(void**)(&n.AllGather) = dlsym(n.h, "ncclAllGather");
   n.CommDestroy = (int (*)(void*))dlsym(n.h, "ncclCommDestroy");
+  n.GroupStart = (int (*)())dlsym(n.h, "ncclGroupStart");
+  n.GroupEnd = (int (*)())dlsym(n.h, "ncclGroupEnd");
   n.GetErrorString = (const char* (*)(int))dlsym(n.h, "ncclGetErrorString");
   if (!n.GetUniqueId || !n.CommInitRank || !n.AllGather) return fail(ctx, THB_ENCCL, "libnccl lacks required symbols");
   return THB_OK;
@@ -749,71 +794,73 @@ int thb_comm_init(thb_ctx* ctx, const void* uid, int rank, int world)
   return THB_OK;
 }
 
-// all-gather one hash set: every rank compacts its keys, pads to the global maximum, exchanges, and
-// inserts everything it received.
-static int allgather_set(thb_ctx* ctx, DevBuf& set, uint64_t& cap, unsigned int* ovf)
+// appends the valid records of a gathered (padded) insertion buffer
+__global__ void ins_append_kernel(const InsRec* src, uint64_t n, InsRec* dst, unsigned long long* count, unsigned long long cap, unsigned int* err)
 {
-  const int W = ctx->world;
-  CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_count.reserve(8 * (size_t)(W + 1)));
-  unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
-  CU(cudaMemsetAsync(d_cnt, 0, 8, ctx->compute));
-  hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, d_cnt);
-  CU(cudaGetLastError()); ctx->own_launches++;
-  // ncclUint64 = 5
-  if (ctx->nccl.AllGather(d_cnt, d_cnt + 1, 1, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
-  std::vector<unsigned long long> counts(W + 1);
-  CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * (size_t)(W + 1), cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
-  unsigned long long mx = 0, total = 0; for (int r = 0; r < W; ++r) { mx = std::max(mx, counts[1 + r]); total += counts[1 + r]; }
-  if (mx == 0) return THB_OK;
-  DevBuf send, recv; CU(send.reserve(mx * 8)); CU(recv.reserve(mx * 8 * W));
-  CU(cudaMemsetAsync(send.p, 0xff, mx * 8, ctx->compute));                     // pad with HS_EMPTY
-  CU(cudaMemcpyAsync(send.p, ctx->d_keys.p, counts[0] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
-  if (ctx->nccl.AllGather(send.p, recv.p, mx, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(keys)");
-  while (cap < 2 * total) { int rc = grow_set(ctx, set, cap, ovf); if (rc) return rc; }
-  HashSet dst; dst.slots = (uint64_t*)set.p; dst.mask = cap - 1; dst.overflow = ovf;
-  hs_insert_list_kernel<<<grid_for(mx * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)recv.p, mx * W, dst);
-  CU(cudaGetLastError()); ctx->own_launches++;
-  CU(cudaStreamSynchronize(ctx->compute));
-  send.release(); recv.release();
-  return THB_OK;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const InsRec r = src[i];
+    if (r.key == ~0ull) continue;
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    if (slot < cap) dst[slot] = r; else atomicOr(err, 1u);
+  }
 }
 
+// Union of the per-rank sets (replaces the per-thread set union of segment_juncs.cpp:4911-4922).  One all-gather of
+// the three set sizes, one host read of them, then one grouped all-gather of the padded payloads and device-side
+// inserts; staging buffers persist in the context.
 int thb_segjuncs_allgather(thb_ctx* ctx)
 {
   if (!ctx) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   if (!ctx->comm) return fail(ctx, THB_ESTATE, "thb_comm_init not called");
-  int rc;
-  if ((rc = allgather_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs))) return rc;
-  if ((rc = allgather_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels))) return rc;
-  // insertion records: gather the append buffers (4 x u64 per record)
   const int W = ctx->world;
-  CU(ctx->d_count.reserve(8 * (size_t)(W + 1)));
+  const uint64_t capj = ctx->cap_juncs, capd = ctx->cap_dels;
+  CU(ctx->d_keys.reserve((capj + capd) * 8)); CU(ctx->d_count.reserve(8 * (size_t)(3 + 3 * W)));
   unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
-  CU(cudaMemcpyAsync(d_cnt, ctx->d_ins_count, 8, cudaMemcpyDeviceToDevice, ctx->compute));
-  if (ctx->nccl.AllGather(d_cnt, d_cnt + 1, 1, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(ins counts)");
-  std::vector<unsigned long long> counts(W + 1);
-  CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * (size_t)(W + 1), cudaMemcpyDeviceToHost, ctx->compute));
+  uint64_t* keys_j = (uint64_t*)ctx->d_keys.p; uint64_t* keys_d = keys_j + capj;
+  CU(cudaMemsetAsync(d_cnt, 0, 24, ctx->compute));
+  hs_compact_kernel<<<grid_for(capj, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_juncs.p, capj, keys_j, d_cnt + 0);
+  hs_compact_kernel<<<grid_for(capd, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_dels.p, capd, keys_d, d_cnt + 1);
+  CU(cudaGetLastError()); ctx->own_launches += 2;
+  CU(cudaMemcpyAsync(d_cnt + 2, ctx->d_ins_count, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  // ncclUint64 = 5
+  if (ctx->nccl.AllGather(d_cnt, d_cnt + 3, 3, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
+  std::vector<unsigned long long> counts(3 + 3 * (size_t)W);
+  CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * counts.size(), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  unsigned long long mx = 0, total = 0; for (int r = 0; r < W; ++r) { mx = std::max(mx, counts[1 + r]); total += counts[1 + r]; }
-  if (mx) {
-    DevBuf send, recv; CU(send.reserve(mx * sizeof(InsRec))); CU(recv.reserve(mx * sizeof(InsRec) * W));
-    CU(cudaMemsetAsync(send.p, 0xff, mx * sizeof(InsRec), ctx->compute));
-    CU(cudaMemcpyAsync(send.p, ctx->d_ins.p, counts[0] * sizeof(InsRec), cudaMemcpyDeviceToDevice, ctx->compute));
-    if (ctx->nccl.AllGather(send.p, recv.p, mx * 4, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(ins)");
-    std::vector<InsRec> all(mx * W);
-    CU(cudaMemcpyAsync(all.data(), recv.p, all.size() * sizeof(InsRec), cudaMemcpyDeviceToHost, ctx->compute));
-    CU(cudaStreamSynchronize(ctx->compute));
-    std::vector<InsRec> keep; keep.reserve(total);
-    for (const InsRec& r : all) if (r.key != ~0ull) keep.push_back(r);
-    if (keep.size() > ctx->cap_ins) { ctx->d_ins.release(); ctx->cap_ins = keep.size() + 1024; CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec))); }
-    unsigned long long n = keep.size();
-    CU(cudaMemcpyAsync(ctx->d_ins.p, keep.data(), n * sizeof(InsRec), cudaMemcpyHostToDevice, ctx->compute));
-    CU(cudaMemcpyAsync(ctx->d_ins_count, &n, 8, cudaMemcpyHostToDevice, ctx->compute));
-    CU(cudaStreamSynchronize(ctx->compute));
-    send.release(); recv.release();
+  unsigned long long mx[3] = {0, 0, 0}, tot[3] = {0, 0, 0};
+  for (int r = 0; r < W; ++r) for (int k = 0; k < 3; ++k) { const unsigned long long c = counts[3 + 3 * r + k]; mx[k] = std::max(mx[k], c); tot[k] += c; }
+  if (counts[2] > ctx->cap_ins) return fail(ctx, THB_ESTATE, "insertion buffer overflow before the all-gather");
+  // staging: [juncs send | dels send | ins send] and the W-fold receive areas
+  const size_t sj = mx[0] * 8, sd = mx[1] * 8, si = mx[2] * sizeof(InsRec);
+  CU(ctx->ag_send.reserve(sj + sd + si + 64)); CU(ctx->ag_recv.reserve((sj + sd + si) * (size_t)W + 64));
+  uint8_t* send = (uint8_t*)ctx->ag_send.p; uint8_t* recv = (uint8_t*)ctx->ag_recv.p;
+  if (sj + sd + si) CU(cudaMemsetAsync(send, 0xff, sj + sd + si, ctx->compute));                     // pad with HS_EMPTY
+  if (counts[0]) CU(cudaMemcpyAsync(send, keys_j, counts[0] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  if (counts[1]) CU(cudaMemcpyAsync(send + sj, keys_d, counts[1] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  if (counts[2]) CU(cudaMemcpyAsync(send + sj + sd, ctx->d_ins.p, counts[2] * sizeof(InsRec), cudaMemcpyDeviceToDevice, ctx->compute));
+  uint8_t* rj = recv; uint8_t* rd = recv + sj * W; uint8_t* ri = rd + sd * W;
+  if (ctx->nccl.GroupStart) ctx->nccl.GroupStart();
+  int e = 0;
+  if (mx[0]) e |= ctx->nccl.AllGather(send, rj, mx[0], 5, ctx->comm, ctx->compute);
+  if (mx[1]) e |= ctx->nccl.AllGather(send + sj, rd, mx[1], 5, ctx->comm, ctx->compute);
+  if (mx[2]) e |= ctx->nccl.AllGather(send + sj + sd, ri, mx[2] * 4, 5, ctx->comm, ctx->compute);
+  if (ctx->nccl.GroupEnd) e |= ctx->nccl.GroupEnd();
+  if (e != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(payload)");
+  int rc;
+  while (ctx->cap_juncs < 2 * tot[0]) { if ((rc = grow_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs))) return rc; }
+  while (ctx->cap_dels < 2 * tot[1]) { if ((rc = grow_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels))) return rc; }
+  if (mx[0]) { hs_insert_list_kernel<<<grid_for(mx[0] * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)rj, mx[0] * W, make_set(ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs)); ctx->own_launches++; }
+  if (mx[1]) { hs_insert_list_kernel<<<grid_for(mx[1] * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)rd, mx[1] * W, make_set(ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels)); ctx->own_launches++; }
+  if (mx[2]) {
+    if (tot[2] > ctx->cap_ins) {                                   // the gathered records replace the local buffer
+      ctx->d_ins.release(); ctx->cap_ins = tot[2] + 1024; CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec)));
+    }
+    CU(cudaMemsetAsync(ctx->d_ins_count, 0, 8, ctx->compute));
+    ins_append_kernel<<<grid_for(mx[2] * W, 256), 256, 0, ctx->compute>>>((const InsRec*)ri, mx[2] * W, (InsRec*)ctx->d_ins.p, ctx->d_ins_count, ctx->cap_ins, ctx->d_err);
+    ctx->own_launches++;
   }
+  CU(cudaGetLastError());
   return THB_OK;
 }
 

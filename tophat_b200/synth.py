@@ -158,6 +158,7 @@ class SynthConfig:
     chunk: int = 500_000
     chunk_seed_base: int = 0           # added to the chunk index in the RNG stream id (per-rank shards)
     keep_truth: bool = False           # keep the per-base genomic origin of every read (needed to place spliced segment hits)
+    keep_candidates: bool = False      # keep compact junction-spanning segment placements instead (large workloads)
 
 
 @dataclasses.dataclass
@@ -168,6 +169,7 @@ class SideData:
     seg_hits: List[np.ndarray]          # per segment: structured array (read_idx + HIT fields)
     mapped_hits: np.ndarray             # full-read hits (the *.mapped.bam stream)
     unmapped: np.ndarray                # bool (n,): read went to segment mapping
+    cand: Optional[list] = None         # keep_candidates: per segment dict of arrays (see _placement_candidates)
     truth: Optional[dict] = None        # keep_truth: fwd (n,L) codes in genome orientation, gpos (n,L) genomic position of
                                         # every base (-1 = inserted), ref_id (n,), rev (n,) read is the reverse complement of fwd
 
@@ -377,7 +379,7 @@ def _gen_chunk(ci: int):
     nseg = offs.shape[0]
     done = ci * cfg.chunk
     n = min(cfg.chunk, cfg.n_pairs - done)
-    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[]) for s in ("left", "right")}
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[], cand=[]) for s in ("left", "right")}
     a0, b0, plus = _sample_mates(rng, cfg, space, contigs, n)
     for which, x0 in (("A", a0), ("B", b0)):
         codes_fwd, emap = _make_read_fwd(rng, cfg, space, exonic, x0)
@@ -408,6 +410,13 @@ def _gen_chunk(ci: int):
             mh["flags"] = (HIT_ANTISENSE if rev else 0) | HIT_END
             A["mapped"].append(mh)
             A["unm"].append((sel + base, ~mapped[sel]))
+            if cfg.keep_candidates:
+                us = sel[~mapped[sel]]
+                if us.size:
+                    oku = emap[us] >= 0
+                    rid_u, gpos_u, _ = space.to_genome(np.where(oku, emap[us], 0))
+                    A["cand"].append(_placement_candidates(cfg, contigs, codes_fwd[us], np.where(oku, gpos_u, -1), rid_u[:, 0],
+                                                           np.full(us.size, rev), us + base))
             if cfg.keep_truth:
                 ok = emap[sel] >= 0
                 rid_t, gpos_t, _ = space.to_genome(np.where(ok, emap[sel], 0))
@@ -488,11 +497,11 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
     else:
         chunk_accs = [_gen_chunk(c) for c in range(nchunks)]
     _GEN_STATE.clear()
-    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[]) for s in ("left", "right")}
+    acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[], cand=[]) for s in ("left", "right")}
     for ca in chunk_accs:
         for s in acc:
             acc[s]["reads"] += ca[s]["reads"]; acc[s]["mapped"] += ca[s]["mapped"]; acc[s]["unm"] += ca[s]["unm"]
-            acc[s]["truth"] += ca[s]["truth"]
+            acc[s]["truth"] += ca[s]["truth"]; acc[s]["cand"] += ca[s]["cand"]
             for k in range(nseg):
                 acc[s]["seg"][k] += ca[s]["seg"][k]
     del chunk_accs
@@ -521,13 +530,29 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
         mh = np.concatenate(A["mapped"]) if A["mapped"] else np.zeros(0, dtype=SEGHIT_DTYPE)
         mh = mh[~qc_fail[mh["read_idx"]]]
         mh = mh[np.argsort(mh["read_idx"], kind="stable")]
+        cand = None
+        if cfg.keep_candidates:
+            cand = []
+            for k in range(nseg):
+                ds = [c[k] for c in A["cand"]]
+                if ds:
+                    d = {f: np.concatenate([x[f] for x in ds]) for f in ds[0] if f != "ln"}
+                    keepc = ~qc_fail[d["read_idx"]]
+                    d = {f: v[keepc] for f, v in d.items()}
+                    order = np.argsort(d["read_idx"], kind="stable")
+                    d = {f: v[order] for f, v in d.items()}
+                    d["ln"] = ds[0]["ln"]
+                else:
+                    d = _placement_candidates(cfg, contigs, np.zeros((0, L), np.uint8), np.zeros((0, L), np.int64), np.zeros(0, np.int64),
+                                              np.zeros(0, bool), np.zeros(0, np.int64))[k]
+                cand.append(d)
         truth = None
         if cfg.keep_truth:
             truth = dict(fwd=np.zeros((cfg.n_pairs, L), np.uint8), gpos=np.full((cfg.n_pairs, L), -1, np.int64),
                          ref_id=np.zeros(cfg.n_pairs, np.int64), rev=np.zeros(cfg.n_pairs, bool), qc_fail=qc_fail)
             for idx, f, gp, rid, rv in A["truth"]:
                 truth["fwd"][idx] = f; truth["gpos"][idx] = gp; truth["ref_id"][idx] = rid; truth["rev"][idx] = rv
-        return SideData(reads, np.arange(1, cfg.n_pairs + 1, dtype="<u4"), seg_hits, mh, unm, truth)
+        return SideData(reads, np.arange(1, cfg.n_pairs + 1, dtype="<u4"), seg_hits, mh, unm, cand, truth)
 
     introns = np.concatenate(anns) if anns else np.zeros(0)
     return Workload(cfg, ref, finish("left"), finish("right"), introns)
@@ -537,8 +562,14 @@ def subset(wl: Workload, n_pairs: int) -> Workload:
     """The first n_pairs fragments of a workload (same reference): a bounded sample for the CPU baseline."""
     def cut(sd: SideData) -> SideData:
         tr = None if sd.truth is None else {k: v[:n_pairs] for k, v in sd.truth.items()}
+        cd = None
+        if sd.cand is not None:
+            cd = []
+            for d in sd.cand:
+                m = d["read_idx"] < n_pairs
+                e = {f: v[m] for f, v in d.items() if f != "ln"}; e["ln"] = d["ln"]; cd.append(e)
         return SideData(sd.reads[:n_pairs], sd.ids[:n_pairs], [h[h["read_idx"] < n_pairs] for h in sd.seg_hits],
-                        sd.mapped_hits[sd.mapped_hits["read_idx"] < n_pairs], sd.unmapped[:n_pairs], tr)
+                        sd.mapped_hits[sd.mapped_hits["read_idx"] < n_pairs], sd.unmapped[:n_pairs], cd, tr)
     cfg = dataclasses.replace(wl.cfg, n_pairs=n_pairs)
     return Workload(cfg, wl.ref, cut(wl.left), cut(wl.right), wl.introns)
 
@@ -787,7 +818,7 @@ def spliced_segment_hits(wl: Workload, side: SideData, contigs, max_mm: int = 2)
     for (name, ref, left_start, jl, jr, typ, seq) in contigs:
         if typ in ("ins", "del", "fus") or not isinstance(jr, int):
             continue
-        key[(ref, jl, jr)] = (name, left_start, seq)
+        key.setdefault((ref, jl, jr), []).append((name, left_start, seq))
     names = wl.ref.names
     tr = side.truth
     out = [[] for _ in range(nseg)]
@@ -808,28 +839,26 @@ def spliced_segment_hits(wl: Workload, side: SideData, contigs, max_mm: int = 2)
             j = int(inside[0])
             if (g[lo:lo + ln] < 0).any():
                 continue
-            ent = key.get((ref, int(g[j]), int(g[j + 1])))
-            if ent is None:
-                continue
-            name, left_start, cseq = ent
-            x = j - lo + 1                                   # bases on the left exon
-            pos0 = (int(g[j]) - left_start + 1) - x
-            if pos0 < 0 or pos0 + ln > len(cseq):
-                continue
-            cc = codes_from_ascii(cseq[pos0:pos0 + ln].encode())
-            seg = fwd[ri, lo:lo + ln]
-            mm = (seg != cc) | (seg > 3) | (cc > 3)
-            nm = int(mm.sum())
-            if nm > max_mm:
-                continue
-            md, run = [], 0
-            for q in range(ln):
-                if mm[q]:
-                    md.append(str(run)); md.append(chr(CODE2CHAR[min(int(cc[q]), 4)])); run = 0
-                else:
-                    run += 1
-            md.append(str(run))
-            out[k].append(dict(read_idx=int(ri), contig=name, pos0=pos0, anti=rev, fwd=seg, nm=nm, md="".join(md)))
+            for (name, left_start, cseq) in key.get((ref, int(g[j]), int(g[j + 1])), []):
+              x = j - lo + 1                                   # bases on the left exon
+              if True:
+                pos0 = (int(g[j]) - left_start + 1) - x
+                if pos0 < 0 or pos0 + ln > len(cseq):
+                    continue
+                cc = codes_from_ascii(cseq[pos0:pos0 + ln].encode())
+                seg = fwd[ri, lo:lo + ln]
+                mm = (seg != cc) | (seg > 3) | (cc > 3)
+                nm = int(mm.sum())
+                if nm > max_mm:
+                    continue
+                md, run = [], 0
+                for q in range(ln):
+                    if mm[q]:
+                        md.append(str(run)); md.append(chr(CODE2CHAR[min(int(cc[q]), 4)])); run = 0
+                    else:
+                        run += 1
+                md.append(str(run))
+                out[k].append(dict(read_idx=int(ri), contig=name, pos0=pos0, anti=rev, fwd=seg, nm=nm, md="".join(md)))
     return out
 
 
@@ -852,3 +881,219 @@ def write_contig_header(path: str, contigs) -> None:
         for c in contigs:
             f.write("@SQ\tSN:%s\tLN:%d\n" % (c[0], len(c[6])))
         f.write("@PG\tID:TopHat\tVN:2.1.2\n")
+
+
+# ---------------------------------------------------------------------------------------------
+# vectorised junction-spanning segment placement + packed join batches (bench / large tests)
+
+JHIT_DTYPE = np.dtype([("ref_id", "<u4"), ("left", "<i4"), ("n_ops", "u1"), ("flags", "u1"), ("mismatches", "u1"),
+                       ("splice_mms", "u1"), ("ops", "<u4", (9,))])
+JBUNDLE_DTYPE = np.dtype([("read_id", "<u4"), ("hit_begin", "<u4"), ("read_len", "<u2"), ("n_segs", "u1"), ("reserved", "u1"),
+                          ("reserved2", "<u4")])
+JOINED_DTYPE = np.dtype([("bundle", "<u4"), ("ref_id", "<u4"), ("left", "<i4"), ("n_ops", "u1"), ("flags", "u1"), ("mismatches", "u1"),
+                         ("edit_dist", "u1"), ("splice_mms", "u1"), ("reserved8", "u1", (3,)), ("ops", "<u4", (27,))])
+assert JHIT_DTYPE.itemsize == 48 and JBUNDLE_DTYPE.itemsize == 16 and JOINED_DTYPE.itemsize == 128
+JHIT_ANTISENSE_SPLICE = 4
+OP_MATCH, OP_INS, OP_DEL, OP_REF_SKIP = 1, 3, 5, 11
+
+
+def _junc_key(ref_id, left, right):
+    return (np.asarray(ref_id, dtype=np.uint64) << np.uint64(56)) | (np.asarray(left, dtype=np.uint64) << np.uint64(28)) | \
+        np.asarray(right, dtype=np.uint64)
+
+
+def _placement_candidates(cfg: SynthConfig, ref_codes, fwd, gpos, rid, rev, read_idx, max_mm: int = 2, min_anchor_len: int = 8,
+                          want_mm: bool = False):
+    """Segments that cross exactly one junction-like jump of the read's genomic origin (no inserted base inside), placed
+    ungapped over the two flanks.  fwd/gpos: (m, L) genome-orientation codes / positions, rid (m,), rev (m,) bool, read_idx (m,).
+    Returns per segment k a dict of arrays: read_idx, ref_id, jl, jr, x (bases left of the splice), anti, nm, smm
+    [+ mm (rows, ln) bool and fwd (rows, ln) codes when want_mm]."""
+    L = cfg.read_len
+    offs, lens = segment_layout(L, cfg.segment_length)
+    nseg = offs.shape[0]
+    out = []
+    for k in range(nseg):
+        ln = int(lens[k])
+        parts = []
+        for r in (False, True):
+            sel = np.nonzero(rev == r)[0]
+            if sel.size == 0:
+                continue
+            lo = int(L - offs[k] - lens[k]) if r else int(offs[k])
+            G = gpos[sel, lo:lo + ln]
+            jump = (G[:, 1:] - G[:, :-1] > 1) & (G[:, 1:] >= 0) & (G[:, :-1] >= 0)
+            ok = (jump.sum(axis=1) == 1) & (G >= 0).all(axis=1)
+            sel, G, jump = sel[ok], G[ok], jump[ok]
+            if sel.size == 0:
+                continue
+            j = np.argmax(jump, axis=1)
+            ar = np.arange(sel.size)
+            jl, jr = G[ar, j], G[ar, j + 1]
+            seg = fwd[sel, lo:lo + ln]
+            refb = np.empty_like(seg)
+            rsel = rid[sel]
+            for ci, codes in enumerate(ref_codes):
+                m = rsel == ci + 1
+                if m.any():
+                    refb[m] = codes[G[m]]
+            mm = (seg != refb) | (seg > 3) | (refb > 3)
+            nm = mm.sum(axis=1)
+            x = j + 1
+            near = np.abs(x[:, None] - np.arange(ln)[None, :]) < min_anchor_len
+            smm = (mm & near).sum(axis=1)
+            keep = (nm <= max_mm) & (jl >= 26)
+            d = dict(read_idx=read_idx[sel][keep], ref_id=rsel[keep].astype(np.int64), jl=jl[keep].astype(np.int64), jr=jr[keep].astype(np.int64),
+                     x=x[keep].astype(np.int16), anti=np.full(int(keep.sum()), r), nm=nm[keep].astype(np.uint8), smm=smm[keep].astype(np.uint8))
+            if want_mm:
+                d["mm"] = mm[keep]; d["fwd"] = seg[keep]
+            parts.append(d)
+        if parts:
+            d = {f: np.concatenate([p[f] for p in parts]) for f in parts[0]}
+        else:
+            d = dict(read_idx=np.zeros(0, np.int64), ref_id=np.zeros(0, np.int64), jl=np.zeros(0, np.int64), jr=np.zeros(0, np.int64),
+                     x=np.zeros(0, np.int16), anti=np.zeros(0, bool), nm=np.zeros(0, np.uint8), smm=np.zeros(0, np.uint8))
+            if want_mm:
+                d["mm"] = np.zeros((0, ln), bool); d["fwd"] = np.zeros((0, ln), np.uint8)
+        d["ln"] = ln
+        out.append(d)
+    return out
+
+
+def _filter_by_junctions(cands, junctions: np.ndarray):
+    """Keeps the placements whose (ref, left, right) is a junction record; one output row per strand variant present
+    (juncs_db writes one contig per record).  Adds `asplice`; rows sorted by read index."""
+    jk = {}
+    for anti in (0, 1):
+        sel = junctions[junctions["antisense"] == anti]
+        jk[anti] = np.sort(_junc_key(sel["ref_id"], sel["left"], sel["right"]))
+    out = []
+    for d in cands:
+        key = _junc_key(d["ref_id"], d["jl"], d["jr"])
+        parts = []
+        for anti in (0, 1):
+            pos = np.searchsorted(jk[anti], key)
+            has = pos < jk[anti].shape[0]
+            has[has] &= jk[anti][pos[has]] == key[has]
+            if has.any():
+                p = {f: v[has] for f, v in d.items() if f != "ln"}
+                p["asplice"] = np.full(int(has.sum()), anti, np.uint8)
+                parts.append(p)
+        if parts:
+            o = {f: np.concatenate([p[f] for p in parts]) for f in parts[0]}
+            order = np.argsort(o["read_idx"], kind="stable")
+            o = {f: v[order] for f, v in o.items()}
+        else:
+            o = {f: v[:0] for f, v in d.items() if f != "ln"}
+            o["asplice"] = np.zeros(0, np.uint8)
+        o["ln"] = d["ln"]
+        out.append(o)
+    return out
+
+
+def spliced_placements(wl: Workload, side: SideData, junctions: np.ndarray, max_mm: int = 2, min_anchor_len: int = 8, want_mm: bool = False):
+    """Junction-index segment hits of one side for the given junction set (segment_juncs output)."""
+    if side.cand is not None and not want_mm:
+        return _filter_by_junctions(side.cand, junctions)
+    assert side.truth is not None, "generate the workload with keep_truth=True or keep_candidates=True"
+    tr = side.truth
+    rows = np.nonzero(side.unmapped & ~tr["qc_fail"])[0]
+    cands = _placement_candidates(wl.cfg, wl.ref.codes, tr["fwd"][rows], tr["gpos"][rows], tr["ref_id"][rows], tr["rev"][rows], rows,
+                                  max_mm, min_anchor_len, want_mm)
+    return _filter_by_junctions(cands, junctions)
+
+
+@dataclasses.dataclass
+class PackedJoinBatch:
+    n_segs: int
+    read_words: int
+    bundles: np.ndarray
+    seg_count: np.ndarray
+    reads: np.ndarray
+    hits: np.ndarray
+
+    @property
+    def n_bundles(self) -> int:
+        return int(self.bundles.shape[0])
+
+    def nbytes(self) -> int:
+        return int(self.bundles.nbytes + self.seg_count.nbytes + self.reads.nbytes + self.hits.nbytes)
+
+
+def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> PackedJoinBatch:
+    """Per-read bundles of long_spanning_reads (JoinSegmentsWorker rules, long_spanning_reads.cpp:2706-2785): contiguous segment
+    hits followed by the junction-index hits mapped back to the genome (SplicedBAMHitFactory, bwt_map.cpp:1469-1770); a read is
+    kept when every segment has at least one hit."""
+    nseg = len(side.seg_hits)
+    n, L = side.reads.shape
+    spl = spliced_placements(wl, side, junctions)
+    counts = np.zeros((n, nseg), dtype=np.int64)
+    for k in range(nseg):
+        counts[:, k] = np.bincount(side.seg_hits[k]["read_idx"], minlength=n) + np.bincount(spl[k]["read_idx"], minlength=n)
+    visit = (counts > 0).all(axis=1)
+    sel = np.nonzero(visit)[0]
+    nb = sel.shape[0]
+    remap = np.full(n, -1, dtype=np.int64)
+    remap[sel] = np.arange(nb)
+    parts, keys = [], []
+    for k in range(nseg):
+        h = side.seg_hits[k]
+        b = remap[h["read_idx"]]; m = b >= 0
+        jh = np.zeros(int(m.sum()), dtype=JHIT_DTYPE)
+        hm = h[m]
+        jh["ref_id"] = hm["ref_id"]; jh["left"] = hm["left"]; jh["n_ops"] = 1; jh["flags"] = hm["flags"]; jh["mismatches"] = hm["edit_dist"]
+        jh["ops"][:, 0] = (hm["read_len"].astype(np.uint32) << 4) | OP_MATCH
+        parts.append(jh); keys.append(b[m] * (2 * nseg) + 2 * k)
+        d = spl[k]
+        b = remap[d["read_idx"]]; m = b >= 0
+        js = np.zeros(int(m.sum()), dtype=JHIT_DTYPE)
+        x = d["x"][m]; ln = d["ln"]
+        js["ref_id"] = d["ref_id"][m]; js["left"] = d["jl"][m] - x + 1; js["n_ops"] = 3
+        js["flags"] = np.where(d["anti"][m], HIT_ANTISENSE, 0) | (HIT_END if k == nseg - 1 else 0) | np.where(d["asplice"][m] > 0, JHIT_ANTISENSE_SPLICE, 0)
+        js["mismatches"] = d["nm"][m]; js["splice_mms"] = d["smm"][m]
+        js["ops"][:, 0] = (x.astype(np.uint32) << 4) | OP_MATCH
+        js["ops"][:, 1] = ((d["jr"][m] - d["jl"][m] - 1).astype(np.uint32) << 4) | OP_REF_SKIP
+        js["ops"][:, 2] = ((ln - x).astype(np.uint32) << 4) | OP_MATCH
+        parts.append(js); keys.append(b[m] * (2 * nseg) + 2 * k + 1)
+    allh = np.concatenate(parts); key = np.concatenate(keys)
+    allh = allh[np.argsort(key, kind="stable")]
+    bundles = np.zeros(nb, dtype=JBUNDLE_DTYPE)
+    bundles["read_id"] = side.ids[sel]
+    bundles["hit_begin"] = np.concatenate([[0], np.cumsum(counts[sel].sum(axis=1))])[:-1]
+    bundles["read_len"] = L; bundles["n_segs"] = nseg
+    rw = (L + 63) // 64
+    return PackedJoinBatch(nseg, rw, bundles, np.ascontiguousarray(counts[sel].astype("<u2")), pack_reads(side.reads[sel], rw), allh)
+
+
+def spliced_hits_for_sam(wl: Workload, side: SideData, junctions: np.ndarray, contigs):
+    """Placements (vectorised) -> the per-segment record lists write_spliced_sam consumes; needs keep_truth."""
+    key = {}
+    for (name, ref, left_start, jl, jr, typ, seq) in contigs:
+        if typ in ("ins", "del", "fus") or not isinstance(jr, int):
+            continue
+        key[(ref, jl, jr, 1 if name.endswith("|rev") else 0)] = (name, left_start, seq)
+    names = wl.ref.names
+    out = []
+    for d in spliced_placements(wl, side, junctions, want_mm=True):
+        rows = []
+        ln = d["ln"]
+        for i in range(d["read_idx"].shape[0]):
+            ent = key.get((names[int(d["ref_id"][i]) - 1], int(d["jl"][i]), int(d["jr"][i]), int(d["asplice"][i])))
+            if ent is None:
+                continue
+            name, left_start, cseq = ent
+            x = int(d["x"][i]); pos0 = (int(d["jl"][i]) - left_start + 1) - x
+            if pos0 < 0 or pos0 + ln > len(cseq):
+                continue
+            if d["nm"][i] == 0:
+                md = str(ln)
+            else:
+                mm = d["mm"][i]; parts, run = [], 0
+                for q in range(ln):
+                    if mm[q]:
+                        parts.append(str(run)); parts.append(cseq[pos0 + q] if cseq[pos0 + q] in "ACGT" else "N"); run = 0
+                    else:
+                        run += 1
+                parts.append(str(run)); md = "".join(parts)
+            rows.append(dict(read_idx=int(d["read_idx"][i]), contig=name, pos0=pos0, anti=bool(d["anti"][i]), fwd=d["fwd"][i], nm=int(d["nm"][i]), md=md))
+        out.append(rows)
+    return out
