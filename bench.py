@@ -306,12 +306,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        acc = dict(scan_ms=0.0, alg=0, launches=0, join_ms=0.0, join_alg=0, join_launches=0, kms={k: 0.0 for k in KERNELS})
+        acc = dict(scan_ms=0.0, alg=0, launches=0, join_ms=0.0, join_alg=0, join_launches=0, enum_ms=0.0, merge_ms=0.0,
+                   kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
         for _ in range(steps):
             res, tm, jt, n_joined, d2h = step(device_resident)
             acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
             acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
+            acc["enum_ms"] += jt.enum_ms; acc["merge_ms"] += jt.merge_ms
             for k in KERNELS:
                 acc["kms"][k] += getattr(tm, k + "_ms")
         e1.record(stream)
@@ -357,17 +359,20 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         #   hit         : 40 (read) per bundle + 16 per segment hit
         #   window_scan : 32 (descriptor) + 64 (two reference sectors) per window + 16 per emitted junction record
         #   rescue      : 32 + 128 per mate-anchor task;  indel: 32 + 64 per task + 16 per record
-        #   chain_join  : 56 per read + 48 per segment hit + 128 per closure + 96 per merged chain + 128 per output record
+        #   chain_enum  : 16 (header) per read + 48 per segment hit
+        #   chain_merge : 40 (read) per read + 128 per closure + 96 per merged chain + 128 per output record
         n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
         n_hh = sum(int(b.hits.shape[0]) for b in batches)
         steps = args.steps
         kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh,
                   "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
                   "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions)),
-                  "chain_join": A["join_alg"] / steps}
-        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_join"] = A["join_ms"] / steps
-        klaunch = {k: A["scan_launches"] for k in KERNELS}; klaunch["chain_join"] = max(1, A["join_launches"] // steps)
-        allk = KERNELS + ("chain_join",)
+                  "chain_enum": 16 * sum(b.n_bundles for b in jbatches) + 48 * sum(int(b.hits.shape[0]) for b in jbatches)}
+        kbytes["chain_merge"] = A["join_alg"] / steps - kbytes["chain_enum"]
+        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps; kms["chain_merge"] = A["merge_ms"] / steps
+        klaunch = {k: A["scan_launches"] for k in KERNELS}
+        klaunch["chain_enum"] = klaunch["chain_merge"] = max(1, A["join_launches"] // (2 * steps))
+        allk = KERNELS + ("chain_enum", "chain_merge")
         dom = max(allk, key=lambda k: kms[k])
         dom_ms = kms[dom] / klaunch[dom]; dom_bytes = kbytes[dom] / klaunch[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

@@ -270,7 +270,8 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* host_batch, const thb_jo
  * thb_join_fetch copies them to the host (same lifetime as above).                                          */
 int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* device_batch, uint64_t* n_out);
 int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out);
-typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; uint32_t launches; uint32_t reserved;
+typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; float enum_ms, merge_ms;   /* kernel_ms = enum + merge */
+                                 uint32_t launches;
                                  uint64_t n_chains, n_closures, n_joined, algorithmic_bytes; } thb_join_timing;
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out);
 

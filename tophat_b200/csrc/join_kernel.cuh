@@ -1,4 +1,5 @@
-// join_kernel.cuh -- long_spanning_reads' per-read arithmetic as one sm_100a kernel (thread = read).
+// join_kernel.cuh -- long_spanning_reads' per-read arithmetic as two sm_100a kernels:
+//   chain_enum_kernel (thread = read) enumerates segment-hit chains, chain_merge_kernel (thread = chain) merges them.
 //
 // Replaces, for --fusion-search off and base-space reads, the reference's
 //   join_segments_for_read   long_spanning_reads.cpp:2612-2667   (multihit guard, one DFS per first-segment hit)
@@ -130,8 +131,11 @@ __device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
   int n = (int)(a.z & 0xffu); if (n > THB_JHIT_MAX_OPS) n = THB_JHIT_MAX_OPS;
   LiteHit l; l.ref = a.x; l.left = (int)a.y; l.anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0;
   int r = l.left;
-  #pragma unroll
-  for (int i = 0; i < 9; ++i) if (i < n) { const int cc = opc(ops[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(ops[i]); }
+  if (n == 1) r += (int)opl(ops[0]);                 // the common case: one match op
+  else {
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) if (i < n) { const int cc = opc(ops[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(ops[i]); }
+  }
   l.right = r;
   return l;
 }
@@ -355,7 +359,9 @@ __device__ bool merge_chain(const RefView& ref, const JoinParams& P, const JoinS
       if (nNC == 0) return false;
     } else {
       if (!finalize(prev)) return false;
-      prev = curr;
+      prev.ref = curr.ref; prev.left = curr.left; prev.n = curr.n; prev.anti = curr.anti; prev.asplice = curr.asplice;
+      prev.mism = curr.mism; prev.smm = curr.smm; prev.seq_pos = curr.seq_pos; prev.seq_len = curr.seq_len;
+      for (int k = 0; k < curr.n; ++k) prev.ops[k] = curr.ops[k];
     }
   }
   if (!finalize(prev)) return false;
@@ -379,56 +385,64 @@ __device__ __forceinline__ void emit_joined(const JoinOut& o, const thb_joined& 
   o.rec[slot] = j;
 }
 
-// join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610) for one read
-__device__ void join_read(const RefView& ref, const JoinParams& P, const JoinSets& S, const JoinBatchView& bv, const JoinOut& o,
-                          uint32_t bi, unsigned& n_leaves, unsigned& n_closures, unsigned& n_emit)
+// Reverse complement of a whole read held as stride-4 planes (non-ACGT stays N, reads.cpp:191-207): reverse the 256-bit
+// planes (bit reversal of every word, words in reverse order), shift right by 256 - n, complement the code bits.
+__device__ __forceinline__ void revcomp_read(const uint64_t* F, int n, uint64_t* R)
+{
+  const int sh = 256 - n, ws = sh >> 6, bs = sh & 63;
+  #pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    uint64_t t[5];
+    #pragma unroll
+    for (int w = 0; w < 4; ++w) t[w] = __brevll(F[pl * 4 + 3 - w]);
+    t[4] = 0;
+    #pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      uint64_t lo = 0, hi = 0;
+      #pragma unroll
+      for (int k = 0; k < 5; ++k) { if (k == w + ws) lo = t[k]; if (k == w + ws + 1) hi = t[k]; }
+      R[pl * 4 + w] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+    }
+  }
+  #pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int rem = n - 64 * w; const uint64_t valid = rem >= 64 ? ~0ull : (rem > 0 ? ((1ull << rem) - 1ull) : 0ull);
+    const uint64_t keep = valid & ~R[8 + w];
+    R[w] = ~R[w] & keep; R[4 + w] = ~R[4 + w] & keep;
+  }
+}
+
+struct ChainQueue {
+  uint32_t* tasks; unsigned long long cap; uint32_t stride;     // task = [bundle, hit index of segment 0 .. n-1] (absolute indices)
+  unsigned long long* count; unsigned int* overflow;
+};
+
+// K-J1: join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610): enumerate the compatible segment-hit chains of one
+// read in the reference's DFS order, with its budget of 10,000 complete chains per first-segment hit.
+__device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const ChainQueue& q, uint32_t bi, unsigned& n_leaves)
 {
   const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
-  const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
+  const int n = (int)((hdr.z >> 16) & 0xffu);
   if (n < 1 || n > JMAXSEGS) return;
   uint32_t off[JMAXSEGS]; int cnt[JMAXSEGS];
   { uint32_t a = hdr.y;
     for (int s = 0; s < n; ++s) { cnt[s] = (int)__ldg(bv.seg_count + (size_t)bi * bv.n_segs + s); off[s] = a; a += (uint32_t)cnt[s]; } }
   if (P.bowtie2) for (int s = 0; s < n; ++s) if (cnt[s] > P.max_seg_multihits) return;      // 2624-2632
-  // the read in both orientations, stride-4 planes
-  uint64_t Rf[12], Rr[12];
-  { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
-    for (int k = 0; k < 12; ++k) { Rf[k] = 0; Rr[k] = 0; }
-    for (int pl = 0; pl < 3; ++pl) for (int w = 0; w < rw && w < 4; ++w) Rf[pl * 4 + w] = __ldg(rd + pl * rw + w);
-    // reverse complement of the whole read (non-ACGT stays N, reads.cpp:191-207)
-    for (int i = 0; i < read_len; ++i) {
-      const int c = read_code5(Rf, read_len - 1 - i); const int w = i >> 6, j = i & 63;
-      if (c == 4) Rr[8 + w] |= 1ull << j; else { const int d = 3 - c; if (d & 1) Rr[w] |= 1ull << j; if (d & 2) Rr[4 + w] |= 1ull << j; }
-    } }
-  int seglen_of[JMAXSEGS];
-  for (int s = 0; s < n; ++s) seglen_of[s] = (s == n - 1) ? read_len - s * P.seglen : P.seglen;
-
-  int sel[JMAXSEGS], it[JMAXSEGS];
-  const thb_jhit* chain[JMAXSEGS]; int clen[JMAXSEGS];
+  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS];
   auto leaf = [&]() {
     ++n_leaves;
-    thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0;
-    bool ok;
-    if (n == 1) {                                                  // merge_segment_chain, single hit (2196-2213)
-      WHit w; load_whit(w, bv.hits + off[0] + sel[0], 0, read_len);
-      ok = w.n > 0 && valid_cigar(P, w.ops, w.n);
-      if (ok) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
-                j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
-                for (int k = 0; k < w.n; ++k) j.ops[k] = w.ops[k]; }
-    } else {
-      const bool anti = (bv.hits[off[0] + sel[0]].flags & THB_HIT_ANTISENSE) != 0;     // chain orientation (2117-2121)
-      for (int e = 0; e < n; ++e) { const int s = anti ? n - 1 - e : e; chain[e] = bv.hits + off[s] + sel[s]; clen[e] = seglen_of[s]; }
-      ok = merge_chain(ref, P, S, anti ? Rr : Rf, chain, clen, n, j, n_closures);
-      if (ok) ok = valid_cigar(P, j.ops, j.n_ops);
-    }
-    if (ok) { emit_joined(o, j); ++n_emit; }
+    const unsigned long long slot = atomicAdd(q.count, 1ull);
+    if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
+    uint32_t* t = q.tasks + slot * q.stride;
+    t[0] = bi;
+    for (int s = 0; s < n; ++s) t[1 + s] = off[s] + (uint32_t)sel[s];
   };
   for (int i0 = 0; i0 < cnt[0]; ++i0) {
     sel[0] = i0;
     int num_try = 10000;                                           // 2647
     if (n == 1) { --num_try; leaf(); continue; }
     int lvl = 1; it[1] = 0;
-    LiteHit top[JMAXSEGS]; top[0] = load_lite(bv.hits + off[0] + i0);
+    top[0] = load_lite(bv.hits + off[0] + i0);
     while (lvl >= 1) {
       if (it[lvl] >= cnt[lvl]) { --lvl; if (lvl >= 1) ++it[lvl]; continue; }
       const LiteHit cand = load_lite(bv.hits + off[lvl] + it[lvl]);
@@ -440,18 +454,68 @@ __device__ void join_read(const RefView& ref, const JoinParams& P, const JoinSet
   }
 }
 
-__global__ void __launch_bounds__(128)
-chain_join_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, JoinOut o)
+__global__ void __launch_bounds__(256)
+chain_enum_kernel(JoinParams P, JoinBatchView bv, ChainQueue q, unsigned long long* counters)
 {
-  unsigned n_leaves = 0, n_closures = 0, n_emit = 0;
+  unsigned n_leaves = 0;
   const unsigned lane = threadIdx.x & 31u;
   for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < bv.n_bundles; base += gridDim.x * blockDim.x) {
-    if (base + lane < bv.n_bundles) join_read(ref, P, S, bv, o, base + lane, n_leaves, n_closures, n_emit);
+    if (base + lane < bv.n_bundles) enum_read(P, bv, q, base + lane, n_leaves);
     __syncwarp();
   }
-  for (int k = 16; k > 0; k >>= 1) { n_leaves += __shfl_xor_sync(0xffffffffu, n_leaves, k); n_closures += __shfl_xor_sync(0xffffffffu, n_closures, k); n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k); }
-  if (lane == 0) { if (n_leaves) atomicAdd(o.counters + 0, (unsigned long long)n_leaves); if (n_closures) atomicAdd(o.counters + 1, (unsigned long long)n_closures);
-                   if (n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit); }
+  for (int k = 16; k > 0; k >>= 1) n_leaves += __shfl_xor_sync(0xffffffffu, n_leaves, k);
+  if (lane == 0 && n_leaves) atomicAdd(counters + 0, (unsigned long long)n_leaves);
+}
+
+// K-J2: merge_segment_chain (2101-2220) + merge_chain (805-2038) + valid_hit (2045-2099) for one chain
+__device__ void merge_task(const RefView& ref, const JoinParams& P, const JoinSets& S, const JoinBatchView& bv, const ChainQueue& q,
+                           const JoinOut& o, unsigned long long ti, unsigned& n_closures, unsigned& n_emit)
+{
+  const uint32_t* __restrict__ t = q.tasks + ti * q.stride;
+  const uint32_t bi = t[0];
+  const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
+  const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
+  thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0;
+  bool ok;
+  if (n == 1) {                                                    // merge_segment_chain, single hit (2196-2213)
+    WHit w; load_whit(w, bv.hits + t[1], 0, read_len);
+    ok = w.n > 0 && valid_cigar(P, w.ops, w.n);
+    if (ok) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
+              j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
+              for (int k = 0; k < w.n; ++k) j.ops[k] = w.ops[k]; }
+  } else {
+    uint64_t Rf[12], R[12];
+    { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
+      #pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) Rf[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull; }
+    const bool anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE;     // chain orientation (2117-2121)
+    if (anti) revcomp_read(Rf, read_len, R);
+    else {
+      #pragma unroll
+      for (int k = 0; k < 12; ++k) R[k] = Rf[k];
+    }
+    const thb_jhit* chain[JMAXSEGS]; int clen[JMAXSEGS];
+    for (int e = 0; e < n; ++e) { const int s = anti ? n - 1 - e : e; chain[e] = bv.hits + t[1 + s]; clen[e] = (s == n - 1) ? read_len - s * P.seglen : P.seglen; }
+    ok = merge_chain(ref, P, S, R, chain, clen, n, j, n_closures);
+    if (ok) ok = valid_cigar(P, j.ops, j.n_ops);
+  }
+  if (ok) { emit_joined(o, j); ++n_emit; }
+}
+
+__global__ void __launch_bounds__(128)
+chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, ChainQueue q, JoinOut o)
+{
+  unsigned n_closures = 0, n_emit = 0;
+  unsigned long long n = *q.count; if (n > q.cap) n = q.cap;
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < n; base += (unsigned long long)gridDim.x * blockDim.x) {
+    if (base + lane < n) merge_task(ref, P, S, bv, q, o, base + lane, n_closures, n_emit);
+    __syncwarp();
+  }
+  for (int k = 16; k > 0; k >>= 1) { n_closures += __shfl_xor_sync(0xffffffffu, n_closures, k); n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k); }
+  if (lane == 0) { if (n_closures) atomicAdd(o.counters + 1, (unsigned long long)n_closures); if (n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit); }
 }
 
 }  // namespace thb

@@ -90,7 +90,7 @@ struct thb_ctx {
   uint64_t n_ins_out = 0, n_del_out = 0;
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // long_spanning_reads join
-  DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out; uint64_t j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
+  DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
   JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
@@ -328,7 +328,7 @@ void thb_destroy(thb_ctx* ctx)
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
-                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out }) b->release();
+                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
@@ -665,26 +665,37 @@ static int join_validate(thb_ctx* ctx, const thb_join_batch* b)
 static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsigned long long* n_res)
 {
   ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+  ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
   unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f;
+  const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
     CU(ctx->j_out.reserve(ctx->j_cap_out * sizeof(thb_joined)));
+    CU(ctx->j_chain.reserve(ctx->j_cap_chain * stride * sizeof(uint32_t)));
     CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
     JoinOut o; o.rec = (thb_joined*)ctx->j_out.p; o.cap = ctx->j_cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
+    ChainQueue q; q.tasks = (uint32_t*)ctx->j_chain.p; q.cap = ctx->j_cap_chain; q.stride = stride; q.count = ctx->d_qcounts + 1; q.overflow = ctx->d_qovf;
     CU(cudaEventRecord(ctx->kev[0], ctx->compute));
-    chain_join_kernel<<<grid_for(bv.n_bundles, 128), 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, o);
-    CU(cudaGetLastError());
+    chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
     CU(cudaEventRecord(ctx->kev[1], ctx->compute));
-    ctx->jtiming.launches++;
-    unsigned int ovf = 0;
-    CU(cudaMemcpyAsync(&n, ctx->d_qcounts, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    chain_merge_kernel<<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->kev[2], ctx->compute));
+    ctx->jtiming.launches += 2;
+    unsigned int ovf = 0; unsigned long long qn[2] = {0, 0};
+    CU(cudaMemcpyAsync(qn, ctx->d_qcounts, 16, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
-    if (!ovf && n <= ctx->j_cap_out) { CU(cudaEventElapsedTime(&kms, ctx->kev[0], ctx->kev[1])); break; }
-    ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out * 2, n + 1024);
+    n = qn[0];
+    if (!ovf && n <= ctx->j_cap_out && qn[1] <= ctx->j_cap_chain) {
+      float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
+      kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2; break;
+    }
+    ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, 2 * n + 1024);
+    ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, 2 * qn[1] + 1024);
     if (attempt == 23) return fail(ctx, THB_ENOMEM, "joined-hit buffer still overflows");
   }
   thb_join_timing& t = ctx->jtiming;
