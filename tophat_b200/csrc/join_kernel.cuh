@@ -197,185 +197,96 @@ __device__ __forceinline__ bool editdist_consistent(const RefView& ref, uint32_t
 __device__ __forceinline__ bool cig_push(uint32_t* ops, int& n, uint32_t op)
 { if (n >= JMAXOPS) return false; ops[n++] = op; return true; }
 
-// merge_chain (805-2038), fusion_dir == FUSION_NOTHING, base space.  `chain[e]` are the hits in genomic order, R the
-// read in the chain's orientation, seq_len[e] the read bases of element e.  Returns false where the reference
-// returns an empty BowtieHit.
-__device__ bool merge_chain(const RefView& ref, const JoinParams& P, const JoinSets& S, const uint64_t* R,
-                            const thb_jhit* const* chain, const int* seq_len, int n, thb_joined& out, unsigned& n_closures)
+// ---- merge_chain (805-2038), fusion_dir == FUSION_NOTHING, base space -- the pieces ----------------------------------
+// The closure searches are separate functions so that chain_merge_kernel can run them as warp-converged phases.
+
+// junction / deletion closure (1311-1591) between prev (ending at pright, last op length prml) and curr (starting at
+// cleft, first op length clml).  Returns false where the reference finds no closure.
+struct JuncClosure { int dtl; uint32_t glen; bool anti; int new_diff; };
+__device__ __forceinline__ int junction_closure(const RefView& ref, const JoinSets& S, const uint64_t* R, uint64_t cs, int64_t clen,
+                                                uint32_t ref_id, int pright, int cleft, int prml, int clml, int prev_seq_end, int curr_seq_pos,
+                                                JuncClosure& out)
 {
-  // first pass (843-897): more than one gap that only a fusion could explain -> give up
-  {
-    int num_fusions = 0;
-    LiteHit prev = load_lite(chain[0]);
-    for (int e = 1; e < n; ++e) {
-      const LiteHit curr = load_lite(chain[e]);
-      if (prev.ref != curr.ref) ++num_fusions;
-      else {
-        const int gap = curr.left - prev.right;
-        const int hi = min(P.max_report_intron, P.fusion_min_dist);
-        if (gap < -P.max_ins || (gap > P.max_del && (gap < P.min_report_intron || gap > hi))) ++num_fusions;
+  // return: 1 found, 0 not found, -1 chain invalid (reference would read outside the contig)
+  const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(cleft + 4);
+  uint32_t it = junc_upper_bound(S, ref_id, lbnd, rbnd - 8u, 1u);
+  const uint32_t ub = junc_lower_bound(S, ref_id, lbnd + 8u, rbnd, 0u);
+  int new_diff = 0xff; bool found = false;
+  for (; it != ub && it < S.n_juncs; ++it) {
+    const thb_junction J = S.juncs[it];
+    const int dtl = (int)(J.left - (uint32_t)pright + 1u), dtr = (int)(J.right - (uint32_t)cleft);
+    if (!(abs(dtl) <= 4 && abs(dtr) <= 4 && dtl == dtr)) continue;
+    if (dtl > clml || -dtl > prml) continue;                  // enough matched bases on either side (1343-1348)
+    int new_mm = 0, old_mm = 0;
+    if (dtl > 0) {
+      if ((int64_t)pright + dtl > clen || (int64_t)cleft + dtl > clen) return -1;
+      for (int i = 0; i < dtl; ++i) {
+        const int sc = read_code5(R, curr_seq_pos + i);
+        if (sc != ref_code5(ref, cs + (uint64_t)(pright + i))) ++new_mm;
+        if (sc != ref_code5(ref, cs + (uint64_t)(cleft + i))) ++old_mm;
       }
-      if (num_fusions >= 2) return false;
-      prev = curr;
+    } else if (dtl < 0) {
+      const int ad = -dtl;
+      if ((int64_t)J.right + ad > clen) return -1;
+      for (int i = 0; i < ad; ++i) {
+        const int sc = read_code5(R, prev_seq_end - (ad - i));
+        if (sc != ref_code5(ref, cs + (uint64_t)J.right + (uint64_t)i)) ++new_mm;
+        if (sc != ref_code5(ref, cs + (uint64_t)J.left + 1u + (uint64_t)i)) ++old_mm;
+      }
     }
+    const int temp = new_mm - old_mm;
+    if (temp >= new_diff || new_mm >= 2) continue;            // first strictly better candidate in Junction order (1497-1512)
+    new_diff = temp; out.dtl = dtl; out.glen = J.right - J.left - 1u; out.anti = J.antisense != 0; found = true;
   }
-  if (!(chain[0]->ref_id >= 1 && chain[0]->ref_id <= ref.n_contigs)) return false;
-  const uint64_t cs = __ldg(ref.contig_start + chain[0]->ref_id - 1);
-  const int64_t clen = (int64_t)__ldg(ref.contig_len + chain[0]->ref_id - 1);
+  out.new_diff = new_diff;
+  return found ? 1 : 0;
+}
 
-  // accumulators of the final pass (1888-1945), filled as blocks are finalised
-  uint32_t LC[JMAXOPS]; int nLC = 0; int num_mm = 0, num_smm = 0; bool saw_as = false, saw_s = false;
-  int old_read_length = 0;
-  auto finalize = [&](const WHit& h) -> bool {
-    num_mm += h.mism; num_smm += h.smm;
-    if (cig_spliced(h.ops, h.n)) {
-      if (h.asplice) { if (saw_s) return false; saw_as = true; } else { if (saw_as) return false; saw_s = true; }
-    }
-    int b = 0;
-    if (nLC > 0 && opc(LC[nLC - 1]) == opc(h.ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(h.ops[0])); b = 1; }
-    for (; b < h.n; ++b) if (!cig_push(LC, nLC, h.ops[b])) return false;
-    return true;
-  };
-
-  WHit prev; load_whit(prev, chain[0], 0, seq_len[0]);
-  const int left0 = prev.left; const uint32_t ref0 = prev.ref;
-  old_read_length += cig_read_len(prev.ops, prev.n);
-  bool antisense = prev.anti;
-  for (int e = 1; e < n; ++e) {
-    WHit curr; load_whit(curr, chain[e], prev.seq_pos + prev.seq_len, seq_len[e]);
-    old_read_length += cig_read_len(curr.ops, curr.n);
-    antisense = prev.anti;
-    if (!(opc(prev.ops[prev.n - 1]) == OP_MATCH || opc(curr.ops[0]) == OP_MATCH)) return false;          // 930-934
-    const bool ps = cig_spliced(prev.ops, prev.n), csp = cig_spliced(curr.ops, curr.n);
-    if (ps && csp && prev.asplice != curr.asplice) return false;                                          // 942-949
-    bool found = false;
-    bool antisense_closure = ps ? prev.asplice : curr.asplice;
-    int mismatch = 0;
-    const int prml = (int)opl(prev.ops[prev.n - 1]), clml = (int)opl(curr.ops[0]);
-    const int pright = cig_right(prev.left, prev.ops, prev.n);
-    const int dist = curr.left - pright;
-    const bool same_strand = prev.anti == curr.anti;
-    uint32_t NC[JMAXOPS]; int nNC = 0;
-    if (curr.ref != prev.ref) return false;
-    if (dist < 0 && dist >= -P.max_ins && same_strand) {
-      // ---- insertion closure (1010-1306)
-      const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(curr.left + 4);
-      uint32_t it = ins_upper_bound(S, prev.ref, lbnd, 0u);
-      const uint32_t ub = ins_upper_bound(S, prev.ref, rbnd, (uint32_t)P.max_ins);
-      n_closures++;
-      int best_itpr = 0; uint32_t best_len = 0;
-      for (; it != ub && it < S.n_ins; ++it) {
-        const thb_insertion& I = S.ins[it];
-        if ((int)I.len != pright - curr.left) continue;
-        const int itpr = pright - (int)I.left - 1;               // insert_to_prev_right
-        const int clti = (int)I.left - curr.left + 1;            // curr_left_to_insert
-        if (itpr > prml || clti > clml) continue;
-        int this_ref_mm = 0, ins_mm = 0; const int ilen = (int)I.len;
-        auto ins_code = [&](int k) -> int { const char ch = I.seq[k]; return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; };
-        if (itpr > 0) {
-          // referenceSequence = ref[I.left + 1, prev.right); old/new segment = last itpr bases of prev's sequence
-          const int64_t g0 = (int64_t)I.left + 1; const int s0 = prev.seq_pos + prev.seq_len - itpr;
-          if (g0 < 0 || g0 + itpr > clen) return false;
-          for (int ri = 0; ri < itpr; ++ri) {
-            const int rc = ref_code5(ref, cs + (uint64_t)(g0 + ri)), sc = read_code5(R, s0 + ri);
-            if (rc == 4 || rc != sc) ++this_ref_mm;
-            if (ri < ilen) { const int ic = ins_code(ri); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
-            else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + ri - ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
-          }
-        }
-        if (clti > 0) {
-          // referenceSequence = ref[curr.left, I.left + 1); old/new segment = first clti bases of curr's sequence
-          const int64_t g0 = curr.left; const int s0 = curr.seq_pos;
-          if (g0 < 0 || g0 + clti > clen) return false;
-          for (int ri = 0; ri < clti; ++ri) {
-            const int sp = clti - ri - 1, ip = ilen - ri - 1;
-            const int rc = ref_code5(ref, cs + (uint64_t)(g0 + sp)), sc = read_code5(R, s0 + sp);
-            if (rc == 4 || rc != sc) ++this_ref_mm;
-            if (ri < ilen) { const int ic = ins_code(ip); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
-            else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + sp + ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
-          }
-        }
-        if (found) return false;                                  // a second same-length candidate rejects the chain (1246-1250)
-        if (ins_mm == 0) { mismatch = -this_ref_mm; found = true; best_itpr = itpr; best_len = I.len; }
+// insertion closure (1010-1306).  Returns 1 found (itpr / len / mismatch filled), 0 none, -1 chain invalid
+struct InsClosure { int itpr; uint32_t len; int mismatch; };
+__device__ __forceinline__ int insertion_closure(const RefView& ref, const JoinSets& S, const JoinParams& P, const uint64_t* R, uint64_t cs,
+                                                 int64_t clen, uint32_t ref_id, int pright, int cleft, int prml, int clml, int prev_seq_end,
+                                                 int curr_seq_pos, InsClosure& out)
+{
+  const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(cleft + 4);
+  uint32_t it = ins_upper_bound(S, ref_id, lbnd, 0u);
+  const uint32_t ub = ins_upper_bound(S, ref_id, rbnd, (uint32_t)P.max_ins);
+  bool found = false;
+  for (; it != ub && it < S.n_ins; ++it) {
+    const thb_insertion& I = S.ins[it];
+    if ((int)I.len != pright - cleft) continue;
+    const int itpr = pright - (int)I.left - 1;               // insert_to_prev_right
+    const int clti = (int)I.left - cleft + 1;                // curr_left_to_insert
+    if (itpr > prml || clti > clml) continue;
+    int this_ref_mm = 0, ins_mm = 0; const int ilen = (int)I.len;
+    auto ins_code = [&](int k) -> int { const char ch = I.seq[k]; return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; };
+    if (itpr > 0) {
+      // referenceSequence = ref[I.left + 1, prev.right); old/new segment = last itpr bases of prev's sequence
+      const int64_t g0 = (int64_t)I.left + 1; const int s0 = prev_seq_end - itpr;
+      if (g0 < 0 || g0 + itpr > clen) return -1;
+      for (int ri = 0; ri < itpr; ++ri) {
+        const int rc = ref_code5(ref, cs + (uint64_t)(g0 + ri)), sc = read_code5(R, s0 + ri);
+        if (rc == 4 || rc != sc) ++this_ref_mm;
+        if (ri < ilen) { const int ic = ins_code(ri); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
+        else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + ri - ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
       }
-      if (!found) return false;
-      // new cigar (1262-1290); lengths are uint32 in the reference, the arithmetic wraps the same way
-      for (int k = 0; k < prev.n; ++k) NC[nNC++] = prev.ops[k];
-      { const uint32_t bl = opl(NC[nNC - 1]) - (uint32_t)best_itpr; if ((bl & 0x0fffffffu) == 0) --nNC; else NC[nNC - 1] = mkop(opc(NC[nNC - 1]), bl & 0x0fffffffu); }
-      if (!cig_push(NC, nNC, mkop(OP_INS, best_len))) return false;
-      { const uint32_t fl = (opl(curr.ops[0]) + (uint32_t)(best_itpr - (int)best_len)) & 0x0fffffffu;
-        int c0 = 1; if (fl > 0) { c0 = 0; }
-        for (int k = c0; k < curr.n; ++k) if (!cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), fl) : curr.ops[k])) return false; }
-    } else if (dist > 0 && dist <= P.max_report_intron && same_strand) {
-      // ---- junction / deletion closure (1311-1591)
-      const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(curr.left + 4);
-      uint32_t it = junc_upper_bound(S, prev.ref, lbnd, rbnd - 8u, 1u);
-      const uint32_t ub = junc_lower_bound(S, prev.ref, lbnd + 8u, rbnd, 0u);
-      n_closures++;
-      int new_diff = 0xff, best_dtl = 0; uint32_t best_glen = 0; bool best_anti = false;
-      for (; it != ub && it < S.n_juncs; ++it) {
-        const thb_junction J = S.juncs[it];
-        const int dtl = (int)(J.left - (uint32_t)pright + 1u), dtr = (int)(J.right - (uint32_t)curr.left);
-        if (!(abs(dtl) <= 4 && abs(dtr) <= 4 && dtl == dtr)) continue;
-        if (dtl > clml || -dtl > prml) continue;                  // enough matched bases on either side (1343-1348)
-        int new_mm = 0, old_mm = 0;
-        if (dtl > 0) {
-          if ((int64_t)pright + dtl > clen || (int64_t)curr.left + dtl > clen) return false;
-          for (int i = 0; i < dtl; ++i) {
-            const int sc = read_code5(R, curr.seq_pos + i);
-            if (sc != ref_code5(ref, cs + (uint64_t)(pright + i))) ++new_mm;
-            if (sc != ref_code5(ref, cs + (uint64_t)(curr.left + i))) ++old_mm;
-          }
-        } else if (dtl < 0) {
-          const int ad = -dtl;
-          if ((int64_t)J.right + ad > clen) return false;
-          for (int i = 0; i < ad; ++i) {
-            const int sc = read_code5(R, prev.seq_pos + prev.seq_len - (ad - i));
-            if (sc != ref_code5(ref, cs + (uint64_t)J.right + (uint64_t)i)) ++new_mm;
-            if (sc != ref_code5(ref, cs + (uint64_t)J.left + 1u + (uint64_t)i)) ++old_mm;
-          }
-        }
-        const int temp = new_mm - old_mm;
-        if (temp >= new_diff || new_mm >= 2) continue;            // first strictly better candidate in Junction order (1497-1512)
-        new_diff = temp; best_dtl = dtl; best_glen = J.right - J.left - 1u; best_anti = J.antisense != 0; found = true;
+    }
+    if (clti > 0) {
+      // referenceSequence = ref[curr.left, I.left + 1); old/new segment = first clti bases of curr's sequence
+      const int64_t g0 = cleft; const int s0 = curr_seq_pos;
+      if (g0 < 0 || g0 + clti > clen) return -1;
+      for (int ri = 0; ri < clti; ++ri) {
+        const int sp = clti - ri - 1, ip = ilen - ri - 1;
+        const int rc = ref_code5(ref, cs + (uint64_t)(g0 + sp)), sc = read_code5(R, s0 + sp);
+        if (rc == 4 || rc != sc) ++this_ref_mm;
+        if (ri < ilen) { const int ic = ins_code(ip); if (ic == 4 || ic != sc) { ++ins_mm; break; } }
+        else { const int rc2 = ref_code5(ref, cs + (uint64_t)(g0 + sp + ilen)); if (rc2 == 4 || rc2 != sc) --this_ref_mm; }
       }
-      if (!found) return false;
-      mismatch = new_diff;
-      for (int k = 0; k < prev.n; ++k) NC[nNC++] = prev.ops[k];
-      { const int nlb = prml + best_dtl; if (nlb > 0) NC[nNC - 1] = mkop(opc(NC[nNC - 1]), (uint32_t)nlb); else --nNC; }
-      if (best_glen <= (uint32_t)P.max_del) { if (!cig_push(NC, nNC, mkop(OP_DEL, best_glen))) return false; }
-      else { if (!cig_push(NC, nNC, mkop(OP_REF_SKIP, best_glen))) return false; antisense_closure = best_anti; }
-      { const int nrf = clml - best_dtl;
-        for (int k = nrf > 0 ? 0 : 1; k < curr.n; ++k) if (!cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), (uint32_t)nrf) : curr.ops[k])) return false; }
-    } else if (!(dist == 0 && same_strand)) {
-      return false;                                               // only a fusion could close this gap (1592-1819)
     }
-    if (found) {
-      // merged_hit (1822-1838); _mismatches / _edit_dist are unsigned chars in the reference
-      const int mm = (int)prev.mism + (int)curr.mism + mismatch;
-      prev.n = nNC; for (int k = 0; k < nNC; ++k) prev.ops[k] = NC[k];
-      prev.asplice = antisense_closure; prev.anti = antisense; prev.mism = (uint8_t)mm; prev.smm = (uint8_t)(prev.smm + curr.smm);
-      prev.seq_len += curr.seq_len;
-      if (nNC == 0) return false;
-    } else {
-      if (!finalize(prev)) return false;
-      prev.ref = curr.ref; prev.left = curr.left; prev.n = curr.n; prev.anti = curr.anti; prev.asplice = curr.asplice;
-      prev.mism = curr.mism; prev.smm = curr.smm; prev.seq_pos = curr.seq_pos; prev.seq_len = curr.seq_len;
-      for (int k = 0; k < curr.n; ++k) prev.ops[k] = curr.ops[k];
-    }
+    if (found) return -1;                                     // a second same-length candidate rejects the chain (1246-1250)
+    if (ins_mm == 0) { out.mismatch = -this_ref_mm; out.itpr = itpr; out.len = I.len; found = true; }
   }
-  if (!finalize(prev)) return false;
-  // new_hit (1947-1957) + final checks (2023-2035)
-  if (nLC == 0) return false;
-  const uint8_t mism = (uint8_t)num_mm;
-  const uint8_t edit = (uint8_t)(num_mm + cig_gap_length(LC, nLC));
-  if (cig_read_len(LC, nLC) != old_read_length) return false;
-  if (!editdist_consistent(ref, ref0, left0, LC, nLC, R, 4, mism)) return false;
-  out.ref_id = ref0; out.left = left0; out.n_ops = (uint8_t)nLC;
-  out.flags = (uint8_t)((antisense ? THB_HIT_ANTISENSE : 0) | (saw_as ? THB_JHIT_ANTISENSE_SPLICE : 0));
-  out.mismatches = mism; out.edit_dist = edit; out.splice_mms = (uint8_t)num_smm;
-  for (int k = 0; k < nLC; ++k) out.ops[k] = LC[k];
-  return true;
+  return found ? 1 : 0;
 }
 
 __device__ __forceinline__ void emit_joined(const JoinOut& o, const thb_joined& j)
@@ -431,7 +342,10 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
   int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS];
   auto leaf = [&]() {
     ++n_leaves;
-    const unsigned long long slot = atomicAdd(q.count, 1ull);
+    unsigned long long slot;
+    { const unsigned m = __activemask(); const unsigned ln = threadIdx.x & 31u; const int leader = __ffs((int)m) - 1;
+      unsigned long long b0 = 0; if ((int)ln == leader) b0 = atomicAdd(q.count, (unsigned long long)__popc(m));
+      b0 = __shfl_sync(m, b0, leader); slot = b0 + (unsigned long long)__popc(m & ((1u << ln) - 1u)); }
     if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
     uint32_t* t = q.tasks + slot * q.stride;
     t[0] = bi;
@@ -467,51 +381,227 @@ chain_enum_kernel(JoinParams P, JoinBatchView bv, ChainQueue q, unsigned long lo
   if (lane == 0 && n_leaves) atomicAdd(counters + 0, (unsigned long long)n_leaves);
 }
 
-// K-J2: merge_segment_chain (2101-2220) + merge_chain (805-2038) + valid_hit (2045-2099) for one chain
-__device__ void merge_task(const RefView& ref, const JoinParams& P, const JoinSets& S, const JoinBatchView& bv, const ChainQueue& q,
-                           const JoinOut& o, unsigned long long ti, unsigned& n_closures, unsigned& n_emit)
-{
-  const uint32_t* __restrict__ t = q.tasks + ti * q.stride;
-  const uint32_t bi = t[0];
-  const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
-  const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
-  thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0;
-  bool ok;
-  if (n == 1) {                                                    // merge_segment_chain, single hit (2196-2213)
-    WHit w; load_whit(w, bv.hits + t[1], 0, read_len);
-    ok = w.n > 0 && valid_cigar(P, w.ops, w.n);
-    if (ok) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
-              j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
-              for (int k = 0; k < w.n; ++k) j.ops[k] = w.ops[k]; }
-  } else {
-    uint64_t Rf[12], R[12];
-    { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
-      #pragma unroll
-      for (int pl = 0; pl < 3; ++pl)
-        #pragma unroll
-        for (int w = 0; w < 4; ++w) Rf[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull; }
-    const bool anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE;     // chain orientation (2117-2121)
-    if (anti) revcomp_read(Rf, read_len, R);
-    else {
-      #pragma unroll
-      for (int k = 0; k < 12; ++k) R[k] = Rf[k];
-    }
-    const thb_jhit* chain[JMAXSEGS]; int clen[JMAXSEGS];
-    for (int e = 0; e < n; ++e) { const int s = anti ? n - 1 - e : e; chain[e] = bv.hits + t[1 + s]; clen[e] = (s == n - 1) ? read_len - s * P.seglen : P.seglen; }
-    ok = merge_chain(ref, P, S, R, chain, clen, n, j, n_closures);
-    if (ok) ok = valid_cigar(P, j.ops, j.n_ops);
-  }
-  if (ok) { emit_joined(o, j); ++n_emit; }
-}
-
+// K-J2: merge_segment_chain (2101-2220) + merge_chain (805-2038) + valid_hit (2045-2099), one chain per thread.
+// Every lane walks the same phase sequence with an `alive` predicate and the warp re-converges at each __syncwarp():
+// the closure searches (equal-length binary searches) and the consistency re-read then run with all the lanes that
+// need them side by side (profiles/r1h: 4 of 32 lanes active in the straightforward per-thread form).
 __global__ void __launch_bounds__(128)
 chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, ChainQueue q, JoinOut o)
 {
   unsigned n_closures = 0, n_emit = 0;
-  unsigned long long n = *q.count; if (n > q.cap) n = q.cap;
+  unsigned long long nq = *q.count; if (nq > q.cap) nq = q.cap;
   const unsigned lane = threadIdx.x & 31u;
-  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < n; base += (unsigned long long)gridDim.x * blockDim.x) {
-    if (base + lane < n) merge_task(ref, P, S, bv, q, o, base + lane, n_closures, n_emit);
+  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long ti = base + lane;
+    // ---- phase 0: task, read, orientation
+    bool alive = ti < nq;
+    const uint32_t* __restrict__ t = q.tasks + (alive ? ti : 0) * q.stride;
+    uint32_t bi = 0; int read_len = 0, n = 0; bool anti = false;
+    uint64_t R[12];
+    #pragma unroll
+    for (int k = 0; k < 12; ++k) R[k] = 0;
+    if (alive) {
+      bi = t[0];
+      const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
+      read_len = (int)(hdr.z & 0xffffu); n = (int)((hdr.z >> 16) & 0xffu);
+      const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
+      #pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) R[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull;
+      anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE;       // chain orientation (2117-2121)
+    }
+    __syncwarp();
+    if (alive && anti && n > 1) { uint64_t F[12];
+      #pragma unroll
+      for (int k = 0; k < 12; ++k) F[k] = R[k];
+      revcomp_read(F, read_len, R); }
+    __syncwarp();
+    int nmax = n;
+    #pragma unroll
+    for (int k = 16; k > 0; k >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, k));
+    auto chain_hit = [&](int e) -> const thb_jhit* { const int s = anti ? n - 1 - e : e; return bv.hits + t[1 + s]; };
+    auto chain_len = [&](int e) -> int { const int s = anti ? n - 1 - e : e; return (s == n - 1) ? read_len - s * P.seglen : P.seglen; };
+
+    thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0; j.n_ops = 0;
+    // ---- single-segment reads: merge_segment_chain 2196-2213
+    const bool single = alive && n == 1;
+    if (single) {
+      WHit w; load_whit(w, bv.hits + t[1], 0, read_len);
+      alive = w.n > 0 && valid_cigar(P, w.ops, w.n);
+      if (alive) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
+                   j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
+                   for (int k = 0; k < w.n; ++k) j.ops[k] = w.ops[k]; }
+    }
+    bool multi = alive && !single;
+    __syncwarp();
+    // ---- first pass (843-897): more than one gap that only a fusion could explain -> give up
+    {
+      int num_fusions = 0; LiteHit pl; pl.ref = 0; pl.left = pl.right = 0; pl.anti = false;
+      if (multi) pl = load_lite(chain_hit(0));
+      for (int e = 1; e < nmax; ++e) {
+        if (multi && e < n) {
+          const LiteHit cl = load_lite(chain_hit(e));
+          if (pl.ref != cl.ref) ++num_fusions;
+          else {
+            const int gap = cl.left - pl.right;
+            const int hi = min(P.max_report_intron, P.fusion_min_dist);
+            if (gap < -P.max_ins || (gap > P.max_del && (gap < P.min_report_intron || gap > hi))) ++num_fusions;
+          }
+          if (num_fusions >= 2) multi = false;
+          pl = cl;
+        }
+      }
+    }
+    __syncwarp();
+    uint64_t cs = 0; int64_t clen = 0;
+    if (multi) {
+      const uint32_t r0 = chain_hit(0)->ref_id;
+      if (!(r0 >= 1 && r0 <= ref.n_contigs)) multi = false;
+      else { cs = __ldg(ref.contig_start + r0 - 1); clen = (int64_t)__ldg(ref.contig_len + r0 - 1); }
+    }
+    // accumulators of the final pass (1888-1945), filled as blocks are finalised
+    uint32_t LC[JMAXOPS]; int nLC = 0; int num_mm = 0, num_smm = 0; bool saw_as = false, saw_s = false;
+    int old_read_length = 0;
+    auto finalize = [&](const WHit& h) -> bool {
+      num_mm += h.mism; num_smm += h.smm;
+      if (cig_spliced(h.ops, h.n)) {
+        if (h.asplice) { if (saw_s) return false; saw_as = true; } else { if (saw_as) return false; saw_s = true; }
+      }
+      int b = 0;
+      if (nLC > 0 && opc(LC[nLC - 1]) == opc(h.ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(h.ops[0])); b = 1; }
+      for (; b < h.n; ++b) if (!cig_push(LC, nLC, h.ops[b])) return false;
+      return true;
+    };
+    WHit prev; prev.n = 0; prev.ref = 0; prev.left = 0; prev.anti = prev.asplice = false; prev.mism = prev.smm = 0; prev.seq_pos = prev.seq_len = 0;
+    int left0 = 0; uint32_t ref0 = 0; bool antisense = false;
+    if (multi) {
+      load_whit(prev, chain_hit(0), 0, chain_len(0));
+      left0 = prev.left; ref0 = prev.ref; antisense = prev.anti;
+      old_read_length += cig_read_len(prev.ops, prev.n);
+    }
+    __syncwarp();
+    // ---- stitch loop (899-1880)
+    for (int e = 1; e < nmax; ++e) {
+      const bool on = multi && e < n;
+      WHit curr; curr.n = 0;
+      int kind = 0;                 // 0 contiguous, 1 insertion closure, 2 junction closure
+      bool found = false, antisense_closure = false; int mismatch = 0, prml = 0, clml = 0, pright = 0;
+      // phase 1: load + classify
+      if (on) {
+        load_whit(curr, chain_hit(e), prev.seq_pos + prev.seq_len, chain_len(e));
+        old_read_length += cig_read_len(curr.ops, curr.n);
+        antisense = prev.anti;
+        const bool ps = cig_spliced(prev.ops, prev.n), csp = cig_spliced(curr.ops, curr.n);
+        if (!(opc(prev.ops[prev.n - 1]) == OP_MATCH || opc(curr.ops[0]) == OP_MATCH)) multi = false;          // 930-934
+        else if (ps && csp && prev.asplice != curr.asplice) multi = false;                                      // 942-949
+        else if (curr.ref != prev.ref) multi = false;
+        else {
+          antisense_closure = ps ? prev.asplice : curr.asplice;
+          prml = (int)opl(prev.ops[prev.n - 1]); clml = (int)opl(curr.ops[0]);
+          pright = cig_right(prev.left, prev.ops, prev.n);
+          const int dist = curr.left - pright;
+          const bool same_strand = prev.anti == curr.anti;
+          if (dist < 0 && dist >= -P.max_ins && same_strand) kind = 1;
+          else if (dist > 0 && dist <= P.max_report_intron && same_strand) kind = 2;
+          else if (!(dist == 0 && same_strand)) multi = false;     // only a fusion could close this gap (1592-1819)
+        }
+      }
+      __syncwarp();
+      // phase 2: junction / deletion closure
+      JuncClosure jc; jc.dtl = 0; jc.glen = 0; jc.anti = false; jc.new_diff = 0;
+      if (on && multi && kind == 2) {
+        n_closures++;
+        const int rc = junction_closure(ref, S, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, jc);
+        if (rc <= 0) multi = false; else { found = true; mismatch = jc.new_diff; }
+      }
+      __syncwarp();
+      // phase 3: insertion closure
+      InsClosure ic; ic.itpr = 0; ic.len = 0; ic.mismatch = 0;
+      if (on && multi && kind == 1) {
+        n_closures++;
+        const int rc = insertion_closure(ref, S, P, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, ic);
+        if (rc <= 0) multi = false; else { found = true; mismatch = ic.mismatch; }
+      }
+      __syncwarp();
+      // phase 4: stitch (1262-1290, 1520-1585, 1822-1880)
+      if (on && multi) {
+        if (found) {
+          uint32_t NC[JMAXOPS]; int nNC = 0; bool okc = true;
+          for (int k = 0; k < prev.n; ++k) NC[nNC++] = prev.ops[k];
+          if (kind == 1) {
+            // lengths are uint32 in the reference, the arithmetic wraps the same way
+            { const uint32_t bl = opl(NC[nNC - 1]) - (uint32_t)ic.itpr; if ((bl & 0x0fffffffu) == 0) --nNC; else NC[nNC - 1] = mkop(opc(NC[nNC - 1]), bl & 0x0fffffffu); }
+            okc = cig_push(NC, nNC, mkop(OP_INS, ic.len));
+            const uint32_t fl = (opl(curr.ops[0]) + (uint32_t)(ic.itpr - (int)ic.len)) & 0x0fffffffu;
+            for (int k = fl > 0 ? 0 : 1; k < curr.n && okc; ++k) okc = cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), fl) : curr.ops[k]);
+          } else {
+            { const int nlb = prml + jc.dtl; if (nlb > 0) NC[nNC - 1] = mkop(opc(NC[nNC - 1]), (uint32_t)nlb); else --nNC; }
+            if (jc.glen <= (uint32_t)P.max_del) okc = cig_push(NC, nNC, mkop(OP_DEL, jc.glen));
+            else { okc = cig_push(NC, nNC, mkop(OP_REF_SKIP, jc.glen)); antisense_closure = jc.anti; }
+            const int nrf = clml - jc.dtl;
+            for (int k = nrf > 0 ? 0 : 1; k < curr.n && okc; ++k) okc = cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), (uint32_t)nrf) : curr.ops[k]);
+          }
+          if (!okc || nNC == 0) multi = false;
+          else {
+            // merged_hit (1822-1838); _mismatches / _edit_dist are unsigned chars in the reference
+            const int mm = (int)prev.mism + (int)curr.mism + mismatch;
+            prev.n = nNC; for (int k = 0; k < nNC; ++k) prev.ops[k] = NC[k];
+            prev.asplice = antisense_closure; prev.anti = antisense; prev.mism = (uint8_t)mm; prev.smm = (uint8_t)(prev.smm + curr.smm);
+            prev.seq_len += curr.seq_len;
+          }
+        } else {
+          if (!finalize(prev)) multi = false;
+          else {
+            prev.ref = curr.ref; prev.left = curr.left; prev.n = curr.n; prev.anti = curr.anti; prev.asplice = curr.asplice;
+            prev.mism = curr.mism; prev.smm = curr.smm; prev.seq_pos = curr.seq_pos; prev.seq_len = curr.seq_len;
+            for (int k = 0; k < curr.n; ++k) prev.ops[k] = curr.ops[k];
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- new_hit (1947-1957) + final checks (2023-2035) + valid_hit
+    if (multi) {
+      if (!finalize(prev) || nLC == 0) multi = false;
+      else if (cig_read_len(LC, nLC) != old_read_length) multi = false;
+    }
+    __syncwarp();
+    if (multi) {
+      const uint8_t mism = (uint8_t)num_mm;
+      if (!editdist_consistent(ref, ref0, left0, LC, nLC, R, 4, mism) || !valid_cigar(P, LC, nLC)) multi = false;
+      else {
+        j.ref_id = ref0; j.left = left0; j.n_ops = (uint8_t)nLC;
+        j.flags = (uint8_t)((antisense ? THB_HIT_ANTISENSE : 0) | (saw_as ? THB_JHIT_ANTISENSE_SPLICE : 0));
+        j.mismatches = mism; j.edit_dist = (uint8_t)(num_mm + cig_gap_length(LC, nLC)); j.splice_mms = (uint8_t)num_smm;
+        for (int k = 0; k < nLC; ++k) j.ops[k] = LC[k];
+      }
+    }
+    __syncwarp();
+    // ---- emit (warp-aggregated slot allocation)
+    const bool out_ok = (single && alive) || multi;
+    const unsigned em = __ballot_sync(0xffffffffu, out_ok);
+    if (em) {
+      unsigned long long slot0 = 0;
+      if (lane == (unsigned)(__ffs((int)em) - 1)) slot0 = atomicAdd(o.count, (unsigned long long)__popc(em));
+      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs((int)em) - 1);
+      if (out_ok) {
+        const unsigned long long slot = slot0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
+        if (slot >= o.cap) atomicOr(o.overflow, 1u);
+        else {
+          uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
+          const uint32_t hdr3 = (uint32_t)j.n_ops | ((uint32_t)j.flags << 8) | ((uint32_t)j.mismatches << 16) | ((uint32_t)j.edit_dist << 24);
+          dst[0] = make_uint4(j.bundle, j.ref_id, (uint32_t)j.left, hdr3);
+          const int nop = j.n_ops;
+          uint32_t w[28]; w[0] = (uint32_t)j.splice_mms;
+          #pragma unroll
+          for (int k = 0; k < 27; ++k) w[1 + k] = k < nop ? j.ops[k] : 0u;
+          #pragma unroll
+          for (int k = 0; k < 7; ++k) if (k == 0 || 4 * k - 1 < nop) dst[1 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        }
+        ++n_emit;
+      }
+    }
     __syncwarp();
   }
   for (int k = 16; k > 0; k >>= 1) { n_closures += __shfl_xor_sync(0xffffffffu, n_closures, k); n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k); }
