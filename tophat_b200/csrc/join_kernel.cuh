@@ -33,6 +33,8 @@ struct JoinParams {
 
 struct JoinSets {
   const thb_junction* juncs; uint32_t n_juncs;        // Junction order (junctions.h:39-57)
+  const uint32_t* jidx; uint64_t n_buckets;           // jidx[b] = first junction whose global left lies in 64-base block >= b
+                                                      // (NULL: fall back to binary search)
   const thb_insertion* ins; uint32_t n_ins;           // (refid, left, length) order (insertions.h:52-67)
 };
 
@@ -96,6 +98,20 @@ __device__ __forceinline__ uint32_t junc_lower_bound(const JoinSets& S, uint32_t
 { uint32_t lo = 0, hi = S.n_juncs; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_less(S.juncs[mid], ref, left, right, anti)) lo = mid + 1; else hi = mid; } return lo; }
 __device__ __forceinline__ uint32_t junc_upper_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t right, uint32_t anti)
 { uint32_t lo = 0, hi = S.n_juncs; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_greater(S.juncs[mid], ref, left, right, anti)) hi = mid; else lo = mid + 1; } return lo; }
+// The same bounds through the 64-base bucket index: one table load + a scan of the (few) junctions in the bucket instead of
+// two 17-step dependent binary searches (SURVEY.md 8d counts the look-up as "bucket offset + bucket").
+__device__ __forceinline__ uint32_t junc_bound_idx(const JoinSets& S, uint64_t cs, int64_t clen, uint32_t ref, uint32_t left, uint32_t right,
+                                                   uint32_t anti, bool upper)
+{
+  if (S.jidx == nullptr || (int64_t)left > clen + 32) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
+  const uint64_t b = (cs + (uint64_t)left) >> 6;
+  if (b >= S.n_buckets) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
+  uint32_t i = __ldg(S.jidx + b);
+  if (upper) { while (i < S.n_juncs && !junc_greater(S.juncs[i], ref, left, right, anti)) ++i; }
+  else       { while (i < S.n_juncs && junc_less(S.juncs[i], ref, left, right, anti)) ++i; }
+  return i;
+}
+
 // std::set<Insertion>::upper_bound(Insertion(ref, left, <string of length len>))
 __device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t len)
 {
@@ -111,13 +127,16 @@ __device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t 
 
 __device__ __forceinline__ void load_whit(WHit& w, const thb_jhit* h, int seq_pos, int seq_len)
 {
+  // most hits carry one op: the first 16 bytes hold everything but ops[1..8]
   const uint4* p = reinterpret_cast<const uint4*>(h);
-  const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  const uint4 a = __ldg(p);
   w.ref = a.x; w.left = (int)a.y;
   w.n = (int)(a.z & 0xffu); const uint32_t fl = (a.z >> 8) & 0xffu; w.mism = (uint8_t)((a.z >> 16) & 0xffu); w.smm = (uint8_t)(a.z >> 24);
   w.anti = (fl & THB_HIT_ANTISENSE) != 0; w.asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
-  w.ops[0] = a.w; w.ops[1] = b.x; w.ops[2] = b.y; w.ops[3] = b.z; w.ops[4] = b.w; w.ops[5] = c.x; w.ops[6] = c.y; w.ops[7] = c.z; w.ops[8] = c.w;
   if (w.n > THB_JHIT_MAX_OPS) w.n = THB_JHIT_MAX_OPS;
+  w.ops[0] = a.w;
+  if (w.n > 1) { const uint4 b = __ldg(p + 1); w.ops[1] = b.x; w.ops[2] = b.y; w.ops[3] = b.z; w.ops[4] = b.w; }
+  if (w.n > 5) { const uint4 c = __ldg(p + 2); w.ops[5] = c.x; w.ops[6] = c.y; w.ops[7] = c.z; w.ops[8] = c.w; }
   w.seq_pos = seq_pos; w.seq_len = seq_len;
 }
 
@@ -126,15 +145,22 @@ struct LiteHit { uint32_t ref; int left, right; bool anti; };
 __device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
 {
   const uint4* p = reinterpret_cast<const uint4*>(h);
-  const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  uint32_t ops[9] = { a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w };
+  const uint4 a = __ldg(p);
   int n = (int)(a.z & 0xffu); if (n > THB_JHIT_MAX_OPS) n = THB_JHIT_MAX_OPS;
   LiteHit l; l.ref = a.x; l.left = (int)a.y; l.anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0;
   int r = l.left;
-  if (n == 1) r += (int)opl(ops[0]);                 // the common case: one match op
-  else {
+  { const int cc = opc(a.w); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(a.w); }
+  if (n > 1) {
+    const uint4 b = __ldg(p + 1);
+    const uint32_t o1[4] = { b.x, b.y, b.z, b.w };
     #pragma unroll
-    for (int i = 0; i < 9; ++i) if (i < n) { const int cc = opc(ops[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(ops[i]); }
+    for (int i = 0; i < 4; ++i) if (1 + i < n) { const int cc = opc(o1[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(o1[i]); }
+    if (n > 5) {
+      const uint4 c = __ldg(p + 2);
+      const uint32_t o2[4] = { c.x, c.y, c.z, c.w };
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) if (5 + i < n) { const int cc = opc(o2[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(o2[i]); }
+    }
   }
   l.right = r;
   return l;
@@ -209,8 +235,8 @@ __device__ __forceinline__ int junction_closure(const RefView& ref, const JoinSe
 {
   // return: 1 found, 0 not found, -1 chain invalid (reference would read outside the contig)
   const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(cleft + 4);
-  uint32_t it = junc_upper_bound(S, ref_id, lbnd, rbnd - 8u, 1u);
-  const uint32_t ub = junc_lower_bound(S, ref_id, lbnd + 8u, rbnd, 0u);
+  uint32_t it = junc_bound_idx(S, cs, clen, ref_id, lbnd, rbnd - 8u, 1u, true);
+  const uint32_t ub = junc_bound_idx(S, cs, clen, ref_id, lbnd + 8u, rbnd, 0u, false);
   int new_diff = 0xff; bool found = false;
   for (; it != ub && it < S.n_juncs; ++it) {
     const thb_junction J = S.juncs[it];
@@ -320,6 +346,18 @@ __device__ __forceinline__ void revcomp_read(const uint64_t* F, int n, uint64_t*
     const int rem = n - 64 * w; const uint64_t valid = rem >= 64 ? ~0ull : (rem > 0 ? ((1ull << rem) - 1ull) : 0ull);
     const uint64_t keep = valid & ~R[8 + w];
     R[w] = ~R[w] & keep; R[4 + w] = ~R[4 + w] & keep;
+  }
+}
+
+// jidx[b] = number of junctions whose global left coordinate lies before 64-base block b (= index of the first one at or after it)
+__global__ void junction_index_kernel(const thb_junction* juncs, uint32_t n, const uint64_t* contig_start, uint32_t* jidx, uint64_t n_buckets)
+{
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t g0 = b << 6;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const thb_junction j = juncs[mid];
+      if (contig_start[j.ref_id - 1] + (uint64_t)j.left < g0) lo = mid + 1; else hi = mid; }
+    jidx[b] = lo;
   }
 }
 

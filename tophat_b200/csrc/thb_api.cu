@@ -88,8 +88,10 @@ struct thb_ctx {
   // accounting
   thb_timing timing{}; uint64_t n_bundles_total = 0, n_hits_total = 0, n_partner_total = 0;
   uint64_t n_ins_out = 0, n_del_out = 0;
+  unsigned long long h_ins_count = 0;   // host mirror of *d_ins_count after the last completed launch
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // long_spanning_reads join
+  DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false;
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
   JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   // nccl
@@ -245,6 +247,7 @@ int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* r
     CU(cudaStreamSynchronize(ctx->compute));
     ctx->d_ins.release(); ctx->d_ins = nb; ctx->cap_ins = ncap; *redo = true;
   }
+  if (!*redo) ctx->h_ins_count = ins_now;
   if (*redo) {
     CU(cudaMemcpyAsync(ctx->d_ins_count, &ins_before, sizeof ins_before, cudaMemcpyHostToDevice, ctx->compute));
     CU(cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(unsigned int), ctx->compute));   // err + queue overflow flags
@@ -328,7 +331,7 @@ void thb_destroy(thb_ctx* ctx)
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
-                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain }) b->release();
+                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
@@ -432,6 +435,7 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   ctx->h_juncs.clear(); ctx->h_dels.clear(); ctx->h_ins.clear(); ctx->h_fus.clear();
   memset(&ctx->timing, 0, sizeof ctx->timing);
   ctx->own_launches = 2;            // the two hs_clear launches above
+  ctx->h_ins_count = 0;
   ctx->n_bundles_total = ctx->n_hits_total = ctx->n_partner_total = 0; ctx->n_ins_out = ctx->n_del_out = 0;
   ctx->begun = true;
   return THB_OK;
@@ -446,9 +450,7 @@ int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* b)
   bv.partner = b->partner_hits; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
   bv.order_base = b->order_base;
   bv.partner_base = 0; bv.hit_base = 0;
-  unsigned long long ins_before = 0;
-  CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
+  unsigned long long ins_before = ctx->h_ins_count;
   float ms_total = 0.f; bool done = false;
   for (int attempt = 0; attempt < 24 && !done; ++attempt) {
     unsigned long long cnt0[4];
@@ -476,9 +478,6 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
   if (b->n_bundles == 0) return THB_OK;
   const uint32_t CH = 1u << 20;                         // bundles per pipeline chunk
   const size_t rdw = (size_t)3 * b->read_words;
-  unsigned long long ins_before_all = 0;
-  CU(cudaMemcpyAsync(&ins_before_all, ctx->d_ins_count, sizeof ins_before_all, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
   float kernel_ms = 0.f;
   const uint32_t nchunks = (b->n_bundles + CH - 1) / CH;
@@ -513,8 +512,7 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
     bv.reads = (const uint64_t*)s.reads.p; bv.hits = (const thb_hit*)s.hits.p - r.h0; bv.partner = (const thb_hit*)s.partner.p - r.p0;
     bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.order_base = b->order_base + r.b0;
     bv.partner_base = r.p0; bv.hit_base = r.h0;
-    unsigned long long ins_before = 0;
-    CU(cudaMemcpyAsync(&ins_before, ctx->d_ins_count, sizeof ins_before, cudaMemcpyDeviceToHost, ctx->compute));
+    unsigned long long ins_before = ctx->h_ins_count;
     bool done = false;
     for (int attempt = 0; attempt < 24; ++attempt) {
       unsigned long long cnt0[4];
@@ -537,7 +535,6 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
   float tot = 0.f; CU(cudaEventElapsedTime(&tot, ctx->ev_c, ctx->ev_d));
   ctx->timing.scan_kernel_ms += kernel_ms; ctx->timing.total_ms += tot; ctx->timing.h2d_ms += std::max(0.f, tot - kernel_ms);
   ctx->n_bundles_total += b->n_bundles; ctx->n_hits_total += b->n_hits; ctx->n_partner_total += b->n_partner_hits;
-  (void)ins_before_all;
   return THB_OK;
 }
 
@@ -641,6 +638,27 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   CU(ctx->j_juncs.reserve((n_juncs + 1) * sizeof(thb_junction))); CU(ctx->j_ins.reserve((n_ins + 1) * sizeof(thb_insertion)));
   if (n_juncs) CU(cudaMemcpyAsync(ctx->j_juncs.p, juncs, n_juncs * sizeof(thb_junction), cudaMemcpyHostToDevice, ctx->compute));
   if (n_ins) CU(cudaMemcpyAsync(ctx->j_ins.p, ins, n_ins * sizeof(thb_insertion), cudaMemcpyHostToDevice, ctx->compute));
+  // 64-base bucket index over the junction array (valid when global lefts are monotone, i.e. every junction lies
+  // inside its contig's slot of the image; otherwise the kernels binary-search)
+  {
+    const uint64_t nb = ctx->d_nmask.cap / 8;       // blocks allocated for the image (>= n_blocks)
+    bool mono = n_juncs > 0; uint64_t prev_g = 0;
+    for (uint64_t i = 0; i < n_juncs && mono; ++i) {
+      const thb_junction& j = juncs[i];
+      if (j.ref_id < 1 || j.ref_id > ctx->h_cstart.size() || (uint64_t)j.left > (uint64_t)ctx->h_clen[j.ref_id - 1] + 63) { mono = false; break; }
+      const uint64_t g = ctx->h_cstart[j.ref_id - 1] + j.left;
+      if (g < prev_g || (g >> 6) >= nb) mono = false;
+      prev_g = g;
+    }
+    ctx->j_use_idx = mono;
+    if (mono) {
+      CU(ctx->j_idx.reserve((nb + 1) * 4));
+      junction_index_kernel<<<grid_for(nb + 1, 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, (uint32_t)n_juncs, ctx->ref.contig_start,
+                                                                           (uint32_t*)ctx->j_idx.p, nb);
+      CU(cudaGetLastError());
+      ctx->j_nbuckets = nb;
+    }
+  }
   CU(cudaStreamSynchronize(ctx->compute));
   ctx->j_n_juncs = n_juncs; ctx->j_n_ins = n_ins;
   JoinParams& j = ctx->jp;
@@ -667,6 +685,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
   ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
+  S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets;
   unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f;
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
@@ -870,6 +889,7 @@ int thb_segjuncs_allgather(thb_ctx* ctx)
     CU(cudaMemsetAsync(ctx->d_ins_count, 0, 8, ctx->compute));
     ins_append_kernel<<<grid_for(mx[2] * W, 256), 256, 0, ctx->compute>>>((const InsRec*)ri, mx[2] * W, (InsRec*)ctx->d_ins.p, ctx->d_ins_count, ctx->cap_ins, ctx->d_err);
     ctx->own_launches++;
+    ctx->h_ins_count = tot[2];
   }
   CU(cudaGetLastError());
   return THB_OK;
