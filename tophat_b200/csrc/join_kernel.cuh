@@ -52,6 +52,7 @@ struct JoinOut {
 struct WHit {
   uint32_t ref; int left; int n; uint32_t ops[JMAXOPS];
   bool anti, asplice; uint8_t mism, smm; int seq_pos, seq_len;
+  int right, rlen; bool spliced;      // cached: right(), read_len(), is_spliced() of the ops
 };
 
 __device__ __forceinline__ int cig_right(int left, const uint32_t* ops, int n)
@@ -138,16 +139,21 @@ __device__ __forceinline__ void load_whit(WHit& w, const thb_jhit* h, int seq_po
   if (w.n > 1) { const uint4 b = __ldg(p + 1); w.ops[1] = b.x; w.ops[2] = b.y; w.ops[3] = b.z; w.ops[4] = b.w; }
   if (w.n > 5) { const uint4 c = __ldg(p + 2); w.ops[5] = c.x; w.ops[6] = c.y; w.ops[7] = c.z; w.ops[8] = c.w; }
   w.seq_pos = seq_pos; w.seq_len = seq_len;
+  if (w.n == 1) { const int c = opc(a.w); const int l = (int)opl(a.w);
+    w.right = w.left + ((c == OP_MATCH || c == OP_REF_SKIP || c == OP_DEL) ? l : 0);
+    w.rlen = (c == OP_MATCH || c == OP_INS || c == OP_SOFT_CLIP) ? l : 0; w.spliced = c == OP_REF_SKIP; }
+  else { w.right = cig_right(w.left, w.ops, w.n); w.rlen = cig_read_len(w.ops, w.n); w.spliced = cig_spliced(w.ops, w.n); }
 }
 
 // the few fields of a segment hit the DFS needs
-struct LiteHit { uint32_t ref; int left, right; bool anti; };
+struct LiteHit { uint32_t ref; int left, right; bool anti; bool one_m; };   // one_m: the CIGAR is a single match op
 __device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
 {
   const uint4* p = reinterpret_cast<const uint4*>(h);
   const uint4 a = __ldg(p);
   int n = (int)(a.z & 0xffu); if (n > THB_JHIT_MAX_OPS) n = THB_JHIT_MAX_OPS;
   LiteHit l; l.ref = a.x; l.left = (int)a.y; l.anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0;
+  l.one_m = n == 1 && opc(a.w) == OP_MATCH;
   int r = l.left;
   { const int cc = opc(a.w); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(a.w); }
   if (n > 1) {
@@ -168,10 +174,10 @@ __device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
 
 // dfs_seg_hits' pair test with --fusion-search off (2250-2558): same contig, same strand, and the genomic gap between
 // the (strand-ordered) pair within [-max_insertion_length, max_report_intron_length].
-__device__ __forceinline__ bool chain_compatible(const JoinParams& P, const LiteHit& prev, const LiteHit& curr)
+__device__ __forceinline__ bool chain_compatible(const JoinParams& P, const LiteHit& prev, const LiteHit& curr, int& dist)
 {
+  dist = 0x7fffffff;
   if (prev.ref != curr.ref || prev.anti != curr.anti) return false;     // would need a fusion (dir != FUSION_NOTHING, 2402)
-  int dist;
   if (prev.anti) dist = prev.left - curr.right;                         // pair swapped for antisense hits (2355-2361)
   else {
     dist = curr.left - prev.right;                                      // 2366-2379
@@ -364,6 +370,8 @@ __global__ void junction_index_kernel(const thb_junction* juncs, uint32_t n, con
 struct ChainQueue {
   uint32_t* tasks; unsigned long long cap; uint32_t stride;     // task = [bundle, hit index of segment 0 .. n-1] (absolute indices)
   unsigned long long* count; unsigned int* overflow;
+  // chains of single-match hits that abut exactly (no closure needed): merged by chain_merge_simple_kernel
+  uint32_t* simple_tasks; unsigned long long* simple_count;
 };
 
 // K-J1: join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610): enumerate the compatible segment-hit chains of one
@@ -377,15 +385,18 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
   { uint32_t a = hdr.y;
     for (int s = 0; s < n; ++s) { cnt[s] = (int)__ldg(bv.seg_count + (size_t)bi * bv.n_segs + s); off[s] = a; a += (uint32_t)cnt[s]; } }
   if (P.bowtie2) for (int s = 0; s < n; ++s) if (cnt[s] > P.max_seg_multihits) return;      // 2624-2632
-  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS];
+  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS]; bool simp[JMAXSEGS];
   auto leaf = [&]() {
     ++n_leaves;
+    const bool simple = n > 1 && simp[n - 1];
+    unsigned long long* ctr = simple ? q.simple_count : q.count;
     unsigned long long slot;
-    { const unsigned m = __activemask(); const unsigned ln = threadIdx.x & 31u; const int leader = __ffs((int)m) - 1;
-      unsigned long long b0 = 0; if ((int)ln == leader) b0 = atomicAdd(q.count, (unsigned long long)__popc(m));
-      b0 = __shfl_sync(m, b0, leader); slot = b0 + (unsigned long long)__popc(m & ((1u << ln) - 1u)); }
+    { const unsigned m = __activemask(); const unsigned ms = __ballot_sync(m, simple); const unsigned grp = simple ? ms : (m & ~ms);
+      const unsigned ln = threadIdx.x & 31u; const int leader = __ffs((int)grp) - 1;
+      unsigned long long b0 = 0; if ((int)ln == leader) b0 = atomicAdd(ctr, (unsigned long long)__popc(grp));
+      b0 = __shfl_sync(grp, b0, leader); slot = b0 + (unsigned long long)__popc(grp & ((1u << ln) - 1u)); }
     if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
-    uint32_t* t = q.tasks + slot * q.stride;
+    uint32_t* t = (simple ? q.simple_tasks : q.tasks) + slot * q.stride;
     t[0] = bi;
     for (int s = 0; s < n; ++s) t[1 + s] = off[s] + (uint32_t)sel[s];
   };
@@ -394,12 +405,13 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
     int num_try = 10000;                                           // 2647
     if (n == 1) { --num_try; leaf(); continue; }
     int lvl = 1; it[1] = 0;
-    top[0] = load_lite(bv.hits + off[0] + i0);
+    top[0] = load_lite(bv.hits + off[0] + i0); simp[0] = top[0].one_m;
     while (lvl >= 1) {
       if (it[lvl] >= cnt[lvl]) { --lvl; if (lvl >= 1) ++it[lvl]; continue; }
       const LiteHit cand = load_lite(bv.hits + off[lvl] + it[lvl]);
-      if (!chain_compatible(P, top[lvl - 1], cand)) { ++it[lvl]; continue; }
-      sel[lvl] = it[lvl]; top[lvl] = cand;
+      int dist;
+      if (!chain_compatible(P, top[lvl - 1], cand, dist)) { ++it[lvl]; continue; }
+      sel[lvl] = it[lvl]; top[lvl] = cand; simp[lvl] = simp[lvl - 1] && cand.one_m && dist == 0;
       if (lvl == n - 1) { --num_try; leaf(); if (num_try <= 0) break; ++it[lvl]; }
       else { ++lvl; it[lvl] = 0; }
     }
@@ -417,6 +429,69 @@ chain_enum_kernel(JoinParams P, JoinBatchView bv, ChainQueue q, unsigned long lo
   }
   for (int k = 16; k > 0; k >>= 1) n_leaves += __shfl_xor_sync(0xffffffffu, n_leaves, k);
   if (lane == 0 && n_leaves) atomicAdd(counters + 0, (unsigned long long)n_leaves);
+}
+
+// K-J2a: chains of single-match hits that abut exactly.  merge_chain reduces to: no closure anywhere (dist == 0, 1592),
+// CIGAR = one match op over the whole read (1926-1936), mismatches = sum of the segments' (1900), then the consistency
+// re-read (2023-2035); valid_hit holds trivially.  One uniform straight-line path, so these chains get their own queue.
+__global__ void __launch_bounds__(256)
+chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, JoinOut o)
+{
+  unsigned n_emit = 0;
+  unsigned long long nq = *q.simple_count; if (nq > q.cap) nq = q.cap;
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long ti = base + lane;
+    bool ok = ti < nq;
+    uint32_t bi = 0, ref0 = 0, total = 0; int left0 = 0; unsigned mism = 0, smm = 0; bool anti = false;
+    if (ok) {
+      const uint32_t* __restrict__ t = q.simple_tasks + ti * q.stride;
+      bi = t[0];
+      const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
+      const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
+      uint64_t R[12];
+      { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
+        #pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+          #pragma unroll
+          for (int w = 0; w < 4; ++w) R[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull; }
+      int minleft = 0x7fffffff;
+      for (int s = 0; s < n; ++s) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bv.hits + t[1 + s]));
+        if (s == 0) { ref0 = a.x; anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0; }
+        minleft = min(minleft, (int)a.y);                     // chain[0] is the leftmost hit in either orientation
+        mism += (a.z >> 16) & 0xffu; smm += a.z >> 24; total += opl(a.w);
+      }
+      left0 = minleft;
+      if (anti) { uint64_t F[12];
+        #pragma unroll
+        for (int k = 0; k < 12; ++k) F[k] = R[k];
+        revcomp_read(F, read_len, R); }
+      // new_read_len == old_read_length (2023) holds by construction
+      const uint32_t op = mkop(OP_MATCH, total);
+      ok = editdist_consistent(ref, ref0, left0, &op, 1, R, 4, (uint8_t)mism);
+    }
+    const unsigned em = __ballot_sync(0xffffffffu, ok);
+    if (em) {
+      unsigned long long slot0 = 0;
+      if (lane == (unsigned)(__ffs((int)em) - 1)) slot0 = atomicAdd(o.count, (unsigned long long)__popc(em));
+      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs((int)em) - 1);
+      if (ok) {
+        const unsigned long long slot = slot0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
+        if (slot >= o.cap) atomicOr(o.overflow, 1u);
+        else {
+          uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
+          const uint32_t m8 = mism & 0xffu;
+          dst[0] = make_uint4(bi, ref0, (uint32_t)left0, 1u | ((anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) << 8) | (m8 << 16) | (m8 << 24));
+          dst[1] = make_uint4(smm & 0xffu, mkop(OP_MATCH, total), 0u, 0u);
+        }
+        ++n_emit;
+      }
+    }
+    __syncwarp();
+  }
+  for (int k = 16; k > 0; k >>= 1) n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k);
+  if (lane == 0 && n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit);
 }
 
 // K-J2: merge_segment_chain (2101-2220) + merge_chain (805-2038) + valid_hit (2045-2099), one chain per thread.
@@ -473,25 +548,9 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     }
     bool multi = alive && !single;
     __syncwarp();
-    // ---- first pass (843-897): more than one gap that only a fusion could explain -> give up
-    {
-      int num_fusions = 0; LiteHit pl; pl.ref = 0; pl.left = pl.right = 0; pl.anti = false;
-      if (multi) pl = load_lite(chain_hit(0));
-      for (int e = 1; e < nmax; ++e) {
-        if (multi && e < n) {
-          const LiteHit cl = load_lite(chain_hit(e));
-          if (pl.ref != cl.ref) ++num_fusions;
-          else {
-            const int gap = cl.left - pl.right;
-            const int hi = min(P.max_report_intron, P.fusion_min_dist);
-            if (gap < -P.max_ins || (gap > P.max_del && (gap < P.min_report_intron || gap > hi))) ++num_fusions;
-          }
-          if (num_fusions >= 2) multi = false;
-          pl = cl;
-        }
-      }
-    }
-    __syncwarp();
+    // the first pass of merge_chain (843-897: two gaps that only a fusion could explain -> give up) is folded into the stitch
+    // loop below: its `gap` is the `dist` of phase 1 (a merged block keeps the right end of its last hit)
+    int num_fusions = 0;
     uint64_t cs = 0; int64_t clen = 0;
     if (multi) {
       const uint32_t r0 = chain_hit(0)->ref_id;
@@ -503,7 +562,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     int old_read_length = 0;
     auto finalize = [&](const WHit& h) -> bool {
       num_mm += h.mism; num_smm += h.smm;
-      if (cig_spliced(h.ops, h.n)) {
+      if (h.spliced) {
         if (h.asplice) { if (saw_s) return false; saw_as = true; } else { if (saw_as) return false; saw_s = true; }
       }
       int b = 0;
@@ -512,11 +571,12 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       return true;
     };
     WHit prev; prev.n = 0; prev.ref = 0; prev.left = 0; prev.anti = prev.asplice = false; prev.mism = prev.smm = 0; prev.seq_pos = prev.seq_len = 0;
+    prev.right = 0; prev.rlen = 0; prev.spliced = false;
     int left0 = 0; uint32_t ref0 = 0; bool antisense = false;
     if (multi) {
       load_whit(prev, chain_hit(0), 0, chain_len(0));
       left0 = prev.left; ref0 = prev.ref; antisense = prev.anti;
-      old_read_length += cig_read_len(prev.ops, prev.n);
+      old_read_length += prev.rlen;
     }
     __syncwarp();
     // ---- stitch loop (899-1880)
@@ -528,18 +588,21 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       // phase 1: load + classify
       if (on) {
         load_whit(curr, chain_hit(e), prev.seq_pos + prev.seq_len, chain_len(e));
-        old_read_length += cig_read_len(curr.ops, curr.n);
+        old_read_length += curr.rlen;
         antisense = prev.anti;
-        const bool ps = cig_spliced(prev.ops, prev.n), csp = cig_spliced(curr.ops, curr.n);
+        const bool ps = prev.spliced, csp = curr.spliced;
         if (!(opc(prev.ops[prev.n - 1]) == OP_MATCH || opc(curr.ops[0]) == OP_MATCH)) multi = false;          // 930-934
         else if (ps && csp && prev.asplice != curr.asplice) multi = false;                                      // 942-949
         else if (curr.ref != prev.ref) multi = false;
         else {
           antisense_closure = ps ? prev.asplice : curr.asplice;
           prml = (int)opl(prev.ops[prev.n - 1]); clml = (int)opl(curr.ops[0]);
-          pright = cig_right(prev.left, prev.ops, prev.n);
+          pright = prev.right;
           const int dist = curr.left - pright;
           const bool same_strand = prev.anti == curr.anti;
+          { const int hi = min(P.max_report_intron, P.fusion_min_dist);
+            if (dist < -P.max_ins || (dist > P.max_del && (dist < P.min_report_intron || dist > hi))) ++num_fusions;
+            if (num_fusions >= 2) multi = false; }
           if (dist < 0 && dist >= -P.max_ins && same_strand) kind = 1;
           else if (dist > 0 && dist <= P.max_report_intron && same_strand) kind = 2;
           else if (!(dist == 0 && same_strand)) multi = false;     // only a fusion could close this gap (1592-1819)
@@ -587,12 +650,15 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
             prev.n = nNC; for (int k = 0; k < nNC; ++k) prev.ops[k] = NC[k];
             prev.asplice = antisense_closure; prev.anti = antisense; prev.mism = (uint8_t)mm; prev.smm = (uint8_t)(prev.smm + curr.smm);
             prev.seq_len += curr.seq_len;
+            prev.right = curr.right; prev.rlen += curr.rlen;
+            prev.spliced = prev.spliced || curr.spliced || (kind == 2 && jc.glen > (uint32_t)P.max_del);
           }
         } else {
           if (!finalize(prev)) multi = false;
           else {
             prev.ref = curr.ref; prev.left = curr.left; prev.n = curr.n; prev.anti = curr.anti; prev.asplice = curr.asplice;
             prev.mism = curr.mism; prev.smm = curr.smm; prev.seq_pos = curr.seq_pos; prev.seq_len = curr.seq_len;
+            prev.right = curr.right; prev.rlen = curr.rlen; prev.spliced = curr.spliced;
             for (int k = 0; k < curr.n; ++k) prev.ops[k] = curr.ops[k];
           }
         }
@@ -612,7 +678,6 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
         j.ref_id = ref0; j.left = left0; j.n_ops = (uint8_t)nLC;
         j.flags = (uint8_t)((antisense ? THB_HIT_ANTISENSE : 0) | (saw_as ? THB_JHIT_ANTISENSE_SPLICE : 0));
         j.mismatches = mism; j.edit_dist = (uint8_t)(num_mm + cig_gap_length(LC, nLC)); j.splice_mms = (uint8_t)num_smm;
-        for (int k = 0; k < nLC; ++k) j.ops[k] = LC[k];
       }
     }
     __syncwarp();
@@ -631,11 +696,10 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
           const uint32_t hdr3 = (uint32_t)j.n_ops | ((uint32_t)j.flags << 8) | ((uint32_t)j.mismatches << 16) | ((uint32_t)j.edit_dist << 24);
           dst[0] = make_uint4(j.bundle, j.ref_id, (uint32_t)j.left, hdr3);
           const int nop = j.n_ops;
-          uint32_t w[28]; w[0] = (uint32_t)j.splice_mms;
-          #pragma unroll
-          for (int k = 0; k < 27; ++k) w[1 + k] = k < nop ? j.ops[k] : 0u;
-          #pragma unroll
-          for (int k = 0; k < 7; ++k) if (k == 0 || 4 * k - 1 < nop) dst[1 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+          uint32_t* dw = reinterpret_cast<uint32_t*>(dst + 1);
+          dw[0] = (uint32_t)j.splice_mms;
+          if (single) { for (int k = 0; k < nop; ++k) dw[1 + k] = j.ops[k]; }
+          else        { for (int k = 0; k < nop; ++k) dw[1 + k] = LC[k]; }
         }
         ++n_emit;
       }
