@@ -371,7 +371,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         kbytes["chain_merge"] = A["join_alg"] / steps - kbytes["chain_enum"]
         kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps; kms["chain_merge"] = A["merge_ms"] / steps
         klaunch = {k: A["scan_launches"] for k in KERNELS}
-        klaunch["chain_enum"] = klaunch["chain_merge"] = max(1, A["join_launches"] // (3 * steps))
+        klaunch["chain_enum"] = klaunch["chain_merge"] = max(1, A["join_launches"] // (4 * steps))
         allk = KERNELS + ("chain_enum", "chain_merge")
         dom = max(allk, key=lambda k: kms[k])
         dom_ms = kms[dom] / klaunch[dom]; dom_bytes = kbytes[dom] / klaunch[dom]

@@ -372,6 +372,8 @@ struct ChainQueue {
   unsigned long long* count; unsigned int* overflow;
   // chains of single-match hits that abut exactly (no closure needed): merged by chain_merge_simple_kernel
   uint32_t* simple_tasks; unsigned long long* simple_count;
+  // chains whose hits all abut exactly but carry multi-op CIGARs (spliced hits): no closure search needed
+  uint32_t* abut_tasks; unsigned long long* abut_count;
 };
 
 // K-J1: join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610): enumerate the compatible segment-hit chains of one
@@ -385,18 +387,20 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
   { uint32_t a = hdr.y;
     for (int s = 0; s < n; ++s) { cnt[s] = (int)__ldg(bv.seg_count + (size_t)bi * bv.n_segs + s); off[s] = a; a += (uint32_t)cnt[s]; } }
   if (P.bowtie2) for (int s = 0; s < n; ++s) if (cnt[s] > P.max_seg_multihits) return;      // 2624-2632
-  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS]; bool simp[JMAXSEGS];
+  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS]; bool simp[JMAXSEGS], abut[JMAXSEGS];
   auto leaf = [&]() {
     ++n_leaves;
     const bool simple = n > 1 && simp[n - 1];
-    unsigned long long* ctr = simple ? q.simple_count : q.count;
+    const bool abutting = !simple && n > 1 && abut[n - 1];
+    unsigned long long* ctr = simple ? q.simple_count : (abutting ? q.abut_count : q.count);
     unsigned long long slot;
-    { const unsigned m = __activemask(); const unsigned ms = __ballot_sync(m, simple); const unsigned grp = simple ? ms : (m & ~ms);
+    { const unsigned m = __activemask(); const unsigned ms = __ballot_sync(m, simple); const unsigned ma = __ballot_sync(m, abutting);
+      const unsigned grp = simple ? ms : (abutting ? ma : (m & ~ms & ~ma));
       const unsigned ln = threadIdx.x & 31u; const int leader = __ffs((int)grp) - 1;
       unsigned long long b0 = 0; if ((int)ln == leader) b0 = atomicAdd(ctr, (unsigned long long)__popc(grp));
       b0 = __shfl_sync(grp, b0, leader); slot = b0 + (unsigned long long)__popc(grp & ((1u << ln) - 1u)); }
     if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
-    uint32_t* t = (simple ? q.simple_tasks : q.tasks) + slot * q.stride;
+    uint32_t* t = (simple ? q.simple_tasks : (abutting ? q.abut_tasks : q.tasks)) + slot * q.stride;
     t[0] = bi;
     for (int s = 0; s < n; ++s) t[1 + s] = off[s] + (uint32_t)sel[s];
   };
@@ -405,13 +409,13 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
     int num_try = 10000;                                           // 2647
     if (n == 1) { --num_try; leaf(); continue; }
     int lvl = 1; it[1] = 0;
-    top[0] = load_lite(bv.hits + off[0] + i0); simp[0] = top[0].one_m;
+    top[0] = load_lite(bv.hits + off[0] + i0); simp[0] = top[0].one_m; abut[0] = true;
     while (lvl >= 1) {
       if (it[lvl] >= cnt[lvl]) { --lvl; if (lvl >= 1) ++it[lvl]; continue; }
       const LiteHit cand = load_lite(bv.hits + off[lvl] + it[lvl]);
       int dist;
       if (!chain_compatible(P, top[lvl - 1], cand, dist)) { ++it[lvl]; continue; }
-      sel[lvl] = it[lvl]; top[lvl] = cand; simp[lvl] = simp[lvl - 1] && cand.one_m && dist == 0;
+      sel[lvl] = it[lvl]; top[lvl] = cand; simp[lvl] = simp[lvl - 1] && cand.one_m && dist == 0; abut[lvl] = abut[lvl - 1] && dist == 0;
       if (lvl == n - 1) { --num_try; leaf(); if (num_try <= 0) break; ++it[lvl]; }
       else { ++lvl; it[lvl] = 0; }
     }
@@ -498,17 +502,19 @@ chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueu
 // Every lane walks the same phase sequence with an `alive` predicate and the warp re-converges at each __syncwarp():
 // the closure searches (equal-length binary searches) and the consistency re-read then run with all the lanes that
 // need them side by side (profiles/r1h: 4 of 32 lanes active in the straightforward per-thread form).
+template <bool CLOSURES>
 __global__ void __launch_bounds__(128)
 chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, ChainQueue q, JoinOut o)
 {
   unsigned n_closures = 0, n_emit = 0;
-  unsigned long long nq = *q.count; if (nq > q.cap) nq = q.cap;
+  unsigned long long nq = CLOSURES ? *q.count : *q.abut_count; if (nq > q.cap) nq = q.cap;
+  const uint32_t* __restrict__ qtasks = CLOSURES ? q.tasks : q.abut_tasks;
   const unsigned lane = threadIdx.x & 31u;
   for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long ti = base + lane;
     // ---- phase 0: task, read, orientation
     bool alive = ti < nq;
-    const uint32_t* __restrict__ t = q.tasks + (alive ? ti : 0) * q.stride;
+    const uint32_t* __restrict__ t = qtasks + (alive ? ti : 0) * q.stride;
     uint32_t bi = 0; int read_len = 0, n = 0; bool anti = false;
     uint64_t R[12];
     #pragma unroll
@@ -608,10 +614,11 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
           else if (!(dist == 0 && same_strand)) multi = false;     // only a fusion could close this gap (1592-1819)
         }
       }
+      if (!CLOSURES && kind != 0) multi = false;   // cannot happen: the abutting queue only holds dist == 0 chains
       __syncwarp();
       // phase 2: junction / deletion closure
       JuncClosure jc; jc.dtl = 0; jc.glen = 0; jc.anti = false; jc.new_diff = 0;
-      if (on && multi && kind == 2) {
+      if (CLOSURES && on && multi && kind == 2) {
         n_closures++;
         const int rc = junction_closure(ref, S, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, jc);
         if (rc <= 0) multi = false; else { found = true; mismatch = jc.new_diff; }
@@ -619,7 +626,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       __syncwarp();
       // phase 3: insertion closure
       InsClosure ic; ic.itpr = 0; ic.len = 0; ic.mismatch = 0;
-      if (on && multi && kind == 1) {
+      if (CLOSURES && on && multi && kind == 1) {
         n_closures++;
         const int rc = insertion_closure(ref, S, P, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, ic);
         if (rc <= 0) multi = false; else { found = true; mismatch = ic.mismatch; }

@@ -690,33 +690,35 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
     CU(ctx->j_out.reserve(ctx->j_cap_out * sizeof(thb_joined)));
-    CU(ctx->j_chain.reserve(2 * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // general + simple queues
+    CU(ctx->j_chain.reserve(3 * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // general + simple + abutting queues
     CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
     JoinOut o; o.rec = (thb_joined*)ctx->j_out.p; o.cap = ctx->j_cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
     ChainQueue q; q.tasks = (uint32_t*)ctx->j_chain.p; q.cap = ctx->j_cap_chain; q.stride = stride; q.count = ctx->d_qcounts + 1; q.overflow = ctx->d_qovf;
     q.simple_tasks = q.tasks + ctx->j_cap_chain * stride; q.simple_count = ctx->d_qcounts + 2;
+    q.abut_tasks = q.tasks + 2 * ctx->j_cap_chain * stride; q.abut_count = ctx->d_qcounts + 3;
     CU(cudaEventRecord(ctx->kev[0], ctx->compute));
     chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
     CU(cudaEventRecord(ctx->kev[1], ctx->compute));
     chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    chain_merge_kernel<<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    chain_merge_kernel<false><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    chain_merge_kernel<true><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
-    ctx->jtiming.launches += 3;
-    unsigned int ovf = 0; unsigned long long qn[3] = {0, 0, 0};
-    CU(cudaMemcpyAsync(qn, ctx->d_qcounts, 24, cudaMemcpyDeviceToHost, ctx->compute));
+    ctx->jtiming.launches += 4;
+    unsigned int ovf = 0; unsigned long long qn[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(qn, ctx->d_qcounts, 32, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     n = qn[0];
-    if (!ovf && n <= ctx->j_cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain) {
+    if (!ovf && n <= ctx->j_cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
       kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2; break;
     }
     ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, 2 * n + 1024);
-    ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, 2 * std::max(qn[1], qn[2]) + 1024);
+    ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, 2 * std::max(qn[1], std::max(qn[2], qn[3])) + 1024);
     if (attempt == 23) return fail(ctx, THB_ENOMEM, "joined-hit buffer still overflows");
   }
   thb_join_timing& t = ctx->jtiming;
