@@ -53,7 +53,7 @@ def build_host_binaries(force: bool = False) -> list:
         return outs
     os.makedirs(BIN_DIR, exist_ok=True)
     common = sorted(os.path.join(host, f) for f in os.listdir(host) if f.endswith(".cpp") and not f.endswith("_main.cpp"))
-    for prog in ("segment_juncs", "long_spanning_reads"):
+    for prog in ("segment_juncs", "long_spanning_reads", "thb_host_selftest"):
         main = os.path.join(host, prog + "_main.cpp")
         if not os.path.exists(main):
             continue
