@@ -42,6 +42,8 @@ if os.path.exists(rp):
     traffic = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = name[5:] if name.startswith("void ") else name
+        name = name.split("<")[0].replace("thb::", "")
         out += ["### `%s`" % name, "", "| metric | value | unit |", "|---|---|---|"]
         vals = {}
         for w in want:

@@ -165,3 +165,23 @@ def test_medium_workload_full_pipeline_properties():
     assert (np.diff(key) >= 0).all()
     span = j["right"].astype(np.int64) - j["left"].astype(np.int64)
     assert span.min() >= 50 - 16 and span.max() <= 500000 + 25 + 16
+
+
+def test_global_coordinates_beyond_32_bits():
+    """hg38-scale addressing: a contig placed past global base 5e9 (39-bit global coordinates in keys, window tasks and
+    reference fetches).  The image is sparse: two small contigs, the second one far out."""
+    wl = synth.generate(synth.SynthConfig(contig_lens=(300_000, 200_000), n_pairs=4000, seed=221, indel_prob=0.3))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    batches = helpers.pack_both(wl)
+    want, _ = pyoracle.segjuncs(P, wl.ref, batches)
+    ref = wl.ref
+    far = 5_000_000_000 // 64 * 64
+    nb2 = (far + ((int(ref.contig_len[1]) + 63) // 64 + 1) * 64) // 64 + 1
+    planes = np.zeros(2 * nb2, dtype="<u8"); nmask = np.zeros(nb2, dtype="<u8")
+    b0 = int(ref.contig_start[1]) // 64; n1 = ref.n_blocks - b0
+    planes[:2 * b0] = ref.planes[:2 * b0]; nmask[:b0] = ref.nmask[:b0]
+    planes[2 * (far // 64): 2 * (far // 64) + 2 * n1] = ref.planes[2 * b0:]; nmask[far // 64: far // 64 + n1] = ref.nmask[b0:]
+    moved = synth.RefImage(ref.names, ref.contig_len, np.array([0, far], dtype="<u8"), planes, nmask, None)
+    got, _ = helpers.gpu_segjuncs(P, moved, batches)
+    helpers.assert_same_results(got, want, "far contig")
+    assert (got.junctions["ref_id"] == 2).sum() > 20
