@@ -16,3 +16,15 @@ def pytest_configure(config):
 def built_library():
     from tophat_b200 import build
     return build.build_library()
+
+
+@pytest.fixture()
+def emu_lib(monkeypatch):
+    """Development harness (tests/emu): the library's kernels compiled for the host against an emulation shim, so that
+    their logic can be checked against the oracle without a GPU.  Test-only: capi's own loader never picks it up."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from tophat_b200 import capi
+    lib = capi.load_library(build_emu.build())
+    monkeypatch.setattr(capi, "_lib", lib)
+    return lib

@@ -1,0 +1,70 @@
+"""Kernel-logic checks WITHOUT a GPU: tophat_b200/csrc compiled for the host against tests/emu/shim (every warp = 32
+cooperative fibers, warp collectives = barriers; see tests/emu/shim/cuda_runtime.h) and compared with the oracle.
+This is a development harness for catching logic and warp-divergence bugs before GPU time is spent; the parity gate
+remains tests/test_gpu_*.py (-m gpu), which run the real sm_100a build."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+import kat
+from tophat_b200 import capi, synth
+from oracle import pyoracle
+
+
+@pytest.mark.parametrize("kw,over", [
+    (dict(contig_lens=(300_000, 100_000), n_pairs=2500, seed=301, indel_prob=0.3), {}),
+    (dict(contig_lens=(200_000,), n_pairs=1500, seed=302, decoy_rate=3.0, n_rate=0.01), dict(library_type=2)),
+    (dict(contig_lens=(200_000,), n_pairs=1500, seed=303, read_len=150, indel_prob=0.2), dict(inner_dist_mean=10, inner_dist_std_dev=40)),
+])
+def test_emu_segjuncs_matches_oracle(emu_lib, kw, over):
+    wl = synth.generate(synth.SynthConfig(**kw))
+    o = dict(inner_dist_mean=50, inner_dist_std_dev=20); o.update(over)
+    P = capi.default_params(**o)
+    batches = helpers.pack_both(wl)
+    got, t = helpers.gpu_segjuncs(P, wl.ref, batches)
+    want, cnt = pyoracle.segjuncs(P, wl.ref, batches)
+    helpers.assert_same_results(got, want, str(kw))
+    assert (t.n_windows, t.n_indel_tasks, t.n_rescue_tasks, t.n_juncs_emitted) == \
+        (cnt.n_windows, cnt.n_indel_tasks, cnt.n_rescue_tasks, cnt.n_juncs_emitted)
+
+
+@pytest.mark.parametrize("case", ["kat_junction", "kat_junction_seg1_unmapped", "kat_deletion", "kat_insertion", "kat_q0_quirk"])
+def test_emu_known_answers(emu_lib, case):
+    contigs, reads, exp = getattr(kat, case)()
+    ref, batch = helpers.manual_workload(contigs, reads)
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    got, _ = helpers.gpu_segjuncs(P, ref, [batch])
+    want, _ = pyoracle.segjuncs(P, ref, [batch])
+    helpers.assert_same_results(got, want, case)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_emu_join_matches_reference_records(emu_lib):
+    from test_gpu_join import joined_to_keys
+    wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(200_000, 80_000), n_pairs=1200, seed=511, indel_prob=0.4))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    ctx = capi.Context(0); ctx.ref_upload(wl.ref)
+    res, _ = helpers.gpu_segjuncs(P, wl.ref, helpers.pack_both(wl), ctx)
+    juncs, ins = capi.join_sets_from_results(res)
+    ctx.join_begin(P, juncs, ins)
+    names = wl.ref.names
+    with tempfile.TemporaryDirectory() as td:
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg)
+        assert open(outs["juncs"]).read() == pyoracle.format_juncs(res.junctions, names)
+        jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+        for sname, side in (("left", wl.left), ("right", wl.right)):
+            batch = synth.pack_join_side(wl, side, res.junctions)
+            got = joined_to_keys(ctx.join_submit(batch), batch, P)
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=sname, tag=".ref")
+            _, recs = pyoracle.read_bam(ref_bam)
+            want = set((int(r[0]), names.index(r[2]) + 1, r[3], r[5], r[1], r[11]["NM"]) for r in recs)
+            assert got == want, "%s: only ours %r; only reference %r" % (sname, sorted(got - want)[:3], sorted(want - got)[:3])
+            assert len(want) > 50
+    ctx.close()
