@@ -193,6 +193,46 @@ def format_insertions(i: np.ndarray, names: List[str]) -> str:
                                          r["seq"].decode()) for r in i)
 
 
+def format_fusions(f: np.ndarray, juncs: np.ndarray, names: List[str], resolve_conflicts: bool = True) -> str:
+    """segment.fusions text: the driver's conflict resolution between neighbouring fusions (same contigs, left
+    coordinates < 10 apart, same direction, same offset on both sides: keep the better supported one, ties broken by
+    coincidence with a splice-junction coordinate) and its print-out (segment_juncs.cpp:5096-5180).  `f` in Fusion order."""
+    coords = set()
+    for j in juncs:                                                   # 5048-5052
+        coords.add((int(j["ref_id"]), int(np.int32(j["left"])))); coords.add((int(j["ref_id"]), int(np.int32(j["right"]))))
+    n = len(f)
+    r1 = [int(x) for x in f["ref_id1"]]; r2 = [int(x) for x in f["ref_id2"]]
+    left = [int(np.int32(x)) for x in f["left"]]; right = [int(np.int32(x)) for x in f["right"]]
+    dr = [int(x) for x in f["dir"]]; count = [int(x) for x in f["count"]]
+    lc = [(r1[i], left[i]) in coords for i in range(n)]               # 5104-5115
+    rc = [(r2[i], right[i]) in coords for i in range(n)]
+    skip = [False] * n
+    out = []
+    for i in range(n):
+        k = i + 1
+        while k < n:                                                  # 5124-5155
+            ld = abs(left[i] - left[k])
+            if r1[i] == r1[k] and r2[i] == r2[k] and ld < 10:
+                if dr[i] == dr[k] and ld == abs(right[i] - right[k]):
+                    if count[k] > count[i]:
+                        skip[i] = True
+                    elif count[k] == count[i]:
+                        if int(lc[i]) + int(rc[i]) < int(lc[k]) + int(rc[k]):
+                            skip[i] = True
+                        else:
+                            skip[k] = True
+                    else:
+                        skip[k] = True
+                k += 1
+            else:
+                break
+        if skip[i] and resolve_conflicts:                             # 5157
+            continue
+        d = {8: "fr", 9: "rf", 10: "rr"}.get(dr[i], "ff")             # 5163-5171
+        out.append("%s\t%d\t%s\t%d\t%s\n" % (names[r1[i] - 1], left[i], names[r2[i] - 1], right[i], d))
+    return "".join(out)
+
+
 # ---------------------------------------------------------------------------------------------
 # long_spanning_reads: junction index + spliced segment hits + the reference binary
 

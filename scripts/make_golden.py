@@ -17,6 +17,11 @@ CASES = {
     "indel_heavy": (dict(contig_lens=(300_000,), n_pairs=2500, seed=102, indel_prob=0.5), 50, 20, []),
     "wide_flank": (dict(contig_lens=(500_000,), n_pairs=2000, seed=103, indel_prob=0.1, n_rate=0.004), 200, 20, []),
     "firststrand": (dict(contig_lens=(300_000, 100_000), n_pairs=2000, seed=104), 50, 20, ["--library-type", "fr-firststrand"]),
+    # BASELINE configs[4] style: chimeric fragments (ff / fr / rf / rr, intra- and inter-contig) with --fusion-search
+    "fusion_inter_intra": (dict(contig_lens=(250_000, 90_000, 60_000), n_pairs=3000, seed=105, indel_prob=0.1, fusion_frac=0.15), 50, 20,
+                           ["--fusion-search", "--fusion-anchor-length", "20", "--fusion-min-dist", "20000"]),
+    "fusion_default_dist": (dict(contig_lens=(200_000, 120_000), n_pairs=2500, seed=106, fusion_frac=0.25, decoy_rate=1.0), 50, 20,
+                            ["--fusion-search"]),
 }
 
 
@@ -33,12 +38,13 @@ def main():
             bams = pyoracle.make_bams(files, td, nseg)
             outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg,
                                               opts=pyoracle.tophat_common_opts(im, isd, extra))
-            for k in ("juncs", "insertions", "deletions"):
+            for k in ("juncs", "insertions", "deletions") + (("fusions",) if "--fusion-search" in extra else ()):
                 shutil.copy(outs[k], os.path.join(out, "segment." + k))
         with open(os.path.join(out, "config.json"), "w") as f:
             json.dump(dict(synth=kw, inner_dist_mean=im, inner_dist_std_dev=isd, extra=extra,
                            generator="scripts/make_golden.py", binary="oracle/_ref/segment_juncs (TopHat 2.1.2, -p1)"), f, indent=1)
-        print(name, {k: sum(1 for _ in open(os.path.join(out, "segment." + k))) for k in ("juncs", "insertions", "deletions")})
+        print(name, {k: sum(1 for _ in open(os.path.join(out, "segment." + k))) for k in ("juncs", "insertions", "deletions", "fusions")
+                     if os.path.exists(os.path.join(out, "segment." + k))})
 
 
 if __name__ == "__main__":

@@ -27,19 +27,27 @@ def load_golden(name):
     ex = cfg.get("extra", [])
     if "--library-type" in ex:
         over["library_type"] = LIBTYPE[ex[ex.index("--library-type") + 1]]
+    if "--fusion-search" in ex:
+        over["fusion_search"] = 1
+        for opt, field in (("--fusion-anchor-length", "fusion_anchor_length"), ("--fusion-min-dist", "fusion_min_dist")):
+            if opt in ex:
+                over[field] = int(ex[ex.index(opt) + 1])
     P = capi.default_params(**over)
-    texts = {k: open(os.path.join(d, "segment." + k)).read() for k in ("juncs", "insertions", "deletions")}
+    texts = {k: open(os.path.join(d, "segment." + k)).read() for k in ("juncs", "insertions", "deletions", "fusions")
+             if os.path.exists(os.path.join(d, "segment." + k))}
     return wl, P, texts
 
 
 def pack_both(wl, fusion_search=False):
+    fusion_search = bool(getattr(fusion_search, "fusion_search", fusion_search))      # accepts the Params struct too
     bl = synth.pack_side(wl.left, wl.right, False, fusion_search)
     br = synth.pack_side(wl.right, wl.left, True, fusion_search, order_base=bl.n_bundles)
     return [bl, br]
 
 
 def as_text(res, names):
-    return {"juncs": pyoracle.format_juncs(res.junctions, names),
+    return {"fusions": pyoracle.format_fusions(res.fusions, res.junctions, names),
+            "juncs": pyoracle.format_juncs(res.junctions, names),
             "insertions": pyoracle.format_insertions(res.insertions, names),
             "deletions": pyoracle.format_deletions(res.deletions, names)}
 

@@ -16,9 +16,9 @@ from oracle import pyoracle
 @pytest.mark.parametrize("name", helpers.golden_cases())
 def test_oracle_matches_golden(name):
     wl, P, want = helpers.load_golden(name)
-    res, _ = pyoracle.segjuncs(P, wl.ref, helpers.pack_both(wl))
+    res, _ = pyoracle.segjuncs(P, wl.ref, helpers.pack_both(wl, P))
     got = helpers.as_text(res, wl.ref.names)
-    for k in ("juncs", "insertions", "deletions"):
+    for k in want:
         assert got[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
 
 
@@ -44,6 +44,25 @@ def test_oracle_matches_live_reference(seed, indel, threads):
         outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg,
                                           threads=threads)
         for k in ("juncs", "insertions", "deletions"):
+            assert got[k] == open(outs[k]).read(), "segment.%s differs (seed %d)" % (k, seed)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,threads,min_dist", [(41, 1, 20000), (43, 2, 10000000)])
+def test_oracle_fusions_match_live_reference(seed, threads, min_dist):
+    """find_fusions / detect_fusion (segment_juncs.cpp:2976-3291, 2629-2805) + the fusion writer (5096-5180)."""
+    wl = synth.generate(synth.SynthConfig(contig_lens=(250_000, 90_000, 60_000), n_pairs=2500, seed=seed, indel_prob=0.1, fusion_frac=0.2))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20, fusion_search=1, fusion_min_dist=min_dist)
+    res, cnt = pyoracle.segjuncs(P, wl.ref, helpers.pack_both(wl, P))
+    got = helpers.as_text(res, wl.ref.names)
+    assert cnt.n_fusion_tasks > 500 and len(set(int(d) for d in res.fusions["dir"])) == 4      # ff, fr, rf, rr all occur
+    with tempfile.TemporaryDirectory() as td:
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        opts = pyoracle.tophat_common_opts(extra=["--fusion-search", "--fusion-min-dist", str(min_dist)])
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts, threads=threads)
+        for k in ("juncs", "insertions", "deletions", "fusions"):
             assert got[k] == open(outs[k]).read(), "segment.%s differs (seed %d)" % (k, seed)
 
 

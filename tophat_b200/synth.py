@@ -333,7 +333,25 @@ def _make_read_fwd(rng, cfg: SynthConfig, space: _ExonSpace, exonic: np.ndarray,
         shift[isel] = np.where(ar >= (p + ln)[isel, None], -ln[isel, None], 0)
         emap = emap + shift
         emap[ins_zone] = -1
+    inv = None
+    if cfg.fusion_frac > 0:
+        # chimeric fragments (config 5): the read's tail, from breakpoint p on, comes from a second exonic locus,
+        # in the same orientation (ff / rr fusions) or reverse-complemented (fr / rf)
+        chim = rng.random(n) < cfg.fusion_frac
+        bp = rng.integers(22, L - 21, size=n)
+        x1 = (rng.random(n) * (exonic.shape[0] - 2 * L)).astype(np.int64) + L
+        kind = rng.integers(0, 4, size=n)                  # 0, 1: same orientation; 2: tail inverted; 3: head inverted
+        tail = chim[:, None] & (ar >= bp[:, None])
+        head = chim[:, None] & (ar < bp[:, None]) & (kind == 3)[:, None]
+        fwd_tail = x1[:, None] + (ar - bp[:, None])
+        rev_tail = x1[:, None] + (L - 1 - ar)
+        rev_head = x1[:, None] + (bp[:, None] - 1 - ar)
+        emap = np.where(tail & (kind != 3)[:, None], np.where((kind == 2)[:, None], rev_tail, fwd_tail), emap)
+        emap = np.where(head, rev_head, emap)
+        inv = (tail & (kind == 2)[:, None]) | head
     codes = exonic[np.clip(emap, 0, exonic.shape[0] - 1)]
+    if inv is not None:
+        codes = np.where(inv & (codes < 4), 3 - codes, codes)
     inserted = emap < 0
     if inserted.any():
         codes = np.where(inserted, rng.integers(0, 4, size=codes.shape, dtype=np.uint8), codes)
@@ -341,6 +359,8 @@ def _make_read_fwd(rng, cfg: SynthConfig, space: _ExonSpace, exonic: np.ndarray,
     codes = np.where(sub & (codes < 4), (codes + rng.integers(1, 4, size=codes.shape, dtype=np.uint8)) % 4, codes)
     nn = rng.random(codes.shape) < cfg.n_rate
     codes = np.where(nn, 4, codes).astype(np.uint8)
+    if inv is not None:
+        return codes, emap, inv
     return codes, emap
 
 
@@ -382,7 +402,9 @@ def _gen_chunk(ci: int):
     acc = {s: dict(reads=[], seg=[[] for _ in range(nseg)], mapped=[], unm=[], truth=[], cand=[]) for s in ("left", "right")}
     a0, b0, plus = _sample_mates(rng, cfg, space, contigs, n)
     for which, x0 in (("A", a0), ("B", b0)):
-        codes_fwd, emap = _make_read_fwd(rng, cfg, space, exonic, x0)
+        made = _make_read_fwd(rng, cfg, space, exonic, x0)
+        codes_fwd, emap = made[0], made[1]
+        inv = made[2] if len(made) > 2 else None
         # A is sequenced forward, B reverse-complemented (fr library); fragment strand decides
         # which one is mate 1.
         rev = which == "B"
@@ -441,6 +463,26 @@ def _gen_chunk(ci: int):
                     part = sh[selmask[rows]]
                     if part.size:
                         acc[side]["seg"][k].append(part)
+            if inv is not None:
+                # segments lying entirely inside a reverse-complemented tail map to the opposite strand
+                rows = np.nonzero(inv[:, lo] & inv[:, lo + ln - 1] & ~mapped)[0]
+                if rows.size:
+                    rid_a, g_a, _ = space.to_genome(emap[rows, lo + ln - 1])
+                    rid_b, g_b, _ = space.to_genome(emap[rows, lo])
+                    refb = _gather_ref(contigs, rid_a, g_a, ln)
+                    seg_rc = revcomp_codes(codes_fwd[rows, lo:lo + ln])
+                    mm = ((seg_rc != refb) | (seg_rc > 3) | (refb > 3)).sum(axis=1)
+                    good = (rid_a == rid_b) & (g_b == g_a + ln - 1) & (mm <= 2) & (refb != 5).all(axis=1)
+                    rows, rid_a, g_a, mm = rows[good], rid_a[good], g_a[good], mm[good]
+                    sh = np.zeros(rows.size, dtype=SEGHIT_DTYPE)
+                    sh["read_idx"] = rows + done
+                    sh["ref_id"] = rid_a; sh["left"] = g_a; sh["right"] = g_a + ln
+                    sh["read_len"] = ln; sh["edit_dist"] = mm
+                    sh["flags"] = (0 if rev else HIT_ANTISENSE) | (HIT_END if k == nseg - 1 else 0)
+                    for side, selmask in (("left", is_left), ("right", ~is_left)):
+                        part = sh[selmask[rows]]
+                        if part.size:
+                            acc[side]["seg"][k].append(part)
             # decoy multihits at random positions
             if cfg.decoy_rate > 0:
                 nd = rng.poisson(cfg.decoy_rate, size=n)
