@@ -186,6 +186,10 @@ typedef struct thb_segjuncs_results {
 /* Clears the accumulated junction / deletion / insertion / fusion sets of the context. */
 int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* params);
 
+/* --fusion-ignore-chromosomes (common.cpp:174, segment_juncs.cpp:3213-3230): contig ids (1-based, as in thb_hit.ref_id)
+ * whose hits find_fusions skips.  Call after thb_segjuncs_begin; cleared by the next thb_segjuncs_begin.           */
+int thb_segjuncs_fusion_ignore(thb_ctx* ctx, const uint32_t* ref_ids, uint32_t n);
+
 /* Processes one batch whose arrays live in HOST memory (copied to the device inside the call).
  * Replaces, for every bundle, find_insertions_and_deletions -> detect_small_{deletion,insertion}
  * -> simpleSplitAlignment (2807-2942, 2554-2627, 2470-2541, 2390-2456), find_gaps (3293-3650)
@@ -281,7 +285,9 @@ typedef struct thb_timing {
   float scan_kernel_ms;         /* sum of the five scan-phase kernels below                              */
   float finish_ms; float total_ms;
   float bundle_ms, hit_ms, rescue_ms, rescued_windows_ms, window_scan_ms, indel_ms;   /* per kernel, CUDA events */
+  float fusion_enum_ms, fusion_detect_ms;                                              /* --fusion-search only    */
   uint64_t n_windows; uint64_t n_indel_tasks; uint64_t n_rescue_tasks; uint64_t n_juncs_emitted;
+  uint64_t n_fusion_tasks;      /* detect_fusion calls that reached simpleSplitAlignment                 */
   uint64_t algorithmic_bytes;
   uint32_t kernel_launches;   /* launches of the scan kernel                                       */
   uint32_t total_launches;    /* every kernel of this library since thb_segjuncs_begin (valid after finish) */

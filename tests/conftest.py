@@ -8,8 +8,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emu", action="store_true", default=False,
+                     help="development aid: run the C-ABI tests against the host-emulated kernels (tests/emu) instead of the GPU build")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    if config.getoption("--emu"):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        from tophat_b200 import capi
+        capi._lib = capi.load_library(build_emu.build())
 
 
 @pytest.fixture(scope="session")

@@ -42,6 +42,10 @@ def test_usage_and_empty_segment_list_exit_codes():
     (dict(contig_lens=(300_000, 120_000), n_pairs=3000, seed=301, indel_prob=0.3), True, []),
     (dict(contig_lens=(300_000,), n_pairs=3000, seed=302, indel_prob=0.2, n_rate=0.003), False, []),
     (dict(contig_lens=(250_000, 80_000), n_pairs=2500, seed=303), True, ["--library-type", "fr-secondstrand"]),
+    (dict(contig_lens=(250_000, 80_000, 60_000), n_pairs=3000, seed=305, indel_prob=0.1, fusion_frac=0.2), True,
+     ["--fusion-search", "--fusion-min-dist", "20000"]),
+    (dict(contig_lens=(250_000, 80_000), n_pairs=2500, seed=306, fusion_frac=0.2), True,
+     ["--fusion-search", "--fusion-ignore-chromosomes", "chrS2", "--fusion-do-not-resolve-conflicts"]),
 ])
 def test_cli_matches_reference_binary(kw, paired, extra):
     build.build_all()

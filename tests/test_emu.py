@@ -68,3 +68,64 @@ def test_emu_join_matches_reference_records(emu_lib):
             assert got == want, "%s: only ours %r; only reference %r" % (sname, sorted(got - want)[:3], sorted(want - got)[:3])
             assert len(want) > 50
     ctx.close()
+
+
+# ---- --fusion-search ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kw,over", [
+    (dict(contig_lens=(250_000, 90_000, 60_000), n_pairs=2500, seed=321, indel_prob=0.1, fusion_frac=0.15), dict(fusion_min_dist=20000)),
+    (dict(contig_lens=(200_000,), n_pairs=1500, seed=322, fusion_frac=0.3, decoy_rate=2.0), {}),
+    (dict(contig_lens=(150_000, 50_000), n_pairs=1200, seed=323, read_len=150, fusion_frac=0.2, n_rate=0.005), dict(fusion_anchor_length=30, fusion_min_dist=100)),
+])
+def test_emu_fusions_match_oracle(emu_lib, kw, over):
+    wl = synth.generate(synth.SynthConfig(**kw))
+    o = dict(inner_dist_mean=50, inner_dist_std_dev=20, fusion_search=1); o.update(over)
+    P = capi.default_params(**o)
+    batches = helpers.pack_both(wl, P)
+    got, t = helpers.gpu_segjuncs(P, wl.ref, batches)
+    want, cnt = pyoracle.segjuncs(P, wl.ref, batches)
+    helpers.assert_same_results(got, want, str(kw))
+    assert len(want.fusions) > 50
+    assert (t.n_windows, t.n_indel_tasks, t.n_rescue_tasks, t.n_juncs_emitted, t.n_fusion_tasks) == \
+        (cnt.n_windows, cnt.n_indel_tasks, cnt.n_rescue_tasks, cnt.n_juncs_emitted, cnt.n_fusion_tasks)
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.golden_cases() if n.startswith("fusion")])
+def test_emu_fusion_goldens(emu_lib, name):
+    wl, P, want = helpers.load_golden(name)
+    got, _ = helpers.gpu_segjuncs(P, wl.ref, helpers.pack_both(wl, P))
+    txt = helpers.as_text(got, wl.ref.names)
+    for k in want:
+        assert txt[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("extra", [["--fusion-search", "--fusion-min-dist", "20000"],
+                                   ["--fusion-search", "--fusion-ignore-chromosomes", "chrS2", "--fusion-do-not-resolve-conflicts"]])
+def test_emu_cli_fusions_match_reference_binary(extra):
+    """The segment_juncs host executable (BAM ingestion, bundle rules incl. the fusion-only reads, fusion writer) linked
+    against the emulated library, against the reference binary: all four output files byte for byte."""
+    import sys
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "emu"))
+    import build_emu
+    exe = build_emu.build_cli("segment_juncs")
+    with tempfile.TemporaryDirectory() as td:
+        wl = synth.generate(synth.SynthConfig(contig_lens=(200_000, 90_000, 50_000), n_pairs=2000, seed=331, indel_prob=0.1, fusion_frac=0.2))
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        opts = pyoracle.tophat_common_opts(50, 20, extra)
+        ref = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts, tag=".ref")
+        ours = pyoracle.run_segment_juncs(exe, files, bams, td, nseg, opts=opts, tag=".emu")
+        for k in ("juncs", "insertions", "deletions", "fusions"):
+            a, b = open(ours[k]).read(), open(ref[k]).read()
+            assert a == b, "segment.%s differs from the reference binary (%d vs %d lines)" % (k, a.count("\n"), b.count("\n"))
+        assert open(ref["fusions"]).read().count("\n") > 50
+
+
+def test_emu_allgather_world1():
+    """thb_segjuncs_allgather's staging / padding / re-insertion of all four record kinds, in a fresh process with a
+    single-rank stand-in for libnccl (tests/emu/fake_nccl.c)."""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "allgather_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "allgather ok" in r.stdout, r.stdout + r.stderr

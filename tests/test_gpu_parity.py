@@ -53,6 +53,31 @@ def test_gpu_matches_oracle(kw, over):
     assert t.kernel_launches >= 1
 
 
+@pytest.mark.parametrize("kw,over", [
+    (dict(contig_lens=(900_000, 300_000, 50_000), n_pairs=20_000, seed=231, indel_prob=0.1, fusion_frac=0.1), dict(fusion_min_dist=50000)),
+    (dict(contig_lens=(400_000, 400_000), n_pairs=10_000, seed=232, fusion_frac=0.3, decoy_rate=2.0), {}),
+    (dict(contig_lens=(400_000,), n_pairs=6_000, seed=233, read_len=150, fusion_frac=0.2, n_rate=0.005), dict(fusion_anchor_length=30, fusion_min_dist=100)),
+    (dict(contig_lens=(400_000, 100_000), n_pairs=6_000, seed=234, read_len=75, fusion_frac=0.2, ref_n_frac=0.05), dict(inner_dist_mean=10, inner_dist_std_dev=40)),
+])
+def test_gpu_fusions_match_oracle(kw, over):
+    """--fusion-search: find_fusions / detect_fusion (segment_juncs.cpp:2976-3291, 2629-2805) -- ff / fr / rf / rr, intra- and
+    inter-contig, with the mate-flank rescue; counts and minimum edit distances per fusion included."""
+    wl = synth.generate(synth.SynthConfig(**kw))
+    o = dict(inner_dist_mean=50, inner_dist_std_dev=20, fusion_search=1); o.update(over)
+    P = capi.default_params(**o)
+    batches = helpers.pack_both(wl, P)
+    got, t = helpers.gpu_segjuncs(P, wl.ref, batches)
+    want, cnt = pyoracle.segjuncs(P, wl.ref, batches)
+    helpers.assert_same_results(got, want, str(kw))
+    assert len(set(int(d) for d in want.fusions["dir"])) == 4 and len(want.fusions) > 200
+    assert (t.n_windows, t.n_indel_tasks, t.n_rescue_tasks, t.n_juncs_emitted, t.n_fusion_tasks) == \
+        (cnt.n_windows, cnt.n_indel_tasks, cnt.n_rescue_tasks, cnt.n_juncs_emitted, cnt.n_fusion_tasks)
+    # fusion records are order-independent: shards in any order give the same reduced set
+    parts = [shard.shard_batch(b, r, 3) for r in (1, 2, 0) for b in batches]
+    got3, _ = helpers.gpu_segjuncs(P, wl.ref, parts)
+    helpers.assert_same_results(got3, want, "3 shards " + str(kw))
+
+
 @pytest.mark.parametrize("case", ["kat_junction", "kat_junction_seg1_unmapped", "kat_deletion", "kat_insertion", "kat_q0_quirk"])
 def test_gpu_known_answers(case):
     contigs, reads, exp = getattr(kat, case)()

@@ -90,8 +90,9 @@ class ResultsC(C.Structure):
 class TimingC(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("scan_kernel_ms", C.c_float), ("finish_ms", C.c_float),
                 ("total_ms", C.c_float), ("bundle_ms", C.c_float), ("hit_ms", C.c_float), ("rescue_ms", C.c_float),
-                ("rescued_windows_ms", C.c_float), ("window_scan_ms", C.c_float), ("indel_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
-                ("n_rescue_tasks", C.c_uint64), ("n_juncs_emitted", C.c_uint64),
+                ("rescued_windows_ms", C.c_float), ("window_scan_ms", C.c_float), ("indel_ms", C.c_float),
+                ("fusion_enum_ms", C.c_float), ("fusion_detect_ms", C.c_float), ("n_windows", C.c_uint64), ("n_indel_tasks", C.c_uint64),
+                ("n_rescue_tasks", C.c_uint64), ("n_juncs_emitted", C.c_uint64), ("n_fusion_tasks", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("total_launches", C.c_uint32)]
 
 
@@ -165,6 +166,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_params_default.restype = None
     lib.thb_ref_upload.argtypes = [C.c_void_p, C.POINTER(RefImageC)]
     lib.thb_segjuncs_begin.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.thb_segjuncs_fusion_ignore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.thb_segjuncs_submit.argtypes = [C.c_void_p, C.POINTER(BatchC)]
     lib.thb_segjuncs_submit_device.argtypes = [C.c_void_p, C.POINTER(BatchC)]
     lib.thb_segjuncs_finish.argtypes = [C.c_void_p, C.POINTER(ResultsC)]
@@ -227,6 +229,10 @@ class Context:
 
     def segjuncs_begin(self, params: Params) -> None:
         self._check(self.lib.thb_segjuncs_begin(self.h, C.byref(params)), "thb_segjuncs_begin")
+
+    def segjuncs_fusion_ignore(self, ref_ids) -> None:
+        a = np.ascontiguousarray(np.asarray(ref_ids, dtype="<u4"))
+        self._check(self.lib.thb_segjuncs_fusion_ignore(self.h, a.ctypes.data if a.size else None, a.size), "thb_segjuncs_fusion_ignore")
 
     def segjuncs_submit(self, batch: synth.PackedBatch) -> None:
         b = batch_c(batch)

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <algorithm>
+#include <mutex>
 #include "tophat_b200.h"
 #include "thb_options.hpp"
 #include "thb_input.hpp"
@@ -92,8 +94,8 @@ static void process_side(thb_ctx* ctx, const Options& o, RefTable& rt, std::mute
     if (t > 0) flags |= THB_BUNDLE_INDELS | THB_BUNDLE_GAPS;
     if (fusion) { flags |= THB_BUNDLE_FUSIONS; if (t > 0 && t < (int)nseg - 1) flags |= THB_BUNDLE_FUSIONS_LAST; }
     bu.flags = flags;
-    // partner group: the mate's full-read hits, else the mate's last-segment hits (3322-3344)
-    if (t > 0) {
+    // partner group: the mate's full-read hits, else the mate's last-segment hits (3322-3344; find_fusions 3041-3064)
+    if (t > 0 || fusion) {
       bool has = false;
       if (pm) { uint32_t g; while ((g = pm->next_group_id()) != 0 && g < id) pm->skip_group();
                 if (g == id) { pm->next_group(b.partner); has = true; } }
@@ -161,6 +163,11 @@ int main(int argc, char** argv)
   { thb_ref_image img = g.image(); if (thb_ref_upload(ctx, &img) != THB_OK) die("Error: thb_ref_upload: %s", thb_last_error(ctx)); }
   auto t1 = std::chrono::steady_clock::now();
   if (thb_segjuncs_begin(ctx, &o.p) != THB_OK) die("Error: %s", thb_last_error(ctx));
+  if (o.p.fusion_search && !o.fusion_ignore_chromosomes.empty()) {                               // 3213-3219
+    std::vector<uint32_t> ids;
+    for (auto& nm : o.fusion_ignore_chromosomes) ids.push_back(rt.get_id(nm));
+    if (thb_segjuncs_fusion_ignore(ctx, ids.data(), (uint32_t)ids.size()) != THB_OK) die("Error: %s", thb_last_error(ctx));
+  }
 
   std::mutex rtm; uint64_t order_base = 0; Stats st;
   fprintf(stderr, ">> Performing segment-search:\n");
@@ -195,7 +202,40 @@ int main(int argc, char** argv)
     fprintf(ins_out, "%s\t%d\t%d\t%s\n", rt.name(r.insertions[i].ref_id).c_str(), (int)r.insertions[i].left, (int)r.insertions[i].left,
             r.insertions[i].seq);
   fclose(ins_out);
+  {
+    // segment.fusions (5096-5180): neighbouring fusions (same contigs, left ends < 10 apart, same direction and the same
+    // offset on both sides) compete -- the better supported one stays, ties go to the one whose ends coincide with
+    // splice-junction coordinates
+    struct Coord { uint32_t ref; int c; bool operator<(const Coord& r) const { return ref < r.ref || (ref == r.ref && c < r.c); } };
+    std::vector<Coord> coords;
+    if (o.p.fusion_search)
+      for (uint64_t i = 0; i < r.n_junctions; ++i) { coords.push_back({r.junctions[i].ref_id, (int)r.junctions[i].left}); coords.push_back({r.junctions[i].ref_id, (int)r.junctions[i].right}); }
+    std::sort(coords.begin(), coords.end());
+    const uint64_t nf = r.n_fusions;
+    std::vector<char> skip(nf, 0), lc(nf, 0), rc(nf, 0);
+    for (uint64_t i = 0; i < nf; ++i) {
+      lc[i] = std::binary_search(coords.begin(), coords.end(), Coord{r.fusions[i].ref_id1, (int)r.fusions[i].left});
+      rc[i] = std::binary_search(coords.begin(), coords.end(), Coord{r.fusions[i].ref_id2, (int)r.fusions[i].right});
+    }
+    for (uint64_t i = 0; i < nf; ++i) {
+      const thb_fusion& f = r.fusions[i];
+      for (uint64_t k = i + 1; k < nf; ++k) {
+        const thb_fusion& g2 = r.fusions[k];
+        const int left_diff = abs((int)f.left - (int)g2.left);
+        if (!(f.ref_id1 == g2.ref_id1 && f.ref_id2 == g2.ref_id2 && left_diff < 10)) break;
+        if (f.dir == g2.dir && left_diff == abs((int)f.right - (int)g2.right)) {
+          if (g2.count > f.count) skip[i] = 1;
+          else if (g2.count == f.count) { if ((int)lc[i] + (int)rc[i] < (int)lc[k] + (int)rc[k]) skip[i] = 1; else skip[k] = 1; }
+          else skip[k] = 1;
+        }
+      }
+      if (skip[i] && !o.fusion_do_not_resolve_conflicts) continue;
+      const char* dir = f.dir == 8 ? "fr" : f.dir == 9 ? "rf" : f.dir == 10 ? "rr" : "ff";
+      fprintf(fus_out, "%s\t%d\t%s\t%d\t%s\n", rt.name(f.ref_id1).c_str(), (int)f.left, rt.name(f.ref_id2).c_str(), (int)f.right, dir);
+    }
+  }
   fclose(fus_out);
+  fprintf(stderr, "Reporting potential fusions...\n");
   if (getenv("TOPHAT_GPU_STATS")) {
     thb_timing tm; thb_last_timing(ctx, &tm);
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };

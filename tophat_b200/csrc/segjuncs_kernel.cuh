@@ -71,6 +71,7 @@ constexpr int ORDER_SHIFT = 24;         // order = (global bundle position) << 2
 struct SegParams {
   int seglen, segmm, min_intron, max_intron, max_ins, max_del, max_multihits;
   int inner_mean, inner_sd, bowtie2, library_type;
+  int fusion_search, fusion_min_dist;
 };
 
 struct BatchView {
@@ -234,7 +235,7 @@ __device__ __forceinline__ void push_indel(const Queues& q, uint64_t gL, int P, 
 // A thread-per-bundle enumeration walks three nested data-dependent loops; lanes drift apart and are effectively
 // serialised (profiles/r1b: 8 of 32 lanes active, 1.0-1.2 ms per 5.3 M bundles).
 
-// per-bundle state written by K1a: last(4) | indel_pairs(4) << 4 | do_windows << 8 | right_mate << 9
+// per-bundle state written by K1a: last(4) | indel_pairs(4) << 4 | do_windows << 8 | right_mate << 9 | re-anchored by the mate << 10
 struct HitOwner { uint32_t v; };     // bundle index in launch << 4 | segment
 
 // Geometry of the mate-flank rescue for one partner hit (find_gaps 3421-3451).
@@ -309,16 +310,27 @@ bundle_kernel(RefView ref, SegParams P, BatchView bv, Queues q, uint32_t* __rest
     }
     __syncwarp();
     const bool rescued = gaps && last > 0 && check_partner && B.n_partner > 0;    // 3392: the mate re-anchors the read
+    // find_fusions re-anchors too, under its own pair rule (3123-3142); whether it gets that far is decided in
+    // fusion_enum_kernel, here every partner hit it could ask for is queued (a superset; the search is a pure function)
+    const bool fus = act && P.fusion_search && (B.flags & THB_BUNDLE_FUSIONS) && B.n_partner > 0 && B.seg_n[0] > 0;
     if (rescued) {
       const unsigned long long rb = agg_slot(q.counts + 3);
       q.rbundle[rb] = bi;
+    }
+    if (rescued || fus) {
+      const int minus_dist = -P.max_ins * 2;
       for (int r = 0; r < B.n_partner; ++r) {
         const Hit rightHit = load_hit(B.partner + r);
         if (rescue_geom(ref, P, rightHit, B.read_len).status != RG_COMPUTE) continue;
         bool any = false;
         for (int l = 0; l < B.seg_n[0] && !any; ++l) {
           const Hit leftHit = load_hit(B.seg_ptr[0] + l);
-          any = leftHit.ref_id == rightHit.ref_id && leftHit.anti != rightHit.anti;    // 3412
+          const bool opposite = leftHit.ref_id == rightHit.ref_id && leftHit.anti != rightHit.anti;
+          if (rescued) any = opposite;                                                 // 3412
+          if (fus && !any) {
+            const int dist = leftHit.anti ? leftHit.left - rightHit.right : rightHit.left - leftHit.right;
+            any = !(opposite && dist > minus_dist && dist <= P.fusion_min_dist);       // 3132-3142
+          }
         }
         if (!any) continue;
         const unsigned long long slot = agg_slot(q.counts + 2);
@@ -333,7 +345,7 @@ bundle_kernel(RefView ref, SegParams P, BatchView bv, Queues q, uint32_t* __rest
         for (int s = 0; s < NSMAX; ++s) if (s <= last && B.seg_n[s] > P.max_multihits) do_windows = false;
       }
       bstate[bi] = (uint32_t)last | ((uint32_t)indel_pairs << 4) | ((uint32_t)do_windows << 8) |
-                   (((B.flags & THB_BUNDLE_RIGHT_MATE) ? 1u : 0u) << 9);
+                   (((B.flags & THB_BUNDLE_RIGHT_MATE) ? 1u : 0u) << 9) | ((rescued ? 1u : 0u) << 10);
     }
     __syncwarp();
   }

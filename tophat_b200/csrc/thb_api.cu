@@ -16,6 +16,7 @@
 #include "../../include/tophat_b200.h"
 #include "segjuncs_kernel.cuh"
 #include "join_kernel.cuh"
+#include "fusion_kernel.cuh"
 
 using namespace thb;
 
@@ -69,6 +70,10 @@ struct thb_ctx {
   // result sets
   DevBuf d_juncs, d_dels; uint64_t cap_juncs = 0, cap_dels = 0;
   DevBuf d_ins; uint64_t cap_ins = 0;
+  // --fusion-search: candidate pair queue, record append buffer, ignored contigs
+  DevBuf d_fus, q_fus, d_fus_ignore; uint64_t cap_fus = 0, cap_fustask = 0; FusionParams fp{};
+  unsigned long long* d_fus_count = nullptr; unsigned long long* d_fustask_count = nullptr; unsigned long long h_fus_count = 0;
+  std::vector<FusRec> h_fusrec;
   DevBuf d_scalars;                 // [0..7] counters (u64), then ins_count(u64), then flags (u32 x4)
   unsigned long long* d_counters = nullptr; unsigned long long* d_ins_count = nullptr;
   unsigned int* d_ovf_juncs = nullptr; unsigned int* d_ovf_dels = nullptr; unsigned int* d_err = nullptr;
@@ -78,7 +83,7 @@ struct thb_ctx {
   DevBuf q_win, q_indel, q_rescue, q_rescue_out, q_rbundle, q_bstate, q_owner;
   uint64_t cap_win = 0, cap_indel = 0;
   unsigned long long* d_qcounts = nullptr; unsigned int* d_qovf = nullptr;
-  cudaEvent_t kev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool kev_pending = false;
   int sms = 148;
   Staging stage[2];
@@ -151,10 +156,11 @@ SegOutputs outputs(thb_ctx* ctx)
 
 struct Flags { unsigned int ovf_juncs, ovf_dels, err, qovf; };
 
-int read_state(thb_ctx* ctx, Flags* f, unsigned long long* ins_count)
+int read_state(thb_ctx* ctx, Flags* f, unsigned long long* ins_count, unsigned long long* fus_counts2)
 {
   CU(cudaMemcpyAsync(f, ctx->d_ovf_juncs, sizeof(Flags), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaMemcpyAsync(ins_count, ctx->d_ins_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaMemcpyAsync(fus_counts2, ctx->d_fus_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   return THB_OK;
 }
@@ -179,6 +185,14 @@ void launch_phase(thb_ctx* ctx, const BatchView& bv, const Queues& q, const SegO
   cudaEventRecord(ctx->kev[5], ctx->compute);
   indel_kernel<<<g_t, 256, 0, ctx->compute>>>(ctx->ref, q, o);
   cudaEventRecord(ctx->kev[6], ctx->compute);
+  if (ctx->sp.fusion_search) {
+    FusionQueues fq; fq.tasks = (FusionTask*)ctx->q_fus.p; fq.cap = ctx->cap_fustask; fq.count = ctx->d_fustask_count;
+    fq.rec = (FusRec*)ctx->d_fus.p; fq.rec_cap = ctx->cap_fus; fq.rec_count = ctx->d_fus_count; fq.err = ctx->d_err; fq.counters = ctx->d_counters;
+    fusion_enum_kernel<NSMAX><<<grid_for(bv.n_bundles, 128), 128, 0, ctx->compute>>>(ctx->ref, ctx->sp, ctx->fp, bv, q, fq, bstate);
+    cudaEventRecord(ctx->kev[7], ctx->compute);
+    fusion_detect_kernel<<<g_t, 128, 0, ctx->compute>>>(ctx->ref, ctx->fp, bv, fq);
+    cudaEventRecord(ctx->kev[8], ctx->compute);
+  }
 }
 
 int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t n_hits)
@@ -195,13 +209,18 @@ int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t 
   q.rescue = (uint2*)ctx->q_rescue.p; q.rescue_out = (int2*)ctx->q_rescue_out.p; q.rbundle = (uint32_t*)ctx->q_rbundle.p;
   q.counts = ctx->d_qcounts; q.overflow = ctx->d_qovf;
   CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
+  if (ctx->sp.fusion_search) {
+    ctx->cap_fustask = std::max<uint64_t>(ctx->cap_fustask, std::max<uint64_t>(bv.n_bundles, 1u << 16));
+    CU(ctx->q_fus.reserve(ctx->cap_fustask * sizeof(FusionTask)));
+    CU(cudaMemsetAsync(ctx->d_fustask_count, 0, sizeof(unsigned long long), ctx->compute));
+  }
   const SegOutputs o = outputs(ctx);
   if (bv.n_segs <= 4) launch_phase<4>(ctx, bv, q, o, n_hits);
   else if (bv.n_segs <= 8) launch_phase<8>(ctx, bv, q, o, n_hits);
   else launch_phase<14>(ctx, bv, q, o, n_hits);
   CU(cudaGetLastError());
   ctx->kev_pending = true;
-  ctx->timing.kernel_launches++; ctx->own_launches += 6;
+  ctx->timing.kernel_launches++; ctx->own_launches += ctx->sp.fusion_search ? 8 : 6;
   return THB_OK;
 }
 
@@ -211,8 +230,9 @@ void collect_kernel_times(thb_ctx* ctx, float* total)
   *total = 0.f;
   if (!ctx->kev_pending) return;
   ctx->kev_pending = false;
-  float* dst[6] = { &ctx->timing.bundle_ms, &ctx->timing.hit_ms, &ctx->timing.rescue_ms, &ctx->timing.rescued_windows_ms, &ctx->timing.window_scan_ms, &ctx->timing.indel_ms };
-  for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]) == cudaSuccess) { *dst[k] += ms; *total += ms; } }
+  float* dst[8] = { &ctx->timing.bundle_ms, &ctx->timing.hit_ms, &ctx->timing.rescue_ms, &ctx->timing.rescued_windows_ms, &ctx->timing.window_scan_ms, &ctx->timing.indel_ms,
+                    &ctx->timing.fusion_enum_ms, &ctx->timing.fusion_detect_ms };
+  for (int k = 0; k < (ctx->sp.fusion_search ? 8 : 6); ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]) == cudaSuccess) { *dst[k] += ms; *total += ms; } }
 }
 
 int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
@@ -232,9 +252,18 @@ int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
 // (set inserts are idempotent; the insertion buffer is rolled back to `ins_before`).
 int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* redo)
 {
-  Flags f; unsigned long long ins_now; *redo = false;
-  int rc = read_state(ctx, &f, &ins_now); if (rc) return rc;
+  Flags f; unsigned long long ins_now, fus_now[2]; *redo = false;
+  int rc = read_state(ctx, &f, &ins_now, fus_now); if (rc) return rc;
   const unsigned long long ins_before = *ins_before_p;      // valid only after the sync above
+  const unsigned long long fus_before = ctx->h_fus_count;   // fusion records of the launches completed before this one
+  if ((f.err & 4u) || fus_now[1] > ctx->cap_fustask) { ctx->cap_fustask = std::max<uint64_t>(ctx->cap_fustask * 2, fus_now[1] + 1024); *redo = true; }
+  if ((f.err & 8u) || fus_now[0] > ctx->cap_fus) {
+    uint64_t ncap = std::max<uint64_t>(ctx->cap_fus * 2, fus_now[0] + 1024);
+    DevBuf nb; CU(nb.reserve(ncap * sizeof(FusRec)));
+    CU(cudaMemcpyAsync(nb.p, ctx->d_fus.p, (size_t)std::min<uint64_t>(fus_before, ctx->cap_fus) * sizeof(FusRec), cudaMemcpyDeviceToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    ctx->d_fus.release(); ctx->d_fus = nb; ctx->cap_fus = ncap; *redo = true;
+  }
   if (f.err & 2u) return fail(ctx, THB_EUNSUPPORTED, "more than %d rescued mate-anchor hits for one read (raise RES_MAX)", RES_MAX);
   if (f.qovf & 1u) { ctx->cap_win *= 2; *redo = true; }
   if (f.qovf & 2u) { ctx->cap_indel *= 2; *redo = true; }
@@ -247,9 +276,10 @@ int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* r
     CU(cudaStreamSynchronize(ctx->compute));
     ctx->d_ins.release(); ctx->d_ins = nb; ctx->cap_ins = ncap; *redo = true;
   }
-  if (!*redo) ctx->h_ins_count = ins_now;
+  if (!*redo) { ctx->h_ins_count = ins_now; ctx->h_fus_count = fus_now[0]; }
   if (*redo) {
     CU(cudaMemcpyAsync(ctx->d_ins_count, &ins_before, sizeof ins_before, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaMemcpyAsync(ctx->d_fus_count, &fus_before, sizeof fus_before, cudaMemcpyHostToDevice, ctx->compute));
     CU(cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(unsigned int), ctx->compute));   // err + queue overflow flags
     CU(cudaStreamSynchronize(ctx->compute));
   }
@@ -264,6 +294,18 @@ uint64_t algorithmic_bytes(const thb_ctx* ctx, const unsigned long long* cnt)
          cnt[0] * (32ull + 64ull) + 16ull * cnt[3] +               // windows + junction records
          cnt[1] * (32ull + 64ull) + 16ull * (ctx->n_ins_out + ctx->n_del_out) +
          cnt[2] * (32ull + 128ull);
+}
+
+// appends the valid records of a gathered (padded) insertion / fusion buffer; padding = all-ones first word
+template <class Rec>
+__global__ void rec_append_kernel(const Rec* src, uint64_t n, Rec* dst, unsigned long long* count, unsigned long long cap, unsigned int* err, unsigned int err_bit)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const Rec r = src[i];
+    if (*reinterpret_cast<const unsigned long long*>(&r) == ~0ull) continue;
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    if (slot < cap) dst[slot] = r; else atomicOr(err, err_bit);
+  }
 }
 
 }  // namespace
@@ -314,6 +356,7 @@ int thb_create(int device, thb_ctx** out)
   ctx->d_ovf_juncs = (unsigned int*)(ctx->d_counters + 9);
   ctx->d_ovf_dels = ctx->d_ovf_juncs + 1; ctx->d_err = ctx->d_ovf_juncs + 2; ctx->d_qovf = ctx->d_ovf_juncs + 3;
   ctx->d_qcounts = ctx->d_counters + 12;
+  ctx->d_fus_count = ctx->d_counters + 16; ctx->d_fustask_count = ctx->d_counters + 17;
   for (auto& e : ctx->kev) cudaEventCreate(&e);
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
   cudaMemset(ctx->d_scalars.p, 0, 256);
@@ -331,7 +374,7 @@ void thb_destroy(thb_ctx* ctx)
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
-                     &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx }) b->release();
+                     &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
@@ -414,7 +457,6 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
     return fail(ctx, THB_EUNSUPPORTED, "--max-segment-intron %d too large for the 24-bit span field", p->max_segment_intron_length);
   if (p->max_insertion_length > 20 || p->max_deletion_length > 1000)
     return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 20 / --max-deletion-length > 1000 not supported");
-  if (p->fusion_search) return fail(ctx, THB_EUNSUPPORTED, "--fusion-search is not implemented on the GPU path yet");
   if (p->inner_dist_mean + p->inner_dist_std_dev + std::max(0, p->inner_dist_std_dev - p->inner_dist_mean) > 100000)
     return fail(ctx, THB_EUNSUPPORTED, "mate flank longer than 100000 bases");
   ctx->params = *p;
@@ -423,6 +465,9 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   s.max_intron = p->max_segment_intron_length; s.max_ins = p->max_insertion_length; s.max_del = p->max_deletion_length;
   s.max_multihits = p->max_seg_multihits; s.inner_mean = p->inner_dist_mean; s.inner_sd = p->inner_dist_std_dev;
   s.bowtie2 = p->bowtie2; s.library_type = p->library_type;
+  s.fusion_search = p->fusion_search ? 1 : 0; s.fusion_min_dist = p->fusion_min_dist;
+  ctx->fp.fusion_min_dist = p->fusion_min_dist; ctx->fp.fusion_anchor = p->fusion_anchor_length; ctx->fp.n_ignore = 0; ctx->fp.ignore = nullptr;
+  if (s.fusion_search) { if (ctx->cap_fus == 0) ctx->cap_fus = 1ull << 16; CU(ctx->d_fus.reserve(ctx->cap_fus * sizeof(FusRec))); }
   if (ctx->cap_juncs == 0) ctx->cap_juncs = 1ull << 21;
   if (ctx->cap_dels == 0) ctx->cap_dels = 1ull << 18;
   if (ctx->cap_ins == 0) ctx->cap_ins = 1ull << 18;
@@ -435,9 +480,22 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   ctx->h_juncs.clear(); ctx->h_dels.clear(); ctx->h_ins.clear(); ctx->h_fus.clear();
   memset(&ctx->timing, 0, sizeof ctx->timing);
   ctx->own_launches = 2;            // the two hs_clear launches above
-  ctx->h_ins_count = 0;
+  ctx->h_ins_count = 0; ctx->h_fus_count = 0;
   ctx->n_bundles_total = ctx->n_hits_total = ctx->n_partner_total = 0; ctx->n_ins_out = ctx->n_del_out = 0;
   ctx->begun = true;
+  return THB_OK;
+}
+
+int thb_segjuncs_fusion_ignore(thb_ctx* ctx, const uint32_t* ref_ids, uint32_t n)
+{
+  if (!ctx || (n && !ref_ids)) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  if (n > 4096) return fail(ctx, THB_EUNSUPPORTED, "more than 4096 ignored contigs");
+  CU(ctx->d_fus_ignore.reserve((size_t)(n + 1) * 4));
+  if (n) CU(cudaMemcpyAsync(ctx->d_fus_ignore.p, ref_ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->fp.n_ignore = (int)n; ctx->fp.ignore = (const uint32_t*)ctx->d_fus_ignore.p;
   return THB_OK;
 }
 
@@ -453,7 +511,7 @@ int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* b)
   unsigned long long ins_before = ctx->h_ins_count;
   float ms_total = 0.f; bool done = false;
   for (int attempt = 0; attempt < 24 && !done; ++attempt) {
-    unsigned long long cnt0[4];
+    unsigned long long cnt0[8];
     CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
     rc = launch_scan(ctx, bv, b->n_partner_hits, b->n_hits); if (rc) return rc;
     bool redo = false;
@@ -515,7 +573,7 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
     unsigned long long ins_before = ctx->h_ins_count;
     bool done = false;
     for (int attempt = 0; attempt < 24; ++attempt) {
-      unsigned long long cnt0[4];
+      unsigned long long cnt0[8];
       CU(cudaMemcpyAsync(cnt0, ctx->d_counters, sizeof cnt0, cudaMemcpyDeviceToHost, ctx->compute));
       rc = launch_scan(ctx, bv, r.p1 - r.p0, r.h1 - r.h0); if (rc) return rc;
       // the next chunk's copy (other staging buffer, whose kernel already completed) overlaps this scan
@@ -590,6 +648,29 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
     for (uint32_t k = 0; k < len && k < 19; ++k) o.seq[k] = "ACGTN"[(r.seq >> (3 * k)) & 7];
     ctx->h_ins.push_back(o);
   }
+  // fusions: reduce the appended records by key -- count, minimum edit distance (2787-2803, fusions.h:87-101)
+  ctx->h_fus.clear();
+  if (ctx->sp.fusion_search) {
+    unsigned long long nfus = 0;
+    CU(cudaMemcpyAsync(&nfus, ctx->d_fus_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    ctx->h_fusrec.resize(nfus);
+    if (nfus) { CU(cudaMemcpyAsync(ctx->h_fusrec.data(), ctx->d_fus.p, nfus * sizeof(FusRec), cudaMemcpyDeviceToHost, ctx->compute)); CU(cudaStreamSynchronize(ctx->compute)); }
+    auto key_lt = [](const FusRec& a, const FusRec& b) {          // Fusion::operator<, fusions.h:40-70
+      if (a.r1 != b.r1) return a.r1 < b.r1; if (a.r2 != b.r2) return a.r2 < b.r2; if (a.left != b.left) return a.left < b.left;
+      if (a.right != b.right) return a.right < b.right; return a.dir < b.dir; };
+    std::sort(ctx->h_fusrec.begin(), ctx->h_fusrec.end(), key_lt);
+    for (size_t i = 0; i < ctx->h_fusrec.size(); ++i) {
+      const FusRec& r = ctx->h_fusrec[i];
+      const uint32_t cnt1 = r.pad0 ? r.pad0 : 1u;                  // pad0: count carried by an already reduced record (all-gather)
+      if (!ctx->h_fus.empty()) {
+        thb_fusion& b = ctx->h_fus.back();
+        if (b.ref_id1 == r.r1 && b.ref_id2 == r.r2 && b.left == r.left && b.right == r.right && b.dir == r.dir) { b.count += cnt1; b.edit_dist = std::min(b.edit_dist, r.edit); continue; }
+      }
+      thb_fusion o; o.ref_id1 = r.r1; o.ref_id2 = r.r2; o.left = r.left; o.right = r.right; o.dir = r.dir; o.count = cnt1; o.edit_dist = r.edit; o.reserved = 0;
+      ctx->h_fus.push_back(o);
+    }
+  }
   CU(cudaEventRecord(ctx->ev_b, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   float ms = 0.f; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
@@ -598,6 +679,7 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   CU(cudaMemcpy(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
   ctx->n_ins_out = nins; ctx->n_del_out = ctx->h_dels.size();
   ctx->timing.n_windows = cnt[0]; ctx->timing.n_indel_tasks = cnt[1]; ctx->timing.n_rescue_tasks = cnt[2]; ctx->timing.n_juncs_emitted = cnt[3];
+  ctx->timing.n_fusion_tasks = cnt[7];
   ctx->timing.algorithmic_bytes = algorithmic_bytes(ctx, cnt);
   ctx->timing.total_launches = ctx->own_launches;
   out->n_junctions = ctx->h_juncs.size(); out->junctions = ctx->h_juncs.data();
@@ -828,17 +910,6 @@ int thb_comm_init(thb_ctx* ctx, const void* uid, int rank, int world)
   return THB_OK;
 }
 
-// appends the valid records of a gathered (padded) insertion buffer
-__global__ void ins_append_kernel(const InsRec* src, uint64_t n, InsRec* dst, unsigned long long* count, unsigned long long cap, unsigned int* err)
-{
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const InsRec r = src[i];
-    if (r.key == ~0ull) continue;
-    const unsigned long long slot = atomicAdd(count, 1ull);
-    if (slot < cap) dst[slot] = r; else atomicOr(err, 1u);
-  }
-}
-
 // Union of the per-rank sets (replaces the per-thread set union of segment_juncs.cpp:4911-4922).  One all-gather of
 // the three set sizes, one host read of them, then one grouped all-gather of the padded payloads and device-side
 // inserts; staging buffers persist in the context.
@@ -849,36 +920,40 @@ int thb_segjuncs_allgather(thb_ctx* ctx)
   if (!ctx->comm) return fail(ctx, THB_ESTATE, "thb_comm_init not called");
   const int W = ctx->world;
   const uint64_t capj = ctx->cap_juncs, capd = ctx->cap_dels;
-  CU(ctx->d_keys.reserve((capj + capd) * 8)); CU(ctx->d_count.reserve(8 * (size_t)(3 + 3 * W)));
+  CU(ctx->d_keys.reserve((capj + capd) * 8)); CU(ctx->d_count.reserve(8 * (size_t)(4 + 4 * W)));
   unsigned long long* d_cnt = (unsigned long long*)ctx->d_count.p;
   uint64_t* keys_j = (uint64_t*)ctx->d_keys.p; uint64_t* keys_d = keys_j + capj;
-  CU(cudaMemsetAsync(d_cnt, 0, 24, ctx->compute));
+  CU(cudaMemsetAsync(d_cnt, 0, 32, ctx->compute));
   hs_compact_kernel<<<grid_for(capj, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_juncs.p, capj, keys_j, d_cnt + 0);
   hs_compact_kernel<<<grid_for(capd, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_dels.p, capd, keys_d, d_cnt + 1);
   CU(cudaGetLastError()); ctx->own_launches += 2;
   CU(cudaMemcpyAsync(d_cnt + 2, ctx->d_ins_count, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  if (ctx->sp.fusion_search) CU(cudaMemcpyAsync(d_cnt + 3, ctx->d_fus_count, 8, cudaMemcpyDeviceToDevice, ctx->compute));
   // ncclUint64 = 5
-  if (ctx->nccl.AllGather(d_cnt, d_cnt + 3, 3, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
-  std::vector<unsigned long long> counts(3 + 3 * (size_t)W);
+  if (ctx->nccl.AllGather(d_cnt, d_cnt + 4, 4, 5, ctx->comm, ctx->compute) != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(counts)");
+  std::vector<unsigned long long> counts(4 + 4 * (size_t)W);
   CU(cudaMemcpyAsync(counts.data(), d_cnt, 8 * counts.size(), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  unsigned long long mx[3] = {0, 0, 0}, tot[3] = {0, 0, 0};
-  for (int r = 0; r < W; ++r) for (int k = 0; k < 3; ++k) { const unsigned long long c = counts[3 + 3 * r + k]; mx[k] = std::max(mx[k], c); tot[k] += c; }
+  unsigned long long mx[4] = {0, 0, 0, 0}, tot[4] = {0, 0, 0, 0};
+  for (int r = 0; r < W; ++r) for (int k = 0; k < 4; ++k) { const unsigned long long c = counts[4 + 4 * r + k]; mx[k] = std::max(mx[k], c); tot[k] += c; }
   if (counts[2] > ctx->cap_ins) return fail(ctx, THB_ESTATE, "insertion buffer overflow before the all-gather");
-  // staging: [juncs send | dels send | ins send] and the W-fold receive areas
-  const size_t sj = mx[0] * 8, sd = mx[1] * 8, si = mx[2] * sizeof(InsRec);
-  CU(ctx->ag_send.reserve(sj + sd + si + 64)); CU(ctx->ag_recv.reserve((sj + sd + si) * (size_t)W + 64));
+  if (counts[3] > ctx->cap_fus) return fail(ctx, THB_ESTATE, "fusion buffer overflow before the all-gather");
+  // staging: [juncs send | dels send | ins send | fusion send] and the W-fold receive areas
+  const size_t sj = mx[0] * 8, sd = mx[1] * 8, si = mx[2] * sizeof(InsRec), sf = mx[3] * sizeof(FusRec);
+  CU(ctx->ag_send.reserve(sj + sd + si + sf + 64)); CU(ctx->ag_recv.reserve((sj + sd + si + sf) * (size_t)W + 64));
   uint8_t* send = (uint8_t*)ctx->ag_send.p; uint8_t* recv = (uint8_t*)ctx->ag_recv.p;
-  if (sj + sd + si) CU(cudaMemsetAsync(send, 0xff, sj + sd + si, ctx->compute));                     // pad with HS_EMPTY
+  if (sj + sd + si + sf) CU(cudaMemsetAsync(send, 0xff, sj + sd + si + sf, ctx->compute));           // pad with HS_EMPTY
   if (counts[0]) CU(cudaMemcpyAsync(send, keys_j, counts[0] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
   if (counts[1]) CU(cudaMemcpyAsync(send + sj, keys_d, counts[1] * 8, cudaMemcpyDeviceToDevice, ctx->compute));
   if (counts[2]) CU(cudaMemcpyAsync(send + sj + sd, ctx->d_ins.p, counts[2] * sizeof(InsRec), cudaMemcpyDeviceToDevice, ctx->compute));
-  uint8_t* rj = recv; uint8_t* rd = recv + sj * W; uint8_t* ri = rd + sd * W;
+  if (counts[3]) CU(cudaMemcpyAsync(send + sj + sd + si, ctx->d_fus.p, counts[3] * sizeof(FusRec), cudaMemcpyDeviceToDevice, ctx->compute));
+  uint8_t* rj = recv; uint8_t* rd = recv + sj * W; uint8_t* ri = rd + sd * W; uint8_t* rf = ri + si * W;
   if (ctx->nccl.GroupStart) ctx->nccl.GroupStart();
   int e = 0;
   if (mx[0]) e |= ctx->nccl.AllGather(send, rj, mx[0], 5, ctx->comm, ctx->compute);
   if (mx[1]) e |= ctx->nccl.AllGather(send + sj, rd, mx[1], 5, ctx->comm, ctx->compute);
   if (mx[2]) e |= ctx->nccl.AllGather(send + sj + sd, ri, mx[2] * 4, 5, ctx->comm, ctx->compute);
+  if (mx[3]) e |= ctx->nccl.AllGather(send + sj + sd + si, rf, mx[3] * 4, 5, ctx->comm, ctx->compute);
   if (ctx->nccl.GroupEnd) e |= ctx->nccl.GroupEnd();
   if (e != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(payload)");
   int rc;
@@ -891,9 +966,16 @@ int thb_segjuncs_allgather(thb_ctx* ctx)
       ctx->d_ins.release(); ctx->cap_ins = tot[2] + 1024; CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec)));
     }
     CU(cudaMemsetAsync(ctx->d_ins_count, 0, 8, ctx->compute));
-    ins_append_kernel<<<grid_for(mx[2] * W, 256), 256, 0, ctx->compute>>>((const InsRec*)ri, mx[2] * W, (InsRec*)ctx->d_ins.p, ctx->d_ins_count, ctx->cap_ins, ctx->d_err);
+    rec_append_kernel<InsRec><<<grid_for(mx[2] * W, 256), 256, 0, ctx->compute>>>((const InsRec*)ri, mx[2] * W, (InsRec*)ctx->d_ins.p, ctx->d_ins_count, ctx->cap_ins, ctx->d_err, 1u);
     ctx->own_launches++;
     ctx->h_ins_count = tot[2];
+  }
+  if (mx[3]) {                                                     // fusion records: every rank ends up with the union
+    if (tot[3] > ctx->cap_fus) { ctx->d_fus.release(); ctx->cap_fus = tot[3] + 1024; CU(ctx->d_fus.reserve(ctx->cap_fus * sizeof(FusRec))); }
+    CU(cudaMemsetAsync(ctx->d_fus_count, 0, 8, ctx->compute));
+    rec_append_kernel<FusRec><<<grid_for(mx[3] * W, 256), 256, 0, ctx->compute>>>((const FusRec*)rf, mx[3] * W, (FusRec*)ctx->d_fus.p, ctx->d_fus_count, ctx->cap_fus, ctx->d_err, 8u);
+    ctx->own_launches++;
+    ctx->h_fus_count = tot[3];
   }
   CU(cudaGetLastError());
   return THB_OK;
