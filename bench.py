@@ -406,7 +406,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
                             "indel_tasks": int(tm.n_indel_tasks), "rescue_tasks": int(tm.n_rescue_tasks),
                             "join_reads": int(sum(b.n_bundles for b in jbatches)), "joined_alignments": int(A["n_joined"]),
-                            "join_chains": int(A["jt"].n_chains), "join_closures": int(A["jt"].n_closures)}}
+                            "join_chains": int(A["jt"].n_chains), "join_closures": int(A["jt"].n_closures),
+                            "join_simple_chains": int(A["jt"].n_simple_chains), "join_abutting_chains": int(A["jt"].n_abutting_chains)}}
     ctx.close()
 
     if rank == 0:

@@ -23,6 +23,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static      /* blocks and warps run one after the other */
 #define THB_EMU 1
 
 struct uint2 { unsigned x, y; };

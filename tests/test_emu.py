@@ -42,8 +42,11 @@ def test_emu_known_answers(emu_lib, case):
 
 
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
-def test_emu_join_matches_reference_records(emu_lib):
+@pytest.mark.parametrize("chunk", [None, 96])
+def test_emu_join_matches_reference_records(emu_lib, monkeypatch, chunk):
     from test_gpu_join import joined_to_keys
+    if chunk:                                                       # many pipeline chunks per submit
+        monkeypatch.setenv("THB_JOIN_CHUNK_READS", str(chunk))
     wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(200_000, 80_000), n_pairs=1200, seed=511, indel_prob=0.4))
     P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
     ctx = capi.Context(0); ctx.ref_upload(wl.ref)

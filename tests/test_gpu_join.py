@@ -31,11 +31,14 @@ def joined_to_keys(joined, batch, P):
 
 
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
-@pytest.mark.parametrize("kw", [
-    dict(contig_lens=(300_000, 100_000), n_pairs=3000, seed=501),
-    dict(contig_lens=(300_000,), n_pairs=3000, seed=502, indel_prob=0.5),
+@pytest.mark.parametrize("kw,chunk", [
+    (dict(contig_lens=(300_000, 100_000), n_pairs=3000, seed=501), None),
+    (dict(contig_lens=(300_000,), n_pairs=3000, seed=502, indel_prob=0.5), None),
+    (dict(contig_lens=(300_000, 50_000), n_pairs=3000, seed=503, indel_prob=0.3), 512),      # 6 pipeline chunks per submit
 ])
-def test_join_capi_matches_reference_records(kw):
+def test_join_capi_matches_reference_records(kw, chunk, monkeypatch):
+    if chunk:
+        monkeypatch.setenv("THB_JOIN_CHUNK_READS", str(chunk))
     wl = synth.generate(synth.SynthConfig(keep_truth=True, **kw))
     P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
     ctx = capi.Context(0); ctx.ref_upload(wl.ref)

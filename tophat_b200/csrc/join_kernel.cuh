@@ -41,6 +41,8 @@ struct JoinSets {
 struct JoinBatchView {
   const thb_join_bundle* bundles; const uint16_t* seg_count; const uint64_t* reads; const thb_jhit* hits;
   uint32_t n_bundles, n_segs, read_words;
+  uint32_t bundle_base;               // added to the bundle index reported in thb_joined (chunked submission)
+  uint32_t hit_end;                   // index one past the last hit of the last bundle of this view
 };
 
 struct JoinOut {
@@ -486,7 +488,7 @@ chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueu
         else {
           uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
           const uint32_t m8 = mism & 0xffu;
-          dst[0] = make_uint4(bi, ref0, (uint32_t)left0, 1u | ((anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) << 8) | (m8 << 16) | (m8 << 24));
+          dst[0] = make_uint4(bi + bv.bundle_base, ref0, (uint32_t)left0, 1u | ((anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) << 8) | (m8 << 16) | (m8 << 24));
           dst[1] = make_uint4(smm & 0xffu, mkop(OP_MATCH, total), 0u, 0u);
         }
         ++n_emit;
@@ -701,12 +703,16 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
         else {
           uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
           const uint32_t hdr3 = (uint32_t)j.n_ops | ((uint32_t)j.flags << 8) | ((uint32_t)j.mismatches << 16) | ((uint32_t)j.edit_dist << 24);
-          dst[0] = make_uint4(j.bundle, j.ref_id, (uint32_t)j.left, hdr3);
+          dst[0] = make_uint4(j.bundle + bv.bundle_base, j.ref_id, (uint32_t)j.left, hdr3);
+          // whole 32-byte sectors only (a partly written sector costs a DRAM read to fill it): ops beyond n_ops are zero
           const int nop = j.n_ops;
-          uint32_t* dw = reinterpret_cast<uint32_t*>(dst + 1);
-          dw[0] = (uint32_t)j.splice_mms;
-          if (single) { for (int k = 0; k < nop; ++k) dw[1 + k] = j.ops[k]; }
-          else        { for (int k = 0; k < nop; ++k) dw[1 + k] = LC[k]; }
+          const uint32_t* src = single ? j.ops : LC;
+          auto op_at = [&](int k) -> uint32_t { return k < nop ? src[k] : 0u; };
+          dst[1] = make_uint4((uint32_t)j.splice_mms, op_at(0), op_at(1), op_at(2));
+          for (int q = 2; 4 * q - 5 < nop; q += 2) {
+            dst[q] = make_uint4(op_at(4 * q - 5), op_at(4 * q - 4), op_at(4 * q - 3), op_at(4 * q - 2));
+            dst[q + 1] = make_uint4(op_at(4 * q - 1), op_at(4 * q), op_at(4 * q + 1), op_at(4 * q + 2));
+          }
         }
         ++n_emit;
       }

@@ -39,6 +39,8 @@ struct DevBuf {
 };
 
 struct Staging { DevBuf bundles, seg_count, reads, hits, partner; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; };
+// join pipeline stage: input staging + the chunk's result buffer (its device->host copy overlaps the next chunk's kernels)
+struct JStage { DevBuf bundles, seg_count, reads, hits, out; uint64_t cap_out = 0; cudaEvent_t copied = nullptr, out_free = nullptr; bool out_busy = false; };
 
 // dynamically bound NCCL (the library is only needed for the multi-GPU exchange)
 struct NcclUid { char b[128]; };          // ncclUniqueId is passed BY VALUE to ncclCommInitRank
@@ -58,7 +60,7 @@ struct Nccl {
 
 struct thb_ctx {
   int device = 0;
-  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, d2h = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
   std::string err;
   // reference
@@ -98,7 +100,9 @@ struct thb_ctx {
   // long_spanning_reads join
   DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false;
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
-  JoinParams jp{}; bool join_begun = false; std::vector<thb_joined> h_joined; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
+  JoinParams jp{}; bool join_begun = false; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
+  JStage jstage[2];
+  thb_joined* h_joined = nullptr; uint64_t h_joined_cap = 0;      // page-locked result buffer, grow-only
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
 };
@@ -348,6 +352,8 @@ int thb_create(int device, thb_ctx** out)
   auto bail = [&](const char* what, cudaError_t ee) { int rc = fail(nullptr, THB_ECUDA, "%s: %s", what, cudaGetErrorString(ee)); delete ctx; return rc; };
   if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (auto& s : ctx->jstage) { cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.out_free, cudaEventDisableTiming); }
   cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b); cudaEventCreate(&ctx->ev_c); cudaEventCreate(&ctx->ev_d);
   for (auto& s : ctx->stage) { cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming); }
   if ((e = ctx->d_scalars.reserve(256)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -378,7 +384,9 @@ void thb_destroy(thb_ctx* ctx)
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
-  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
+  for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
+  if (ctx->h_joined) cudaFreeHost(ctx->h_joined);
+  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
   delete ctx;
 }
 
@@ -758,25 +766,26 @@ static int join_validate(thb_ctx* ctx, const thb_join_batch* b)
   if (b->n_segs < 1 || b->n_segs > (uint32_t)JMAXSEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, JMAXSEGS);
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4]", b->read_words);
   if (!b->bundles || !b->seg_count || !b->reads || (b->n_hits && !b->hits)) return fail(ctx, THB_EINVAL, "null batch array");
+  if (b->n_hits >= (1ull << 32)) return fail(ctx, THB_EUNSUPPORTED, "more than 2^32 segment hits in one batch (hit_begin is 32 bits)");
   return THB_OK;
 }
 
 // launches the chain join over device-resident arrays; results stay in ctx->j_out, *n receives their number
-static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsigned long long* n_res)
+static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsigned long long* n_res, DevBuf& out_buf, uint64_t& cap_out)
 {
-  ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+  cap_out = std::max<uint64_t>(cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
   S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets;
-  unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f;
+  unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f; unsigned long long qn_simple = 0, qn_abut = 0;
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
-    CU(ctx->j_out.reserve(ctx->j_cap_out * sizeof(thb_joined)));
+    CU(out_buf.reserve(cap_out * sizeof(thb_joined)));
     CU(ctx->j_chain.reserve(3 * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // general + simple + abutting queues
     CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
-    JoinOut o; o.rec = (thb_joined*)ctx->j_out.p; o.cap = ctx->j_cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
+    JoinOut o; o.rec = (thb_joined*)out_buf.p; o.cap = cap_out; o.count = ctx->d_qcounts; o.overflow = ctx->d_qovf; o.counters = ctx->d_counters + 4;
     ChainQueue q; q.tasks = (uint32_t*)ctx->j_chain.p; q.cap = ctx->j_cap_chain; q.stride = stride; q.count = ctx->d_qcounts + 1; q.overflow = ctx->d_qovf;
     q.simple_tasks = q.tasks + ctx->j_cap_chain * stride; q.simple_count = ctx->d_qcounts + 2;
     q.abut_tasks = q.tasks + 2 * ctx->j_cap_chain * stride; q.abut_count = ctx->d_qcounts + 3;
@@ -794,17 +803,18 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
     CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
-    n = qn[0];
-    if (!ovf && n <= ctx->j_cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
+    n = qn[0]; qn_simple = qn[2]; qn_abut = qn[3];
+    if (!ovf && n <= cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
       kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2; break;
     }
-    ctx->j_cap_out = std::max<uint64_t>(ctx->j_cap_out, 2 * n + 1024);
+    cap_out = std::max<uint64_t>(cap_out, 2 * n + 1024);
     ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, 2 * std::max(qn[1], std::max(qn[2], qn[3])) + 1024);
     if (attempt == 23) return fail(ctx, THB_ENOMEM, "joined-hit buffer still overflows");
   }
   thb_join_timing& t = ctx->jtiming;
   t.kernel_ms += kms; t.n_chains += cnt[0]; t.n_closures += cnt[1]; t.n_joined += cnt[2];
+  t.n_simple_chains += qn_simple; t.n_abutting_chains += qn_abut;
   // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 48 per segment hit, per closure
   // 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain, 128 per output record
   t.algorithmic_bytes += 56ull * bv.n_bundles + 48ull * n_hits + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
@@ -813,18 +823,31 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
   return THB_OK;
 }
 
+// page-locked host buffer for joined records: at least `need` records, the first `keep` preserved
+static int join_host_reserve(thb_ctx* ctx, uint64_t need, uint64_t keep)
+{
+  if (need <= ctx->h_joined_cap) return THB_OK;
+  const uint64_t ncap = std::max<uint64_t>(need + need / 4, 1u << 16);
+  thb_joined* nb = nullptr;
+  if (cudaHostAlloc((void**)&nb, ncap * sizeof(thb_joined), cudaHostAllocDefault) != cudaSuccess) return fail(ctx, THB_ENOMEM, "cannot page-lock %llu joined records", (unsigned long long)ncap);
+  if (keep) { CU(cudaStreamSynchronize(ctx->d2h)); memcpy(nb, ctx->h_joined, keep * sizeof(thb_joined)); }
+  if (ctx->h_joined) cudaFreeHost(ctx->h_joined);
+  ctx->h_joined = nb; ctx->h_joined_cap = ncap;
+  return THB_OK;
+}
+
 int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out)
 {
   if (!ctx || !out || !n_out) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   const unsigned long long n = ctx->j_last_n;
-  ctx->h_joined.resize(n);
+  int rc = join_host_reserve(ctx, n, 0); if (rc) return rc;
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
-  if (n) CU(cudaMemcpyAsync(ctx->h_joined.data(), ctx->j_out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->compute));
+  if (n) CU(cudaMemcpyAsync(ctx->h_joined, ctx->j_out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaEventRecord(ctx->ev_d, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   float d2h = 0.f; cudaEventElapsedTime(&d2h, ctx->ev_c, ctx->ev_d); ctx->jtiming.d2h_ms += d2h;
-  *out = ctx->h_joined.data(); *n_out = n;
+  *out = ctx->h_joined; *n_out = n;
   return THB_OK;
 }
 
@@ -836,13 +859,15 @@ int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* b, uint64_t* n_ou
   int rc = join_validate(ctx, b); if (rc) return rc;
   if (b->n_bundles == 0) return THB_OK;
   JoinBatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
-  bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
+  bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = 0; bv.hit_end = (uint32_t)b->n_hits;
   unsigned long long n = 0;
-  rc = join_run(ctx, bv, b->n_hits, &n); if (rc) return rc;
+  rc = join_run(ctx, bv, b->n_hits, &n, ctx->j_out, ctx->j_cap_out); if (rc) return rc;
   *n_out = n;
   return THB_OK;
 }
 
+// Host batch: a three-stream pipeline over chunks of reads.  While the kernels of chunk c run on the compute stream, the
+// copy stream uploads chunk c+1 and the d2h stream downloads the records of chunk c-1 into the page-locked result buffer.
 int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** out, uint64_t* n_out)
 {
   if (!ctx || !b || !out || !n_out) return THB_EINVAL;
@@ -851,20 +876,54 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
   int rc = join_validate(ctx, b); if (rc) return rc;
   if (b->n_bundles == 0) return THB_OK;
   const size_t rdw = (size_t)3 * b->read_words;
-  CU(ctx->j_bundles.reserve((size_t)b->n_bundles * sizeof(thb_join_bundle))); CU(ctx->j_segc.reserve((size_t)b->n_bundles * b->n_segs * 2));
-  CU(ctx->j_reads.reserve((size_t)b->n_bundles * rdw * 8)); CU(ctx->j_hits.reserve((size_t)(b->n_hits + 1) * sizeof(thb_jhit)));
+  uint32_t CH = 1u << 19;                                // reads per pipeline chunk (tuning knob: THB_JOIN_CHUNK_READS)
+  if (const char* e = getenv("THB_JOIN_CHUNK_READS")) { const long v = atol(e); if (v >= 32 && v <= (1l << 26)) CH = (uint32_t)v; }
+  const uint32_t nchunks = (b->n_bundles + CH - 1) / CH;
+  struct Range { uint32_t b0, nb; uint64_t h0, h1; };
+  auto range_of = [&](uint32_t c, Range* r) -> bool {
+    r->b0 = c * CH; const uint32_t b1 = std::min<uint32_t>(b->n_bundles, r->b0 + CH); r->nb = b1 - r->b0;
+    r->h0 = b->bundles[r->b0].hit_begin; r->h1 = (b1 < b->n_bundles) ? b->bundles[b1].hit_begin : b->n_hits;
+    return !(r->h1 < r->h0 || r->h1 > b->n_hits);
+  };
+  auto enqueue_copy = [&](uint32_t c) -> int {
+    JStage& s = ctx->jstage[c & 1]; Range r;
+    if (!range_of(c, &r)) return fail(ctx, THB_EINVAL, "hit_begin not monotonic near bundle %u", c * CH);
+    CU(s.bundles.reserve((size_t)r.nb * sizeof(thb_join_bundle))); CU(s.seg_count.reserve((size_t)r.nb * b->n_segs * 2));
+    CU(s.reads.reserve((size_t)r.nb * rdw * 8)); CU(s.hits.reserve((size_t)(r.h1 - r.h0 + 1) * sizeof(thb_jhit)));
+    CU(cudaMemcpyAsync(s.bundles.p, b->bundles + r.b0, (size_t)r.nb * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaMemcpyAsync(s.seg_count.p, b->seg_count + (size_t)r.b0 * b->n_segs, (size_t)r.nb * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaMemcpyAsync(s.reads.p, b->reads + (size_t)r.b0 * rdw, (size_t)r.nb * rdw * 8, cudaMemcpyHostToDevice, ctx->copy));
+    if (r.h1 > r.h0) CU(cudaMemcpyAsync(s.hits.p, b->hits + r.h0, (size_t)(r.h1 - r.h0) * sizeof(thb_jhit), cudaMemcpyHostToDevice, ctx->copy));
+    CU(cudaEventRecord(s.copied, ctx->copy));
+    return THB_OK;
+  };
+  rc = join_host_reserve(ctx, (uint64_t)b->n_bundles + b->n_bundles / 2, 0); if (rc) return rc;
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_bundles.p, b->bundles, (size_t)b->n_bundles * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_segc.p, b->seg_count, (size_t)b->n_bundles * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->j_reads.p, b->reads, (size_t)b->n_bundles * rdw * 8, cudaMemcpyHostToDevice, ctx->compute));
-  if (b->n_hits) CU(cudaMemcpyAsync(ctx->j_hits.p, b->hits, (size_t)b->n_hits * sizeof(thb_jhit), cudaMemcpyHostToDevice, ctx->compute));
+  rc = enqueue_copy(0); if (rc) return rc;
+  uint64_t total = 0;
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    JStage& s = ctx->jstage[c & 1]; Range r; range_of(c, &r);
+    CU(cudaStreamWaitEvent(ctx->compute, s.copied, 0));
+    // staging buffer (c+1)&1 was last read by the kernels of chunk c-1, which have completed (join_run synchronises)
+    if (c + 1 < nchunks) { rc = enqueue_copy(c + 1); if (rc) return rc; }
+    if (s.out_busy) CU(cudaStreamWaitEvent(ctx->compute, s.out_free, 0));      // records of chunk c-2 have left this buffer
+    JoinBatchView bv; bv.bundles = (const thb_join_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p; bv.reads = (const uint64_t*)s.reads.p;
+    bv.hits = (const thb_jhit*)s.hits.p - r.h0; bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = r.b0; bv.hit_end = (uint32_t)r.h1;
+    unsigned long long n = 0;
+    rc = join_run(ctx, bv, r.h1 - r.h0, &n, s.out, s.cap_out); if (rc) return rc;       // returns with the compute stream idle
+    rc = join_host_reserve(ctx, total + n, total); if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(ctx->h_joined + total, s.out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->d2h));
+    CU(cudaEventRecord(s.out_free, ctx->d2h)); s.out_busy = true;
+    total += n;
+  }
+  CU(cudaStreamSynchronize(ctx->d2h));
   CU(cudaEventRecord(ctx->ev_b, ctx->compute));
-  JoinBatchView bv; bv.bundles = (const thb_join_bundle*)ctx->j_bundles.p; bv.seg_count = (const uint16_t*)ctx->j_segc.p; bv.reads = (const uint64_t*)ctx->j_reads.p;
-  bv.hits = (const thb_jhit*)ctx->j_hits.p; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
-  unsigned long long n = 0;
-  rc = join_run(ctx, bv, b->n_hits, &n); if (rc) return rc;
-  float h2d = 0.f; cudaEventElapsedTime(&h2d, ctx->ev_a, ctx->ev_b); ctx->jtiming.h2d_ms += h2d;
-  return thb_join_fetch(ctx, out, n_out);
+  CU(cudaStreamSynchronize(ctx->compute));
+  float tot_ms = 0.f; cudaEventElapsedTime(&tot_ms, ctx->ev_a, ctx->ev_b);
+  ctx->jtiming.h2d_ms += tot_ms;          // wall time of the pipelined submit (copies, kernels and downloads overlap)
+  ctx->j_last_n = 0;                      // nothing left on the device for thb_join_fetch
+  *out = ctx->h_joined; *n_out = total;
+  return THB_OK;
 }
 
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out)
