@@ -20,6 +20,7 @@ def pytest_configure(config):
         import build_emu
         from tophat_b200 import capi
         capi._lib = capi.load_library(build_emu.build())
+        os.environ["THB_TEST_EMU"] = "1"
 
 
 @pytest.fixture(scope="session")

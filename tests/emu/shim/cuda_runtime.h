@@ -188,3 +188,5 @@ static inline unsigned __ballot_sync(unsigned mask, int pred)
   unsigned r = 0; for (int l = 0; l < 32; ++l) if (emu::g_warp.buf[p][l]) r |= 1u << l;
   return r;
 }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }

@@ -108,3 +108,15 @@ def manual_workload(contigs, reads):
     H = np.array(hits, dtype=synth.HIT_DTYPE) if hits else np.zeros(0, dtype=synth.HIT_DTYPE)
     PH = np.array(partner, dtype=synth.HIT_DTYPE) if partner else np.zeros(0, dtype=synth.HIT_DTYPE)
     return ref, synth.PackedBatch(nseg, rw, bundles, np.ascontiguousarray(seg_count), np.ascontiguousarray(rd), H, PH, 0)
+
+
+def our_bin(prog):
+    """Path of our drop-in executable; under `pytest --emu` (development aid) the one linked against the host-emulated library."""
+    if os.environ.get("THB_TEST_EMU") == "1":
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        return build_emu.build_cli(prog)
+    from tophat_b200 import build
+    build.build_all()
+    return os.path.join(build.BIN_DIR, prog)

@@ -7,6 +7,7 @@ import tempfile
 
 import pytest
 
+import helpers
 from tophat_b200 import build, synth
 from oracle import pyoracle
 
@@ -30,7 +31,7 @@ def test_host_binary_builds():
     (dict(contig_lens=(250_000,), n_pairs=1500, seed=406, read_len=150, indel_prob=0.3, n_rate=0.004), True),
 ])
 def test_cli_matches_reference_binary(kw, spliced):
-    build.build_all()
+    OUR_BIN = helpers.our_bin("long_spanning_reads")
     with tempfile.TemporaryDirectory() as td:
         wl = synth.generate(synth.SynthConfig(keep_truth=True, **kw))
         files = synth.write_pipeline_files(wl, td)

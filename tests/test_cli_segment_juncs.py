@@ -48,7 +48,7 @@ def test_usage_and_empty_segment_list_exit_codes():
      ["--fusion-search", "--fusion-ignore-chromosomes", "chrS2", "--fusion-do-not-resolve-conflicts"]),
 ])
 def test_cli_matches_reference_binary(kw, paired, extra):
-    build.build_all()
+    OUR_BIN = helpers.our_bin("segment_juncs")
     with tempfile.TemporaryDirectory() as td:
         wl, files, bams, nseg = _prepare(td, synth.SynthConfig(**kw))
         opts = pyoracle.tophat_common_opts(50, 20, extra)
@@ -66,7 +66,7 @@ def test_cli_matches_reference_binary(kw, paired, extra):
 @pytest.mark.gpu
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
 def test_cli_no_hits_exit_zero():
-    build.build_all()
+    OUR_BIN = helpers.our_bin("segment_juncs")
     with tempfile.TemporaryDirectory() as td:
         wl, files, bams, nseg = _prepare(td, synth.SynthConfig(contig_lens=(100_000,), n_pairs=200, seed=304))
         outs = [os.path.join(td, "o.%s" % k) for k in ("j", "i", "d", "f")]

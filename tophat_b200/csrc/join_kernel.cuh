@@ -380,6 +380,8 @@ struct ChainQueue {
 
 // K-J1: join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610): enumerate the compatible segment-hit chains of one
 // read in the reference's DFS order, with its budget of 10,000 complete chains per first-segment hit.
+// (Measured alternatives, both slower on B200 than this per-thread walk at 2.5 ms / 10.5 M reads: the walk as a warp lock-step
+// state machine, 3.1 ms; the hits of the warp's 32 reads staged in shared memory first, 3.6 ms -- profiles/README.md.)
 __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const ChainQueue& q, uint32_t bi, unsigned& n_leaves)
 {
   const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
@@ -490,6 +492,100 @@ chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueu
           const uint32_t m8 = mism & 0xffu;
           dst[0] = make_uint4(bi + bv.bundle_base, ref0, (uint32_t)left0, 1u | ((anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) << 8) | (m8 << 16) | (m8 << 24));
           dst[1] = make_uint4(smm & 0xffu, mkop(OP_MATCH, total), 0u, 0u);
+        }
+        ++n_emit;
+      }
+    }
+    __syncwarp();
+  }
+  for (int k = 16; k > 0; k >>= 1) n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k);
+  if (lane == 0 && n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit);
+}
+
+// K-J2b: chains whose hits all abut exactly (gap 0 between neighbours) but carry multi-op CIGARs -- reads crossing a
+// junction through a hit against the junction index.  merge_chain never searches a closure for them: every hit is
+// "finalised" in turn (1888-1945: mismatch sums, splice-strand agreement, CIGAR appended with equal neighbouring ops fused),
+// after the pair checks of 930-949.  That is one streaming pass over the chain's hit records, so these chains (the bulk of
+// the spliced reads) get a kernel without the closure machinery of K-J2: no working copies of the hits, no phases.
+__global__ void __launch_bounds__(128)
+chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, JoinOut o)
+{
+  unsigned n_emit = 0;
+  unsigned long long nq = *q.abut_count; if (nq > q.cap) nq = q.cap;
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long ti = base + lane;
+    bool ok = ti < nq;
+    uint32_t bi = 0, ref0 = 0; int left0 = 0, nLC = 0, num_mm = 0, num_smm = 0; bool anti = false, saw_as = false, saw_s = false;
+    uint32_t LC[JMAXOPS];
+    if (ok) {
+      const uint32_t* __restrict__ t = q.abut_tasks + ti * q.stride;
+      bi = t[0];
+      const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
+      const int read_len = (int)(hdr.z & 0xffffu); const int n = (int)((hdr.z >> 16) & 0xffu);
+      uint64_t R[12];
+      { const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
+        #pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+          #pragma unroll
+          for (int w = 0; w < 4; ++w) R[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull; }
+      anti = ((__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE) != 0;   // chain orientation (2117-2121)
+      bool prev_spliced = false, prev_asplice = false, prev_last_match = false; uint32_t prev_ref = 0;
+      for (int e = 0; e < n && ok; ++e) {
+        const int sg = anti ? n - 1 - e : e;
+        const uint4* p = reinterpret_cast<const uint4*>(bv.hits + t[1 + sg]);
+        const uint4 a = __ldg(p);
+        int nops = (int)(a.z & 0xffu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
+        const uint32_t fl = (a.z >> 8) & 0xffu; const bool asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
+        uint32_t ops[THB_JHIT_MAX_OPS]; ops[0] = a.w;
+        if (nops > 1) { const uint4 b = __ldg(p + 1); ops[1] = b.x; ops[2] = b.y; ops[3] = b.z; ops[4] = b.w; }
+        if (nops > 5) { const uint4 c = __ldg(p + 2); ops[5] = c.x; ops[6] = c.y; ops[7] = c.z; ops[8] = c.w; }
+        if (nops < 1) { ok = false; break; }
+        bool spliced = false;
+        for (int k = 0; k < nops; ++k) spliced = spliced || opc(ops[k]) == OP_REF_SKIP;
+        if (e == 0) { ref0 = a.x; left0 = (int)a.y; }
+        else {
+          if (!(prev_last_match || opc(ops[0]) == OP_MATCH)) { ok = false; break; }               // 930-934
+          if (prev_spliced && spliced && prev_asplice != asplice) { ok = false; break; }            // 942-949
+          if (a.x != prev_ref) { ok = false; break; }
+        }
+        // finalise this hit (1888-1945)
+        num_mm += (int)((a.z >> 16) & 0xffu); num_smm += (int)(a.z >> 24);
+        if (spliced) { if (asplice) { if (saw_s) { ok = false; break; } saw_as = true; } else { if (saw_as) { ok = false; break; } saw_s = true; } }
+        int b0 = 0;
+        if (nLC > 0 && opc(LC[nLC - 1]) == opc(ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(ops[0])); b0 = 1; }
+        for (; b0 < nops; ++b0) if (!cig_push(LC, nLC, ops[b0])) { ok = false; break; }
+        prev_spliced = spliced; prev_asplice = asplice; prev_last_match = opc(ops[nops - 1]) == OP_MATCH; prev_ref = a.x;
+      }
+      if (ok && nLC == 0) ok = false;
+      if (ok) {
+        if (anti) { uint64_t F[12];
+          #pragma unroll
+          for (int k = 0; k < 12; ++k) F[k] = R[k];
+          revcomp_read(F, read_len, R); }
+        // new_read_len == old_read_length (2023): fusing equal neighbours preserves the lengths
+        ok = editdist_consistent(ref, ref0, left0, LC, nLC, R, 4, (uint8_t)num_mm) && valid_cigar(P, LC, nLC);
+      }
+    }
+    const unsigned em = __ballot_sync(0xffffffffu, ok);
+    if (em) {
+      unsigned long long slot0 = 0;
+      if (lane == (unsigned)(__ffs((int)em) - 1)) slot0 = atomicAdd(o.count, (unsigned long long)__popc(em));
+      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs((int)em) - 1);
+      if (ok) {
+        const unsigned long long slot = slot0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
+        if (slot >= o.cap) atomicOr(o.overflow, 1u);
+        else {
+          uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
+          const uint32_t mism = (uint32_t)num_mm & 0xffu, ed = ((uint32_t)num_mm + (uint32_t)cig_gap_length(LC, nLC)) & 0xffu;
+          const uint32_t flags = (anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) | (saw_as ? (uint32_t)THB_JHIT_ANTISENSE_SPLICE : 0u);
+          dst[0] = make_uint4(bi + bv.bundle_base, ref0, (uint32_t)left0, (uint32_t)nLC | (flags << 8) | (mism << 16) | (ed << 24));
+          auto op_at = [&](int k) -> uint32_t { return k < nLC ? LC[k] : 0u; };
+          dst[1] = make_uint4((uint32_t)num_smm & 0xffu, op_at(0), op_at(1), op_at(2));
+          for (int qd = 2; 4 * qd - 5 < nLC; qd += 2) {
+            dst[qd] = make_uint4(op_at(4 * qd - 5), op_at(4 * qd - 4), op_at(4 * qd - 3), op_at(4 * qd - 2));
+            dst[qd + 1] = make_uint4(op_at(4 * qd - 1), op_at(4 * qd), op_at(4 * qd + 1), op_at(4 * qd + 2));
+          }
         }
         ++n_emit;
       }

@@ -793,7 +793,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
     chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
     CU(cudaEventRecord(ctx->kev[1], ctx->compute));
     chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    chain_merge_kernel<false><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    chain_merge_abut_kernel<<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
     chain_merge_kernel<true><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
