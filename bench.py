@@ -282,7 +282,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
     log("[bench] rank %d: join batches %d + %d reads, %d segment hits (%.1f s)" % (
         rank, jbatches[0].n_bundles, jbatches[1].n_bundles, sum(int(b.hits.shape[0]) for b in jbatches), time.time() - t0))
-    j_fields = ("bundles", "seg_count", "reads", "hits")
+    j_fields = ("bundles", "seg_count", "reads", "hits", "ops_ext")
     j_keep, j_dev, j_host = stage(jbatches, j_fields, capi.join_batch_c)
     h2d_bytes = sum(b.nbytes() for b in batches) + sum(b.nbytes() for b in jbatches) + int(jsets[0].nbytes + jsets[1].nbytes)
 
@@ -359,15 +359,15 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         #   hit         : 40 (read) per bundle + 16 per segment hit
         #   window_scan : 32 (descriptor) + 64 (two reference sectors) per window + 16 per emitted junction record
         #   rescue      : 32 + 128 per mate-anchor task;  indel: 32 + 64 per task + 16 per record
-        #   chain_enum  : 16 (header) per read + 48 per segment hit
-        #   chain_merge : 40 (read) per read + 128 per closure + 96 per merged chain + 128 per output record
+        #   chain_enum  : 16 (header) per read + 16 per segment hit (the 16-byte wire record)
+        #   chain_merge : 40 (read) per read + 32 per multi-op hit + 128 per closure + 96 per merged chain + 128 per output record
         n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
         n_hh = sum(int(b.hits.shape[0]) for b in batches)
         steps = args.steps
         kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh,
                   "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
                   "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions)),
-                  "chain_enum": 16 * sum(b.n_bundles for b in jbatches) + 48 * sum(int(b.hits.shape[0]) for b in jbatches)}
+                  "chain_enum": 16 * sum(b.n_bundles for b in jbatches) + 16 * sum(int(b.hits.shape[0]) for b in jbatches)}
         kbytes["chain_merge"] = A["join_alg"] / steps - kbytes["chain_enum"]
         kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps; kms["chain_merge"] = A["merge_ms"] / steps
         klaunch = {k: A["scan_launches"] for k in KERNELS}

@@ -226,12 +226,31 @@ int thb_segjuncs_allgather(thb_ctx* ctx);
 #define THB_JHIT_ANTISENSE_SPLICE 0x04    /* antisense_splice() (with THB_HIT_ANTISENSE / THB_HIT_END)        */
 /* CIGAR ops are packed as length << 4 | CigarOpCode (bwt_map.h:36-55: MATCH 1, INS 3, DEL 5, REF_SKIP 11,
  * SOFT_CLIP 13, PAD 15; lower-case fusion-side codes never occur without --fusion-search).                    */
-typedef struct thb_jhit {          /* BowtieHit of one segment (BAMHitFactory / SplicedBAMHitFactory)           */
+#define THB_JHIT_ONE_MATCH  0x08   /* the CIGAR is a single MATCH of right-left bases: no thb_jops record        */
+/* Wire form of one segment's BowtieHit (BAMHitFactory / SplicedBAMHitFactory).  Nearly every hit is an un-gapped match,
+ * so the record the kernels stream is 16 bytes: position, right() and the small fields; the CIGAR of the other hits
+ * (against the junction index: M N M, indels ...) sits in a side array, one thb_jops per such hit, in hit order.       */
+typedef struct thb_jhit {
+  uint32_t ref_id;
+  int32_t  left;
+  int32_t  right;                  /* right() = left + bases of MATCH / DEL / REF_SKIP ops                       */
+  uint8_t  flags_nops;             /* THB_HIT_ANTISENSE | THB_HIT_END | THB_JHIT_ANTISENSE_SPLICE | THB_JHIT_ONE_MATCH
+                                      in the low nibble, number of CIGAR ops (1..9) in the high nibble           */
+  uint8_t  ops_index;              /* without THB_JHIT_ONE_MATCH: ops_ext[bundle.ops_begin + ops_index]          */
+  uint8_t  mismatches, splice_mms;
+} thb_jhit;                        /* 16 bytes */
+typedef struct thb_jops { uint32_t ops[12]; } thb_jops;    /* 48 bytes; ops[0 .. n_ops) valid, the rest zero     */
+
+/* Unpacked form (one record per hit, CIGAR inline) and the host helper that converts the hits of ONE read -- all its
+ * segments, in batch order -- to the wire form.  Returns the number of thb_jops records written (<= n), or
+ * THB_EUNSUPPORTED when the read has more than 256 hits with a multi-op CIGAR.                                    */
+typedef struct thb_jhit_full {
   uint32_t ref_id;
   int32_t  left;
   uint8_t  n_ops, flags, mismatches, splice_mms;
   uint32_t ops[THB_JHIT_MAX_OPS];
-} thb_jhit;                        /* 48 bytes */
+} thb_jhit_full;                   /* 48 bytes */
+int thb_join_pack_hits(const thb_jhit_full* hits, uint32_t n, thb_jhit* heads, thb_jops* ops_ext);
 
 typedef struct thb_join_bundle {
   uint32_t read_id;
@@ -239,7 +258,7 @@ typedef struct thb_join_bundle {
   uint16_t read_len;
   uint8_t  n_segs;                 /* segments of THIS read (all non-empty)                                    */
   uint8_t  reserved;
-  uint32_t reserved2;
+  uint32_t ops_begin;              /* first thb_jops record of this read's hits in ops_ext[]                   */
 } thb_join_bundle;                 /* 16 bytes */
 
 typedef struct thb_join_batch {
@@ -252,6 +271,8 @@ typedef struct thb_join_batch {
   const uint64_t*        reads;        /* [n_bundles * 3 * read_words], as in thb_segjuncs_batch                */
   uint64_t               n_hits;
   const thb_jhit*        hits;
+  uint64_t               n_ops_ext;
+  const thb_jops*        ops_ext;      /* [n_ops_ext] CIGARs of the hits without THB_JHIT_ONE_MATCH, in hit order     */
 } thb_join_batch;
 
 typedef struct thb_joined {        /* the BowtieHit merge_chain returns                                         */

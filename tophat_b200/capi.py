@@ -64,7 +64,8 @@ class BatchC(C.Structure):
 
 class JoinBatchC(C.Structure):
     _fields_ = [("n_bundles", C.c_uint32), ("n_segs", C.c_uint32), ("read_words", C.c_uint32), ("reserved", C.c_uint32),
-                ("bundles", C.c_void_p), ("seg_count", C.c_void_p), ("reads", C.c_void_p), ("n_hits", C.c_uint64), ("hits", C.c_void_p)]
+                ("bundles", C.c_void_p), ("seg_count", C.c_void_p), ("reads", C.c_void_p), ("n_hits", C.c_uint64), ("hits", C.c_void_p),
+                ("n_ops_ext", C.c_uint64), ("ops_ext", C.c_void_p)]
 
 
 class JoinTimingC(C.Structure):
@@ -78,6 +79,7 @@ def join_batch_c(b: "synth.PackedJoinBatch") -> JoinBatchC:
     s.n_bundles = b.n_bundles; s.n_segs = b.n_segs; s.read_words = b.read_words
     s.bundles = b.bundles.ctypes.data; s.seg_count = b.seg_count.ctypes.data; s.reads = b.reads.ctypes.data
     s.n_hits = b.hits.shape[0]; s.hits = b.hits.ctypes.data
+    s.n_ops_ext = b.ops_ext.shape[0]; s.ops_ext = b.ops_ext.ctypes.data
     return s
 
 
@@ -178,6 +180,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_pack_bases.restype = None
     lib.thb_pack_read.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.thb_pack_read.restype = None
+    lib.thb_join_pack_hits.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.thb_join_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.thb_join_submit.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_join_submit_device.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_uint64)]

@@ -167,14 +167,15 @@ int main(int argc, char** argv)
   const size_t nseg = seg_files.size();
 
   struct Pending { uint32_t id; FullRead read; };
-  std::vector<thb_join_bundle> bundles; std::vector<uint16_t> segc; std::vector<uint64_t> rplanes; std::vector<thb_jhit> hits; std::vector<Pending> pend;
+  std::vector<thb_join_bundle> bundles; std::vector<uint16_t> segc; std::vector<uint64_t> rplanes; std::vector<thb_jhit> hits; std::vector<thb_jops> ops_ext; std::vector<Pending> pend;
+  std::vector<thb_jhit_full> read_hits;
   uint64_t n_reads = 0, n_out = 0;
   auto flush = [&]() {
     if (bundles.empty()) return;
     // reads of one batch share read_words = 4 (reads up to 255 bases)
     thb_join_batch jb; memset(&jb, 0, sizeof jb);
     jb.n_bundles = (uint32_t)bundles.size(); jb.n_segs = (uint32_t)nseg; jb.read_words = 4; jb.bundles = bundles.data(); jb.seg_count = segc.data();
-    jb.reads = rplanes.data(); jb.n_hits = hits.size(); jb.hits = hits.data();
+    jb.reads = rplanes.data(); jb.n_hits = hits.size(); jb.hits = hits.data(); jb.n_ops_ext = ops_ext.size(); jb.ops_ext = ops_ext.data();
     const thb_joined* out = nullptr; uint64_t no = 0;
     if (thb_join_submit(ctx, &jb, &out, &no) != THB_OK) die("Error: thb_join_submit: %s", thb_last_error(ctx));
     std::vector<std::vector<Joined>> per(bundles.size());
@@ -238,12 +239,12 @@ int main(int argc, char** argv)
         ++n_out;
       }
     }
-    bundles.clear(); segc.clear(); rplanes.clear(); hits.clear(); pend.clear();
+    bundles.clear(); segc.clear(); rplanes.clear(); hits.clear(); ops_ext.clear(); pend.clear();
   };
 
   // JoinSegmentsWorker::operator() (2671-2845)
   const size_t BATCH = 1u << 20;
-  std::vector<std::vector<thb_jhit>> seg_hits(nseg);
+  std::vector<std::vector<thb_jhit_full>> seg_hits(nseg);
   for (;;) {
     const uint32_t cid = contig[0]->next_group_id();
     const uint32_t sid = spliced.empty() ? 0 : spliced[0]->next_group_id();
@@ -269,11 +270,20 @@ int main(int argc, char** argv)
     if (rd->seq.size() > 255) die("Error: reads longer than 255 bases are not supported");
     thb_join_bundle bu; memset(&bu, 0, sizeof bu);
     bu.read_id = id; bu.hit_begin = (uint32_t)hits.size(); bu.read_len = (uint16_t)rd->seq.size(); bu.n_segs = (uint8_t)(last_non_empty + 1);
+    bu.ops_begin = (uint32_t)ops_ext.size();
+    read_hits.clear();
     for (size_t s = 0; s < nseg; ++s) {
       const size_t c = (int)s <= last_non_empty ? seg_hits[s].size() : 0;
       if (c > 65535) die("Error: more than 65535 hits for one segment of one read");
       segc.push_back((uint16_t)c);
-      if ((int)s <= last_non_empty) hits.insert(hits.end(), seg_hits[s].begin(), seg_hits[s].end());
+      if ((int)s <= last_non_empty) read_hits.insert(read_hits.end(), seg_hits[s].begin(), seg_hits[s].end());
+    }
+    {                                   // wire form: 16-byte records + the CIGARs of the multi-op hits
+      const size_t h0 = hits.size(), e0 = ops_ext.size();
+      hits.resize(h0 + read_hits.size()); ops_ext.resize(e0 + read_hits.size());
+      const int ne = thb_join_pack_hits(read_hits.data(), (uint32_t)read_hits.size(), hits.data() + h0, ops_ext.data() + e0);
+      if (ne < 0) die("Error: a read has more than 256 segment hits with a gapped / spliced CIGAR (outside the GPU path)");
+      ops_ext.resize(e0 + (size_t)ne);
     }
     ReadRec rr; pack_read_ascii(rd->seq.data(), (uint32_t)rd->seq.size(), rr);
     rplanes.insert(rplanes.end(), rr.planes, rr.planes + 12);

@@ -64,10 +64,10 @@ int main(int argc, char** argv)
   if (mode == "jhits" && argc == 5) {
     RefTable rt; if (!rt.load_sam_header(argv[3], &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     std::mutex m; JoinHitStream hs(argv[2], rt, m, atoi(argv[4]) != 0, 500000, 8);
-    std::vector<thb_jhit> v;
+    std::vector<thb_jhit_full> v;
     for (uint32_t id; (id = hs.next_group_id()) != 0;) {
       v.clear(); hs.next_group(v);
-      for (const thb_jhit& h : v) {
+      for (const thb_jhit_full& h : v) {
         printf("%u %s %d %u %u %u", id, rt.name(h.ref_id).c_str(), h.left, h.flags, h.mismatches, h.splice_mms);
         for (int k = 0; k < h.n_ops; ++k) printf(" %u:%u", h.ops[k] >> 4, h.ops[k] & 15);
         printf("\n");

@@ -225,7 +225,7 @@ bool JoinHitStream::ensure()
   return true;
 }
 uint32_t JoinHitStream::next_group_id() { while (ensure()) { if (cur_[pos_].id != 0) return cur_[pos_].id; ++pos_; } return 0; }
-void JoinHitStream::next_group(std::vector<thb_jhit>& out)
+void JoinHitStream::next_group(std::vector<thb_jhit_full>& out)
 { const uint32_t id = next_group_id(); if (!id) return; while (ensure() && cur_[pos_].id == id) { out.push_back(cur_[pos_].h); ++pos_; } }
 void JoinHitStream::skip_group()
 { const uint32_t id = next_group_id(); if (!id) return; while (ensure() && cur_[pos_].id == id) ++pos_; }

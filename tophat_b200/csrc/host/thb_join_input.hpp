@@ -1,12 +1,12 @@
 // thb_join_input.hpp -- hit streams of long_spanning_reads: BAMHitFactory (contiguous segment hits) and
 // SplicedBAMHitFactory (hits against juncs_db contigs mapped back to genomic coordinates), each producing the
-// packed thb_jhit record of the C ABI, plus the full read records (name, bases, qualities) the BAM writer needs.
+// packed thb_jhit_full record of the C ABI, plus the full read records (name, bases, qualities) the BAM writer needs.
 #pragma once
 #include "thb_input.hpp"
 
 namespace thbhost {
 
-struct JHitRec { uint32_t id; thb_jhit h; };
+struct JHitRec { uint32_t id; thb_jhit_full h; };
 
 class JoinHitStream {
  public:
@@ -16,7 +16,7 @@ class JoinHitStream {
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
   uint32_t next_group_id();
-  void next_group(std::vector<thb_jhit>& out);
+  void next_group(std::vector<thb_jhit_full>& out);
   void skip_group();
   uint64_t dropped_long_cigars() const { return dropped_; }
  private:

@@ -40,6 +40,7 @@ struct JoinSets {
 
 struct JoinBatchView {
   const thb_join_bundle* bundles; const uint16_t* seg_count; const uint64_t* reads; const thb_jhit* hits;
+  const thb_jops* ops_ext;            // CIGARs of the hits without THB_JHIT_ONE_MATCH; indexed bundle.ops_begin + hit.ops_index
   uint32_t n_bundles, n_segs, read_words;
   uint32_t bundle_base;               // added to the bundle index reported in thb_joined (chunked submission)
   uint32_t hit_end;                   // index one past the last hit of the last bundle of this view
@@ -128,49 +129,32 @@ __device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t 
   return lo;
 }
 
-__device__ __forceinline__ void load_whit(WHit& w, const thb_jhit* h, int seq_pos, int seq_len)
+// head word 3 of a thb_jhit: flags (low nibble) | n_ops << 4 | ops_index << 8 | mismatches << 16 | splice_mms << 24
+__device__ __forceinline__ void load_whit(WHit& w, const JoinBatchView& bv, uint32_t hit, uint32_t ops_begin, int seq_pos, int seq_len)
 {
-  // most hits carry one op: the first 16 bytes hold everything but ops[1..8]
-  const uint4* p = reinterpret_cast<const uint4*>(h);
-  const uint4 a = __ldg(p);
-  w.ref = a.x; w.left = (int)a.y;
-  w.n = (int)(a.z & 0xffu); const uint32_t fl = (a.z >> 8) & 0xffu; w.mism = (uint8_t)((a.z >> 16) & 0xffu); w.smm = (uint8_t)(a.z >> 24);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(bv.hits + hit));
+  w.ref = a.x; w.left = (int)a.y; w.right = (int)a.z;
+  const uint32_t fl = a.w & 0xfu; w.mism = (uint8_t)((a.w >> 16) & 0xffu); w.smm = (uint8_t)(a.w >> 24);
   w.anti = (fl & THB_HIT_ANTISENSE) != 0; w.asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
-  if (w.n > THB_JHIT_MAX_OPS) w.n = THB_JHIT_MAX_OPS;
-  w.ops[0] = a.w;
-  if (w.n > 1) { const uint4 b = __ldg(p + 1); w.ops[1] = b.x; w.ops[2] = b.y; w.ops[3] = b.z; w.ops[4] = b.w; }
-  if (w.n > 5) { const uint4 c = __ldg(p + 2); w.ops[5] = c.x; w.ops[6] = c.y; w.ops[7] = c.z; w.ops[8] = c.w; }
   w.seq_pos = seq_pos; w.seq_len = seq_len;
-  if (w.n == 1) { const int c = opc(a.w); const int l = (int)opl(a.w);
-    w.right = w.left + ((c == OP_MATCH || c == OP_REF_SKIP || c == OP_DEL) ? l : 0);
-    w.rlen = (c == OP_MATCH || c == OP_INS || c == OP_SOFT_CLIP) ? l : 0; w.spliced = c == OP_REF_SKIP; }
-  else { w.right = cig_right(w.left, w.ops, w.n); w.rlen = cig_read_len(w.ops, w.n); w.spliced = cig_spliced(w.ops, w.n); }
+  if (fl & THB_JHIT_ONE_MATCH) {                                  // the common case: everything is in the 16-byte record
+    w.n = 1; w.ops[0] = mkop(OP_MATCH, (uint32_t)(a.z - a.y)); w.rlen = (int)(a.z - a.y); w.spliced = false;
+  } else {
+    w.n = (int)((a.w >> 4) & 0xfu); if (w.n > THB_JHIT_MAX_OPS) w.n = THB_JHIT_MAX_OPS;
+    const uint4* p = reinterpret_cast<const uint4*>(bv.ops_ext + ops_begin + ((a.w >> 8) & 0xffu));
+    const uint4 b = __ldg(p); w.ops[0] = b.x; w.ops[1] = b.y; w.ops[2] = b.z; w.ops[3] = b.w;
+    if (w.n > 4) { const uint4 c = __ldg(p + 1); w.ops[4] = c.x; w.ops[5] = c.y; w.ops[6] = c.z; w.ops[7] = c.w; }
+    if (w.n > 8) { w.ops[8] = __ldg(reinterpret_cast<const uint32_t*>(p + 2)); }
+    w.rlen = cig_read_len(w.ops, w.n); w.spliced = cig_spliced(w.ops, w.n);
+  }
 }
 
-// the few fields of a segment hit the DFS needs
+// the few fields of a segment hit the DFS needs: one 16-byte load
 struct LiteHit { uint32_t ref; int left, right; bool anti; bool one_m; };   // one_m: the CIGAR is a single match op
 __device__ __forceinline__ LiteHit load_lite(const thb_jhit* h)
 {
-  const uint4* p = reinterpret_cast<const uint4*>(h);
-  const uint4 a = __ldg(p);
-  int n = (int)(a.z & 0xffu); if (n > THB_JHIT_MAX_OPS) n = THB_JHIT_MAX_OPS;
-  LiteHit l; l.ref = a.x; l.left = (int)a.y; l.anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0;
-  l.one_m = n == 1 && opc(a.w) == OP_MATCH;
-  int r = l.left;
-  { const int cc = opc(a.w); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(a.w); }
-  if (n > 1) {
-    const uint4 b = __ldg(p + 1);
-    const uint32_t o1[4] = { b.x, b.y, b.z, b.w };
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) if (1 + i < n) { const int cc = opc(o1[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(o1[i]); }
-    if (n > 5) {
-      const uint4 c = __ldg(p + 2);
-      const uint32_t o2[4] = { c.x, c.y, c.z, c.w };
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) if (5 + i < n) { const int cc = opc(o2[i]); if (cc == OP_MATCH || cc == OP_REF_SKIP || cc == OP_DEL) r += (int)opl(o2[i]); }
-    }
-  }
-  l.right = r;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(h));
+  LiteHit l; l.ref = a.x; l.left = (int)a.y; l.right = (int)a.z; l.anti = (a.w & THB_HIT_ANTISENSE) != 0; l.one_m = (a.w & THB_JHIT_ONE_MATCH) != 0;
   return l;
 }
 
@@ -466,9 +450,9 @@ chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueu
       int minleft = 0x7fffffff;
       for (int s = 0; s < n; ++s) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(bv.hits + t[1 + s]));
-        if (s == 0) { ref0 = a.x; anti = ((a.z >> 8) & THB_HIT_ANTISENSE) != 0; }
+        if (s == 0) { ref0 = a.x; anti = (a.w & THB_HIT_ANTISENSE) != 0; }
         minleft = min(minleft, (int)a.y);                     // chain[0] is the leftmost hit in either orientation
-        mism += (a.z >> 16) & 0xffu; smm += a.z >> 24; total += opl(a.w);
+        mism += (a.w >> 16) & 0xffu; smm += a.w >> 24; total += a.z - a.y;
       }
       left0 = minleft;
       if (anti) { uint64_t F[12];
@@ -529,17 +513,20 @@ chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue 
         for (int pl = 0; pl < 3; ++pl)
           #pragma unroll
           for (int w = 0; w < 4; ++w) R[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull; }
-      anti = ((__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE) != 0;   // chain orientation (2117-2121)
+      anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 3) & THB_HIT_ANTISENSE) != 0;   // chain orientation (2117-2121)
       bool prev_spliced = false, prev_asplice = false, prev_last_match = false; uint32_t prev_ref = 0;
       for (int e = 0; e < n && ok; ++e) {
         const int sg = anti ? n - 1 - e : e;
-        const uint4* p = reinterpret_cast<const uint4*>(bv.hits + t[1 + sg]);
-        const uint4 a = __ldg(p);
-        int nops = (int)(a.z & 0xffu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
-        const uint32_t fl = (a.z >> 8) & 0xffu; const bool asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
-        uint32_t ops[THB_JHIT_MAX_OPS]; ops[0] = a.w;
-        if (nops > 1) { const uint4 b = __ldg(p + 1); ops[1] = b.x; ops[2] = b.y; ops[3] = b.z; ops[4] = b.w; }
-        if (nops > 5) { const uint4 c = __ldg(p + 2); ops[5] = c.x; ops[6] = c.y; ops[7] = c.z; ops[8] = c.w; }
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bv.hits + t[1 + sg]));
+        const uint32_t fl = a.w & 0xfu; const bool asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
+        int nops = 1; uint32_t ops[THB_JHIT_MAX_OPS]; ops[0] = mkop(OP_MATCH, (uint32_t)(a.z - a.y));
+        if (!(fl & THB_JHIT_ONE_MATCH)) {
+          nops = (int)((a.w >> 4) & 0xfu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
+          const uint4* p = reinterpret_cast<const uint4*>(bv.ops_ext + hdr.w + ((a.w >> 8) & 0xffu));
+          const uint4 b = __ldg(p); ops[0] = b.x; ops[1] = b.y; ops[2] = b.z; ops[3] = b.w;
+          if (nops > 4) { const uint4 c = __ldg(p + 1); ops[4] = c.x; ops[5] = c.y; ops[6] = c.z; ops[7] = c.w; }
+          if (nops > 8) ops[8] = __ldg(reinterpret_cast<const uint32_t*>(p + 2));
+        }
         if (nops < 1) { ok = false; break; }
         bool spliced = false;
         for (int k = 0; k < nops; ++k) spliced = spliced || opc(ops[k]) == OP_REF_SKIP;
@@ -550,7 +537,7 @@ chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue 
           if (a.x != prev_ref) { ok = false; break; }
         }
         // finalise this hit (1888-1945)
-        num_mm += (int)((a.z >> 16) & 0xffu); num_smm += (int)(a.z >> 24);
+        num_mm += (int)((a.w >> 16) & 0xffu); num_smm += (int)(a.w >> 24);
         if (spliced) { if (asplice) { if (saw_s) { ok = false; break; } saw_as = true; } else { if (saw_as) { ok = false; break; } saw_s = true; } }
         int b0 = 0;
         if (nLC > 0 && opc(LC[nLC - 1]) == opc(ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(ops[0])); b0 = 1; }
@@ -613,20 +600,20 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     // ---- phase 0: task, read, orientation
     bool alive = ti < nq;
     const uint32_t* __restrict__ t = qtasks + (alive ? ti : 0) * q.stride;
-    uint32_t bi = 0; int read_len = 0, n = 0; bool anti = false;
+    uint32_t bi = 0, ops_begin = 0; int read_len = 0, n = 0; bool anti = false;
     uint64_t R[12];
     #pragma unroll
     for (int k = 0; k < 12; ++k) R[k] = 0;
     if (alive) {
       bi = t[0];
       const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
-      read_len = (int)(hdr.z & 0xffffu); n = (int)((hdr.z >> 16) & 0xffu);
+      read_len = (int)(hdr.z & 0xffffu); n = (int)((hdr.z >> 16) & 0xffu); ops_begin = hdr.w;
       const uint64_t* rd = bv.reads + (size_t)bi * 3 * bv.read_words; const int rw = (int)bv.read_words;
       #pragma unroll
       for (int pl = 0; pl < 3; ++pl)
         #pragma unroll
         for (int w = 0; w < 4; ++w) R[pl * 4 + w] = w < rw ? __ldg(rd + pl * rw + w) : 0ull;
-      anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 2) >> 8) & THB_HIT_ANTISENSE;       // chain orientation (2117-2121)
+      anti = (__ldg(reinterpret_cast<const uint32_t*>(bv.hits + t[1]) + 3) & THB_HIT_ANTISENSE) != 0;     // chain orientation (2117-2121)
     }
     __syncwarp();
     if (alive && anti && n > 1) { uint64_t F[12];
@@ -637,14 +624,14 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     int nmax = n;
     #pragma unroll
     for (int k = 16; k > 0; k >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, k));
-    auto chain_hit = [&](int e) -> const thb_jhit* { const int s = anti ? n - 1 - e : e; return bv.hits + t[1 + s]; };
+    auto chain_hit = [&](int e) -> uint32_t { const int s = anti ? n - 1 - e : e; return t[1 + s]; };
     auto chain_len = [&](int e) -> int { const int s = anti ? n - 1 - e : e; return (s == n - 1) ? read_len - s * P.seglen : P.seglen; };
 
     thb_joined j; j.bundle = bi; j.reserved8[0] = j.reserved8[1] = j.reserved8[2] = 0; j.n_ops = 0;
     // ---- single-segment reads: merge_segment_chain 2196-2213
     const bool single = alive && n == 1;
     if (single) {
-      WHit w; load_whit(w, bv.hits + t[1], 0, read_len);
+      WHit w; load_whit(w, bv, t[1], ops_begin, 0, read_len);
       alive = w.n > 0 && valid_cigar(P, w.ops, w.n);
       if (alive) { j.ref_id = w.ref; j.left = w.left; j.n_ops = (uint8_t)w.n; j.flags = (uint8_t)((w.anti ? THB_HIT_ANTISENSE : 0) | (w.asplice ? THB_JHIT_ANTISENSE_SPLICE : 0));
                    j.mismatches = w.mism; j.edit_dist = (uint8_t)(w.mism + cig_gap_length(w.ops, w.n)); j.splice_mms = w.smm;
@@ -657,7 +644,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     int num_fusions = 0;
     uint64_t cs = 0; int64_t clen = 0;
     if (multi) {
-      const uint32_t r0 = chain_hit(0)->ref_id;
+      const uint32_t r0 = __ldg(&bv.hits[chain_hit(0)].ref_id);
       if (!(r0 >= 1 && r0 <= ref.n_contigs)) multi = false;
       else { cs = __ldg(ref.contig_start + r0 - 1); clen = (int64_t)__ldg(ref.contig_len + r0 - 1); }
     }
@@ -678,7 +665,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     prev.right = 0; prev.rlen = 0; prev.spliced = false;
     int left0 = 0; uint32_t ref0 = 0; bool antisense = false;
     if (multi) {
-      load_whit(prev, chain_hit(0), 0, chain_len(0));
+      load_whit(prev, bv, chain_hit(0), ops_begin, 0, chain_len(0));
       left0 = prev.left; ref0 = prev.ref; antisense = prev.anti;
       old_read_length += prev.rlen;
     }
@@ -691,7 +678,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       bool found = false, antisense_closure = false; int mismatch = 0, prml = 0, clml = 0, pright = 0;
       // phase 1: load + classify
       if (on) {
-        load_whit(curr, chain_hit(e), prev.seq_pos + prev.seq_len, chain_len(e));
+        load_whit(curr, bv, chain_hit(e), ops_begin, prev.seq_pos + prev.seq_len, chain_len(e));
         old_read_length += curr.rlen;
         antisense = prev.anti;
         const bool ps = prev.spliced, csp = curr.spliced;

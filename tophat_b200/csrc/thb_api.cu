@@ -40,7 +40,7 @@ struct DevBuf {
 
 struct Staging { DevBuf bundles, seg_count, reads, hits, partner; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; };
 // join pipeline stage: input staging + the chunk's result buffer (its device->host copy overlaps the next chunk's kernels)
-struct JStage { DevBuf bundles, seg_count, reads, hits, out; uint64_t cap_out = 0; cudaEvent_t copied = nullptr, out_free = nullptr; bool out_busy = false; };
+struct JStage { DevBuf bundles, seg_count, reads, hits, ops, out; uint64_t cap_out = 0; cudaEvent_t copied = nullptr, out_free = nullptr; bool out_busy = false; };
 
 // dynamically bound NCCL (the library is only needed for the multi-GPU exchange)
 struct NcclUid { char b[128]; };          // ncclUniqueId is passed BY VALUE to ncclCommInitRank
@@ -384,7 +384,7 @@ void thb_destroy(thb_ctx* ctx)
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
-  for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
+  for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.ops, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
   if (ctx->h_joined) cudaFreeHost(ctx->h_joined);
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
   delete ctx;
@@ -423,6 +423,29 @@ void thb_pack_read(const char* seq, uint32_t len, uint32_t read_words, uint64_t*
     if (c & 2) out[read_words + w] |= 1ull << j;
     if (isn) out[2 * read_words + w] |= 1ull << j;
   }
+}
+
+int thb_join_pack_hits(const thb_jhit_full* hits, uint32_t n, thb_jhit* heads, thb_jops* ops_ext)
+{
+  if ((n && (!hits || !heads)) ) return THB_EINVAL;
+  uint32_t n_ext = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const thb_jhit_full& f = hits[i]; thb_jhit& h = heads[i];
+    uint32_t nops = f.n_ops; if (nops > THB_JHIT_MAX_OPS) return THB_EINVAL;
+    int64_t right = f.left;
+    for (uint32_t k = 0; k < nops; ++k) { const uint32_t c = f.ops[k] & 15u; if (c == 1 || c == 5 || c == 11) right += (int64_t)(f.ops[k] >> 4); }
+    const bool one_match = nops == 1 && (f.ops[0] & 15u) == 1u;
+    h.ref_id = f.ref_id; h.left = f.left; h.right = (int32_t)right;
+    h.flags_nops = (uint8_t)((f.flags & 0x7u) | (one_match ? THB_JHIT_ONE_MATCH : 0) | (nops << 4));
+    h.mismatches = f.mismatches; h.splice_mms = f.splice_mms; h.ops_index = 0;
+    if (!one_match) {
+      if (n_ext > 255 || !ops_ext) return THB_EUNSUPPORTED;
+      h.ops_index = (uint8_t)n_ext;
+      thb_jops& o = ops_ext[n_ext++]; memset(&o, 0, sizeof o);
+      for (uint32_t k = 0; k < nops; ++k) o.ops[k] = f.ops[k];
+    }
+  }
+  return (int)n_ext;
 }
 
 int thb_ref_upload(thb_ctx* ctx, const thb_ref_image* img)
@@ -765,13 +788,13 @@ static int join_validate(thb_ctx* ctx, const thb_join_batch* b)
   if (!ctx->join_begun) return fail(ctx, THB_ESTATE, "thb_join_begin not called");
   if (b->n_segs < 1 || b->n_segs > (uint32_t)JMAXSEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, JMAXSEGS);
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4]", b->read_words);
-  if (!b->bundles || !b->seg_count || !b->reads || (b->n_hits && !b->hits)) return fail(ctx, THB_EINVAL, "null batch array");
+  if (!b->bundles || !b->seg_count || !b->reads || (b->n_hits && !b->hits) || (b->n_ops_ext && !b->ops_ext)) return fail(ctx, THB_EINVAL, "null batch array");
   if (b->n_hits >= (1ull << 32)) return fail(ctx, THB_EUNSUPPORTED, "more than 2^32 segment hits in one batch (hit_begin is 32 bits)");
   return THB_OK;
 }
 
 // launches the chain join over device-resident arrays; results stay in ctx->j_out, *n receives their number
-static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsigned long long* n_res, DevBuf& out_buf, uint64_t& cap_out)
+static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint64_t n_ext, unsigned long long* n_res, DevBuf& out_buf, uint64_t& cap_out)
 {
   cap_out = std::max<uint64_t>(cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
@@ -815,9 +838,10 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, unsi
   thb_join_timing& t = ctx->jtiming;
   t.kernel_ms += kms; t.n_chains += cnt[0]; t.n_closures += cnt[1]; t.n_joined += cnt[2];
   t.n_simple_chains += qn_simple; t.n_abutting_chains += qn_abut;
-  // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 48 per segment hit, per closure
-  // 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain, 128 per output record
-  t.algorithmic_bytes += 56ull * bv.n_bundles + 48ull * n_hits + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
+  // SURVEY.md 8(d) B_join on this batch's actual counts: 16 (header) + 40 (read) per read, 16 per segment hit + 32 per hit
+  // with a multi-op CIGAR, per closure 64 (set lookup) + 64 (reference), 96 for the consistency re-read per merged chain,
+  // 128 per output record
+  t.algorithmic_bytes += 56ull * bv.n_bundles + 16ull * n_hits + 32ull * n_ext + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
   ctx->j_last_n = n;
   *n_res = n;
   return THB_OK;
@@ -858,10 +882,10 @@ int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* b, uint64_t* n_ou
   *n_out = 0; ctx->j_last_n = 0;
   int rc = join_validate(ctx, b); if (rc) return rc;
   if (b->n_bundles == 0) return THB_OK;
-  JoinBatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
+  JoinBatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits; bv.ops_ext = b->ops_ext;
   bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = 0; bv.hit_end = (uint32_t)b->n_hits;
   unsigned long long n = 0;
-  rc = join_run(ctx, bv, b->n_hits, &n, ctx->j_out, ctx->j_cap_out); if (rc) return rc;
+  rc = join_run(ctx, bv, b->n_hits, b->n_ops_ext, &n, ctx->j_out, ctx->j_cap_out); if (rc) return rc;
   *n_out = n;
   return THB_OK;
 }
@@ -879,17 +903,20 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
   uint32_t CH = 1u << 19;                                // reads per pipeline chunk (tuning knob: THB_JOIN_CHUNK_READS)
   if (const char* e = getenv("THB_JOIN_CHUNK_READS")) { const long v = atol(e); if (v >= 32 && v <= (1l << 26)) CH = (uint32_t)v; }
   const uint32_t nchunks = (b->n_bundles + CH - 1) / CH;
-  struct Range { uint32_t b0, nb; uint64_t h0, h1; };
+  struct Range { uint32_t b0, nb; uint64_t h0, h1, e0, e1; };
   auto range_of = [&](uint32_t c, Range* r) -> bool {
     r->b0 = c * CH; const uint32_t b1 = std::min<uint32_t>(b->n_bundles, r->b0 + CH); r->nb = b1 - r->b0;
     r->h0 = b->bundles[r->b0].hit_begin; r->h1 = (b1 < b->n_bundles) ? b->bundles[b1].hit_begin : b->n_hits;
-    return !(r->h1 < r->h0 || r->h1 > b->n_hits);
+    r->e0 = b->bundles[r->b0].ops_begin; r->e1 = (b1 < b->n_bundles) ? b->bundles[b1].ops_begin : b->n_ops_ext;
+    return !(r->h1 < r->h0 || r->h1 > b->n_hits || r->e1 < r->e0 || r->e1 > b->n_ops_ext);
   };
   auto enqueue_copy = [&](uint32_t c) -> int {
     JStage& s = ctx->jstage[c & 1]; Range r;
-    if (!range_of(c, &r)) return fail(ctx, THB_EINVAL, "hit_begin not monotonic near bundle %u", c * CH);
+    if (!range_of(c, &r)) return fail(ctx, THB_EINVAL, "hit_begin / ops_begin not monotonic near bundle %u", c * CH);
     CU(s.bundles.reserve((size_t)r.nb * sizeof(thb_join_bundle))); CU(s.seg_count.reserve((size_t)r.nb * b->n_segs * 2));
     CU(s.reads.reserve((size_t)r.nb * rdw * 8)); CU(s.hits.reserve((size_t)(r.h1 - r.h0 + 1) * sizeof(thb_jhit)));
+    CU(s.ops.reserve((size_t)(r.e1 - r.e0 + 1) * sizeof(thb_jops)));
+    if (r.e1 > r.e0) CU(cudaMemcpyAsync(s.ops.p, b->ops_ext + r.e0, (size_t)(r.e1 - r.e0) * sizeof(thb_jops), cudaMemcpyHostToDevice, ctx->copy));
     CU(cudaMemcpyAsync(s.bundles.p, b->bundles + r.b0, (size_t)r.nb * sizeof(thb_join_bundle), cudaMemcpyHostToDevice, ctx->copy));
     CU(cudaMemcpyAsync(s.seg_count.p, b->seg_count + (size_t)r.b0 * b->n_segs, (size_t)r.nb * b->n_segs * 2, cudaMemcpyHostToDevice, ctx->copy));
     CU(cudaMemcpyAsync(s.reads.p, b->reads + (size_t)r.b0 * rdw, (size_t)r.nb * rdw * 8, cudaMemcpyHostToDevice, ctx->copy));
@@ -908,9 +935,9 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
     if (c + 1 < nchunks) { rc = enqueue_copy(c + 1); if (rc) return rc; }
     if (s.out_busy) CU(cudaStreamWaitEvent(ctx->compute, s.out_free, 0));      // records of chunk c-2 have left this buffer
     JoinBatchView bv; bv.bundles = (const thb_join_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p; bv.reads = (const uint64_t*)s.reads.p;
-    bv.hits = (const thb_jhit*)s.hits.p - r.h0; bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = r.b0; bv.hit_end = (uint32_t)r.h1;
+    bv.hits = (const thb_jhit*)s.hits.p - r.h0; bv.ops_ext = (const thb_jops*)s.ops.p - r.e0; bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = r.b0; bv.hit_end = (uint32_t)r.h1;
     unsigned long long n = 0;
-    rc = join_run(ctx, bv, r.h1 - r.h0, &n, s.out, s.cap_out); if (rc) return rc;       // returns with the compute stream idle
+    rc = join_run(ctx, bv, r.h1 - r.h0, r.e1 - r.e0, &n, s.out, s.cap_out); if (rc) return rc;       // returns with the compute stream idle
     rc = join_host_reserve(ctx, total + n, total); if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(ctx->h_joined + total, s.out.p, n * sizeof(thb_joined), cudaMemcpyDeviceToHost, ctx->d2h));
     CU(cudaEventRecord(s.out_free, ctx->d2h)); s.out_busy = true;

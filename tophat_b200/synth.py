@@ -928,13 +928,19 @@ def write_contig_header(path: str, contigs) -> None:
 # ---------------------------------------------------------------------------------------------
 # vectorised junction-spanning segment placement + packed join batches (bench / large tests)
 
-JHIT_DTYPE = np.dtype([("ref_id", "<u4"), ("left", "<i4"), ("n_ops", "u1"), ("flags", "u1"), ("mismatches", "u1"),
-                       ("splice_mms", "u1"), ("ops", "<u4", (9,))])
+# thb_jhit_full (unpacked, CIGAR inline) and the wire form thb_jhit (16 bytes) + thb_jops (include/tophat_b200.h)
+JHIT_FULL_DTYPE = np.dtype([("ref_id", "<u4"), ("left", "<i4"), ("n_ops", "u1"), ("flags", "u1"), ("mismatches", "u1"),
+                            ("splice_mms", "u1"), ("ops", "<u4", (9,))])
+JHIT_DTYPE = np.dtype([("ref_id", "<u4"), ("left", "<i4"), ("right", "<i4"), ("flags_nops", "u1"), ("ops_index", "u1"),
+                       ("mismatches", "u1"), ("splice_mms", "u1")])
+JOPS_DTYPE = np.dtype([("ops", "<u4", (12,))])
+JHIT_ONE_MATCH = 8
 JBUNDLE_DTYPE = np.dtype([("read_id", "<u4"), ("hit_begin", "<u4"), ("read_len", "<u2"), ("n_segs", "u1"), ("reserved", "u1"),
-                          ("reserved2", "<u4")])
+                          ("ops_begin", "<u4")])
 JOINED_DTYPE = np.dtype([("bundle", "<u4"), ("ref_id", "<u4"), ("left", "<i4"), ("n_ops", "u1"), ("flags", "u1"), ("mismatches", "u1"),
                          ("edit_dist", "u1"), ("splice_mms", "u1"), ("reserved8", "u1", (3,)), ("ops", "<u4", (27,))])
-assert JHIT_DTYPE.itemsize == 48 and JBUNDLE_DTYPE.itemsize == 16 and JOINED_DTYPE.itemsize == 128
+assert JHIT_FULL_DTYPE.itemsize == 48 and JHIT_DTYPE.itemsize == 16 and JOPS_DTYPE.itemsize == 48
+assert JBUNDLE_DTYPE.itemsize == 16 and JOINED_DTYPE.itemsize == 128
 JHIT_ANTISENSE_SPLICE = 4
 OP_MATCH, OP_INS, OP_DEL, OP_REF_SKIP = 1, 3, 5, 11
 
@@ -1051,14 +1057,40 @@ class PackedJoinBatch:
     bundles: np.ndarray
     seg_count: np.ndarray
     reads: np.ndarray
-    hits: np.ndarray
+    hits: np.ndarray                   # JHIT_DTYPE (wire form)
+    ops_ext: np.ndarray                # JOPS_DTYPE, one per hit without JHIT_ONE_MATCH
 
     @property
     def n_bundles(self) -> int:
         return int(self.bundles.shape[0])
 
     def nbytes(self) -> int:
-        return int(self.bundles.nbytes + self.seg_count.nbytes + self.reads.nbytes + self.hits.nbytes)
+        return int(self.bundles.nbytes + self.seg_count.nbytes + self.reads.nbytes + self.hits.nbytes + self.ops_ext.nbytes)
+
+
+def pack_join_hits(full: np.ndarray, hit_begin: np.ndarray):
+    """Vectorised thb_join_pack_hits: unpacked hits in batch order + the first hit of every read -> (heads, ops_ext, ops_begin)."""
+    n = full.shape[0]
+    ops = full["ops"].astype(np.int64)
+    code = ops & 15
+    k = np.arange(9)[None, :] < full["n_ops"][:, None].astype(np.int64)
+    adv = np.where(k & ((code == OP_MATCH) | (code == OP_DEL) | (code == OP_REF_SKIP)), ops >> 4, 0).sum(axis=1)
+    one = (full["n_ops"] == 1) & ((full["ops"][:, 0] & 15) == OP_MATCH)
+    heads = np.zeros(n, dtype=JHIT_DTYPE)
+    heads["ref_id"] = full["ref_id"]; heads["left"] = full["left"]; heads["right"] = full["left"].astype(np.int64) + adv
+    heads["flags_nops"] = (full["flags"] & 7) | np.where(one, JHIT_ONE_MATCH, 0) | (full["n_ops"].astype(np.uint8) << 4)
+    heads["mismatches"] = full["mismatches"]; heads["splice_mms"] = full["splice_mms"]
+    multi = ~one
+    before = np.concatenate([[0], np.cumsum(multi)])                 # multi-op hits before hit i
+    ops_begin = before[hit_begin] if hit_begin.size else np.zeros(0, dtype=np.int64)
+    owner = np.searchsorted(hit_begin, np.arange(n), side="right") - 1 if n else np.zeros(0, dtype=np.int64)
+    ordinal = before[:-1] - ops_begin[owner] if n else np.zeros(0, dtype=np.int64)
+    if multi.any() and int(ordinal[multi].max()) > 255:
+        raise ValueError("more than 256 multi-op hits in one read")
+    heads["ops_index"] = np.where(multi, ordinal, 0)
+    ext = np.zeros(int(multi.sum()), dtype=JOPS_DTYPE)
+    ext["ops"][:, :9] = np.where(k[multi], full["ops"][multi], 0)
+    return heads, ext, ops_begin.astype("<u4")
 
 
 def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> PackedJoinBatch:
@@ -1080,14 +1112,14 @@ def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> Packe
     for k in range(nseg):
         h = side.seg_hits[k]
         b = remap[h["read_idx"]]; m = b >= 0
-        jh = np.zeros(int(m.sum()), dtype=JHIT_DTYPE)
+        jh = np.zeros(int(m.sum()), dtype=JHIT_FULL_DTYPE)
         hm = h[m]
         jh["ref_id"] = hm["ref_id"]; jh["left"] = hm["left"]; jh["n_ops"] = 1; jh["flags"] = hm["flags"]; jh["mismatches"] = hm["edit_dist"]
         jh["ops"][:, 0] = (hm["read_len"].astype(np.uint32) << 4) | OP_MATCH
         parts.append(jh); keys.append(b[m] * (2 * nseg) + 2 * k)
         d = spl[k]
         b = remap[d["read_idx"]]; m = b >= 0
-        js = np.zeros(int(m.sum()), dtype=JHIT_DTYPE)
+        js = np.zeros(int(m.sum()), dtype=JHIT_FULL_DTYPE)
         x = d["x"][m]; ln = d["ln"]
         js["ref_id"] = d["ref_id"][m]; js["left"] = d["jl"][m] - x + 1; js["n_ops"] = 3
         js["flags"] = np.where(d["anti"][m], HIT_ANTISENSE, 0) | (HIT_END if k == nseg - 1 else 0) | np.where(d["asplice"][m] > 0, JHIT_ANTISENSE_SPLICE, 0)
@@ -1102,8 +1134,10 @@ def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> Packe
     bundles["read_id"] = side.ids[sel]
     bundles["hit_begin"] = np.concatenate([[0], np.cumsum(counts[sel].sum(axis=1))])[:-1]
     bundles["read_len"] = L; bundles["n_segs"] = nseg
+    heads, ext, ops_begin = pack_join_hits(allh, bundles["hit_begin"].astype(np.int64))
+    bundles["ops_begin"] = ops_begin
     rw = (L + 63) // 64
-    return PackedJoinBatch(nseg, rw, bundles, np.ascontiguousarray(counts[sel].astype("<u2")), pack_reads(side.reads[sel], rw), allh)
+    return PackedJoinBatch(nseg, rw, bundles, np.ascontiguousarray(counts[sel].astype("<u2")), pack_reads(side.reads[sel], rw), heads, ext)
 
 
 def spliced_hits_for_sam(wl: Workload, side: SideData, junctions: np.ndarray, contigs):
