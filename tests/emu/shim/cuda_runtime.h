@@ -190,3 +190,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred)
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta)
+{ const unsigned lane = threadIdx.x & 31u; const T o = __shfl_sync(mask, v, (int)(lane >= delta ? lane - delta : lane)); return o; }
+template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta)
+{ const unsigned lane = threadIdx.x & 31u; const T o = __shfl_sync(mask, v, (int)(lane + delta < 32u ? lane + delta : lane)); return o; }

@@ -364,22 +364,46 @@ struct ChainQueue {
 
 // K-J1: join_segments_for_read (2612-2667) + dfs_seg_hits (2222-2610): enumerate the compatible segment-hit chains of one
 // read in the reference's DFS order, with its budget of 10,000 complete chains per first-segment hit.
-// (Measured alternatives, both slower on B200 than this per-thread walk at 2.5 ms / 10.5 M reads: the walk as a warp lock-step
-// state machine, 3.1 ms; the hits of the warp's 32 reads staged in shared memory first, 3.6 ms -- profiles/README.md.)
-__device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const ChainQueue& q, uint32_t bi, unsigned& n_leaves)
+// (Measured alternatives, both slower on B200 than this per-thread walk: the walk as a warp lock-step state machine, and the
+// hits of the warp's 32 reads staged in shared memory first -- profiles/README.md.)
+// Complete chains are NOT appended to the queues from inside the walk: a returning atomic there costs an L2 round trip per
+// chain with the lanes diverged (a third of all stall samples in profiles/r1w).  Each lane parks its first ENUM_PARK chains
+// in local memory; after the walk the warp is converged again and reserves queue space with one atomic per queue for all
+// 32 reads.  Only a read with more chains than that falls back to reserving from inside the walk.
+constexpr int ENUM_PARK = 4;
+struct ParkedChains { uint16_t sel[ENUM_PARK][JMAXSEGS]; uint8_t kind[ENUM_PARK]; int n; };    // kind: 0 general, 1 simple, 2 abutting
+
+__device__ __forceinline__ void write_chain(const ChainQueue& q, int kind, unsigned long long slot, uint32_t bi, int n, const uint32_t* off, const uint16_t* sel)
+{
+  if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
+  uint32_t* t = (kind == 1 ? q.simple_tasks : (kind == 2 ? q.abut_tasks : q.tasks)) + slot * q.stride;
+  t[0] = bi;
+  for (int s = 0; s < n; ++s) t[1 + s] = off[s] + (uint32_t)sel[s];
+}
+
+__device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const ChainQueue& q, uint32_t bi, unsigned& n_leaves,
+                          ParkedChains& park, int& n_out, uint32_t* off)
 {
   const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(bv.bundles + bi));
   const int n = (int)((hdr.z >> 16) & 0xffu);
   if (n < 1 || n > JMAXSEGS) return;
-  uint32_t off[JMAXSEGS]; int cnt[JMAXSEGS];
+  n_out = n;
+  int cnt[JMAXSEGS];
   { uint32_t a = hdr.y;
     for (int s = 0; s < n; ++s) { cnt[s] = (int)__ldg(bv.seg_count + (size_t)bi * bv.n_segs + s); off[s] = a; a += (uint32_t)cnt[s]; } }
   if (P.bowtie2) for (int s = 0; s < n; ++s) if (cnt[s] > P.max_seg_multihits) return;      // 2624-2632
-  int sel[JMAXSEGS], it[JMAXSEGS]; LiteHit top[JMAXSEGS]; bool simp[JMAXSEGS], abut[JMAXSEGS];
+  int it[JMAXSEGS]; uint16_t sel[JMAXSEGS]; LiteHit top[JMAXSEGS]; bool simp[JMAXSEGS], abut[JMAXSEGS];
   auto leaf = [&]() {
     ++n_leaves;
     const bool simple = n > 1 && simp[n - 1];
     const bool abutting = !simple && n > 1 && abut[n - 1];
+    const int kind = simple ? 1 : (abutting ? 2 : 0);
+    if (park.n < ENUM_PARK) {
+      for (int s = 0; s < n; ++s) park.sel[park.n][s] = sel[s];
+      park.kind[park.n] = (uint8_t)kind; ++park.n;
+      return;
+    }
+    // overflow of the parking area: reserve from here (lanes that are converged at this point share the atomic)
     unsigned long long* ctr = simple ? q.simple_count : (abutting ? q.abut_count : q.count);
     unsigned long long slot;
     { const unsigned m = __activemask(); const unsigned ms = __ballot_sync(m, simple); const unsigned ma = __ballot_sync(m, abutting);
@@ -387,13 +411,10 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
       const unsigned ln = threadIdx.x & 31u; const int leader = __ffs((int)grp) - 1;
       unsigned long long b0 = 0; if ((int)ln == leader) b0 = atomicAdd(ctr, (unsigned long long)__popc(grp));
       b0 = __shfl_sync(grp, b0, leader); slot = b0 + (unsigned long long)__popc(grp & ((1u << ln) - 1u)); }
-    if (slot >= q.cap) { atomicOr(q.overflow, 1u); return; }
-    uint32_t* t = (simple ? q.simple_tasks : (abutting ? q.abut_tasks : q.tasks)) + slot * q.stride;
-    t[0] = bi;
-    for (int s = 0; s < n; ++s) t[1 + s] = off[s] + (uint32_t)sel[s];
+    write_chain(q, kind, slot, bi, n, off, sel);
   };
   for (int i0 = 0; i0 < cnt[0]; ++i0) {
-    sel[0] = i0;
+    sel[0] = (uint16_t)i0;
     int num_try = 10000;                                           // 2647
     if (n == 1) { --num_try; leaf(); continue; }
     int lvl = 1; it[1] = 0;
@@ -403,7 +424,7 @@ __device__ void enum_read(const JoinParams& P, const JoinBatchView& bv, const Ch
       const LiteHit cand = load_lite(bv.hits + off[lvl] + it[lvl]);
       int dist;
       if (!chain_compatible(P, top[lvl - 1], cand, dist)) { ++it[lvl]; continue; }
-      sel[lvl] = it[lvl]; top[lvl] = cand; simp[lvl] = simp[lvl - 1] && cand.one_m && dist == 0; abut[lvl] = abut[lvl - 1] && dist == 0;
+      sel[lvl] = (uint16_t)it[lvl]; top[lvl] = cand; simp[lvl] = simp[lvl - 1] && cand.one_m && dist == 0; abut[lvl] = abut[lvl - 1] && dist == 0;
       if (lvl == n - 1) { --num_try; leaf(); if (num_try <= 0) break; ++it[lvl]; }
       else { ++lvl; it[lvl] = 0; }
     }
@@ -416,7 +437,32 @@ chain_enum_kernel(JoinParams P, JoinBatchView bv, ChainQueue q, unsigned long lo
   unsigned n_leaves = 0;
   const unsigned lane = threadIdx.x & 31u;
   for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < bv.n_bundles; base += gridDim.x * blockDim.x) {
-    if (base + lane < bv.n_bundles) enum_read(P, bv, q, base + lane, n_leaves);
+    ParkedChains park; park.n = 0; int n = 0; uint32_t off[JMAXSEGS];
+    const uint32_t bi = base + lane;
+    if (bi < bv.n_bundles) enum_read(P, bv, q, bi, n_leaves, park, n, off);
+    __syncwarp();
+    // converged: one reservation per queue for the parked chains of all 32 reads
+    unsigned c[3] = {0u, 0u, 0u};
+    for (int k = 0; k < park.n; ++k) c[park.kind[k]]++;
+    unsigned long long slot[3];
+    #pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      unsigned incl = c[kd];
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long b0 = 0;
+      if (total) {
+        if (lane == 0) b0 = atomicAdd(kd == 1 ? q.simple_count : (kd == 2 ? q.abut_count : q.count), (unsigned long long)total);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+      }
+      slot[kd] = b0 + (unsigned long long)(incl - c[kd]);
+    }
+    for (int k = 0; k < park.n; ++k) {
+      const int kd = park.kind[k];
+      const unsigned long long sl = kd == 1 ? slot[1]++ : (kd == 2 ? slot[2]++ : slot[0]++);
+      write_chain(q, kd, sl, bi, n, off, park.sel[k]);
+    }
     __syncwarp();
   }
   for (int k = 16; k > 0; k >>= 1) n_leaves += __shfl_xor_sync(0xffffffffu, n_leaves, k);
