@@ -300,7 +300,9 @@ int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out);
 typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; float enum_ms, merge_ms;   /* kernel_ms = enum + merge */
                                  uint32_t launches;
                                  uint64_t n_chains, n_closures, n_joined, algorithmic_bytes;
-                                 uint64_t n_simple_chains, n_abutting_chains;   /* chains merged without a closure search */ } thb_join_timing;
+                                 uint64_t n_simple_chains, n_abutting_chains;   /* chains merged without a closure search */
+                                 float merge_simple_ms, merge_abutting_ms, merge_general_ms;   /* the three merge kernels  */
+                                 float reserved_f; } thb_join_timing;
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out);
 
 /* Kernel timing of the last submit (CUDA events on the context's stream), milliseconds.        */

@@ -15,13 +15,14 @@ js = capi.join_sets_from_results(res)
 jb = [synth.pack_join_side(wl, wl.left, res.junctions), synth.pack_join_side(wl, wl.right, res.junctions)]
 keep, structs = [], []
 for b in jb:
-    t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k)).view(np.uint8).reshape(-1)).cuda() for k in ("bundles", "seg_count", "reads", "hits")}
+    t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k)).view(np.uint8).reshape(-1)).cuda() for k in ("bundles", "seg_count", "reads", "hits", "ops_ext")}
     keep.append(t); bc = capi.join_batch_c(b)
     for k in t: setattr(bc, k, t[k].data_ptr())
     structs.append(bc)
 torch.cuda.synchronize()
-for _ in range(2):
+for _ in range(3):
     ctx.join_begin(P, js[0], js[1])
     n = sum(ctx.join_submit_device(bc) for bc in structs)
     t = ctx.join_timing()
-    print("join: enum %.3f ms merge %.3f ms, %d chains %d closures %d joined" % (t.enum_ms, t.merge_ms, t.n_chains, t.n_closures, n), flush=True)
+    print("join: enum %.3f ms merge %.3f ms (simple %.3f abutting %.3f general %.3f), %d chains %d closures %d joined" % (
+        t.enum_ms, t.merge_ms, t.merge_simple_ms, t.merge_abutting_ms, t.merge_general_ms, t.n_chains, t.n_closures, n), flush=True)

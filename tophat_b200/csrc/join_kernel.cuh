@@ -235,22 +235,23 @@ __device__ __forceinline__ int junction_closure(const RefView& ref, const JoinSe
     const int dtl = (int)(J.left - (uint32_t)pright + 1u), dtr = (int)(J.right - (uint32_t)cleft);
     if (!(abs(dtl) <= 4 && abs(dtr) <= 4 && dtl == dtr)) continue;
     if (dtl > clml || -dtl > prml) continue;                  // enough matched bases on either side (1343-1348)
+    // mismatches of the <= 4 shifted read bases against their new and old reference positions: Dna5 character compares
+    // (N equals N), done on bit planes -- two reference fetches instead of two loads per base
     int new_mm = 0, old_mm = 0;
+    auto slice_mm = [&](int read_pos, uint64_t g, int len) -> int {
+      const P3 r = ref_fetch3(ref, g, len);
+      const uint64_t q0 = plane_slice(R, 4, read_pos, len), q1 = plane_slice(R + 4, 4, read_pos, len), qn = plane_slice(R + 8, 4, read_pos, len);
+      return __popcll((r.p0 ^ q0) | (r.p1 ^ q1) | (r.pn ^ qn));
+    };
     if (dtl > 0) {
       if ((int64_t)pright + dtl > clen || (int64_t)cleft + dtl > clen) return -1;
-      for (int i = 0; i < dtl; ++i) {
-        const int sc = read_code5(R, curr_seq_pos + i);
-        if (sc != ref_code5(ref, cs + (uint64_t)(pright + i))) ++new_mm;
-        if (sc != ref_code5(ref, cs + (uint64_t)(cleft + i))) ++old_mm;
-      }
+      new_mm = slice_mm(curr_seq_pos, cs + (uint64_t)pright, dtl);
+      old_mm = slice_mm(curr_seq_pos, cs + (uint64_t)cleft, dtl);
     } else if (dtl < 0) {
       const int ad = -dtl;
       if ((int64_t)J.right + ad > clen) return -1;
-      for (int i = 0; i < ad; ++i) {
-        const int sc = read_code5(R, prev_seq_end - (ad - i));
-        if (sc != ref_code5(ref, cs + (uint64_t)J.right + (uint64_t)i)) ++new_mm;
-        if (sc != ref_code5(ref, cs + (uint64_t)J.left + 1u + (uint64_t)i)) ++old_mm;
-      }
+      new_mm = slice_mm(prev_seq_end - ad, cs + (uint64_t)J.right, ad);
+      old_mm = slice_mm(prev_seq_end - ad, cs + (uint64_t)J.left + 1u, ad);
     }
     const int temp = new_mm - old_mm;
     if (temp >= new_diff || new_mm >= 2) continue;            // first strictly better candidate in Junction order (1497-1512)
@@ -537,17 +538,44 @@ chain_merge_simple_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueu
 // "finalised" in turn (1888-1945: mismatch sums, splice-strand agreement, CIGAR appended with equal neighbouring ops fused),
 // after the pair checks of 930-949.  That is one streaming pass over the chain's hit records, so these chains (the bulk of
 // the spliced reads) get a kernel without the closure machinery of K-J2: no working copies of the hits, no phases.
-__global__ void __launch_bounds__(128)
+template <bool DEFER, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, JoinOut o)
 {
   unsigned n_emit = 0;
   unsigned long long nq = *q.abut_count; if (nq > q.cap) nq = q.cap;
   const unsigned lane = threadIdx.x & 31u;
+  // The record of a chain is written one iteration late: the atomic that reserves the warp's output slots is issued at the
+  // end of iteration i and its result is first needed at the end of iteration i+1, so its L2 round trip (a quarter of the
+  // stall samples of this kernel in profiles/r1w) overlaps the next chain's loads.  CIGAR buffers ping-pong between the two.
+  uint32_t LCB[2][JMAXOPS]; int par = 0;
+  unsigned p_em = 0; unsigned long long p_slot0 = 0; bool p_ok = false; uint4 p_hdr = make_uint4(0u, 0u, 0u, 0u); uint32_t p_smm = 0; int p_n = 0;
+  auto flush = [&]() {
+    if (!p_em) return;
+    const unsigned long long slot0 = __shfl_sync(0xffffffffu, p_slot0, __ffs((int)p_em) - 1);
+    if (p_ok) {
+      const unsigned long long slot = slot0 + (unsigned long long)__popc(p_em & ((1u << lane) - 1u));
+      if (slot >= o.cap) atomicOr(o.overflow, 1u);
+      else {
+        const uint32_t* PL = LCB[par ^ 1];
+        uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
+        dst[0] = p_hdr;
+        auto op_at = [&](int k) -> uint32_t { return k < p_n ? PL[k] : 0u; };
+        dst[1] = make_uint4(p_smm, op_at(0), op_at(1), op_at(2));
+        for (int qd = 2; 4 * qd - 5 < p_n; qd += 2) {
+          dst[qd] = make_uint4(op_at(4 * qd - 5), op_at(4 * qd - 4), op_at(4 * qd - 3), op_at(4 * qd - 2));
+          dst[qd + 1] = make_uint4(op_at(4 * qd - 1), op_at(4 * qd), op_at(4 * qd + 1), op_at(4 * qd + 2));
+        }
+      }
+      ++n_emit;
+    }
+    p_em = 0;
+  };
   for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long ti = base + lane;
     bool ok = ti < nq;
     uint32_t bi = 0, ref0 = 0; int left0 = 0, nLC = 0, num_mm = 0, num_smm = 0; bool anti = false, saw_as = false, saw_s = false;
-    uint32_t LC[JMAXOPS];
+    uint32_t* LC = LCB[par];
     if (ok) {
       const uint32_t* __restrict__ t = q.abut_tasks + ti * q.stride;
       bi = t[0];
@@ -601,30 +629,19 @@ chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue 
       }
     }
     const unsigned em = __ballot_sync(0xffffffffu, ok);
-    if (em) {
-      unsigned long long slot0 = 0;
-      if (lane == (unsigned)(__ffs((int)em) - 1)) slot0 = atomicAdd(o.count, (unsigned long long)__popc(em));
-      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs((int)em) - 1);
-      if (ok) {
-        const unsigned long long slot = slot0 + (unsigned long long)__popc(em & ((1u << lane) - 1u));
-        if (slot >= o.cap) atomicOr(o.overflow, 1u);
-        else {
-          uint4* dst = reinterpret_cast<uint4*>(o.rec + slot);
-          const uint32_t mism = (uint32_t)num_mm & 0xffu, ed = ((uint32_t)num_mm + (uint32_t)cig_gap_length(LC, nLC)) & 0xffu;
-          const uint32_t flags = (anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) | (saw_as ? (uint32_t)THB_JHIT_ANTISENSE_SPLICE : 0u);
-          dst[0] = make_uint4(bi + bv.bundle_base, ref0, (uint32_t)left0, (uint32_t)nLC | (flags << 8) | (mism << 16) | (ed << 24));
-          auto op_at = [&](int k) -> uint32_t { return k < nLC ? LC[k] : 0u; };
-          dst[1] = make_uint4((uint32_t)num_smm & 0xffu, op_at(0), op_at(1), op_at(2));
-          for (int qd = 2; 4 * qd - 5 < nLC; qd += 2) {
-            dst[qd] = make_uint4(op_at(4 * qd - 5), op_at(4 * qd - 4), op_at(4 * qd - 3), op_at(4 * qd - 2));
-            dst[qd + 1] = make_uint4(op_at(4 * qd - 1), op_at(4 * qd), op_at(4 * qd + 1), op_at(4 * qd + 2));
-          }
-        }
-        ++n_emit;
-      }
+    flush();                                                     // the previous iteration's records, CIGARs in LCB[par ^ 1]
+    p_em = em; p_ok = ok; p_n = nLC; p_smm = (uint32_t)num_smm & 0xffu;
+    if (ok) {
+      const uint32_t mism = (uint32_t)num_mm & 0xffu, ed = ((uint32_t)num_mm + (uint32_t)cig_gap_length(LC, nLC)) & 0xffu;
+      const uint32_t flags = (anti ? (uint32_t)THB_HIT_ANTISENSE : 0u) | (saw_as ? (uint32_t)THB_JHIT_ANTISENSE_SPLICE : 0u);
+      p_hdr = make_uint4(bi + bv.bundle_base, ref0, (uint32_t)left0, (uint32_t)nLC | (flags << 8) | (mism << 16) | (ed << 24));
     }
+    if (em && lane == (unsigned)(__ffs((int)em) - 1)) p_slot0 = atomicAdd(o.count, (unsigned long long)__popc(em));
+    par ^= 1;
+    if (!DEFER) flush();
     __syncwarp();
   }
+  flush();
   for (int k = 16; k > 0; k >>= 1) n_emit += __shfl_xor_sync(0xffffffffu, n_emit, k);
   if (lane == 0 && n_emit) atomicAdd(o.counters + 2, (unsigned long long)n_emit);
 }
@@ -633,8 +650,8 @@ chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue 
 // Every lane walks the same phase sequence with an `alive` predicate and the warp re-converges at each __syncwarp():
 // the closure searches (equal-length binary searches) and the consistency re-read then run with all the lanes that
 // need them side by side (profiles/r1h: 4 of 32 lanes active in the straightforward per-thread form).
-template <bool CLOSURES>
-__global__ void __launch_bounds__(128)
+template <bool CLOSURES, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, ChainQueue q, JoinOut o)
 {
   unsigned n_closures = 0, n_emit = 0;

@@ -313,28 +313,54 @@ bundle_kernel(RefView ref, SegParams P, BatchView bv, Queues q, uint32_t* __rest
     // find_fusions re-anchors too, under its own pair rule (3123-3142); whether it gets that far is decided in
     // fusion_enum_kernel, here every partner hit it could ask for is queued (a superset; the search is a pure function)
     const bool fus = act && P.fusion_search && (B.flags & THB_BUNDLE_FUSIONS) && B.n_partner > 0 && B.seg_n[0] > 0;
-    if (rescued) {
-      const unsigned long long rb = agg_slot(q.counts + 3);
-      q.rbundle[rb] = bi;
-    }
-    if (rescued || fus) {
+    // Which partner hits need the flank search: decided per lane first (bit r of `need` for the first 64 partner hits), so
+    // that queue space is reserved ONCE per warp at a converged point -- a returning atomic inside this data-dependent loop
+    // stalled the diverged lanes for an L2 round trip per task (43% of this kernel's stall samples in profiles/r1u).
+    uint64_t need = 0; int n_need = 0;
+    auto partner_needed = [&](int r) -> bool {
+      const Hit rightHit = load_hit(B.partner + r);
+      if (rescue_geom(ref, P, rightHit, B.read_len).status != RG_COMPUTE) return false;
       const int minus_dist = -P.max_ins * 2;
-      for (int r = 0; r < B.n_partner; ++r) {
-        const Hit rightHit = load_hit(B.partner + r);
-        if (rescue_geom(ref, P, rightHit, B.read_len).status != RG_COMPUTE) continue;
-        bool any = false;
-        for (int l = 0; l < B.seg_n[0] && !any; ++l) {
-          const Hit leftHit = load_hit(B.seg_ptr[0] + l);
-          const bool opposite = leftHit.ref_id == rightHit.ref_id && leftHit.anti != rightHit.anti;
-          if (rescued) any = opposite;                                                 // 3412
-          if (fus && !any) {
-            const int dist = leftHit.anti ? leftHit.left - rightHit.right : rightHit.left - leftHit.right;
-            any = !(opposite && dist > minus_dist && dist <= P.fusion_min_dist);       // 3132-3142
+      bool any = false;
+      for (int l = 0; l < B.seg_n[0] && !any; ++l) {
+        const Hit leftHit = load_hit(B.seg_ptr[0] + l);
+        const bool opposite = leftHit.ref_id == rightHit.ref_id && leftHit.anti != rightHit.anti;
+        if (rescued) any = opposite;                                                 // 3412
+        if (fus && !any) {
+          const int dist = leftHit.anti ? leftHit.left - rightHit.right : rightHit.left - leftHit.right;
+          any = !(opposite && dist > minus_dist && dist <= P.fusion_min_dist);       // 3132-3142
+        }
+      }
+      return any;
+    };
+    if (rescued || fus)
+      for (int r = 0; r < B.n_partner; ++r)
+        if (partner_needed(r)) {
+          if (r < 64) { need |= 1ull << r; ++n_need; }
+          else {                                                                     // rare: reserve from here
+            const unsigned long long slot = agg_slot(q.counts + 2);
+            q.rescue[slot] = make_uint2(bi, (unsigned)(B.partner_index + (uint64_t)r - bv.partner_base));
           }
         }
-        if (!any) continue;
-        const unsigned long long slot = agg_slot(q.counts + 2);
-        q.rescue[slot] = make_uint2(bi, (unsigned)(B.partner_index + (uint64_t)r - bv.partner_base));
+    __syncwarp();
+    {
+      // warp-wide reservation: rescued-bundle list and rescue task queue
+      const unsigned mres = __ballot_sync(0xffffffffu, rescued);
+      unsigned long long rb0 = 0;
+      if (mres) { if (lane == (unsigned)(__ffs((int)mres) - 1)) rb0 = atomicAdd(q.counts + 3, (unsigned long long)__popc(mres)); }
+      unsigned incl = (unsigned)n_need;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long t0 = 0;
+      if (total && lane == 0) t0 = atomicAdd(q.counts + 2, (unsigned long long)total);
+      if (mres) rb0 = __shfl_sync(0xffffffffu, rb0, __ffs((int)mres) - 1);
+      if (total) t0 = __shfl_sync(0xffffffffu, t0, 0);
+      if (rescued) q.rbundle[rb0 + (unsigned long long)__popc(mres & ((1u << lane) - 1u))] = bi;
+      unsigned long long slot = t0 + (unsigned long long)(incl - (unsigned)n_need);
+      while (need) {
+        const int r = __ffsll((long long)need) - 1; need &= need - 1;
+        q.rescue[slot++] = make_uint2(bi, (unsigned)(B.partner_index + (uint64_t)r - bv.partner_base));
       }
     }
     __syncwarp();
@@ -355,7 +381,7 @@ bundle_kernel(RefView ref, SegParams P, BatchView bv, Queues q, uint32_t* __rest
 // __syncwarp(): lanes that skip a phase wait at the barrier instead of running ahead, so the expensive phases (read
 // slice + task emission) execute once per warp with every qualifying lane converged (profiles/r1e: 1.7 lanes before).
 template <int NSMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 hit_kernel(RefView ref, SegParams P, BatchView bv, Queues q, const uint32_t* __restrict__ bstate, const uint32_t* __restrict__ owner,
            uint64_t n_hits, SegOutputs out)
 {

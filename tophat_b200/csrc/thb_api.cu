@@ -816,8 +816,12 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
     CU(cudaEventRecord(ctx->kev[1], ctx->compute));
     chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    chain_merge_abut_kernel<<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    chain_merge_kernel<true><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    CU(cudaEventRecord(ctx->kev[3], ctx->compute));
+    // launch bounds chosen by measurement on B200 (profiles/README.md): 64 registers for the abutting-chain kernel, 80 for the
+    // closure kernel -- both are latency-bound, so residency is traded against spills
+    chain_merge_abut_kernel<false, 8><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
+    CU(cudaEventRecord(ctx->kev[4], ctx->compute));
+    chain_merge_kernel<true, 6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
     ctx->jtiming.launches += 4;
@@ -829,7 +833,10 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     n = qn[0]; qn_simple = qn[2]; qn_abut = qn[3];
     if (!ovf && n <= cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
-      kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2; break;
+      kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2;
+      float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+      cudaEventElapsedTime(&m1, ctx->kev[1], ctx->kev[3]); cudaEventElapsedTime(&m2, ctx->kev[3], ctx->kev[4]); cudaEventElapsedTime(&m3, ctx->kev[4], ctx->kev[2]);
+      ctx->jtiming.merge_simple_ms += m1; ctx->jtiming.merge_abutting_ms += m2; ctx->jtiming.merge_general_ms += m3; break;
     }
     cap_out = std::max<uint64_t>(cap_out, 2 * n + 1024);
     ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, 2 * std::max(qn[1], std::max(qn[2], qn[3])) + 1024);
