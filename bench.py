@@ -34,6 +34,11 @@ if ROOT not in sys.path:
 import numpy as np
 
 CHR20 = 64_444_167
+# BASELINE configs[2]: 24 contigs of hg38's primary-assembly sizes (chr1..22, X, Y), 3.09 Gbp
+HG38 = (248_956_422, 242_193_529, 198_295_559, 190_214_555, 181_538_259, 170_805_979, 159_345_973, 145_138_636, 138_394_717,
+        133_797_422, 135_086_622, 133_275_309, 114_364_328, 107_043_718, 101_991_189, 90_338_345, 83_257_441, 80_373_285,
+        58_617_616, 64_444_167, 46_709_983, 50_818_468, 156_040_895, 57_227_415)
+WORKLOAD = "chr20"            # set from --workload: chr20 (configs[1], default) | hg38 (configs[2]) | indel (configs[3])
 KERNELS = ("bundle", "hit", "rescue", "rescued_windows", "window_scan", "indel")
 METRIC = "spliced reads aligned/s (segment_juncs + long_spanning_reads), 2x101bp"
 UNIT = "reads/s"
@@ -51,7 +56,8 @@ def make_workload(pairs: int, rank: int, workers: int, keep_candidates: bool = F
     from tophat_b200 import synth
     chunk = 500_000 if pairs >= 500_000 else max(1000, pairs)
     nchunks = (pairs + chunk - 1) // chunk
-    cfg = synth.SynthConfig(contig_lens=(CHR20,), n_pairs=pairs, seed=20240611, chunk=chunk,
+    cfg = synth.SynthConfig(contig_lens=HG38 if WORKLOAD == "hg38" else (CHR20,), n_pairs=pairs, seed=20240611, chunk=chunk,
+                            indel_prob=0.5 if WORKLOAD == "indel" else 0.0,
                             chunk_seed_base=rank * nchunks, keep_candidates=keep_candidates, keep_truth=keep_truth)
     t = time.time()
     wl = synth.generate(cfg, workers=workers)
@@ -161,8 +167,10 @@ def run_reference_arm(args, rank: int, world: int):
 
 
 def workload_config(pairs: int, world: int, note: str = ""):
-    c = {"workload": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, "
-                     "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
+    what = {"chr20": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, ",
+            "hg38": "BASELINE configs[2]: synthetic 2x101 bp pairs, hg38-sized reference (24 contigs, 3.09 Gbp, 0.5% N), ",
+            "indel": "BASELINE configs[3]: indel-heavy synthetic 2x101 bp pairs (1-3 bp indel in half of the mates), chr20-sized reference, "}[WORKLOAD]
+    c = {"workload": what + "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
          "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)",
          "l2": "inputs (>1 GB per step at the default size) exceed the 126 MB L2; no explicit flush",
          "parallelism": "read-shard x%d%s" % (world, " + NCCL all-gather of the junction/indel sets" if world > 1 else "")}
@@ -307,6 +315,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = dict(scan_ms=0.0, alg=0, launches=0, join_ms=0.0, join_alg=0, join_launches=0, enum_ms=0.0, merge_ms=0.0,
+                   merge_simple_ms=0.0, merge_abutting_ms=0.0, merge_general_ms=0.0,
                    kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
         for _ in range(steps):
@@ -314,6 +323,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
             acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
             acc["enum_ms"] += jt.enum_ms; acc["merge_ms"] += jt.merge_ms
+            for k in ("merge_simple_ms", "merge_abutting_ms", "merge_general_ms"):
+                acc[k] += getattr(jt, k)
             for k in KERNELS:
                 acc["kms"][k] += getattr(tm, k + "_ms")
         e1.record(stream)
@@ -368,11 +379,23 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                   "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
                   "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions)),
                   "chain_enum": 16 * sum(b.n_bundles for b in jbatches) + 16 * sum(int(b.hits.shape[0]) for b in jbatches)}
-        kbytes["chain_merge"] = A["join_alg"] / steps - kbytes["chain_enum"]
-        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps; kms["chain_merge"] = A["merge_ms"] / steps
+        # the three merge kernels share the rest of B_join by their number of chains; the closure terms (128 per closure) belong
+        # to the general kernel alone
+        jt_ = A["jt"]
+        merge_total = A["join_alg"] / steps - kbytes["chain_enum"]
+        n_ch = max(1, int(jt_.n_chains)); n_s, n_a = int(jt_.n_simple_chains), int(jt_.n_abutting_chains); n_g = max(0, n_ch - n_s - n_a)
+        closure_bytes = 128.0 * int(jt_.n_closures)
+        rest = max(0.0, merge_total - closure_bytes)
+        kbytes["chain_merge_simple"] = rest * n_s / n_ch
+        kbytes["chain_merge_abut"] = rest * n_a / n_ch
+        kbytes["chain_merge"] = rest * n_g / n_ch + closure_bytes
+        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps
+        kms["chain_merge_simple"] = A["merge_simple_ms"] / steps; kms["chain_merge_abut"] = A["merge_abutting_ms"] / steps
+        kms["chain_merge"] = A["merge_general_ms"] / steps
         klaunch = {k: A["scan_launches"] for k in KERNELS}
-        klaunch["chain_enum"] = klaunch["chain_merge"] = max(1, A["join_launches"] // (4 * steps))
-        allk = KERNELS + ("chain_enum", "chain_merge")
+        allk = KERNELS + ("chain_enum", "chain_merge_simple", "chain_merge_abut", "chain_merge")
+        for k in allk[len(KERNELS):]:
+            klaunch[k] = max(1, A["join_launches"] // (4 * steps))
         dom = max(allk, key=lambda k: kms[k])
         dom_ms = kms[dom] / klaunch[dom]; dom_bytes = kbytes[dom] / klaunch[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -441,8 +464,12 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 100_000)),
                     help="pairs in the bounded sample the reference CPU binary is timed on")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chr20", choices=["chr20", "hg38", "indel"],
+                    help="chr20 = BASELINE configs[1] (the default, the configuration the metric is quoted on at one GPU); hg38 = configs[2]; indel = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)

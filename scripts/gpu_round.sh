@@ -11,6 +11,7 @@ timeout 900 python bench.py --pairs $PAIRS > gpurun_out/bench_$TAG.json 2> gpuru
 cat gpurun_out/bench_$TAG.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --pairs $PAIRS --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bundle_kernel|hit_kernel|rescue_kernel|rescued_windows_kernel|window_scan_kernel|indel_kernel|chain_enum_kernel|chain_merge" -s 20 -c 20 -f -o gpurun_out/prof_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bundle_kernel|hit_kernel|rescue_kernel|rescued_windows_kernel|window_scan_kernel|indel_kernel|chain_enum_kernel|chain_merge" -s 22 -c 22 -f -o gpurun_out/prof_$TAG \
   python bench.py --pairs $PAIRS --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full exit $?"
 ls -la gpurun_out
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "reference arm exit $?"; cut -c1-600 gpurun_out/bench_ref_$TAG.json
