@@ -270,7 +270,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     sj_fields = ("bundles", "seg_count", "reads", "hits", "partner_hits")
     sj_keep, sj_dev, sj_host = stage(batches, sj_fields, capi.batch_c)
 
-    def segjuncs_pass(device_resident: bool):
+    def segjuncs_pass(device_resident: bool, copy: bool = True):
         ctx.segjuncs_begin(P)
         for i in range(len(batches)):
             if device_resident:
@@ -279,7 +279,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit")
         if world > 1:
             ctx.segjuncs_allgather()
-        res = ctx.segjuncs_finish()
+        res = ctx.segjuncs_finish(copy)       # copy=False: views of the library's page-locked result arrays (no Python-side memcpy)
         return res, ctx.timing()
 
     # stage 2 inputs: the junction-index segment hits depend on the junction set stage 1 finds (tophat.py:3686-3741 runs
@@ -287,6 +287,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     t0 = time.time()
     res0, _ = segjuncs_pass(True)
     jsets = capi.join_sets_from_results(res0)
+    # page-locked copies of the junction / insertion sets (stage-2 inputs that thb_join_begin uploads every step)
+    _jpin = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory() for a in jsets]
+    jsets = tuple(t.numpy().view(a.dtype) for t, a in zip(_jpin, jsets))
     jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
     log("[bench] rank %d: join batches %d + %d reads, %d segment hits (%.1f s)" % (
         rank, jbatches[0].n_bundles, jbatches[1].n_bundles, sum(int(b.hits.shape[0]) for b in jbatches), time.time() - t0))
@@ -294,8 +297,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     j_keep, j_dev, j_host = stage(jbatches, j_fields, capi.join_batch_c)
     h2d_bytes = sum(b.nbytes() for b in batches) + sum(b.nbytes() for b in jbatches) + int(jsets[0].nbytes + jsets[1].nbytes)
 
-    def step(device_resident: bool):
-        res, tm = segjuncs_pass(device_resident)
+    def step(device_resident: bool, copy: bool = False):
+        res, tm = segjuncs_pass(device_resident, copy)
         ctx.join_begin(P, jsets[0], jsets[1])
         n_joined, d2h = 0, 0
         for i in range(len(jbatches)):
@@ -318,8 +321,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                    merge_simple_ms=0.0, merge_abutting_ms=0.0, merge_general_ms=0.0,
                    kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
-        for _ in range(steps):
-            res, tm, jt, n_joined, d2h = step(device_resident)
+        for k_ in range(steps):
+            res, tm, jt, n_joined, d2h = step(device_resident, copy=(k_ == steps - 1))     # the last step's sets are kept for the checks below
             acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
             acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
             acc["enum_ms"] += jt.enum_ms; acc["merge_ms"] += jt.merge_ms

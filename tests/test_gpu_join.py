@@ -78,3 +78,87 @@ def test_join_requires_begin_and_sorted_sets():
     with pytest.raises(capi.ThbError):
         ctx.join_begin(capi.default_params(fusion_search=1), j[::-1].copy(), np.zeros(0, dtype=synth.INSERTION_DTYPE))
     ctx.close()
+
+
+def _recount_mismatches(wl, batch, joined):
+    """Independent numpy re-read of every joined alignment: walks the CIGAR over the genome codes and the (oriented) read and
+    counts differing bases the way check_editdist_consistency does (bwt_map.cpp:2349-2465)."""
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    # unpack the batch's read planes back to codes
+    rw = batch.read_words
+    planes = batch.reads.reshape(batch.n_bundles, 3, rw)
+    out_mm, out_len, out_nn = np.zeros(len(joined), dtype=np.int64), np.zeros(len(joined), dtype=np.int64), np.zeros(len(joined), dtype=np.int64)
+    for i, r in enumerate(joined):
+        b = int(r["bundle"]); L = int(batch.bundles["read_len"][b])
+        bits = lambda w: ((planes[b, w][:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)).reshape(-1)[:L].astype(np.uint8)
+        codes = bits(0) | (bits(1) << 1); codes[bits(2) == 1] = 4
+        if r["flags"] & 1:
+            codes = comp[codes[::-1]]
+        ref = wl.ref.codes[int(r["ref_id"]) - 1]
+        pos_ref, pos_seq, mm, nn = int(r["left"]), 0, 0, 0
+        for o in r["ops"][:r["n_ops"]]:
+            c, l = int(o) & 15, int(o) >> 4
+            if c == 1:
+                g = ref[pos_ref:pos_ref + l]; s = codes[pos_seq:pos_seq + l]
+                mm += int(((g != s) & ~((g > 3) & (s > 3))).sum()) if len(g) == l else 10**6
+                nn += int(((g > 3) & (s > 3)).sum()) if len(g) == l else 0
+                pos_ref += l; pos_seq += l
+            elif c == 3:
+                pos_seq += l
+            elif c in (5, 11):
+                pos_ref += l
+        out_mm[i] = mm; out_len[i] = pos_seq; out_nn[i] = nn
+    return out_mm, out_len, out_nn
+
+
+def test_join_properties_at_scale(monkeypatch):
+    """100k pairs through both stages: size-independent properties of the joined alignments -- the CIGAR covers the whole read,
+    starts and ends with a match, every REF_SKIP is a junction of the set handed to thb_join_begin (after the +-4 bp boundary
+    adjustment the skip itself is an exact set member), the mismatch field equals an independent recount for a sample of the
+    records, and the record set does not depend on how the batch is cut into pipeline chunks or shards."""
+    wl = synth.generate(synth.SynthConfig(contig_lens=(6_000_000, 2_000_000), n_pairs=100_000, seed=521, indel_prob=0.2, keep_candidates=True), workers=4)
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    ctx = capi.Context(0); ctx.ref_upload(wl.ref)
+    res, _ = helpers.gpu_segjuncs(P, wl.ref, helpers.pack_both(wl), ctx)
+    juncs, ins = capi.join_sets_from_results(res)
+    ctx.join_begin(P, juncs, ins)
+    jset = set((int(j["ref_id"]), int(j["left"]), int(j["right"])) for j in juncs)
+    batch = synth.pack_join_side(wl, wl.left, res.junctions)
+    joined = ctx.join_submit(batch)
+    assert len(joined) > 40_000
+    def key(recs, bundle_ids):
+        return sorted((int(bundle_ids[r["bundle"]]), int(r["ref_id"]), int(r["left"]), int(r["flags"]), int(r["mismatches"]), int(r["edit_dist"]),
+                       tuple(int(o) for o in r["ops"][:r["n_ops"]])) for r in recs)
+    whole = key(joined, batch.bundles["read_id"])
+    n_skip = 0
+    for r in joined:
+        ops = [(int(o) & 15, int(o) >> 4) for o in r["ops"][:r["n_ops"]]]
+        assert ops[0][0] == 1 and ops[-1][0] == 1
+        assert sum(l for c, l in ops if c in (1, 3, 13)) == int(batch.bundles["read_len"][r["bundle"]])
+        pos = int(r["left"])
+        for c, l in ops:
+            if c == 11:
+                assert (int(r["ref_id"]), pos - 1, pos + l) in jset, "REF_SKIP that is not in the junction set"
+                n_skip += 1
+            if c in (1, 5, 11):
+                pos += l
+    assert n_skip > 20_000
+    sample = joined[:: max(1, len(joined) // 3000)]
+    mm, ln, nn = _recount_mismatches(wl, batch, sample)          # positions where read and genome are both N may count or not
+    assert ((mm == sample["mismatches"]) | (mm + nn == sample["mismatches"])).all() and (ln == batch.bundles["read_len"][sample["bundle"]]).all()
+    # chunk pipeline: 13 chunks instead of 1
+    monkeypatch.setenv("THB_JOIN_CHUNK_READS", "4096")
+    assert key(ctx.join_submit(batch), batch.bundles["read_id"]) == whole
+    monkeypatch.delenv("THB_JOIN_CHUNK_READS")
+    # shards of the reads, submitted in reverse order (what the multi-GPU join does per rank)
+    got = []
+    nb = batch.n_bundles
+    for lo, hi in [(2 * nb // 3, nb), (nb // 3, 2 * nb // 3), (0, nb // 3)]:
+        h0 = int(batch.bundles["hit_begin"][lo]); h1 = int(batch.bundles["hit_begin"][hi]) if hi < nb else len(batch.hits)
+        e0 = int(batch.bundles["ops_begin"][lo]); e1 = int(batch.bundles["ops_begin"][hi]) if hi < nb else len(batch.ops_ext)
+        bu = batch.bundles[lo:hi].copy(); bu["hit_begin"] -= h0; bu["ops_begin"] -= e0
+        part = synth.PackedJoinBatch(batch.n_segs, batch.read_words, bu, np.ascontiguousarray(batch.seg_count[lo:hi]),
+                                     np.ascontiguousarray(batch.reads[lo:hi]), np.ascontiguousarray(batch.hits[h0:h1]), np.ascontiguousarray(batch.ops_ext[e0:e1]))
+        got += key(ctx.join_submit(part), bu["read_id"])
+    assert sorted(got) == whole
+    ctx.close()

@@ -129,11 +129,12 @@ def batch_c(b: synth.PackedBatch) -> BatchC:
     return s
 
 
-def _copy_records(ptr: Optional[int], n: int, dtype: np.dtype) -> np.ndarray:
+def _copy_records(ptr: Optional[int], n: int, dtype: np.dtype, copy: bool = True) -> np.ndarray:
     if not n:
         return np.zeros(0, dtype=dtype)
     buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    a = np.frombuffer(buf, dtype=dtype, count=n)
+    return a.copy() if copy else a
 
 
 class SegJuncsResults:
@@ -141,11 +142,12 @@ class SegJuncsResults:
         self.junctions, self.deletions, self.insertions, self.fusions = juncs, dels, ins, fus
 
     @classmethod
-    def from_c(cls, r: ResultsC) -> "SegJuncsResults":
-        return cls(_copy_records(r.junctions, r.n_junctions, synth.JUNCTION_DTYPE),
-                   _copy_records(r.deletions, r.n_deletions, synth.JUNCTION_DTYPE),
-                   _copy_records(r.insertions, r.n_insertions, synth.INSERTION_DTYPE),
-                   _copy_records(r.fusions, r.n_fusions, synth.FUSION_DTYPE))
+    def from_c(cls, r: ResultsC, copy: bool = True) -> "SegJuncsResults":
+        """copy=False: views of the context's own (page-locked) result arrays, valid until the next thb_segjuncs_begin."""
+        return cls(_copy_records(r.junctions, r.n_junctions, synth.JUNCTION_DTYPE, copy),
+                   _copy_records(r.deletions, r.n_deletions, synth.JUNCTION_DTYPE, copy),
+                   _copy_records(r.insertions, r.n_insertions, synth.INSERTION_DTYPE, copy),
+                   _copy_records(r.fusions, r.n_fusions, synth.FUSION_DTYPE, copy))
 
 
 _lib = None
@@ -246,10 +248,10 @@ class Context:
     def segjuncs_submit_device(self, b: BatchC) -> None:
         self._check(self.lib.thb_segjuncs_submit_device(self.h, C.byref(b)), "thb_segjuncs_submit_device")
 
-    def segjuncs_finish(self) -> SegJuncsResults:
+    def segjuncs_finish(self, copy: bool = True) -> SegJuncsResults:
         r = ResultsC()
         self._check(self.lib.thb_segjuncs_finish(self.h, C.byref(r)), "thb_segjuncs_finish")
-        return SegJuncsResults.from_c(r)
+        return SegJuncsResults.from_c(r, copy)
 
     def timing(self) -> TimingC:
         t = TimingC()

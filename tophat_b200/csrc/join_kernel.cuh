@@ -33,7 +33,7 @@ struct JoinParams {
 
 struct JoinSets {
   const thb_junction* juncs; uint32_t n_juncs;        // Junction order (junctions.h:39-57)
-  const uint32_t* jidx; uint64_t n_buckets;           // jidx[b] = first junction whose global left lies in 64-base block >= b
+  const uint32_t* jidx; uint64_t n_buckets; int shift; // jidx[b] = first junction whose global left lies in bucket >= b; bucket = 2^shift bases
                                                       // (NULL: fall back to binary search)
   const thb_insertion* ins; uint32_t n_ins;           // (refid, left, length) order (insertions.h:52-67)
 };
@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t junc_bound_idx(const JoinSets& S, uint64_t c
                                                    uint32_t anti, bool upper)
 {
   if (S.jidx == nullptr || (int64_t)left > clen + 32) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
-  const uint64_t b = (cs + (uint64_t)left) >> 6;
+  const uint64_t b = (cs + (uint64_t)left) >> S.shift;
   if (b >= S.n_buckets) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
   uint32_t i = __ldg(S.jidx + b);
   if (upper) { while (i < S.n_juncs && !junc_greater(S.juncs[i], ref, left, right, anti)) ++i; }
@@ -342,11 +342,12 @@ __device__ __forceinline__ void revcomp_read(const uint64_t* F, int n, uint64_t*
   }
 }
 
-// jidx[b] = number of junctions whose global left coordinate lies before 64-base block b (= index of the first one at or after it)
-__global__ void junction_index_kernel(const thb_junction* juncs, uint32_t n, const uint64_t* contig_start, uint32_t* jidx, uint64_t n_buckets)
+// jidx[b] = number of junctions whose global left coordinate lies before bucket b (= index of the first one at or after it);
+// a bucket is 2^shift bases, sized by the host so that there are a few buckets per junction
+__global__ void junction_index_kernel(const thb_junction* juncs, uint32_t n, const uint64_t* contig_start, uint32_t* jidx, uint64_t n_buckets, int shift)
 {
   for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t g0 = b << 6;
+    const uint64_t g0 = b << shift;
     uint32_t lo = 0, hi = n;
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const thb_junction j = juncs[mid];
       if (contig_start[j.ref_id - 1] + (uint64_t)j.left < g0) lo = mid + 1; else hi = mid; }

@@ -38,6 +38,26 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// grow-only page-locked host array for result records (device->host copies at full PCIe speed, no zero fill)
+template <class T> struct PinnedVec {
+  T* p = nullptr; size_t n = 0, cap = 0;
+  cudaError_t resize(size_t m) {
+    if (m > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      const size_t want = m + m / 4 + 1024;
+      cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+      if (e != cudaSuccess) { n = 0; return e; }
+      cap = want;
+    }
+    n = m; return cudaSuccess;
+  }
+  void clear() { n = 0; }
+  size_t size() const { return n; }
+  T* data() { return p; }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+};
+
 struct Staging { DevBuf bundles, seg_count, reads, hits, partner; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; };
 // join pipeline stage: input staging + the chunk's result buffer (its device->host copy overlaps the next chunk's kernels)
 struct JStage { DevBuf bundles, seg_count, reads, hits, ops, out; uint64_t cap_out = 0; cudaEvent_t copied = nullptr, out_free = nullptr; bool out_busy = false; };
@@ -90,15 +110,15 @@ struct thb_ctx {
   int sms = 148;
   Staging stage[2];
   // host results
-  std::vector<thb_junction> h_juncs, h_dels; std::vector<thb_insertion> h_ins; std::vector<thb_fusion> h_fus;
-  std::vector<InsRec> h_insrec;
+  PinnedVec<thb_junction> h_juncs, h_dels; PinnedVec<thb_insertion> h_ins; std::vector<thb_fusion> h_fus;
+  DevBuf d_ins_a, d_ins_b, d_ins_c, d_ins_d, d_ins_out;     // scratch of the insertion reduction
   // accounting
   thb_timing timing{}; uint64_t n_bundles_total = 0, n_hits_total = 0, n_partner_total = 0;
   uint64_t n_ins_out = 0, n_del_out = 0;
   unsigned long long h_ins_count = 0;   // host mirror of *d_ins_count after the last completed launch
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // long_spanning_reads join
-  DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false;
+  DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false; int j_shift = 6;
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
   JoinParams jp{}; bool join_begun = false; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   JStage jstage[2];
@@ -300,6 +320,62 @@ uint64_t algorithmic_bytes(const thb_ctx* ctx, const unsigned long long* cnt)
          cnt[2] * (32ull + 128ull);
 }
 
+// thb_join_begin: order / uniqueness of the uploaded sets and monotonicity of the junctions' global coordinates
+__global__ void join_sets_check_kernel(const thb_junction* juncs, uint64_t n_juncs, const thb_insertion* ins, uint64_t n_ins, RefView ref, uint64_t n_buckets,
+                                       int shift, unsigned int* flags)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_juncs || i < n_ins; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (i < n_juncs) {
+      const thb_junction b = juncs[i];
+      bool mono = b.ref_id >= 1 && b.ref_id <= ref.n_contigs && (uint64_t)b.left <= (uint64_t)ref.contig_len[b.ref_id >= 1 && b.ref_id <= ref.n_contigs ? b.ref_id - 1 : 0] + 63;
+      uint64_t g = 0;
+      if (mono) { g = ref.contig_start[b.ref_id - 1] + b.left; if ((g >> shift) >= n_buckets) mono = false; }
+      if (i) {
+        const thb_junction a = juncs[i - 1];
+        const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.right != b.right ? a.right < b.right : a.antisense < b.antisense;
+        if (!lt) { atomicOr(flags, 1u); flags[1] = (unsigned int)i; }
+        if (mono && a.ref_id >= 1 && a.ref_id <= ref.n_contigs && ref.contig_start[a.ref_id - 1] + a.left > g) mono = false;
+      }
+      if (!mono) atomicOr(flags, 4u);
+    }
+    if (i && i < n_ins) {
+      const thb_insertion a = ins[i - 1], b = ins[i];
+      const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.len < b.len;
+      if (!lt) { atomicOr(flags, 2u); flags[1] = (unsigned int)i; }
+    }
+  }
+}
+
+// insertion reduction (thb_segjuncs_finish): field extraction for the two stable sorts, winner selection, decoding
+__global__ void ins_field_kernel(const InsRec* rec, const uint64_t* idx, uint64_t n, int want_order, uint64_t* key_out, uint64_t* val_out)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = idx ? idx[i] : i;
+    key_out[i] = want_order ? rec[r].order : rec[r].key; val_out[i] = r;
+  }
+}
+__global__ void ins_winner_kernel(const InsRec* rec, const uint64_t* keys_sorted, const uint64_t* idx_sorted, uint64_t n, uint64_t* wkey, uint64_t* wseq,
+                                  unsigned long long* count)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (i && keys_sorted[i - 1] == keys_sorted[i]) continue;       // not the first-inserted record of its key
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    wkey[slot] = keys_sorted[i]; wseq[slot] = rec[idx_sorted[i]].seq;
+  }
+}
+__global__ void ins_decode_kernel(const uint64_t* keys, const uint64_t* seqs, uint64_t n, RefView ref, thb_insertion* out)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t gl1 = keys[i] >> 8; const uint32_t len = (uint32_t)(keys[i] & 0xffu); const uint64_t sq = seqs[i];
+    int lo = 0, hi = (int)ref.n_contigs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ref.contig_start[mid] <= gl1) lo = mid; else hi = mid - 1; }
+    thb_insertion o; o.ref_id = (uint32_t)lo + 1u; o.left = (uint32_t)(gl1 - ref.contig_start[lo]) - 1u; o.len = len;
+    for (int k = 0; k < 20; ++k) o.seq[k] = 0;
+    for (uint32_t k = 0; k < len && k < 19; ++k) { const unsigned c = (unsigned)((sq >> (3 * k)) & 7u); o.seq[k] = c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : c == 3 ? 'T' : 'N'; }
+    out[i] = o;
+  }
+}
+
 // appends the valid records of a gathered (padded) insertion / fusion buffer; padding = all-ones first word
 template <class Rec>
 __global__ void rec_append_kernel(const Rec* src, uint64_t n, Rec* dst, unsigned long long* count, unsigned long long cap, unsigned int* err, unsigned int err_bit)
@@ -386,6 +462,8 @@ void thb_destroy(thb_ctx* ctx)
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
   for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.ops, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
   if (ctx->h_joined) cudaFreeHost(ctx->h_joined);
+  ctx->h_juncs.release(); ctx->h_dels.release(); ctx->h_ins.release();
+  for (DevBuf* b : { &ctx->d_ins_a, &ctx->d_ins_b, &ctx->d_ins_c, &ctx->d_ins_d, &ctx->d_ins_out }) b->release();
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
   delete ctx;
 }
@@ -627,7 +705,7 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
   return THB_OK;
 }
 
-static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, std::vector<thb_junction>& out, uint64_t limit)
+static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit)
 {
   CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8)); CU(ctx->d_count.reserve(64));
   CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
@@ -646,7 +724,7 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, std::vector<thb_j
   CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
   decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_keys_sorted.p, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
   CU(cudaGetLastError()); ctx->own_launches++;
-  out.resize(n);
+  CU(out.resize(n));
   CU(cudaMemcpyAsync(out.data(), ctx->d_decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   return THB_OK;
@@ -665,19 +743,34 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   unsigned long long nins = 0;
   CU(cudaMemcpyAsync(&nins, ctx->d_ins_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
-  ctx->h_insrec.resize(nins);
-  if (nins) { CU(cudaMemcpyAsync(ctx->h_insrec.data(), ctx->d_ins.p, nins * sizeof(InsRec), cudaMemcpyDeviceToHost, ctx->compute)); CU(cudaStreamSynchronize(ctx->compute)); }
-  std::sort(ctx->h_insrec.begin(), ctx->h_insrec.end(), [](const InsRec& a, const InsRec& b) { return a.key != b.key ? a.key < b.key : a.order < b.order; });
+  // Reduced on the device: stable radix sort by processing order, then by (position, length) key -- the first record of every
+  // key run is the one std::set would have kept -- winners compacted, sorted by key, decoded.  (The first version copied every
+  // raw record to the host and std::sort-ed them: 60 ms per 5 M indel-heavy pairs.)
   ctx->h_ins.clear();
-  for (size_t i = 0; i < ctx->h_insrec.size(); ++i) {
-    const InsRec& r = ctx->h_insrec[i];
-    if (i && ctx->h_insrec[i - 1].key == r.key) continue;
-    const uint64_t gl1 = r.key >> 8; const uint32_t len = (uint32_t)(r.key & 0xff);
-    size_t c = std::upper_bound(ctx->h_cstart.begin(), ctx->h_cstart.end(), gl1) - ctx->h_cstart.begin() - 1;
-    thb_insertion o; memset(&o, 0, sizeof o);
-    o.ref_id = (uint32_t)c + 1; o.left = (uint32_t)(gl1 - ctx->h_cstart[c]) - 1u; o.len = len;
-    for (uint32_t k = 0; k < len && k < 19; ++k) o.seq[k] = "ACGTN"[(r.seq >> (3 * k)) & 7];
-    ctx->h_ins.push_back(o);
+  if (nins) {
+    const int n = (int)nins;
+    CU(ctx->d_ins_a.reserve(nins * 8)); CU(ctx->d_ins_b.reserve(nins * 8)); CU(ctx->d_ins_c.reserve(nins * 8)); CU(ctx->d_ins_d.reserve(nins * 8));
+    uint64_t* ka = (uint64_t*)ctx->d_ins_a.p; uint64_t* kb = (uint64_t*)ctx->d_ins_b.p; uint64_t* va = (uint64_t*)ctx->d_ins_c.p; uint64_t* vb = (uint64_t*)ctx->d_ins_d.p;
+    const InsRec* rec = (const InsRec*)ctx->d_ins.p;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ka, kb, va, vb, n, 0, 64, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    ins_field_kernel<<<grid_for(nins, 256), 256, 0, ctx->compute>>>(rec, nullptr, nins, 1, ka, va);                 // ka = order, va = index
+    CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, ka, kb, va, vb, n, 0, 64, ctx->compute));              // vb = indices by order
+    ins_field_kernel<<<grid_for(nins, 256), 256, 0, ctx->compute>>>(rec, vb, nins, 0, ka, va);                      // ka = key of vb[i], va = vb[i]
+    CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, ka, kb, va, vb, n, 0, 64, ctx->compute));              // kb = keys sorted, vb = indices (ties by order)
+    CU(ctx->d_count.reserve(64)); CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
+    ins_winner_kernel<<<grid_for(nins, 256), 256, 0, ctx->compute>>>(rec, kb, vb, nins, ka, va, (unsigned long long*)ctx->d_count.p);   // ka / va = winners' key / seq
+    unsigned long long nw = 0;
+    CU(cudaMemcpyAsync(&nw, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, ka, kb, va, vb, (int)nw, 0, 64, ctx->compute));        // winners in key order
+    CU(ctx->d_ins_out.reserve(nw * sizeof(thb_insertion)));
+    ins_decode_kernel<<<grid_for(nw, 256), 256, 0, ctx->compute>>>(kb, vb, nw, ctx->ref, (thb_insertion*)ctx->d_ins_out.p);
+    CU(cudaGetLastError()); ctx->own_launches += 4;
+    CU(ctx->h_ins.resize(nw));
+    CU(cudaMemcpyAsync(ctx->h_ins.data(), ctx->d_ins_out.p, nw * sizeof(thb_insertion), cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
   }
   // fusions: reduce the appended records by key -- count, minimum edit distance (2787-2803, fusions.h:87-101)
   ctx->h_fus.clear();
@@ -738,36 +831,37 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   if (p->segment_length < 4 || p->segment_length > 255) return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside [4,255]", p->segment_length);
   if (p->max_insertion_length > 19) return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 not supported");
   if ((n_juncs && !juncs) || (n_ins && !ins) || n_juncs >= (1ull << 31) || n_ins >= (1ull << 31)) return fail(ctx, THB_EINVAL, "bad junction / insertion set");
-  for (uint64_t i = 1; i < n_juncs; ++i) {
-    const thb_junction &a = juncs[i - 1], &b = juncs[i];
-    const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.right != b.right ? a.right < b.right : a.antisense < b.antisense;
-    if (!lt) return fail(ctx, THB_EINVAL, "junction set not sorted / unique at %llu", (unsigned long long)i);
-  }
-  for (uint64_t i = 1; i < n_ins; ++i) {
-    const thb_insertion &a = ins[i - 1], &b = ins[i];
-    const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.len < b.len;
-    if (!lt) return fail(ctx, THB_EINVAL, "insertion set not sorted / unique at %llu", (unsigned long long)i);
-  }
   CU(ctx->j_juncs.reserve((n_juncs + 1) * sizeof(thb_junction))); CU(ctx->j_ins.reserve((n_ins + 1) * sizeof(thb_insertion)));
   if (n_juncs) CU(cudaMemcpyAsync(ctx->j_juncs.p, juncs, n_juncs * sizeof(thb_junction), cudaMemcpyHostToDevice, ctx->compute));
   if (n_ins) CU(cudaMemcpyAsync(ctx->j_ins.p, ins, n_ins * sizeof(thb_insertion), cudaMemcpyHostToDevice, ctx->compute));
-  // 64-base bucket index over the junction array (valid when global lefts are monotone, i.e. every junction lies
-  // inside its contig's slot of the image; otherwise the kernels binary-search)
+  // The sets are validated where they now live (a pass over 1.4 M junctions of an hg38-sized run on the host cost more than
+  // the join kernels): strictly increasing in Junction / Insertion order; and, for the bucket index, monotone global lefts
+  // (every junction inside its contig's slot of the image -- otherwise the kernels binary-search).
+  // Bucket size: a power of two >= 64 bases giving about four buckets per junction -- on an hg38-sized image 64-base buckets
+  // would be 48 M entries, rebuilt per thb_join_begin.
+  const uint64_t blocks = ctx->d_nmask.cap / 8;     // 64-base blocks allocated for the image (>= n_blocks)
+  int shift = 6;
+  while (shift < 20 && ((blocks << 6) >> shift) > 4 * std::max<uint64_t>(n_juncs, 1u << 16)) ++shift;
+  const uint64_t nb = ((blocks << 6) >> shift) + 1;
+  ctx->j_shift = shift;
+  CU(ctx->d_count.reserve(64));
+  CU(cudaMemsetAsync(ctx->d_count.p, 0, 16, ctx->compute));
+  unsigned int* vflags = (unsigned int*)ctx->d_count.p;            // [0] bit0 junctions unsorted, bit1 insertions unsorted, bit2 not monotone; [1] first bad index
+  if (n_juncs || n_ins)
+    join_sets_check_kernel<<<grid_for(std::max(n_juncs, n_ins), 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, n_juncs, (const thb_insertion*)ctx->j_ins.p, n_ins,
+                                                                                              ctx->ref, nb, shift, vflags);
+  unsigned int hflags[2] = {0, 0};
+  CU(cudaMemcpyAsync(hflags, vflags, 8, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  if (hflags[0] & 1u) return fail(ctx, THB_EINVAL, "junction set not sorted / unique near %u", hflags[1]);
+  if (hflags[0] & 2u) return fail(ctx, THB_EINVAL, "insertion set not sorted / unique near %u", hflags[1]);
   {
-    const uint64_t nb = ctx->d_nmask.cap / 8;       // blocks allocated for the image (>= n_blocks)
-    bool mono = n_juncs > 0; uint64_t prev_g = 0;
-    for (uint64_t i = 0; i < n_juncs && mono; ++i) {
-      const thb_junction& j = juncs[i];
-      if (j.ref_id < 1 || j.ref_id > ctx->h_cstart.size() || (uint64_t)j.left > (uint64_t)ctx->h_clen[j.ref_id - 1] + 63) { mono = false; break; }
-      const uint64_t g = ctx->h_cstart[j.ref_id - 1] + j.left;
-      if (g < prev_g || (g >> 6) >= nb) mono = false;
-      prev_g = g;
-    }
+    const bool mono = n_juncs > 0 && !(hflags[0] & 4u);
     ctx->j_use_idx = mono;
     if (mono) {
       CU(ctx->j_idx.reserve((nb + 1) * 4));
       junction_index_kernel<<<grid_for(nb + 1, 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, (uint32_t)n_juncs, ctx->ref.contig_start,
-                                                                           (uint32_t*)ctx->j_idx.p, nb);
+                                                                           (uint32_t*)ctx->j_idx.p, nb, shift);
       CU(cudaGetLastError());
       ctx->j_nbuckets = nb;
     }
@@ -799,7 +893,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
   cap_out = std::max<uint64_t>(cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
-  S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets;
+  S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets; S.shift = ctx->j_shift;
   unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f; unsigned long long qn_simple = 0, qn_abut = 0;
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {

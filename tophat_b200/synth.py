@@ -360,7 +360,7 @@ def _make_read_fwd(rng, cfg: SynthConfig, space: _ExonSpace, exonic: np.ndarray,
     nn = rng.random(codes.shape) < cfg.n_rate
     codes = np.where(nn, 4, codes).astype(np.uint8)
     if inv is not None:
-        return codes, emap, inv
+        return codes, emap, inv, chim
     return codes, emap
 
 
@@ -405,6 +405,7 @@ def _gen_chunk(ci: int):
         made = _make_read_fwd(rng, cfg, space, exonic, x0)
         codes_fwd, emap = made[0], made[1]
         inv = made[2] if len(made) > 2 else None
+        chim = made[3] if len(made) > 3 else None
         # A is sequenced forward, B reverse-complemented (fr library); fragment strand decides
         # which one is mate 1.
         rev = which == "B"
@@ -433,7 +434,7 @@ def _gen_chunk(ci: int):
             A["mapped"].append(mh)
             A["unm"].append((sel + base, ~mapped[sel]))
             if cfg.keep_candidates:
-                us = sel[~mapped[sel]]
+                us = sel[~mapped[sel]] if chim is None else sel[~mapped[sel] & ~chim[sel]]     # chimeric reads span two loci: no single-locus candidates
                 if us.size:
                     oku = emap[us] >= 0
                     rid_u, gpos_u, _ = space.to_genome(np.where(oku, emap[us], 0))
