@@ -36,6 +36,7 @@ struct JoinSets {
   const uint32_t* jidx; uint64_t n_buckets; int shift; // jidx[b] = first junction whose global left lies in bucket >= b; bucket = 2^shift bases
                                                       // (NULL: fall back to binary search)
   const thb_insertion* ins; uint32_t n_ins;           // (refid, left, length) order (insertions.h:52-67)
+  const uint32_t* iidx; uint64_t n_ibuckets; int ishift;   // the same kind of bucket index over the insertion array (NULL: binary search)
 };
 
 struct JoinBatchView {
@@ -110,14 +111,16 @@ __device__ __forceinline__ uint32_t junc_bound_idx(const JoinSets& S, uint64_t c
   if (S.jidx == nullptr || (int64_t)left > clen + 32) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
   const uint64_t b = (cs + (uint64_t)left) >> S.shift;
   if (b >= S.n_buckets) return upper ? junc_upper_bound(S, ref, left, right, anti) : junc_lower_bound(S, ref, left, right, anti);
-  uint32_t i = __ldg(S.jidx + b);
-  if (upper) { while (i < S.n_juncs && !junc_greater(S.juncs[i], ref, left, right, anti)) ++i; }
-  else       { while (i < S.n_juncs && junc_less(S.juncs[i], ref, left, right, anti)) ++i; }
-  return i;
+  // every junction of an earlier bucket is smaller, every junction of a later one greater: the bound lies in [jidx[b], jidx[b+1]]
+  // (binary search inside the bucket: indel-dense regions put tens of records into one bucket, profiles/README.md)
+  uint32_t lo = __ldg(S.jidx + b), hi = __ldg(S.jidx + b + 1);
+  if (upper) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_greater(S.juncs[mid], ref, left, right, anti)) hi = mid; else lo = mid + 1; } }
+  else       { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (junc_less(S.juncs[mid], ref, left, right, anti)) lo = mid + 1; else hi = mid; } }
+  return lo;
 }
 
 // std::set<Insertion>::upper_bound(Insertion(ref, left, <string of length len>))
-__device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t len)
+__device__ __forceinline__ uint32_t ins_upper_bound_bs(const JoinSets& S, uint32_t ref, uint32_t left, uint32_t len)
 {
   uint32_t lo = 0, hi = S.n_ins;
   while (lo < hi) {
@@ -130,6 +133,22 @@ __device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint32_t 
 }
 
 // head word 3 of a thb_jhit: flags (low nibble) | n_ops << 4 | ops_index << 8 | mismatches << 16 | splice_mms << 24
+// the same bound through the bucket index: one table load + a scan of the few insertions in the bucket
+__device__ __forceinline__ uint32_t ins_upper_bound(const JoinSets& S, uint64_t cs, int64_t clen, uint32_t ref, uint32_t left, uint32_t len)
+{
+  if (S.iidx == nullptr || (int64_t)left > clen + 32) return ins_upper_bound_bs(S, ref, left, len);
+  const uint64_t b = (cs + (uint64_t)left) >> S.ishift;
+  if (b >= S.n_ibuckets) return ins_upper_bound_bs(S, ref, left, len);
+  uint32_t lo = __ldg(S.iidx + b), hi = __ldg(S.iidx + b + 1);
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1; const thb_insertion& a = S.ins[mid];
+    bool greater;
+    if (a.ref_id != ref) greater = a.ref_id > ref; else if (a.left != left) greater = a.left > left; else greater = a.len > len;
+    if (greater) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ void load_whit(WHit& w, const JoinBatchView& bv, uint32_t hit, uint32_t ops_begin, int seq_pos, int seq_len)
 {
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(bv.hits + hit));
@@ -268,8 +287,8 @@ __device__ __forceinline__ int insertion_closure(const RefView& ref, const JoinS
                                                  int curr_seq_pos, InsClosure& out)
 {
   const uint32_t lbnd = (uint32_t)(pright - 4), rbnd = (uint32_t)(cleft + 4);
-  uint32_t it = ins_upper_bound(S, ref_id, lbnd, 0u);
-  const uint32_t ub = ins_upper_bound(S, ref_id, rbnd, (uint32_t)P.max_ins);
+  uint32_t it = ins_upper_bound(S, cs, clen, ref_id, lbnd, 0u);
+  const uint32_t ub = ins_upper_bound(S, cs, clen, ref_id, rbnd, (uint32_t)P.max_ins);
   bool found = false;
   for (; it != ub && it < S.n_ins; ++it) {
     const thb_insertion& I = S.ins[it];
@@ -344,12 +363,13 @@ __device__ __forceinline__ void revcomp_read(const uint64_t* F, int n, uint64_t*
 
 // jidx[b] = number of junctions whose global left coordinate lies before bucket b (= index of the first one at or after it);
 // a bucket is 2^shift bases, sized by the host so that there are a few buckets per junction
-__global__ void junction_index_kernel(const thb_junction* juncs, uint32_t n, const uint64_t* contig_start, uint32_t* jidx, uint64_t n_buckets, int shift)
+template <class Rec>
+__global__ void junction_index_kernel(const Rec* juncs, uint32_t n, const uint64_t* contig_start, uint32_t* jidx, uint64_t n_buckets, int shift)
 {
   for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t g0 = b << shift;
     uint32_t lo = 0, hi = n;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const thb_junction j = juncs[mid];
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const Rec j = juncs[mid];
       if (contig_start[j.ref_id - 1] + (uint64_t)j.left < g0) lo = mid + 1; else hi = mid; }
     jidx[b] = lo;
   }

@@ -119,6 +119,7 @@ struct thb_ctx {
   uint32_t own_launches = 0;        // every kernel of this library launched since thb_segjuncs_begin
   // long_spanning_reads join
   DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false; int j_shift = 6;
+  DevBuf j_iidx; uint64_t j_nibuckets = 0; bool j_use_iidx = false; int j_ishift = 6;
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
   JoinParams jp{}; bool join_begun = false; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   JStage jstage[2];
@@ -322,7 +323,7 @@ uint64_t algorithmic_bytes(const thb_ctx* ctx, const unsigned long long* cnt)
 
 // thb_join_begin: order / uniqueness of the uploaded sets and monotonicity of the junctions' global coordinates
 __global__ void join_sets_check_kernel(const thb_junction* juncs, uint64_t n_juncs, const thb_insertion* ins, uint64_t n_ins, RefView ref, uint64_t n_buckets,
-                                       int shift, unsigned int* flags)
+                                       int shift, uint64_t n_ibuckets, int ishift, unsigned int* flags)
 {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_juncs || i < n_ins; i += (uint64_t)gridDim.x * blockDim.x) {
     if (i < n_juncs) {
@@ -338,10 +339,18 @@ __global__ void join_sets_check_kernel(const thb_junction* juncs, uint64_t n_jun
       }
       if (!mono) atomicOr(flags, 4u);
     }
-    if (i && i < n_ins) {
-      const thb_insertion a = ins[i - 1], b = ins[i];
-      const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.len < b.len;
-      if (!lt) { atomicOr(flags, 2u); flags[1] = (unsigned int)i; }
+    if (i < n_ins) {
+      const thb_insertion b = ins[i];
+      bool mono = b.ref_id >= 1 && b.ref_id <= ref.n_contigs && (uint64_t)b.left <= (uint64_t)ref.contig_len[b.ref_id >= 1 && b.ref_id <= ref.n_contigs ? b.ref_id - 1 : 0] + 63;
+      uint64_t g = 0;
+      if (mono) { g = ref.contig_start[b.ref_id - 1] + b.left; if ((g >> ishift) >= n_ibuckets) mono = false; }
+      if (i) {
+        const thb_insertion a = ins[i - 1];
+        const bool lt = a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.left != b.left ? a.left < b.left : a.len < b.len;
+        if (!lt) { atomicOr(flags, 2u); flags[1] = (unsigned int)i; }
+        if (mono && a.ref_id >= 1 && a.ref_id <= ref.n_contigs && ref.contig_start[a.ref_id - 1] + a.left > g) mono = false;
+      }
+      if (!mono) atomicOr(flags, 8u);
     }
   }
 }
@@ -456,7 +465,7 @@ void thb_destroy(thb_ctx* ctx)
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
-                     &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx }) b->release();
+                     &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx, &ctx->j_iidx }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
@@ -844,12 +853,16 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   while (shift < 20 && ((blocks << 6) >> shift) > 4 * std::max<uint64_t>(n_juncs, 1u << 16)) ++shift;
   const uint64_t nb = ((blocks << 6) >> shift) + 1;
   ctx->j_shift = shift;
+  int ishift = 6;
+  while (ishift < 20 && ((blocks << 6) >> ishift) > 4 * std::max<uint64_t>(n_ins, 1u << 16)) ++ishift;
+  const uint64_t nib = ((blocks << 6) >> ishift) + 1;
+  ctx->j_ishift = ishift;
   CU(ctx->d_count.reserve(64));
   CU(cudaMemsetAsync(ctx->d_count.p, 0, 16, ctx->compute));
   unsigned int* vflags = (unsigned int*)ctx->d_count.p;            // [0] bit0 junctions unsorted, bit1 insertions unsorted, bit2 not monotone; [1] first bad index
   if (n_juncs || n_ins)
     join_sets_check_kernel<<<grid_for(std::max(n_juncs, n_ins), 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, n_juncs, (const thb_insertion*)ctx->j_ins.p, n_ins,
-                                                                                              ctx->ref, nb, shift, vflags);
+                                                                                              ctx->ref, nb, shift, nib, ishift, vflags);
   unsigned int hflags[2] = {0, 0};
   CU(cudaMemcpyAsync(hflags, vflags, 8, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
@@ -860,10 +873,19 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
     ctx->j_use_idx = mono;
     if (mono) {
       CU(ctx->j_idx.reserve((nb + 1) * 4));
-      junction_index_kernel<<<grid_for(nb + 1, 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, (uint32_t)n_juncs, ctx->ref.contig_start,
-                                                                           (uint32_t*)ctx->j_idx.p, nb, shift);
+      junction_index_kernel<thb_junction><<<grid_for(nb + 1, 256), 256, 0, ctx->compute>>>((const thb_junction*)ctx->j_juncs.p, (uint32_t)n_juncs, ctx->ref.contig_start,
+                                                                                         (uint32_t*)ctx->j_idx.p, nb, shift);
       CU(cudaGetLastError());
       ctx->j_nbuckets = nb;
+    }
+    const bool imono = n_ins > 0 && !(hflags[0] & 8u);
+    ctx->j_use_iidx = imono;
+    if (imono) {
+      CU(ctx->j_iidx.reserve((nib + 1) * 4));
+      junction_index_kernel<thb_insertion><<<grid_for(nib + 1, 256), 256, 0, ctx->compute>>>((const thb_insertion*)ctx->j_ins.p, (uint32_t)n_ins, ctx->ref.contig_start,
+                                                                                           (uint32_t*)ctx->j_iidx.p, nib, ishift);
+      CU(cudaGetLastError());
+      ctx->j_nibuckets = nib;
     }
   }
   CU(cudaStreamSynchronize(ctx->compute));
@@ -894,6 +916,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
   ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
   S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets; S.shift = ctx->j_shift;
+  S.iidx = ctx->j_use_iidx ? (const uint32_t*)ctx->j_iidx.p : nullptr; S.n_ibuckets = ctx->j_nibuckets; S.ishift = ctx->j_ishift;
   unsigned long long n = 0; unsigned long long cnt[3] = {0, 0, 0}; float kms = 0.f; unsigned long long qn_simple = 0, qn_abut = 0;
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
