@@ -47,5 +47,38 @@ def main():
                      if os.path.exists(os.path.join(out, "segment." + k))})
 
 
+JOIN_CASES = {
+    # long_spanning_reads: records of the reference binary (qname, contig, pos, cigar, flag, NM) per mate side
+    "join_splice_indel": (dict(contig_lens=(200_000, 80_000), n_pairs=1500, seed=111, indel_prob=0.4, keep_truth=True), 50, 20),
+}
+
+
+def main_join():
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, im, isd) in JOIN_CASES.items():
+        out = os.path.join(gdir, name)
+        os.makedirs(out, exist_ok=True)
+        wl = synth.generate(synth.SynthConfig(**kw))
+        with tempfile.TemporaryDirectory() as td:
+            files = synth.write_pipeline_files(wl, td)
+            nseg = len(wl.left.seg_hits)
+            bams = pyoracle.make_bams(files, td, nseg)
+            outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg,
+                                              opts=pyoracle.tophat_common_opts(im, isd))
+            jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+            for side in ("left", "right"):
+                bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=side, tag=".ref", opts=pyoracle.tophat_common_opts(im, isd))
+                _, recs = pyoracle.read_bam(bam)
+                with open(os.path.join(out, side + ".records.tsv"), "w") as f:
+                    for r in recs:          # file order = the reference's output order
+                        f.write("%s\t%s\t%d\t%s\t%d\t%d\n" % (r[0], r[2], r[3], r[5], r[1], r[11]["NM"]))
+                print(name, side, len(recs), "records")
+        with open(os.path.join(out, "config.json"), "w") as f:
+            json.dump(dict(synth=kw, inner_dist_mean=im, inner_dist_std_dev=isd, generator="scripts/make_golden.py",
+                           binary="oracle/_ref/segment_juncs + juncs_db + long_spanning_reads (TopHat 2.1.2, -p1)"), f, indent=1)
+
+
 if __name__ == "__main__":
     main()
+    main_join()

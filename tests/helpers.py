@@ -14,7 +14,40 @@ LIBTYPE = {"fr-unstranded": 1, "fr-firststrand": 2, "fr-secondstrand": 3}
 
 
 def golden_cases():
-    return sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "config.json")))
+    """segment_juncs goldens (outputs of the reference binary); the join goldens are the join_* directories"""
+    return sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "segment.juncs")))
+
+
+def join_golden_cases():
+    return sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "left.records.tsv")))
+
+
+def check_join_golden(name):
+    """Both stages through the C ABI on the golden's workload; the joined alignments (after the worker's sort / unique / filters)
+    must equal the records the reference's long_spanning_reads wrote (tests/golden/<name>/{left,right}.records.tsv)."""
+    from test_gpu_join import joined_to_keys
+    d = os.path.join(GOLDEN, name)
+    cfg = json.load(open(os.path.join(d, "config.json")))
+    kw = dict(cfg["synth"]); kw["contig_lens"] = tuple(kw["contig_lens"])
+    wl = synth.generate(synth.SynthConfig(**kw))
+    P = capi.default_params(inner_dist_mean=cfg["inner_dist_mean"], inner_dist_std_dev=cfg["inner_dist_std_dev"])
+    ctx = capi.Context(0); ctx.ref_upload(wl.ref)
+    res, _ = gpu_segjuncs(P, wl.ref, pack_both(wl), ctx)
+    juncs, ins = capi.join_sets_from_results(res)
+    ctx.join_begin(P, juncs, ins)
+    names = wl.ref.names
+    total = 0
+    for sname, side in (("left", wl.left), ("right", wl.right)):
+        batch = synth.pack_join_side(wl, side, res.junctions)
+        got = joined_to_keys(ctx.join_submit(batch), batch, P)
+        want = set()
+        for line in open(os.path.join(d, sname + ".records.tsv")):
+            q, c, pos, cig, flag, nm = line.rstrip("\n").split("\t")
+            want.add((int(q), names.index(c) + 1, int(pos), cig, int(flag), int(nm)))
+        assert got == want, "%s %s: only ours %r; only reference %r" % (name, sname, sorted(got - want)[:3], sorted(want - got)[:3])
+        total += len(want)
+    ctx.close()
+    assert total > 500
 
 
 def load_golden(name):

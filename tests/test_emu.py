@@ -132,3 +132,8 @@ def test_emu_allgather_world1():
     import subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "allgather_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "allgather ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", helpers.join_golden_cases())
+def test_emu_join_golden(emu_lib, name):
+    helpers.check_join_golden(name)

@@ -162,3 +162,64 @@ def test_join_properties_at_scale(monkeypatch):
         got += key(ctx.join_submit(part), bu["read_id"])
     assert sorted(got) == whole
     ctx.close()
+
+
+def _manual_join_batch(reads):
+    """reads: list of dict(seq=ascii, hits=[[(ref_id, left, len, mism, anti)] per segment]) -> PackedJoinBatch (single-match hits)."""
+    nseg = max(len(r["hits"]) for r in reads)
+    L = max(len(r["seq"]) for r in reads); rw = (L + 63) // 64
+    bundles = np.zeros(len(reads), dtype=synth.JBUNDLE_DTYPE); segc = np.zeros((len(reads), nseg), dtype="<u2")
+    rd = np.zeros((len(reads), 3 * rw), dtype="<u8"); full = []
+    for i, r in enumerate(reads):
+        codes = synth.codes_from_ascii(r["seq"]); pad = np.zeros((1, L), dtype=np.uint8); pad[0, :len(codes)] = codes
+        rd[i] = synth.pack_reads(pad, rw)[0]
+        bundles[i]["read_id"] = i + 1; bundles[i]["hit_begin"] = len(full); bundles[i]["read_len"] = len(codes); bundles[i]["n_segs"] = len(r["hits"])
+        for s, hs in enumerate(r["hits"]):
+            segc[i, s] = len(hs)
+            for (rid, left, ln, mm, anti) in hs:
+                full.append((rid, left, 1, (1 if anti else 0) | (2 if s == len(r["hits"]) - 1 else 0), mm, 0, [(ln << 4) | 1] + [0] * 8))
+    fa = np.array([(a, b, c, d, e, f, tuple(g)) for (a, b, c, d, e, f, g) in full], dtype=synth.JHIT_FULL_DTYPE) if full else np.zeros(0, dtype=synth.JHIT_FULL_DTYPE)
+    heads, ext, ops_begin = synth.pack_join_hits(fa, bundles["hit_begin"].astype(np.int64))
+    bundles["ops_begin"] = ops_begin
+    return synth.PackedJoinBatch(nseg, rw, bundles, np.ascontiguousarray(segc), np.ascontiguousarray(rd), heads, ext)
+
+
+def test_join_guards_and_budget():
+    """join_segments_for_read's multihit guard (long_spanning_reads.cpp:2624-2632: a read with more than max_seg_multihits hits in
+    a segment is skipped under bowtie2) and dfs_seg_hits' budget of 10,000 complete chains per first-segment hit (2647, 2236):
+    checked through the chain counter of the C ABI; plus the exact abutting read, an empty batch and a one-segment read."""
+    rng = np.random.default_rng(12)
+    ref = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 400_000)])
+    refimg = synth.build_ref_image(["c1"], [synth.codes_from_ascii(ref)])
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    ctx = capi.Context(0); ctx.ref_upload(refimg)
+    ctx.join_begin(P, np.zeros(0, dtype=synth.JUNCTION_DTYPE), np.zeros(0, dtype=synth.INSERTION_DTYPE))
+    read = ref[1000:1101]
+    exact = [[(1, 1000, 25, 0, 0)], [(1, 1025, 25, 0, 0)], [(1, 1050, 25, 0, 0)], [(1, 1075, 26, 0, 0)]]
+    # (a) exact read -> one alignment 101M; (b) 41 hits in segment 1 -> skipped; (c) the same with 40 -> processed
+    many = lambda k: [(1, 1025, 25, 0, 0)] + [(1, 5000 + 40 * j, 25, 0, 0) for j in range(k - 1)]
+    b = _manual_join_batch([dict(seq=read, hits=exact),
+                            dict(seq=read, hits=[exact[0], many(41), exact[2], exact[3]]),
+                            dict(seq=read, hits=[exact[0], many(40), exact[2], exact[3]])])
+    out = ctx.join_submit(b)
+    got = sorted((int(r["bundle"]), int(r["left"]), int(r["n_ops"]), int(r["ops"][0])) for r in out)
+    assert got == [(0, 1000, 1, (101 << 4) | 1), (2, 1000, 1, (101 << 4) | 1)]
+    # (d) budget: 2 first-segment hits x 25^3 mutually compatible chains each -> 10,000 leaves per first-segment hit
+    spaced = lambda base, ln: [(1, base + 200 * j, ln, 0, 0) for j in range(25)]
+    b = _manual_join_batch([dict(seq=read, hits=[[(1, 1000, 25, 0, 0), (1, 1200, 25, 0, 0)], spaced(10_000, 25), spaced(50_000, 25), spaced(100_000, 26)])])
+    assert len(ctx.join_submit(b)) == 0
+    t = ctx.join_timing()
+    assert t.n_chains == 1 + 1 + 20_000, t.n_chains          # counters accumulate since thb_join_begin: (a) + (c) + the budgeted read
+    # (e) empty batch, one-segment read
+    e = _manual_join_batch([dict(seq=read, hits=exact)])
+    empty = synth.PackedJoinBatch(e.n_segs, e.read_words, e.bundles[:0], e.seg_count[:0], e.reads[:0], e.hits[:0], e.ops_ext[:0])
+    assert len(ctx.join_submit(empty)) == 0
+    one = _manual_join_batch([dict(seq=ref[2000:2030], hits=[[(1, 2000, 30, 0, 0)]])])
+    out = ctx.join_submit(one)
+    assert len(out) == 1 and int(out[0]["left"]) == 2000 and int(out[0]["ops"][0]) == (30 << 4) | 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", helpers.join_golden_cases())
+def test_join_matches_reference_golden(name):
+    helpers.check_join_golden(name)
