@@ -197,7 +197,8 @@ int thb_segjuncs_fusion_ignore(thb_ctx* ctx, const uint32_t* ref_ids, uint32_t n
  * GC-AG, AT-AC (2051-2377, 1669-1696), and find_fusions/detect_fusion (2976-3291, 2629-2805). */
 int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* host_batch);
 
-/* Same, for a batch whose arrays already live in DEVICE memory of ctx's device.               */
+/* Same, for a batch whose arrays already live in DEVICE memory of ctx's device (every array 16-byte aligned:
+ * the kernels use 128-bit loads; cudaMalloc / torch allocations are).                                        */
 int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* device_batch);
 
 /* Sorts and de-duplicates the accumulated sets (the std::set semantics of 4907-4922, insertion

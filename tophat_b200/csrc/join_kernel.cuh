@@ -671,13 +671,13 @@ chain_merge_abut_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue 
 // Every lane walks the same phase sequence with an `alive` predicate and the warp re-converges at each __syncwarp():
 // the closure searches (equal-length binary searches) and the consistency re-read then run with all the lanes that
 // need them side by side (profiles/r1h: 4 of 32 lanes active in the straightforward per-thread form).
-template <bool CLOSURES, int MINB>
+template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, ChainQueue q, JoinOut o)
 {
   unsigned n_closures = 0, n_emit = 0;
-  unsigned long long nq = CLOSURES ? *q.count : *q.abut_count; if (nq > q.cap) nq = q.cap;
-  const uint32_t* __restrict__ qtasks = CLOSURES ? q.tasks : q.abut_tasks;
+  unsigned long long nq = *q.count; if (nq > q.cap) nq = q.cap;
+  const uint32_t* __restrict__ qtasks = q.tasks;
   const unsigned lane = threadIdx.x & 31u;
   for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x - lane; base < nq; base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long ti = base + lane;
@@ -783,11 +783,10 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
           else if (!(dist == 0 && same_strand)) multi = false;     // only a fusion could close this gap (1592-1819)
         }
       }
-      if (!CLOSURES && kind != 0) multi = false;   // cannot happen: the abutting queue only holds dist == 0 chains
       __syncwarp();
       // phase 2: junction / deletion closure
       JuncClosure jc; jc.dtl = 0; jc.glen = 0; jc.anti = false; jc.new_diff = 0;
-      if (CLOSURES && on && multi && kind == 2) {
+      if (on && multi && kind == 2) {
         n_closures++;
         const int rc = junction_closure(ref, S, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, jc);
         if (rc <= 0) multi = false; else { found = true; mismatch = jc.new_diff; }
@@ -795,7 +794,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       __syncwarp();
       // phase 3: insertion closure
       InsClosure ic; ic.itpr = 0; ic.len = 0; ic.mismatch = 0;
-      if (CLOSURES && on && multi && kind == 1) {
+      if (on && multi && kind == 1) {
         n_closures++;
         const int rc = insertion_closure(ref, S, P, R, cs, clen, prev.ref, pright, curr.left, prml, clml, prev.seq_pos + prev.seq_len, curr.seq_pos, ic);
         if (rc <= 0) multi = false; else { found = true; mismatch = ic.mismatch; }

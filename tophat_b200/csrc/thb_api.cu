@@ -938,7 +938,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     // closure kernel -- both are latency-bound, so residency is traded against spills
     chain_merge_abut_kernel<false, 8><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
     CU(cudaEventRecord(ctx->kev[4], ctx->compute));
-    chain_merge_kernel<true, 6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    chain_merge_kernel<6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
     ctx->jtiming.launches += 4;
@@ -1146,6 +1146,9 @@ int thb_segjuncs_allgather(thb_ctx* ctx)
   CU(cudaStreamSynchronize(ctx->compute));
   unsigned long long mx[4] = {0, 0, 0, 0}, tot[4] = {0, 0, 0, 0};
   for (int r = 0; r < W; ++r) for (int k = 0; k < 4; ++k) { const unsigned long long c = counts[4 + 4 * r + k]; mx[k] = std::max(mx[k], c); tot[k] += c; }
+  // key sections are padded to an even number of 8-byte keys so that the record sections behind them stay 16-byte aligned for
+  // every world size (FusRec is loaded with 128-bit accesses); padding keys are HS_EMPTY and ignored on insertion
+  mx[0] = (mx[0] + 1) & ~1ull; mx[1] = (mx[1] + 1) & ~1ull;
   if (counts[2] > ctx->cap_ins) return fail(ctx, THB_ESTATE, "insertion buffer overflow before the all-gather");
   if (counts[3] > ctx->cap_fus) return fail(ctx, THB_ESTATE, "fusion buffer overflow before the all-gather");
   // staging: [juncs send | dels send | ins send | fusion send] and the W-fold receive areas
