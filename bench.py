@@ -112,18 +112,19 @@ class ReferenceArm:
         self.tjin = pyoracle.make_join_inputs(tiny, self.tfiles, self.touts, self.tdir, self.nseg, fast=True)
         log("[bench] reference arm inputs for %d pairs ready in %.1f s" % (self.sample_pairs, time.time() - t))
 
-    def _run(self, files, bams, jin, outdir, threads):
+    def _run(self, files, bams, jin, outdir, threads, bins=None, tag=""):
+        sj, lsr = bins if bins else (self.sj, self.lsr)
         t = time.perf_counter()
-        outs = self.py.run_segment_juncs(self.sj, files, bams, outdir, self.nseg, opts=self.opts, threads=threads)
+        outs = self.py.run_segment_juncs(sj, files, bams, outdir, self.nseg, opts=self.opts, threads=threads, tag=tag)
         for side in ("left", "right"):
-            self.py.run_long_spanning_reads(self.lsr, files, bams, jin, outs, outdir, self.nseg, side=side, opts=self.opts, threads=threads)
+            self.py.run_long_spanning_reads(lsr, files, bams, jin, outs, outdir, self.nseg, side=side, opts=self.opts, threads=threads, tag=tag)
         return time.perf_counter() - t
 
-    def startup(self) -> float:
-        return min(self._run(self.tfiles, self.tbams, self.tjin, self.tdir, 1) for _ in range(2))
+    def startup(self, bins=None) -> float:
+        return min(self._run(self.tfiles, self.tbams, self.tjin, self.tdir, 1, bins, ".b200" if bins else "") for _ in range(2))
 
-    def step(self) -> float:
-        return self._run(self.files, self.bams, self.jin, self.dir, self.threads)
+    def step(self, bins=None) -> float:
+        return self._run(self.files, self.bams, self.jin, self.dir, self.threads, bins, ".b200" if bins else "")
 
     def close(self):
         shutil.rmtree(self.dir, ignore_errors=True)
@@ -442,10 +443,28 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 threads = usable_threads(args.ref_pairs)
                 swl = make_workload(args.ref_pairs, 0, os.cpu_count() or 1, keep_truth=True)
                 arm = ReferenceArm(swl, args.ref_pairs, threads)
+                cli = None
                 try:
                     st = arm.startup(); arm.step(); wall = arm.step()
+                    # the drop-in executables themselves (tophat_b200/bin, C++ hosts over the C ABI) on the very same files: BAM
+                    # decode, bundle building, GPU work, text / BAM output -- what a tophat.py run would see per stage
+                    try:
+                        from tophat_b200 import build as _b
+                        ours = (os.path.join(_b.BIN_DIR, "segment_juncs"), os.path.join(_b.BIN_DIR, "long_spanning_reads"))
+                        if all(os.access(x, os.X_OK) for x in ours):
+                            st_o = arm.startup(ours); arm.step(ours); wall_o = arm.step(ours)
+                            same = all(open(os.path.join(arm.dir, "segment.b200." + k)).read() == open(os.path.join(arm.dir, "segment." + k)).read()
+                                       for k in ("juncs", "insertions", "deletions"))
+                            cli = {"value": 2 * arm.sample_pairs / max(wall_o - st_o, 1e-6), "unit": UNIT, "wall_s": wall_o, "startup_s": st_o,
+                                   "reference_wall_s": wall, "reference_startup_s": st, "segment_files_identical_to_reference": same,
+                                   "note": "our segment_juncs + long_spanning_reads executables on the reference arm's sample files; "
+                                           "start-up (CUDA context, FASTA load, image upload) measured on a 1-pair input and excluded like the reference's"}
+                    except Exception as e:
+                        cli = {"value": None, "note": "failed: %r" % (e,)}
                 finally:
                     arm.close()
+                if cli is not None:
+                    line["drop_in_cli"] = cli
                 reads = 2 * arm.sample_pairs
                 line["cpu_baseline"] = {"value": reads / max(wall - st, 1e-6), "unit": UNIT, "cores": threads, "kind": "reference",
                                         "sample": "%d pairs (%d reads) from the same generator and reference; oracle/_ref segment_juncs + "
