@@ -6,6 +6,8 @@
 // print_bamhit (1888-2093).  There is no CPU fallback for the join itself.
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -170,22 +172,37 @@ int main(int argc, char** argv)
   std::vector<thb_join_bundle> bundles; std::vector<uint16_t> segc; std::vector<uint64_t> rplanes; std::vector<thb_jhit> hits; std::vector<thb_jops> ops_ext; std::vector<Pending> pend;
   std::vector<thb_jhit_full> read_hits;
   uint64_t n_reads = 0, n_out = 0;
+  double submit_s = 0, post_s = 0;           // TOPHAT_GPU_STATS: time inside thb_join_submit / in sorting, SAM fields and BAM output
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   auto flush = [&]() {
     if (bundles.empty()) return;
+    const auto f0 = now();
     // reads of one batch share read_words = 4 (reads up to 255 bases)
     thb_join_batch jb; memset(&jb, 0, sizeof jb);
     jb.n_bundles = (uint32_t)bundles.size(); jb.n_segs = (uint32_t)nseg; jb.read_words = 4; jb.bundles = bundles.data(); jb.seg_count = segc.data();
     jb.reads = rplanes.data(); jb.n_hits = hits.size(); jb.hits = hits.data(); jb.n_ops_ext = ops_ext.size(); jb.ops_ext = ops_ext.data();
     const thb_joined* out = nullptr; uint64_t no = 0;
     if (thb_join_submit(ctx, &jb, &out, &no) != THB_OK) die("Error: thb_join_submit: %s", thb_last_error(ctx));
+    const auto f1 = now(); submit_s += secs(f0, f1);
     std::vector<std::vector<Joined>> per(bundles.size());
     for (uint64_t i = 0; i < no; ++i) {
       const thb_joined& j = out[i]; Joined J; J.ref_id = j.ref_id; J.left = j.left; J.anti = (j.flags & THB_HIT_ANTISENSE) != 0;
       J.asplice = (j.flags & THB_JHIT_ANTISENSE_SPLICE) != 0; J.mism = j.mismatches; J.edit = j.edit_dist; J.smm = j.splice_mms;
       J.ops.assign(j.ops, j.ops + j.n_ops); per[j.bundle].push_back(std::move(J));
     }
+    // the records of the batch are built on -p threads (each a contiguous slice of the reads, so the output order is kept),
+    // then handed to the writer, which deflates the BGZF blocks in parallel too
+    { std::lock_guard<std::mutex> l(rtm);
+      ref2tid.assign(rt.size() + 1, -1);
+      for (uint32_t id = 1; id <= rt.size(); ++id) ref2tid[id] = bw.target_id(rt.name(id)); }
+    const int T = std::max(1, std::min(o.num_threads, 64));
+    std::vector<BamWriter::RecordPart> parts((size_t)T);
+    auto build_slice = [&](int t) {
+    BamWriter::RecordPart& part = parts[(size_t)t];
     std::vector<uint8_t> aux; std::vector<uint32_t> bcig; std::string MD;
-    for (size_t b = 0; b < bundles.size(); ++b) {
+    const size_t nbu = bundles.size();
+    for (size_t b = nbu * (size_t)t / (size_t)T; b < nbu * (size_t)(t + 1) / (size_t)T; ++b) {
       std::vector<Joined>& v = per[b];
       std::sort(v.begin(), v.end(), joined_less);
       v.erase(std::unique(v.begin(), v.end(), joined_equal), v.end());
@@ -233,13 +250,19 @@ int main(int argc, char** argv)
         BamWriter::aux_int(aux, "NM", (int)J.mism + gap);
         if (has_splice) BamWriter::aux_char(aux, "XS", J.asplice ? '-' : '+');
         bcig.clear(); for (uint32_t op : J.ops) bcig.push_back(((op >> 4) << 4) | (uint32_t)bam_op((int)(op & 15)));
-        if (ref2tid.size() < rt.size() + 1) { ref2tid.assign(rt.size() + 1, -2); }
-        int& tid = ref2tid[J.ref_id]; if (tid == -2) tid = bw.target_id(rt.name(J.ref_id));
-        bw.write(rd.name, pend[b].id, J.anti ? 0x10 : 0, tid, J.left, 255, bcig, seq, quals, aux);
-        ++n_out;
+        const int tid = J.ref_id < ref2tid.size() ? ref2tid[J.ref_id] : -1;
+        const size_t before = part.bytes.size();
+        BamWriter::encode(part.bytes, rd.name, J.anti ? 0x10 : 0, tid, J.left, 255, bcig, seq, quals, aux);
+        part.sizes.push_back((uint32_t)(part.bytes.size() - before)); part.ids.push_back(pend[b].id);
       }
     }
+    };
+    if (T == 1) build_slice(0);
+    else { std::vector<std::thread> th; for (int t = 1; t < T; ++t) th.emplace_back(build_slice, t); build_slice(0); for (auto& x : th) x.join(); }
+    for (const auto& part : parts) n_out += part.sizes.size();
+    bw.append_records(parts, T);
     bundles.clear(); segc.clear(); rplanes.clear(); hits.clear(); ops_ext.clear(); pend.clear();
+    post_s += secs(f1, now());
   };
 
   // JoinSegmentsWorker::operator() (2671-2845)
@@ -299,8 +322,10 @@ int main(int argc, char** argv)
   if (getenv("TOPHAT_GPU_STATS")) {
     thb_join_timing tm; thb_join_last_timing(ctx, &tm);
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-    fprintf(stderr, "{\"gpu_stats\": {\"reads\": %llu, \"records\": %llu, \"ref_load_s\": %.3f, \"join_s\": %.3f, \"kernel_ms\": %.3f, \"chains\": %llu, \"closures\": %llu}}\n",
-            (unsigned long long)n_reads, (unsigned long long)n_out, sec(t0, t1), sec(t1, t2), tm.kernel_ms, (unsigned long long)tm.n_chains, (unsigned long long)tm.n_closures);
+    fprintf(stderr, "{\"gpu_stats\": {\"reads\": %llu, \"records\": %llu, \"ref_load_s\": %.3f, \"join_s\": %.3f, \"submit_s\": %.3f, \"post_s\": %.3f, "
+                    "\"kernel_ms\": %.3f, \"chains\": %llu, \"closures\": %llu}}\n",
+            (unsigned long long)n_reads, (unsigned long long)n_out, sec(t0, t1), sec(t1, t2), submit_s, post_s, tm.kernel_ms, (unsigned long long)tm.n_chains,
+            (unsigned long long)tm.n_closures);
   }
   thb_destroy(ctx);
   return 0;

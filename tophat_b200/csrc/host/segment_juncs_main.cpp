@@ -37,7 +37,8 @@ struct Batch {
   void clear() { bundles.clear(); seg_count.clear(); reads4.clear(); hits.clear(); partner.clear(); max_len = 0; }
 };
 
-struct Stats { uint64_t bundles = 0, hits = 0; };
+struct Stats { uint64_t bundles = 0, hits = 0; double submit_s = 0, sides_s = 0; };
+static Stats* g_stats = nullptr;
 
 static void submit(thb_ctx* ctx, Batch& b, uint32_t nseg, uint64_t& order_base, std::vector<uint64_t>& packed)
 {
@@ -52,7 +53,9 @@ static void submit(thb_ctx* ctx, Batch& b, uint32_t nseg, uint64_t& order_base, 
   sb.n_bundles = (uint32_t)n; sb.n_segs = nseg; sb.read_words = rw; sb.bundles = b.bundles.data(); sb.seg_count = b.seg_count.data();
   sb.reads = packed.data(); sb.n_hits = b.hits.size(); sb.hits = b.hits.data(); sb.n_partner_hits = b.partner.size();
   sb.partner_hits = b.partner.data(); sb.order_base = order_base;
+  const auto s0 = std::chrono::steady_clock::now();
   if (thb_segjuncs_submit(ctx, &sb) != THB_OK) die("Error: thb_segjuncs_submit: %s", thb_last_error(ctx));
+  if (g_stats) g_stats->submit_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
   order_base += n;
   b.clear();
 }
@@ -169,7 +172,7 @@ int main(int argc, char** argv)
     if (thb_segjuncs_fusion_ignore(ctx, ids.data(), (uint32_t)ids.size()) != THB_OK) die("Error: %s", thb_last_error(ctx));
   }
 
-  std::mutex rtm; uint64_t order_base = 0; Stats st;
+  std::mutex rtm; uint64_t order_base = 0; Stats st; g_stats = &st;
   fprintf(stderr, ">> Performing segment-search:\n");
   if (left_segs.size() > 1) {
     fprintf(stderr, "Loading left segment hits... "); fflush(stderr);
@@ -181,6 +184,7 @@ int main(int argc, char** argv)
     process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_base, st);
     fprintf(stderr, "done.\n");
   }
+  st.sides_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   thb_segjuncs_results r;
   if (thb_segjuncs_finish(ctx, &r) != THB_OK) die("Error: thb_segjuncs_finish: %s", thb_last_error(ctx));
   auto t2 = std::chrono::steady_clock::now();
@@ -240,8 +244,8 @@ int main(int argc, char** argv)
     thb_timing tm; thb_last_timing(ctx, &tm);
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     fprintf(stderr, "{\"gpu_stats\": {\"bundles\": %llu, \"hits\": %llu, \"ref_load_s\": %.3f, \"search_s\": %.3f, \"scan_kernel_ms\": %.3f, "
-                    "\"h2d_ms\": %.3f, \"windows\": %llu, \"indel_tasks\": %llu, \"rescue_tasks\": %llu}}\n",
-            (unsigned long long)st.bundles, (unsigned long long)st.hits, sec(t0, t1), sec(t1, t2), tm.scan_kernel_ms, tm.h2d_ms,
+                    "\"h2d_ms\": %.3f, \"submit_s\": %.3f, \"begin_and_sides_s\": %.3f, \"windows\": %llu, \"indel_tasks\": %llu, \"rescue_tasks\": %llu}}\n",
+            (unsigned long long)st.bundles, (unsigned long long)st.hits, sec(t0, t1), sec(t1, t2), tm.scan_kernel_ms, tm.h2d_ms, st.submit_s, st.sides_s,
             (unsigned long long)tm.n_windows, (unsigned long long)tm.n_indel_tasks, (unsigned long long)tm.n_rescue_tasks);
   }
   thb_destroy(ctx);

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
+#include <algorithm>
 
 namespace thbhost {
 
@@ -76,6 +78,28 @@ void BamWriter::flush_block()
   file_off_ += total; blk_.clear();
 }
 
+void BamWriter::encode(std::vector<uint8_t>& rec, const std::string& qname, int flag, int tid, int pos0, int mapq, const std::vector<uint32_t>& cigar,
+                       const std::string& seq, const std::string& qual, const std::vector<uint8_t>& aux)
+{
+  int end = pos0; for (uint32_t c : cigar) { const int op = (int)(c & 15); if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += (int)(c >> 4); }
+  if (end == pos0) end = pos0 + 1;
+  const int32_t l_seq = (int32_t)seq.size();
+  const int32_t block_size = 32 + (int32_t)qname.size() + 1 + 4 * (int32_t)cigar.size() + (l_seq + 1) / 2 + l_seq + (int32_t)aux.size();
+  auto p32 = [&](int32_t v) { const uint8_t* b = (const uint8_t*)&v; rec.insert(rec.end(), b, b + 4); };
+  p32(block_size); p32(tid); p32(pos0);
+  const uint32_t bin_mq_nl = ((uint32_t)reg2bin(pos0, end) << 16) | ((uint32_t)mapq << 8) | (uint32_t)(qname.size() + 1);
+  p32((int32_t)bin_mq_nl); p32((int32_t)(((uint32_t)flag << 16) | (uint32_t)cigar.size()));
+  p32(l_seq); p32(-1); p32(-1); p32(0);
+  rec.insert(rec.end(), qname.begin(), qname.end()); rec.push_back(0);
+  for (uint32_t c : cigar) p32((int32_t)c);
+  auto nt = [](char c) -> uint8_t { switch (c) { case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': return 3; case 'G': case 'g': return 4;
+    case 'R': return 5; case 'S': return 6; case 'V': return 7; case 'T': case 't': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
+    case 'D': return 13; case 'B': return 14; default: return 15; } };
+  for (int i = 0; i < l_seq; i += 2) rec.push_back((uint8_t)((nt(seq[i]) << 4) | (i + 1 < l_seq ? nt(seq[i + 1]) : 0)));
+  for (int i = 0; i < l_seq; ++i) rec.push_back((uint8_t)(i < (int)qual.size() ? qual[i] - 33 : 0xff));
+  rec.insert(rec.end(), aux.begin(), aux.end());
+}
+
 void BamWriter::write(const std::string& qname, uint32_t read_id, int flag, int tid, int pos0, int mapq, const std::vector<uint32_t>& cigar,
                       const std::string& seq, const std::string& qual, const std::vector<uint8_t>& aux)
 {
@@ -85,31 +109,79 @@ void BamWriter::write(const std::string& qname, uint32_t read_id, int flag, int 
     if (idxcount_ >= 1000 && (long)read_id != idx_last_id_) { pre_pos = tell(); write_index = true; }
     idx_last_id_ = (long)read_id; idxcount_++;
   }
-  int end = pos0; for (uint32_t c : cigar) { const int op = (int)(c & 15); if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += (int)(c >> 4); }
-  if (end == pos0) end = pos0 + 1;
-  const int32_t l_seq = (int32_t)seq.size();
-  const int32_t block_size = 32 + (int32_t)qname.size() + 1 + 4 * (int32_t)cigar.size() + (l_seq + 1) / 2 + l_seq + (int32_t)aux.size();
-  std::vector<uint8_t> rec; rec.reserve((size_t)block_size + 4);
-  auto p32 = [&](int32_t v) { const uint8_t* b = (const uint8_t*)&v; rec.insert(rec.end(), b, b + 4); };
-  p32(block_size); p32(tid); p32(pos0);
-  const uint32_t bin_mq_nl = ((uint32_t)reg2bin(pos0, end) << 16) | ((uint32_t)mapq << 8) | (uint32_t)(qname.size() + 1);
-  p32((int32_t)bin_mq_nl); p32((int32_t)(((uint32_t)flag << 16) | (uint32_t)cigar.size()));
-  p32(l_seq); p32(-1); p32(-1); p32(0);
-  rec.insert(rec.end(), qname.begin(), qname.end()); rec.push_back(0);
-  for (uint32_t c : cigar) p32((int32_t)c);
-  static const uint8_t code[256] = {0};
-  (void)code;
-  auto nt = [](char c) -> uint8_t { switch (c) { case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': return 3; case 'G': case 'g': return 4;
-    case 'R': return 5; case 'S': return 6; case 'V': return 7; case 'T': case 't': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
-    case 'D': return 13; case 'B': return 14; default: return 15; } };
-  for (int i = 0; i < l_seq; i += 2) rec.push_back((uint8_t)((nt(seq[i]) << 4) | (i + 1 < l_seq ? nt(seq[i + 1]) : 0)));
-  for (int i = 0; i < l_seq; ++i) rec.push_back((uint8_t)(i < (int)qual.size() ? qual[i] - 33 : 0xff));
-  rec.insert(rec.end(), aux.begin(), aux.end());
+  std::vector<uint8_t> rec;
+  encode(rec, qname, flag, tid, pos0, mapq, cigar, seq, qual, aux);
   // samtools' bgzf_write flushes the current block first when a record does not fit in it
   if (blk_.size() + rec.size() > BLOCK_DATA && !blk_.empty() && rec.size() <= BLOCK_DATA) flush_block();
   put(rec.data(), rec.size());
   wcount_++;
   if (write_index) { fprintf(fidx_, "%ld\t%ld\n", (long)read_id, (long)pre_pos); idxcount_ = 0; }
+}
+
+// deflates one BGZF block payload into `out` (header + data + crc + isize); returns the block's size or 0
+static size_t bgzf_compress(const uint8_t* src, size_t n, uint8_t* out, size_t out_cap)
+{
+  z_stream zs; memset(&zs, 0, sizeof zs);
+  deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+  zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = (uInt)(out_cap - 18 - 8);
+  const int rc = deflate(&zs, Z_FINISH); const size_t clen = zs.total_out; deflateEnd(&zs);
+  if (rc != Z_STREAM_END) return 0;
+  const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  memcpy(out, hdr, 16);
+  const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1); memcpy(out + 16, &bsize, 2);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), src, (uInt)n), isize = (uint32_t)n;
+  memcpy(out + 18 + clen, &crc, 4); memcpy(out + 18 + clen + 4, &isize, 4);
+  return clen + 26;
+}
+
+void BamWriter::append_records(const std::vector<RecordPart>& parts, int threads)
+{
+  if (!f_) return;
+  // 1. block formation, exactly as a sequence of write() calls would do it: `payload` = the bytes of the blocks completed by
+  //    this batch (the first one starts with what blk_ already holds); the tail stays in blk_ for the next batch / close()
+  std::vector<uint8_t> payload(blk_.begin(), blk_.end());
+  std::vector<size_t> block_start(1, 0);                   // offsets into payload where completed blocks begin
+  struct IdxEntry { long id; size_t block; size_t in_block; };
+  std::vector<IdxEntry> idx;
+  size_t cur = blk_.size();                                // bytes in the block being filled
+  auto close_block = [&]() { block_start.push_back(payload.size()); cur = 0; };
+  for (const RecordPart& p : parts) {
+    size_t off = 0;
+    for (size_t r = 0; r < p.sizes.size(); ++r) {
+      const size_t n = p.sizes[r]; const uint32_t read_id = p.ids[r];
+      bool write_index = false; IdxEntry ie{0, 0, 0};
+      if (fidx_ && read_id) {          // position taken before a possible flush, like write() does with tell()
+        if (idxcount_ >= 1000 && (long)read_id != idx_last_id_) { ie = IdxEntry{(long)read_id, block_start.size() - 1, cur}; write_index = true; }
+        idx_last_id_ = (long)read_id; idxcount_++;
+      }
+      if (cur + n > BLOCK_DATA && cur > 0 && n <= BLOCK_DATA) close_block();
+      size_t left = n; const uint8_t* src = p.bytes.data() + off;
+      while (left) { const size_t room = BLOCK_DATA - cur; const size_t k = left < room ? left : room;
+        payload.insert(payload.end(), src, src + k); src += k; left -= k; cur += k; if (cur >= BLOCK_DATA) close_block(); }
+      off += n; wcount_++;
+      if (write_index) { idx.push_back(ie); idxcount_ = 0; }
+    }
+  }
+  const size_t n_blocks = block_start.size() - 1;          // completed blocks; payload[block_start.back() ..) is the new tail
+  // 2. parallel deflate of the completed blocks
+  std::vector<std::vector<uint8_t>> comp(n_blocks); std::vector<size_t> clen(n_blocks, 0);
+  auto work = [&](size_t t, size_t nt) {
+    for (size_t b = t; b < n_blocks; b += nt) {
+      comp[b].resize(70000);
+      clen[b] = bgzf_compress(payload.data() + block_start[b], block_start[b + 1] - block_start[b], comp[b].data(), comp[b].size());
+    }
+  };
+  const size_t nt = (size_t)std::max(1, std::min<int>(threads, (int)n_blocks));
+  if (nt <= 1) work(0, 1);
+  else { std::vector<std::thread> th; for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t, nt); work(0, nt); for (auto& x : th) x.join(); }
+  // 3. ordered output + side index (virtual offset = file offset of the block << 16 | offset inside it)
+  std::vector<uint64_t> block_file_off(n_blocks + 1, file_off_);
+  for (size_t b = 0; b < n_blocks; ++b) {
+    if (clen[b] == 0 || fwrite(comp[b].data(), 1, clen[b], f_) != clen[b]) fail_ = true;
+    file_off_ += clen[b]; block_file_off[b + 1] = file_off_;
+  }
+  if (fidx_) for (const IdxEntry& e : idx) fprintf(fidx_, "%ld\t%ld\n", e.id, (long)((block_file_off[e.block] << 16) | (uint64_t)e.in_block));
+  blk_.assign(payload.begin() + (long)block_start.back(), payload.end());
 }
 
 bool BamWriter::close(std::string* err)

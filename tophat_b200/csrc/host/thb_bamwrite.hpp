@@ -18,6 +18,14 @@ class BamWriter {
   // one alignment; cigar ops as (len << 4 | BAM op code 0..8); aux = already encoded tag bytes
   void write(const std::string& qname, uint32_t read_id, int flag, int tid, int pos0, int mapq, const std::vector<uint32_t>& cigar,
              const std::string& seq, const std::string& qual, const std::vector<uint8_t>& aux);
+  // The same in two steps, for batches: `encode` serialises one alignment record (thread-safe, no writer state) behind
+  // `out`; `append_records` takes the records of a batch in output order -- any number of byte buffers, each with the sizes
+  // and read ids of its records -- forms the BGZF blocks (same boundaries as record-by-record `write` calls), deflates them on
+  // `threads` threads and writes blocks and side-index entries in order.
+  static void encode(std::vector<uint8_t>& out, const std::string& qname, int flag, int tid, int pos0, int mapq, const std::vector<uint32_t>& cigar,
+                     const std::string& seq, const std::string& qual, const std::vector<uint8_t>& aux);
+  struct RecordPart { std::vector<uint8_t> bytes; std::vector<uint32_t> sizes, ids; };
+  void append_records(const std::vector<RecordPart>& parts, int threads);
   bool close(std::string* err);
   uint64_t written() const { return wcount_; }
   // aux encoders (GBamRecord::add_aux typing rules, common.cpp:1111-1200)
