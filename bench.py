@@ -453,10 +453,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                         ours = (os.path.join(_b.BIN_DIR, "segment_juncs"), os.path.join(_b.BIN_DIR, "long_spanning_reads"))
                         if all(os.access(x, os.X_OK) for x in ours):
                             st_o = arm.startup(ours); arm.step(ours); wall_o = arm.step(ours)
-                            same = all(open(os.path.join(arm.dir, "segment.b200." + k)).read() == open(os.path.join(arm.dir, "segment." + k)).read()
+                            # compared with the reference at -p1: its own -pN output can lack junctions of reads at the thread
+                            # partition boundaries (observed: 1 of 28,969 at -p12 on this sample), ours equals the -p1 answer
+                            p1 = arm.py.run_segment_juncs(arm.sj, arm.files, arm.bams, arm.dir, arm.nseg, opts=arm.opts, threads=1, tag=".p1")
+                            same = all(open(os.path.join(arm.dir, "segment.b200." + k)).read() == open(p1[k]).read()
                                        for k in ("juncs", "insertions", "deletions"))
                             cli = {"value": 2 * arm.sample_pairs / max(wall_o - st_o, 1e-6), "unit": UNIT, "wall_s": wall_o, "startup_s": st_o,
-                                   "reference_wall_s": wall, "reference_startup_s": st, "segment_files_identical_to_reference": same,
+                                   "reference_wall_s": wall, "reference_startup_s": st, "segment_files_identical_to_reference_p1": same,
                                    "note": "our segment_juncs + long_spanning_reads executables on the reference arm's sample files; "
                                            "start-up (CUDA context, FASTA load, image upload) measured on a 1-pair input and excluded like the reference's"}
                     except Exception as e:
