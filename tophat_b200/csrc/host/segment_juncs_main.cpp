@@ -244,8 +244,8 @@ int main(int argc, char** argv)
     thb_timing tm; thb_last_timing(ctx, &tm);
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     fprintf(stderr, "{\"gpu_stats\": {\"bundles\": %llu, \"hits\": %llu, \"ref_load_s\": %.3f, \"search_s\": %.3f, \"scan_kernel_ms\": %.3f, "
-                    "\"h2d_ms\": %.3f, \"submit_s\": %.3f, \"begin_and_sides_s\": %.3f, \"windows\": %llu, \"indel_tasks\": %llu, \"rescue_tasks\": %llu}}\n",
-            (unsigned long long)st.bundles, (unsigned long long)st.hits, sec(t0, t1), sec(t1, t2), tm.scan_kernel_ms, tm.h2d_ms, st.submit_s, st.sides_s,
+                    "\"h2d_ms\": %.3f, \"submit_s\": %.3f, \"begin_and_sides_s\": %.3f, \"main_thread_cpu_s\": %.3f, \"decoder_threads_cpu_s\": %.3f, \"windows\": %llu, \"indel_tasks\": %llu, \"rescue_tasks\": %llu}}\n",
+            (unsigned long long)st.bundles, (unsigned long long)st.hits, sec(t0, t1), sec(t1, t2), tm.scan_kernel_ms, tm.h2d_ms, st.submit_s, st.sides_s, thread_cpu_seconds(), producer_cpu_seconds(),
             (unsigned long long)tm.n_windows, (unsigned long long)tm.n_indel_tasks, (unsigned long long)tm.n_rescue_tasks);
   }
   thb_destroy(ctx);

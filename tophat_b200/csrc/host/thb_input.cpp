@@ -6,8 +6,14 @@
 #include <fstream>
 #include <atomic>
 #include <zlib.h>
+#include <time.h>
 
 namespace thbhost {
+
+static std::atomic<long long> g_producer_cpu_us(0);
+double thread_cpu_seconds() { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+void add_producer_cpu() { g_producer_cpu_us += (long long)(thread_cpu_seconds() * 1e6); }
+double producer_cpu_seconds() { return 1e-6 * (double)g_producer_cpu_us.load(); }
 
 // ---- RefTable -----------------------------------------------------------------------------------------
 uint32_t RefTable::get_id(const std::string& name)
@@ -180,6 +186,7 @@ void HitStream::produce()
   }
   if (!br.error().empty()) err_ = br.error();
   if (!chunk.empty()) q_.push(std::move(chunk));
+  add_producer_cpu();
   q_.finish();
 }
 
@@ -260,6 +267,7 @@ void ReadStream::produce_bam()
   }
   if (!br.error().empty() && err_.empty()) err_ = br.error();
   if (!chunk.empty()) q_.push(std::move(chunk));
+  add_producer_cpu();
   q_.finish();
 }
 

@@ -16,6 +16,11 @@
 
 namespace thbhost {
 
+// CPU seconds spent by the decoder threads (TOPHAT_GPU_STATS)
+void add_producer_cpu();            // called by a decoder thread when it finishes: adds its own CPU time
+double producer_cpu_seconds();
+double thread_cpu_seconds();        // CPU time of the calling thread
+
 // RefSequenceTable (bwt_map.h:579-788): ids are 1-based in first-seen order, SAM header first.
 class RefTable {
  public:
