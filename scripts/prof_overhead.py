@@ -20,7 +20,7 @@ k1, s1 = dev(batches, ("bundles", "seg_count", "reads", "hits", "partner_hits"),
 ctx.segjuncs_begin(P); [ctx.segjuncs_submit_device(x) for x in s1]; res = ctx.segjuncs_finish()
 js = capi.join_sets_from_results(res)
 jb = [synth.pack_join_side(wl, wl.left, res.junctions), synth.pack_join_side(wl, wl.right, res.junctions)]
-k2, s2 = dev(jb, ("bundles", "seg_count", "reads", "hits"), capi.join_batch_c)
+k2, s2 = dev(jb, ("bundles", "seg_count", "reads", "hits", "ops_ext"), capi.join_batch_c)
 torch.cuda.synchronize()
 for rep in range(4):
     T = {}
