@@ -137,3 +137,11 @@ def test_emu_allgather_world1():
 @pytest.mark.parametrize("name", helpers.join_golden_cases())
 def test_emu_join_golden(emu_lib, name):
     helpers.check_join_golden(name)
+
+
+def test_emu_growth_paths_tiny_capacities():
+    """Overflow -> grow -> repeat paths of every device structure (tests/emu/tiny_caps_check.py, fresh process with THB_TINY_CAPS=1)."""
+    import subprocess, sys
+    env = dict(os.environ, THB_TINY_CAPS="1")
+    r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "tiny_caps_check.py")], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "tiny caps ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

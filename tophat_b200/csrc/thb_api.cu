@@ -138,6 +138,9 @@ int fail(thb_ctx* c, int code, const char* fmt, ...)
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, THB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// THB_TINY_CAPS=1 (test knob): every growable structure starts tiny, so that the overflow -> grow -> repeat paths run on small inputs
+bool tiny_caps() { static const bool v = getenv("THB_TINY_CAPS") != nullptr; return v; }
+
 HashSet make_set(DevBuf& b, uint64_t cap, unsigned int* ovf) { HashSet h; h.slots = (uint64_t*)b.p; h.mask = cap - 1; h.overflow = ovf; return h; }
 
 int grid_for(uint64_t n, int block) {
@@ -223,8 +226,11 @@ void launch_phase(thb_ctx* ctx, const BatchView& bv, const Queues& q, const SegO
 int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t n_hits)
 {
   if (bv.n_bundles == 0) return THB_OK;
-  ctx->cap_win = std::max<uint64_t>(ctx->cap_win, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
-  ctx->cap_indel = std::max<uint64_t>(ctx->cap_indel, std::max<uint64_t>(bv.n_bundles / 2, 1u << 16));
+  if (tiny_caps()) { ctx->cap_win = std::max<uint64_t>(ctx->cap_win, 64); ctx->cap_indel = std::max<uint64_t>(ctx->cap_indel, 64); }
+  else {
+    ctx->cap_win = std::max<uint64_t>(ctx->cap_win, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+    ctx->cap_indel = std::max<uint64_t>(ctx->cap_indel, std::max<uint64_t>(bv.n_bundles / 2, 1u << 16));
+  }
   CU(ctx->q_win.reserve(ctx->cap_win * sizeof(WindowTask))); CU(ctx->q_indel.reserve(ctx->cap_indel * sizeof(IndelTask)));
   CU(ctx->q_rescue.reserve((n_partner + 1) * sizeof(uint2))); CU(ctx->q_rescue_out.reserve((n_partner + 1) * sizeof(int2)));
   CU(ctx->q_rbundle.reserve((size_t)bv.n_bundles * sizeof(uint32_t)));
@@ -235,7 +241,7 @@ int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t 
   q.counts = ctx->d_qcounts; q.overflow = ctx->d_qovf;
   CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
   if (ctx->sp.fusion_search) {
-    ctx->cap_fustask = std::max<uint64_t>(ctx->cap_fustask, std::max<uint64_t>(bv.n_bundles, 1u << 16));
+    ctx->cap_fustask = std::max<uint64_t>(ctx->cap_fustask, tiny_caps() ? 64 : std::max<uint64_t>(bv.n_bundles, 1u << 16));
     CU(ctx->q_fus.reserve(ctx->cap_fustask * sizeof(FusionTask)));
     CU(cudaMemsetAsync(ctx->d_fustask_count, 0, sizeof(unsigned long long), ctx->compute));
   }
@@ -585,10 +591,10 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   s.bowtie2 = p->bowtie2; s.library_type = p->library_type;
   s.fusion_search = p->fusion_search ? 1 : 0; s.fusion_min_dist = p->fusion_min_dist;
   ctx->fp.fusion_min_dist = p->fusion_min_dist; ctx->fp.fusion_anchor = p->fusion_anchor_length; ctx->fp.n_ignore = 0; ctx->fp.ignore = nullptr;
-  if (s.fusion_search) { if (ctx->cap_fus == 0) ctx->cap_fus = 1ull << 16; CU(ctx->d_fus.reserve(ctx->cap_fus * sizeof(FusRec))); }
-  if (ctx->cap_juncs == 0) ctx->cap_juncs = 1ull << 21;
-  if (ctx->cap_dels == 0) ctx->cap_dels = 1ull << 18;
-  if (ctx->cap_ins == 0) ctx->cap_ins = 1ull << 18;
+  if (s.fusion_search) { if (ctx->cap_fus == 0) ctx->cap_fus = tiny_caps() ? 64 : 1ull << 16; CU(ctx->d_fus.reserve(ctx->cap_fus * sizeof(FusRec))); }
+  if (ctx->cap_juncs == 0) ctx->cap_juncs = tiny_caps() ? 64 : 1ull << 21;
+  if (ctx->cap_dels == 0) ctx->cap_dels = tiny_caps() ? 64 : 1ull << 18;
+  if (ctx->cap_ins == 0) ctx->cap_ins = tiny_caps() ? 64 : 1ull << 18;
   int rc;
   if ((rc = alloc_set(ctx, ctx->d_juncs, ctx->cap_juncs))) return rc;
   if ((rc = alloc_set(ctx, ctx->d_dels, ctx->cap_dels))) return rc;
@@ -912,8 +918,8 @@ static int join_validate(thb_ctx* ctx, const thb_join_batch* b)
 // launches the chain join over device-resident arrays; results stay in ctx->j_out, *n receives their number
 static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint64_t n_ext, unsigned long long* n_res, DevBuf& out_buf, uint64_t& cap_out)
 {
-  cap_out = std::max<uint64_t>(cap_out, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
-  ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+  cap_out = std::max<uint64_t>(cap_out, tiny_caps() ? 64 : std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
+  ctx->j_cap_chain = std::max<uint64_t>(ctx->j_cap_chain, tiny_caps() ? 64 : std::max<uint64_t>(2ull * bv.n_bundles, 1u << 16));
   JoinSets S; S.juncs = (const thb_junction*)ctx->j_juncs.p; S.n_juncs = (uint32_t)ctx->j_n_juncs; S.ins = (const thb_insertion*)ctx->j_ins.p; S.n_ins = (uint32_t)ctx->j_n_ins;
   S.jidx = ctx->j_use_idx ? (const uint32_t*)ctx->j_idx.p : nullptr; S.n_buckets = ctx->j_nbuckets; S.shift = ctx->j_shift;
   S.iidx = ctx->j_use_iidx ? (const uint32_t*)ctx->j_iidx.p : nullptr; S.n_ibuckets = ctx->j_nibuckets; S.ishift = ctx->j_ishift;
