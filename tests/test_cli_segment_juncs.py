@@ -75,3 +75,19 @@ def test_cli_no_hits_exit_zero():
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0 and "No hits to process, exiting" in r.stderr
         assert all(os.path.exists(o) for o in outs)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_cli_two_side_threads_equal_reference_p1():
+    """-p N > 1: our executable assembles the two mate sides on two threads; all four outputs (insertions depend on the first-wins
+    order between the sides) must equal the reference's -p1 output."""
+    OUR_BIN = helpers.our_bin("segment_juncs")
+    with tempfile.TemporaryDirectory() as td:
+        wl, files, bams, nseg = _prepare(td, synth.SynthConfig(contig_lens=(300_000, 100_000), n_pairs=4000, seed=307, indel_prob=0.5, fusion_frac=0.1))
+        opts = pyoracle.tophat_common_opts(50, 20, ["--fusion-search", "--fusion-min-dist", "20000"])
+        ref = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts, tag=".ref", threads=1)
+        ours = pyoracle.run_segment_juncs(OUR_BIN, files, bams, td, nseg, opts=opts, tag=".b200p4", threads=4)
+        for k in ("juncs", "insertions", "deletions", "fusions"):
+            assert open(ours[k]).read() == open(ref[k]).read(), "segment.%s differs from the reference's -p1 output" % k
+        assert open(ref["insertions"]).read().count("\n") > 100

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include "tophat_b200.h"
 #include "thb_options.hpp"
 #include "thb_input.hpp"
@@ -40,6 +41,8 @@ struct Batch {
 struct Stats { uint64_t bundles = 0, hits = 0; double submit_s = 0, sides_s = 0; };
 static Stats* g_stats = nullptr;
 
+static std::mutex g_submit_mutex;      // the two mate sides are assembled on two threads; the library is entered by one at a time
+
 static void submit(thb_ctx* ctx, Batch& b, uint32_t nseg, uint64_t& order_base, std::vector<uint64_t>& packed)
 {
   if (b.bundles.empty()) return;
@@ -53,9 +56,12 @@ static void submit(thb_ctx* ctx, Batch& b, uint32_t nseg, uint64_t& order_base, 
   sb.n_bundles = (uint32_t)n; sb.n_segs = nseg; sb.read_words = rw; sb.bundles = b.bundles.data(); sb.seg_count = b.seg_count.data();
   sb.reads = packed.data(); sb.n_hits = b.hits.size(); sb.hits = b.hits.data(); sb.n_partner_hits = b.partner.size();
   sb.partner_hits = b.partner.data(); sb.order_base = order_base;
-  const auto s0 = std::chrono::steady_clock::now();
-  if (thb_segjuncs_submit(ctx, &sb) != THB_OK) die("Error: thb_segjuncs_submit: %s", thb_last_error(ctx));
-  if (g_stats) g_stats->submit_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+  {
+    std::lock_guard<std::mutex> l(g_submit_mutex);
+    const auto s0 = std::chrono::steady_clock::now();
+    if (thb_segjuncs_submit(ctx, &sb) != THB_OK) die("Error: thb_segjuncs_submit: %s", thb_last_error(ctx));
+    if (g_stats) g_stats->submit_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+  }
   order_base += n;
   b.clear();
 }
@@ -172,18 +178,27 @@ int main(int argc, char** argv)
     if (thb_segjuncs_fusion_ignore(ctx, ids.data(), (uint32_t)ids.size()) != THB_OK) die("Error: %s", thb_last_error(ctx));
   }
 
-  std::mutex rtm; uint64_t order_base = 0; Stats st; g_stats = &st;
+  // The two mate sides are independent passes over disjoint files (4752, 4831): with -p > 1 they are assembled on two threads.
+  // Insertions keep the single-threaded first-wins order because every right-side bundle carries a priority above every
+  // left-side one (order_base of the right side starts at 2^38).
+  std::mutex rtm; uint64_t order_left = 0, order_right = 1ull << 38; Stats st, st_r; g_stats = &st;
   fprintf(stderr, ">> Performing segment-search:\n");
+  std::thread right_thread;
+  const bool two_threads = o.num_threads > 1 && left_segs.size() > 1 && right_segs.size() > 1;
+  if (two_threads)
+    right_thread = std::thread([&] { process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_right, st_r); });
   if (left_segs.size() > 1) {
     fprintf(stderr, "Loading left segment hits... "); fflush(stderr);
-    process_side(ctx, o, rt, rtm, left_reads, left_segs, right_map, right_segs.empty() ? std::string() : right_segs.back(), false, order_base, st);
+    process_side(ctx, o, rt, rtm, left_reads, left_segs, right_map, right_segs.empty() ? std::string() : right_segs.back(), false, order_left, st);
     fprintf(stderr, "done.\n");
   }
   if (right_segs.size() > 1) {
     fprintf(stderr, "Loading right segment hits..."); fflush(stderr);
-    process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_base, st);
+    if (two_threads) right_thread.join();
+    else { order_right = order_left; process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_right, st_r); }
     fprintf(stderr, "done.\n");
   }
+  st.bundles += st_r.bundles; st.hits += st_r.hits;
   st.sides_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   thb_segjuncs_results r;
   if (thb_segjuncs_finish(ctx, &r) != THB_OK) die("Error: thb_segjuncs_finish: %s", thb_last_error(ctx));
