@@ -355,6 +355,16 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     # the two arms must agree with each other (same sets / same number of alignments from device-resident and host submission)
     assert res.junctions.shape == res_h.junctions.shape and (res.junctions == res_h.junctions).all()
     assert A["n_joined"] == E["n_joined"]
+    # size-independent properties of the full-size result (std::set semantics of the reference's containers): strictly increasing
+    # in Junction order, spans inside [min_segment_intron - 16, max_segment_intron + segment_length + 16]
+    for arr in (res.junctions, res.deletions):
+        if len(arr) > 1:
+            k1 = (arr["ref_id"].astype(np.uint64) << np.uint64(32)) | arr["left"].astype(np.uint64)
+            k2 = (arr["right"].astype(np.uint64) << np.uint64(1)) | arr["antisense"].astype(np.uint64)
+            assert ((k1[1:] > k1[:-1]) | ((k1[1:] == k1[:-1]) & (k2[1:] > k2[:-1]))).all(), "result set not strictly increasing"
+    if len(res.junctions):
+        span = res.junctions["right"].astype(np.int64) - res.junctions["left"].astype(np.int64)
+        assert span.min() >= 50 - 16 and span.max() <= 500000 + 25 + 16
 
     total_reads = n_reads * world
     per_step = A["ms"] / args.steps
