@@ -153,3 +153,37 @@ def our_bin(prog):
     from tophat_b200 import build
     build.build_all()
     return os.path.join(build.BIN_DIR, prog)
+
+
+# ---- goldens made from the reference's own test inputs (fusion_test/, scripts/make_fusion_test_golden.py) -----------------------
+
+def reference_input_cases():
+    return sorted(d for d in os.listdir(GOLDEN) if d.startswith("reference_") and os.path.exists(os.path.join(GOLDEN, d, "inputs.npz")))
+
+
+def load_reference_input_case(name):
+    """-> (Workload with an empty right side, Params of the tophat command line in fusion_test/run_test.sh, expected segment.* texts)"""
+    d = os.path.join(GOLDEN, name)
+    z = np.load(os.path.join(d, "inputs.npz"))
+    lens = [int(x) for x in z["contig_lens"]]
+    codes, off = [], 0
+    for n in lens:
+        codes.append(z["contig_codes"][off:off + n]); off += n
+    ref = synth.build_ref_image([str(x) for x in z["contig_names"]], codes)
+    reads = z["reads"]; L = reads.shape[1]
+    nseg = sum(1 for k in z.files if k.startswith("seg"))
+    left = synth.SideData(reads, np.arange(1, reads.shape[0] + 1, dtype="<u4"), [z["seg%d" % k] for k in range(nseg)], z["mapped_hits"], z["unmapped"])
+    e = np.zeros(0, dtype=synth.SEGHIT_DTYPE)
+    right = synth.SideData(np.zeros((0, L), dtype=np.uint8), np.zeros(0, dtype="<u4"), [e] * nseg, e, np.zeros(0, dtype=bool))
+    wl = synth.Workload(synth.SynthConfig(contig_lens=tuple(lens), n_pairs=reads.shape[0], read_len=L, segment_length=25), ref, left, right,
+                        np.zeros((0, 4), dtype=np.int64))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20, bowtie2=0, fusion_search=1, fusion_min_dist=500,
+                            max_segment_intron_length=500, max_report_intron_length=500)
+    texts = {k: open(os.path.join(d, "segment." + k)).read() for k in ("juncs", "insertions", "deletions", "fusions")}
+    return wl, P, texts
+
+
+def reference_input_texts(res, names):
+    t = as_text(res, names)
+    t["fusions"] = pyoracle.format_fusions(res.fusions, res.junctions, names, resolve_conflicts=False)    # --fusion-do-not-resolve-conflicts
+    return t

@@ -145,3 +145,17 @@ def test_emu_growth_paths_tiny_capacities():
     env = dict(os.environ, THB_TINY_CAPS="1")
     r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "tiny_caps_check.py")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "tiny caps ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", helpers.reference_input_cases())
+def test_emu_on_the_references_own_test_inputs(emu_lib, name):
+    """The reference's own fusion_test/ read sets (BASELINE configs[0] / configs[4]): single-end, --bowtie1, --fusion-search
+    --fusion-min-dist 500 --max-intron-length 500; all four outputs equal the reference binary's (tests/golden/reference_*)."""
+    wl, P, want = helpers.load_reference_input_case(name)
+    batch = synth.pack_side(wl.left, None, False, True)
+    got, _ = helpers.gpu_segjuncs(P, wl.ref, [batch])
+    txt = helpers.reference_input_texts(got, wl.ref.names)
+    for k in want:
+        assert txt[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
+    oracle, _ = pyoracle.segjuncs(P, wl.ref, [batch])
+    helpers.assert_same_results(got, oracle, name)

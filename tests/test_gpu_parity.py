@@ -210,3 +210,17 @@ def test_global_coordinates_beyond_32_bits():
     got, _ = helpers.gpu_segjuncs(P, moved, batches)
     helpers.assert_same_results(got, want, "far contig")
     assert (got.junctions["ref_id"] == 2).sum() > 20
+
+
+@pytest.mark.parametrize("name", helpers.reference_input_cases())
+def test_gpu_on_the_references_own_test_inputs(name):
+    """The reference's own fusion_test/ read sets (BASELINE configs[0] / configs[4]): single-end, --bowtie1, --fusion-search
+    --fusion-min-dist 500 --max-intron-length 500; all four outputs equal the reference binary's (tests/golden/reference_*)."""
+    wl, P, want = helpers.load_reference_input_case(name)
+    batch = synth.pack_side(wl.left, None, False, True)
+    got, _ = helpers.gpu_segjuncs(P, wl.ref, [batch])
+    txt = helpers.reference_input_texts(got, wl.ref.names)
+    for k in want:
+        assert txt[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
+    oracle, _ = pyoracle.segjuncs(P, wl.ref, [batch])
+    helpers.assert_same_results(got, oracle, name)

@@ -116,3 +116,15 @@ def test_empty_batch():
     empty = synth.PackedBatch(b.n_segs, b.read_words, b.bundles[:0], b.seg_count[:0], b.reads[:0], b.hits[:0], b.partner_hits[:0])
     res, cnt = pyoracle.segjuncs(P, wl.ref, [empty])
     assert len(res.junctions) == 0 and cnt.n_windows == 0
+
+
+@pytest.mark.parametrize("name", helpers.reference_input_cases())
+def test_oracle_on_the_references_own_test_inputs(name):
+    """fusion_test/ read sets of the reference (BASELINE configs[0] / configs[4]) through the oracle: single-end, --bowtie1,
+    --fusion-search --fusion-min-dist 500 --max-intron-length 500; expected = outputs of the reference binary on the same files."""
+    wl, P, want = helpers.load_reference_input_case(name)
+    batch = synth.pack_side(wl.left, None, False, True)
+    res, _ = pyoracle.segjuncs(P, wl.ref, [batch])
+    got = helpers.reference_input_texts(res, wl.ref.names)
+    for k in want:
+        assert got[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
