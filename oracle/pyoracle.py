@@ -264,12 +264,12 @@ def make_join_inputs(wl, files: Dict[str, str], outs: Dict[str, str], outdir: st
 
 def run_long_spanning_reads(binary: str, files: Dict[str, str], bams: Dict[str, str], jin: Dict[str, str], outs: Dict[str, str], outdir: str,
                             nseg: int, side: str = "left", opts: Optional[List[str]] = None, tag: str = "", env: Optional[dict] = None,
-                            with_spliced: bool = True, threads: int = 1) -> str:
+                            with_spliced: bool = True, threads: int = 1, fusions: str = "/dev/null") -> str:
     out_bam = os.path.join(outdir, "%s_candidates%s.bam" % (side, tag))
     cmd = [binary] + (opts if opts is not None else tophat_common_opts()) + \
           ["-p%d" % threads, "--sam-header", files["header"], "--bowtie2-max-penalty", "6", "--bowtie2-min-penalty", "2", "--bowtie2-penalty-for-N", "1",
            "--bowtie2-read-gap-open", "5", "--bowtie2-read-gap-cont", "3", "--bowtie2-ref-gap-open", "5", "--bowtie2-ref-gap-cont", "3",
-           files["fasta"], bams[side + "_reads"], outs["juncs"], outs["insertions"], outs["deletions"], "/dev/null", out_bam,
+           files["fasta"], bams[side + "_reads"], outs["juncs"], outs["insertions"], outs["deletions"], fusions, out_bam,
            ",".join(bams["%s_seg%d" % (side, k + 1)] for k in range(nseg))]
     if with_spliced:
         cmd.append(",".join(jin["%s_spl%d" % (side, k + 1)] for k in range(nseg)))

@@ -53,6 +53,41 @@ JOIN_CASES = {
 }
 
 
+JOIN_FUSION_CASES = {
+    # long_spanning_reads --fusion-search (NOT built on the GPU path yet: DESIGN.md sections 2 / 10): the reference's records incl. the
+    # two-part fusion alignments (XF tag) for chimeric reads, committed so that the next round starts from pinned expectations
+    "join_fusion_chimeric": (dict(contig_lens=(250_000, 90_000, 60_000), n_pairs=3000, seed=41, indel_prob=0.1, fusion_frac=0.15, keep_truth=True), 50, 20,
+                             ["--fusion-search", "--fusion-min-dist", "20000"]),
+}
+
+
+def main_join_fusion():
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, im, isd, extra) in JOIN_FUSION_CASES.items():
+        out = os.path.join(gdir, name)
+        os.makedirs(out, exist_ok=True)
+        wl = synth.generate(synth.SynthConfig(**kw))
+        opts = pyoracle.tophat_common_opts(im, isd, extra)
+        with tempfile.TemporaryDirectory() as td:
+            files = synth.write_pipeline_files(wl, td)
+            nseg = len(wl.left.seg_hits)
+            bams = pyoracle.make_bams(files, td, nseg)
+            outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts)
+            jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+            for side in ("left", "right"):
+                bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=side, tag=".ref", opts=opts, fusions=outs["fusions"])
+                _, recs = pyoracle.read_bam(bam)
+                with open(os.path.join(out, side + ".fusion_records.tsv"), "w") as f:
+                    for r in recs:
+                        f.write("%s\t%s\t%d\t%s\t%d\t%d\t%s\n" % (r[0], r[2], r[3], r[5], r[1], r[11]["NM"], r[11].get("XF", "-")))
+                print(name, side, len(recs), "records,", sum(1 for r in recs if "XF" in r[11]), "with XF")
+        with open(os.path.join(out, "config.json"), "w") as f:
+            json.dump(dict(synth=kw, inner_dist_mean=im, inner_dist_std_dev=isd, extra=extra, generator="scripts/make_golden.py",
+                           status="expectations for the fusion path of the join, which the GPU path does not implement yet",
+                           binary="oracle/_ref/segment_juncs + juncs_db + long_spanning_reads --fusion-search (TopHat 2.1.2, -p1)"), f, indent=1)
+
+
 def main_join():
     gdir = os.path.join(ROOT, "tests", "golden")
     for name, (kw, im, isd) in JOIN_CASES.items():
@@ -82,3 +117,4 @@ def main_join():
 if __name__ == "__main__":
     main()
     main_join()
+    main_join_fusion()
