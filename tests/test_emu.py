@@ -159,3 +159,57 @@ def test_emu_on_the_references_own_test_inputs(emu_lib, name):
         assert txt[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
     oracle, _ = pyoracle.segjuncs(P, wl.ref, [batch])
     helpers.assert_same_results(got, oracle, name)
+
+
+@pytest.mark.parametrize("params", [
+    dict(segment_mismatches=1), dict(segment_mismatches=3), dict(max_insertion_length=5, max_deletion_length=6),
+    dict(min_segment_intron_length=200, max_segment_intron_length=3000), dict(max_seg_multihits=2),
+    dict(fusion_search=1, fusion_anchor_length=10, fusion_min_dist=1000, segment_mismatches=1),
+    dict(bowtie2=0, fusion_search=1, fusion_min_dist=20000, max_seg_multihits=2),
+])
+def test_emu_option_variants_match_oracle(emu_lib, params):
+    """Non-default values of every option the path reads (the oracle is pinned on the reference binary under the same variants:
+    tests/test_oracle.py::test_oracle_matches_live_reference_under_option_variants)."""
+    wl = synth.generate(synth.SynthConfig(contig_lens=(250_000, 90_000), n_pairs=2000, seed=61, indel_prob=0.4, decoy_rate=1.5,
+                                          fusion_frac=0.15 if params.get("fusion_search") else 0.0))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20, **params)
+    batches = helpers.pack_both(wl, P)
+    got, t = helpers.gpu_segjuncs(P, wl.ref, batches)
+    want, cnt = pyoracle.segjuncs(P, wl.ref, batches)
+    helpers.assert_same_results(got, want, str(params))
+    assert (t.n_windows, t.n_indel_tasks, t.n_rescue_tasks, t.n_juncs_emitted, t.n_fusion_tasks) == \
+        (cnt.n_windows, cnt.n_indel_tasks, cnt.n_rescue_tasks, cnt.n_juncs_emitted, cnt.n_fusion_tasks)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("over", [
+    {"--max-insertion-length": 5, "--max-deletion-length": 6},
+    {"--min-report-intron": 150, "--max-report-intron": 3000},
+    {"--read-mismatches": 1, "--read-edit-dist": 1, "--read-gap-length": 1},
+    {"--min-anchor": 5, "--max-seg-multihits": 3},
+])
+def test_emu_cli_join_option_variants_match_reference(over):
+    """long_spanning_reads executable (emulated library) under non-default options of the join (indel lengths, reported intron bounds,
+    read-level filters, multihit guard) against the reference binary: records identical, in order."""
+    import sys
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "emu"))
+    import build_emu
+    exe = build_emu.build_cli("long_spanning_reads")
+    opts = pyoracle.tophat_common_opts(50, 20)
+    for k, v in over.items():
+        opts[opts.index(k) + 1] = str(v)
+    with tempfile.TemporaryDirectory() as td:
+        wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(250_000, 80_000), n_pairs=2000, seed=71, indel_prob=0.5, decoy_rate=1.0))
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts)
+        jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+        n = 0
+        for side in ("left", "right"):
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg, side=side, tag=".ref", opts=opts)
+            our_bam = pyoracle.run_long_spanning_reads(exe, files, bams, jin, outs, td, nseg, side=side, tag=".emu", opts=opts, threads=3)
+            a, b = pyoracle.read_bam(our_bam)[1], pyoracle.read_bam(ref_bam)[1]
+            assert a == b, "%s: records differ under %r (%d vs %d)" % (side, over, len(a), len(b))
+            n += len(b)
+        assert n > 100

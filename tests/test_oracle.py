@@ -128,3 +128,37 @@ def test_oracle_on_the_references_own_test_inputs(name):
     got = helpers.reference_input_texts(res, wl.ref.names)
     for k in want:
         assert got[k] == want[k], "%s: segment.%s differs from the reference binary's output" % (name, k)
+
+
+def _opts_with(over):
+    o = pyoracle.tophat_common_opts(50, 20)
+    for k, v in over.items():
+        o[o.index(k) + 1] = str(v)
+    return o
+
+
+OPTION_VARIANTS = [
+    ({"--segment-mismatches": 1}, dict(segment_mismatches=1)),
+    ({"--segment-mismatches": 3}, dict(segment_mismatches=3)),
+    ({"--max-insertion-length": 5, "--max-deletion-length": 6}, dict(max_insertion_length=5, max_deletion_length=6)),
+    ({"--min-segment-intron": 200, "--max-segment-intron": 3000}, dict(min_segment_intron_length=200, max_segment_intron_length=3000)),
+    ({"--max-seg-multihits": 2}, dict(max_seg_multihits=2)),
+]
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("opts,params", OPTION_VARIANTS)
+def test_oracle_matches_live_reference_under_option_variants(opts, params):
+    """Non-default values of the options the path reads (segment mismatches -> rescue seed length, indel lengths, segment intron
+    bounds, multihit guard): oracle vs the reference binary on identical files."""
+    wl = synth.generate(synth.SynthConfig(contig_lens=(250_000, 90_000), n_pairs=2500, seed=61, indel_prob=0.4, decoy_rate=1.5))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20, **params)
+    res, _ = pyoracle.segjuncs(P, wl.ref, helpers.pack_both(wl))
+    got = helpers.as_text(res, wl.ref.names)
+    with tempfile.TemporaryDirectory() as td:
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=_opts_with(opts))
+        for k in ("juncs", "insertions", "deletions"):
+            assert got[k] == open(outs[k]).read(), "segment.%s differs under %r" % (k, opts)
