@@ -146,9 +146,7 @@ void HitStream::produce()
     bool end = true;
     const char* pipe = strrchr(r.qname, '|');
     if (pipe && strchr(pipe + 1, ':')) {
-      unsigned so = 0, sn = 0, ns = 0;
-      sscanf(pipe + 1, "%u:%u:%u", &so, &sn, &ns);
-      end = (sn + 1 == ns);
+      end = last_segment_from_suffix(pipe + 1);
     }
     HitRec hr; memset(&hr, 0, sizeof hr);
     hr.id = (uint32_t)atoi(r.qname);          // atoi stops at '|' (ReadTable::get_id, bwt_map.h:546-552)
@@ -224,13 +222,14 @@ void pack_read_ascii(const char* s, uint32_t len, ReadRec& r)
 {
   memset(r.planes, 0, sizeof r.planes);
   r.len = len;
+  // bit0 / bit1 = 2-bit code, bit2 = "not ACGT" (code bits 0 there); branch-free: this runs once per read in the consumer loop
+  static const struct Table { uint8_t v[256]; Table() { for (int i = 0; i < 256; ++i) v[i] = 4; v[(int)'A'] = 0; v[(int)'C'] = 1; v[(int)'G'] = 2; v[(int)'T'] = 3; } } T;
   for (uint32_t i = 0; i < len && i < 256; ++i) {
-    unsigned c; bool isn = false;
-    switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 0; isn = true; }
+    const uint64_t c = T.v[(unsigned char)s[i]];
     const uint32_t w = i >> 6, j = i & 63;
-    if (c & 1) r.planes[w] |= 1ull << j;
-    if (c & 2) r.planes[4 + w] |= 1ull << j;
-    if (isn) r.planes[8 + w] |= 1ull << j;
+    r.planes[w] |= (c & 1ull) << j;
+    r.planes[4 + w] |= ((c >> 1) & 1ull) << j;
+    r.planes[8 + w] |= (c >> 2) << j;
   }
 }
 

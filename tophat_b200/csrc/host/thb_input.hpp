@@ -4,6 +4,7 @@
 #pragma once
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <memory>
@@ -15,6 +16,19 @@
 #include "thb_bam.hpp"
 
 namespace thbhost {
+
+// "<offset>:<seg>:<nsegs>" behind the last '|' of a segment read name (bwt_map.cpp:1126-1143): is this the read's last segment?
+// Same answer as sscanf(s, "%u:%u:%u") followed by seg + 1 == nsegs (fields that do not parse stay 0).
+inline bool last_segment_from_suffix(const char* s)
+{
+  unsigned long sn = 0, ns = 0; char* e = nullptr;
+  strtoul(s, &e, 10);
+  if (e != s && *e == ':') {
+    const char* p2 = e + 1; const unsigned long v2 = strtoul(p2, &e, 10);
+    if (e != p2) { sn = v2; if (*e == ':') { const char* p3 = e + 1; const unsigned long v3 = strtoul(p3, &e, 10); if (e != p3) ns = v3; } }
+  }
+  return sn + 1 == ns;
+}
 
 // CPU seconds spent by the decoder threads (TOPHAT_GPU_STATS)
 void add_producer_cpu();            // called by a decoder thread when it finishes: adds its own CPU time

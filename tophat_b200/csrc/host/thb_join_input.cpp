@@ -132,7 +132,7 @@ void JoinHitStream::produce()
   while (br.next(r)) {
     bool end = true;
     const char* pipe = strrchr(r.qname, '|');
-    if (pipe && strchr(pipe + 1, ':')) { unsigned so = 0, sn = 0, ns = 0; sscanf(pipe + 1, "%u:%u:%u", &so, &sn, &ns); end = (sn + 1 == ns); }
+    if (pipe && strchr(pipe + 1, ':')) end = last_segment_from_suffix(pipe + 1);
     JHitRec hr; memset(&hr, 0, sizeof hr);
     hr.id = (uint32_t)atoi(r.qname);
     if (r.tid < 0) {
