@@ -5,6 +5,7 @@ sm_100a only: `-gencode arch=compute_100a,code=sm_100a`.  The cudart is linked s
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -21,11 +22,27 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-I", os.path.join(ROOT, "include")]
 
 
-def _newer(target: str, sources) -> bool:
-    if not os.path.exists(target):
+def _digest(sources, extra: str = "") -> str:
+    """Content hash of the sources (+ the command line): checkout times say nothing about what a binary was built from."""
+    h = hashlib.sha256(extra.encode())
+    for s in sorted(sources):
+        h.update(os.path.relpath(s, ROOT).encode())
+        with open(s, "rb") as f:
+            h.update(hashlib.sha256(f.read()).digest())
+    return h.hexdigest()
+
+
+def _stale(target: str, digest: str) -> bool:
+    stamp = target + ".srchash"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    with open(stamp) as f:
+        return f.read().strip() != digest
+
+
+def _stamp(target: str, digest: str) -> None:
+    with open(target + ".srchash", "w") as f:
+        f.write(digest + "\n")
 
 
 def _csrc_files():
@@ -38,10 +55,13 @@ def _csrc_files():
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, "thb_api.cu")]
-    if force or _newer(LIB, _csrc_files()):
+    lib_srcs = [f for f in _csrc_files() if os.sep + "host" + os.sep not in f]
+    digest = _digest(lib_srcs, " ".join(NVCC_FLAGS))
+    if force or _stale(LIB, digest):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs + ["-ldl"]
         subprocess.run(cmd, check=True)
+        _stamp(LIB, digest)
     return LIB
 
 
@@ -58,10 +78,13 @@ def build_host_binaries(force: bool = False) -> list:
         if not os.path.exists(main):
             continue
         exe = os.path.join(BIN_DIR, prog)
-        if force or _newer(exe, _csrc_files() + [LIB]):
-            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unused-function", "-Wno-misleading-indentation", "-I", os.path.join(ROOT, "include"), "-I", host,
-                   "-o", exe, main] + common + ["-L", HERE, "-ltophat_b200", "-Wl,-rpath,$ORIGIN/..", "-lz", "-lpthread"]
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unused-function", "-Wno-misleading-indentation", "-I", os.path.join(ROOT, "include"), "-I", host,
+               "-o", exe, main] + common + ["-L", HERE, "-ltophat_b200", "-Wl,-rpath,$ORIGIN/..", "-lz", "-lpthread"]
+        host_srcs = [main] + common + [f for f in _csrc_files() if f.endswith((".h", ".hpp"))]
+        digest = _digest(host_srcs, " ".join(cmd))
+        if force or _stale(exe, digest):
             subprocess.run(cmd, check=True)
+            _stamp(exe, digest)
         outs.append(exe)
     return outs
 
