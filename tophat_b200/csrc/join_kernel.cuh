@@ -45,6 +45,7 @@ struct JoinBatchView {
   uint32_t n_bundles, n_segs, read_words;
   uint32_t bundle_base;               // added to the bundle index reported in thb_joined (chunked submission)
   uint32_t hit_end;                   // index one past the last hit of the last bundle of this view
+  uint32_t ops_end;                   // index one past the last thb_jops record of the last bundle of this view
 };
 
 struct JoinOut {

@@ -16,6 +16,7 @@
 #include "../../include/tophat_b200.h"
 #include "segjuncs_kernel.cuh"
 #include "join_kernel.cuh"
+#include "join_tile_kernel.cuh"
 #include "fusion_kernel.cuh"
 
 using namespace thb;
@@ -140,6 +141,9 @@ int fail(thb_ctx* c, int code, const char* fmt, ...)
 
 // THB_TINY_CAPS=1 (test knob): every growable structure starts tiny, so that the overflow -> grow -> repeat paths run on small inputs
 bool tiny_caps() { static const bool v = getenv("THB_TINY_CAPS") != nullptr; return v; }
+// THB_JOIN_LEGACY=1 / THB_SCAN_LEGACY=1 (measurement knobs): round 1's queue-based kernels instead of the TMA-staged tile kernels
+bool join_legacy() { static const bool v = getenv("THB_JOIN_LEGACY") != nullptr; return v; }
+bool scan_legacy() { static const bool v = getenv("THB_SCAN_LEGACY") != nullptr; return v; }
 
 HashSet make_set(DevBuf& b, uint64_t cap, unsigned int* ovf) { HashSet h; h.slots = (uint64_t*)b.p; h.mask = cap - 1; h.overflow = ovf; return h; }
 
@@ -927,7 +931,8 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
     CU(out_buf.reserve(cap_out * sizeof(thb_joined)));
-    CU(ctx->j_chain.reserve(3 * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // general + simple + abutting queues
+    const bool legacy = join_legacy();
+    CU(ctx->j_chain.reserve((legacy ? 3 : 1) * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // legacy: general + simple + abutting queues
     CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_counters + 4, 0, 3 * sizeof(unsigned long long), ctx->compute));
@@ -935,25 +940,36 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     ChainQueue q; q.tasks = (uint32_t*)ctx->j_chain.p; q.cap = ctx->j_cap_chain; q.stride = stride; q.count = ctx->d_qcounts + 1; q.overflow = ctx->d_qovf;
     q.simple_tasks = q.tasks + ctx->j_cap_chain * stride; q.simple_count = ctx->d_qcounts + 2;
     q.abut_tasks = q.tasks + 2 * ctx->j_cap_chain * stride; q.abut_count = ctx->d_qcounts + 3;
+    CU(cudaMemsetAsync(ctx->d_counters + 18, 0, 2 * sizeof(unsigned long long), ctx->compute));
     CU(cudaEventRecord(ctx->kev[0], ctx->compute));
-    chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
-    CU(cudaEventRecord(ctx->kev[1], ctx->compute));
-    chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    CU(cudaEventRecord(ctx->kev[3], ctx->compute));
-    // launch bounds chosen by measurement on B200 (profiles/README.md): 64 registers for the abutting-chain kernel, 80 for the
-    // closure kernel -- both are latency-bound, so residency is traded against spills
-    chain_merge_abut_kernel<false, 8><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
-    CU(cudaEventRecord(ctx->kev[4], ctx->compute));
+    if (legacy) {
+      chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
+      CU(cudaEventRecord(ctx->kev[1], ctx->compute));
+      chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
+      CU(cudaEventRecord(ctx->kev[3], ctx->compute));
+      chain_merge_abut_kernel<false, 8><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
+      CU(cudaEventRecord(ctx->kev[4], ctx->compute));
+    } else {
+      // one pass over the batch: TMA-staged tiles of 32 reads, chain enumeration + the closure-free merges (join_tile_kernel.cuh)
+      const uint32_t n_tiles = (bv.n_bundles + 31u) / 32u;
+      const int grid = (int)std::min<uint64_t>((n_tiles + JT_WARPS - 1) / JT_WARPS, (uint64_t)ctx->sms * 64);
+      join_tile_kernel<5><<<grid, JT_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o, ctx->d_counters + 18);
+      CU(cudaEventRecord(ctx->kev[1], ctx->compute));
+      CU(cudaEventRecord(ctx->kev[3], ctx->compute)); CU(cudaEventRecord(ctx->kev[4], ctx->compute));
+    }
+    // launch bounds chosen by measurement on B200 (profiles/README.md): 80 registers for the closure kernel -- it is
+    // latency-bound, so residency is traded against spills
     chain_merge_kernel<6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
-    ctx->jtiming.launches += 4;
-    unsigned int ovf = 0; unsigned long long qn[4] = {0, 0, 0, 0};
+    ctx->jtiming.launches += legacy ? 4 : 2;
+    unsigned int ovf = 0; unsigned long long qn[4] = {0, 0, 0, 0}, tc[2] = {0, 0};
     CU(cudaMemcpyAsync(qn, ctx->d_qcounts, 32, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(tc, ctx->d_counters + 18, 16, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
-    n = qn[0]; qn_simple = qn[2]; qn_abut = qn[3];
+    n = qn[0]; qn_simple = legacy ? qn[2] : tc[0]; qn_abut = legacy ? qn[3] : tc[1];
     if (!ovf && n <= cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
       kms = a + b2; ctx->jtiming.enum_ms += a; ctx->jtiming.merge_ms += b2;
@@ -1013,7 +1029,7 @@ int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* b, uint64_t* n_ou
   int rc = join_validate(ctx, b); if (rc) return rc;
   if (b->n_bundles == 0) return THB_OK;
   JoinBatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits; bv.ops_ext = b->ops_ext;
-  bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = 0; bv.hit_end = (uint32_t)b->n_hits;
+  bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = 0; bv.hit_end = (uint32_t)b->n_hits; bv.ops_end = (uint32_t)b->n_ops_ext;
   unsigned long long n = 0;
   rc = join_run(ctx, bv, b->n_hits, b->n_ops_ext, &n, ctx->j_out, ctx->j_cap_out); if (rc) return rc;
   *n_out = n;
@@ -1065,7 +1081,7 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* b, const thb_joined** ou
     if (c + 1 < nchunks) { rc = enqueue_copy(c + 1); if (rc) return rc; }
     if (s.out_busy) CU(cudaStreamWaitEvent(ctx->compute, s.out_free, 0));      // records of chunk c-2 have left this buffer
     JoinBatchView bv; bv.bundles = (const thb_join_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p; bv.reads = (const uint64_t*)s.reads.p;
-    bv.hits = (const thb_jhit*)s.hits.p - r.h0; bv.ops_ext = (const thb_jops*)s.ops.p - r.e0; bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = r.b0; bv.hit_end = (uint32_t)r.h1;
+    bv.hits = (const thb_jhit*)s.hits.p - r.h0; bv.ops_ext = (const thb_jops*)s.ops.p - r.e0; bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.bundle_base = r.b0; bv.hit_end = (uint32_t)r.h1; bv.ops_end = (uint32_t)r.e1;
     unsigned long long n = 0;
     rc = join_run(ctx, bv, r.h1 - r.h0, r.e1 - r.e0, &n, s.out, s.cap_out); if (rc) return rc;       // returns with the compute stream idle
     rc = join_host_reserve(ctx, total + n, total); if (rc) return rc;
