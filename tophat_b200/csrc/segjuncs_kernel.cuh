@@ -80,6 +80,7 @@ struct BatchView {
   uint32_t n_bundles, n_segs, read_words; uint64_t order_base;
   uint64_t partner_base;                           // absolute index of the first partner hit present in this launch
   uint64_t hit_base;                               // absolute index of the first hit present in this launch
+  uint64_t hit_end, partner_end;                   // absolute indices one past the last hit / partner hit of this launch
 };
 
 // ---- task records -----------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "../../include/tophat_b200.h"
 #include "segjuncs_kernel.cuh"
+#include "scan_tile_kernel.cuh"
 #include "join_kernel.cuh"
 #include "join_tile_kernel.cuh"
 #include "fusion_kernel.cuh"
@@ -205,9 +206,17 @@ void launch_phase(thb_ctx* ctx, const BatchView& bv, const Queues& q, const SegO
   const int g_b = grid_for(bv.n_bundles, 256), g_h = grid_for(n_hits, 256), g_t = ctx->sms * 8;
   uint32_t* bstate = (uint32_t*)ctx->q_bstate.p; uint32_t* owner = (uint32_t*)ctx->q_owner.p;
   cudaEventRecord(ctx->kev[0], ctx->compute);
-  bundle_kernel<NSMAX><<<g_b, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner);
-  cudaEventRecord(ctx->kev[1], ctx->compute);
-  if (n_hits) hit_kernel<NSMAX><<<g_h, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, n_hits, o);
+  if (scan_legacy()) {
+    bundle_kernel<NSMAX><<<g_b, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner);
+    cudaEventRecord(ctx->kev[1], ctx->compute);
+    if (n_hits) hit_kernel<NSMAX><<<g_h, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, n_hits, o);
+  } else {
+    // one pass over the batch: TMA-staged tiles of 32 bundles, bundle bookkeeping + per-hit task construction (scan_tile_kernel.cuh)
+    const uint32_t n_tiles = (bv.n_bundles + 31u) / 32u;
+    const int grid = (int)std::min<uint64_t>((n_tiles + ST_WARPS - 1) / ST_WARPS, (uint64_t)ctx->sms * 64);
+    scan_tile_kernel<NSMAX><<<grid, ST_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, o);
+    cudaEventRecord(ctx->kev[1], ctx->compute);
+  }
   cudaEventRecord(ctx->kev[2], ctx->compute);
   rescue_kernel<<<g_t, 256, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q);
   cudaEventRecord(ctx->kev[3], ctx->compute);
@@ -255,7 +264,7 @@ int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t 
   else launch_phase<14>(ctx, bv, q, o, n_hits);
   CU(cudaGetLastError());
   ctx->kev_pending = true;
-  ctx->timing.kernel_launches++; ctx->own_launches += ctx->sp.fusion_search ? 8 : 6;
+  ctx->timing.kernel_launches++; ctx->own_launches += (ctx->sp.fusion_search ? 8 : 6) - (scan_legacy() ? 0 : 1);
   return THB_OK;
 }
 
@@ -299,6 +308,7 @@ int check_and_grow(thb_ctx* ctx, const unsigned long long* ins_before_p, bool* r
     CU(cudaStreamSynchronize(ctx->compute));
     ctx->d_fus.release(); ctx->d_fus = nb; ctx->cap_fus = ncap; *redo = true;
   }
+  if (f.err & 16u) return fail(ctx, THB_EINVAL, "hit ranges of consecutive bundles are not laid out back to back (hit_begin[i+1] != hit_begin[i] + hits of bundle i)");
   if (f.err & 2u) return fail(ctx, THB_EUNSUPPORTED, "more than %d rescued mate-anchor hits for one read (raise RES_MAX)", RES_MAX);
   if (f.qovf & 1u) { ctx->cap_win *= 2; *redo = true; }
   if (f.qovf & 2u) { ctx->cap_indel *= 2; *redo = true; }
@@ -635,7 +645,7 @@ int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* b)
   BatchView bv; bv.bundles = b->bundles; bv.seg_count = b->seg_count; bv.reads = b->reads; bv.hits = b->hits;
   bv.partner = b->partner_hits; bv.n_bundles = b->n_bundles; bv.n_segs = b->n_segs; bv.read_words = b->read_words;
   bv.order_base = b->order_base;
-  bv.partner_base = 0; bv.hit_base = 0;
+  bv.partner_base = 0; bv.hit_base = 0; bv.hit_end = b->n_hits; bv.partner_end = b->n_partner_hits;
   unsigned long long ins_before = ctx->h_ins_count;
   float ms_total = 0.f; bool done = false;
   for (int attempt = 0; attempt < 24 && !done; ++attempt) {
@@ -697,7 +707,7 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
     BatchView bv; bv.bundles = (const thb_bundle*)s.bundles.p; bv.seg_count = (const uint16_t*)s.seg_count.p;
     bv.reads = (const uint64_t*)s.reads.p; bv.hits = (const thb_hit*)s.hits.p - r.h0; bv.partner = (const thb_hit*)s.partner.p - r.p0;
     bv.n_bundles = r.nb; bv.n_segs = b->n_segs; bv.read_words = b->read_words; bv.order_base = b->order_base + r.b0;
-    bv.partner_base = r.p0; bv.hit_base = r.h0;
+    bv.partner_base = r.p0; bv.hit_base = r.h0; bv.hit_end = r.h1; bv.partner_end = r.p1;
     unsigned long long ins_before = ctx->h_ins_count;
     bool done = false;
     for (int attempt = 0; attempt < 24; ++attempt) {
