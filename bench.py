@@ -6,13 +6,18 @@
 One "step" = one pass of the hot path over one batch of synthetic 2x101 bp read pairs:
   stage 1 segment_juncs       thb_segjuncs_begin -> submit(left mates) -> submit(right mates) -> [N>1: NCCL all-gather
                               of the discovered sets] -> thb_segjuncs_finish
-  stage 2 long_spanning_reads thb_join_begin(junction / indel sets) -> join(left mates) -> join(right mates)  Workload at N=1: BASELINE.json configs[1] (10 M pairs, chr20-sized reference).  For
-N>1 every rank runs the same number of pairs (its own shard of reads, same reference): weak scaling.
+  stage 2 long_spanning_reads thb_join_begin(junction / indel sets) -> join(left mates) -> join(right mates)
+Default workload at every N: BASELINE.json configs[2] -- the configuration the metric is quoted on (hg38-sized reference at 1/2/4/8
+GPUs) -- sharded by read: 6.25 M pairs per GPU, so that N = 8 is the 50 M-pair configuration (weak scaling; every rank draws its own
+read chunks over the same genome).  --workload chr20 (configs[1], 10 M pairs) and --workload indel (configs[3]) are one flag away;
+their lines are kept under profiles/.
 
   value  : reads (mates) per second, whole job, inputs resident in HBM (CUDA events on the library's stream)
   e2e    : same metric through the C ABI with HOST (pinned) buffers: H2D copies + D2H results inside the timing
-  roofline : scan kernel, algorithmic bytes (SURVEY.md §8d formula on the actual task counts) / CUDA-event time
-  cpu_baseline : the reference's own segment_juncs binary (oracle/_ref) on a bounded sample, same box
+  roofline : dominant kernel, algorithmic bytes (SURVEY.md §8d formula on the actual task counts) / CUDA-event time; every kernel and
+             the non-kernel parts of the step are listed beside it
+  parity_checked : every rank, after the timed region: sharded + all-gathered sets == single context == CPU oracle on a 200 k-pair sample
+  cpu_baseline / drop_in_cli (N = 1) : the reference's own binaries (oracle/_ref) and OUR executables on the same BAM / FASTA files
 
 `--impl reference` times the reference CPU binary only (rank 0 alone under torchrun).
 """
@@ -38,7 +43,7 @@ CHR20 = 64_444_167
 HG38 = (248_956_422, 242_193_529, 198_295_559, 190_214_555, 181_538_259, 170_805_979, 159_345_973, 145_138_636, 138_394_717,
         133_797_422, 135_086_622, 133_275_309, 114_364_328, 107_043_718, 101_991_189, 90_338_345, 83_257_441, 80_373_285,
         58_617_616, 64_444_167, 46_709_983, 50_818_468, 156_040_895, 57_227_415)
-WORKLOAD = "chr20"            # set from --workload: chr20 (configs[1], default) | hg38 (configs[2]) | indel (configs[3])
+WORKLOAD = "hg38"             # set from --workload: hg38 (configs[2], default) | chr20 (configs[1]) | indel (configs[3])
 KERNELS = ("bundle", "hit", "rescue", "rescued_windows", "window_scan", "indel")
 METRIC = "spliced reads aligned/s (segment_juncs + long_spanning_reads), 2x101bp"
 UNIT = "reads/s"
@@ -52,16 +57,57 @@ def log(*a):
 # workload
 
 
-def make_workload(pairs: int, rank: int, workers: int, keep_candidates: bool = False, keep_truth: bool = False):
+def contig_lens(kind: str):
+    return HG38 if kind == "hg38" else (CHR20,)
+
+
+def default_pairs(kind: str) -> int:
+    # hg38: BASELINE configs[2] (50 M pairs over 8 GPUs) sharded by read: 6.25 M pairs per GPU at every N (weak scaling; N = 8 is configs[2])
+    return 6_250_000 if kind == "hg38" else 10_000_000
+
+
+_REFDATA = {}
+
+
+def get_refdata(kind: str, rank: int = 0, world: int = 1, barrier=None):
+    """The synthetic genome of a workload kind.  With several ranks on one box rank 0 generates it once and the others map
+    it from /dev/shm (an hg38-sized genome is 3.1 GB of codes + 1.2 GB of bit planes: not something to build 8 times)."""
     from tophat_b200 import synth
+    if kind in _REFDATA:
+        return _REFDATA[kind]
+    cfg = synth.SynthConfig(contig_lens=contig_lens(kind), n_pairs=1, seed=20240611)
+    t = time.time()
+    if world == 1:
+        rd = synth.make_reference(cfg)
+    else:
+        d = "/dev/shm/thb_bench_ref_%s_%s" % (kind, os.environ.get("MASTER_PORT", "0"))
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+            rd0 = synth.make_reference(cfg)
+            synth.save_refdata(rd0, d + ".tmp"); os.rename(d + ".tmp", d)
+            del rd0
+        barrier()
+        rd = synth.load_refdata(d)
+        barrier()
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)      # the mappings stay valid until the last rank exits
+    log("[bench] rank %d: %s reference ready in %.1f s" % (rank, kind, time.time() - t))
+    _REFDATA[kind] = rd
+    return rd
+
+
+def make_workload(pairs: int, rank: int, workers: int, keep_candidates: bool = False, keep_truth: bool = False, kind: str = None,
+                  refdata=None, seed_base: int = None):
+    from tophat_b200 import synth
+    kind = kind or WORKLOAD
     chunk = 500_000 if pairs >= 500_000 else max(1000, pairs)
     nchunks = (pairs + chunk - 1) // chunk
-    cfg = synth.SynthConfig(contig_lens=HG38 if WORKLOAD == "hg38" else (CHR20,), n_pairs=pairs, seed=20240611, chunk=chunk,
-                            indel_prob=0.5 if WORKLOAD == "indel" else 0.0,
-                            chunk_seed_base=rank * nchunks, keep_candidates=keep_candidates, keep_truth=keep_truth)
+    cfg = synth.SynthConfig(contig_lens=contig_lens(kind), n_pairs=pairs, seed=20240611, chunk=chunk,
+                            indel_prob=0.5 if kind == "indel" else 0.0,
+                            chunk_seed_base=rank * nchunks if seed_base is None else seed_base, keep_candidates=keep_candidates, keep_truth=keep_truth)
     t = time.time()
-    wl = synth.generate(cfg, workers=workers)
-    log("[bench] rank %d: generated %d pairs in %.1f s (%d workers)" % (rank, pairs, time.time() - t, workers))
+    wl = synth.generate(cfg, workers=workers, refdata=refdata if refdata is not None else get_refdata(kind))
+    log("[bench] rank %d: generated %d pairs (%s) in %.1f s (%d workers)" % (rank, pairs, kind, time.time() - t, workers))
     return wl
 
 
@@ -121,7 +167,9 @@ class ReferenceArm:
         return time.perf_counter() - t
 
     def startup(self, bins=None) -> float:
-        return min(self._run(self.tfiles, self.tbams, self.tjin, self.tdir, 1, bins, ".b200" if bins else "") for _ in range(2))
+        """Fixed cost of one step (three process starts: FASTA loads; ours also CUDA context + image upload), measured on a 1-pair
+        input with the SAME -p and the same (warm) file cache as the step; best of two."""
+        return min(self._run(self.tfiles, self.tbams, self.tjin, self.tdir, self.threads, bins, ".b200" if bins else "") for _ in range(2))
 
     def step(self, bins=None) -> float:
         return self._run(self.files, self.bams, self.jin, self.dir, self.threads, bins, ".b200" if bins else "")
@@ -137,10 +185,25 @@ def usable_threads(sample_pairs: int) -> int:
     return max(1, min(n, sample_pairs // 8000))
 
 
+def reference_kind() -> str:
+    # The reference binaries load the whole FASTA on every start (three starts per step): ~37 s each for an hg38-sized genome, which no
+    # bounded sample can amortise.  Their per-read work does not depend on the genome size, so the CPU arm of the hg38 workload is timed
+    # on the chr20-sized genome of the same generator (smaller working set: if anything this favours the reference).
+    return "chr20" if WORKLOAD == "hg38" else WORKLOAD
+
+
+def reference_note(st: float) -> str:
+    n = "bounded sample from the GPU arm's generator; value excludes the %.2f s fixed start-up (three FASTA loads) measured on a 1-pair input at the same -p" % st
+    if WORKLOAD == "hg38":
+        n += "; timed on the chr20-sized genome: an hg38-sized FASTA costs the reference ~37 s per process start, per-read work is genome-size independent"
+    return n
+
+
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
-    wl = make_workload(args.ref_pairs, 0, max(1, (os.cpu_count() or 1)), keep_truth=True)
+    kind = reference_kind()
+    wl = make_workload(args.ref_pairs, 0, max(1, (os.cpu_count() or 1)), keep_truth=True, kind=kind)
     threads = usable_threads(args.ref_pairs)
     arm = ReferenceArm(wl, args.ref_pairs, threads)
     try:
@@ -152,16 +215,15 @@ def run_reference_arm(args, rank: int, world: int):
         arm.close()
     reads = 2 * arm.sample_pairs
     per = sum(times) / len(times)
-    work = max(per - st, 1e-6)
-    val = reads / work
+    val = reads / (per - st) if per > st else reads / per
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args.ref_pairs, 1, note="bounded sample of the GPU arm's workload; value excludes the "
-                                      "%.2f s fixed start-up (FASTA load) measured on a 1-pair input" % st),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": "%d pairs (%d reads), oracle/_ref segment_juncs + long_spanning_reads (left, right) -p%d, wall %.2f s/step incl. %.2f s start-up"
-                                       % (arm.sample_pairs, reads, threads, per, st)},
+            "config": workload_config(args.ref_pairs, 1, note=reference_note(st)),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_cpu_count": os.cpu_count(), "kind": "reference",
+                             "wall_s_per_step": per, "startup_s": st, "value_incl_startup": reads / per,
+                             "sample": "%d pairs (%d reads), %s-sized genome, oracle/_ref segment_juncs + long_spanning_reads (left, right) -p%d of %d host "
+                                       "CPUs, wall %.2f s/step incl. %.2f s start-up" % (arm.sample_pairs, reads, kind, threads, os.cpu_count() or 0, per, st)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -169,7 +231,8 @@ def run_reference_arm(args, rank: int, world: int):
 
 def workload_config(pairs: int, world: int, note: str = ""):
     what = {"chr20": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, ",
-            "hg38": "BASELINE configs[2]: synthetic 2x101 bp pairs, hg38-sized reference (24 contigs, 3.09 Gbp, 0.5% N), ",
+            "hg38": "BASELINE configs[2] sharded by read (50 M pairs over 8 GPUs = 6.25 M per GPU): synthetic 2x101 bp pairs, hg38-sized reference "
+                    "(24 contigs, 3.09 Gbp, 0.5% N; 1.2 GB image, not L2-resident), ",
             "indel": "BASELINE configs[3]: indel-heavy synthetic 2x101 bp pairs (1-3 bp indel in half of the mates), chr20-sized reference, "}[WORKLOAD]
     c = {"workload": what + "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
          "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)",
@@ -226,6 +289,67 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
+# parity inside the measured run
+
+
+def _digest(res) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for a in (res.junctions, res.deletions, res.insertions, res.fusions):
+        h.update(np.ascontiguousarray(a).tobytes()); h.update(b"|")
+    return h.hexdigest()
+
+
+def parity_check(ctx, wl, P, rank: int, world: int, dist, total_pairs: int):
+    """Run by EVERY rank after the timed region, on the configuration being measured: a sample of `total_pairs` pairs (every rank
+    contributes the head of its own shard) goes through (1) the sharded path -- own batches + thb_segjuncs_allgather, (2) a
+    single context over all ranks' batches in the reference's processing order (left mates, then right mates: the -p1 answer,
+    segment_juncs.cpp:4752-4922) and (3) the CPU oracle (rank 0).  All three must agree record for record on every rank."""
+    from tophat_b200 import synth
+    from oracle import pyoracle
+    t0 = time.time()
+    sub = max(1000, min(wl.cfg.n_pairs, total_pairs // world))
+    swl = synth.subset(wl, sub)
+    mine = (synth.pack_side(swl.left, swl.right, False), synth.pack_side(swl.right, swl.left, True))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
+    order = [g[0] for g in gathered] + [g[1] for g in gathered]
+    base = 0
+    for b in order:
+        b.order_base = base; base += b.n_bundles
+    ctx.segjuncs_begin(P)
+    ctx.segjuncs_submit(gathered[rank][0]); ctx.segjuncs_submit(gathered[rank][1])
+    if world > 1:
+        ctx.segjuncs_allgather()
+    U = ctx.segjuncs_finish()
+    ctx.segjuncs_begin(P)
+    for b in order:
+        ctx.segjuncs_submit(b)
+    V = ctx.segjuncs_finish()
+    du, dv = _digest(U), _digest(V)
+    dorc = [None]
+    if rank == 0:
+        want, _ = pyoracle.segjuncs(P, wl.ref, order)
+        dorc[0] = _digest(want)
+    if world > 1:
+        dist.broadcast_object_list(dorc, src=0)
+    ok = {"sharded_union_equals_single_context": du == dv, "single_context_equals_cpu_oracle": dv == dorc[0]}
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        ok = {k: all(f[k] for f in flags) for k in ok}
+    out = {"pairs": sub * world, "bundles": int(base), "junctions": int(len(V.junctions)), "deletions": int(len(V.deletions)),
+           "insertions": int(len(V.insertions)), "ranks_checked": world, "seconds": round(time.time() - t0, 1)}
+    out.update(ok)
+    if not all(ok.values()):
+        raise AssertionError("parity check failed on rank %d: %r" % (rank, out))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
 # GPU arm
 
 
@@ -235,10 +359,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     import torch.distributed as dist
     from tophat_b200 import capi, synth
     torch.cuda.set_device(local_rank)
+    barrier = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
+        barrier = dist.barrier
     workers = max(1, (os.cpu_count() or 1) // world)
-    wl = make_workload(args.pairs, rank, workers, keep_candidates=True)
+    refdata = get_refdata(WORKLOAD, rank, world, barrier)
+    wl = make_workload(args.pairs, rank, workers, keep_candidates=True, refdata=refdata)
     batches = pack(wl)
     n_reads = 2 * args.pairs
     P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
@@ -319,7 +447,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = dict(scan_ms=0.0, alg=0, launches=0, join_ms=0.0, join_alg=0, join_launches=0, enum_ms=0.0, merge_ms=0.0,
-                   merge_simple_ms=0.0, merge_abutting_ms=0.0, merge_general_ms=0.0,
+                   merge_simple_ms=0.0, merge_abutting_ms=0.0, merge_general_ms=0.0, finish_ms=0.0, begin_ms=0.0,
                    kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
         for k_ in range(steps):
@@ -327,6 +455,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
             acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
             acc["enum_ms"] += jt.enum_ms; acc["merge_ms"] += jt.merge_ms
+            acc["finish_ms"] += tm.finish_ms; acc["begin_ms"] += jt.begin_ms
             for k in ("merge_simple_ms", "merge_abutting_ms", "merge_general_ms"):
                 acc[k] += getattr(jt, k)
             for k in KERNELS:
@@ -365,6 +494,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     if len(res.junctions):
         span = res.junctions["right"].astype(np.int64) - res.junctions["left"].astype(np.int64)
         assert span.min() >= 50 - 16 and span.max() <= 500000 + 25 + 16
+    # parity on this very configuration, every rank (N > 1: the all-gathered union against a single context and the CPU oracle)
+    parity = parity_check(ctx, wl, P, rank, world, dist, args.parity_pairs) if args.parity_pairs > 0 else None
 
     total_reads = n_reads * world
     per_step = A["ms"] / args.steps
@@ -380,36 +511,44 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         except Exception:
             pass
         # Per-kernel split of SURVEY.md 8(d)'s B_segjuncs / B_join, on this run's actual task counts:
-        #   bundle      : 16 (bundle header) per bundle + 16 per partner hit
-        #   hit         : 40 (read) per bundle + 16 per segment hit
+        #   scan_tile   : 16 (bundle header) + 40 (read) per bundle + 16 per segment hit + 16 per partner hit
         #   window_scan : 32 (descriptor) + 64 (two reference sectors) per window + 16 per emitted junction record
         #   rescue      : 32 + 128 per mate-anchor task;  indel: 32 + 64 per task + 16 per record
-        #   chain_enum  : 16 (header) per read + 16 per segment hit (the 16-byte wire record)
-        #   chain_merge : 40 (read) per read + 32 per multi-op hit + 128 per closure + 96 per merged chain + 128 per output record
+        #   join_tile   : 16 (header) per read + 16 per segment hit, + the share of [40 (read) per read + 32 per multi-op hit + 96 per merged
+        #                 chain + 128 per output record] of the chains it merges itself (those without a closure)
+        #   chain_merge : the same share for the chains with a closure + 128 per closure
+        legacy_scan, legacy_join = "THB_SCAN_LEGACY" in os.environ, "THB_JOIN_LEGACY" in os.environ
         n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
         n_hh = sum(int(b.hits.shape[0]) for b in batches)
         steps = args.steps
-        kbytes = {"bundle": 16 * n_b + 16 * (n_h - n_hh), "hit": 40 * n_b + 16 * n_hh,
-                  "window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
-                  "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions)),
-                  "chain_enum": 16 * sum(b.n_bundles for b in jbatches) + 16 * sum(int(b.hits.shape[0]) for b in jbatches)}
-        # the three merge kernels share the rest of B_join by their number of chains; the closure terms (128 per closure) belong
-        # to the general kernel alone
+        kbytes = {"window_scan": 96 * int(tm.n_windows) + 16 * int(tm.n_juncs_emitted), "rescue": 160 * int(tm.n_rescue_tasks),
+                  "rescued_windows": 0, "indel": 96 * int(tm.n_indel_tasks) + 16 * (len(res.deletions) + len(res.insertions))}
+        b_bundle, b_hit = 16 * n_b + 16 * (n_h - n_hh), 40 * n_b + 16 * n_hh
+        b_enum = 16 * sum(b.n_bundles for b in jbatches) + 16 * sum(int(b.hits.shape[0]) for b in jbatches)
         jt_ = A["jt"]
-        merge_total = A["join_alg"] / steps - kbytes["chain_enum"]
+        merge_total = A["join_alg"] / steps - b_enum
         n_ch = max(1, int(jt_.n_chains)); n_s, n_a = int(jt_.n_simple_chains), int(jt_.n_abutting_chains); n_g = max(0, n_ch - n_s - n_a)
         closure_bytes = 128.0 * int(jt_.n_closures)
         rest = max(0.0, merge_total - closure_bytes)
-        kbytes["chain_merge_simple"] = rest * n_s / n_ch
-        kbytes["chain_merge_abut"] = rest * n_a / n_ch
+        kms = {k: A["kms"][k] / steps for k in KERNELS}
+        if legacy_scan:
+            kbytes["bundle"], kbytes["hit"] = b_bundle, b_hit
+        else:
+            kbytes["scan_tile"] = b_bundle + b_hit
+            kms["scan_tile"] = kms.pop("bundle"); kms.pop("hit")
+        if legacy_join:
+            kbytes["chain_enum"] = b_enum
+            kbytes["chain_merge_simple"] = rest * n_s / n_ch; kbytes["chain_merge_abut"] = rest * n_a / n_ch
+            kms["chain_enum"] = A["enum_ms"] / steps
+            kms["chain_merge_simple"] = A["merge_simple_ms"] / steps; kms["chain_merge_abut"] = A["merge_abutting_ms"] / steps
+        else:
+            kbytes["join_tile"] = b_enum + rest * (n_s + n_a) / n_ch
+            kms["join_tile"] = A["enum_ms"] / steps
         kbytes["chain_merge"] = rest * n_g / n_ch + closure_bytes
-        kms = {k: A["kms"][k] / steps for k in KERNELS}; kms["chain_enum"] = A["enum_ms"] / steps
-        kms["chain_merge_simple"] = A["merge_simple_ms"] / steps; kms["chain_merge_abut"] = A["merge_abutting_ms"] / steps
         kms["chain_merge"] = A["merge_general_ms"] / steps
-        klaunch = {k: A["scan_launches"] for k in KERNELS}
-        allk = KERNELS + ("chain_enum", "chain_merge_simple", "chain_merge_abut", "chain_merge")
-        for k in allk[len(KERNELS):]:
-            klaunch[k] = max(1, A["join_launches"] // (4 * steps))
+        allk = tuple(kms.keys())
+        n_join_kernels = 4 if legacy_join else 2
+        klaunch = {k: (A["scan_launches"] if k in KERNELS or k == "scan_tile" else max(1, A["join_launches"] // (n_join_kernels * steps))) for k in allk}
         dom = max(allk, key=lambda k: kms[k])
         dom_ms = kms[dom] / klaunch[dom]; dom_bytes = kbytes[dom] / klaunch[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -419,26 +558,34 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                traffic = next((v for k, v in tj.items() if k.startswith(dom + "_kernel")), None)
+                traffic = next((v for k, v in tj.get(WORKLOAD, tj).items() if k.startswith(dom + "_kernel")), None)
             except Exception:
                 traffic = None
+        non_kernel = {"segjuncs_finish (set compaction, CUB sorts, decode, D2H of the sets)": A["finish_ms"] / steps,
+                      "join_begin (set upload, validation, bucket index build)": A["begin_ms"] / steps}
+        non_kernel["other (queue counters read back, launch gaps, Python between calls)"] = max(0.0, per_step - tot_ms - sum(non_kernel.values()))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(args.pairs, world),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": E["ms"] / args.steps,
-                        "api": "thb_segjuncs_begin/submit(host, pinned)/finish + thb_join_begin/submit(host, pinned)"},
+                        "api": "thb_segjuncs_begin/submit(host, pinned)/finish + thb_join_begin/submit(host, pinned); the packed batches are built "
+                               "once outside the timed region (in the executables that is BAM decoding: see drop_in_cli)"},
                 "gpu_launches": int(A["launches"]),
                 "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
-                             "frac": achieved / peaks, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peaks, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, per launch)" if traffic else None,
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
                              "launches_per_step": klaunch[dom],
                              "per_kernel_ms_per_step": kms,
                              "per_kernel_gbs": {k: (kbytes[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0) for k in allk},
+                             "per_kernel_frac": {k: (kbytes[k] / (kms[k] * 1e-3) / 1e9 / peaks if kms[k] > 0 else 0.0) for k in allk},
+                             "non_kernel_ms_per_step": non_kernel,
                              "all_kernels": {"ms_per_step": tot_ms, "algorithmic_bytes_per_step": tot_bytes,
                                              "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
                                              "frac": (tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks) if tot_ms > 0 else 0.0}},
-                "clocks": clocks,
+                "clocks": clocks, "parity_checked": parity,
+                "host": {"cpu_count": os.cpu_count()},
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
                             "indel_tasks": int(tm.n_indel_tasks), "rescue_tasks": int(tm.n_rescue_tasks),
@@ -446,48 +593,69 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                             "join_chains": int(A["jt"].n_chains), "join_closures": int(A["jt"].n_closures),
                             "join_simple_chains": int(A["jt"].n_simple_chains), "join_abutting_chains": int(A["jt"].n_abutting_chains)}}
     ctx.close()
+    del sj_keep, j_keep
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                threads = usable_threads(args.ref_pairs)
-                swl = make_workload(args.ref_pairs, 0, os.cpu_count() or 1, keep_truth=True)
-                arm = ReferenceArm(swl, args.ref_pairs, threads)
-                cli = None
-                try:
-                    st = arm.startup(); arm.step(); wall = arm.step()
-                    # the drop-in executables themselves (tophat_b200/bin, C++ hosts over the C ABI) on the very same files: BAM
-                    # decode, bundle building, GPU work, text / BAM output -- what a tophat.py run would see per stage
-                    try:
-                        from tophat_b200 import build as _b
-                        ours = (os.path.join(_b.BIN_DIR, "segment_juncs"), os.path.join(_b.BIN_DIR, "long_spanning_reads"))
-                        if all(os.access(x, os.X_OK) for x in ours):
-                            st_o = arm.startup(ours); arm.step(ours); wall_o = arm.step(ours)
-                            # compared with the reference at -p1: its own -pN output can lack junctions of reads at the thread
-                            # partition boundaries (observed: 1 of 28,969 at -p12 on this sample), ours equals the -p1 answer
-                            p1 = arm.py.run_segment_juncs(arm.sj, arm.files, arm.bams, arm.dir, arm.nseg, opts=arm.opts, threads=1, tag=".p1")
-                            same = all(open(os.path.join(arm.dir, "segment.b200." + k)).read() == open(p1[k]).read()
-                                       for k in ("juncs", "insertions", "deletions"))
-                            cli = {"value": 2 * arm.sample_pairs / max(wall_o - st_o, 1e-6), "unit": UNIT, "wall_s": wall_o, "startup_s": st_o,
-                                   "reference_wall_s": wall, "reference_startup_s": st, "segment_files_identical_to_reference_p1": same,
-                                   "note": "our segment_juncs + long_spanning_reads executables on the reference arm's sample files; "
-                                           "start-up (CUDA context, FASTA load, image upload) measured on a 1-pair input and excluded like the reference's"}
-                    except Exception as e:
-                        cli = {"value": None, "note": "failed: %r" % (e,)}
-                finally:
-                    arm.close()
+                cpu, cli = cpu_and_cli(args)
+                line["cpu_baseline"] = cpu
                 if cli is not None:
                     line["drop_in_cli"] = cli
-                reads = 2 * arm.sample_pairs
-                line["cpu_baseline"] = {"value": reads / max(wall - st, 1e-6), "unit": UNIT, "cores": threads, "kind": "reference",
-                                        "sample": "%d pairs (%d reads) from the same generator and reference; oracle/_ref segment_juncs + "
-                                                  "long_spanning_reads (left, right) -p%d; wall %.2f s of which %.2f s fixed start-up "
-                                                  "(FASTA loads, excluded)" % (arm.sample_pairs, reads, threads, wall, st)}
             except Exception as e:  # the baseline leg must never hide the GPU result
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_and_cli(args):
+    """cpu_baseline (the reference's own binaries) and drop_in_cli (OUR executables on the same BAM / FASTA files: BAM decode, bundle
+    building, GPU work, text / BAM output -- what a tophat.py run sees per stage), both as plain wall clock of one step = segment_juncs +
+    long_spanning_reads (left) + long_spanning_reads (right) at -p<threads>, file cache warm, nothing subtracted or clamped; the fixed
+    start-up of a step (measured on a 1-pair input at the same -p) is reported beside it."""
+    kind = reference_kind()
+    threads = usable_threads(args.cli_pairs)
+    swl = make_workload(args.cli_pairs, 0, os.cpu_count() or 1, keep_truth=True, kind=kind)
+    arm = ReferenceArm(swl, args.cli_pairs, threads)
+    cli = None
+    try:
+        reads = 2 * arm.sample_pairs
+        st = arm.startup(); arm.step(); wall = arm.step()
+        cpu = {"value": reads / (wall - st) if wall > st else reads / wall, "unit": UNIT, "cores": threads, "host_cpu_count": os.cpu_count(), "kind": "reference",
+               "wall_s": wall, "startup_s": st, "value_incl_startup": reads / wall,
+               "sample": "%d pairs (%d reads) from the same generator, %s-sized genome; oracle/_ref segment_juncs + long_spanning_reads (left, right) "
+                         "-p%d of %d host CPUs; wall %.2f s of which %.2f s fixed start-up (three FASTA loads; `value` excludes it, "
+                         "`value_incl_startup` does not)" % (arm.sample_pairs, reads, kind, threads, os.cpu_count() or 0, wall, st)}
+        try:
+            from tophat_b200 import build as _b
+            ours = (os.path.join(_b.BIN_DIR, "segment_juncs"), os.path.join(_b.BIN_DIR, "long_spanning_reads"))
+            if all(os.access(x, os.X_OK) for x in ours):
+                st_o = arm.startup(ours); arm.step(ours); wall_o = arm.step(ours)
+                # our output equals the reference's -p1 answer (tests/test_cli_*); the reference's own -pN output can lack junctions of
+                # reads at its thread-partition boundaries, so here: every line the reference found must be in ours, and the count of
+                # extra lines is reported (exact equality vs -p1 is checked when the sample is small enough for a -p1 run)
+                cmp_ = {}
+                for k in ("juncs", "insertions", "deletions"):
+                    a = open(os.path.join(arm.dir, "segment.b200." + k)).read().splitlines(); b = open(arm.outs[k]).read().splitlines()
+                    cmp_[k] = {"ours": len(a), "reference_pN": len(b), "reference_lines_missing_from_ours": len(set(b) - set(a))}
+                same_p1 = None
+                if arm.sample_pairs <= 150_000:
+                    p1 = arm.py.run_segment_juncs(arm.sj, arm.files, arm.bams, arm.dir, arm.nseg, opts=arm.opts, threads=1, tag=".p1")
+                    same_p1 = all(open(os.path.join(arm.dir, "segment.b200." + k)).read() == open(p1[k]).read() for k in ("juncs", "insertions", "deletions"))
+                cli = {"value": reads / wall_o, "unit": UNIT, "wall_s": wall_o, "startup_s": st_o,
+                       "value_excl_startup": reads / (wall_o - st_o) if wall_o > st_o else None,
+                       "reference_wall_s": wall, "reference_startup_s": st, "reference_value": reads / wall,
+                       "speedup_wall": wall / wall_o, "threads": threads, "pairs": arm.sample_pairs,
+                       "segment_files_vs_reference_pN": cmp_, "segment_files_identical_to_reference_p1": same_p1,
+                       "note": "our segment_juncs + long_spanning_reads executables on the reference arm's sample files, whole wall clock of a step "
+                               "(process starts, CUDA context, FASTA / image load included)"}
+        except Exception as e:
+            cli = {"value": None, "note": "failed: %r" % (e,)}
+    finally:
+        arm.close()
+    return cpu, cli
 
 
 def main():
@@ -495,16 +663,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("THB_BENCH_PAIRS", 10_000_000)), help="read pairs per GPU")
-    ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 100_000)),
-                    help="pairs in the bounded sample the reference CPU binary is timed on")
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("THB_BENCH_PAIRS", 0)), help="read pairs per GPU (default: by workload)")
+    ap.add_argument("--ref-pairs", type=int, default=int(os.environ.get("THB_BENCH_REF_PAIRS", 250_000)),
+                    help="pairs in the bounded sample the reference CPU binaries are timed on (--impl reference); >= 8000 x host CPUs lets -p use them all")
+    ap.add_argument("--cli-pairs", type=int, default=int(os.environ.get("THB_BENCH_CLI_PAIRS", 500_000)),
+                    help="pairs in the sample on which cpu_baseline and drop_in_cli are timed inside the GPU arm's run (N = 1)")
+    ap.add_argument("--parity-pairs", type=int, default=200_000, help="pairs in the in-run parity check (0 = off)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chr20", choices=["chr20", "hg38", "indel"],
-                    help="chr20 = BASELINE configs[1] (the default, the configuration the metric is quoted on at one GPU); hg38 = configs[2]; indel = configs[3]")
+    ap.add_argument("--workload", default=os.environ.get("THB_BENCH_WORKLOAD", "hg38"), choices=["chr20", "hg38", "indel"],
+                    help="hg38 = BASELINE configs[2] (the configuration the metric is quoted on: hg38-sized reference at 1/2/4/8 GPUs, sharded by read); "
+                         "chr20 = configs[1]; indel = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    if args.pairs <= 0:
+        args.pairs = default_pairs(WORKLOAD)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)

@@ -296,14 +296,17 @@ int thb_join_submit(thb_ctx* ctx, const thb_join_batch* host_batch, const thb_jo
  * thb_join_fetch copies them to the host (same lifetime as above).                                          */
 int thb_join_submit_device(thb_ctx* ctx, const thb_join_batch* device_batch, uint64_t* n_out);
 int thb_join_fetch(thb_ctx* ctx, const thb_joined** out, uint64_t* n_out);
-/* h2d_ms: wall time of thb_join_submit's pipeline (upload, kernels and download of consecutive chunks overlap);
+/* Since round 2 the enumeration and the closure-free merges are one kernel (join_tile_kernel): its time is enum_ms,
+ * merge_simple_ms / merge_abutting_ms stay 0, merge_general_ms is the closure kernel.
+ * h2d_ms: wall time of thb_join_submit's pipeline (upload, kernels and download of consecutive chunks overlap);
  * d2h_ms: thb_join_fetch only.                                                                                 */
 typedef struct thb_join_timing { float h2d_ms, kernel_ms, d2h_ms; float enum_ms, merge_ms;   /* kernel_ms = enum + merge */
                                  uint32_t launches;
                                  uint64_t n_chains, n_closures, n_joined, algorithmic_bytes;
                                  uint64_t n_simple_chains, n_abutting_chains;   /* chains merged without a closure search */
                                  float merge_simple_ms, merge_abutting_ms, merge_general_ms;   /* the three merge kernels  */
-                                 float reserved_f; } thb_join_timing;
+                                 float begin_ms;   /* thb_join_begin: set upload, validation, bucket index build (CUDA events) */
+                               } thb_join_timing;
 int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out);
 
 /* Kernel timing of the last submit (CUDA events on the context's stream), milliseconds.        */

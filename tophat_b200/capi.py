@@ -72,7 +72,7 @@ class JoinTimingC(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("enum_ms", C.c_float), ("merge_ms", C.c_float), ("launches", C.c_uint32),
                 ("n_chains", C.c_uint64), ("n_closures", C.c_uint64), ("n_joined", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("n_simple_chains", C.c_uint64), ("n_abutting_chains", C.c_uint64),
-                ("merge_simple_ms", C.c_float), ("merge_abutting_ms", C.c_float), ("merge_general_ms", C.c_float), ("reserved_f", C.c_float)]
+                ("merge_simple_ms", C.c_float), ("merge_abutting_ms", C.c_float), ("merge_general_ms", C.c_float), ("begin_ms", C.c_float)]
 
 
 def join_batch_c(b: "synth.PackedJoinBatch") -> JoinBatchC:

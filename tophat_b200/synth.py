@@ -507,9 +507,19 @@ def _gen_chunk(ci: int):
     return acc
 
 
-def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
-    """Reference + reads + analytic hits.  Chunks of cfg.chunk fragments carry their own RNG stream
-    (seed, chunk index), so the result does not depend on `workers` (fork-based process pool)."""
+@dataclasses.dataclass
+class RefData:
+    """The synthetic genome + its annotation: what generate() needs besides the read parameters.  Depends only on
+    (contig_lens, seed, ref_n_frac, exon / intron distribution), so ranks of one box can share one copy (save_refdata /
+    load_refdata: arrays memory-mapped from /dev/shm)."""
+    names: List[str]
+    contigs: List[np.ndarray]
+    exons_pc: List[np.ndarray]
+    introns: np.ndarray
+    ref: RefImage
+
+
+def make_reference(cfg: SynthConfig) -> RefData:
     rng = np.random.default_rng(np.random.PCG64(cfg.seed))
     names, contigs, exons_pc, anns = [], [], [], []
     for ci, n in enumerate(cfg.contig_lens):
@@ -519,13 +529,44 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
         exons_pc.append(ex)
         anns.append(ann)
     ref = build_ref_image(names, contigs)
+    introns = np.concatenate(anns) if anns else np.zeros(0)
+    return RefData(names, contigs, exons_pc, introns, ref)
+
+
+def save_refdata(rd: RefData, dirname: str) -> None:
+    os.makedirs(dirname, exist_ok=True)
+    for i, (c, e) in enumerate(zip(rd.contigs, rd.exons_pc)):
+        np.save(os.path.join(dirname, "contig%d.npy" % i), c); np.save(os.path.join(dirname, "exons%d.npy" % i), e)
+    np.save(os.path.join(dirname, "introns.npy"), rd.introns)
+    for k in ("contig_start", "contig_len", "planes", "nmask"):
+        np.save(os.path.join(dirname, "ref_%s.npy" % k), getattr(rd.ref, k))
+    with open(os.path.join(dirname, "names.txt"), "w") as f:
+        f.write("\n".join(rd.names) + "\n")
+
+
+def load_refdata(dirname: str) -> RefData:
+    names = open(os.path.join(dirname, "names.txt")).read().split()
+    mm = lambda n: np.load(os.path.join(dirname, n), mmap_mode="r")
+    contigs = [mm("contig%d.npy" % i) for i in range(len(names))]
+    exons = [np.load(os.path.join(dirname, "exons%d.npy" % i)) for i in range(len(names))]
+    ref = RefImage(names, np.load(os.path.join(dirname, "ref_contig_len.npy")), np.load(os.path.join(dirname, "ref_contig_start.npy")),
+                   mm("ref_planes.npy"), mm("ref_nmask.npy"), contigs)
+    return RefData(names, contigs, exons, np.load(os.path.join(dirname, "introns.npy")), ref)
+
+
+def generate(cfg: SynthConfig, workers: int = 1, refdata: Optional[RefData] = None) -> Workload:
+    """Reference + reads + analytic hits.  Chunks of cfg.chunk fragments carry their own RNG stream
+    (seed, chunk index), so the result does not depend on `workers` (fork-based process pool)."""
+    if refdata is None:
+        refdata = make_reference(cfg)
+    contigs, exons_pc, ref = refdata.contigs, refdata.exons_pc, refdata.ref
     space = _ExonSpace(exons_pc)
     ex_parts = []
     for ci, ex in enumerate(exons_pc):
         ln = ex[:, 1] - ex[:, 0]
         cum = np.concatenate([[0], np.cumsum(ln)])
         idx = np.arange(int(cum[-1])) - np.repeat(cum[:-1], ln) + np.repeat(ex[:, 0], ln)
-        ex_parts.append(contigs[ci][idx])
+        ex_parts.append(np.asarray(contigs[ci][idx]))
     exonic = np.concatenate(ex_parts)
     L = cfg.read_len
     offs, lens = segment_layout(L, cfg.segment_length)
@@ -597,8 +638,7 @@ def generate(cfg: SynthConfig, workers: int = 1) -> Workload:
                 truth["fwd"][idx] = f; truth["gpos"][idx] = gp; truth["ref_id"][idx] = rid; truth["rev"][idx] = rv
         return SideData(reads, np.arange(1, cfg.n_pairs + 1, dtype="<u4"), seg_hits, mh, unm, cand, truth)
 
-    introns = np.concatenate(anns) if anns else np.zeros(0)
-    return Workload(cfg, ref, finish("left"), finish("right"), introns)
+    return Workload(cfg, ref, finish("left"), finish("right"), refdata.introns)
 
 
 def subset(wl: Workload, n_pairs: int) -> Workload:
