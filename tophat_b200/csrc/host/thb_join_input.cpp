@@ -8,71 +8,88 @@ namespace thbhost {
 namespace {
 
 // CigarOpCode values of the reference (bwt_map.h:36-55)
-enum { C_MATCH = 1, C_INS = 3, C_DEL = 5, C_REF_SKIP = 11, C_SOFT_CLIP = 13, C_HARD_CLIP = 14, C_PAD = 15 };
+enum { C_MATCH = 1, C_mATCH = 2, C_INS = 3, C_iNS = 4, C_DEL = 5, C_dEL = 6, C_FUSION_FF = 7, C_FUSION_FR = 8, C_FUSION_RF = 9, C_FUSION_RR = 10,
+       C_REF_SKIP = 11, C_rEF_SKIP = 12, C_SOFT_CLIP = 13, C_HARD_CLIP = 14, C_PAD = 15 };
 struct Op { int code; int len; };
 
 inline uint32_t pack_op(const Op& o) { return ((uint32_t)o.len << 4) | (uint32_t)o.code; }
 
-// cigar_add (bwt_map.cpp:670-676): extends an equal trailing op AND still appends the op (sic)
-void cigar_add(std::vector<Op>& c, const Op& op)
-{
-  if (op.len <= 0) return;
-  if (!c.empty() && c.back().code == op.code) c.back().len += op.len;
-  c.push_back(op);
-}
+// ---- placing a junction-index hit back on the genome ------------------------------------------------------------------
+// A segment that bowtie aligned to a juncs_db contig (the two flanks of a junction / deletion / fusion glued together, or
+// a reference stretch with an insertion's bases spliced in) carries a CIGAR against that contig.  On the genome the same
+// alignment has one more operation -- the event -- at reference offset `at` from the hit's start:
+//   gap events (REF_SKIP, DEL, FUSION_*): zero-width on the contig; the operation covering `at` is cut in two around it, or,
+//       when `at` falls on the boundary in front of an operation, the gap goes in front of that operation;
+//   INS: the contig bases [at, at + len) are the inserted bases; what the hit's operations cover of them becomes one INS
+//       operation (shortened when the hit starts inside the insertion).
+// Behaviour contract = the reference's spliceCigar (bwt_map.cpp:678-883), including two quirks that change records:
+//   * its appender lengthens an equal trailing operation AND still appends the new one (bwt_map.cpp:672-677);
+//   * a hit that does not reach the event from the left (event at or before the hit's first base) or that ends exactly at it
+//     never gains the two extra operations and is rejected by the final size test (874).
+// Fusion events: the operations on the far side of the fusion point are the lower-case codes when that side is read
+// leftwards (FR / RR: after the point, RF / RR: before it; bwt_map.h:36-55).
+struct EventOnContig { int code; int at; int len; };
 
-// spliceCigar (bwt_map.cpp:678-883) for INS / DEL / REF_SKIP events
-bool splice_cigar(std::vector<Op>& spl, const std::vector<Op>& cigar, const std::vector<bool>& mism, int& left, int spl_start,
+inline bool is_fusion_code(int c) { return c >= C_FUSION_FF && c <= C_FUSION_RR; }
+inline int lower_case(int c) { return c == C_MATCH ? C_mATCH : c == C_INS ? C_iNS : c == C_DEL ? C_dEL : c == C_REF_SKIP ? C_rEF_SKIP : c; }
+
+struct SplicedCigarBuilder {
+  std::vector<Op>& out;
+  void put(int code, int len)
+  {
+    if (len <= 0) return;
+    if (!out.empty() && out.back().code == code) out.back().len += len;      // sic: and the operation is appended as well
+    out.push_back(Op{code, len});
+  }
+};
+
+// Returns false where the reference discards the hit.  `spl_mismatches` receives the MD mismatches the reference attributes to
+// the event: within min_anchor_len of a gap, or on inserted bases.
+bool splice_cigar(std::vector<Op>& spl, const std::vector<Op>& cigar, const std::vector<bool>& mism, int left, int spl_start,
                   int spl_len, int spl_code, int& spl_mismatches, int min_anchor_len)
 {
-  const int spl_ofs = spl_start - left;
-  int spl_ofs_end = spl_ofs;
-  const Op gapop{spl_code, spl_len};
-  if (spl_code == C_INS) spl_ofs_end += spl_len;
-  int ref_ofs = 0, read_ofs = 0; bool xfound = false;
-  if (spl_ofs_end > 0) {
-    for (size_t c = 0; c < cigar.size(); ++c) {
-      const int prev_read_ofs = read_ofs, cur_op_ofs = ref_ofs, cur_opcode = cigar[c].code, cur_oplen = cigar[c].len;
-      switch (cur_opcode) {
-        case C_MATCH:
-          ref_ofs += cur_oplen; read_ofs += cur_oplen;
-          if (spl_code == C_REF_SKIP || spl_code == C_DEL) {
-            for (int o = cur_op_ofs; o < ref_ofs; ++o) { const int rofs = prev_read_ofs + (o - cur_op_ofs);
-              if (std::abs(spl_ofs - o) < min_anchor_len && rofs >= 0 && (size_t)rofs < mism.size() && mism[rofs]) spl_mismatches++; }
-          } else if (spl_code == C_INS) {
-            for (int o = cur_op_ofs; o < ref_ofs; ++o) { const int rofs = prev_read_ofs + (o - cur_op_ofs);
-              if (o >= spl_ofs && o < spl_ofs_end && rofs >= 0 && (size_t)rofs < mism.size() && mism[rofs]) spl_mismatches++; }
-          }
-          break;
-        case C_DEL: case C_REF_SKIP: case C_PAD: ref_ofs += cur_oplen; break;
-        case C_SOFT_CLIP: case C_INS: read_ofs += cur_oplen; break;
+  EventOnContig ev{spl_code, spl_start - left, spl_len};
+  const bool fusion = is_fusion_code(spl_code), insertion = spl_code == C_INS;
+  if (fusion && ev.at < 0) ev.at = -ev.at;
+  const int ev_end = insertion ? ev.at + ev.len : ev.at;          // first contig offset behind the event
+  if (ev_end <= 0) return false;                                  // the hit lies wholly behind the event: never spliced (871-874)
+  const bool lower_before = spl_code == C_FUSION_RF || spl_code == C_FUSION_RR;
+  const bool lower_after = spl_code == C_FUSION_FR || spl_code == C_FUSION_RR;
+  SplicedCigarBuilder b{spl};
+  int ref_at = 0, read_at = 0; bool behind_event = false;
+  for (const Op& op : cigar) {
+    const int a = ref_at, r0 = read_at;
+    const bool on_ref = op.code == C_MATCH || op.code == C_DEL || op.code == C_REF_SKIP || op.code == C_PAD;
+    const bool on_read = op.code == C_MATCH || op.code == C_INS || op.code == C_SOFT_CLIP;
+    if (on_ref) ref_at += op.len;
+    if (on_read) read_at += op.len;
+    const int z = ref_at;                                         // the operation covers contig offsets [a, z)
+    if (op.code == C_MATCH)
+      for (int r = r0; r < read_at; ++r) {
+        if (r < 0 || (size_t)r >= mism.size() || !mism[r]) continue;
+        const int o = a + (r - r0);
+        if (insertion ? (o >= ev.at && o < ev_end) : std::abs(ev.at - o) < min_anchor_len) ++spl_mismatches;
       }
-      if (cur_op_ofs >= spl_ofs_end || ref_ofs <= spl_ofs) {
-        if (cur_op_ofs == spl_ofs_end && spl_code != C_INS && cur_opcode != C_INS) { xfound = true; cigar_add(spl, gapop); }
-        cigar_add(spl, cigar[c]);
-      } else {
-        xfound = true;
-        if (spl_code == C_INS) {
-          Op op = cigar[c]; op.len = spl_ofs - cur_op_ofs;
-          if (spl_ofs > cur_op_ofs) cigar_add(spl, op);
-          if (spl_ofs < 0) { Op t = gapop; t.len += spl_ofs; if (t.len > 0) cigar_add(spl, t); }
-          else cigar_add(spl, gapop);
-          op.len = ref_ofs - spl_ofs_end;
-          if (ref_ofs > spl_ofs_end) cigar_add(spl, op);
-        } else {
-          Op op = cigar[c]; op.len = spl_ofs - cur_op_ofs; cigar_add(spl, op);
-          cigar_add(spl, gapop);
-          op.len = ref_ofs - spl_ofs; cigar_add(spl, op);
-        }
-      }
+    if (a >= ev_end || z <= ev.at) {                              // untouched by the event
+      if (a == ev_end && !insertion && op.code != C_INS) { behind_event = true; b.put(ev.code, ev.len); }
+      const bool lower = behind_event ? lower_after : lower_before;
+      b.put(lower ? lower_case(op.code) : op.code, op.len);
+      continue;
+    }
+    behind_event = true;
+    if (insertion) {
+      b.put(op.code, ev.at - a);
+      b.put(C_INS, ev.at < 0 ? ev.len + ev.at : ev.len);          // a hit starting inside the insertion sees only its tail
+      b.put(op.code, z - ev_end);
+    } else {
+      b.put(lower_before ? lower_case(op.code) : op.code, ev.at - a);
+      b.put(ev.code, ev.len);
+      b.put(lower_after ? lower_case(op.code) : op.code, z - ev.at);
     }
   }
-  (void)xfound;
-  if (spl_ofs_end <= 0) { if (spl_code == C_INS) left -= spl_len; else left += spl_len; spl = cigar; }
   if (spl.size() < cigar.size() + 2) return false;
-  if (spl.front().code != C_MATCH) return false;
-  if (spl.back().code != C_MATCH) return false;
-  return true;
+  const int f = spl.front().code, l = spl.back().code;
+  return (f == C_MATCH || f == C_mATCH) && (l == C_MATCH || l == C_mATCH);
 }
 
 void split(const std::string& s, char sep, std::vector<std::string>& out, bool strict)
