@@ -3,6 +3,8 @@ cooperative fibers, warp collectives = barriers; see tests/emu/shim/cuda_runtime
 This is a development harness for catching logic and warp-divergence bugs before GPU time is spent; the parity gate
 remains tests/test_gpu_*.py (-m gpu), which run the real sm_100a build."""
 import os
+import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -213,3 +215,17 @@ def test_emu_cli_join_option_variants_match_reference(over):
             assert a == b, "%s: records differ under %r (%d vs %d)" % (side, over, len(a), len(b))
             n += len(b)
         assert n > 100
+
+
+def test_emu_join_tile_kernel_equals_queue_kernels():
+    """Multi-hit-heavy reads (more than 8 hits in a segment, more than 4 chains per read): the tile kernel's generic walk and parking
+    overflow give the records of round 1's queue kernels (tests/emu/join_variant_check.py, one process per variant)."""
+    outs = []
+    for legacy in (False, True):
+        env = dict(os.environ); env.pop("THB_JOIN_LEGACY", None); env.pop("THB_CHECK_GPU", None)
+        if legacy:
+            env["THB_JOIN_LEGACY"] = "1"
+        r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "join_variant_check.py")], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("JOIN_DIGEST")][-1])
+    assert outs[0] == outs[1] and int(outs[0].split()[-1]) > 3000

@@ -92,9 +92,24 @@ def test_24_contig_join_matches_reference_binary():
     ctx.close()
 
 
+@pytest.mark.skipif(SMALL, reason="runs the real library in a fresh process")
 def test_growth_paths_on_hardware():
     """THB_TINY_CAPS=1 in a fresh process on the GPU: overflow -> grow -> repeat of every device structure (tests/gpu_tiny_caps_check.py)."""
     env = dict(os.environ, THB_TINY_CAPS="1")
     r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "gpu_tiny_caps_check.py")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "tiny caps ok: join goldens" in r.stdout
+
+
+@pytest.mark.skipif(SMALL, reason="runs the real library in a fresh process")
+def test_join_tile_kernel_equals_queue_kernels_on_hardware():
+    """The tile kernel against round 1's queue kernels (THB_JOIN_LEGACY=1) on multi-hit-heavy reads, on the GPU."""
+    outs = []
+    for legacy in (False, True):
+        env = dict(os.environ, THB_CHECK_GPU="1"); env.pop("THB_JOIN_LEGACY", None)
+        if legacy:
+            env["THB_JOIN_LEGACY"] = "1"
+        r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "join_variant_check.py")], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("JOIN_DIGEST")][-1])
+    assert outs[0] == outs[1] and int(outs[0].split()[-1]) > 3000

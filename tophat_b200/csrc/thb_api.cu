@@ -945,7 +945,8 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
   const uint32_t stride = bv.n_segs + 1;
   for (int attempt = 0; attempt < 24; ++attempt) {
     CU(out_buf.reserve(cap_out * sizeof(thb_joined)));
-    const bool legacy = join_legacy();
+    // reads of up to four segments (2x101 bp at --segment-length 25) take the tile kernel; other layouts the queue kernels
+    const bool legacy = join_legacy() || bv.n_segs > (uint32_t)JT_SEGS || !(bv.read_words == 2 || bv.read_words == 4);
     CU(ctx->j_chain.reserve((legacy ? 3 : 1) * ctx->j_cap_chain * stride * sizeof(uint32_t)));     // legacy: general + simple + abutting queues
     CU(cudaMemsetAsync(ctx->d_qcounts, 0, 4 * sizeof(unsigned long long), ctx->compute));
     CU(cudaMemsetAsync(ctx->d_qovf, 0, sizeof(unsigned int), ctx->compute));
@@ -967,7 +968,8 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
       // one pass over the batch: TMA-staged tiles of 32 reads, chain enumeration + the closure-free merges (join_tile_kernel.cuh)
       const uint32_t n_tiles = (bv.n_bundles + 31u) / 32u;
       const int grid = (int)std::min<uint64_t>((n_tiles + JT_WARPS - 1) / JT_WARPS, (uint64_t)ctx->sms * 64);
-      join_tile_kernel<5><<<grid, JT_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o, ctx->d_counters + 18);
+      if (bv.read_words == 2) join_tile_kernel<2, 6><<<grid, JT_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o, ctx->d_counters + 18);
+      else join_tile_kernel<4, 6><<<grid, JT_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o, ctx->d_counters + 18);
       CU(cudaEventRecord(ctx->kev[1], ctx->compute));
       CU(cudaEventRecord(ctx->kev[3], ctx->compute)); CU(cudaEventRecord(ctx->kev[4], ctx->compute));
     }
