@@ -40,6 +40,10 @@ extern "C" {
 
 typedef struct thb_ctx thb_ctx;
 
+/* Segments per read both stages accept (reads of up to 12 x --segment-length bases; the reference has no fixed limit, tophat.py
+ * splits 2x101 bp reads into 4).  One limit for batches and executables alike.                                                  */
+#define THB_MAX_SEGS 12
+
 /* ---- option globals consumed on the hot path (common.cpp:79-180, parsed at common.cpp:459-721) */
 typedef struct thb_params {
   int32_t segment_length;             /* --segment-length            (common.cpp:121) 25      */

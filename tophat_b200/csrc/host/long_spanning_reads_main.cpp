@@ -88,7 +88,7 @@ int main(int argc, char** argv)
   if (seg_files.empty()) { fprintf(stderr, "No hits to process, exiting\n"); return 0; }          // 2883-2887
   if (o.color) die("Error: colorspace reads are outside the GPU path");
   if (o.p.fusion_search) die("Error: --fusion-search is not implemented on the GPU join path yet");
-  if (seg_files.size() > 12) die("Error: more than 12 segments per read are not supported by the GPU path");
+  if (seg_files.size() > THB_MAX_SEGS) die("Error: more than %s segments per read are not supported by the GPU path", std::to_string(THB_MAX_SEGS));
 
   thb_ctx* ctx = nullptr;
   const char* dev_env = getenv("TOPHAT_GPU_DEVICE");
@@ -317,6 +317,8 @@ int main(int argc, char** argv)
   for (auto& h : contig) if (!h->ok()) die("Error: %s", h->error());
   for (auto& h : spliced) if (!h->ok()) die("Error: %s", h->error());
   if (!reads.ok()) die("Error: %s", reads.error());
+  { uint64_t dropped = 0; for (auto& h : contig) dropped += h->dropped_long_cigars(); for (auto& h : spliced) dropped += h->dropped_long_cigars();
+    if (dropped) die("Error: %s segment hits carry more than 9 CIGAR operations (outside the GPU path; the output would lack their alignments)", std::to_string(dropped)); }
   if (!bw.close(&err)) die("Error: %s", err);
   auto t2 = std::chrono::steady_clock::now();
   if (getenv("TOPHAT_GPU_STATS")) {

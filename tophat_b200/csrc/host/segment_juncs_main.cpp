@@ -72,7 +72,7 @@ static void process_side(thb_ctx* ctx, const Options& o, RefTable& rt, std::mute
                          bool right_mate, uint64_t& order_base, Stats& st)
 {
   const uint32_t nseg = (uint32_t)segs.size();
-  if (nseg > 16) die("Error: more than 16 segments per read are not supported by the GPU path");
+  if (nseg > THB_MAX_SEGS) die("Error: more than %s segments per read are not supported by the GPU path", std::to_string(THB_MAX_SEGS));
   std::vector<std::unique_ptr<HitStream>> hs;
   for (auto& f : segs) hs.emplace_back(new HitStream(f, rt, rtm, o.p.max_report_intron_length));
   std::unique_ptr<HitStream> pm, ps;
@@ -149,10 +149,13 @@ int main(int argc, char** argv)
   if (a.size() >= 11) { right_reads = a[8]; right_map = a[9]; right_segs = split_list(a[10]); }
 
   { FILE* f = fopen(ref_fname.c_str(), "r"); if (!f) die("Error: cannot open %s for reading", ref_fname); fclose(f); }
-  FILE* juncs_out = fopen(juncs_fname.c_str(), "w"); if (!juncs_out) die("Error: cannot open %s for writing", juncs_fname);
-  FILE* ins_out = fopen(ins_fname.c_str(), "w"); if (!ins_out) die("Error: cannot open %s for writing", ins_fname);
-  FILE* del_out = fopen(del_fname.c_str(), "w"); if (!del_out) die("Error: cannot open %s for writing", del_fname);
-  FILE* fus_out = fopen(fus_fname.c_str(), "w"); if (!fus_out) die("Error: cannot open %s for writing", fus_fname);
+  // The four outputs are written under temporary names and renamed when complete: tophat.py --resume skips this stage when
+  // segment.juncs exists (tophat.py:3087-3088), so a killed run must never leave a plausible partial file behind.
+  auto tmp_of = [](const std::string& n) { return n.compare(0, 5, "/dev/") == 0 ? n : n + ".thb_tmp"; };
+  FILE* juncs_out = fopen(tmp_of(juncs_fname).c_str(), "w"); if (!juncs_out) die("Error: cannot open %s for writing", juncs_fname);
+  FILE* ins_out = fopen(tmp_of(ins_fname).c_str(), "w"); if (!ins_out) die("Error: cannot open %s for writing", ins_fname);
+  FILE* del_out = fopen(tmp_of(del_fname).c_str(), "w"); if (!del_out) die("Error: cannot open %s for writing", del_fname);
+  FILE* fus_out = fopen(tmp_of(fus_fname).c_str(), "w"); if (!fus_out) die("Error: cannot open %s for writing", fus_fname);
 
   if (left_segs.empty()) { fprintf(stderr, "No hits to process, exiting\n"); return 0; }          // 4724-4728
   if (!o.no_coverage_search || !o.no_microexon_search || o.butterfly_search)
@@ -254,6 +257,8 @@ int main(int argc, char** argv)
     }
   }
   fclose(fus_out);
+  for (const std::string* n : { &juncs_fname, &ins_fname, &del_fname, &fus_fname })
+    if (tmp_of(*n) != *n && rename(tmp_of(*n).c_str(), n->c_str()) != 0) die("Error: cannot move the finished output into place: %s", *n);
   fprintf(stderr, "Reporting potential fusions...\n");
   if (getenv("TOPHAT_GPU_STATS")) {
     thb_timing tm; thb_last_timing(ctx, &tm);

@@ -25,6 +25,8 @@ bool inflate_block(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_len)
   return ok;
 }
 
+// Returns a pointer to the type byte of `tag`, or NULL; a field whose value does not lie wholly inside the record (truncated /
+// corrupt input, unterminated string) ends the search.
 const uint8_t* aux_find(const uint8_t* p, int n, const char tag[2])
 {
   const uint8_t* e = p + n;
@@ -32,17 +34,19 @@ const uint8_t* aux_find(const uint8_t* p, int n, const char tag[2])
     const bool hit = p[0] == (uint8_t)tag[0] && p[1] == (uint8_t)tag[1];
     const uint8_t type = p[2];
     const uint8_t* v = p + 3;
-    if (hit) return p + 2;
     switch (type) {
       case 'A': case 'c': case 'C': v += 1; break;
       case 's': case 'S': v += 2; break;
       case 'i': case 'I': case 'f': v += 4; break;
       case 'd': v += 8; break;
-      case 'Z': case 'H': while (v < e && *v) ++v; ++v; break;
+      case 'Z': case 'H': while (v < e && *v) ++v; if (v >= e) return nullptr; ++v; break;
       case 'B': { if (v + 5 > e) return nullptr; const uint8_t st = v[0]; const uint32_t cnt = rd32(v + 1);
-                  const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; v += 5 + (size_t)sz * cnt; break; }
+                  const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                  if ((uint64_t)sz * cnt > (uint64_t)(e - v)) return nullptr; v += 5 + (size_t)sz * cnt; break; }
       default: return nullptr;
     }
+    if (v > e) return nullptr;
+    if (hit) return p + 2;
     p = v;
   }
   return nullptr;
@@ -170,6 +174,10 @@ bool BamReader::next(BamRecord& r)
   r.tid = (int32_t)rd32(p); r.pos = (int32_t)rd32(p + 4);
   r.l_qname = p[8]; r.mapq = p[9]; r.n_cigar = rd16(p + 12); r.flag = rd16(p + 14);
   r.l_seq = (int32_t)rd32(p + 16); r.mtid = (int32_t)rd32(p + 20); r.mpos = (int32_t)rd32(p + 24); r.tlen = (int32_t)rd32(p + 28);
+  // the variable-length fields must fit the record before any pointer into them is formed
+  if (r.l_seq < 0 || r.l_qname < 1 ||
+      32ull + (uint64_t)r.l_qname + 4ull * (uint64_t)r.n_cigar + ((uint64_t)r.l_seq + 1) / 2 + (uint64_t)r.l_seq > (uint64_t)bs ||
+      p[32 + r.l_qname - 1] != 0) { err_ = path_ + ": corrupt BAM record"; return false; }
   const uint8_t* q = p + 32;
   r.qname = (const char*)q; q += r.l_qname;
   r.cigar = (const uint32_t*)q; q += 4 * (size_t)r.n_cigar;

@@ -22,13 +22,36 @@ int reg2bin(int beg, int end)
 }
 }  // namespace
 
+// Deflates one BGZF block payload (<= BLOCK_DATA bytes) into `out` (header + data + crc + isize); returns the block's size or 0.
+// BSIZE is 16 bits: a payload that deflate cannot shrink below 64 KiB - 26 is stored instead (level 0: payload + 5 bytes always fits).
+static size_t bgzf_compress(const uint8_t* src, size_t n, uint8_t* out, size_t out_cap)
+{
+  size_t clen = 0;
+  for (int level : {6, 0}) {
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = (uInt)(out_cap - 18 - 8);
+    const int rc = deflate(&zs, Z_FINISH); clen = zs.total_out; deflateEnd(&zs);
+    if (rc == Z_STREAM_END && clen + 26 <= 65536) break;
+    if (level == 0) return 0;
+  }
+  const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  memcpy(out, hdr, 16);
+  const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1); memcpy(out + 16, &bsize, 2);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), src, (uInt)n), isize = (uint32_t)n;
+  memcpy(out + 18 + clen, &crc, 4); memcpy(out + 18 + clen + 4, &isize, 4);
+  return clen + 26;
+}
+
 BamWriter::~BamWriter() { std::string e; close(&e); }
 
 bool BamWriter::open(const std::string& path, const std::string& header_sam_path, const std::string& index_path, std::string* err)
 {
-  f_ = fopen(path.c_str(), "wb");
+  // written under a temporary name, renamed by close(): a killed run leaves no plausible partial BAM for tophat.py --resume
+  path_ = path; index_path_ = index_path; tmp_ = path.compare(0, 5, "/dev/") != 0;
+  f_ = fopen((tmp_ ? path + ".thb_tmp" : path).c_str(), "wb");
   if (!f_) { *err = "cannot open " + path + " for writing"; return false; }
-  if (!index_path.empty()) fidx_ = fopen(index_path.c_str(), "w");
+  if (!index_path.empty()) fidx_ = fopen((tmp_ ? index_path + ".thb_tmp" : index_path).c_str(), "w");
   std::string text; std::vector<uint32_t> tlen;
   { std::ifstream in(header_sam_path.c_str()); if (!in.good()) { *err = "Failed to open SAM header file " + header_sam_path; return false; }
     std::stringstream ss; ss << in.rdbuf(); text = ss.str(); }
@@ -63,17 +86,8 @@ void BamWriter::flush_block()
 {
   if (blk_.empty() || !f_) return;
   uint8_t out[70000];
-  z_stream zs; memset(&zs, 0, sizeof zs);
-  deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-  zs.next_in = blk_.data(); zs.avail_in = (uInt)blk_.size(); zs.next_out = out + 18; zs.avail_out = sizeof(out) - 18 - 8;
-  const int rc = deflate(&zs, Z_FINISH); const size_t clen = zs.total_out; deflateEnd(&zs);
-  if (rc != Z_STREAM_END) { fail_ = true; return; }
-  const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-  memcpy(out, hdr, 16);
-  const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1); memcpy(out + 16, &bsize, 2);
-  const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), blk_.data(), (uInt)blk_.size()), isize = (uint32_t)blk_.size();
-  memcpy(out + 18 + clen, &crc, 4); memcpy(out + 18 + clen + 4, &isize, 4);
-  const size_t total = clen + 26;
+  const size_t total = bgzf_compress(blk_.data(), blk_.size(), out, sizeof out);
+  if (!total) { fail_ = true; return; }
   if (fwrite(out, 1, total, f_) != total) fail_ = true;
   file_off_ += total; blk_.clear();
 }
@@ -116,22 +130,6 @@ void BamWriter::write(const std::string& qname, uint32_t read_id, int flag, int 
   put(rec.data(), rec.size());
   wcount_++;
   if (write_index) { fprintf(fidx_, "%ld\t%ld\n", (long)read_id, (long)pre_pos); idxcount_ = 0; }
-}
-
-// deflates one BGZF block payload into `out` (header + data + crc + isize); returns the block's size or 0
-static size_t bgzf_compress(const uint8_t* src, size_t n, uint8_t* out, size_t out_cap)
-{
-  z_stream zs; memset(&zs, 0, sizeof zs);
-  deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-  zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = (uInt)(out_cap - 18 - 8);
-  const int rc = deflate(&zs, Z_FINISH); const size_t clen = zs.total_out; deflateEnd(&zs);
-  if (rc != Z_STREAM_END) return 0;
-  const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-  memcpy(out, hdr, 16);
-  const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1); memcpy(out + 16, &bsize, 2);
-  const uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), src, (uInt)n), isize = (uint32_t)n;
-  memcpy(out + 18 + clen, &crc, 4); memcpy(out + 18 + clen + 4, &isize, 4);
-  return clen + 26;
 }
 
 void BamWriter::append_records(const std::vector<RecordPart>& parts, int threads)
@@ -192,7 +190,12 @@ bool BamWriter::close(std::string* err)
   if (fwrite(eof_block, 1, 28, f_) != 28) fail_ = true;
   if (fclose(f_) != 0) fail_ = true;
   f_ = nullptr;
-  if (fidx_) { fclose(fidx_); fidx_ = nullptr; }
+  const bool had_index = fidx_ != nullptr;
+  if (fidx_) { if (fclose(fidx_) != 0) fail_ = true; fidx_ = nullptr; }
+  if (!fail_ && tmp_) {
+    if (had_index && rename((index_path_ + ".thb_tmp").c_str(), index_path_.c_str()) != 0) fail_ = true;
+    if (rename((path_ + ".thb_tmp").c_str(), path_.c_str()) != 0) fail_ = true;
+  }
   if (fail_ && err) *err = "error writing BAM output";
   return !fail_;
 }

@@ -39,6 +39,7 @@ class BamWriter {
   FILE* f_ = nullptr; FILE* fidx_ = nullptr;
   std::vector<uint8_t> blk_; uint64_t file_off_ = 0; bool fail_ = false;
   std::vector<std::string> tnames_;
+  std::string path_, index_path_; bool tmp_ = false;
   uint64_t wcount_ = 0; int idxcount_ = 0; long idx_last_id_ = 0;
 };
 

@@ -19,7 +19,7 @@
 namespace thb {
 
 constexpr int JMAXOPS = THB_JOINED_MAX_OPS;
-constexpr int JMAXSEGS = 12;
+constexpr int JMAXSEGS = THB_MAX_SEGS;
 // CigarOpCode values (bwt_map.h:36-55); ops are packed as length << 4 | opcode
 enum { OP_MATCH = 1, OP_mATCH = 2, OP_INS = 3, OP_iNS = 4, OP_DEL = 5, OP_dEL = 6, OP_REF_SKIP = 11, OP_rEF_SKIP = 12,
        OP_SOFT_CLIP = 13, OP_HARD_CLIP = 14, OP_PAD = 15 };
@@ -735,6 +735,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
     }
     // accumulators of the final pass (1888-1945), filled as blocks are finalised
     uint32_t LC[JMAXOPS]; int nLC = 0; int num_mm = 0, num_smm = 0; bool saw_as = false, saw_s = false;
+    bool cig_ovf = false;              // a CIGAR outgrew JMAXOPS: reported, never silently dropped (the reference has no such limit)
     int old_read_length = 0;
     auto finalize = [&](const WHit& h) -> bool {
       num_mm += h.mism; num_smm += h.smm;
@@ -743,7 +744,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
       }
       int b = 0;
       if (nLC > 0 && opc(LC[nLC - 1]) == opc(h.ops[0])) { LC[nLC - 1] = mkop(opc(LC[nLC - 1]), opl(LC[nLC - 1]) + opl(h.ops[0])); b = 1; }
-      for (; b < h.n; ++b) if (!cig_push(LC, nLC, h.ops[b])) return false;
+      for (; b < h.n; ++b) if (!cig_push(LC, nLC, h.ops[b])) { cig_ovf = true; return false; }
       return true;
     };
     WHit prev; prev.n = 0; prev.ref = 0; prev.left = 0; prev.anti = prev.asplice = false; prev.mism = prev.smm = 0; prev.seq_pos = prev.seq_len = 0;
@@ -819,6 +820,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
             const int nrf = clml - jc.dtl;
             for (int k = nrf > 0 ? 0 : 1; k < curr.n && okc; ++k) okc = cig_push(NC, nNC, k == 0 ? mkop(opc(curr.ops[0]), (uint32_t)nrf) : curr.ops[k]);
           }
+          if (!okc) cig_ovf = true;
           if (!okc || nNC == 0) multi = false;
           else {
             // merged_hit (1822-1838); _mismatches / _edit_dist are unsigned chars in the reference
@@ -856,6 +858,7 @@ chain_merge_kernel(RefView ref, JoinParams P, JoinSets S, JoinBatchView bv, Chai
         j.mismatches = mism; j.edit_dist = (uint8_t)(num_mm + cig_gap_length(LC, nLC)); j.splice_mms = (uint8_t)num_smm;
       }
     }
+    if (cig_ovf) atomicOr(o.overflow, 2u);
     __syncwarp();
     // ---- emit (warp-aggregated slot allocation)
     const bool out_ok = (single && alive) || multi;

@@ -311,7 +311,7 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
             // a single match op: the pair checks of 930-949 hold, the op extends a trailing match (1926-1936)
             const uint32_t len = (uint32_t)(a.z - a.y);
             if (last != 0u && opc(last) == OP_MATCH) last += len << 4;
-            else { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else ok = false; } last = mkop(OP_MATCH, len); }
+            else { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else { ok = false; atomicOr(o.overflow, 2u); } } last = mkop(OP_MATCH, len); }
             prev_spliced = false; prev_last_match = true;
           } else {
             int nops = (int)((a.w >> 4) & 0xfu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
@@ -331,7 +331,7 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
               if (spliced) { if (asplice) { if (saw_s) ok = false; saw_as = true; } else { if (saw_as) ok = false; saw_s = true; } }   // 1888-1945
               int x0 = 0;
               if (last != 0u && opc(last) == opc(ops[0])) { last += opl(ops[0]) << 4; x0 = 1; }
-              for (; x0 < nops; ++x0) { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else ok = false; } last = ops[x0]; }
+              for (; x0 < nops; ++x0) { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else { ok = false; atomicOr(o.overflow, 2u); } } last = ops[x0]; }
               prev_spliced = spliced; prev_asplice = asplice; prev_last_match = opc(ops[nops - 1]) == OP_MATCH;
             }
           }
@@ -342,7 +342,7 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
       // the chain's CIGAR: LC[0 .. nfl) followed by `last`
       int nLC = nfl + 1;
       const uint32_t* cig = &last;
-      if (ok && nfl > 0) { if (nfl < JMAXOPS) { LC[nfl] = last; cig = LC; } else ok = false; }
+      if (ok && nfl > 0) { if (nfl < JMAXOPS) { LC[nfl] = last; cig = LC; } else { ok = false; atomicOr(o.overflow, 2u); } }
       if (ok && nfl == 0) nLC = 1;
       __syncwarp();
       if (ok) {

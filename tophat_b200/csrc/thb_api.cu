@@ -261,7 +261,7 @@ int launch_scan(thb_ctx* ctx, const BatchView& bv, uint64_t n_partner, uint64_t 
   const SegOutputs o = outputs(ctx);
   if (bv.n_segs <= 4) launch_phase<4>(ctx, bv, q, o, n_hits);
   else if (bv.n_segs <= 8) launch_phase<8>(ctx, bv, q, o, n_hits);
-  else launch_phase<14>(ctx, bv, q, o, n_hits);
+  else launch_phase<THB_MAX_SEGS>(ctx, bv, q, o, n_hits);
   CU(cudaGetLastError());
   ctx->kev_pending = true;
   ctx->timing.kernel_launches++; ctx->own_launches += (ctx->sp.fusion_search ? 8 : 6) - (scan_legacy() ? 0 : 1);
@@ -283,7 +283,7 @@ int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
 {
   if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
   if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
-  if (b->n_segs < 1 || b->n_segs > 14u) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,14]", b->n_segs);
+  if (b->n_segs < 1 || b->n_segs > (uint32_t)THB_MAX_SEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, THB_MAX_SEGS);
   if (b->n_bundles >= (1u << 28)) return fail(ctx, THB_EUNSUPPORTED, "more than 2^28 bundles in one batch");
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4] (reads up to 255 bp)", b->read_words);
   if (b->n_bundles && (!b->bundles || !b->seg_count || !b->reads)) return fail(ctx, THB_EINVAL, "null batch array");
@@ -593,8 +593,8 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
     return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside the GPU path's [4,32] (two segments must fit one 64-bit plane word)", p->segment_length);
   if (p->max_segment_intron_length + p->segment_length + 64 >= (1 << KEY_LEN_BITS))
     return fail(ctx, THB_EUNSUPPORTED, "--max-segment-intron %d too large for the 24-bit span field", p->max_segment_intron_length);
-  if (p->max_insertion_length > 20 || p->max_deletion_length > 1000)
-    return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 20 / --max-deletion-length > 1000 not supported");
+  if (p->max_insertion_length > 19 || p->max_deletion_length > 1000)      // thb_insertion.seq holds 19 bases + NUL
+    return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 / --max-deletion-length > 1000 not supported");
   if (p->inner_dist_mean + p->inner_dist_std_dev + std::max(0, p->inner_dist_std_dev - p->inner_dist_mean) > 100000)
     return fail(ctx, THB_EUNSUPPORTED, "mate flank longer than 100000 bases");
   ctx->params = *p;
@@ -985,6 +985,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     CU(cudaMemcpyAsync(&ovf, ctx->d_qovf, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
+    if (ovf & 2u) return fail(ctx, THB_EUNSUPPORTED, "a merged alignment needs more than %d CIGAR operations (outside the GPU path)", JMAXOPS);
     n = qn[0]; qn_simple = legacy ? qn[2] : tc[0]; qn_abut = legacy ? qn[3] : tc[1];
     if (!ovf && n <= cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
