@@ -426,13 +426,35 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     j_keep, j_dev, j_host = stage(jbatches, j_fields, capi.join_batch_c)
     h2d_bytes = sum(b.nbytes() for b in batches) + sum(b.nbytes() for b in jbatches) + int(jsets[0].nbytes + jsets[1].nbytes)
 
+    wall = {}
+
+    def clock(name, f, *a):
+        """per-call host wall clock (every C-ABI call returns with its stream idle), reported with --breakdown"""
+        t = time.perf_counter(); r = f(*a); wall[name] = wall.get(name, 0.0) + (time.perf_counter() - t); return r
+
+    def segjuncs_pass_timed(device_resident: bool, copy: bool):
+        clock("segjuncs_begin", ctx.segjuncs_begin, P)
+        for i in range(len(batches)):
+            if device_resident:
+                clock("segjuncs_submit", ctx.segjuncs_submit_device, sj_dev[i])
+            else:
+                clock("segjuncs_submit", lambda: ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit"))
+        if world > 1:
+            clock("allgather", ctx.segjuncs_allgather)
+        res = clock("segjuncs_finish", ctx.segjuncs_finish, copy)
+        return res, ctx.timing()
+
     def step(device_resident: bool, copy: bool = False):
-        res, tm = segjuncs_pass(device_resident, copy)
-        ctx.join_begin(P, jsets[0], jsets[1])
+        if args.breakdown:
+            res, tm = segjuncs_pass_timed(device_resident, copy)
+            clock("join_begin", ctx.join_begin, P, jsets[0], jsets[1])
+        else:
+            res, tm = segjuncs_pass(device_resident, copy)
+            ctx.join_begin(P, jsets[0], jsets[1])
         n_joined, d2h = 0, 0
         for i in range(len(jbatches)):
             if device_resident:
-                n_joined += ctx.join_submit_device(j_dev[i])
+                n_joined += clock("join_submit", ctx.join_submit_device, j_dev[i]) if args.breakdown else ctx.join_submit_device(j_dev[i])
             else:
                 out = C.c_void_p(); n = C.c_uint64()
                 ctx._check(ctx.lib.thb_join_submit(ctx.h, C.byref(j_host[i]), C.byref(out), C.byref(n)), "thb_join_submit")
@@ -476,6 +498,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         clk.start()
     A = timed(True, args.steps, args.warmup)
+    wall_dev = {k: v / (args.steps + args.warmup) * 1e3 for k, v in wall.items()}; wall.clear()
     E = timed(False, args.steps, args.warmup)
     clocks = clk.stop() if rank == 0 else None
     res, res_h, tm = A["res"], E["res"], A["tm"]
@@ -517,7 +540,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         #   join_tile   : 16 (header) per read + 16 per segment hit, + the share of [40 (read) per read + 32 per multi-op hit + 96 per merged
         #                 chain + 128 per output record] of the chains it merges itself (those without a closure)
         #   chain_merge : the same share for the chains with a closure + 128 per closure
-        legacy_scan, legacy_join = "THB_SCAN_LEGACY" in os.environ, "THB_JOIN_LEGACY" in os.environ
+        legacy_scan, legacy_join = "THB_SCAN_LEGACY" in os.environ, "THB_JOIN_TILE" not in os.environ
         n_b = sum(b.n_bundles for b in batches); n_h = sum(int(b.hits.shape[0]) + int(b.partner_hits.shape[0]) for b in batches)
         n_hh = sum(int(b.hits.shape[0]) for b in batches)
         steps = args.steps
@@ -584,7 +607,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                              "all_kernels": {"ms_per_step": tot_ms, "algorithmic_bytes_per_step": tot_bytes,
                                              "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
                                              "frac": (tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks) if tot_ms > 0 else 0.0}},
-                "clocks": clocks, "parity_checked": parity,
+                "clocks": clocks, "parity_checked": parity, "host_wall_ms_per_call_kind": wall_dev if args.breakdown else None,
                 "host": {"cpu_count": os.cpu_count()},
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
@@ -674,6 +697,7 @@ def main():
                     help="hg38 = BASELINE configs[2] (the configuration the metric is quoted on: hg38-sized reference at 1/2/4/8 GPUs, sharded by read); "
                          "chr20 = configs[1]; indel = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also report the host wall clock of every C-ABI call kind (device-resident pass)")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload

@@ -9,7 +9,7 @@ try:
     print("value %.4g reads/s  step %.3f ms  e2e %.4g reads/s (%.1f ms)  frac(all) %.4f  dom %s %.3f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["roofline"]["all_kernels"]["frac"], d["roofline"]["kernel"], d["roofline"]["frac"]))
     print({k: round(v, 3) for k, v in d["roofline"]["per_kernel_ms_per_step"].items()})
     print({k: round(v, 3) for k, v in d["roofline"]["per_kernel_frac"].items()})
-    print({k[:14]: round(v, 3) for k, v in d["roofline"]["non_kernel_ms_per_step"].items()})
+    print({k[:14]: round(v, 3) for k, v in d["roofline"]["non_kernel_ms_per_step"].items()}); print("host wall per call kind", {k: round(v, 3) for k, v in (d.get("host_wall_ms_per_call_kind") or {}).items()})
 except Exception as e:
     print("no line:", e)
 PY
@@ -19,7 +19,7 @@ i=0
 for v in "${VS[@]}"; do
   i=$((i+1))
   ( if [ "$v" != "none" ]; then for kv in $v; do export "$kv"; done; fi
-    timeout 900 python bench.py --workload $WL --pairs $PAIRS --steps 5 --no-cpu-baseline --parity-pairs 50000 > gpurun_out/bench_${TAG}_v$i.json 2> gpurun_out/bench_${TAG}_v$i.err; echo "variant $i [$v] exit $?" )
+    timeout 900 python bench.py --workload $WL --pairs $PAIRS --steps 5 --no-cpu-baseline --parity-pairs 50000 --breakdown > gpurun_out/bench_${TAG}_v$i.json 2> gpurun_out/bench_${TAG}_v$i.err; echo "variant $i [$v] exit $?" )
   show gpurun_out/bench_${TAG}_v$i.json
 done
 if [ -n "$KRE" ]; then

@@ -222,9 +222,9 @@ def test_emu_join_tile_kernel_equals_queue_kernels():
     overflow give the records of round 1's queue kernels (tests/emu/join_variant_check.py, one process per variant)."""
     outs = []
     for legacy in (False, True):
-        env = dict(os.environ); env.pop("THB_JOIN_LEGACY", None); env.pop("THB_CHECK_GPU", None)
-        if legacy:
-            env["THB_JOIN_LEGACY"] = "1"
+        env = dict(os.environ); env.pop("THB_JOIN_LEGACY", None); env.pop("THB_JOIN_TILE", None); env.pop("THB_CHECK_GPU", None)
+        if not legacy:
+            env["THB_JOIN_TILE"] = "1"
         r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "join_variant_check.py")], capture_output=True, text=True, timeout=900, env=env)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith("JOIN_DIGEST")][-1])

@@ -66,32 +66,40 @@ __device__ __forceinline__ void reg_revcomp(uint64_t (&p0)[RW], uint64_t (&p1)[R
   }
 }
 
-// BowtieHit::check_editdist_consistency (bwt_map.cpp:2349-2465) for a single-contig hit, read planes in registers
+// BowtieHit::check_editdist_consistency (bwt_map.cpp:2349-2465) for a single-contig hit, read planes in registers.
+// Written as a flat loop over <= 64-base chunks of the match operations: the t-th chunk of every lane is compared in the same
+// iteration whatever the shape of the lane's CIGAR (101M and 51M 900N 50M both have two), so the expensive part -- reference
+// fetch, read slices, popcounts -- runs converged.  All 32 lanes call; `alive` says whether the lane has a hit to check.
 template <int RW>
 __device__ __forceinline__ bool editdist_consistent_reg(const RefView& ref, uint32_t ref_id, int left, const uint32_t* ops, int n,
-                                                        const uint64_t (&r0)[RW], const uint64_t (&r1)[RW], const uint64_t (&rn)[RW], unsigned mismatches)
+                                                        const uint64_t (&r0)[RW], const uint64_t (&r1)[RW], const uint64_t (&rn)[RW], unsigned mismatches, bool alive)
 {
-  if (!(ref_id >= 1 && ref_id <= ref.n_contigs)) return false;
-  const int64_t len = (int64_t)__ldg(ref.contig_len + ref_id - 1);
-  if (len <= 0) return false;
-  const uint64_t cs = __ldg(ref.contig_start + ref_id - 1);
-  int64_t pos_ref = left; int pos_seq = 0; unsigned mm = 0, nmm = 0;
-  for (int i = 0; i < n; ++i) {
-    const int c = opc(ops[i]); const int l = (int)opl(ops[i]);
-    if (c == OP_MATCH) {
-      if (pos_ref < 0 || pos_ref + l > len) return false;               // the reference would read outside the contig
-      for (int o = 0; o < l; o += 64) {
-        const int m = min(64, l - o);
-        const P3 g = ref_fetch3(ref, cs + (uint64_t)(pos_ref + o), m);
-        const uint64_t q0 = reg_slice<RW>(r0, pos_seq + o, m), q1 = reg_slice<RW>(r1, pos_seq + o, m), qn = reg_slice<RW>(rn, pos_seq + o, m);
-        mm += (unsigned)__popcll((g.p0 ^ q0) | (g.p1 ^ q1) | (g.pn ^ qn));
-        nmm += (unsigned)__popcll(g.pn & qn);
-      }
-      pos_ref += l; pos_seq += l;
-    } else if (c == OP_INS) pos_seq += l;
-    else if (c == OP_DEL || c == OP_REF_SKIP) pos_ref += l;
+  int64_t len = 0; uint64_t cs = 0;
+  if (alive) {
+    if (!(ref_id >= 1 && ref_id <= ref.n_contigs)) alive = false;
+    else { len = (int64_t)__ldg(ref.contig_len + ref_id - 1); cs = __ldg(ref.contig_start + ref_id - 1); if (len <= 0) alive = false; }
   }
-  return mm == mismatches || mm + nmm == mismatches;
+  int64_t pos_ref = left; int pos_seq = 0, i = 0, rem = 0; unsigned mm = 0, nmm = 0;
+  #pragma unroll 1
+  for (;;) {
+    while (alive && rem == 0 && i < n) {                                 // next match operation
+      const uint32_t op = ops[i++]; const int c = opc(op), l = (int)opl(op);
+      if (c == OP_MATCH) { if (pos_ref < 0 || pos_ref + l > len) alive = false; else rem = l; }   // the reference would read outside the contig
+      else if (c == OP_INS) pos_seq += l;
+      else if (c == OP_DEL || c == OP_REF_SKIP) pos_ref += l;
+    }
+    const bool work = alive && rem > 0;
+    if (!__any_sync(0xffffffffu, work)) break;
+    if (work) {
+      const int m = min(64, rem);
+      const P3 g = ref_fetch3(ref, cs + (uint64_t)pos_ref, m);
+      const uint64_t q0 = reg_slice<RW>(r0, pos_seq, m), q1 = reg_slice<RW>(r1, pos_seq, m), qn = reg_slice<RW>(rn, pos_seq, m);
+      mm += (unsigned)__popcll((g.p0 ^ q0) | (g.p1 ^ q1) | (g.pn ^ qn));
+      nmm += (unsigned)__popcll(g.pn & qn);
+      pos_ref += m; pos_seq += m; rem -= m;
+    }
+  }
+  return alive && (mm == mismatches || mm + nmm == mismatches);
 }
 
 // the generic walk for a read with more than JT_HITS hits in a segment: every chain goes to the closure kernel's queue
@@ -194,33 +202,33 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
       if (skip) n = 0;
       else if (big) { enum_big_read(P, HH, q, bi, n, cnt, offs, n_leaves); n = 0; }
       else {
-        // pair matrices: bit 8 * i + j of M[s] <=> hit i of segment s and hit j of segment s+1 can be neighbours in a chain
+        // pair matrices: bit 8 * i + j of M[s] <=> hit i of segment s and hit j of segment s+1 can be neighbours in a chain.
+        // One flat loop over all (segment pair, i, j): the lanes' t-th pair tests run together.
         uint64_t M[JT_SEGS - 1] = {0ull, 0ull, 0ull}, A[JT_SEGS - 1] = {0ull, 0ull, 0ull}; uint32_t onem = 0;
-        #pragma unroll
-        for (int s = 0; s < JT_SEGS; ++s) if (s < n) {
-          for (int i = 0; i < cnt[s]; ++i) {
-            const uint4 v = *reinterpret_cast<const uint4*>(HH + offs[s] + i);
-            if (v.w & THB_JHIT_ONE_MATCH) onem |= 1u << (8 * s + i);
-            if (s + 1 < JT_SEGS && s + 1 < n) {
-              const bool anti = (v.w & THB_HIT_ANTISENSE) != 0;
-              for (int j = 0; j < cnt[s + 1 < JT_SEGS ? s + 1 : s]; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(HH + offs[s + 1 < JT_SEGS ? s + 1 : s] + j);
-                if (u.x != v.x || ((u.w & THB_HIT_ANTISENSE) != 0) != anti) continue;          // would need a fusion (2402)
-                const int dist = anti ? (int)v.y - (int)u.z : (int)u.y - (int)v.z;             // 2355-2379
-                if (dist > P.max_report_intron || dist < -P.max_ins) continue;                  // 2554-2556
-                M[s < JT_SEGS - 1 ? s : 0] |= 1ull << (8 * i + j);
-                if (dist == 0) A[s < JT_SEGS - 1 ? s : 0] |= 1ull << (8 * i + j);
-              }
-            }
-          }
-        }
+        { const int tot = cnt[0] + cnt[1] + cnt[2] + cnt[3];            // hits of a read are contiguous: hit t = HH[offs[0] + t]
+          #pragma unroll 1
+          for (int t = 0; t < tot; ++t) if ((*(reinterpret_cast<const uint32_t*>(HH + offs[0] + t) + 3)) & THB_JHIT_ONE_MATCH) onem |= 1u << t; }
+        { int ps = 0, pi = 0, pj = 0;
+          #pragma unroll 1
+          while (ps < n - 1) {
+            const int ca = ps == 0 ? cnt[0] : (ps == 1 ? cnt[1] : cnt[2]), cb = ps == 0 ? cnt[1] : (ps == 1 ? cnt[2] : cnt[3]);
+            const uint32_t oa = ps == 0 ? offs[0] : (ps == 1 ? offs[1] : offs[2]), ob = ps == 0 ? offs[1] : (ps == 1 ? offs[2] : offs[3]);
+            const uint4 v = *reinterpret_cast<const uint4*>(HH + oa + pi), u = *reinterpret_cast<const uint4*>(HH + ob + pj);
+            const bool anti = (v.w & THB_HIT_ANTISENSE) != 0;
+            const int dist = anti ? (int)v.y - (int)u.z : (int)u.y - (int)v.z;                   // 2355-2379
+            const bool okp = u.x == v.x && ((u.w & THB_HIT_ANTISENSE) != 0) == anti                // else: would need a fusion (2402)
+                             && dist <= P.max_report_intron && dist >= -P.max_ins;                 // 2554-2556
+            const uint64_t bit = okp ? (1ull << (8 * pi + pj)) : 0ull, abit = dist == 0 ? bit : 0ull;
+            if (ps == 0) { M[0] |= bit; A[0] |= abit; } else if (ps == 1) { M[1] |= bit; A[1] |= abit; } else { M[2] |= bit; A[2] |= abit; }
+            if (++pj == cb) { pj = 0; if (++pi == ca) { pi = 0; ++ps; } }
+          } }
         // paths through the matrices = dfs_seg_hits' chains, in its order.  At most 8^3 chains per first-segment hit: the
         // budget of 10,000 (2647) cannot run out here.
         auto leaf = [&](uint32_t sel, bool all_abut) {
           ++n_leaves;
           bool all_one = true;
           #pragma unroll
-          for (int s = 0; s < JT_SEGS; ++s) if (s < n) all_one = all_one && ((onem >> (8 * s + ((sel >> (8 * s)) & 0xffu))) & 1u);
+          for (int s = 0; s < JT_SEGS; ++s) if (s < n) all_one = all_one && ((onem >> ((offs[s] - offs[0]) + ((sel >> (8 * s)) & 0xffu))) & 1u);
           const uint32_t kind = (n > 1 && all_abut) ? (all_one ? 1u : 2u) : 0u;
           if (n_park < ENUM_PARK) { tile_park[wib][n_park][lane] = sel; park_kind |= kind << (2 * n_park); ++n_park; return; }
           // more chains than the parking area holds (a multi-mapped read): the closure kernel merges any chain
@@ -293,49 +301,35 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
       if (ok) {
         if (kind == 1u) ++n_simple; else ++n_abut;
         const uint32_t sel = tile_park[wib][k][lane];
-        uint32_t hidx[JT_SEGS];
-        #pragma unroll
-        for (int s = 0; s < JT_SEGS; ++s) hidx[s] = offs[s] + ((sel >> (8 * s)) & 0xffu);
-        anti = ((*(reinterpret_cast<const uint32_t*>(HH + hidx[0]) + 3)) & THB_HIT_ANTISENSE) != 0;       // chain orientation (2117-2121)
+        anti = ((*(reinterpret_cast<const uint32_t*>(HH + offs[0] + (sel & 0xffu)) + 3)) & THB_HIT_ANTISENSE) != 0;       // chain orientation (2117-2121)
         bool prev_spliced = false, prev_asplice = false, prev_last_match = false; uint32_t prev_ref = 0;
-        #pragma unroll
-        for (int e = 0; e < JT_SEGS; ++e) if (e < n && ok) {
-          uint32_t hi_ = 0;
-          #pragma unroll
-          for (int s = 0; s < JT_SEGS; ++s) if (s == (anti ? n - 1 - e : e)) hi_ = hidx[s];
-          const uint4 a = *reinterpret_cast<const uint4*>(HH + hi_);
-          const uint32_t fl = a.w & 0xfu; const bool asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0;
+        #pragma unroll 1
+        for (int e = 0; e < n; ++e) {
+          const int sg = anti ? n - 1 - e : e;
+          const uint32_t osg = sg == 0 ? offs[0] : (sg == 1 ? offs[1] : (sg == 2 ? offs[2] : offs[3]));
+          const uint4 a = *reinterpret_cast<const uint4*>(HH + osg + ((sel >> (8 * sg)) & 0xffu));
+          const uint32_t fl = a.w & 0xfu; const bool asplice = (fl & THB_JHIT_ANTISENSE_SPLICE) != 0, one = (fl & THB_JHIT_ONE_MATCH) != 0;
           num_mm += (int)((a.w >> 16) & 0xffu); num_smm += (int)(a.w >> 24);
           if (e == 0) { ref0 = a.x; left0 = (int)a.y; } else if (a.x != prev_ref) ok = false;
-          if (fl & THB_JHIT_ONE_MATCH) {
-            // a single match op: the pair checks of 930-949 hold, the op extends a trailing match (1926-1936)
-            const uint32_t len = (uint32_t)(a.z - a.y);
-            if (last != 0u && opc(last) == OP_MATCH) last += len << 4;
-            else { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else { ok = false; atomicOr(o.overflow, 2u); } } last = mkop(OP_MATCH, len); }
-            prev_spliced = false; prev_last_match = true;
-          } else {
-            int nops = (int)((a.w >> 4) & 0xfu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
-            uint32_t ops[THB_JHIT_MAX_OPS];
-            const uint4* p = reinterpret_cast<const uint4*>(EE + ops_begin + ((a.w >> 8) & 0xffu));
-            const uint4 b = p[0]; ops[0] = b.x; ops[1] = b.y; ops[2] = b.z; ops[3] = b.w;
-            if (nops > 4) { const uint4 c = p[1]; ops[4] = c.x; ops[5] = c.y; ops[6] = c.z; ops[7] = c.w; }
-            if (nops > 8) ops[8] = *reinterpret_cast<const uint32_t*>(p + 2);
-            if (nops < 1) { ok = false; }
-            else {
-              bool spliced = false;
-              for (int x = 0; x < nops; ++x) spliced = spliced || opc(ops[x]) == OP_REF_SKIP;
-              if (e > 0) {
-                if (!(prev_last_match || opc(ops[0]) == OP_MATCH)) ok = false;                    // 930-934
-                if (prev_spliced && spliced && prev_asplice != asplice) ok = false;                // 942-949
-              }
-              if (spliced) { if (asplice) { if (saw_s) ok = false; saw_as = true; } else { if (saw_as) ok = false; saw_s = true; } }   // 1888-1945
-              int x0 = 0;
-              if (last != 0u && opc(last) == opc(ops[0])) { last += opl(ops[0]) << 4; x0 = 1; }
-              for (; x0 < nops; ++x0) { if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else { ok = false; atomicOr(o.overflow, 2u); } } last = ops[x0]; }
-              prev_spliced = spliced; prev_asplice = asplice; prev_last_match = opc(ops[nops - 1]) == OP_MATCH;
+          // every hit goes through the same op loop: a single-match hit is the one-op case (ops synthesised from the 16-byte record)
+          int nops = one ? 1 : (int)((a.w >> 4) & 0xfu); if (nops > THB_JHIT_MAX_OPS) nops = THB_JHIT_MAX_OPS;
+          if (nops < 1) { ok = false; nops = 0; }
+          const uint32_t* po = reinterpret_cast<const uint32_t*>(EE + ops_begin + ((a.w >> 8) & 0xffu));
+          bool spliced = false; uint32_t op = 0;
+          #pragma unroll 1
+          for (int x = 0; x < nops; ++x) {
+            op = one ? mkop(OP_MATCH, (uint32_t)(a.z - a.y)) : po[x];
+            spliced = spliced || opc(op) == OP_REF_SKIP;
+            if (x == 0) {
+              if (e > 0 && !(prev_last_match || opc(op) == OP_MATCH)) ok = false;                  // 930-934
+              if (last != 0u && opc(last) == opc(op)) { last += opl(op) << 4; continue; }          // equal neighbours fuse (1926-1936)
             }
+            if (last != 0u) { if (nfl < JMAXOPS) LC[nfl++] = last; else { ok = false; atomicOr(o.overflow, 2u); } }
+            last = op;
           }
-          prev_ref = a.x;
+          if (e > 0 && prev_spliced && spliced && prev_asplice != asplice) ok = false;             // 942-949
+          if (spliced) { if (asplice) { if (saw_s) ok = false; saw_as = true; } else { if (saw_as) ok = false; saw_s = true; } }   // 1888-1945
+          prev_spliced = spliced; prev_asplice = asplice; prev_last_match = opc(op) == OP_MATCH; prev_ref = a.x;
         }
         if (last == 0u) ok = false;
       }
@@ -345,14 +339,15 @@ join_tile_kernel(RefView ref, JoinParams P, JoinBatchView bv, ChainQueue q, Join
       if (ok && nfl > 0) { if (nfl < JMAXOPS) { LC[nfl] = last; cig = LC; } else { ok = false; atomicOr(o.overflow, 2u); } }
       if (ok && nfl == 0) nLC = 1;
       __syncwarp();
-      if (ok) {
+      {
         // the read, oriented like the chain; new_read_len == old_read_length (2023) holds: fusing equal neighbours keeps lengths
         uint64_t r0[RW], r1[RW], rn[RW];
         { const uint64_t* rd = s_rd + (size_t)lane * 3u * RW;
           #pragma unroll
           for (int w = 0; w < RW; ++w) { r0[w] = rd[w]; r1[w] = rd[RW + w]; rn[w] = rd[2 * RW + w]; } }
-        if (anti) reg_revcomp<RW>(r0, r1, rn, read_len);
-        ok = editdist_consistent_reg<RW>(ref, ref0, left0, cig, nLC, r0, r1, rn, (unsigned)(num_mm & 0xff)) && valid_cigar(P, cig, nLC);
+        if (ok && anti) reg_revcomp<RW>(r0, r1, rn, read_len);
+        ok = editdist_consistent_reg<RW>(ref, ref0, left0, cig, nLC, r0, r1, rn, (unsigned)(num_mm & 0xff), ok);
+        if (ok) ok = valid_cigar(P, cig, nLC);
       }
       const unsigned em = __ballot_sync(0xffffffffu, ok);
       if (em) {

@@ -142,8 +142,10 @@ int fail(thb_ctx* c, int code, const char* fmt, ...)
 
 // THB_TINY_CAPS=1 (test knob): every growable structure starts tiny, so that the overflow -> grow -> repeat paths run on small inputs
 bool tiny_caps() { static const bool v = getenv("THB_TINY_CAPS") != nullptr; return v; }
-// THB_JOIN_LEGACY=1 / THB_SCAN_LEGACY=1 (measurement knobs): round 1's queue-based kernels instead of the TMA-staged tile kernels
-bool join_legacy() { static const bool v = getenv("THB_JOIN_LEGACY") != nullptr; return v; }
+// Measurement knobs.  THB_SCAN_LEGACY=1: round 1's bundle_kernel + hit_kernel instead of the TMA-staged scan tile kernel.
+// THB_JOIN_TILE=1: the TMA-staged join tile kernel instead of the queue kernels (chain_enum + merge_simple + merge_abut) -- measured
+// on B200 it is instruction-issue bound at 13 of 32 lanes and 11 % slower than the queue kernels (profiles/r2c_*), so it is not the default.
+bool join_legacy() { static const bool v = getenv("THB_JOIN_TILE") == nullptr || getenv("THB_JOIN_LEGACY") != nullptr; return v; }
 bool scan_legacy() { static const bool v = getenv("THB_SCAN_LEGACY") != nullptr; return v; }
 
 HashSet make_set(DevBuf& b, uint64_t cap, unsigned int* ovf) { HashSet h; h.slots = (uint64_t*)b.p; h.mask = cap - 1; h.overflow = ovf; return h; }
