@@ -279,9 +279,17 @@ def run_long_spanning_reads(binary: str, files: Dict[str, str], bams: Dict[str, 
 
 
 def read_bam(path: str):
-    """Decoded BAM records (BGZF is multi-member gzip): (qname, flag, tid, pos, mapq, cigar, seq, qual, mtid, mpos, tlen, aux dict)."""
+    """Decoded BAM records (BGZF is multi-member gzip): (qname, flag, tid, pos, mapq, cigar, seq, qual, mtid, mpos, tlen, aux dict).
+    A stage run with -p N leaves <path minus .bam>0.bam .. N-1.bam instead of <path> (long_spanning_reads.cpp:3056-3064): those are
+    read in order and concatenated."""
     import gzip
     import struct
+    if not os.path.exists(path) and os.path.exists(path[:-4] + "0.bam"):
+        refs, recs, i = None, [], 0
+        while os.path.exists(path[:-4] + "%d.bam" % i):
+            r, rec = read_bam(path[:-4] + "%d.bam" % i)
+            refs = refs or r; recs += rec; i += 1
+        return refs, recs
     data = gzip.open(path, "rb").read()
     assert data[:4] == b"BAM\x01"
     l_text = struct.unpack_from("<i", data, 4)[0]

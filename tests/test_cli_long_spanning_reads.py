@@ -58,12 +58,15 @@ def test_cli_matches_reference_binary(kw, spliced):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
-def test_cli_host_threads_do_not_change_the_output():
-    """-p N: our executable builds the BAM records and deflates the BGZF blocks on N host threads; records, their order and the
-    side index entries (read id every >= 1000 records) must not depend on N; records equal the reference's (-p1)."""
+def test_cli_read_id_ranges_do_not_change_the_output():
+    """-p N: our executable splits the read ids into N ranges at entries of the reads file's .index (every stream positioned by its
+    own index and filtered by id) and writes <out>0.bam .. <out>N-1.bam like the reference (long_spanning_reads.cpp:3056-3064).  The
+    concatenation must equal the -p1 output = the reference's -p1 records, whatever N; every side-index entry of every file must be the
+    BGZF virtual offset of the first record of that read id."""
+    import struct, zlib
     OUR_BIN = helpers.our_bin("long_spanning_reads")
     with tempfile.TemporaryDirectory() as td:
-        wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(400_000, 150_000), n_pairs=6000, seed=407, indel_prob=0.3))
+        wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(400_000, 150_000), n_pairs=9000, seed=407, indel_prob=0.3))
         files = synth.write_pipeline_files(wl, td)
         nseg = len(wl.left.seg_hits)
         bams = pyoracle.make_bams(files, td, nseg)
@@ -71,22 +74,25 @@ def test_cli_host_threads_do_not_change_the_output():
         jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
         ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg, side="left", tag=".ref")
         _, want = pyoracle.read_bam(ref_bam)
-        idx = {}
-        for n in (1, 5):
+        n_files = {}
+        for n in (1, 3, 7):
             bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, bams, jin, outs, td, nseg, side="left", tag=".p%d" % n, threads=n)
             _, got = pyoracle.read_bam(bam)
             assert got == want, "-p%d: records differ from the reference" % n
-            idx[n] = [l.split("\t")[0] for l in open(bam + ".index")]
-            # every side-index entry is a valid BGZF virtual offset of the first record of that read id
-            import struct, zlib
-            raw = open(bam, "rb").read()
-            for line in open(bam + ".index"):
-                rid, voff = (int(x) for x in line.split("\t"))
-                boff, inoff = voff >> 16, voff & 0xffff
-                data = b""
-                while len(data) < inoff + 64 and boff < len(raw):
-                    bsize = struct.unpack_from("<H", raw, boff + 16)[0] + 1
-                    data += zlib.decompress(raw[boff + 18: boff + bsize - 8], -15); boff += bsize
-                l_qn = data[inoff + 12]
-                assert int(data[inoff + 36: inoff + 36 + l_qn - 1].decode()) == rid
-        assert len(want) > 2000 and len(idx[1]) >= 2 and idx[1] == idx[5]
+            parts = [bam] if os.path.exists(bam) else []
+            while not os.path.exists(bam) and os.path.exists(bam[:-4] + "%d.bam" % len(parts)):
+                parts.append(bam[:-4] + "%d.bam" % len(parts))
+            n_files[n] = len(parts)
+            assert not any(f.endswith(".thb_tmp") for f in os.listdir(td)), "temporary output left behind"
+            for part in parts:
+                raw = open(part, "rb").read()
+                for line in open(part + ".index"):
+                    rid, voff = (int(x) for x in line.split("\t"))
+                    boff, inoff = voff >> 16, voff & 0xffff
+                    data = b""
+                    while len(data) < inoff + 64 and boff < len(raw):
+                        bsize = struct.unpack_from("<H", raw, boff + 16)[0] + 1
+                        data += zlib.decompress(raw[boff + 18: boff + bsize - 8], -15); boff += bsize
+                    l_qn = data[inoff + 12]
+                    assert int(data[inoff + 36: inoff + 36 + l_qn - 1].decode()) == rid
+        assert len(want) > 3000 and n_files[1] == 1 and n_files[3] == 3 and n_files[7] >= 4

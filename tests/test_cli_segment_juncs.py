@@ -79,15 +79,18 @@ def test_cli_no_hits_exit_zero():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
-def test_cli_two_side_threads_equal_reference_p1():
-    """-p N > 1: our executable assembles the two mate sides on two threads; all four outputs (insertions depend on the first-wins
-    order between the sides) must equal the reference's -p1 output."""
+@pytest.mark.parametrize("threads", [4, 9])
+def test_cli_read_id_ranges_equal_reference_p1(threads):
+    """-p N > 1: our executable works through (mate side) x (read-id range) tasks on N threads, every stream positioned by its own
+    .index side file; all four outputs (insertions depend on the first-wins order over sides and ranges) must equal the reference's
+    -p1 output -- the reference's own -p N output can lack the hit groups at its range boundaries."""
     OUR_BIN = helpers.our_bin("segment_juncs")
     with tempfile.TemporaryDirectory() as td:
-        wl, files, bams, nseg = _prepare(td, synth.SynthConfig(contig_lens=(300_000, 100_000), n_pairs=4000, seed=307, indel_prob=0.5, fusion_frac=0.1))
+        wl, files, bams, nseg = _prepare(td, synth.SynthConfig(contig_lens=(300_000, 100_000), n_pairs=9000, seed=307, indel_prob=0.5, fusion_frac=0.1))
         opts = pyoracle.tophat_common_opts(50, 20, ["--fusion-search", "--fusion-min-dist", "20000"])
         ref = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts, tag=".ref", threads=1)
-        ours = pyoracle.run_segment_juncs(OUR_BIN, files, bams, td, nseg, opts=opts, tag=".b200p4", threads=4)
+        ours = pyoracle.run_segment_juncs(OUR_BIN, files, bams, td, nseg, opts=opts, tag=".b200p%d" % threads, threads=threads)
         for k in ("juncs", "insertions", "deletions", "fusions"):
             assert open(ours[k]).read() == open(ref[k]).read(), "segment.%s differs from the reference's -p1 output" % k
         assert open(ref["insertions"]).read().count("\n") > 100
+        assert len(open(files["left_fq"]).read().split("\n")) > 4 * 8000          # enough reads for several index entries per file

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <thread>
+#include <atomic>
 #include <mutex>
 #include <cstdio>
 #include <cstdlib>
@@ -152,29 +153,44 @@ int main(int argc, char** argv)
   std::vector<thb_junction> jv(jset.begin(), jset.end()); std::vector<thb_insertion> iv(iset.begin(), iset.end());
 
   std::mutex rtm;
-  std::vector<std::unique_ptr<JoinHitStream>> contig, spliced;
-  for (auto& f : seg_files) contig.emplace_back(new JoinHitStream(f, rt, rtm, false, o.p.max_report_intron_length, o.p.min_anchor_len));
-  for (auto& f : spl_files) spliced.emplace_back(new JoinHitStream(f, rt, rtm, true, o.p.max_report_intron_length, o.p.min_anchor_len));
-  FullReadStream reads(reads_fname);
-  // spliced streams may name contigs unknown so far: make sure every id has a (possibly empty) slot before upload
-  // (ids created later belong to sequence-less contigs and can never pass the consistency check)
   { thb_ref_image img = g.image(); if (thb_ref_upload(ctx, &img) != THB_OK) die("Error: thb_ref_upload: %s", thb_last_error(ctx)); }
   if (thb_join_begin(ctx, &o.p, jv.data(), jv.size(), iv.data(), iv.size()) != THB_OK) die("Error: thb_join_begin: %s", thb_last_error(ctx));
   auto t1 = std::chrono::steady_clock::now();
 
-  BamWriter bw;
-  if (!bw.open(bam_out, o.sam_header, bam_out + ".index", &err)) die("Error: %s", err);
-  std::vector<int> ref2tid;
+  // Read-id ranges, one output BAM per range -- the reference's own -p N layout (<out minus .bam><i>.bam, 3056-3064, which
+  // tophat.py:3775-3779 picks up): contiguous id ranges split at entries of the reads file's .index, every stream positioned by
+  // its own index and filtered by id.  The library is entered by one range at a time (the kernels are a small part of a range).
+  std::vector<uint32_t> splits;
+  if (o.num_threads > 1) { BamIndex ix; if (ix.load(reads_fname) || ix.load(seg_files.back())) splits = split_ids(ix, std::min(o.num_threads, 64)); }
+  const size_t n_ranges = splits.size() + 1;
+  // tophat.py prefers <out>.bam over the per-range files when it exists and is not empty (3772-3779): one left over from an
+  // earlier run must not shadow this run's output
+  if (n_ranges > 1 && bam_out.compare(0, 5, "/dev/") != 0) { remove(bam_out.c_str()); remove((bam_out + ".index").c_str()); }
+  std::mutex ctx_mutex, stat_mutex;
+  uint64_t n_reads = 0, n_out = 0;
+  double submit_s = 0, post_s = 0;           // TOPHAT_GPU_STATS: time inside thb_join_submit / in sorting, SAM fields and BAM output (summed over ranges)
   const GenomeView gv{&g};
   const size_t nseg = seg_files.size();
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+
+  auto run_range = [&](size_t ri) {
+  const uint32_t begin_id = ri ? splits[ri - 1] : 0u, end_id = ri < splits.size() ? splits[ri] : 0xffffffffu;
+  std::string out_path = bam_out, err;
+  if (n_ranges > 1) out_path = bam_out.substr(0, bam_out.size() >= 4 ? bam_out.size() - 4 : bam_out.size()) + std::to_string(ri) + ".bam";
+  const int T = n_ranges > 1 ? 1 : std::max(1, std::min(o.num_threads, 64));       // record-building threads of one flush
+  std::vector<std::unique_ptr<JoinHitStream>> contig, spliced;
+  for (auto& f : seg_files) contig.emplace_back(new JoinHitStream(f, rt, rtm, false, o.p.max_report_intron_length, o.p.min_anchor_len, range_for(f, begin_id, end_id)));
+  for (auto& f : spl_files) spliced.emplace_back(new JoinHitStream(f, rt, rtm, true, o.p.max_report_intron_length, o.p.min_anchor_len, range_for(f, begin_id, end_id)));
+  FullReadStream reads(reads_fname, range_for(reads_fname, begin_id, end_id));
+  uint64_t r_reads = 0, r_out = 0; double r_submit = 0, r_post = 0;
+  BamWriter bw;
+  if (!bw.open(out_path, o.sam_header, out_path + ".index", &err)) die("Error: %s", err);
+  std::vector<int> ref2tid;
 
   struct Pending { uint32_t id; FullRead read; };
   std::vector<thb_join_bundle> bundles; std::vector<uint16_t> segc; std::vector<uint64_t> rplanes; std::vector<thb_jhit> hits; std::vector<thb_jops> ops_ext; std::vector<Pending> pend;
-  std::vector<thb_jhit_full> read_hits;
-  uint64_t n_reads = 0, n_out = 0;
-  double submit_s = 0, post_s = 0;           // TOPHAT_GPU_STATS: time inside thb_join_submit / in sorting, SAM fields and BAM output
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  std::vector<thb_jhit_full> read_hits; std::vector<thb_joined> joined_copy;
   auto flush = [&]() {
     if (bundles.empty()) return;
     const auto f0 = now();
@@ -182,9 +198,14 @@ int main(int argc, char** argv)
     thb_join_batch jb; memset(&jb, 0, sizeof jb);
     jb.n_bundles = (uint32_t)bundles.size(); jb.n_segs = (uint32_t)nseg; jb.read_words = 4; jb.bundles = bundles.data(); jb.seg_count = segc.data();
     jb.reads = rplanes.data(); jb.n_hits = hits.size(); jb.hits = hits.data(); jb.n_ops_ext = ops_ext.size(); jb.ops_ext = ops_ext.data();
-    const thb_joined* out = nullptr; uint64_t no = 0;
-    if (thb_join_submit(ctx, &jb, &out, &no) != THB_OK) die("Error: thb_join_submit: %s", thb_last_error(ctx));
-    const auto f1 = now(); submit_s += secs(f0, f1);
+    // the result buffer belongs to the context and lives until the next join call: copied out before the next range enters
+    uint64_t no = 0;
+    { std::lock_guard<std::mutex> cl(ctx_mutex);
+      const thb_joined* res = nullptr;
+      if (thb_join_submit(ctx, &jb, &res, &no) != THB_OK) die("Error: thb_join_submit: %s", thb_last_error(ctx));
+      joined_copy.assign(res, res + no); }
+    const thb_joined* out = joined_copy.data();
+    const auto f1 = now(); r_submit += secs(f0, f1);
     std::vector<std::vector<Joined>> per(bundles.size());
     for (uint64_t i = 0; i < no; ++i) {
       const thb_joined& j = out[i]; Joined J; J.ref_id = j.ref_id; J.left = j.left; J.anti = (j.flags & THB_HIT_ANTISENSE) != 0;
@@ -196,7 +217,6 @@ int main(int argc, char** argv)
     { std::lock_guard<std::mutex> l(rtm);
       ref2tid.assign(rt.size() + 1, -1);
       for (uint32_t id = 1; id <= rt.size(); ++id) ref2tid[id] = bw.target_id(rt.name(id)); }
-    const int T = std::max(1, std::min(o.num_threads, 64));
     std::vector<BamWriter::RecordPart> parts((size_t)T);
     auto build_slice = [&](int t) {
     BamWriter::RecordPart& part = parts[(size_t)t];
@@ -259,14 +279,14 @@ int main(int argc, char** argv)
     };
     if (T == 1) build_slice(0);
     else { std::vector<std::thread> th; for (int t = 1; t < T; ++t) th.emplace_back(build_slice, t); build_slice(0); for (auto& x : th) x.join(); }
-    for (const auto& part : parts) n_out += part.sizes.size();
+    for (const auto& part : parts) r_out += part.sizes.size();
     bw.append_records(parts, T);
     bundles.clear(); segc.clear(); rplanes.clear(); hits.clear(); ops_ext.clear(); pend.clear();
-    post_s += secs(f1, now());
+    r_post += secs(f1, now());
   };
 
   // JoinSegmentsWorker::operator() (2671-2845)
-  const size_t BATCH = 1u << 20;
+  const size_t BATCH = n_ranges > 1 ? (1u << 18) : (1u << 20);
   std::vector<std::vector<thb_jhit_full>> seg_hits(nseg);
   for (;;) {
     const uint32_t cid = contig[0]->next_group_id();
@@ -310,7 +330,7 @@ int main(int argc, char** argv)
     }
     ReadRec rr; pack_read_ascii(rd->seq.data(), (uint32_t)rd->seq.size(), rr);
     rplanes.insert(rplanes.end(), rr.planes, rr.planes + 12);
-    bundles.push_back(bu); pend.push_back(Pending{id, *rd}); ++n_reads;
+    bundles.push_back(bu); pend.push_back(Pending{id, *rd}); ++r_reads;
     if (bundles.size() >= BATCH) flush();
   }
   flush();
@@ -320,6 +340,18 @@ int main(int argc, char** argv)
   { uint64_t dropped = 0; for (auto& h : contig) dropped += h->dropped_long_cigars(); for (auto& h : spliced) dropped += h->dropped_long_cigars();
     if (dropped) die("Error: %s segment hits carry more than 9 CIGAR operations (outside the GPU path; the output would lack their alignments)", std::to_string(dropped)); }
   if (!bw.close(&err)) die("Error: %s", err);
+  { std::lock_guard<std::mutex> sl(stat_mutex); n_reads += r_reads; n_out += r_out; submit_s += r_submit; post_s += r_post; }
+  };   // run_range
+
+  {
+    std::atomic<size_t> next(0);
+    auto worker = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n_ranges) break; run_range(i); } };
+    const int nthr = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, o.num_threads), n_ranges));
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nthr; ++k) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+  }
   auto t2 = std::chrono::steady_clock::now();
   if (getenv("TOPHAT_GPU_STATS")) {
     thb_join_timing tm; thb_join_last_timing(ctx, &tm);

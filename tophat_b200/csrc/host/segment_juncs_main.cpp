@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <mutex>
 #include <thread>
+#include <atomic>
 #include "tophat_b200.h"
 #include "thb_options.hpp"
 #include "thb_input.hpp"
@@ -69,19 +70,21 @@ static void submit(thb_ctx* ctx, Batch& b, uint32_t nseg, uint64_t& order_base, 
 // One mate side: SegmentSearchWorker::operator() (4565-4663) at -p1, i.e. every hit group in increasing id order.
 static void process_side(thb_ctx* ctx, const Options& o, RefTable& rt, std::mutex& rtm, const std::string& reads_fname,
                          const std::vector<std::string>& segs, const std::string& partner_map, const std::string& partner_seg,
-                         bool right_mate, uint64_t& order_base, Stats& st)
+                         bool right_mate, uint64_t& order_base, Stats& st, uint32_t begin_id, uint32_t end_id, size_t batch_bundles)
 {
+  // the read ids [begin_id, end_id) of this side (SegmentSearchWorker's begin_id / end_id, 4565-4663): every stream is positioned
+  // by its own .index side file and filtered by id
   const uint32_t nseg = (uint32_t)segs.size();
   if (nseg > THB_MAX_SEGS) die("Error: more than %s segments per read are not supported by the GPU path", std::to_string(THB_MAX_SEGS));
   std::vector<std::unique_ptr<HitStream>> hs;
-  for (auto& f : segs) hs.emplace_back(new HitStream(f, rt, rtm, o.p.max_report_intron_length));
+  for (auto& f : segs) hs.emplace_back(new HitStream(f, rt, rtm, o.p.max_report_intron_length, range_for(f, begin_id, end_id)));
   std::unique_ptr<HitStream> pm, ps;
-  if (!partner_map.empty()) pm.reset(new HitStream(partner_map, rt, rtm, o.p.max_report_intron_length));
-  if (!partner_seg.empty()) ps.reset(new HitStream(partner_seg, rt, rtm, o.p.max_report_intron_length));
-  ReadStream rs(reads_fname);
+  if (!partner_map.empty()) pm.reset(new HitStream(partner_map, rt, rtm, o.p.max_report_intron_length, range_for(partner_map, begin_id, end_id)));
+  if (!partner_seg.empty()) ps.reset(new HitStream(partner_seg, rt, rtm, o.p.max_report_intron_length, range_for(partner_seg, begin_id, end_id)));
+  ReadStream rs(reads_fname, range_for(reads_fname, begin_id, end_id));
   const bool fusion = o.p.fusion_search != 0;
   Batch b; std::vector<uint64_t> packed; std::vector<thb_hit> tmp;
-  const size_t BATCH = 1u << 21;
+  const size_t BATCH = batch_bundles;
   for (;;) {
     uint32_t id = 0;
     for (auto& h : hs) { const uint32_t g = h->next_group_id(); if (g && (!id || g < id)) id = g; }
@@ -157,7 +160,14 @@ int main(int argc, char** argv)
   FILE* del_out = fopen(tmp_of(del_fname).c_str(), "w"); if (!del_out) die("Error: cannot open %s for writing", del_fname);
   FILE* fus_out = fopen(tmp_of(fus_fname).c_str(), "w"); if (!fus_out) die("Error: cannot open %s for writing", fus_fname);
 
-  if (left_segs.empty()) { fprintf(stderr, "No hits to process, exiting\n"); return 0; }          // 4724-4728
+  auto publish_outputs = [&]() {
+    for (const std::string* n : { &juncs_fname, &ins_fname, &del_fname, &fus_fname })
+      if (tmp_of(*n) != *n && rename(tmp_of(*n).c_str(), n->c_str()) != 0) die("Error: cannot move the finished output into place: %s", *n);
+  };
+  if (left_segs.empty()) {                                                                       // 4724-4728: the (empty) files exist
+    fclose(juncs_out); fclose(ins_out); fclose(del_out); fclose(fus_out); publish_outputs();
+    fprintf(stderr, "No hits to process, exiting\n"); return 0;
+  }
   if (!o.no_coverage_search || !o.no_microexon_search || o.butterfly_search)
     die("Error: coverage / microexon / butterfly search are outside the GPU path (tophat.py passes --no-coverage-search "
         "--no-microexon-search for reads of >= 3 segments)");
@@ -181,27 +191,45 @@ int main(int argc, char** argv)
     if (thb_segjuncs_fusion_ignore(ctx, ids.data(), (uint32_t)ids.size()) != THB_OK) die("Error: %s", thb_last_error(ctx));
   }
 
-  // The two mate sides are independent passes over disjoint files (4752, 4831): with -p > 1 they are assembled on two threads.
-  // Insertions keep the single-threaded first-wins order because every right-side bundle carries a priority above every
-  // left-side one (order_base of the right side starts at 2^38).
-  std::mutex rtm; uint64_t order_left = 0, order_right = 1ull << 38; Stats st, st_r; g_stats = &st;
+  // Work list = (mate side) x (read-id range), like the reference's threads (4756-4826 left mates, 4835-4905 right mates): the sides
+  // are independent passes over disjoint files, the ranges are contiguous id ranges split at entries of the reads file's .index.
+  // -p N threads take the tasks; the library is entered by one task at a time (its kernels are a small part of a task).
+  // Insertions keep the single-threaded first-wins order: a bundle's priority is its position in the -p1 processing order
+  // (left mates by id, then right mates by id) -- order_base = side << 38 | range << 31.
+  std::mutex rtm; Stats st; g_stats = &st;
+  std::vector<uint32_t> splits;
+  if (o.num_threads > 1) {
+    BamIndex ix;
+    if (ix.load(left_reads) || ix.load(left_segs.back())) splits = split_ids(ix, std::min(o.num_threads, 64));
+  }
+  struct Task { bool right; uint32_t begin_id, end_id; uint64_t order_base; Stats st; };
+  std::vector<Task> tasks;
+  for (int side = 0; side < 2; ++side) {
+    if ((side == 0 ? left_segs.size() : right_segs.size()) <= 1) continue;
+    for (size_t r = 0; r <= splits.size(); ++r)
+      tasks.push_back(Task{side == 1, r ? splits[r - 1] : 0u, r < splits.size() ? splits[r] : 0xffffffffu, ((uint64_t)side << 38) | ((uint64_t)r << 31), Stats()});
+  }
   fprintf(stderr, ">> Performing segment-search:\n");
-  std::thread right_thread;
-  const bool two_threads = o.num_threads > 1 && left_segs.size() > 1 && right_segs.size() > 1;
-  if (two_threads)
-    right_thread = std::thread([&] { process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_right, st_r); });
-  if (left_segs.size() > 1) {
-    fprintf(stderr, "Loading left segment hits... "); fflush(stderr);
-    process_side(ctx, o, rt, rtm, left_reads, left_segs, right_map, right_segs.empty() ? std::string() : right_segs.back(), false, order_left, st);
-    fprintf(stderr, "done.\n");
+  if (left_segs.size() > 1) fprintf(stderr, "Loading left segment hits... done.\n");
+  if (right_segs.size() > 1) fprintf(stderr, "Loading right segment hits...done.\n");
+  {
+    const size_t batch = tasks.size() > 2 ? (1u << 19) : (1u << 21);
+    std::atomic<size_t> next(0);
+    auto run = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1); if (i >= tasks.size()) break;
+        Task& t = tasks[i];
+        if (!t.right) process_side(ctx, o, rt, rtm, left_reads, left_segs, right_map, right_segs.empty() ? std::string() : right_segs.back(), false, t.order_base, t.st, t.begin_id, t.end_id, batch);
+        else process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, t.order_base, t.st, t.begin_id, t.end_id, batch);
+      }
+    };
+    const int nthr = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, o.num_threads), tasks.size()));
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nthr; ++k) pool.emplace_back(run);
+    run();
+    for (auto& th : pool) th.join();
+    for (const Task& t : tasks) { st.bundles += t.st.bundles; st.hits += t.st.hits; }
   }
-  if (right_segs.size() > 1) {
-    fprintf(stderr, "Loading right segment hits..."); fflush(stderr);
-    if (two_threads) right_thread.join();
-    else { order_right = order_left; process_side(ctx, o, rt, rtm, right_reads, right_segs, left_map, left_segs.back(), true, order_right, st_r); }
-    fprintf(stderr, "done.\n");
-  }
-  st.bundles += st_r.bundles; st.hits += st_r.hits;
   st.sides_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
   thb_segjuncs_results r;
   if (thb_segjuncs_finish(ctx, &r) != THB_OK) die("Error: thb_segjuncs_finish: %s", thb_last_error(ctx));
@@ -257,8 +285,7 @@ int main(int argc, char** argv)
     }
   }
   fclose(fus_out);
-  for (const std::string* n : { &juncs_fname, &ins_fname, &del_fname, &fus_fname })
-    if (tmp_of(*n) != *n && rename(tmp_of(*n).c_str(), n->c_str()) != 0) die("Error: cannot move the finished output into place: %s", *n);
+  publish_outputs();
   fprintf(stderr, "Reporting potential fusions...\n");
   if (getenv("TOPHAT_GPU_STATS")) {
     thb_timing tm; thb_last_timing(ctx, &tm);

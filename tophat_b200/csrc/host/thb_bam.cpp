@@ -3,6 +3,9 @@
 #include <cstring>
 #include <thread>
 #include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
 
 namespace thbhost {
 
@@ -91,7 +94,9 @@ bool BamReader::refill(size_t need)
     if (eof_) return false;
     if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, end_ - pos_); end_ -= pos_; pos_ = 0; }
     std::vector<BlockRef> blocks; size_t raw_used = 0, out_total = 0;
-    const size_t RAW_WINDOW = 8u << 20;
+    // compressed bytes per refill: starts small (a reader of a short id range must not inflate megabytes it will never
+    // deliver) and doubles up to 8 MB while the reader keeps going
+    const size_t RAW_WINDOW = window_; if (window_ < (8u << 20)) window_ *= 2;
     raw_.resize(RAW_WINDOW + 65536);
     while (raw_used < RAW_WINDOW) {
       uint8_t h[18];
@@ -161,6 +166,35 @@ bool BamReader::open(const std::string& path, int inflate_threads)
     name.resize(strlen(name.c_str()));
     hdr_.target_name.push_back(name); hdr_.target_len.push_back(l_ref);
   }
+  return true;
+}
+
+bool BamReader::open_shared(const std::string& path, uint64_t voff, int inflate_threads)
+{
+  static std::mutex m; static std::map<std::string, std::shared_ptr<const BamHeader>> cache;
+  std::shared_ptr<const BamHeader> h;
+  { std::lock_guard<std::mutex> l(m); auto it = cache.find(path); if (it != cache.end()) h = it->second; }
+  if (!h || voff == 0) {
+    if (!open(path, inflate_threads)) return false;                 // parses the header (and leaves the reader behind it)
+    if (!h) { std::lock_guard<std::mutex> l(m); auto& slot = cache[path]; if (!slot) slot = std::make_shared<BamHeader>(hdr_); h = slot; }
+    shared_hdr_ = h; hdr_ = BamHeader();
+    return voff == 0 ? true : seek(voff);
+  }
+  close(); path_ = path; err_.clear(); eof_ = false; pos_ = end_ = 0; threads_ = inflate_threads < 1 ? 1 : inflate_threads;
+  f_ = fopen(path.c_str(), "rb");
+  if (!f_) { err_ = "cannot open " + path + " for reading"; return false; }
+  setvbuf(f_, nullptr, _IOFBF, 1 << 20);
+  shared_hdr_ = h;
+  return seek(voff);
+}
+
+bool BamReader::seek(uint64_t voff)
+{
+  if (!f_) return false;
+  if (fseeko(f_, (off_t)(voff >> 16), SEEK_SET) != 0) { err_ = path_ + ": cannot seek"; return false; }
+  pos_ = end_ = 0; eof_ = false;
+  const size_t within = (size_t)(voff & 0xffffu);
+  if (within) { if (!refill(within)) { if (err_.empty()) err_ = path_ + ": bad virtual offset"; return false; } pos_ += within; }
   return true;
 }
 

@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -40,8 +41,15 @@ class BamReader {
   BamReader& operator=(const BamReader&) = delete;
   // Opens and parses the header.  Returns false (message in error()) on failure.
   bool open(const std::string& path, int inflate_threads = 2);
-  const BamHeader& header() const { return hdr_; }
+  // Same, for one of several readers of the same file (read-id ranges on different threads): the header -- 100 MB of text for a
+  // junction index with a million contigs -- is parsed once per process and shared; a reader that starts at a virtual offset
+  // never touches it.
+  bool open_shared(const std::string& path, uint64_t virtual_offset, int inflate_threads = 1);
+  const BamHeader& header() const { return shared_hdr_ ? *shared_hdr_ : hdr_; }
   bool next(BamRecord& r);                 // false at end of file or on error (check error())
+  // Continues at a BGZF virtual offset (compressed block start << 16 | offset inside the inflated block), e.g. one taken from a
+  // <file>.index side file (common.h:577-611).  Call after open().
+  bool seek(uint64_t virtual_offset);
   const std::string& error() const { return err_; }
   void close();
 
@@ -50,10 +58,10 @@ class BamReader {
   bool read_exact(void* dst, size_t n);
   FILE* f_ = nullptr;
   std::string path_, err_;
-  BamHeader hdr_;
+  BamHeader hdr_; std::shared_ptr<const BamHeader> shared_hdr_;
   std::vector<uint8_t> buf_; size_t pos_ = 0, end_ = 0;
   std::vector<uint8_t> raw_;
-  bool eof_ = false; int threads_ = 2;
+  bool eof_ = false; int threads_ = 2; size_t window_ = 128u << 10;
 };
 
 }  // namespace thbhost

@@ -1,5 +1,6 @@
 #include "thb_bamwrite.hpp"
 #include <zlib.h>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -24,10 +25,18 @@ int reg2bin(int beg, int end)
 
 // Deflates one BGZF block payload (<= BLOCK_DATA bytes) into `out` (header + data + crc + isize); returns the block's size or 0.
 // BSIZE is 16 bits: a payload that deflate cannot shrink below 64 KiB - 26 is stored instead (level 0: payload + 5 bytes always fits).
+// Compression level: the stage's BAM is an intermediate file that tophat_reports reads once; level 1 deflates the 4-bit packed
+// bases and the quality strings three to four times faster than zlib's default 6 (which the reference uses through samtools'
+// bgzf) for about a tenth more bytes.  TOPHAT_GPU_BAM_LEVEL=<0..9> overrides.
+static int bgzf_level()
+{
+  static const int v = [] { const char* e = getenv("TOPHAT_GPU_BAM_LEVEL"); const int l = e ? atoi(e) : 1; return l < 0 ? 0 : (l > 9 ? 9 : l); }();
+  return v;
+}
 static size_t bgzf_compress(const uint8_t* src, size_t n, uint8_t* out, size_t out_cap)
 {
   size_t clen = 0;
-  for (int level : {6, 0}) {
+  for (int level : {bgzf_level(), 0}) {
     z_stream zs; memset(&zs, 0, sizeof zs);
     deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
     zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n; zs.next_out = out + 18; zs.avail_out = (uInt)(out_cap - 18 - 8);

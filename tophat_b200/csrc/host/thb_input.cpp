@@ -123,8 +123,44 @@ bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int 
 }
 
 // ---- HitStream ------------------------------------------------------------------------------------------
-HitStream::HitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, int max_report_intron)
-  : path_(path), rt_(rt), rt_mutex_(rt_mutex), max_report_intron_(max_report_intron), q_(4)
+bool BamIndex::load(const std::string& bam_path)
+{
+  entries.clear();
+  FILE* f = fopen((bam_path + ".index").c_str(), "r");
+  if (!f) return false;
+  unsigned long long id = 0; long long off = 0;
+  while (fscanf(f, "%llu %lld", &id, &off) == 2) if (off > 0) entries.emplace_back((uint32_t)id, (uint64_t)off);
+  fclose(f);
+  return !entries.empty();
+}
+uint64_t BamIndex::offset_for(uint32_t begin_id) const
+{
+  // entries are in increasing id order; upper_bound - 1 = last entry with id <= begin_id
+  size_t lo = 0, hi = entries.size();
+  while (lo < hi) { const size_t mid = (lo + hi) / 2; if (entries[mid].first <= begin_id) lo = mid + 1; else hi = mid; }
+  return lo ? entries[lo - 1].second : 0;
+}
+std::vector<uint32_t> split_ids(const BamIndex& idx, int parts)
+{
+  std::vector<uint32_t> out;
+  const size_t n = idx.entries.size();
+  if (parts < 2 || n < 2) return out;
+  const size_t np = std::min<size_t>((size_t)parts, n);
+  for (size_t k = 1; k < np; ++k) {
+    const uint32_t id = idx.entries[n * k / np].first;
+    if (id > 0 && (out.empty() || id > out.back())) out.push_back(id);
+  }
+  return out;
+}
+StreamRange range_for(const std::string& bam_path, uint32_t begin_id, uint32_t end_id)
+{
+  StreamRange r; r.begin_id = begin_id; r.end_id = end_id;
+  if (begin_id > 0) { BamIndex ix; if (ix.load(bam_path)) r.voffset = ix.offset_for(begin_id); }
+  return r;
+}
+
+HitStream::HitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, int max_report_intron, StreamRange range)
+  : path_(path), rt_(rt), rt_mutex_(rt_mutex), max_report_intron_(max_report_intron), range_(range), q_(4)
 {
   th_ = std::thread([this] { produce(); });
 }
@@ -133,7 +169,7 @@ HitStream::~HitStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 void HitStream::produce()
 {
   BamReader br;
-  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  if (!br.open_shared(path_, range_.voffset)) { err_ = br.error(); q_.finish(); return; }
   std::vector<uint32_t> tid2ref(br.header().target_name.size(), 0);
   { std::lock_guard<std::mutex> l(rt_mutex_);
     for (size_t i = 0; i < tid2ref.size(); ++i) tid2ref[i] = rt_.get_id(br.header().target_name[i]); }
@@ -150,6 +186,8 @@ void HitStream::produce()
     }
     HitRec hr; memset(&hr, 0, sizeof hr);
     hr.id = (uint32_t)atoi(r.qname);          // atoi stops at '|' (ReadTable::get_id, bwt_map.h:546-552)
+    if (hr.id < range_.begin_id) continue;    // id range of this stream (files are id-sorted: fix_map_ordering)
+    if (hr.id >= range_.end_id) break;
     if (r.tid < 0) {                          // unmapped record -> hit on "*" (1145-1156)
       if (!star_id) { std::lock_guard<std::mutex> l(rt_mutex_); star_id = rt_.get_id("*"); }
       hr.h.ref_id = star_id; hr.h.flags = end ? THB_HIT_END : 0;
@@ -233,7 +271,7 @@ void pack_read_ascii(const char* s, uint32_t len, ReadRec& r)
   }
 }
 
-ReadStream::ReadStream(const std::string& path) : path_(path), q_(4)
+ReadStream::ReadStream(const std::string& path, StreamRange range) : path_(path), range_(range), q_(4)
 {
   const bool bam = path.size() >= 4 && path.compare(path.size() - 4, 4, ".bam") == 0;
   th_ = std::thread([this, bam] { if (bam) produce_bam(); else produce_fastx(); });
@@ -243,7 +281,7 @@ ReadStream::~ReadStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 void ReadStream::produce_bam()
 {
   BamReader br;
-  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  if (!br.open_shared(path_, range_.voffset)) { err_ = br.error(); q_.finish(); return; }
   // 4-bit BAM base codes "=ACMGRSVTWYHKDBN": A=1 C=2 G=4 T=8, everything else is treated as N
   static const int8_t code[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};
   const size_t CH = 1 << 15;
@@ -253,6 +291,8 @@ void ReadStream::produce_bam()
     if (r.flag & 0x200) continue;                    // BAM_FQCFAIL reads are skipped (reads.cpp:552)
     ReadRec rr; memset(&rr, 0, sizeof rr);
     rr.id = (uint32_t)atol(r.qname);
+    if (rr.id < range_.begin_id) continue;
+    if (rr.id >= range_.end_id) break;
     if (r.l_seq > 255) { err_ = path_ + ": read longer than 255 bases"; break; }
     rr.len = (uint32_t)r.l_seq;
     for (int i = 0; i < r.l_seq; ++i) {
@@ -288,6 +328,8 @@ void ReadStream::produce_fastx()
     if (!getl(seq)) break;
     if (fq) { getl(plus); getl(qual); }
     ReadRec rr; rr.id = (uint32_t)atol(l.c_str() + 1);
+    if (rr.id < range_.begin_id) continue;             // text read files have no index: a range scans from the start
+    if (rr.id >= range_.end_id) break;
     if (seq.size() > 255) { err_ = path_ + ": read longer than 255 bases"; break; }
     for (char& c : seq) c = (char)toupper((unsigned char)c);
     pack_read_ascii(seq.data(), (uint32_t)seq.size(), rr);

@@ -73,13 +73,30 @@ class ChunkQueue {
   std::mutex m_; std::condition_variable cv_; std::deque<std::vector<T>> q_; size_t depth_; bool done_ = false, stop_ = false;
 };
 
+// A contiguous read-id range of an id-sorted BAM stream: where to start reading (BGZF virtual offset, 0 = behind the header) and
+// the ids to deliver, [begin_id, end_id).  The reference partitions its threads the same way (utils.cpp:22-129), but starts every
+// stream at the index entry of the LAST file's split id and so can lose hit groups at the range boundaries; here every stream is
+// positioned by its own index and filtered by id, so the union over the ranges is exactly the whole file.
+struct StreamRange { uint64_t voffset = 0; uint32_t begin_id = 0; uint32_t end_id = 0xffffffffu; };
+
+// <bam>.index side file: "read_id <TAB> virtual offset" of the first record of that read, an entry every >= 1000 records.
+struct BamIndex {
+  std::vector<std::pair<uint32_t, uint64_t>> entries;
+  bool load(const std::string& bam_path);                 // false if the side file is missing / empty
+  uint64_t offset_for(uint32_t begin_id) const;            // offset of the last entry with id <= begin_id, else 0
+};
+// Split ids for `parts` ranges with about equal numbers of index entries; fewer parts when the index is short.  Returns the
+// begin ids of parts 1.. (part 0 begins at id 0).
+std::vector<uint32_t> split_ids(const BamIndex& idx, int parts);
+StreamRange range_for(const std::string& bam_path, uint32_t begin_id, uint32_t end_id);
+
 struct HitRec { uint32_t id; thb_hit h; };
 
 // HitStream + BAMHitFactory::get_hit_from_buf (bwt_map.h:1040-1227; bwt_map.cpp:1101-1452) reduced to the
 // fields the hot path reads.  Groups = maximal runs of records with the same numeric qname prefix.
 class HitStream {
  public:
-  HitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, int max_report_intron);
+  HitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, int max_report_intron, StreamRange range = StreamRange());
   ~HitStream();
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
@@ -91,7 +108,7 @@ class HitStream {
   void produce();
   bool ensure();
   std::string path_, err_;
-  RefTable& rt_; std::mutex& rt_mutex_; int max_report_intron_;
+  RefTable& rt_; std::mutex& rt_mutex_; int max_report_intron_; StreamRange range_;
   ChunkQueue<HitRec> q_; std::thread th_;
   std::vector<HitRec> cur_; size_t pos_ = 0; bool end_ = false; uint64_t n_records_ = 0;
 };
@@ -101,7 +118,7 @@ struct ReadRec { uint32_t id; uint32_t len; uint64_t planes[12]; };   // plane0[
 // ReadStream::getRead (reads.cpp:571-630) for BAM and FASTA/FASTQ read files with numeric names.
 class ReadStream {
  public:
-  explicit ReadStream(const std::string& path);
+  explicit ReadStream(const std::string& path, StreamRange range = StreamRange());
   ~ReadStream();
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
@@ -110,7 +127,7 @@ class ReadStream {
  private:
   void produce_bam(); void produce_fastx();
   bool ensure();
-  std::string path_, err_;
+  std::string path_, err_; StreamRange range_;
   ChunkQueue<ReadRec> q_; std::thread th_;
   std::vector<ReadRec> cur_; size_t pos_ = 0; bool end_ = false;
 };

@@ -2,6 +2,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 
 namespace thbhost {
 
@@ -92,6 +94,10 @@ bool splice_cigar(std::vector<Op>& spl, const std::vector<Op>& cigar, const std:
   return (f == C_MATCH || f == C_mATCH) && (l == C_MATCH || l == C_mATCH);
 }
 
+// one juncs_db contig: where its event lies on the genome
+struct SplTarget { bool ok = false, ins = false; uint32_t ref_id = 0; int left_edge = 0, splice_left = 0, splice_right = 0; std::string inserted;
+                   int opcode = C_REF_SKIP; bool rev = false; };
+
 void split(const std::string& s, char sep, std::vector<std::string>& out, bool strict)
 {
   out.clear(); std::string cur;
@@ -101,8 +107,9 @@ void split(const std::string& s, char sep, std::vector<std::string>& out, bool s
 
 }  // namespace
 
-JoinHitStream::JoinHitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, bool spliced, int max_report_intron, int min_anchor_len)
-  : path_(path), rt_(rt), rt_mutex_(rt_mutex), spliced_(spliced), max_report_intron_(max_report_intron), min_anchor_len_(min_anchor_len), q_(4)
+JoinHitStream::JoinHitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, bool spliced, int max_report_intron, int min_anchor_len,
+                             StreamRange range)
+  : path_(path), rt_(rt), rt_mutex_(rt_mutex), spliced_(spliced), max_report_intron_(max_report_intron), min_anchor_len_(min_anchor_len), range_(range), q_(4)
 {
   th_ = std::thread([this] { produce(); });
 }
@@ -111,36 +118,45 @@ JoinHitStream::~JoinHitStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 void JoinHitStream::produce()
 {
   BamReader br;
-  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  if (!br.open_shared(path_, range_.voffset)) { err_ = br.error(); q_.finish(); return; }
   const auto& tnames = br.header().target_name;
   std::vector<uint32_t> tid2ref(tnames.size(), 0);
   if (!spliced_) { std::lock_guard<std::mutex> l(rt_mutex_); for (size_t i = 0; i < tid2ref.size(); ++i) tid2ref[i] = rt_.get_id(tnames[i]); }
-  // spliced streams: contig names "ref|left_start|L-R|right_end|type|strand" are parsed once per target
-  struct SplTarget { bool ok = false, ins = false; uint32_t ref_id = 0; int left_edge = 0, splice_left = 0, splice_right = 0; std::string inserted;
-                     int opcode = C_REF_SKIP; bool rev = false; };
-  std::vector<SplTarget> spl(spliced_ ? tnames.size() : 0);
+  // spliced streams: contig names "ref|left_start|L-R|right_end|type|strand" are parsed once per file and process (the table is
+  // shared by the read-id ranges of the file: a junction index has a contig per junction)
+  std::shared_ptr<const std::vector<SplTarget>> spl_tab;
   if (spliced_) {
-    std::vector<std::string> toks, st;
-    for (size_t i = 0; i < tnames.size(); ++i) {
-      split(tnames[i], '|', toks, true);
-      const int extra = (int)toks.size() - 6;
-      if (extra < 0) continue;                                    // malformed splice record -> every hit on it is skipped
-      std::string contig = toks[0];
-      for (int t = 1; t <= extra; ++t) { contig += "|"; contig += toks[t]; }
-      split(toks[extra + 2], '-', st, false);
-      if (st.size() != 2) continue;
-      const std::string& jtype = toks[extra + 4]; const std::string& jstrand = toks[extra + 5];
-      SplTarget T; T.left_edge = atoi(toks[extra + 1].c_str()); T.splice_left = atoi(st[0].c_str());
-      if (jtype == "ins") { T.ins = true; T.inserted = st[1]; T.rev = jstrand == "rev"; }
-      else {
-        if (jtype == "fus") continue;                             // fusion contigs only exist with --fusion-search (unsupported)
-        if (!(jstrand == "rev" || jstrand == "fwd" || jstrand == "ff" || jstrand == "fr" || jstrand == "rf" || jstrand == "rr")) continue;
-        T.opcode = jtype == "del" ? C_DEL : C_REF_SKIP; T.splice_right = atoi(st[1].c_str()); T.rev = jstrand == "rev";
+    static std::mutex cm; static std::map<std::string, std::shared_ptr<const std::vector<SplTarget>>> cache;
+    std::lock_guard<std::mutex> cl(cm);                            // one builder at a time; later ranges find the table ready
+    auto& slot = cache[path_];
+    if (!slot) {
+      auto tab = std::make_shared<std::vector<SplTarget>>(tnames.size());
+      std::vector<std::string> toks, st;
+      for (size_t i = 0; i < tnames.size(); ++i) {
+        split(tnames[i], '|', toks, true);
+        const int extra = (int)toks.size() - 6;
+        if (extra < 0) continue;                                    // malformed splice record -> every hit on it is skipped
+        std::string contig = toks[0];
+        for (int t = 1; t <= extra; ++t) { contig += "|"; contig += toks[t]; }
+        split(toks[extra + 2], '-', st, false);
+        if (st.size() != 2) continue;
+        const std::string& jtype = toks[extra + 4]; const std::string& jstrand = toks[extra + 5];
+        SplTarget T; T.left_edge = atoi(toks[extra + 1].c_str()); T.splice_left = atoi(st[0].c_str());
+        if (jtype == "ins") { T.ins = true; T.inserted = st[1]; T.rev = jstrand == "rev"; }
+        else {
+          if (jtype == "fus") continue;                             // fusion contigs only exist with --fusion-search (unsupported)
+          if (!(jstrand == "rev" || jstrand == "fwd" || jstrand == "ff" || jstrand == "fr" || jstrand == "rf" || jstrand == "rr")) continue;
+          T.opcode = jtype == "del" ? C_DEL : C_REF_SKIP; T.splice_right = atoi(st[1].c_str()); T.rev = jstrand == "rev";
+        }
+        { std::lock_guard<std::mutex> l(rt_mutex_); T.ref_id = rt_.get_id(contig); }
+        T.ok = true; (*tab)[i] = T;
       }
-      { std::lock_guard<std::mutex> l(rt_mutex_); T.ref_id = rt_.get_id(contig); }
-      T.ok = true; spl[i] = T;
+      slot = tab;
     }
+    spl_tab = slot;
   }
+  static const std::vector<SplTarget> no_targets;
+  const std::vector<SplTarget>& spl = spl_tab ? *spl_tab : no_targets;
   uint32_t star_id = 0;
   const size_t CH = 1 << 15;
   std::vector<JHitRec> chunk; chunk.reserve(CH);
@@ -152,6 +168,8 @@ void JoinHitStream::produce()
     if (pipe && strchr(pipe + 1, ':')) end = last_segment_from_suffix(pipe + 1);
     JHitRec hr; memset(&hr, 0, sizeof hr);
     hr.id = (uint32_t)atoi(r.qname);
+    if (hr.id < range_.begin_id) continue;        // id range of this stream (files are id-sorted)
+    if (hr.id >= range_.end_id) break;
     if (r.tid < 0) {
       if (!star_id) { std::lock_guard<std::mutex> l(rt_mutex_); star_id = rt_.get_id("*"); }
       hr.h.ref_id = star_id; hr.h.n_ops = 1; hr.h.ops[0] = pack_op(Op{C_MATCH, 0}); hr.h.flags = end ? THB_HIT_END : 0;
@@ -248,20 +266,23 @@ void JoinHitStream::skip_group()
 { const uint32_t id = next_group_id(); if (!id) return; while (ensure() && cur_[pos_].id == id) ++pos_; }
 
 // ---- FullReadStream ---------------------------------------------------------------------------------------
-FullReadStream::FullReadStream(const std::string& path) : path_(path), q_(4) { th_ = std::thread([this] { produce(); }); }
+FullReadStream::FullReadStream(const std::string& path, StreamRange range) : path_(path), range_(range), q_(4) { th_ = std::thread([this] { produce(); }); }
 FullReadStream::~FullReadStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 
 void FullReadStream::produce()
 {
   BamReader br;
-  if (!br.open(path_)) { err_ = br.error(); q_.finish(); return; }
+  if (!br.open_shared(path_, range_.voffset)) { err_ = br.error(); q_.finish(); return; }
   static const char* nt16 = "=ACMGRSVTWYHKDBN";
   const size_t CH = 1 << 14;
   std::vector<FullRead> chunk; chunk.reserve(CH);
   BamRecord r;
   while (br.next(r)) {
     if (r.flag & 0x200) continue;
-    FullRead fr; fr.id = (uint32_t)atol(r.qname); fr.name = r.qname;
+    const uint32_t rid = (uint32_t)atol(r.qname);
+    if (rid < range_.begin_id) continue;
+    if (rid >= range_.end_id) break;
+    FullRead fr; fr.id = rid; fr.name = r.qname;
     fr.seq.resize((size_t)r.l_seq); fr.qual.resize((size_t)r.l_seq);
     for (int i = 0; i < r.l_seq; ++i) { fr.seq[i] = nt16[(r.seq[i >> 1] >> ((~i & 1) << 2)) & 15]; fr.qual[i] = (char)(r.qual[i] + 33); }
     chunk.push_back(std::move(fr));

@@ -11,7 +11,8 @@ struct JHitRec { uint32_t id; thb_jhit_full h; };
 class JoinHitStream {
  public:
   // spliced = SplicedBAMHitFactory semantics (bwt_map.cpp:1469-1770), else BAMHitFactory (1101-1452)
-  JoinHitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, bool spliced, int max_report_intron, int min_anchor_len);
+  JoinHitStream(const std::string& path, RefTable& rt, std::mutex& rt_mutex, bool spliced, int max_report_intron, int min_anchor_len,
+                StreamRange range = StreamRange());
   ~JoinHitStream();
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
@@ -23,7 +24,7 @@ class JoinHitStream {
   void produce();
   bool ensure();
   std::string path_, err_;
-  RefTable& rt_; std::mutex& rt_mutex_; bool spliced_; int max_report_intron_, min_anchor_len_;
+  RefTable& rt_; std::mutex& rt_mutex_; bool spliced_; int max_report_intron_, min_anchor_len_; StreamRange range_;
   ChunkQueue<JHitRec> q_; std::thread th_;
   std::vector<JHitRec> cur_; size_t pos_ = 0; bool end_ = false; uint64_t dropped_ = 0;
 };
@@ -32,7 +33,7 @@ struct FullRead { uint32_t id; std::string name, seq, qual; };
 
 class FullReadStream {
  public:
-  explicit FullReadStream(const std::string& path);
+  explicit FullReadStream(const std::string& path, StreamRange range = StreamRange());
   ~FullReadStream();
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
@@ -40,7 +41,7 @@ class FullReadStream {
  private:
   void produce();
   bool ensure();
-  std::string path_, err_;
+  std::string path_, err_; StreamRange range_;
   ChunkQueue<FullRead> q_; std::thread th_;
   std::vector<FullRead> cur_; size_t pos_ = 0; bool end_ = false;
 };

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include <dlfcn.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -736,7 +737,15 @@ int thb_segjuncs_submit(thb_ctx* ctx, const thb_segjuncs_batch* b)
   return THB_OK;
 }
 
-static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit)
+// THB_TRACE=1: host wall clock of the phases of thb_segjuncs_finish on stderr (development aid)
+struct Trace {
+  bool on = getenv("THB_TRACE") != nullptr; std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now(); std::string line;
+  void mark(const char* what) { if (!on) return; const auto n = std::chrono::steady_clock::now(); char b[96];
+    snprintf(b, sizeof b, " %s %.3f", what, std::chrono::duration<double, std::milli>(n - t).count()); line += b; t = n; }
+  ~Trace() { if (on && !line.empty()) fprintf(stderr, "[thb trace ms]%s\n", line.c_str()); }
+};
+
+static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit, Trace* tr = nullptr)
 {
   CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8)); CU(ctx->d_count.reserve(64));
   CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
@@ -745,6 +754,7 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_jun
   unsigned long long n = 0;
   CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
+  if (tr) tr->mark("compact");
   out.clear();
   if (n == 0) return THB_OK;
   size_t tmp = 0;
@@ -755,9 +765,12 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_jun
   CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
   decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_keys_sorted.p, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
   CU(cudaGetLastError()); ctx->own_launches++;
+  if (tr) tr->mark("sort+decode(enqueue)");
   CU(out.resize(n));
+  if (tr) tr->mark("host_resize");
   CU(cudaMemcpyAsync(out.data(), ctx->d_decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
+  if (tr) tr->mark("d2h+sync");
   return THB_OK;
 }
 
@@ -766,10 +779,11 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   if (!ctx || !out) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  Trace tr;
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   int rc;
-  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull))) return rc;
-  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull, &tr))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull, &tr))) return rc;
   // insertions: first inserted wins among equal (ref, left, length) -- insertions.h:52-67
   unsigned long long nins = 0;
   CU(cudaMemcpyAsync(&nins, ctx->d_ins_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -826,10 +840,12 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
       ctx->h_fus.push_back(o);
     }
   }
+  tr.mark("ins+fus");
   CU(cudaEventRecord(ctx->ev_b, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   float ms = 0.f; CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
   ctx->timing.finish_ms = ms;
+  tr.mark("events");
   unsigned long long cnt[8];
   CU(cudaMemcpy(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
   ctx->n_ins_out = nins; ctx->n_del_out = ctx->h_dels.size();
