@@ -93,13 +93,16 @@ int main(int argc, char** argv)
 
   thb_ctx* ctx = nullptr;
   const char* dev_env = getenv("TOPHAT_GPU_DEVICE");
-  if (thb_create(dev_env ? atoi(dev_env) : 0, &ctx) != THB_OK) die("Error: %s", thb_last_error(nullptr));
+  // the CUDA context (0.3 - 1.5 s per process) comes up on its own thread while this one loads the genome
+  int create_rc = THB_OK; std::thread ctx_thread([&] { create_rc = thb_create(dev_env ? atoi(dev_env) : 0, &ctx); });
+  auto join_ctx = [&]() { if (ctx_thread.joinable()) ctx_thread.join(); if (create_rc != THB_OK) die("Error: %s", thb_last_error(nullptr)); };
   auto t0 = std::chrono::steady_clock::now();
   RefTable rt; std::string err;
   if (!o.sam_header.empty() && !rt.load_sam_header(o.sam_header, &err)) die("%s", err);
   fprintf(stderr, "Loading reference sequences...\n");
   Genome g;
-  if (!load_fasta(ref_fname, rt, g, false, 8, &err)) die("Error: %s", err);
+  if (!load_fasta(ref_fname, rt, g, false, std::max(8, o.num_threads), &err)) { join_ctx(); die("Error: %s", err); }
+  join_ctx();
   fprintf(stderr, "        reference sequences loaded.\n");
 
   // junctions + deletions -> std::set<Junction>; insertions -> std::set<Insertion> (2895-2980)

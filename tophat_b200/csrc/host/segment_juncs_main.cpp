@@ -174,14 +174,17 @@ int main(int argc, char** argv)
 
   const char* dev_env = getenv("TOPHAT_GPU_DEVICE");
   thb_ctx* ctx = nullptr;
-  if (thb_create(dev_env ? atoi(dev_env) : 0, &ctx) != THB_OK) die("Error: %s", thb_last_error(nullptr));
+  // the CUDA context (0.3 - 1.5 s per process) comes up on its own thread while this one loads the genome
+  int create_rc = THB_OK; std::thread ctx_thread([&] { create_rc = thb_create(dev_env ? atoi(dev_env) : 0, &ctx); });
+  auto join_ctx = [&]() { if (ctx_thread.joinable()) ctx_thread.join(); if (create_rc != THB_OK) die("Error: %s", thb_last_error(nullptr)); };
 
   auto t0 = std::chrono::steady_clock::now();
   RefTable rt; std::string err;
   if (!o.sam_header.empty() && !rt.load_sam_header(o.sam_header, &err)) die("%s", err);
   fprintf(stderr, "Loading reference sequences...\n");
   Genome g;
-  if (!load_fasta(ref_fname, rt, g, true, 8, &err)) die("Error: %s", err);
+  if (!load_fasta(ref_fname, rt, g, true, std::max(8, o.num_threads), &err)) { join_ctx(); die("Error: %s", err); }
+  join_ctx();
   { thb_ref_image img = g.image(); if (thb_ref_upload(ctx, &img) != THB_OK) die("Error: thb_ref_upload: %s", thb_last_error(ctx)); }
   auto t1 = std::chrono::steady_clock::now();
   if (thb_segjuncs_begin(ctx, &o.p) != THB_OK) die("Error: %s", thb_last_error(ctx));

@@ -1,4 +1,6 @@
 #include "thb_input.hpp"
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -55,10 +57,93 @@ thb_ref_image Genome::image() const
   return img;
 }
 
+// ---- packed genome image cached next to the FASTA ---------------------------------------------------------------------
+// Every stage process loads the same FASTA (three processes per sample; the reference spends ~12 ms per Mbp on it, 37 s for an
+// hg38-sized genome, each time).  The first process to parse a FASTA of >= 16 MB leaves <fasta>.thb_img: the contigs in file
+// order (name, length) + the bit planes; later processes check size / mtime of the FASTA, replay the name -> id assignments and
+// read the planes.  TOPHAT_GPU_NO_IMAGE_CACHE=1 turns it off; an unwritable directory just means no cache.
+namespace {
+struct ImgHeader { char magic[8]; uint64_t fasta_size, fasta_mtime_ns, n_blocks; uint32_t n_fasta_contigs, reserved; };
+const char IMG_MAGIC[8] = {'T', 'H', 'B', 'I', 'M', 'G', '2', 0};
+
+bool fasta_stamp(const std::string& path, uint64_t* size, uint64_t* mtime_ns)
+{
+  struct stat st; if (stat(path.c_str(), &st) != 0) return false;
+  *size = (uint64_t)st.st_size; *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec; return true;
+}
+
+void layout_genome(const RefTable& rt, const std::map<uint32_t, uint64_t>& len_of, Genome& g)
+{
+  const uint32_t nc = rt.size();
+  g.contig_start.assign(nc, 0); g.contig_len.assign(nc, 0);
+  uint64_t gpos = 0;
+  for (uint32_t id = 1; id <= nc; ++id) {
+    auto it = len_of.find(id);
+    const uint64_t len = it == len_of.end() ? 0 : it->second;
+    g.contig_start[id - 1] = gpos; g.contig_len[id - 1] = (uint32_t)len;
+    gpos += ((len + 63) / 64 + 1) * 64;
+  }
+  g.n_blocks = gpos / 64 + 1;
+}
+
+bool load_image_cache(const std::string& path, RefTable& rt, Genome& g, bool log)
+{
+  if (getenv("TOPHAT_GPU_NO_IMAGE_CACHE")) return false;
+  uint64_t fsz = 0, fmt = 0; if (!fasta_stamp(path, &fsz, &fmt)) return false;
+  FILE* f = fopen((path + ".thb_img").c_str(), "rb"); if (!f) return false;
+  bool ok = false; ImgHeader h;
+  std::vector<std::pair<std::string, uint64_t>> contigs;
+  if (fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, IMG_MAGIC, 8) == 0 && h.fasta_size == fsz && h.fasta_mtime_ns == fmt && h.n_fasta_contigs < (1u << 26)) {
+    ok = true;
+    for (uint32_t i = 0; ok && i < h.n_fasta_contigs; ++i) {
+      uint32_t nl = 0; uint64_t len = 0;
+      if (fread(&nl, 4, 1, f) != 1 || nl > 65535) { ok = false; break; }
+      std::string nm(nl, '\0');
+      if ((nl && fread(&nm[0], 1, nl, f) != nl) || fread(&len, 8, 1, f) != 1) { ok = false; break; }
+      contigs.emplace_back(nm, len);
+    }
+  }
+  if (ok) {
+    // the same get_id sequence the parse performs (a repeated name keeps the later record, as std::map::operator[] + swap does)
+    RefTable trial = rt; std::map<uint32_t, uint64_t> len_of;
+    for (auto& c : contigs) len_of[trial.get_id(c.first)] = c.second;
+    Genome t; layout_genome(trial, len_of, t);
+    if (t.n_blocks != h.n_blocks) ok = false;
+    else {
+      t.planes.resize(2 * t.n_blocks); t.nmask.resize(t.n_blocks);
+      ok = fread(t.planes.data(), 8, 2 * t.n_blocks, f) == 2 * t.n_blocks && fread(t.nmask.data(), 8, t.n_blocks, f) == t.n_blocks;
+      if (ok) {
+        rt = trial; g = std::move(t);
+        if (log) for (auto& c : contigs) { if (!c.first.empty()) fprintf(stderr, "\tLoading %s...", c.first.c_str()); if (c.second) fprintf(stderr, " done (%ld bases).\n", (long)c.second); }
+      }
+    }
+  }
+  fclose(f);
+  return ok;
+}
+
+void save_image_cache(const std::string& path, const std::vector<std::pair<std::string, uint64_t>>& contigs, const Genome& g)
+{
+  if (getenv("TOPHAT_GPU_NO_IMAGE_CACHE")) return;
+  ImgHeader h; memset(&h, 0, sizeof h); memcpy(h.magic, IMG_MAGIC, 8);
+  if (!fasta_stamp(path, &h.fasta_size, &h.fasta_mtime_ns) || h.fasta_size < (16u << 20)) return;
+  h.n_blocks = g.n_blocks; h.n_fasta_contigs = (uint32_t)contigs.size();
+  const std::string tmp = path + ".thb_img.tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb"); if (!f) return;
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  for (auto& c : contigs) { const uint32_t nl = (uint32_t)c.first.size(); ok = ok && fwrite(&nl, 4, 1, f) == 1 && (!nl || fwrite(c.first.data(), 1, nl, f) == nl) && fwrite(&c.second, 8, 1, f) == 1; }
+  ok = ok && fwrite(g.planes.data(), 8, g.planes.size(), f) == g.planes.size() && fwrite(g.nmask.data(), 8, g.nmask.size(), f) == g.nmask.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), (path + ".thb_img").c_str()) != 0) remove(tmp.c_str());
+}
+}  // namespace
+
 bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int threads, std::string* err)
 {
+  if (load_image_cache(path, rt, g, log)) return true;
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) { *err = "cannot open " + path + " for reading"; return false; }
+  std::vector<std::pair<std::string, uint64_t>> fasta_order;
   std::map<uint32_t, std::string> seqs;          // id -> bases (no line breaks)
   std::vector<char> buf(1 << 22);
   std::string name, seq, header; bool in_header = false, have_record = false, at_line_start = true;
@@ -67,6 +152,7 @@ bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int 
     if (log && !name.empty()) fprintf(stderr, "\tLoading %s...", name.c_str());
     if (log && !seq.empty()) fprintf(stderr, " done (%ld bases).\n", (long)seq.size());
     const uint32_t id = rt.get_id(name);
+    fasta_order.emplace_back(name, (uint64_t)seq.size());
     seqs[id].swap(seq); seq.clear();
   };
   size_t n;
@@ -97,17 +183,9 @@ bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int 
   fclose(f);
   if (in_header) { size_t cut = header.find_first_of(" \t\r"); name = cut == std::string::npos ? header : header.substr(0, cut); }
   flush();
-  const uint32_t nc = rt.size();
-  g.contig_start.assign(nc, 0); g.contig_len.assign(nc, 0);
-  uint64_t gpos = 0;
-  for (uint32_t id = 1; id <= nc; ++id) {
-    auto it = seqs.find(id);
-    const uint64_t len = it == seqs.end() ? 0 : it->second.size();
-    if (len > 0xffffffffull) { *err = "contig longer than 2^32 bases"; return false; }
-    g.contig_start[id - 1] = gpos; g.contig_len[id - 1] = (uint32_t)len;
-    gpos += ((len + 63) / 64 + 1) * 64;
-  }
-  g.n_blocks = gpos / 64 + 1;
+  { std::map<uint32_t, uint64_t> len_of;
+    for (auto& kv : seqs) { if (kv.second.size() > 0xffffffffull) { *err = "contig longer than 2^32 bases"; return false; } len_of[kv.first] = kv.second.size(); }
+    layout_genome(rt, len_of, g); }
   g.planes.assign(2 * g.n_blocks, 0); g.nmask.assign(g.n_blocks, 0);
   // pack 64-aligned slices in parallel (slices never share a plane word)
   struct Job { uint32_t id; uint64_t off, len; };
@@ -119,6 +197,7 @@ bool load_fasta(const std::string& path, RefTable& rt, Genome& g, bool log, int 
   std::vector<std::thread> th; const int nt = std::max(1, std::min<int>(threads, (int)jobs.size()));
   for (int t = 1; t < nt; ++t) th.emplace_back(work);
   work(); for (auto& t : th) t.join();
+  save_image_cache(path, fasta_order, g);
   return true;
 }
 
@@ -278,6 +357,21 @@ ReadStream::ReadStream(const std::string& path, StreamRange range) : path_(path)
 }
 ReadStream::~ReadStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 
+namespace {
+struct Nib2 { uint8_t p0[256], p1[256], pn[256]; };
+Nib2 make_nib2(const int8_t (&code)[16])
+{
+  Nib2 t;
+  for (int b = 0; b < 256; ++b) {
+    uint8_t a0 = 0, a1 = 0, an = 0;
+    for (int h = 0; h < 2; ++h) { const int c = code[h == 0 ? (b >> 4) : (b & 15)];
+      if (c < 0) an |= (uint8_t)(1u << h); else { if (c & 1) a0 |= (uint8_t)(1u << h); if (c & 2) a1 |= (uint8_t)(1u << h); } }
+    t.p0[b] = a0; t.p1[b] = a1; t.pn[b] = an;
+  }
+  return t;
+}
+}  // namespace
+
 void ReadStream::produce_bam()
 {
   BamReader br;
@@ -295,12 +389,17 @@ void ReadStream::produce_bam()
     if (rr.id >= range_.end_id) break;
     if (r.l_seq > 255) { err_ = path_ + ": read longer than 255 bases"; break; }
     rr.len = (uint32_t)r.l_seq;
-    for (int i = 0; i < r.l_seq; ++i) {
-      const int v = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 15; const int c = code[v];
-      const int w = i >> 6, j = i & 63;
-      if (c < 0) rr.planes[8 + w] |= 1ull << j;
-      else { if (c & 1) rr.planes[w] |= 1ull << j; if (c & 2) rr.planes[4 + w] |= 1ull << j; }
-    }
+    // a BAM byte carries two bases (high nibble first): table -> two bits per plane, 32 bytes per plane word
+    { static const Nib2 tab = make_nib2(code);
+      const int nbytes = (r.l_seq + 1) >> 1;
+      for (int k = 0; k < nbytes; ++k) {
+        const uint8_t b = r.seq[k]; const int w = k >> 5, sh = (k & 31) << 1;
+        rr.planes[w] |= (uint64_t)tab.p0[b] << sh; rr.planes[4 + w] |= (uint64_t)tab.p1[b] << sh; rr.planes[8 + w] |= (uint64_t)tab.pn[b] << sh;
+      }
+      if (r.l_seq & 1) {                                  // the unused low nibble of the last byte is not a base
+        const int i = r.l_seq, w = i >> 6; const uint64_t keep = ~(1ull << (i & 63));
+        rr.planes[w] &= keep; rr.planes[4 + w] &= keep; rr.planes[8 + w] &= keep;
+      } }
     chunk.push_back(rr);
     if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<ReadRec>(); chunk.reserve(CH); }
   }

@@ -284,7 +284,8 @@ void FullReadStream::produce()
     if (rid >= range_.end_id) break;
     FullRead fr; fr.id = rid; fr.name = r.qname;
     fr.seq.resize((size_t)r.l_seq); fr.qual.resize((size_t)r.l_seq);
-    for (int i = 0; i < r.l_seq; ++i) { fr.seq[i] = nt16[(r.seq[i >> 1] >> ((~i & 1) << 2)) & 15]; fr.qual[i] = (char)(r.qual[i] + 33); }
+    for (int k = 0; 2 * k < r.l_seq; ++k) { const uint8_t b = r.seq[k]; fr.seq[2 * k] = nt16[b >> 4]; if (2 * k + 1 < r.l_seq) fr.seq[2 * k + 1] = nt16[b & 15]; }
+    for (int i = 0; i < r.l_seq; ++i) fr.qual[i] = (char)(r.qual[i] + 33);
     chunk.push_back(std::move(fr));
     if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<FullRead>(); chunk.reserve(CH); }
   }
