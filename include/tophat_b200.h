@@ -232,6 +232,17 @@ int thb_segjuncs_allgather(thb_ctx* ctx);
 /* CIGAR ops are packed as length << 4 | CigarOpCode (bwt_map.h:36-55: MATCH 1, INS 3, DEL 5, REF_SKIP 11,
  * SOFT_CLIP 13, PAD 15; lower-case fusion-side codes never occur without --fusion-search).                    */
 #define THB_JHIT_ONE_MATCH  0x08   /* the CIGAR is a single MATCH of right-left bases: no thb_jops record        */
+/* --fusion-search: CigarOpCodes 2 / 4 / 6 / 12 (mATCH, iNS, dEL, rEF_SKIP: the lower-case ops of a part that is read leftwards) and
+ * 7 .. 10 (FUSION_FF / FR / RF / RR, length = position on the second contig) occur (bwt_map.h:36-55).  A segment hit against a
+ * `fus` contig of the junction index carries its second contig in thb_jhit_full.ops[8] (so it has at most 8 CIGAR ops), which
+ * thb_join_pack_hits moves to thb_jops.ops[11].  thb_joined.flags of a merged alignment with a fusion has THB_JOINED_FUSION and
+ * its second contig in ops[THB_JOINED_MAX_OPS - 1] (such an alignment has at most 26 ops); THB_JOINED_SEQ_RC says that the
+ * alignment's own sequence (BowtieHit::seq(), what bowtie_sam_extra reads) is the reverse complement of the read.             */
+#define THB_JHIT_SEQ_FLIPPED 0x10  /* thb_jhit_full.flags only: the hit's BAM sequence is oriented opposite to what THB_HIT_ANTISENSE
+                                      says (a hit on an rf / rr fusion contig, whose strand the reference flips, bwt_map.cpp:1740-1741);
+                                      thb_join_pack_hits moves it to thb_jops.ops[10]                                              */
+#define THB_JOINED_FUSION   0x10
+#define THB_JOINED_SEQ_RC   0x20
 /* Wire form of one segment's BowtieHit (BAMHitFactory / SplicedBAMHitFactory).  Nearly every hit is an un-gapped match,
  * so the record the kernels stream is 16 bytes: position, right() and the small fields; the CIGAR of the other hits
  * (against the junction index: M N M, indels ...) sits in a side array, one thb_jops per such hit, in hit order.       */
@@ -293,6 +304,10 @@ typedef struct thb_joined {        /* the BowtieHit merge_chain returns         
  * insertion set (2952-2980).  Arrays must be sorted and unique in the reference's set orders.                */
 int thb_join_begin(thb_ctx* ctx, const thb_params* params, const thb_junction* juncs, uint64_t n_juncs,
                    const thb_insertion* insertions, uint64_t n_insertions);
+/* --fusion-search (params->fusion_search != 0 in thb_join_begin): the fusion set of long_spanning_reads.cpp:2996-3040, sorted and
+ * unique in Fusion order (refid1, refid2, left, right, dir; fusions.h:40-70); count / edit_dist of the records are ignored.
+ * Call after thb_join_begin; thb_join_begin resets the set to empty.                                                          */
+int thb_join_set_fusions(thb_ctx* ctx, const thb_fusion* fusions, uint64_t n_fusions);
 /* Joins one batch (host arrays); *out / *n_out receive the merged alignments of this batch, grouped by nothing
  * in particular (use .bundle), owned by ctx and valid until the next join call.                              */
 int thb_join_submit(thb_ctx* ctx, const thb_join_batch* host_batch, const thb_joined** out, uint64_t* n_out);

@@ -188,3 +188,101 @@ def reference_input_texts(res, names):
     t = as_text(res, names)
     t["fusions"] = pyoracle.format_fusions(res.fusions, res.junctions, names, resolve_conflicts=False)    # --fusion-do-not-resolve-conflicts
     return t
+
+
+# ---- the reference's own fusion_test read sets through BOTH stages (BASELINE configs[0] / configs[4]) ----------------------
+
+FUSION_TEST_EXTRA = ["--bowtie1", "--fusion-search", "--fusion-min-dist", "500", "--fusion-do-not-resolve-conflicts"]
+FUSION_TEST_OVERRIDES = {"--max-report-intron": "500", "--max-segment-intron": "500", "--max-coverage-intron": "500", "--max-closure-intron": "500"}
+
+
+def fusion_test_options():
+    o = pyoracle.tophat_common_opts(50, 20, list(FUSION_TEST_EXTRA))
+    for k, v in FUSION_TEST_OVERRIDES.items():
+        o[o.index(k) + 1] = v
+    return o
+
+
+def _brute_contig_hits(contig_codes, seg, max_mm=2):
+    """(contig index, pos0, anti, aligned codes, mismatch mask) of every un-gapped placement with <= max_mm mismatches"""
+    out = []
+    L = seg.shape[0]
+    for anti, q in ((False, seg), (True, synth.revcomp_codes(seg))):
+        for ci, codes in enumerate(contig_codes):
+            if codes.shape[0] < L:
+                continue
+            win = np.lib.stride_tricks.sliding_window_view(codes, L)
+            mmask = (win != q[None, :]) | (win > 3) | (q[None, :] > 3)
+            for pos in np.nonzero(mmask.sum(axis=1) <= max_mm)[0]:
+                out.append((ci, int(pos), anti, q, mmask[pos], codes[pos:pos + L]))
+    return out
+
+
+def fusion_test_pipeline(name, td):
+    """One of the committed fusion_test input sets (tests/golden/reference_*/inputs.npz) taken through the stage boundary with the
+    reference's own tools: prep_reads / fix_map_ordering BAMs, the reference's segment_juncs, its juncs_db over all four outputs (junction,
+    insertion, deletion AND fusion contigs), and -- standing in for bowtie against that index -- every un-gapped <= 2-mismatch placement
+    of every segment of the unmapped reads on those contigs.  Returns what run_long_spanning_reads needs."""
+    import subprocess
+    wl, P, _ = load_reference_input_case(name)
+    opts = fusion_test_options()
+    files = {"fasta": os.path.join(td, "ref.fa"), "header": os.path.join(td, "hdr.sam"), "left_fq": os.path.join(td, "left.fq")}
+    synth.write_fasta(files["fasta"], wl.ref); synth.write_sam_header(files["header"], wl.ref); synth.write_fastq(files["left_fq"], wl.left)
+    nseg = len(wl.left.seg_hits)
+    sams = {"mapped": os.path.join(td, "left_mapped.sam")}
+    synth.write_hits_sam(sams["mapped"], wl, wl.left, wl.left.mapped_hits, None)
+    for k in range(nseg):
+        sams["seg%d" % (k + 1)] = os.path.join(td, "left_seg%d.sam" % (k + 1))
+        synth.write_hits_sam(sams["seg%d" % (k + 1)], wl, wl.left, wl.left.seg_hits[k], k)
+    bams = {"left_reads": os.path.join(td, "left_kept_reads.bam")}
+    subprocess.run([os.path.join(pyoracle.REF_DIR, "prep_reads"), "--sam-header", files["header"], "--outfile", bams["left_reads"],
+                    "--index-outfile", bams["left_reads"] + ".index", "--aux-outfile", os.path.join(td, "left.info"), files["left_fq"]],
+                   check=True, stderr=subprocess.DEVNULL)
+    for key, sam in sams.items():
+        bam = os.path.join(td, "left_kept_reads_%s.bam" % key)
+        subprocess.run([os.path.join(pyoracle.REF_DIR, "fix_map_ordering"), "--sam-header", files["header"], "--index-outfile", bam + ".index", sam, bam],
+                       check=True, stderr=subprocess.DEVNULL)
+        bams["left_" + key] = bam
+    outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts, paired=False)
+    # the junction index: juncs_db <min_anchor> <read length> juncs insertions deletions fusions ref.fa  (tophat.py:2546-2600)
+    fa = os.path.join(td, "segment_juncs.fa")
+    with open(fa, "w") as f:
+        subprocess.run([os.path.join(pyoracle.REF_DIR, "juncs_db"), "3", "26", outs["juncs"], outs["insertions"], outs["deletions"], outs["fusions"],
+                        files["fasta"]], check=True, stdout=f, stderr=subprocess.DEVNULL)
+    cnames, cseqs = [], []
+    for line in open(fa):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            cnames.append(line[1:]); cseqs.append("")
+        elif cnames:
+            cseqs[-1] += line
+    ccodes = [synth.codes_from_ascii(s.encode()) for s in cseqs]
+    hdr = os.path.join(td, "segment_juncs.hdr.sam")
+    with open(hdr, "w") as f:
+        f.write("@HD\tVN:1.0\tSO:unsorted\n")
+        for n, s in zip(cnames, cseqs):
+            f.write("@SQ\tSN:%s\tLN:%d\n" % (n, len(s)))
+    offs, lens = synth.segment_layout(wl.cfg.read_len, wl.cfg.segment_length)
+    jin = {"juncs_fa": fa, "juncs_header": hdr, "n_contigs": len(cnames), "n_fus_contigs": sum(1 for n in cnames if "|fus|" in n), "left_n_spliced": 0}
+    for k in range(nseg):
+        sam = os.path.join(td, "left_seg%d.to_spliced.sam" % (k + 1))
+        with open(sam, "w") as f:
+            for ri in np.nonzero(wl.left.unmapped)[0]:
+                seg = wl.left.reads[ri, int(offs[k]):int(offs[k]) + int(lens[k])]
+                for (ci, pos, anti, q, mmask, cwin) in _brute_contig_hits(ccodes, seg):
+                    md, run = [], 0
+                    for x in range(q.shape[0]):
+                        if mmask[x]:
+                            md.append(str(run)); md.append(chr(synth.CODE2CHAR[min(int(cwin[x]), 4)])); run = 0
+                        else:
+                            run += 1
+                    md.append(str(run)); nm = int(mmask.sum())
+                    f.write("%d|%d:%d:%d\t%d\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:UU\n" % (
+                        ri + 1, int(offs[k]), k, nseg, 16 if anti else 0, cnames[ci], pos + 1, q.shape[0], synth.CODE2CHAR[q].tobytes().decode(),
+                        "I" * q.shape[0], -6 * nm, nm, nm, "".join(md)))
+                    jin["left_n_spliced"] += 1
+        bam = os.path.join(td, "left_kept_reads_seg%d.to_spliced.bam" % (k + 1))
+        subprocess.run([os.path.join(pyoracle.REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile", bam + ".index", sam, bam],
+                       check=True, stderr=subprocess.DEVNULL)
+        jin["left_spl%d" % (k + 1)] = bam
+    return wl, files, bams, jin, outs, nseg, opts

@@ -96,3 +96,72 @@ def test_cli_read_id_ranges_do_not_change_the_output():
                     l_qn = data[inoff + 12]
                     assert int(data[inoff + 36: inoff + 36 + l_qn - 1].decode()) == rid
         assert len(want) > 3000 and n_files[1] == 1 and n_files[3] == 3 and n_files[7] >= 4
+
+
+def _compare_bams(our_bam, ref_bam, what):
+    refs_a, a = pyoracle.read_bam(our_bam)
+    refs_b, b = pyoracle.read_bam(ref_bam)
+    assert refs_a == refs_b
+    assert len(a) == len(b), "%s: %d records vs %d in the reference output" % (what, len(a), len(b))
+    for x, y in zip(a, b):
+        assert x == y, "%s: record differs:\n ours %r\n ref  %r" % (what, x, y)
+    return b
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("threads", [1, 3])
+def test_cli_fusion_search_matches_reference_binary(threads):
+    """--fusion-search (a7): chimeric synthetic fragments (ff / fr / rf / rr, intra- and inter-contig).  The join closes the fusion
+    point against segment.fusions (merge_chain's fusion closure, long_spanning_reads.cpp:1596-1819) and writes every fusion alignment
+    as two records with XF tags (bwt_map.cpp:2047-2083); every record -- fields, order, all aux tags -- equals the reference's, and
+    equals the expectations pinned in tests/golden/join_fusion_chimeric."""
+    import json
+    OUR_BIN = helpers.our_bin("long_spanning_reads")
+    gdir = os.path.join(helpers.GOLDEN, "join_fusion_chimeric")
+    cfg = json.load(open(os.path.join(gdir, "config.json")))
+    kw = dict(cfg["synth"]); kw["contig_lens"] = tuple(kw["contig_lens"])
+    opts = pyoracle.tophat_common_opts(cfg["inner_dist_mean"], cfg["inner_dist_std_dev"], cfg["extra"])
+    with tempfile.TemporaryDirectory() as td:
+        wl = synth.generate(synth.SynthConfig(**kw))
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg, opts=opts)
+        jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+        n_xf = 0
+        for side in ("left", "right"):
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=side, tag=".ref", opts=opts, fusions=outs["fusions"])
+            our_bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, bams, jin, outs, td, nseg, side=side, tag=".b200p%d" % threads, opts=opts,
+                                                       fusions=outs["fusions"], threads=threads)
+            recs = _compare_bams(our_bam, ref_bam, side)
+            n_xf += sum(1 for r in recs if "XF" in r[11])
+            want = [l.rstrip("\n") for l in open(os.path.join(gdir, side + ".fusion_records.tsv"))]
+            got = ["%s\t%s\t%d\t%s\t%d\t%d\t%s" % (r[0], r[2], r[3], r[5], r[1], r[11]["NM"], r[11].get("XF", "-")) for r in pyoracle.read_bam(our_bam)[1]]
+            assert got == want, "%s: records differ from the pinned expectations" % side
+        assert n_xf > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("name", helpers.reference_input_cases())
+def test_cli_fusion_test_sets_through_both_stages(name):
+    """BASELINE configs[0] / configs[4]: the reference's own fusion_test read sets (junction / indel / fusion / total, intra- and
+    inter-contig) through BOTH stages with the options tophat.py derives from fusion_test/run_test.sh: our segment_juncs reproduces the
+    four segment.* files, and our long_spanning_reads -- fed the junction index the reference's juncs_db builds from them, fusion
+    contigs included -- reproduces every record of the reference's candidates BAM (two-record XF form for the fusion alignments)."""
+    SJ, LSR = helpers.our_bin("segment_juncs"), helpers.our_bin("long_spanning_reads")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as td:
+        wl, files, bams, jin, outs, nseg, opts = helpers.fusion_test_pipeline(name, td)
+        ours1 = pyoracle.run_segment_juncs(SJ, files, bams, td, nseg, opts=opts, paired=False, tag=".b200")
+        for k in ("juncs", "insertions", "deletions", "fusions"):
+            assert open(ours1[k]).read() == open(outs[k]).read(), "segment.%s differs from the reference's" % k
+        ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg, side="left",
+                                                   tag=".ref", opts=opts, fusions=outs["fusions"])
+        our_bam = pyoracle.run_long_spanning_reads(LSR, files, bams, jin, ours1, td, nseg, side="left", tag=".b200", opts=opts, fusions=ours1["fusions"])
+        recs = _compare_bams(our_bam, ref_bam, name)
+        assert len(recs) > 200 and jin["left_n_spliced"] > 100
+        if "fusion" in name or "total" in name:
+            assert jin["n_fus_contigs"] > 10 and sum(1 for r in recs if "XF" in r[11]) > 500

@@ -229,3 +229,20 @@ def test_emu_join_tile_kernel_equals_queue_kernels():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith("JOIN_DIGEST")][-1])
     assert outs[0] == outs[1] and int(outs[0].split()[-1]) > 3000
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("name", ["reference_test_total_inter", "reference_test_indel_intra2"])
+def test_emu_fusion_test_sets_join_matches_reference(name):
+    """--fusion-search in the join (fusion_join_kernel.cuh, emulated): the reference's own fusion_test sets, junction index with fusion
+    contigs from the reference's juncs_db; records (incl. the two-record XF form) equal the reference binary's."""
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "emu"))
+    import build_emu
+    exe = build_emu.build_cli("long_spanning_reads")
+    with tempfile.TemporaryDirectory() as td:
+        wl, files, bams, jin, outs, nseg, opts = helpers.fusion_test_pipeline(name, td)
+        ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg, side="left",
+                                                   tag=".ref", opts=opts, fusions=outs["fusions"])
+        our_bam = pyoracle.run_long_spanning_reads(exe, files, bams, jin, outs, td, nseg, side="left", tag=".emu", opts=opts, fusions=outs["fusions"])
+        _, a = pyoracle.read_bam(our_bam); _, b = pyoracle.read_bam(ref_bam)
+        assert a == b and sum(1 for r in b if "XF" in r[11]) > 200

@@ -75,8 +75,11 @@ def test_join_requires_begin_and_sorted_sets():
     j = np.zeros(2, dtype=synth.JUNCTION_DTYPE); j["ref_id"] = 1; j["left"] = [50, 10]; j["right"] = [90, 40]
     with pytest.raises(capi.ThbError):
         ctx.join_begin(P, j, np.zeros(0, dtype=synth.INSERTION_DTYPE))          # not sorted
+    ctx.join_begin(capi.default_params(fusion_search=1), j[::-1].copy(), np.zeros(0, dtype=synth.INSERTION_DTYPE))     # --fusion-search is on the GPU path
+    f = np.zeros(2, dtype=synth.FUSION_DTYPE); f["ref_id1"] = 1; f["ref_id2"] = 1; f["left"] = [500, 100]; f["right"] = [900, 700]; f["dir"] = 7
     with pytest.raises(capi.ThbError):
-        ctx.join_begin(capi.default_params(fusion_search=1), j[::-1].copy(), np.zeros(0, dtype=synth.INSERTION_DTYPE))
+        ctx.join_set_fusions(f)                                                                                       # not sorted
+    ctx.join_set_fusions(f[::-1].copy())
     ctx.close()
 
 

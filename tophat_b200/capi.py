@@ -184,6 +184,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_pack_read.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.thb_pack_read.restype = None
     lib.thb_join_pack_hits.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.thb_join_set_fusions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.thb_join_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.thb_join_submit.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_join_submit_device.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_uint64)]
@@ -283,6 +284,12 @@ class Context:
         j, i = self._jkeep
         self._check(self.lib.thb_join_begin(self.h, C.byref(params), j.ctypes.data if j.size else None, j.shape[0],
                                             i.ctypes.data if i.size else None, i.shape[0]), "thb_join_begin")
+
+    def join_set_fusions(self, fusions: np.ndarray) -> None:
+        """--fusion-search: FUSION_DTYPE records sorted unique in Fusion order (fusions.h:40-70); call after join_begin."""
+        self._fkeep = np.ascontiguousarray(fusions)
+        f = self._fkeep
+        self._check(self.lib.thb_join_set_fusions(self.h, f.ctypes.data if f.size else None, f.shape[0]), "thb_join_set_fusions")
 
     def join_submit(self, batch) -> np.ndarray:
         b = batch if isinstance(batch, JoinBatchC) else join_batch_c(batch)

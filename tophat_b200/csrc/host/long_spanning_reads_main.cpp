@@ -35,12 +35,13 @@ static void print_usage()
 static int bam_op(int code) { switch (code) { case 1: return 0; case 3: return 1; case 5: return 2; case 11: return 3; case 13: return 4; case 14: return 5; case 15: return 6; default: return 0; } }
 
 struct Joined {
-  uint32_t ref_id; int32_t left; bool anti, asplice; uint8_t mism, edit, smm; std::vector<uint32_t> ops;   // ops: len << 4 | CigarOpCode
+  uint32_t ref_id, ref_id2; int32_t left; bool anti, asplice, fused, seq_rc; uint8_t mism, edit, smm; std::vector<uint32_t> ops;   // ops: len << 4 | CigarOpCode
 };
 // BowtieHit::operator< (bwt_map.h:180-207) within one read
 static bool joined_less(const Joined& a, const Joined& b)
 {
   if (a.ref_id != b.ref_id) return a.ref_id < b.ref_id;
+  if (a.ref_id2 != b.ref_id2) return a.ref_id2 < b.ref_id2;
   if (a.left != b.left) return a.left < b.left;
   if (a.anti != b.anti) return a.anti < b.anti;
   if (a.mism != b.mism) return a.mism < b.mism;
@@ -56,7 +57,53 @@ static bool joined_less(const Joined& a, const Joined& b)
 }
 // BowtieHit::operator== (167-178)
 static bool joined_equal(const Joined& a, const Joined& b)
-{ return a.ref_id == b.ref_id && a.anti == b.anti && a.left == b.left && a.asplice == b.asplice && a.edit == b.edit && a.ops == b.ops; }
+{ return a.ref_id == b.ref_id && a.ref_id2 == b.ref_id2 && a.anti == b.anti && a.left == b.left && a.asplice == b.asplice && a.edit == b.edit && a.ops == b.ops; }
+
+// CIGAR text of print_bamhit (bwt_map.cpp:1944-2003): lower-case letters for the ops of a part read leftwards, <pos + 1>F for a fusion
+static std::string cigar_text(const std::vector<uint32_t>& ops)
+{
+  std::string t;
+  for (uint32_t op : ops) {
+    const int c = (int)(op & 15); const uint32_t l = op >> 4;
+    switch (c) {
+      case 1: t += std::to_string(l) + "M"; break; case 2: t += std::to_string(l) + "m"; break;
+      case 3: t += std::to_string(l) + "I"; break; case 4: t += std::to_string(l) + "i"; break;
+      case 5: t += std::to_string(l) + "D"; break; case 6: t += std::to_string(l) + "d"; break;
+      case 11: t += std::to_string(l) + "N"; break; case 12: t += std::to_string(l) + "n"; break;
+      case 7: case 8: case 9: case 10: t += std::to_string(l + 1) + "F"; break;
+      default: break;
+    }
+  }
+  return t;
+}
+
+// extract_partial_hits (bwt_map.cpp:2148-2346): the two single-contig records of a fusion alignment.  `seq` / `qual` are the
+// (already oriented) sequence of the whole alignment; BAM CIGARs come out as len << 4 | BAM op.
+struct FusionParts { std::vector<uint32_t> cig1, cig2; std::string seq1, seq2, qual1, qual2; int left1 = -1, left2 = -1; };
+static void reverse_complement(std::string& s);
+static FusionParts split_fusion(const Joined& J, const std::string& seq, const std::string& qual)
+{
+  FusionParts P; int right = J.left, fusion_left = -1, fusion_right = -1, dir = 0; size_t fidx = 0, left_len = 0;
+  for (size_t c = 0; c < J.ops.size(); ++c) {
+    const int code = (int)(J.ops[c] & 15); const int l = (int)(J.ops[c] >> 4);
+    if (code == 1 || code == 11 || code == 5) right += l; else if (code == 2 || code == 12 || code == 6) right -= l;
+    else if (code >= 7 && code <= 10) { dir = code; fidx = c; fusion_left = (code == 7 || code == 8) ? right - 1 : right + 1; fusion_right = right = l; }
+    if (!dir && (code == 1 || code == 2 || code == 3 || code == 4)) left_len += (size_t)l;
+  }
+  auto bam_of = [](int code) -> uint32_t { switch (code) { case 1: case 2: return 0; case 3: case 4: return 1; case 5: case 6: return 2; case 11: case 12: return 3; default: return 0; } };
+  if (dir == 7 || dir == 8) for (size_t c = 0; c < fidx; ++c) P.cig1.push_back(((J.ops[c] >> 4) << 4) | bam_of((int)(J.ops[c] & 15)));
+  else if (dir == 9 || dir == 10) for (size_t c = fidx; c-- > 0;) P.cig1.push_back(((J.ops[c] >> 4) << 4) | bam_of((int)(J.ops[c] & 15)));
+  if (dir == 7 || dir == 9) for (size_t c = fidx + 1; c < J.ops.size(); ++c) P.cig2.push_back(((J.ops[c] >> 4) << 4) | bam_of((int)(J.ops[c] & 15)));
+  else if (dir == 8 || dir == 10) for (size_t c = J.ops.size() - 1; c > fidx; --c) P.cig2.push_back(((J.ops[c] >> 4) << 4) | bam_of((int)(J.ops[c] & 15)));
+  if (left_len > seq.size()) left_len = seq.size();
+  P.seq1 = seq.substr(0, left_len); P.qual1 = qual.substr(0, std::min(left_len, qual.size()));
+  if (dir == 9 || dir == 10) { reverse_complement(P.seq1); std::reverse(P.qual1.begin(), P.qual1.end()); }
+  P.seq2 = seq.substr(left_len); P.qual2 = left_len < qual.size() ? qual.substr(left_len) : std::string();
+  if (dir == 8 || dir == 10) { reverse_complement(P.seq2); std::reverse(P.qual2.begin(), P.qual2.end()); }
+  P.left1 = (dir == 7 || dir == 8) ? J.left : fusion_left;
+  P.left2 = (dir == 7 || dir == 9) ? fusion_right : right + 1;
+  return P;
+}
 
 struct GenomeView {
   const Genome* g;
@@ -88,7 +135,6 @@ int main(int argc, char** argv)
   std::vector<std::string> spl_files; if (a.size() >= 9) spl_files = split_list(a[8]);
   if (seg_files.empty()) { fprintf(stderr, "No hits to process, exiting\n"); return 0; }          // 2883-2887
   if (o.color) die("Error: colorspace reads are outside the GPU path");
-  if (o.p.fusion_search) die("Error: --fusion-search is not implemented on the GPU join path yet");
   if (seg_files.size() > THB_MAX_SEGS) die("Error: more than %s segments per read are not supported by the GPU path", std::to_string(THB_MAX_SEGS));
 
   thb_ctx* ctx = nullptr;
@@ -147,6 +193,29 @@ int main(int argc, char** argv)
     fclose(fp);
   }
   fprintf(stderr, "done\n");
+  // fusions (2996-3040)
+  struct FL { bool operator()(const thb_fusion& x, const thb_fusion& y) const {
+    if (x.ref_id1 != y.ref_id1) return x.ref_id1 < y.ref_id1; if (x.ref_id2 != y.ref_id2) return x.ref_id2 < y.ref_id2;
+    if (x.left != y.left) return x.left < y.left; if (x.right != y.right) return x.right < y.right; return x.dir < y.dir; } };
+  std::set<thb_fusion, FL> fset;
+  if (o.p.fusion_search) {
+    fprintf(stderr, "Loading fusions...");
+    for (const std::string& f : split_list(a[5])) {
+      FILE* fp = fopen(f.c_str(), "r"); if (!fp) continue;
+      char buf[2048];
+      while (fgets(buf, sizeof buf, fp)) { char* nl = strrchr(buf, '\n'); if (nl) *nl = 0;
+        char* t1 = strchr(buf, '\t'); if (!t1) die("Error: malformed insertion coordinate record"); *t1++ = 0;
+        char* t2 = strchr(t1, '\t'); if (!t2) die("Error: malformed insertion coordinate record"); *t2++ = 0;
+        char* t3 = strchr(t2, '\t'); if (!t3) die("Error: malformed insertion coordinate record"); *t3++ = 0;
+        char* t4 = strchr(t3, '\t'); if (!t4) die("Error: malformed insertion coordinate record"); *t4++ = 0;
+        char* t5 = strchr(t4, '\t'); if (t5) *t5 = 0;
+        thb_fusion fu; memset(&fu, 0, sizeof fu); fu.ref_id1 = rt.get_id(buf); fu.left = (uint32_t)atoi(t1); fu.ref_id2 = rt.get_id(t2); fu.right = (uint32_t)atoi(t3);
+        fu.dir = strcmp(t4, "fr") == 0 ? 8u : strcmp(t4, "rf") == 0 ? 9u : strcmp(t4, "rr") == 0 ? 10u : 7u;
+        fset.insert(fu); }
+      fclose(fp);
+    }
+    fprintf(stderr, "done\n");
+  }
   // contigs named only by the junction files must exist in the genome image before it is uploaded
   if (g.contig_len.size() < rt.size()) {
     Genome g2 = g; const size_t old = g.contig_len.size(); uint64_t gpos = (g.n_blocks ? (g.n_blocks - 1) * 64 : 0);
@@ -158,6 +227,8 @@ int main(int argc, char** argv)
   std::mutex rtm;
   { thb_ref_image img = g.image(); if (thb_ref_upload(ctx, &img) != THB_OK) die("Error: thb_ref_upload: %s", thb_last_error(ctx)); }
   if (thb_join_begin(ctx, &o.p, jv.data(), jv.size(), iv.data(), iv.size()) != THB_OK) die("Error: thb_join_begin: %s", thb_last_error(ctx));
+  if (o.p.fusion_search) { std::vector<thb_fusion> fv(fset.begin(), fset.end());
+    if (thb_join_set_fusions(ctx, fv.data(), fv.size()) != THB_OK) die("Error: thb_join_set_fusions: %s", thb_last_error(ctx)); }
   auto t1 = std::chrono::steady_clock::now();
 
   // Read-id ranges, one output BAM per range -- the reference's own -p N layout (<out minus .bam><i>.bam, 3056-3064, which
@@ -212,6 +283,8 @@ int main(int argc, char** argv)
     std::vector<std::vector<Joined>> per(bundles.size());
     for (uint64_t i = 0; i < no; ++i) {
       const thb_joined& j = out[i]; Joined J; J.ref_id = j.ref_id; J.left = j.left; J.anti = (j.flags & THB_HIT_ANTISENSE) != 0;
+      J.fused = (j.flags & THB_JOINED_FUSION) != 0; J.ref_id2 = o.p.fusion_search ? j.ops[THB_JOINED_MAX_OPS - 1] : j.ref_id;
+      J.seq_rc = o.p.fusion_search ? (j.flags & THB_JOINED_SEQ_RC) != 0 : J.anti;
       J.asplice = (j.flags & THB_JHIT_ANTISENSE_SPLICE) != 0; J.mism = j.mismatches; J.edit = j.edit_dist; J.smm = j.splice_mms;
       J.ops.assign(j.ops, j.ops + j.n_ops); per[j.bundle].push_back(std::move(J));
     }
@@ -232,20 +305,25 @@ int main(int argc, char** argv)
       const FullRead& rd = pend[b].read;
       for (const Joined& J : v) {
         int gap = 0, rlen = 0; bool has_splice = false;
-        for (uint32_t op : J.ops) { const int c = (int)(op & 15), l = (int)(op >> 4); if (c == 3 || c == 5) gap += l; if (c == 1 || c == 3 || c == 13) rlen += l; if (c == 11) has_splice = true; }
+        for (uint32_t op : J.ops) { const int c = (int)(op & 15), l = (int)(op >> 4);
+          if (c == 3 || c == 4 || c == 5 || c == 6) gap += l; if (c == 1 || c == 2 || c == 3 || c == 4 || c == 13) rlen += l; if (c == 11 || c == 12) has_splice = true; }
         if ((int)J.mism > o.p.read_mismatches || gap > o.p.read_gap_length || (int)J.edit > o.p.read_edit_dist) continue;   // 2810-2813
-        // the hit's own sequence / qualities (merge_chain 1959-1979): forward-genome orientation
+        // the hit's own sequence / qualities (merge_chain 1959-1979, BowtieHit::reverse): the read or its reverse complement
         std::string hseq = rd.seq, hqual = rd.qual;
-        if (J.anti) { reverse_complement(hseq); std::reverse(hqual.begin(), hqual.end()); }
-        // bowtie_sam_extra (bwt_map.cpp:2467-2648)
+        if (J.seq_rc) { reverse_complement(hseq); std::reverse(hqual.begin(), hqual.end()); }
+        // bowtie_sam_extra (bwt_map.cpp:2467-2648); lower-case ops walk leftwards over the reverse-complemented reference, a
+        // fusion op continues on the second contig
         aux.clear(); MD.clear();
-        if (J.ref_id >= 1 && J.ref_id <= g.contig_len.size() && g.contig_len[J.ref_id - 1] > 0) {
-          long pos_ref = J.left; size_t pos_seq = 0; int pos_mm = 0, mm = 0, gap_opens = 0, gap_conts = 0, AS = 0;
+        auto has_seq = [&](uint32_t id) { return id >= 1 && id <= g.contig_len.size() && g.contig_len[id - 1] > 0; };
+        auto comp = [](char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; };
+        if (has_seq(J.ref_id) && has_seq(J.ref_id2)) {
+          long pos_ref = J.left; size_t pos_seq = 0; int pos_mm = 0, mm = 0, gap_opens = 0, gap_conts = 0, AS = 0; uint32_t cur_ref = J.ref_id; bool saw_fusion = false, ok_extra = true;
           for (uint32_t op : J.ops) {
             const int c = (int)(op & 15), l = (int)(op >> 4);
-            if (c == 1) {
+            if (c == 1 || c == 2) {
               for (int k = 0; k < l; ++k, ++pos_seq) {
-                const char rn = gv.base(J.ref_id, pos_ref + k); const char sc = pos_seq < hseq.size() ? hseq[pos_seq] : 'N';
+                const char rn = c == 1 ? gv.base(cur_ref, pos_ref + k) : comp(gv.base(cur_ref, pos_ref - k));
+                const char sc = pos_seq < hseq.size() ? hseq[pos_seq] : 'N';
                 if (sc != rn) {
                   ++mm;
                   if (pos_seq < hqual.size()) {
@@ -255,28 +333,49 @@ int main(int argc, char** argv)
                   MD += std::to_string(pos_mm); MD.push_back(rn); pos_mm = 0;
                 } else { if (rn == 'N') AS -= o.p.bowtie2_penalty_for_N; ++pos_mm; }
               }
-              pos_ref += l;
-            } else if (c == 3) { pos_seq += (size_t)l; AS -= o.p.bowtie2_read_gap_open; AS -= o.p.bowtie2_read_gap_cont * l; gap_opens += 1; gap_conts += l; }
-            else if (c == 5) {
+              pos_ref += c == 1 ? l : -l;
+            } else if (c == 3 || c == 4) { pos_seq += (size_t)l; AS -= o.p.bowtie2_read_gap_open; AS -= o.p.bowtie2_read_gap_cont * l; gap_opens += 1; gap_conts += l; }
+            else if (c == 5 || c == 6) {
               AS -= o.p.bowtie2_ref_gap_open; AS -= o.p.bowtie2_ref_gap_cont * l; gap_opens += 1; gap_conts += l;
-              MD += std::to_string(pos_mm); MD.push_back('^'); for (int k = 0; k < l; ++k) MD.push_back(gv.base(J.ref_id, pos_ref + k));
-              pos_ref += l; pos_mm = 0;
+              MD += std::to_string(pos_mm); MD.push_back('^');
+              for (int k = 0; k < l; ++k) MD.push_back(c == 5 ? gv.base(cur_ref, pos_ref + k) : comp(gv.base(cur_ref, pos_ref - k)));
+              pos_ref += c == 5 ? l : -l; pos_mm = 0;
             } else if (c == 11) pos_ref += l;
+            else if (c == 12) pos_ref -= l;
+            else if (c >= 7 && c <= 10) { if (saw_fusion) { ok_extra = false; break; } cur_ref = J.ref_id2; pos_ref = l; saw_fusion = true; }
           }
-          MD += std::to_string(pos_mm);
-          BamWriter::aux_int(aux, "AS", AS); BamWriter::aux_int(aux, "XM", mm); BamWriter::aux_int(aux, "XO", gap_opens);
-          BamWriter::aux_int(aux, "XG", gap_conts); BamWriter::aux_str(aux, "MD", MD);
+          if (ok_extra) {
+            MD += std::to_string(pos_mm);
+            BamWriter::aux_int(aux, "AS", AS); BamWriter::aux_int(aux, "XM", mm); BamWriter::aux_int(aux, "XO", gap_opens);
+            BamWriter::aux_int(aux, "XG", gap_conts); BamWriter::aux_str(aux, "MD", MD);
+          }
         }
         // print_bamhit (bwt_map.cpp:1888-2093): read sequence cut to the hit's read length, rc for antisense hits
         std::string seq = rd.seq, quals = rd.qual; seq.resize((size_t)rlen, '\0'); quals.resize((size_t)rlen, '\0');
         if (J.anti) { reverse_complement(seq); std::reverse(quals.begin(), quals.end()); }
         BamWriter::aux_int(aux, "NM", (int)J.mism + gap);
         if (has_splice) BamWriter::aux_char(aux, "XS", J.asplice ? '-' : '+');
-        bcig.clear(); for (uint32_t op : J.ops) bcig.push_back(((op >> 4) << 4) | (uint32_t)bam_op((int)(op & 15)));
         const int tid = J.ref_id < ref2tid.size() ? ref2tid[J.ref_id] : -1;
-        const size_t before = part.bytes.size();
-        BamWriter::encode(part.bytes, rd.name, J.anti ? 0x10 : 0, tid, J.left, 255, bcig, seq, quals, aux);
-        part.sizes.push_back((uint32_t)(part.bytes.size() - before)); part.ids.push_back(pend[b].id);
+        if (!J.fused) {
+          bcig.clear(); for (uint32_t op : J.ops) bcig.push_back(((op >> 4) << 4) | (uint32_t)bam_op((int)(op & 15)));
+          const size_t before = part.bytes.size();
+          BamWriter::encode(part.bytes, rd.name, J.anti ? 0x10 : 0, tid, J.left, 255, bcig, seq, quals, aux);
+          part.sizes.push_back((uint32_t)(part.bytes.size() - before)); part.ids.push_back(pend[b].id);
+          continue;
+        }
+        // a fusion alignment is written as two records, one per contig, each carrying the whole alignment in XF (2047-2083)
+        const FusionParts FP = split_fusion(J, seq, quals);
+        const int tid2 = J.ref_id2 < ref2tid.size() ? ref2tid[J.ref_id2] : -1;
+        std::string n1, n2; { std::lock_guard<std::mutex> l(rtm); n1 = rt.name(J.ref_id); n2 = rt.name(J.ref_id2); }
+        const std::string xf_tail = " " + n1 + "-" + n2 + " " + std::to_string(J.left + 1) + " " + cigar_text(J.ops) + " " + seq + " " + quals;
+        for (int partno = 1; partno <= 2; ++partno) {
+          std::vector<uint8_t> aux2 = aux; BamWriter::aux_str(aux2, "XF", std::to_string(partno) + xf_tail);
+          const size_t before = part.bytes.size();
+          if (partno == 1) BamWriter::encode(part.bytes, rd.name, J.anti ? 0x10 : 0, tid, FP.left1, 255, FP.cig1, FP.seq1, FP.qual1, aux2);
+          else BamWriter::encode(part.bytes, rd.name, J.anti ? 0x10 : 0, tid2, FP.left2, 255, FP.cig2, FP.seq2, FP.qual2, aux2);
+          part.sizes.push_back((uint32_t)(part.bytes.size() - before)); part.ids.push_back(pend[b].id);
+        }
+        continue;
       }
     }
     };

@@ -95,7 +95,7 @@ bool splice_cigar(std::vector<Op>& spl, const std::vector<Op>& cigar, const std:
 }
 
 // one juncs_db contig: where its event lies on the genome
-struct SplTarget { bool ok = false, ins = false; uint32_t ref_id = 0; int left_edge = 0, splice_left = 0, splice_right = 0; std::string inserted;
+struct SplTarget { bool ok = false, ins = false; uint32_t ref_id = 0, ref_id2 = 0; int left_edge = 0, splice_left = 0, splice_right = 0; std::string inserted;
                    int opcode = C_REF_SKIP; bool rev = false; };
 
 void split(const std::string& s, char sep, std::vector<std::string>& out, bool strict)
@@ -144,11 +144,20 @@ void JoinHitStream::produce()
         SplTarget T; T.left_edge = atoi(toks[extra + 1].c_str()); T.splice_left = atoi(st[0].c_str());
         if (jtype == "ins") { T.ins = true; T.inserted = st[1]; T.rev = jstrand == "rev"; }
         else {
-          if (jtype == "fus") continue;                             // fusion contigs only exist with --fusion-search (unsupported)
           if (!(jstrand == "rev" || jstrand == "fwd" || jstrand == "ff" || jstrand == "fr" || jstrand == "rf" || jstrand == "rr")) continue;
-          T.opcode = jtype == "del" ? C_DEL : C_REF_SKIP; T.splice_right = atoi(st[1].c_str()); T.rev = jstrand == "rev";
+          T.splice_right = atoi(st[1].c_str()); T.rev = jstrand == "rev";
+          if (jtype == "fus") {
+            // a fusion contig "ref1-ref2|...|L-R|...|fus|ff": the part behind the fusion point lies on ref2 (1690-1704, 1729-1742)
+            T.opcode = jstrand == "ff" ? C_FUSION_FF : jstrand == "fr" ? C_FUSION_FR : jstrand == "rf" ? C_FUSION_RF : C_FUSION_RR;
+            std::vector<std::string> two; split(contig, '-', two, false);
+            if (two.size() != 2) continue;
+            { std::lock_guard<std::mutex> l(rt_mutex_); T.ref_id = rt_.get_id(two[0]); T.ref_id2 = rt_.get_id(two[1]); }
+            T.ok = true; (*tab)[i] = T;
+            continue;
+          }
+          T.opcode = jtype == "del" ? C_DEL : C_REF_SKIP;
         }
-        { std::lock_guard<std::mutex> l(rt_mutex_); T.ref_id = rt_.get_id(contig); }
+        { std::lock_guard<std::mutex> l(rt_mutex_); T.ref_id = rt_.get_id(contig); T.ref_id2 = T.ref_id; }
         T.ok = true; (*tab)[i] = T;
       }
       slot = tab;
@@ -221,7 +230,7 @@ void JoinHitStream::produce()
           if (*p && !isdigit((unsigned char)*p) && !isalpha((unsigned char)*p) && *p != '^') ++p;
         }
       }
-      scig.clear(); int spl_mm = 0; int left;
+      scig.clear(); int spl_mm = 0; int left; bool anti_out = anti;
       if (T.ins) {
         left = T.left_edge + r.pos;
         if (left > T.splice_left) continue;
@@ -229,17 +238,24 @@ void JoinHitStream::produce()
         if (spl_mm < 0) continue;
         num_mm -= spl_mm; spl_mm = 0;                             // create_hit(..., splice_mms = 0) for insertions (1652-1664)
       } else {
-        left = T.left_edge + r.pos;
-        const int left_splice_pos = T.splice_left + 1;
-        const int gap_len = T.splice_right - T.splice_left - 1;
-        if (left >= left_splice_pos) continue;
+        // "del", "intron" or "fusion" (1668-1755)
+        const bool fusion = is_fusion_code(T.opcode), leftwards = T.opcode == C_FUSION_RF || T.opcode == C_FUSION_RR;
+        left = leftwards ? T.left_edge - r.pos : T.left_edge + r.pos;
+        int left_splice_pos = T.splice_left; int gap_len;
+        if (fusion) gap_len = T.splice_right; else gap_len = T.splice_right - T.splice_left - 1;
+        if (leftwards) { left_splice_pos -= 1; if (left <= left_splice_pos) continue; }
+        else { left_splice_pos += 1; if (left >= left_splice_pos) continue; }
         if (!splice_cigar(scig, cig, mism, left, left_splice_pos, gap_len, T.opcode, spl_mm, min_anchor_len_)) continue;
         if (spl_mm < 0) continue;
+        if (leftwards) anti_out = !anti;                              // 1740-1741
       }
-      if (scig.size() > THB_JHIT_MAX_OPS) { ++dropped_; continue; }
+      const bool fused = is_fusion_code(T.opcode) && !T.ins;
+      if (scig.size() > (size_t)(fused ? THB_JHIT_MAX_OPS - 1 : THB_JHIT_MAX_OPS)) { ++dropped_; continue; }
       hr.h.ref_id = T.ref_id; hr.h.left = left;
       hr.h.n_ops = (uint8_t)scig.size(); for (size_t k = 0; k < scig.size(); ++k) hr.h.ops[k] = pack_op(scig[k]);
-      hr.h.flags = (uint8_t)((anti ? THB_HIT_ANTISENSE : 0) | (end ? THB_HIT_END : 0) | (T.rev ? THB_JHIT_ANTISENSE_SPLICE : 0));
+      if (fused) hr.h.ops[THB_JHIT_MAX_OPS - 1] = T.ref_id2;          // second contig (include/tophat_b200.h)
+      hr.h.flags = (uint8_t)((anti_out ? THB_HIT_ANTISENSE : 0) | (end ? THB_HIT_END : 0) | (T.rev ? THB_JHIT_ANTISENSE_SPLICE : 0) |
+                             (anti_out != anti ? THB_JHIT_SEQ_FLIPPED : 0));
       hr.h.mismatches = (uint8_t)num_mm; hr.h.splice_mms = (uint8_t)spl_mm;
     }
     chunk.push_back(hr);

@@ -19,6 +19,7 @@
 #include "scan_tile_kernel.cuh"
 #include "join_kernel.cuh"
 #include "join_tile_kernel.cuh"
+#include "fusion_join_kernel.cuh"
 #include "fusion_kernel.cuh"
 
 using namespace thb;
@@ -124,6 +125,7 @@ struct thb_ctx {
   DevBuf j_idx; uint64_t j_nbuckets = 0; bool j_use_idx = false; int j_shift = 6;
   DevBuf j_iidx; uint64_t j_nibuckets = 0; bool j_use_iidx = false; int j_ishift = 6;
   DevBuf j_juncs, j_ins, j_bundles, j_segc, j_reads, j_hits, j_out, j_chain; uint64_t j_cap_chain = 0, j_cap_out = 0, j_n_juncs = 0, j_n_ins = 0;
+  DevBuf j_fus; uint64_t j_n_fus = 0;              // --fusion-search: the fusion set of the join (FusionKey records)
   JoinParams jp{}; bool join_begun = false; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   JStage jstage[2];
   thb_joined* h_joined = nullptr; uint64_t h_joined_cap = 0;      // page-locked result buffer, grow-only
@@ -488,7 +490,7 @@ void thb_destroy(thb_ctx* ctx)
   for (DevBuf* b : { &ctx->d_planes, &ctx->d_nmask, &ctx->d_cstart, &ctx->d_clen, &ctx->d_juncs, &ctx->d_dels, &ctx->d_ins,
                      &ctx->d_scalars, &ctx->d_keys, &ctx->d_keys_sorted, &ctx->d_cub_tmp, &ctx->d_decoded, &ctx->d_count,
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
-                     &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx, &ctx->j_iidx }) b->release();
+                     &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx, &ctx->j_iidx, &ctx->j_fus }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
@@ -543,7 +545,10 @@ int thb_join_pack_hits(const thb_jhit_full* hits, uint32_t n, thb_jhit* heads, t
     const thb_jhit_full& f = hits[i]; thb_jhit& h = heads[i];
     uint32_t nops = f.n_ops; if (nops > THB_JHIT_MAX_OPS) return THB_EINVAL;
     int64_t right = f.left;
-    for (uint32_t k = 0; k < nops; ++k) { const uint32_t c = f.ops[k] & 15u; if (c == 1 || c == 5 || c == 11) right += (int64_t)(f.ops[k] >> 4); }
+    for (uint32_t k = 0; k < nops; ++k) {                         // BowtieHit::right(), bwt_map.h:213-243
+      const uint32_t c = f.ops[k] & 15u; const int64_t l = (int64_t)(f.ops[k] >> 4);
+      if (c == 1 || c == 5 || c == 11) right += l; else if (c == 2 || c == 6 || c == 12) right -= l; else if (c >= 7 && c <= 10) right = l;
+    }
     const bool one_match = nops == 1 && (f.ops[0] & 15u) == 1u;
     h.ref_id = f.ref_id; h.left = f.left; h.right = (int32_t)right;
     h.flags_nops = (uint8_t)((f.flags & 0x7u) | (one_match ? THB_JHIT_ONE_MATCH : 0) | (nops << 4));
@@ -552,7 +557,10 @@ int thb_join_pack_hits(const thb_jhit_full* hits, uint32_t n, thb_jhit* heads, t
       if (n_ext > 255 || !ops_ext) return THB_EUNSUPPORTED;
       h.ops_index = (uint8_t)n_ext;
       thb_jops& o = ops_ext[n_ext++]; memset(&o, 0, sizeof o);
-      for (uint32_t k = 0; k < nops; ++k) o.ops[k] = f.ops[k];
+      bool fused = false;
+      for (uint32_t k = 0; k < nops; ++k) { o.ops[k] = f.ops[k]; const uint32_t c = f.ops[k] & 15u; fused = fused || (c >= 7u && c <= 10u); }
+      if (fused) { if (nops > 8) return THB_EINVAL; o.ops[11] = f.ops[8]; }          // second contig of a fusion hit
+      if (f.flags & THB_JHIT_SEQ_FLIPPED) o.ops[10] = 1u;
     }
   }
   return (int)n_ext;
@@ -874,7 +882,6 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   if (!ctx || !p) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
-  if (p->fusion_search) return fail(ctx, THB_EUNSUPPORTED, "--fusion-search is not implemented on the GPU join path yet");
   if (p->segment_length < 4 || p->segment_length > 255) return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside [4,255]", p->segment_length);
   if (p->max_insertion_length > 19) return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 not supported");
   if ((n_juncs && !juncs) || (n_ins && !ins) || n_juncs >= (1ull << 31) || n_ins >= (1ull << 31)) return fail(ctx, THB_EINVAL, "bad junction / insertion set");
@@ -935,7 +942,7 @@ int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs,
   j.max_ins = p->max_insertion_length; j.max_del = p->max_deletion_length; j.min_report_intron = p->min_report_intron_length;
   j.max_report_intron = p->max_report_intron_length; j.fusion_min_dist = p->fusion_min_dist; j.max_seg_multihits = p->max_seg_multihits;
   j.bowtie2 = p->bowtie2; j.seglen = p->segment_length;
-  ctx->params = *p; ctx->join_begun = true;
+  ctx->params = *p; ctx->join_begun = true; ctx->j_n_fus = 0;
   memset(&ctx->jtiming, 0, sizeof ctx->jtiming);
   ctx->jtiming.begin_ms = begin_ms;
   return THB_OK;
@@ -975,7 +982,14 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     q.abut_tasks = q.tasks + 2 * ctx->j_cap_chain * stride; q.abut_count = ctx->d_qcounts + 3;
     CU(cudaMemsetAsync(ctx->d_counters + 18, 0, 2 * sizeof(unsigned long long), ctx->compute));
     CU(cudaEventRecord(ctx->kev[0], ctx->compute));
-    if (legacy) {
+    if (ctx->params.fusion_search) {
+      // --fusion-search: every read takes the fusion-aware walk + merge (fusion_join_kernel.cuh); no queues
+      FJoinSets FS; FS.base = S; FS.fus = (const FusionKey*)ctx->j_fus.p; FS.n_fus = (uint32_t)ctx->j_n_fus;
+      FJoinOut fo; fo.rec = o.rec; fo.cap = o.cap; fo.count = o.count; fo.overflow = o.overflow; fo.counters = o.counters;
+      fusion_join_kernel<<<grid_for(bv.n_bundles, 64), 64, 0, ctx->compute>>>(ctx->ref, ctx->jp, FS, bv, fo);
+      CU(cudaEventRecord(ctx->kev[1], ctx->compute));
+      CU(cudaEventRecord(ctx->kev[3], ctx->compute)); CU(cudaEventRecord(ctx->kev[4], ctx->compute));
+    } else if (legacy) {
       chain_enum_kernel<<<grid_for(bv.n_bundles, 256), 256, 0, ctx->compute>>>(ctx->jp, bv, q, ctx->d_counters + 4);
       CU(cudaEventRecord(ctx->kev[1], ctx->compute));
       chain_merge_simple_kernel<<<ctx->sms * 8, 256, 0, ctx->compute>>>(ctx->ref, ctx->jp, bv, q, o);
@@ -993,7 +1007,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     }
     // launch bounds chosen by measurement on B200 (profiles/README.md): 80 registers for the closure kernel -- it is
     // latency-bound, so residency is traded against spills
-    chain_merge_kernel<6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
+    if (!ctx->params.fusion_search) chain_merge_kernel<6><<<ctx->sms * 16, 128, 0, ctx->compute>>>(ctx->ref, ctx->jp, S, bv, q, o);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[2], ctx->compute));
     ctx->jtiming.launches += legacy ? 4 : 2;
@@ -1004,6 +1018,7 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
     CU(cudaMemcpyAsync(cnt, ctx->d_counters + 4, sizeof cnt, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     if (ovf & 2u) return fail(ctx, THB_EUNSUPPORTED, "a merged alignment needs more than %d CIGAR operations (outside the GPU path)", JMAXOPS);
+    if (ovf & 4u) return fail(ctx, THB_EUNSUPPORTED, "a fusion alignment whose sequence is neither the read nor its reverse complement (outside the GPU path)");
     n = qn[0]; qn_simple = legacy ? qn[2] : tc[0]; qn_abut = legacy ? qn[3] : tc[1];
     if (!ovf && n <= cap_out && qn[1] <= ctx->j_cap_chain && qn[2] <= ctx->j_cap_chain && qn[3] <= ctx->j_cap_chain) {
       float a = 0.f, b2 = 0.f; CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1])); CU(cudaEventElapsedTime(&b2, ctx->kev[1], ctx->kev[2]));
@@ -1025,6 +1040,26 @@ static int join_run(thb_ctx* ctx, const JoinBatchView& bv, uint64_t n_hits, uint
   t.algorithmic_bytes += 56ull * bv.n_bundles + 16ull * n_hits + 32ull * n_ext + 128ull * cnt[1] + 96ull * cnt[0] + 128ull * n;
   ctx->j_last_n = n;
   *n_res = n;
+  return THB_OK;
+}
+
+int thb_join_set_fusions(thb_ctx* ctx, const thb_fusion* fus, uint64_t n)
+{
+  if (!ctx || (n && !fus)) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->join_begun) return fail(ctx, THB_ESTATE, "thb_join_begin not called");
+  if (n >= (1ull << 31)) return fail(ctx, THB_EINVAL, "bad fusion set");
+  std::vector<FusionKey> keys((size_t)n);
+  for (uint64_t i = 0; i < n; ++i) {
+    keys[i] = FusionKey{fus[i].ref_id1, fus[i].ref_id2, fus[i].left, fus[i].right, fus[i].dir};
+    if (i) { const FusionKey& a = keys[i - 1]; const FusionKey& b = keys[i];
+      const bool lt = a.r1 != b.r1 ? a.r1 < b.r1 : a.r2 != b.r2 ? a.r2 < b.r2 : a.left != b.left ? a.left < b.left : a.right != b.right ? a.right < b.right : a.dir < b.dir;
+      if (!lt) return fail(ctx, THB_EINVAL, "fusion set not sorted / unique near %llu", (unsigned long long)i); }
+  }
+  CU(ctx->j_fus.reserve((n + 1) * sizeof(FusionKey)));
+  if (n) CU(cudaMemcpyAsync(ctx->j_fus.p, keys.data(), n * sizeof(FusionKey), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  ctx->j_n_fus = n;
   return THB_OK;
 }
 
