@@ -31,7 +31,7 @@ def main():
          dict(fusion_search=1, fusion_min_dist=30000)),
         ("splice + indel", dict(contig_lens=(900_000, 300_000), n_pairs=20_000, seed=612, indel_prob=0.4), {}),
     ]:
-        wl = synth.generate(synth.SynthConfig(**kw))
+        wl = synth.generate(synth.SynthConfig(keep_candidates=True, **kw))
         o = dict(inner_dist_mean=50, inner_dist_std_dev=20); o.update(over)
         P = capi.default_params(**o)
         batches = helpers.pack_both(wl, P)
@@ -54,6 +54,33 @@ def main():
         except AssertionError as e:
             ok = False
             print("[rank %d] MISMATCH %s" % (rank, e), flush=True)
+        # stage 2 on the same ranks (BASELINE configs[4]: closures + fusions path on 2 GPUs): every rank joins its shard of the reads
+        # against the full sets; the shards' records together must be the records one context produces for all reads
+        juncs, ins = capi.join_sets_from_results(got)
+        ctx.join_begin(P, juncs, ins)
+        if o.get("fusion_search"):
+            ctx.join_set_fusions(got.fusions)
+        mine, whole = [], []
+        for side in (wl.left, wl.right):
+            jb = synth.pack_join_side(wl, side, got.junctions)
+            lo, _ = shard.shard_range(jb.n_bundles, rank, world)
+            for r in ctx.join_submit(shard.shard_join_batch(jb, rank, world)):
+                mine.append((int(jb.bundles["read_id"][lo + int(r["bundle"])]), int(r["ref_id"]), int(r["left"]), int(r["flags"]), int(r["mismatches"]), int(r["edit_dist"]),
+                             tuple(int(x) for x in r["ops"][:r["n_ops"]]), int(r["ops"][26]) if (r["flags"] & 0x10) else 0))
+            if rank == 0:
+                for r in ctx.join_submit(jb):
+                    whole.append((int(jb.bundles["read_id"][int(r["bundle"])]), int(r["ref_id"]), int(r["left"]), int(r["flags"]), int(r["mismatches"]), int(r["edit_dist"]),
+                                  tuple(int(x) for x in r["ops"][:r["n_ops"]]), int(r["ops"][26]) if (r["flags"] & 0x10) else 0))
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            union = sorted(x for p_ in parts for x in p_)
+            n_fused = sum(1 for x in union if x[3] & 0x10)
+            if union == sorted(whole) and (not o.get("fusion_search") or n_fused > 20):
+                print("[rank 0] %s: join on %d shards = single context: %d alignments, %d across a fusion" % (name, world, len(union), n_fused), flush=True)
+            else:
+                ok = False
+                print("[rank 0] MISMATCH %s: sharded join %d records vs %d (%d fused)" % (name, len(union), len(whole), n_fused), flush=True)
         ctx.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

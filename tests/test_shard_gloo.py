@@ -71,3 +71,22 @@ def test_insertion_first_wins_across_shards():
     b = a.copy(); b["seq"] = b"CC"
     rec, od = shard.merge_insertion_sets([a, b], [np.array([9000 << 12], dtype=np.uint64), np.array([5 << 12], dtype=np.uint64)])
     assert rec.size == 1 and rec["seq"][0] == b"CC"
+
+
+def test_join_batch_shards_cover_the_batch():
+    """shard_join_batch: contiguous read ranges with re-based hit / CIGAR offsets; together they are the whole batch."""
+    import numpy as np
+    from tophat_b200 import shard, synth
+    wl = synth.generate(synth.SynthConfig(contig_lens=(200_000,), n_pairs=1500, seed=77, indel_prob=0.2, keep_candidates=True))
+    j = np.zeros(0, dtype=synth.JUNCTION_DTYPE)
+    jb = synth.pack_join_side(wl, wl.left, j)
+    for world in (1, 2, 3, 8):
+        parts = [shard.shard_join_batch(jb, r, world) for r in range(world)]
+        assert sum(p.n_bundles for p in parts) == jb.n_bundles
+        assert (np.concatenate([p.hits for p in parts]) == jb.hits).all() and (np.concatenate([p.ops_ext for p in parts]) == jb.ops_ext).all()
+        assert (np.concatenate([p.reads for p in parts]) == jb.reads).all() and (np.concatenate([p.seg_count for p in parts]) == jb.seg_count).all()
+        for p in parts:
+            if p.n_bundles:
+                assert int(p.bundles["hit_begin"][0]) == 0 and int(p.bundles["ops_begin"][0]) == 0
+                cnt = p.seg_count.reshape(p.n_bundles, -1).sum(axis=1)
+                assert (p.bundles["hit_begin"][1:] == np.cumsum(cnt)[:-1]).all()

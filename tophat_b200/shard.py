@@ -40,6 +40,22 @@ def shard_batch(b: synth.PackedBatch, rank: int, world: int) -> synth.PackedBatc
                              np.ascontiguousarray(b.partner_hits[p0:p1]), b.order_base + lo)
 
 
+def shard_join_batch(b: synth.PackedJoinBatch, rank: int, world: int) -> synth.PackedJoinBatch:
+    """The reads [begin, end) of a join batch with re-based hit / CIGAR offsets.  long_spanning_reads needs no exchange: the
+    junction / indel / fusion sets are inputs every rank holds, every read is joined on its own (long_spanning_reads.cpp:3051-3140)."""
+    lo, hi = shard_range(b.n_bundles, rank, world)
+    nb = b.n_bundles
+    h0 = int(b.bundles["hit_begin"][lo]) if lo < nb else int(b.hits.shape[0])
+    h1 = int(b.bundles["hit_begin"][hi]) if hi < nb else int(b.hits.shape[0])
+    e0 = int(b.bundles["ops_begin"][lo]) if lo < nb else int(b.ops_ext.shape[0])
+    e1 = int(b.bundles["ops_begin"][hi]) if hi < nb else int(b.ops_ext.shape[0])
+    bundles = b.bundles[lo:hi].copy()
+    bundles["hit_begin"] -= h0
+    bundles["ops_begin"] -= e0
+    return synth.PackedJoinBatch(b.n_segs, b.read_words, bundles, np.ascontiguousarray(b.seg_count[lo:hi]), np.ascontiguousarray(b.reads[lo:hi]),
+                                 np.ascontiguousarray(b.hits[h0:h1]), np.ascontiguousarray(b.ops_ext[e0:e1]))
+
+
 def _uniq_sorted(rec: np.ndarray, fields: Sequence[str]) -> np.ndarray:
     if rec.size == 0:
         return rec
