@@ -475,7 +475,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                    kms={k: 0.0 for k in KERNELS})
         e0.record(stream)
         for k_ in range(steps):
-            res, tm, jt, n_joined, d2h = step(device_resident, copy=(k_ == steps - 1))     # the last step's sets are kept for the checks below
+            res, tm, jt, n_joined, d2h = step(device_resident, copy=False)
             acc["scan_ms"] += tm.scan_kernel_ms; acc["alg"] += tm.algorithmic_bytes; acc["launches"] += tm.total_launches + jt.launches
             acc["join_ms"] += jt.kernel_ms; acc["join_alg"] += jt.algorithmic_bytes; acc["join_launches"] += jt.launches
             acc["enum_ms"] += jt.enum_ms; acc["merge_ms"] += jt.merge_ms
@@ -486,6 +486,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 acc["kms"][k] += getattr(tm, k + "_ms")
         e1.record(stream)
         torch.cuda.synchronize()
+        # the last step's result sets (still in the library's page-locked arrays) as numpy copies for the checks below
+        res = capi.SegJuncsResults.from_c(res, copy=True)
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)

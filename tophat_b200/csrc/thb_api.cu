@@ -219,8 +219,9 @@ void launch_phase(thb_ctx* ctx, const BatchView& bv, const Queues& q, const SegO
     // one pass over the batch: TMA-staged tiles of 32 bundles, bundle bookkeeping + per-hit task construction (scan_tile_kernel.cuh)
     const uint32_t n_tiles = (bv.n_bundles + 31u) / 32u;
     const int grid = (int)std::min<uint64_t>((n_tiles + ST_WARPS - 1) / ST_WARPS, (uint64_t)ctx->sms * 64);
-    // residency chosen by measurement (THB_SCAN_MINB=4|6 selects the other build for the A/B): the kernel is issue-bound
-    static const int minb = [] { const char* e = getenv("THB_SCAN_MINB"); return e ? atoi(e) : 4; }();
+    // residency chosen by measurement on B200 (hg38-sized workload, 6.25 M pairs: 1.17 ms at 6 CTAs / 80 registers vs 1.40 ms at 4 / 115;
+    // THB_SCAN_MINB=4 selects the other build): the kernel is issue-bound, more resident warps fill more issue slots
+    static const int minb = [] { const char* e = getenv("THB_SCAN_MINB"); return e ? atoi(e) : 6; }();
     if (minb >= 6) scan_tile_kernel<NSMAX, 6><<<grid, ST_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, o);
     else scan_tile_kernel<NSMAX, 4><<<grid, ST_WARPS * 32, 0, ctx->compute>>>(ctx->ref, ctx->sp, bv, q, bstate, owner, o);
     cudaEventRecord(ctx->kev[1], ctx->compute);
