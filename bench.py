@@ -353,18 +353,43 @@ def parity_check(ctx, wl, P, rank: int, world: int, dist, total_pairs: int):
 # GPU arm
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pins this rank (and the threads / worker processes it starts) to the CPUs of the NUMA node its GPU hangs off, so the page-locked
+    batch buffers it allocates are node-local to the GPU's PCIe root (first-touch policy).  Returns what it did for the JSON line."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu": bdf, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError) as e:
+        return {"bound": False, "why": repr(e)[:80]}
+
+
 def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     import ctypes as C
     import torch
     import torch.distributed as dist
     from tophat_b200 import capi, synth
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     barrier = None
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
         barrier = dist.barrier
-    workers = max(1, (os.cpu_count() or 1) // world)
+    workers = max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 1) // world * 2))
     refdata = get_refdata(WORKLOAD, rank, world, barrier)
     wl = make_workload(args.pairs, rank, workers, keep_candidates=True, refdata=refdata)
     batches = pack(wl)
@@ -611,7 +636,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                              "all_kernels": {"ms_per_step": tot_ms, "algorithmic_bytes_per_step": tot_bytes,
                                              "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
                                              "frac": (tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks) if tot_ms > 0 else 0.0}},
-                "clocks": clocks, "parity_checked": parity, "host_wall_ms_per_call_kind": wall_dev if args.breakdown else None,
+                "clocks": clocks, "numa": numa, "parity_checked": parity, "host_wall_ms_per_call_kind": wall_dev if args.breakdown else None,
                 "host": {"cpu_count": os.cpu_count()},
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
@@ -625,6 +650,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
+                os.sched_setaffinity(0, all_cpus)   # the CPU legs get every core of the box again
                 cpu, cli = cpu_and_cli(args)
                 line["cpu_baseline"] = cpu
                 if cli is not None:
@@ -701,6 +727,7 @@ def main():
                     help="hg38 = BASELINE configs[2] (the configuration the metric is quoted on: hg38-sized reference at 1/2/4/8 GPUs, sharded by read); "
                          "chr20 = configs[1]; indel = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank on all CPUs instead of its GPU's NUMA node")
     ap.add_argument("--breakdown", action="store_true", help="also report the host wall clock of every C-ABI call kind (device-resident pass)")
     args = ap.parse_args()
     global WORKLOAD
