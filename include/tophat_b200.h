@@ -343,6 +343,63 @@ typedef struct thb_timing {
 } thb_timing;
 int thb_last_timing(thb_ctx* ctx, thb_timing* out);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Junction-flank matcher: the step BETWEEN the two stages (tophat.py:2546-2600 build_juncs_index, 3686-3741 map2juncs).
+ * Replaces  juncs_db <min_anchor> <max_seg_len> juncs insertions deletions fusions ref.fa   (src/juncs_db.cpp:72-229, 481-528)
+ *           bowtie-build segment_juncs.fa
+ *           bowtie -v <segment_mismatches> -k <max_seg_multihits> -m <max_seg_multihits> <junction index> <segments>
+ * for one resident reference: thb_flank_begin builds the contigs and their seed index on the device, thb_flank_submit reports, for a
+ * batch of reads cut into segments, every un-gapped placement of a segment (or of its reverse complement) on a contig with at
+ * most max_mismatches mismatches -- none for a segment that has more than max_multihits placements (bowtie's -m).  Placements come
+ * back sorted by (read, segment, contig, pos, antisense).  An 'N' of the read is a mismatch; a placement over an 'N' of the contig is
+ * invalid (bowtie 1) or, with ref_n_is_mismatch, a mismatch (bowtie 2's treatment).                                              */
+#define THB_FLANK_JUNC 0u   /* >ref|left_start|left-right|right_end|GTAG|fwd  (or |rev when aux != 0)                           */
+#define THB_FLANK_DEL  1u   /* >ref|left_start|left-right|right_end|del|fwd                                                      */
+#define THB_FLANK_INS  2u   /* >ref|left_start|left-SEQ|right_end|ins|fwd                                                        */
+#define THB_FLANK_FUS  3u   /* >ref1-ref2|left_start|left-right|right_end|fus|{ff,fr,rf,rr}   (aux = dir, CigarOpCode 7..10)     */
+typedef struct thb_flank_contig {        /* what juncs_db encodes in the FASTA name of one contig; contigs are in its output order  */
+  uint32_t kind;                         /* THB_FLANK_*                                                                         */
+  uint32_t ref_id, ref_id2;              /* 1-based; ref_id2 differs from ref_id only for fusions                                */
+  uint32_t left_start;                   /* name field 2                                                                        */
+  uint32_t left, right;                  /* junction / deletion / fusion coordinates; insertion: left, right unused              */
+  uint32_t right_end;                    /* name field 4; 0xffffffff where juncs_db prints (size_t)-1 (fusion, right flank at 0) */
+  uint32_t aux;                          /* junction: antisense; fusion: dir; insertion: inserted length                         */
+  uint32_t length;                       /* bases of the contig                                                                 */
+  char     ins_seq[20];                  /* insertion: NUL-terminated inserted bases                                            */
+} thb_flank_contig;                      /* 56 bytes */
+typedef struct thb_flank_params {
+  int32_t max_mismatches;                /* bowtie -v: --segment-mismatches (0..3)                                              */
+  int32_t max_multihits;                 /* bowtie -k / -m: --max-seg-multihits                                                 */
+  int32_t min_seg_len, max_seg_len;      /* shortest / longest segment that will be submitted; max_seg_len is juncs_db's
+                                            <read_length> (flank length); 4*(max_mismatches+2) <= min_seg_len, max_seg_len <= 56 */
+  int32_t min_anchor;                    /* juncs_db's <min_anchor>: tophat.py passes 3                                          */
+  int32_t ref_n_is_mismatch;             /* 0: bowtie 1 (placement over a contig N invalid); 1: the N counts as a mismatch       */
+} thb_flank_params;
+typedef struct thb_flank_batch {
+  uint32_t        n_reads;               /* < 2^27                                                                              */
+  uint32_t        read_words;            /* 64-bit words per bit plane of a read                                                */
+  uint32_t        n_segs;                /* segments per read (<= THB_MAX_SEGS)                                                  */
+  uint32_t        reserved;
+  const uint64_t* reads;                 /* [n_reads*3*read_words] as in thb_segjuncs_batch                                      */
+  uint16_t        seg_bounds[THB_MAX_SEGS + 1];   /* segment k = read bases [seg_bounds[k], seg_bounds[k+1])                     */
+} thb_flank_batch;
+typedef struct thb_flank_hit { uint32_t read; uint32_t contig; uint8_t seg; uint8_t pos; uint8_t antisense; uint8_t mismatches; } thb_flank_hit; /* 12 bytes */
+typedef struct thb_flank_timing { float index_ms;                 /* thb_flank_begin: contigs + seed entries + sort + bucket table  */
+                                  float h2d_ms, match_ms, post_ms, d2h_ms;   /* last submit: upload, search kernel, -m filter + sort + decode, download */
+                                  uint64_t n_contigs, n_index_entries, n_verified, n_hits, algorithmic_bytes;
+                                  uint32_t launches; uint32_t reserved; } thb_flank_timing;
+/* The four sets as thb_segjuncs_finish returns them (sorted, unique, in their set orders); any may be empty.  Needs thb_ref_upload.       */
+int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* params,
+                    const thb_junction* junctions, uint64_t n_junctions, const thb_junction* deletions, uint64_t n_deletions,
+                    const thb_insertion* insertions, uint64_t n_insertions, const thb_fusion* fusions, uint64_t n_fusions);
+/* The contigs of the index, in juncs_db's output order (owned by ctx, valid until the next thb_flank_begin). */
+int thb_flank_contigs(thb_ctx* ctx, const thb_flank_contig** contigs, uint64_t* n_contigs);
+/* Searches one batch (host arrays); *hits is owned by ctx and valid until the next thb_flank call. */
+int thb_flank_submit(thb_ctx* ctx, const thb_flank_batch* host_batch, const thb_flank_hit** hits, uint64_t* n_hits);
+/* Same for reads that already live in device memory (e.g. the `reads` array of a batch submitted to the other stages). */
+int thb_flank_submit_device(thb_ctx* ctx, const thb_flank_batch* device_batch, const thb_flank_hit** hits, uint64_t* n_hits);
+int thb_flank_last_timing(thb_ctx* ctx, thb_flank_timing* out);
+
 /* Page-locked host memory for batch arrays (full-speed, asynchronous host->device copies).
  * Returns NULL on failure. */
 void* thb_alloc_pinned(size_t bytes);

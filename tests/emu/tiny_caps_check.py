@@ -27,5 +27,10 @@ assert t.kernel_launches > 4, "the scans were expected to be repeated after grow
 assert len(got.junctions) > 64 and len(got.deletions) > 64 and len(got.insertions) > 64 and len(got.fusions) > 64
 for name in helpers.join_golden_cases():
     helpers.check_join_golden(name)
+import numpy as np  # noqa: E402
+import test_flank  # noqa: E402
+fc = test_flank.flank_case(11, 2, np.asarray([0, 25, 50, 75, 101]), 120)
+nf, _ = test_flank.check_flank(fc, 2, 40)       # the placement append buffer starts at 64 records
+assert nf > 64
 print("tiny caps ok: %d launches for 2 batches; %d junctions, %d deletions, %d insertions, %d fusions" % (
     t.kernel_launches, len(got.junctions), len(got.deletions), len(got.insertions), len(got.fusions)))

@@ -246,3 +246,14 @@ def test_emu_fusion_test_sets_join_matches_reference(name):
         our_bam = pyoracle.run_long_spanning_reads(exe, files, bams, jin, outs, td, nseg, side="left", tag=".emu", opts=opts, fusions=outs["fusions"])
         _, a = pyoracle.read_bam(our_bam); _, b = pyoracle.read_bam(ref_bam)
         assert a == b and sum(1 for r in b if "XF" in r[11]) > 200
+
+
+@pytest.mark.parametrize("name", ["v2_101bp", "v2_m2_suppression", "v3_two_word_contigs", "v3_direct_buckets", "v0_exact"])
+def test_emu_flank_matcher_equals_oracle(emu_lib, name):
+    """junction-flank matcher kernels (flank_kernel.cuh) under emulation against oracle/flank_oracle.py"""
+    import numpy as np
+    import test_flank
+    seed, v, bounds, n_reads, max_hits, npol, kw = test_flank.FLANK_CASES[name]
+    case = test_flank.flank_case(seed, v, np.asarray(bounds), n_reads, **kw)
+    n, _ = test_flank.check_flank(case, v, max_hits, npol)
+    assert n > 20

@@ -88,3 +88,147 @@ def test_contigs_equal_reference_juncs_db(tmp_path, seed, max_seg_len):
     assert len(cs) > 60
     assert {c["kind"] for c in cs} == {0, 1, 2, 3}
     assert got == want
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# the device matcher against the oracle (through the C ABI)
+
+def flank_case(seed, max_mm, seg_bounds, n_reads, lens=(3000, 1200, 500, 90), n_j=60, n_d=12, n_i=12, n_f=16, min_anchor=3):
+    """Reference + sets + reads: segments cut out of contigs (either strand, 0..max_mm+1 substitutions, now and then an N),
+    segments cut out of the genome, and random ones."""
+    from tophat_b200 import synth
+    rng = np.random.default_rng(seed)
+    names, codes = random_reference(rng, list(lens))
+    j, d, ins, f = random_sets(rng, list(lens), n_j, n_d, n_i, n_f)
+    seg_lens = np.diff(seg_bounds)
+    max_seg_len = int(seg_lens.max())
+    cs = flank_oracle.contigs(names, codes, max_seg_len, min_anchor, j, d, ins, f)
+    L = int(seg_bounds[-1])
+    reads = rng.integers(0, 4, (n_reads, L)).astype(np.uint8)
+    for r in range(n_reads):
+        for k in range(len(seg_lens)):
+            s = int(seg_lens[k]); u = rng.random()
+            if u < 0.55 and cs:
+                c = cs[int(rng.integers(0, len(cs)))]["codes"]
+                if len(c) < s:
+                    continue
+                o = int(rng.integers(0, len(c) - s + 1))
+                w = c[o:o + s].copy()
+            elif u < 0.7:
+                g = codes[int(rng.integers(0, 3))]
+                o = int(rng.integers(0, len(g) - s))
+                w = g[o:o + s].copy()
+            else:
+                continue
+            w[w > 3] = rng.integers(0, 4, int((w > 3).sum()))
+            for _ in range(int(rng.integers(0, max_mm + 2))):
+                x = int(rng.integers(0, s)); w[x] = (w[x] + 1 + rng.integers(0, 3)) % 4
+            if rng.random() < 0.08:
+                w[int(rng.integers(0, s))] = 4
+            if rng.random() < 0.5:
+                w = flank_oracle._rc(w)
+            reads[r, seg_bounds[k]:seg_bounds[k + 1]] = w
+    ref = synth.build_ref_image(names, codes)
+    return dict(names=names, codes=codes, ref=ref, j=j, d=d, ins=ins, f=f, contigs=cs, reads=reads, max_seg_len=max_seg_len,
+                min_seg_len=int(seg_lens.min()), seg_bounds=[int(x) for x in seg_bounds], min_anchor=min_anchor)
+
+
+def sets_as_records(case):
+    from tophat_b200 import synth
+    j = np.zeros(len(case["j"]), synth.JUNCTION_DTYPE)
+    for n, col in zip(("ref_id", "left", "right", "antisense"), case["j"].T):
+        j[n] = col
+    d = np.zeros(len(case["d"]), synth.JUNCTION_DTYPE)
+    for n, col in zip(("ref_id", "left", "right", "antisense"), case["d"].T):
+        d[n] = col
+    i = np.zeros(len(case["ins"]), synth.INSERTION_DTYPE)
+    for k, (r, left, s) in enumerate(case["ins"]):
+        i[k] = (r, left, len(s), s.encode())
+    f = np.zeros(len(case["f"]), synth.FUSION_DTYPE)
+    for n, col in zip(("ref_id1", "ref_id2", "left", "right", "dir"), case["f"].T):
+        f[n] = col
+    return j, d, i, f
+
+
+def check_flank(case, max_mm, max_hits, ref_n_is_mismatch=0):
+    from tophat_b200 import capi, synth
+    ctx = capi.Context(0)
+    ctx.ref_upload(case["ref"])
+    P = capi.FlankParams(max_mm, max_hits, case["min_seg_len"], case["max_seg_len"], case["min_anchor"], ref_n_is_mismatch)
+    ctx.flank_begin(P, *sets_as_records(case))
+    got_c = ctx.flank_contigs()
+    want_c = case["contigs"]
+    assert len(got_c) == len(want_c)
+    for g, w in zip(got_c, want_c):
+        assert (int(g["kind"]), int(g["ref_id"]), int(g["ref_id2"]), int(g["left_start"]), int(g["left"]), int(g["aux"]), int(g["length"])) == \
+               (w["kind"], w["ref_id"], w["ref_id2"], w["left_start"], w["left"], w["aux"], len(w["codes"])), w["name"]
+        assert int(g["right_end"]) == (w["right_end"] & 0xFFFFFFFF)
+        if w["kind"] != flank_oracle.KIND_INS:
+            assert int(g["right"]) == w["right"]
+        else:
+            assert g["ins_seq"].decode() == w["ins"]
+    rw = (case["reads"].shape[1] + 63) // 64
+    hits = ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, case["seg_bounds"])
+    t = ctx.flank_timing()
+    got = np.stack([hits[n].astype(np.int64) for n in ("read", "seg", "contig", "pos", "antisense", "mismatches")], axis=1).reshape(-1, 6)
+    want = flank_oracle.search([c["codes"] for c in want_c], case["reads"], case["seg_bounds"], max_mm, max_hits, bool(ref_n_is_mismatch))
+    assert got.shape == want.shape, "placements: ours %d, oracle %d" % (got.shape[0], want.shape[0])
+    assert (got == want).all()
+    assert t.n_hits == len(want) and t.n_contigs == len(want_c)
+    # a second batch on the same index (buffers reused), and the empty batch
+    hits2 = ctx.flank_submit(synth.pack_reads(case["reads"][::-1].copy(), rw), rw, case["seg_bounds"])
+    assert len(hits2) == len(hits)
+    assert len(ctx.flank_submit(np.zeros((0, 3 * rw), "<u8"), rw, case["seg_bounds"])) == 0
+    ctx.close()
+    return len(want), got
+
+
+FLANK_CASES = {
+    # name: (seed, max_mm, seg_bounds, n_reads, max_hits, ref_n_is_mismatch, kwargs)
+    "v2_101bp": (11, 2, [0, 25, 50, 75, 101], 120, 40, 0, {}),
+    "v2_bowtie2_n": (12, 2, [0, 25, 50, 75, 101], 80, 40, 1, {}),
+    "v2_m2_suppression": (13, 2, [0, 25, 50, 75], 100, 2, 0, {}),
+    "v0_exact": (14, 0, [0, 25, 50, 76], 80, 40, 0, {}),
+    "v1": (15, 1, [0, 25, 50, 75, 101], 80, 40, 0, {}),
+    "v3_two_word_contigs": (16, 3, [0, 30, 60, 94], 60, 40, 0, {}),
+    "v3_direct_buckets": (17, 3, [0, 20, 40], 40, 40, 0, dict(lens=(60000, 20000, 5000, 90), n_j=1500, n_d=100, n_i=100, n_f=100)),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FLANK_CASES))
+def test_flank_matcher_equals_oracle(name):
+    seed, v, bounds, n_reads, max_hits, npol, kw = FLANK_CASES[name]
+    case = flank_case(seed, v, np.asarray(bounds), n_reads, **kw)
+    n, got = check_flank(case, v, max_hits, npol)
+    assert n > 20, n
+    if name == "v2_101bp":
+        assert set(np.unique(got[:, 5])) == {0, 1, 2} and set(np.unique(got[:, 4])) == {0, 1}
+
+
+@pytest.mark.gpu
+def test_flank_argument_errors():
+    from tophat_b200 import capi, synth
+    case = flank_case(5, 2, np.asarray([0, 25, 50]), 4)
+    ctx = capi.Context(0)
+    rw = 1
+    with pytest.raises(capi.ThbError):
+        ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, case["seg_bounds"])          # no index
+    with pytest.raises(capi.ThbError):
+        ctx.flank_begin(capi.FlankParams(2, 40, 25, 25, 3, 0), *sets_as_records(case))          # no reference
+    ctx.ref_upload(case["ref"])
+    for bad in (capi.FlankParams(4, 40, 25, 25, 3, 0), capi.FlankParams(2, 40, 12, 25, 3, 0), capi.FlankParams(2, 40, 25, 60, 3, 0),
+                capi.FlankParams(2, 0, 25, 25, 3, 0), capi.FlankParams(2, 40, 26, 25, 3, 0)):
+        with pytest.raises(capi.ThbError):
+            ctx.flank_begin(bad, *sets_as_records(case))
+    ctx.flank_begin(capi.FlankParams(2, 40, 25, 25, 3, 0), *sets_as_records(case))
+    with pytest.raises(capi.ThbError):
+        ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, [0, 25, 51])                  # 26-base segment, index built for 25
+    with pytest.raises(capi.ThbError):
+        ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, [0, 25, 50, 75])              # past the read words
+    # empty sets: an index without contigs answers with no placements
+    e = [np.zeros(0, dt) for dt in (synth.JUNCTION_DTYPE, synth.JUNCTION_DTYPE, synth.INSERTION_DTYPE, synth.FUSION_DTYPE)]
+    ctx.flank_begin(capi.FlankParams(2, 40, 25, 25, 3, 0), *e)
+    assert len(ctx.flank_contigs()) == 0
+    assert len(ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, case["seg_bounds"])) == 0
+    ctx.close()

@@ -153,6 +153,36 @@ class SegJuncsResults:
 _lib = None
 
 
+THB_MAX_SEGS = 12
+FLANK_CONTIG_DTYPE = np.dtype([("kind", "<u4"), ("ref_id", "<u4"), ("ref_id2", "<u4"), ("left_start", "<u4"), ("left", "<u4"), ("right", "<u4"),
+                               ("right_end", "<u4"), ("aux", "<u4"), ("length", "<u4"), ("ins_seq", "S20")])
+FLANK_HIT_DTYPE = np.dtype([("read", "<u4"), ("contig", "<u4"), ("seg", "u1"), ("pos", "u1"), ("antisense", "u1"), ("mismatches", "u1")])
+assert FLANK_CONTIG_DTYPE.itemsize == 56 and FLANK_HIT_DTYPE.itemsize == 12
+
+
+class FlankParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("max_mismatches", "max_multihits", "min_seg_len", "max_seg_len", "min_anchor", "ref_n_is_mismatch")]
+
+
+class FlankBatchC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("read_words", C.c_uint32), ("n_segs", C.c_uint32), ("reserved", C.c_uint32),
+                ("reads", C.c_void_p), ("seg_bounds", C.c_uint16 * (THB_MAX_SEGS + 1))]
+
+
+class FlankTimingC(C.Structure):
+    _fields_ = [("index_ms", C.c_float), ("h2d_ms", C.c_float), ("match_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("n_contigs", C.c_uint64), ("n_index_entries", C.c_uint64), ("n_verified", C.c_uint64), ("n_hits", C.c_uint64),
+                ("algorithmic_bytes", C.c_uint64), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def flank_batch_c(reads_ptr: int, n_reads: int, read_words: int, seg_bounds) -> FlankBatchC:
+    b = FlankBatchC()
+    b.n_reads = n_reads; b.read_words = read_words; b.n_segs = len(seg_bounds) - 1; b.reads = reads_ptr
+    for i, v in enumerate(seg_bounds):
+        b.seg_bounds[i] = int(v)
+    return b
+
+
 def load_library(path: Optional[str] = None) -> C.CDLL:
     """Loads libtophat_b200.so; raises ThbError (never falls back) if it is missing."""
     global _lib
@@ -190,6 +220,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_join_submit_device.argtypes = [C.c_void_p, C.POINTER(JoinBatchC), C.POINTER(C.c_uint64)]
     lib.thb_join_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_join_last_timing.argtypes = [C.c_void_p, C.POINTER(JoinTimingC)]
+    lib.thb_flank_begin.argtypes = [C.c_void_p, C.POINTER(FlankParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.thb_flank_contigs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.thb_flank_submit.argtypes = [C.c_void_p, C.POINTER(FlankBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.thb_flank_submit_device.argtypes = [C.c_void_p, C.POINTER(FlankBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.thb_flank_last_timing.argtypes = [C.c_void_p, C.POINTER(FlankTimingC)]
     lib.thb_alloc_pinned.argtypes = [C.c_size_t]
     lib.thb_alloc_pinned.restype = C.c_void_p
     lib.thb_free_pinned.argtypes = [C.c_void_p]
@@ -316,6 +351,36 @@ class Context:
     def join_timing(self) -> JoinTimingC:
         t = JoinTimingC()
         self._check(self.lib.thb_join_last_timing(self.h, C.byref(t)), "thb_join_last_timing")
+        return t
+
+    # ---- junction-flank matcher (juncs_db + bowtie-build + bowtie of the segments, tophat.py:2546-2600, 3686-3741) ----
+    def flank_begin(self, params: FlankParams, junctions: np.ndarray, deletions: np.ndarray, insertions: np.ndarray, fusions: np.ndarray) -> None:
+        keep = [np.ascontiguousarray(a) for a in (junctions, deletions, insertions, fusions)]
+        args = []
+        for a in keep:
+            args += [a.ctypes.data if a.size else None, a.shape[0]]
+        self._check(self.lib.thb_flank_begin(self.h, C.byref(params), *args), "thb_flank_begin")
+
+    def flank_contigs(self) -> np.ndarray:
+        out = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.thb_flank_contigs(self.h, C.byref(out), C.byref(n)), "thb_flank_contigs")
+        return _copy_records(out.value, n.value, FLANK_CONTIG_DTYPE)
+
+    def flank_submit(self, reads: np.ndarray, read_words: int, seg_bounds, device_ptr: Optional[int] = None, copy: bool = True) -> np.ndarray:
+        """reads: (n, 3*read_words) uint64 bit planes (synth.pack_reads); or device_ptr + reads = number of reads."""
+        out = C.c_void_p(); n = C.c_uint64()
+        if device_ptr is None:
+            r = np.ascontiguousarray(reads)
+            b = flank_batch_c(r.ctypes.data if r.size else None, r.shape[0], read_words, seg_bounds)
+            self._check(self.lib.thb_flank_submit(self.h, C.byref(b), C.byref(out), C.byref(n)), "thb_flank_submit")
+        else:
+            b = flank_batch_c(device_ptr, int(reads), read_words, seg_bounds)
+            self._check(self.lib.thb_flank_submit_device(self.h, C.byref(b), C.byref(out), C.byref(n)), "thb_flank_submit_device")
+        return _copy_records(out.value, n.value, FLANK_HIT_DTYPE, copy)
+
+    def flank_timing(self) -> FlankTimingC:
+        t = FlankTimingC()
+        self._check(self.lib.thb_flank_last_timing(self.h, C.byref(t)), "thb_flank_last_timing")
         return t
 
 

@@ -1,0 +1,226 @@
+// flank_kernel.cuh -- the junction index between the two hot stages, as device passes over the resident reference image.
+//
+// Replaces, for the segments-vs-junction-contigs search (tophat.py:2546-2600, 3686-3741):
+//   juncs_db      print_splice / print_insertion / print_fusion, src/juncs_db.cpp:72-229   -> flank_build_kernel
+//   bowtie-build  (third party, suffix array + BWT of segment_juncs.fa)                    -> flank_seed_kernel + one radix sort
+//   bowtie -v <segment_mismatches> -k <max_seg_multihits> -m <max_seg_multihits>           -> flank_match_kernel (+ filter / decode)
+//
+// A contig is at most 128 bases (two flanks of <= max_seg_len bases, an inserted sequence between them for `ins` contigs), held
+// as three bit planes of CW words.  The search is seed-and-verify on the q-gram lemma: the first `smin` bases of a segment are cut
+// into v+2 pieces; a placement with <= v mismatches leaves at least two pieces exact, so every placement is found from the
+// (piece a, piece b) seed of its two FIRST exact pieces -- and is reported from that pair only, which makes the result a set without a
+// de-duplication pass.  The index is a direct-address table per piece pair: bucket -> range of (contig, offset) entries.
+// Everything is exact: seeds only propose, the verify step counts mismatches over the whole segment.
+#pragma once
+#include "../../include/tophat_b200.h"
+#include "bitplanes.cuh"
+
+namespace thb {
+
+constexpr int FLANK_MAX_PIECES = 5;        // v <= 3
+constexpr int FLANK_POS_BITS = 7;          // contig offsets < 128
+
+struct FlankDesc {           // one contig: where its bases come from (32 bytes)
+  uint64_t a_start;          // global coordinate of the left part's first base in the image
+  uint64_t b_start;          // .. of the right part
+  uint64_t ins_code;         // 2 bits per inserted base, base 0 in the low bits
+  uint8_t  a_len, b_len, ins_len, flags;     // flags: 1 = left part reverse-complemented, 2 = right part
+  uint32_t pad;
+};
+
+template <int CW> struct FlankSeq { uint64_t p0[CW], p1[CW], pn[CW]; uint64_t len; };      // 32 bytes (CW=1) / 56 -> padded below
+template <> struct FlankSeq<2> { uint64_t p0[2], p1[2], pn[2]; uint64_t len; uint64_t pad; };   // 64 bytes
+
+struct FlankIndexParams {
+  int npieces, piece_len, npairs, smin;      // pieces cover bases [0, npieces*piece_len) of a segment
+  int bbits;                                 // bucket bits per pair
+  int hashed;                                // seed code wider than bbits: bucket = mix(code) >> (64 - bbits)
+  int max_mm, max_hits, ref_n_mismatch;
+};
+
+__device__ __forceinline__ uint64_t flank_mix(uint64_t x)
+{
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; return x;
+}
+// pair index of pieces (a < b) in lexicographic order
+__device__ __forceinline__ int flank_pair_index(int a, int b, int np) { return a * np - a * (a + 1) / 2 + (b - a - 1); }
+
+__device__ __forceinline__ uint32_t flank_bucket(const FlankIndexParams& ip, uint64_t p0, uint64_t p1, int a, int b)
+{
+  const int pl = ip.piece_len; const uint64_t m = maskn(pl);
+  const uint64_t code = ((p0 >> (a * pl)) & m) | (((p1 >> (a * pl)) & m) << pl) | (((p0 >> (b * pl)) & m) << (2 * pl)) | (((p1 >> (b * pl)) & m) << (3 * pl));
+  return ip.hashed ? (uint32_t)(flank_mix(code) >> (64 - ip.bbits)) : (uint32_t)code;
+}
+
+// ---- 128-bit plane helpers ---------------------------------------------------------------------------------------------
+template <int CW> __device__ __forceinline__ void flank_put(uint64_t* w, int pos, uint64_t v)
+{
+  const int i = pos >> 6, sh = pos & 63;
+  if (CW == 1) { w[0] |= v << sh; return; }
+  w[i] |= v << sh;
+  if (sh && i + 1 < CW) w[i + 1] |= v >> (64 - sh);
+}
+template <int CW> __device__ __forceinline__ uint64_t flank_get(const uint64_t* w, int pos, int n)
+{
+  if (CW == 1) return (w[0] >> pos) & maskn(n);
+  const int i = pos >> 6, sh = pos & 63;
+  const uint64_t lo = w[i], hi = (i + 1 < CW) ? w[i + 1] : 0ull;
+  return shr128(lo, hi, sh) & maskn(n);
+}
+
+// ---- contig sequences from the image (juncs_db.cpp:72-229) ----------------------------------------------------------------
+template <int CW>
+__global__ void flank_build_kernel(RefView ref, const FlankDesc* __restrict__ desc, FlankSeq<CW>* __restrict__ seq, uint32_t n)
+{
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const FlankDesc d = desc[c];
+    FlankSeq<CW> s;
+    for (int i = 0; i < CW; ++i) s.p0[i] = s.p1[i] = s.pn[i] = 0ull;
+    P3 a = ref_fetch3(ref, d.a_start, d.a_len);
+    if (d.flags & 1) a = revcomp(a, d.a_len);
+    flank_put<CW>(s.p0, 0, a.p0); flank_put<CW>(s.p1, 0, a.p1); flank_put<CW>(s.pn, 0, a.pn);
+    int pos = d.a_len;
+    if (d.ins_len) {
+      uint64_t i0 = 0, i1 = 0;
+      for (int k = 0; k < d.ins_len; ++k) { const uint64_t cd = (d.ins_code >> (2 * k)) & 3ull; i0 |= (cd & 1ull) << k; i1 |= (cd >> 1) << k; }
+      flank_put<CW>(s.p0, pos, i0); flank_put<CW>(s.p1, pos, i1);
+      pos += d.ins_len;
+    }
+    P3 b = ref_fetch3(ref, d.b_start, d.b_len);
+    if (d.flags & 2) b = revcomp(b, d.b_len);
+    flank_put<CW>(s.p0, pos, b.p0); flank_put<CW>(s.p1, pos, b.p1); flank_put<CW>(s.pn, pos, b.pn);
+    s.len = (uint64_t)(pos + d.b_len);
+    seq[c] = s;
+  }
+}
+
+// ---- seed entries: one per (contig, offset, piece pair) ---------------------------------------------------------------------
+// entry_base[c] = number of offsets of the contigs before c; an offset o is indexed when a segment of smin bases fits at it.
+// Entries whose seed pieces touch an 'N' of the contig get the key `npairs << bbits` (sorted to the end, never looked up).
+template <int CW>
+__global__ void flank_seed_kernel(const FlankSeq<CW>* __restrict__ seq, const uint64_t* __restrict__ entry_base, uint32_t n_contigs,
+                                  FlankIndexParams ip, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+  for (uint32_t c = blockIdx.x; c < n_contigs; c += gridDim.x) {
+    const int len = (int)seq[c].len;
+    const int noff = len - ip.smin + 1;
+    if (noff <= 0) continue;
+    const uint64_t base = entry_base[c] * (uint64_t)ip.npairs;
+    for (int t = threadIdx.x; t < noff * ip.npairs; t += blockDim.x) {
+      const int o = t / ip.npairs, pr = t - o * ip.npairs;
+      int a = 0, rem = pr;
+      while (rem >= ip.npieces - 1 - a) { rem -= ip.npieces - 1 - a; ++a; }
+      const int b = a + 1 + rem;
+      const int span = ip.npieces * ip.piece_len;
+      const uint64_t w0 = flank_get<CW>(seq[c].p0, o, span), w1 = flank_get<CW>(seq[c].p1, o, span), wn = flank_get<CW>(seq[c].pn, o, span);
+      const uint64_t pm = maskn(ip.piece_len);
+      const bool has_n = (((wn >> (a * ip.piece_len)) | (wn >> (b * ip.piece_len))) & pm) != 0ull;
+      keys[base + t] = has_n ? ((uint32_t)ip.npairs << ip.bbits) : (((uint32_t)pr << ip.bbits) | flank_bucket(ip, w0, w1, a, b));
+      vals[base + t] = (c << FLANK_POS_BITS) | (uint32_t)o;
+    }
+  }
+}
+
+// start[k] = index of the first sorted entry with key >= k, for k in [0, n_keys]  (n_keys = npairs << bbits)
+__global__ void flank_bucket_kernel(const uint32_t* __restrict__ keys, uint64_t n, uint32_t n_keys, uint32_t* __restrict__ start)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t hi = (i < n) ? min(keys[i], n_keys) : n_keys;
+    const int64_t lo = (i == 0) ? -1 : (int64_t)min(keys[i - 1], n_keys);
+    for (int64_t k = lo + 1; k <= (int64_t)hi; ++k) start[k] = (uint32_t)i;
+  }
+}
+
+// ---- the search ----------------------------------------------------------------------------------------------------------
+struct FlankBatchView {
+  const uint64_t* reads; uint32_t n_reads, read_words, n_segs;
+  uint16_t seg_bounds[THB_MAX_SEGS + 1];
+};
+struct FlankOut {
+  uint64_t* keys; uint32_t* mm;            // append buffer: sortable placement key, mismatches
+  unsigned long long* count; uint64_t cap; // *count may pass cap: the batch is then repeated with a larger buffer
+  uint32_t* per_seg;                       // [n_reads * n_segs] placements found so far (the -m rule)
+  unsigned long long* n_verified;
+};
+// read(27) | seg(4) | contig(25) | pos(7) | antisense(1)
+__device__ __forceinline__ uint64_t flank_hit_key(uint32_t read, int seg, uint32_t contig, int pos, int anti)
+{
+  return ((uint64_t)read << 37) | ((uint64_t)seg << 33) | ((uint64_t)contig << 8) | ((uint64_t)pos << 1) | (uint64_t)anti;
+}
+
+// thread = (read, segment, strand, piece pair)
+template <int CW>
+__global__ void flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+                                   FlankIndexParams ip, FlankBatchView bv, FlankOut o)
+{
+  const uint64_t total = (uint64_t)bv.n_reads * bv.n_segs * 2u * (uint32_t)ip.npairs;
+  unsigned long long verified = 0;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const int pr = (int)(t % (uint32_t)ip.npairs); uint64_t r = t / (uint32_t)ip.npairs;
+    const int anti = (int)(r & 1u); r >>= 1;
+    const int seg = (int)(r % bv.n_segs); const uint32_t read = (uint32_t)(r / bv.n_segs);
+    const int s0 = bv.seg_bounds[seg], s = bv.seg_bounds[seg + 1] - s0;
+    P3 q = read_slice(bv.reads + (uint64_t)read * 3u * bv.read_words, (int)bv.read_words, s0, s);
+    if (anti) q = revcomp(q, s);
+    int a = 0, rem = pr;
+    while (rem >= ip.npieces - 1 - a) { rem -= ip.npieces - 1 - a; ++a; }
+    const int b = a + 1 + rem;
+    const int pl = ip.piece_len; const uint64_t pm = maskn(pl);
+    if ((((q.pn >> (a * pl)) | (q.pn >> (b * pl))) & pm) != 0ull) continue;       // an N in the read never matches
+    const uint32_t key = ((uint32_t)pr << ip.bbits) | flank_bucket(ip, q.p0, q.p1, a, b);
+    const uint32_t lo = __ldg(start + key), hi = __ldg(start + key + 1);
+    uint32_t* cnt = o.per_seg + (uint64_t)read * bv.n_segs + seg;
+    const uint64_t sm = maskn(s);
+    for (uint32_t e = lo; e < hi; ++e) {
+      if (((e - lo) & 63u) == 63u && *(volatile uint32_t*)cnt > (uint32_t)ip.max_hits) break;    // already suppressed by -m
+      const uint32_t v = __ldg(vals + e);
+      const uint32_t c = v >> FLANK_POS_BITS; const int pos = (int)(v & ((1u << FLANK_POS_BITS) - 1u));
+      const FlankSeq<CW>& cs = seq[c];
+      if (pos + s > (int)cs.len) continue;
+      ++verified;
+      const uint64_t w0 = flank_get<CW>(cs.p0, pos, s), w1 = flank_get<CW>(cs.p1, pos, s), wn = flank_get<CW>(cs.pn, pos, s);
+      if (wn != 0ull && !ip.ref_n_mismatch) continue;                              // bowtie 1: no placement over an ambiguous reference base
+      const uint64_t mism = ((w0 ^ q.p0) | (w1 ^ q.p1) | q.pn | wn) & sm;
+      const int nm = __popcll(mism);
+      if (nm > ip.max_mm) continue;
+      // reported from the pair of its two first exact pieces only
+      int first = -1, second = -1;
+      for (int i = 0; i < ip.npieces; ++i)
+        if (((mism >> (i * pl)) & pm) == 0ull) { if (first < 0) first = i; else if (second < 0) second = i; }
+      if (first != a || second != b) continue;
+      atomicAdd(cnt, 1u);
+      const unsigned long long slot = atomicAdd(o.count, 1ull);
+      if (slot < o.cap) { o.keys[slot] = flank_hit_key(read, seg, c, pos, anti); o.mm[slot] = (uint32_t)nm; }
+    }
+  }
+  if (verified) atomicAdd(o.n_verified, verified);
+}
+
+// the -m rule: placements of a segment with more than max_hits of them are dropped (the append order is arbitrary, the sort follows)
+__global__ void flank_filter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ mm, uint64_t n, const uint32_t* __restrict__ per_seg,
+                                    uint32_t n_segs, uint32_t max_hits, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_mm,
+                                    unsigned long long* out_count)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    const uint32_t read = (uint32_t)(k >> 37); const uint32_t seg = (uint32_t)((k >> 33) & 15u);
+    if (per_seg[(uint64_t)read * n_segs + seg] > max_hits) continue;
+    const unsigned long long slot = atomicAdd(out_count, 1ull);
+    out_keys[slot] = k; out_mm[slot] = mm[i];
+  }
+}
+
+struct FlankHitRec { uint32_t read, contig; uint8_t seg, pos, antisense, mismatches; };     // = thb_flank_hit
+
+__global__ void flank_decode_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ mm, uint64_t n, FlankHitRec* __restrict__ out)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    FlankHitRec h;
+    h.read = (uint32_t)(k >> 37); h.seg = (uint8_t)((k >> 33) & 15u); h.contig = (uint32_t)((k >> 8) & 0x1ffffffu);
+    h.pos = (uint8_t)((k >> 1) & 127u); h.antisense = (uint8_t)(k & 1u); h.mismatches = (uint8_t)mm[i];
+    out[i] = h;
+  }
+}
+
+}  // namespace thb

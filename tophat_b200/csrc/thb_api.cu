@@ -21,6 +21,7 @@
 #include "join_tile_kernel.cuh"
 #include "fusion_join_kernel.cuh"
 #include "fusion_kernel.cuh"
+#include "flank_kernel.cuh"
 
 using namespace thb;
 
@@ -80,6 +81,15 @@ struct Nccl {
   const char* (*GetErrorString)(int) = nullptr;
 };
 
+// junction-flank matcher (thb_flank_*)
+struct FlankState {
+  DevBuf desc, seq, base, keys, vals, keys2, vals2, start, reads, hkeys, hmm, hkeys2, hmm2, per_seg, out, scalars;
+  std::vector<thb_flank_contig> contigs; PinnedVec<thb_flank_hit> hits;
+  FlankIndexParams ip{}; int cw = 1; bool begun = false; uint64_t n_contigs = 0, n_entries = 0, cap_hits = 0;
+  int min_seg_len = 0, max_seg_len = 0; thb_flank_timing timing{};
+  void release() { for (DevBuf* b : { &desc, &seq, &base, &keys, &vals, &keys2, &vals2, &start, &reads, &hkeys, &hmm, &hkeys2, &hmm2, &per_seg, &out, &scalars }) b->release(); hits.release(); }
+};
+
 }  // namespace
 
 struct thb_ctx {
@@ -129,6 +139,7 @@ struct thb_ctx {
   JoinParams jp{}; bool join_begun = false; thb_join_timing jtiming{}; unsigned long long j_last_n = 0;
   JStage jstage[2];
   thb_joined* h_joined = nullptr; uint64_t h_joined_cap = 0;      // page-locked result buffer, grow-only
+  FlankState fl;
   // nccl
   Nccl nccl; void* comm = nullptr; int rank = 0, world = 1;
 };
@@ -500,7 +511,7 @@ void thb_destroy(thb_ctx* ctx)
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
   for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.ops, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
   if (ctx->h_joined) cudaFreeHost(ctx->h_joined);
-  ctx->h_juncs.release(); ctx->h_dels.release(); ctx->h_ins.release();
+  ctx->h_juncs.release(); ctx->h_dels.release(); ctx->h_ins.release(); ctx->fl.release();
   for (DevBuf* b : { &ctx->d_ins_a, &ctx->d_ins_b, &ctx->d_ins_c, &ctx->d_ins_d, &ctx->d_ins_out }) b->release();
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
   delete ctx;
@@ -1177,6 +1188,269 @@ int thb_join_last_timing(thb_ctx* ctx, thb_join_timing* out)
 {
   if (!ctx || !out) return THB_EINVAL;
   *out = ctx->jtiming;
+  return THB_OK;
+}
+
+// ---- junction-flank matcher -------------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+
+// the flank arithmetic of print_splice / print_insertion / print_fusion (juncs_db.cpp:72-229); false = juncs_db prints nothing
+struct FlankGeom { uint64_t ls, le, rs, re; bool rc_a, rc_b; };
+
+bool flank_splice(uint64_t n, uint64_t left, uint64_t right, int half, FlankGeom& g)
+{
+  if (!(left <= n && right <= n)) return false;
+  g.ls = (int64_t)left - half + 1 >= 0 ? left - half + 1 : 0; g.le = g.ls + half;
+  g.rs = right; g.re = g.rs + half < n ? g.rs + half : n;
+  g.rc_a = g.rc_b = false;
+  return g.ls < g.le && g.le <= n && g.rs < g.re && g.re <= n;
+}
+bool flank_insertion(uint64_t n, uint64_t left, int half, FlankGeom& g)
+{
+  if (!(left <= n) || half <= 0) return false;
+  g.ls = (int64_t)left - half + 1 >= 0 ? left - half + 1 : 0; g.le = g.ls + half;
+  g.rs = g.le; g.re = g.rs + half < n ? g.rs + half : n;
+  g.rc_a = g.rc_b = false;
+  return g.ls < g.le && g.le <= n && g.rs < g.re && g.re <= n;
+}
+bool flank_fusion(uint64_t n1, uint64_t n2, uint64_t left, uint64_t right, uint32_t dir, int half, FlankGeom& g)
+{
+  if (!(left < n1 && right < n2) || half <= 0) return false;
+  if (dir == 7u || dir == 8u) { g.ls = left + 1 >= (uint64_t)half ? left - half + 1 : 0; g.le = g.ls + half; }
+  else { g.ls = left; g.le = g.ls + half < n1 ? g.ls + half : n1; }
+  if (dir == 7u || dir == 9u) { g.rs = right; g.re = g.rs + half < n2 ? g.rs + half : n2; }
+  else { g.re = right + 1; g.rs = g.re >= (uint64_t)half ? g.re - half : 0; }
+  g.rc_a = dir == 9u || dir == 10u; g.rc_b = dir == 8u || dir == 10u;
+  return g.ls < g.le && g.le <= n1 && g.rs < g.re && g.re <= n2;
+}
+
+template <int CW>
+int flank_build_index(thb_ctx* ctx, uint64_t n_contigs, uint64_t n_entries, int sort_bits, uint32_t n_keys)
+{
+  FlankState& f = ctx->fl;
+  flank_build_kernel<CW><<<grid_for(n_contigs, 128), 128, 0, ctx->compute>>>(ctx->ref, (const FlankDesc*)f.desc.p, (FlankSeq<CW>*)f.seq.p, (uint32_t)n_contigs);
+  CU(cudaGetLastError());
+  flank_seed_kernel<CW><<<(unsigned)std::min<uint64_t>(n_contigs, (uint64_t)ctx->sms * 64), 64, 0, ctx->compute>>>(
+      (const FlankSeq<CW>*)f.seq.p, (const uint64_t*)f.base.p, (uint32_t)n_contigs, f.ip, (uint32_t*)f.keys.p, (uint32_t*)f.vals.p);
+  CU(cudaGetLastError());
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint32_t*)f.vals.p, (uint32_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute);
+  CU(ctx->d_cub_tmp.reserve(tmp + 16));
+  CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint32_t*)f.vals.p, (uint32_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute));
+  flank_bucket_kernel<<<grid_for(n_entries + 1, 256), 256, 0, ctx->compute>>>((const uint32_t*)f.keys2.p, n_entries, n_keys, (uint32_t*)f.start.p);
+  CU(cudaGetLastError());
+  f.timing.launches = 4;
+  return THB_OK;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
+                    const thb_junction* junctions, uint64_t n_junctions, const thb_junction* deletions, uint64_t n_deletions,
+                    const thb_insertion* insertions, uint64_t n_insertions, const thb_fusion* fusions, uint64_t n_fusions)
+{
+  if (!ctx || !P) return THB_EINVAL;
+  if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "thb_flank_begin before thb_ref_upload");
+  if ((n_junctions && !junctions) || (n_deletions && !deletions) || (n_insertions && !insertions) || (n_fusions && !fusions))
+    return fail(ctx, THB_EINVAL, "thb_flank_begin: null set with a non-zero count");
+  if (P->max_mismatches < 0 || P->max_mismatches > 3) return fail(ctx, THB_EUNSUPPORTED, "thb_flank_begin: max_mismatches %d outside 0..3 (tophat.py:2286 clamps --segment-mismatches to 3)", P->max_mismatches);
+  if (P->max_multihits < 1) return fail(ctx, THB_EINVAL, "thb_flank_begin: max_multihits %d", P->max_multihits);
+  const int npieces = P->max_mismatches + 2;
+  if (P->min_seg_len > P->max_seg_len || P->min_seg_len < 4 * npieces || P->max_seg_len > 56)
+    return fail(ctx, THB_EUNSUPPORTED, "thb_flank_begin: segment lengths %d..%d outside %d..56", P->min_seg_len, P->max_seg_len, 4 * npieces);
+  if (P->min_anchor < 0 || P->min_anchor >= P->max_seg_len) return fail(ctx, THB_EINVAL, "thb_flank_begin: min_anchor %d", P->min_anchor);
+  CU(cudaSetDevice(ctx->device));
+  FlankState& f = ctx->fl;
+  f.begun = false; f.contigs.clear(); f.timing = thb_flank_timing{};
+  f.min_seg_len = P->min_seg_len; f.max_seg_len = P->max_seg_len;
+  const int h = P->max_seg_len;
+  std::vector<FlankDesc> desc; std::vector<uint64_t> base;
+  desc.reserve(n_junctions + n_deletions + n_insertions + n_fusions); base.reserve(desc.capacity() + 1);
+  const uint32_t nref = (uint32_t)ctx->h_clen.size();
+  uint64_t n_off = 0; int max_len = 0;
+  auto ref_len = [&](uint32_t id) -> uint64_t { return (id >= 1 && id <= nref) ? ctx->h_clen[id - 1] : 0; };    // 0: no sequence (rt.get_seq == NULL)
+  auto push = [&](const FlankGeom& g, uint32_t r1, uint32_t r2, uint64_t ins_code, int ins_len, thb_flank_contig c) {
+    FlankDesc d{};
+    d.a_start = ctx->h_cstart[r1 - 1] + g.ls; d.b_start = ctx->h_cstart[r2 - 1] + g.rs;
+    d.a_len = (uint8_t)(g.le - g.ls); d.b_len = (uint8_t)(g.re - g.rs); d.ins_len = (uint8_t)ins_len; d.ins_code = ins_code;
+    d.flags = (uint8_t)((g.rc_a ? 1 : 0) | (g.rc_b ? 2 : 0));
+    const int len = d.a_len + d.ins_len + d.b_len;
+    c.length = (uint32_t)len; c.ref_id = r1; c.ref_id2 = r2;
+    base.push_back(n_off);
+    if (len >= P->min_seg_len) n_off += (uint64_t)(len - P->min_seg_len + 1);
+    if (len > max_len) max_len = len;
+    desc.push_back(d); f.contigs.push_back(c);
+  };
+  for (int pass = 0; pass < 2; ++pass) {          // junctions, then deletions read back as junctions (juncs_db.cpp:481-503)
+    const thb_junction* set = pass ? deletions : junctions; const uint64_t n = pass ? n_deletions : n_junctions;
+    for (uint64_t i = 0; i < n; ++i) {
+      const thb_junction& j = set[i]; const uint64_t rl = ref_len(j.ref_id); FlankGeom g;
+      if (!rl || !flank_splice(rl, j.left, j.right, h, g)) continue;
+      thb_flank_contig c{}; c.kind = pass ? THB_FLANK_DEL : THB_FLANK_JUNC; c.left_start = (uint32_t)g.ls; c.left = j.left; c.right = j.right;
+      c.right_end = (uint32_t)g.re; c.aux = pass ? 0u : (j.antisense ? 1u : 0u);
+      push(g, j.ref_id, j.ref_id, 0, 0, c);
+    }
+  }
+  for (uint64_t i = 0; i < n_insertions; ++i) {
+    const thb_insertion& in = insertions[i]; const uint64_t rl = ref_len(in.ref_id); FlankGeom g;
+    if (!rl || in.len == 0 || in.len > 19) continue;
+    uint64_t code = 0; bool amb = false;
+    for (uint32_t k = 0; k < in.len; ++k) {
+      uint64_t cd;
+      switch (in.seq[k]) { case 'A': cd = 0; break; case 'C': cd = 1; break; case 'G': cd = 2; break; case 'T': cd = 3; break; default: cd = 0; amb = true; }
+      code |= cd << (2 * k);
+    }
+    if (amb || !flank_insertion(rl, in.left, h - P->min_anchor, g)) continue;       // juncs_db.cpp:418-430: no ambiguity in an insertion
+    thb_flank_contig c{}; c.kind = THB_FLANK_INS; c.left_start = (uint32_t)g.ls; c.left = in.left; c.right = 0; c.right_end = (uint32_t)g.re; c.aux = in.len;
+    memcpy(c.ins_seq, in.seq, in.len); c.ins_seq[in.len] = 0;
+    push(g, in.ref_id, in.ref_id, code, (int)in.len, c);
+  }
+  for (uint64_t i = 0; i < n_fusions; ++i) {
+    const thb_fusion& fu = fusions[i]; const uint64_t r1 = ref_len(fu.ref_id1), r2 = ref_len(fu.ref_id2); FlankGeom g;
+    if (!r1 || !r2 || fu.dir < 7u || fu.dir > 10u || !flank_fusion(r1, r2, fu.left, fu.right, fu.dir, h - P->min_anchor, g)) continue;
+    thb_flank_contig c{}; c.kind = THB_FLANK_FUS; c.left = fu.left; c.right = fu.right; c.aux = fu.dir;
+    c.left_start = (uint32_t)(g.rc_a ? g.le - 1 : g.ls); c.right_end = (uint32_t)(g.rc_b ? g.rs - 1 : g.re);      // juncs_db.cpp:205-215
+    push(g, fu.ref_id1, fu.ref_id2, 0, 0, c);
+  }
+  base.push_back(n_off);
+  const uint64_t nc = desc.size();
+  if (nc >= (1ull << 25)) return fail(ctx, THB_EUNSUPPORTED, "thb_flank_begin: %llu contigs (limit 2^25)", (unsigned long long)nc);
+  FlankIndexParams ip{};
+  ip.npieces = npieces; ip.piece_len = P->min_seg_len / npieces; if (ip.piece_len > 16) ip.piece_len = 16;
+  ip.npairs = npieces * (npieces - 1) / 2; ip.smin = P->min_seg_len;
+  ip.max_mm = P->max_mismatches; ip.max_hits = P->max_multihits; ip.ref_n_mismatch = P->ref_n_is_mismatch ? 1 : 0;
+  int bb = 10; while (bb < 24 && (1ull << bb) < 2 * n_off) ++bb;
+  if (4 * ip.piece_len <= bb) { ip.bbits = 4 * ip.piece_len; ip.hashed = 0; } else { ip.bbits = bb; ip.hashed = 1; }
+  f.ip = ip; f.cw = max_len > 64 ? 2 : 1; f.n_contigs = nc;
+  const uint64_t n_entries = n_off * (uint64_t)ip.npairs;
+  if (n_entries >= 0x7fffffffull) return fail(ctx, THB_EUNSUPPORTED, "thb_flank_begin: %llu index entries (limit 2^31)", (unsigned long long)n_entries);
+  f.n_entries = n_entries;
+  f.timing.n_contigs = nc; f.timing.n_index_entries = n_entries;
+  CU(f.scalars.reserve(64));
+  if (nc == 0 || n_entries == 0) { f.begun = true; return THB_OK; }
+  const uint32_t n_keys = (uint32_t)ip.npairs << ip.bbits;
+  int sort_bits = ip.bbits; while ((1u << (sort_bits - ip.bbits)) <= (uint32_t)ip.npairs) ++sort_bits;
+  CU(f.desc.reserve(nc * sizeof(FlankDesc))); CU(f.base.reserve((nc + 1) * 8));
+  CU(f.seq.reserve(nc * (f.cw == 2 ? sizeof(FlankSeq<2>) : sizeof(FlankSeq<1>))));
+  CU(f.keys.reserve(n_entries * 4)); CU(f.vals.reserve(n_entries * 4)); CU(f.keys2.reserve(n_entries * 4)); CU(f.vals2.reserve(n_entries * 4));
+  CU(f.start.reserve(((uint64_t)n_keys + 2) * 4));
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  CU(cudaMemcpyAsync(f.desc.p, desc.data(), nc * sizeof(FlankDesc), cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(f.base.p, base.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->compute));
+  int rc = f.cw == 2 ? flank_build_index<2>(ctx, nc, n_entries, sort_bits, n_keys) : flank_build_index<1>(ctx, nc, n_entries, sort_bits, n_keys);
+  if (rc != THB_OK) return rc;
+  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));      // desc / base are host vectors of this call
+  CU(cudaEventElapsedTime(&f.timing.index_ms, ctx->ev_a, ctx->ev_b));
+  f.keys.release(); f.vals.release(); f.keys2.release(); f.desc.release(); f.base.release();      // the search needs seq, start and the sorted values
+  f.begun = true;
+  return THB_OK;
+}
+
+int thb_flank_contigs(thb_ctx* ctx, const thb_flank_contig** contigs, uint64_t* n_contigs)
+{
+  if (!ctx || !contigs || !n_contigs) return THB_EINVAL;
+  if (!ctx->fl.begun) return fail(ctx, THB_ESTATE, "thb_flank_contigs before thb_flank_begin");
+  *contigs = ctx->fl.contigs.data(); *n_contigs = ctx->fl.contigs.size();
+  return THB_OK;
+}
+
+static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, const thb_flank_hit** hits, uint64_t* n_hits)
+{
+  if (!ctx || !b || !hits || !n_hits) return THB_EINVAL;
+  FlankState& f = ctx->fl;
+  if (!f.begun) return fail(ctx, THB_ESTATE, "thb_flank_submit before thb_flank_begin");
+  *hits = nullptr; *n_hits = 0;
+  if (b->n_segs < 1 || b->n_segs > THB_MAX_SEGS || b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EINVAL, "thb_flank_submit: n_segs %u / read_words %u", b->n_segs, b->read_words);
+  if (b->n_reads >= (1u << 27)) return fail(ctx, THB_EUNSUPPORTED, "thb_flank_submit: %u reads in one batch (limit 2^27)", b->n_reads);
+  if (b->n_reads && !b->reads) return fail(ctx, THB_EINVAL, "thb_flank_submit: null reads");
+  for (uint32_t k = 0; k < b->n_segs; ++k) {
+    const int s = (int)b->seg_bounds[k + 1] - (int)b->seg_bounds[k];
+    if (s < f.min_seg_len || s > f.max_seg_len || b->seg_bounds[k + 1] > 64u * b->read_words)
+      return fail(ctx, THB_EINVAL, "thb_flank_submit: segment %u has %d bases (index built for %d..%d) or ends past the read", k, s, f.min_seg_len, f.max_seg_len);
+  }
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t launches0 = f.timing.launches;
+  f.timing.h2d_ms = f.timing.match_ms = f.timing.post_ms = f.timing.d2h_ms = 0; f.timing.n_verified = f.timing.n_hits = 0;
+  f.hits.clear();
+  if (b->n_reads == 0 || f.n_contigs == 0 || f.n_entries == 0) { *hits = f.hits.data(); return THB_OK; }
+  const size_t rbytes = (size_t)b->n_reads * 3 * b->read_words * 8;
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  const uint64_t* d_reads = b->reads;
+  if (!on_device) {
+    CU(f.reads.reserve(rbytes));
+    CU(cudaMemcpyAsync(f.reads.p, b->reads, rbytes, cudaMemcpyHostToDevice, ctx->compute));
+    d_reads = (const uint64_t*)f.reads.p;
+  }
+  CU(cudaEventRecord(ctx->ev_b, ctx->compute));
+  const uint64_t nsegs_total = (uint64_t)b->n_reads * b->n_segs;
+  CU(f.per_seg.reserve(nsegs_total * 4));
+  if (f.cap_hits == 0) f.cap_hits = tiny_caps() ? 64 : std::max<uint64_t>(1u << 16, nsegs_total / 2);
+  FlankBatchView bv{}; bv.reads = d_reads; bv.n_reads = b->n_reads; bv.read_words = b->read_words; bv.n_segs = b->n_segs;
+  for (uint32_t k = 0; k <= b->n_segs; ++k) bv.seg_bounds[k] = b->seg_bounds[k];
+  unsigned long long* sc = (unsigned long long*)f.scalars.p;      // [0] appended, [1] kept, [2] verified
+  unsigned long long counts[3] = {0, 0, 0};
+  const uint64_t threads = nsegs_total * 2u * (uint64_t)f.ip.npairs;
+  for (;;) {
+    CU(f.hkeys.reserve(f.cap_hits * 8)); CU(f.hmm.reserve(f.cap_hits * 4));
+    CU(cudaMemsetAsync(f.per_seg.p, 0, nsegs_total * 4, ctx->compute));
+    CU(cudaMemsetAsync(sc, 0, 24, ctx->compute));
+    FlankOut o{}; o.keys = (uint64_t*)f.hkeys.p; o.mm = (uint32_t*)f.hmm.p; o.count = sc; o.cap = f.cap_hits; o.per_seg = (uint32_t*)f.per_seg.p; o.n_verified = sc + 2;
+    if (f.cw == 2) flank_match_kernel<2><<<grid_for(threads, 256), 256, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
+    else           flank_match_kernel<1><<<grid_for(threads, 256), 256, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
+    CU(cudaGetLastError()); f.timing.launches++;
+    CU(cudaMemcpyAsync(counts, sc, 24, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (counts[0] <= f.cap_hits) break;
+    while (f.cap_hits < counts[0]) f.cap_hits *= 2;               // the append buffer was too small: repeat the batch with a larger one
+  }
+  CU(cudaEventRecord(ctx->ev_c, ctx->compute));
+  const uint64_t n_app = counts[0];
+  uint64_t n_keep = 0;
+  if (n_app) {
+    CU(f.hkeys2.reserve(n_app * 8)); CU(f.hmm2.reserve(n_app * 4));
+    flank_filter_kernel<<<grid_for(n_app, 256), 256, 0, ctx->compute>>>((const uint64_t*)f.hkeys.p, (const uint32_t*)f.hmm.p, n_app, (const uint32_t*)f.per_seg.p,
+                                                                       b->n_segs, (uint32_t)f.ip.max_hits, (uint64_t*)f.hkeys2.p, (uint32_t*)f.hmm2.p, sc + 1);
+    CU(cudaGetLastError()); f.timing.launches++;
+    CU(cudaMemcpyAsync(counts + 1, sc + 1, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    n_keep = counts[1];
+  }
+  if (n_keep) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)f.hkeys2.p, (uint64_t*)f.hkeys.p, (const uint32_t*)f.hmm2.p, (uint32_t*)f.hmm.p, (int)n_keep, 0, 64, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, (const uint64_t*)f.hkeys2.p, (uint64_t*)f.hkeys.p, (const uint32_t*)f.hmm2.p, (uint32_t*)f.hmm.p, (int)n_keep, 0, 64, ctx->compute));
+    CU(f.out.reserve(n_keep * sizeof(thb_flank_hit)));
+    flank_decode_kernel<<<grid_for(n_keep, 256), 256, 0, ctx->compute>>>((const uint64_t*)f.hkeys.p, (const uint32_t*)f.hmm.p, n_keep, (FlankHitRec*)f.out.p);
+    CU(cudaGetLastError()); f.timing.launches += 2;
+  }
+  CU(cudaEventRecord(ctx->ev_d, ctx->compute));
+  CU(f.hits.resize(n_keep));
+  if (n_keep) CU(cudaMemcpyAsync(f.hits.data(), f.out.p, n_keep * sizeof(thb_flank_hit), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaEventRecord(ctx->kev[0], ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaEventElapsedTime(&f.timing.h2d_ms, ctx->ev_a, ctx->ev_b));
+  CU(cudaEventElapsedTime(&f.timing.match_ms, ctx->ev_b, ctx->ev_c));
+  CU(cudaEventElapsedTime(&f.timing.post_ms, ctx->ev_c, ctx->ev_d));
+  CU(cudaEventElapsedTime(&f.timing.d2h_ms, ctx->ev_d, ctx->kev[0]));
+  f.timing.n_verified = counts[2]; f.timing.n_hits = n_keep;
+  // per segment and strand: the read words once; per proposed placement: its index entry and the contig's planes; per placement kept: the record
+  f.timing.algorithmic_bytes = rbytes + threads * 8 + counts[2] * (4 + (f.cw == 2 ? 48 : 24)) + n_keep * sizeof(thb_flank_hit);
+  (void)launches0;
+  *hits = f.hits.data(); *n_hits = n_keep;
+  return THB_OK;
+}
+
+int thb_flank_submit(thb_ctx* ctx, const thb_flank_batch* b, const thb_flank_hit** hits, uint64_t* n_hits) { return flank_submit(ctx, b, false, hits, n_hits); }
+int thb_flank_submit_device(thb_ctx* ctx, const thb_flank_batch* b, const thb_flank_hit** hits, uint64_t* n_hits) { return flank_submit(ctx, b, true, hits, n_hits); }
+
+int thb_flank_last_timing(thb_ctx* ctx, thb_flank_timing* out)
+{
+  if (!ctx || !out) return THB_EINVAL;
+  *out = ctx->fl.timing;
   return THB_OK;
 }
 
