@@ -398,6 +398,11 @@ int thb_flank_contigs(thb_ctx* ctx, const thb_flank_contig** contigs, uint64_t* 
 int thb_flank_submit(thb_ctx* ctx, const thb_flank_batch* host_batch, const thb_flank_hit** hits, uint64_t* n_hits);
 /* Same for reads that already live in device memory (e.g. the `reads` array of a batch submitted to the other stages). */
 int thb_flank_submit_device(thb_ctx* ctx, const thb_flank_batch* device_batch, const thb_flank_hit** hits, uint64_t* n_hits);
+/* The placements of the LAST submit as the BowtieHits SplicedBAMHitFactory makes of them (bwt_map.cpp:1469-1770: genomic left, the
+ * CIGAR with the event spliced in, mismatches, splice_mms within min_anchor_len of a gap, strand flags, second contig of a fusion in
+ * ops[8]) -- record i belongs to hit i of that submit; n_ops == 0 where the reference discards the hit (it does not reach over the
+ * event).  After thb_flank_submit_device the batch's device reads must still be alive.  Owned by ctx until the next thb_flank call. */
+int thb_flank_spliced_hits(thb_ctx* ctx, int min_anchor_len, const thb_jhit_full** jhits, uint64_t* n);
 int thb_flank_last_timing(thb_ctx* ctx, thb_flank_timing* out);
 
 /* Page-locked host memory for batch arrays (full-speed, asynchronous host->device copies).

@@ -154,3 +154,46 @@ def search(contig_codes: Sequence[np.ndarray], reads: np.ndarray, seg_bounds: Se
                 rows.extend(found)
     out = np.asarray(sorted(rows), dtype=np.int64).reshape(-1, 6)
     return out
+
+
+# CigarOpCode values (bwt_map.h:36-55) and the wire flags of include/tophat_b200.h
+OP_MATCH, OP_mATCH, OP_INS, OP_DEL, OP_REF_SKIP = 1, 2, 3, 5, 11
+HIT_ANTISENSE, HIT_END, JHIT_ANTISENSE_SPLICE, JHIT_SEQ_FLIPPED = 1, 2, 4, 0x10
+
+
+def spliced_hit(c: dict, pos: int, anti: int, mism: np.ndarray, min_anchor_len: int, last_segment: bool):
+    """An un-gapped placement (len(mism) matched bases at contig offset pos; mism[o] = base o mismatches) as the BowtieHit that
+    SplicedBAMHitFactory::get_hit_from_buf makes of it (bwt_map.cpp:1469-1770 with spliceCigar 678-883 for a single MATCH):
+    dict(ref_id, ref_id2, left, ops [(code, len)..], flags, mismatches, splice_mms) or None where the reference discards the hit.
+    PINNED end to end: tests/test_flank.py feeds the same placements to oracle/_ref/long_spanning_reads and to the join."""
+    s = len(mism); nm = int(np.sum(mism))
+    end = HIT_END if last_segment else 0
+    if c["kind"] == KIND_INS:
+        left = c["left_start"] + pos                                     # 1640-1651
+        if left > c["left"]:
+            return None
+        at = c["left"] + 1 - left; ln = c["aux"]; ev_end = at + ln
+        if s <= ev_end:                                                  # the hit ends inside or in front of the insertion: < 3 ops (874)
+            return None
+        smm = int(np.sum(mism[at:ev_end]))
+        return dict(ref_id=c["ref_id"], ref_id2=c["ref_id"], left=left, ops=[(OP_MATCH, at), (OP_INS, ln), (OP_MATCH, s - ev_end)],
+                    flags=(HIT_ANTISENSE if anti else 0) | end, mismatches=nm - smm, splice_mms=0)
+    fusion = c["kind"] == KIND_FUS
+    leftwards = fusion and c["aux"] in (FUSION_RF, FUSION_RR)            # 1690-1742
+    left = c["left_start"] - pos if leftwards else c["left_start"] + pos
+    lsp = c["left"] - 1 if leftwards else c["left"] + 1
+    if (left <= lsp) if leftwards else (left >= lsp):
+        return None
+    at = abs(lsp - left)
+    gap = c["right"] if fusion else c["right"] - c["left"] - 1
+    if at >= s or gap <= 0:
+        return None
+    smm = int(sum(1 for o in range(s) if mism[o] and abs(at - o) < min_anchor_len))
+    code = c["aux"] if fusion else (OP_DEL if c["kind"] == KIND_DEL else OP_REF_SKIP)
+    before = OP_mATCH if fusion and c["aux"] in (FUSION_RF, FUSION_RR) else OP_MATCH
+    after = OP_mATCH if fusion and c["aux"] in (FUSION_FR, FUSION_RR) else OP_MATCH
+    anti_out = (not anti) if leftwards else bool(anti)
+    flags = (HIT_ANTISENSE if anti_out else 0) | end | (JHIT_ANTISENSE_SPLICE if c["kind"] == KIND_JUNC and c["aux"] else 0) | \
+            (JHIT_SEQ_FLIPPED if leftwards else 0)
+    return dict(ref_id=c["ref_id"], ref_id2=c["ref_id2"], left=left, ops=[(before, at), (code, gap), (after, s - at)], flags=flags,
+                mismatches=nm, splice_mms=smm)

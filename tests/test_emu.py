@@ -257,3 +257,10 @@ def test_emu_flank_matcher_equals_oracle(emu_lib, name):
     case = test_flank.flank_case(seed, v, np.asarray(bounds), n_reads, **kw)
     n, _ = test_flank.check_flank(case, v, max_hits, npol)
     assert n > 20
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_emu_flank_pipeline_matches_reference_binaries(emu_lib):
+    """stage 1 -> junction-flank matcher -> join, against segment_juncs -> juncs_db -> long_spanning_reads of the reference"""
+    import test_flank
+    assert test_flank.flank_pipeline_check() > 500

@@ -175,6 +175,31 @@ def check_flank(case, max_mm, max_hits, ref_n_is_mismatch=0):
     assert got.shape == want.shape, "placements: ours %d, oracle %d" % (got.shape[0], want.shape[0])
     assert (got == want).all()
     assert t.n_hits == len(want) and t.n_contigs == len(want_c)
+    # the placements as BowtieHits on the genome (thb_flank_spliced_hits) against the restated SplicedBAMHitFactory
+    for ma in (8, 3):
+        jh = ctx.flank_spliced_hits(ma)
+        assert len(jh) == len(hits)
+        kinds_kept = set()
+        for h, g in zip(got, jh):
+            c = want_c[int(h[2])]
+            a, b = case["seg_bounds"][int(h[1])], case["seg_bounds"][int(h[1]) + 1]
+            q = case["reads"][int(h[0]), a:b]
+            if h[4]:
+                q = flank_oracle._rc(q)
+            cw = c["codes"][int(h[3]):int(h[3]) + (b - a)]
+            mism = (q != cw) | (q > 3) | ((cw > 3) if ref_n_is_mismatch else False)
+            w = flank_oracle.spliced_hit(c, int(h[3]), int(h[4]), mism, ma, int(h[1]) == len(case["seg_bounds"]) - 2)
+            if w is None:
+                assert int(g["n_ops"]) == 0, (c["name"], h)
+                continue
+            kinds_kept.add(c["kind"])
+            ops = [(int(x) & 15, int(x) >> 4) for x in g["ops"][:int(g["n_ops"])]]
+            assert (int(g["ref_id"]), int(g["left"]), ops, int(g["flags"]), int(g["mismatches"]), int(g["splice_mms"])) == \
+                   (w["ref_id"], w["left"], w["ops"], w["flags"], w["mismatches"], w["splice_mms"]), (c["name"], h)
+            if c["kind"] == flank_oracle.KIND_FUS:
+                assert int(g["ops"][8]) == w["ref_id2"]
+        if len(want_c) > 50 and max_mm >= 2:
+            assert kinds_kept == {0, 1, 2, 3}, kinds_kept
     # a second batch on the same index (buffers reused), and the empty batch
     hits2 = ctx.flank_submit(synth.pack_reads(case["reads"][::-1].copy(), rw), rw, case["seg_bounds"])
     assert len(hits2) == len(hits)
@@ -232,3 +257,112 @@ def test_flank_argument_errors():
     assert len(ctx.flank_contigs()) == 0
     assert len(ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, case["seg_bounds"])) == 0
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# both stages with the matcher in between, against the reference's own binaries fed the same placements
+
+def flank_pipeline_check(n_pairs=1200, seed=511, indel_prob=0.4):
+    """stage 1 (ours) -> thb_flank_* -> join (ours)   versus   segment_juncs -> juncs_db -> [the matcher's placements written as bowtie
+    would: SAM records on the contig names of the reference's juncs_db] -> fix_map_ordering -> long_spanning_reads, all reference
+    binaries.  Checks (1) our contigs are juncs_db's, name for name; (2) the join over thb_flank_spliced_hits gives the records the
+    reference's long_spanning_reads writes, i.e. the kernel's placement -> BowtieHit conversion is SplicedBAMHitFactory's."""
+    import tempfile
+    from tophat_b200 import capi, synth
+    import helpers
+    from test_gpu_join import joined_to_keys
+    wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(200_000, 80_000), n_pairs=n_pairs, seed=seed, indel_prob=indel_prob))
+    P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+    ctx = capi.Context(0); ctx.ref_upload(wl.ref)
+    res, _ = helpers.gpu_segjuncs(P, wl.ref, helpers.pack_both(wl), ctx)
+    juncs, ins = capi.join_sets_from_results(res)
+    names = wl.ref.names
+    offs, lens = synth.segment_layout(wl.cfg.read_len, wl.cfg.segment_length)
+    bounds = [int(o) for o in offs] + [int(offs[-1] + lens[-1])]
+    nseg = len(lens); rw = (wl.cfg.read_len + 63) // 64
+    FP = capi.FlankParams(P.segment_mismatches, P.max_seg_multihits, int(lens.min()), int(lens.max()), 3, 1)   # bowtie2 run: N = mismatch
+    ctx.flank_begin(FP, res.junctions, res.deletions, res.insertions, res.fusions)
+    contigs = ctx.flank_contigs()
+    total = 0
+    with tempfile.TemporaryDirectory() as td:
+        files = synth.write_pipeline_files(wl, td)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg)
+        fa = os.path.join(td, "segment_juncs.fa")
+        with open(fa, "w") as f:
+            subprocess.run([os.path.join(pyoracle.REF_DIR, "juncs_db"), "3", str(int(lens.max())), outs["juncs"], outs["insertions"], outs["deletions"],
+                            "/dev/null", files["fasta"]], check=True, stdout=f, stderr=subprocess.DEVNULL)
+        cnames, cseqs = [], []
+        for line in open(fa):
+            if line.startswith(">"):
+                cnames.append(line[1:].rstrip("\n"))
+            else:
+                cseqs.append(line.rstrip("\n"))
+        assert len(cnames) == len(contigs) > 100
+        kinds = {"GTAG": 0, "del": 1, "ins": 2}
+        for nme, sq, c in zip(cnames, cseqs, contigs):
+            t = nme.split("|")
+            assert (names.index(t[0]) + 1, int(t[1]), int(t[2].split("-")[0]), int(t[3]), kinds[t[4]], len(sq)) == \
+                   (int(c["ref_id"]), int(c["left_start"]), int(c["left"]), int(c["right_end"]), int(c["kind"]), int(c["length"])), nme
+        hdr = os.path.join(td, "segment_juncs.hdr.sam")
+        with open(hdr, "w") as f:
+            f.write("@HD\tVN:1.0\tSO:unsorted\n")
+            for n, sq in zip(cnames, cseqs):
+                f.write("@SQ\tSN:%s\tLN:%d\n" % (n, len(sq)))
+        ccodes = [synth.codes_from_ascii(sq.encode()) for sq in cseqs]
+        ctx.join_begin(P, juncs, ins)
+        for sname, side in (("left", wl.left), ("right", wl.right)):
+            idx = np.nonzero(side.unmapped)[0]
+            hits = ctx.flank_submit(synth.pack_reads(side.reads[idx], rw), rw, bounds)
+            jh = ctx.flank_spliced_hits(P.min_anchor_len)
+            assert len(hits) == len(jh) > 100
+            jin = {"juncs_fa": fa, "juncs_header": hdr, "n_contigs": len(cnames)}
+            spliced = []
+            for k in range(nseg):
+                m = hits["seg"] == k
+                hk, jk = hits[m], jh[m]
+                sam = os.path.join(td, "%s_seg%d.to_spliced.sam" % (sname, k + 1))
+                with open(sam, "w") as f:
+                    for h in hk:
+                        ri = int(idx[int(h["read"])]); s = int(lens[k])
+                        q = side.reads[ri, bounds[k]:bounds[k + 1]]
+                        if h["antisense"]:
+                            q = flank_oracle._rc(q)
+                        cw = ccodes[int(h["contig"])][int(h["pos"]):int(h["pos"]) + s]
+                        mm = (q != cw) | (q > 3) | (cw > 3)
+                        md, run = [], 0
+                        for x in range(s):
+                            if mm[x]:
+                                md.append(str(run)); md.append(chr(synth.CODE2CHAR[min(int(cw[x]), 4)])); run = 0
+                            else:
+                                run += 1
+                        md.append(str(run)); nm = int(mm.sum())
+                        assert nm == int(h["mismatches"])
+                        f.write("%d|%d:%d:%d\t%d\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:UU\n" % (
+                            int(side.ids[ri]), bounds[k], k, nseg, 16 if h["antisense"] else 0, cnames[int(h["contig"])], int(h["pos"]) + 1, s,
+                            synth.CODE2CHAR[q].tobytes().decode(), "I" * s, -6 * nm, nm, nm, "".join(md)))
+                bam = os.path.join(td, "%s_kept_reads_seg%d.to_spliced.bam" % (sname, k + 1))
+                subprocess.run([os.path.join(pyoracle.REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile", bam + ".index", sam, bam],
+                               check=True, stderr=subprocess.DEVNULL)
+                jin["%s_spl%d" % (sname, k + 1)] = bam
+                keep = jk["n_ops"] > 0
+                spliced.append((idx[hk["read"][keep]], jk[keep]))
+            jin["%s_n_spliced" % sname] = int(len(hits))
+            batch = synth.assemble_join_batch(side, spliced)
+            got = joined_to_keys(ctx.join_submit(batch), batch, P)
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, nseg,
+                                                       side=sname, tag=".ref")
+            _, recs = pyoracle.read_bam(ref_bam)
+            want = set((int(r[0]), names.index(r[2]) + 1, r[3], r[5], r[1], r[11]["NM"]) for r in recs)
+            assert got == want, "%s: only ours %r; only reference %r" % (sname, sorted(got - want)[:3], sorted(want - got)[:3])
+            spl = [r for r in want if "N" in r[3] or "D" in r[3] or "I" in r[3]]
+            assert len(spl) > 50, len(spl)
+            total += len(want)
+    ctx.close()
+    return total
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_flank_pipeline_matches_reference_binaries():
+    assert flank_pipeline_check() > 500

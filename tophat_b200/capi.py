@@ -225,6 +225,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_flank_submit.argtypes = [C.c_void_p, C.POINTER(FlankBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_flank_submit_device.argtypes = [C.c_void_p, C.POINTER(FlankBatchC), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_flank_last_timing.argtypes = [C.c_void_p, C.POINTER(FlankTimingC)]
+    lib.thb_flank_spliced_hits.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.thb_alloc_pinned.argtypes = [C.c_size_t]
     lib.thb_alloc_pinned.restype = C.c_void_p
     lib.thb_free_pinned.argtypes = [C.c_void_p]
@@ -377,6 +378,12 @@ class Context:
             b = flank_batch_c(device_ptr, int(reads), read_words, seg_bounds)
             self._check(self.lib.thb_flank_submit_device(self.h, C.byref(b), C.byref(out), C.byref(n)), "thb_flank_submit_device")
         return _copy_records(out.value, n.value, FLANK_HIT_DTYPE, copy)
+
+    def flank_spliced_hits(self, min_anchor_len: int, copy: bool = True) -> np.ndarray:
+        """JHIT_FULL_DTYPE records, one per placement of the last flank_submit (n_ops == 0: discarded by the reference's rules)."""
+        out = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.thb_flank_spliced_hits(self.h, min_anchor_len, C.byref(out), C.byref(n)), "thb_flank_spliced_hits")
+        return _copy_records(out.value, n.value, synth.JHIT_FULL_DTYPE, copy)
 
     def flank_timing(self) -> FlankTimingC:
         t = FlankTimingC()

@@ -223,4 +223,70 @@ __global__ void flank_decode_kernel(const uint64_t* __restrict__ keys, const uin
   }
 }
 
+// ---- placements back on the genome: SplicedBAMHitFactory::get_hit_from_buf + spliceCigar for an un-gapped hit ------------------
+// (bwt_map.cpp:1469-1770, 678-883).  A placement is `s` matched bases at offset pos of a contig; on the genome it is
+//   junction / deletion   left = left_start + pos, x = left + 1 .. : xM <gap>N|D (s-x)M         (x bases on the left flank)
+//   insertion             xM <len>I (s-x-len)M, mismatches on inserted bases are not counted
+//   fusion                xM <right>F (s-x)M with the lower-case match on the side that is read leftwards, strand flipped for rf / rr
+// and is dropped (n_ops = 0) where the reference drops it: the hit does not reach over the event, or starts at / behind it.
+// splice_mms = mismatches within min_anchor_len of the gap (1675-1689); the arithmetic follows the contig NAME, as the reference's does.
+struct FlankContigDev { uint32_t kind, ref_id, ref_id2, left_start, left, right, right_end, aux, length; char ins_seq[20]; };   // = thb_flank_contig
+struct FlankJHit { uint32_t ref_id; int32_t left; uint8_t n_ops, flags, mismatches, splice_mms; uint32_t ops[THB_JHIT_MAX_OPS]; };   // = thb_jhit_full
+
+template <int CW>
+__global__ void flank_splice_kernel(const FlankSeq<CW>* __restrict__ seq, const FlankContigDev* __restrict__ cdesc, const uint64_t* __restrict__ keys,
+                                    uint64_t n, FlankBatchView bv, int min_anchor_len, int ref_n_mismatch, FlankJHit* __restrict__ out)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    const uint32_t read = (uint32_t)(k >> 37); const int seg = (int)((k >> 33) & 15u); const uint32_t c = (uint32_t)((k >> 8) & 0x1ffffffu);
+    const int pos = (int)((k >> 1) & 127u); const int anti = (int)(k & 1u);
+    const int s0 = bv.seg_bounds[seg], s = bv.seg_bounds[seg + 1] - s0;
+    P3 q = read_slice(bv.reads + (uint64_t)read * 3u * bv.read_words, (int)bv.read_words, s0, s);
+    if (anti) q = revcomp(q, s);
+    const FlankSeq<CW>& cs = seq[c];
+    const uint64_t w0 = flank_get<CW>(cs.p0, pos, s), w1 = flank_get<CW>(cs.p1, pos, s), wn = flank_get<CW>(cs.pn, pos, s);
+    const uint64_t mism = ((w0 ^ q.p0) | (w1 ^ q.p1) | q.pn | (ref_n_mismatch ? wn : 0ull)) & maskn(s);      // bit o: contig offset pos + o
+    const int nm = __popcll(mism);
+    const FlankContigDev T = cdesc[c];
+    FlankJHit h;
+    h.ref_id = T.ref_id; h.left = 0; h.n_ops = 0; h.flags = 0; h.mismatches = 0; h.splice_mms = 0;
+    for (int j = 0; j < THB_JHIT_MAX_OPS; ++j) h.ops[j] = 0u;
+    const int end = (seg == (int)bv.n_segs - 1) ? THB_HIT_END : 0;
+    if (T.kind == THB_FLANK_INS) {
+      const int left = (int)T.left_start + pos;
+      const int at = (int)T.left + 1 - left, len = (int)T.aux, ev_end = at + len;
+      if (left <= (int)T.left && s > ev_end) {
+        const int smm = __popcll(mism & (maskn(ev_end) & ~maskn(at)));
+        h.left = left; h.n_ops = 3;
+        h.ops[0] = ((uint32_t)at << 4) | 1u; h.ops[1] = ((uint32_t)len << 4) | 3u; h.ops[2] = ((uint32_t)(s - ev_end) << 4) | 1u;
+        h.flags = (uint8_t)((anti ? THB_HIT_ANTISENSE : 0) | end);
+        h.mismatches = (uint8_t)(nm - smm); h.splice_mms = 0;                      // create_hit(.., splice_mms = 0) for insertions (1652-1664)
+      }
+    } else {
+      const bool fusion = T.kind == THB_FLANK_FUS;
+      const bool leftwards = fusion && (T.aux == 9u || T.aux == 10u);
+      const int left = leftwards ? (int)T.left_start - pos : (int)T.left_start + pos;
+      const int lsp = leftwards ? (int)T.left - 1 : (int)T.left + 1;
+      const bool reach = leftwards ? left > lsp : left < lsp;
+      int at = lsp - left; if (at < 0) at = -at;
+      const int gap = fusion ? (int)T.right : (int)T.right - (int)T.left - 1;
+      if (reach && at < s && gap > 0) {
+        const int lo = at - min_anchor_len + 1 > 0 ? at - min_anchor_len + 1 : 0, hi = at + min_anchor_len < s ? at + min_anchor_len : s;
+        const int smm = hi > lo ? __popcll(mism & (maskn(hi) & ~maskn(lo))) : 0;
+        const uint32_t code = fusion ? T.aux : (T.kind == THB_FLANK_DEL ? 5u : 11u);
+        const uint32_t before = (fusion && (T.aux == 9u || T.aux == 10u)) ? 2u : 1u, after = (fusion && (T.aux == 8u || T.aux == 10u)) ? 2u : 1u;
+        h.left = left; h.n_ops = 3;
+        h.ops[0] = ((uint32_t)at << 4) | before; h.ops[1] = ((uint32_t)gap << 4) | code; h.ops[2] = ((uint32_t)(s - at) << 4) | after;
+        if (fusion) h.ops[THB_JHIT_MAX_OPS - 1] = T.ref_id2;
+        const int anti_out = leftwards ? !anti : anti;
+        h.flags = (uint8_t)((anti_out ? THB_HIT_ANTISENSE : 0) | end | ((T.kind == THB_FLANK_JUNC && T.aux) ? THB_JHIT_ANTISENSE_SPLICE : 0) |
+                            (leftwards ? THB_JHIT_SEQ_FLIPPED : 0));
+        h.mismatches = (uint8_t)nm; h.splice_mms = (uint8_t)smm;
+      }
+    }
+    out[i] = h;
+  }
+}
+
 }  // namespace thb

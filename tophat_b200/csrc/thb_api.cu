@@ -83,11 +83,12 @@ struct Nccl {
 
 // junction-flank matcher (thb_flank_*)
 struct FlankState {
-  DevBuf desc, seq, base, keys, vals, keys2, vals2, start, reads, hkeys, hmm, hkeys2, hmm2, per_seg, out, scalars;
-  std::vector<thb_flank_contig> contigs; PinnedVec<thb_flank_hit> hits;
+  DevBuf desc, seq, base, keys, vals, keys2, vals2, start, reads, hkeys, hmm, hkeys2, hmm2, per_seg, out, scalars, cdesc, jout;
+  std::vector<thb_flank_contig> contigs; PinnedVec<thb_flank_hit> hits; PinnedVec<thb_jhit_full> jhits;
+  FlankBatchView last_bv{}; uint64_t last_n = 0; bool have_last = false;
   FlankIndexParams ip{}; int cw = 1; bool begun = false; uint64_t n_contigs = 0, n_entries = 0, cap_hits = 0;
   int min_seg_len = 0, max_seg_len = 0; thb_flank_timing timing{};
-  void release() { for (DevBuf* b : { &desc, &seq, &base, &keys, &vals, &keys2, &vals2, &start, &reads, &hkeys, &hmm, &hkeys2, &hmm2, &per_seg, &out, &scalars }) b->release(); hits.release(); }
+  void release() { for (DevBuf* b : { &desc, &seq, &base, &keys, &vals, &keys2, &vals2, &start, &reads, &hkeys, &hmm, &hkeys2, &hmm2, &per_seg, &out, &scalars, &cdesc, &jout }) b->release(); hits.release(); jhits.release(); }
 };
 
 }  // namespace
@@ -1263,7 +1264,7 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   if (P->min_anchor < 0 || P->min_anchor >= P->max_seg_len) return fail(ctx, THB_EINVAL, "thb_flank_begin: min_anchor %d", P->min_anchor);
   CU(cudaSetDevice(ctx->device));
   FlankState& f = ctx->fl;
-  f.begun = false; f.contigs.clear(); f.timing = thb_flank_timing{};
+  f.begun = false; f.have_last = false; f.contigs.clear(); f.timing = thb_flank_timing{};
   f.min_seg_len = P->min_seg_len; f.max_seg_len = P->max_seg_len;
   const int h = P->max_seg_len;
   std::vector<FlankDesc> desc; std::vector<uint64_t> base;
@@ -1339,6 +1340,8 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   CU(cudaMemcpyAsync(f.desc.p, desc.data(), nc * sizeof(FlankDesc), cudaMemcpyHostToDevice, ctx->compute));
   CU(cudaMemcpyAsync(f.base.p, base.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->compute));
+  CU(f.cdesc.reserve(nc * sizeof(thb_flank_contig)));
+  CU(cudaMemcpyAsync(f.cdesc.p, f.contigs.data(), nc * sizeof(thb_flank_contig), cudaMemcpyHostToDevice, ctx->compute));
   int rc = f.cw == 2 ? flank_build_index<2>(ctx, nc, n_entries, sort_bits, n_keys) : flank_build_index<1>(ctx, nc, n_entries, sort_bits, n_keys);
   if (rc != THB_OK) return rc;
   CU(cudaEventRecord(ctx->ev_b, ctx->compute));
@@ -1374,8 +1377,8 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
   CU(cudaSetDevice(ctx->device));
   const uint32_t launches0 = f.timing.launches;
   f.timing.h2d_ms = f.timing.match_ms = f.timing.post_ms = f.timing.d2h_ms = 0; f.timing.n_verified = f.timing.n_hits = 0;
-  f.hits.clear();
-  if (b->n_reads == 0 || f.n_contigs == 0 || f.n_entries == 0) { *hits = f.hits.data(); return THB_OK; }
+  f.hits.clear(); f.have_last = false;
+  if (b->n_reads == 0 || f.n_contigs == 0 || f.n_entries == 0) { *hits = f.hits.data(); f.have_last = true; f.last_n = 0; return THB_OK; }
   const size_t rbytes = (size_t)b->n_reads * 3 * b->read_words * 8;
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   const uint64_t* d_reads = b->reads;
@@ -1440,12 +1443,34 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
   // per segment and strand: the read words once; per proposed placement: its index entry and the contig's planes; per placement kept: the record
   f.timing.algorithmic_bytes = rbytes + threads * 8 + counts[2] * (4 + (f.cw == 2 ? 48 : 24)) + n_keep * sizeof(thb_flank_hit);
   (void)launches0;
+  f.last_bv = bv; f.last_n = n_keep; f.have_last = true;
   *hits = f.hits.data(); *n_hits = n_keep;
   return THB_OK;
 }
 
 int thb_flank_submit(thb_ctx* ctx, const thb_flank_batch* b, const thb_flank_hit** hits, uint64_t* n_hits) { return flank_submit(ctx, b, false, hits, n_hits); }
 int thb_flank_submit_device(thb_ctx* ctx, const thb_flank_batch* b, const thb_flank_hit** hits, uint64_t* n_hits) { return flank_submit(ctx, b, true, hits, n_hits); }
+
+int thb_flank_spliced_hits(thb_ctx* ctx, int min_anchor_len, const thb_jhit_full** jhits, uint64_t* n)
+{
+  if (!ctx || !jhits || !n) return THB_EINVAL;
+  FlankState& f = ctx->fl;
+  if (!f.begun || !f.have_last) return fail(ctx, THB_ESTATE, "thb_flank_spliced_hits without a preceding thb_flank_submit");
+  if (min_anchor_len < 0) return fail(ctx, THB_EINVAL, "thb_flank_spliced_hits: min_anchor_len %d", min_anchor_len);
+  static_assert(sizeof(FlankJHit) == sizeof(thb_jhit_full) && sizeof(FlankContigDev) == sizeof(thb_flank_contig) && sizeof(FlankHitRec) == sizeof(thb_flank_hit), "wire records");
+  CU(cudaSetDevice(ctx->device));
+  *jhits = nullptr; *n = f.last_n;
+  CU(f.jhits.resize(f.last_n));
+  if (f.last_n == 0) { *jhits = f.jhits.data(); return THB_OK; }
+  CU(f.jout.reserve(f.last_n * sizeof(thb_jhit_full)));
+  if (f.cw == 2) flank_splice_kernel<2><<<grid_for(f.last_n, 128), 128, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const FlankContigDev*)f.cdesc.p, (const uint64_t*)f.hkeys.p, f.last_n, f.last_bv, min_anchor_len, f.ip.ref_n_mismatch, (FlankJHit*)f.jout.p);
+  else           flank_splice_kernel<1><<<grid_for(f.last_n, 128), 128, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const FlankContigDev*)f.cdesc.p, (const uint64_t*)f.hkeys.p, f.last_n, f.last_bv, min_anchor_len, f.ip.ref_n_mismatch, (FlankJHit*)f.jout.p);
+  CU(cudaGetLastError()); f.timing.launches++;
+  CU(cudaMemcpyAsync(f.jhits.data(), f.jout.p, f.last_n * sizeof(thb_jhit_full), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  *jhits = f.jhits.data();
+  return THB_OK;
+}
 
 int thb_flank_last_timing(thb_ctx* ctx, thb_flank_timing* out)
 {

@@ -1134,16 +1134,15 @@ def pack_join_hits(full: np.ndarray, hit_begin: np.ndarray):
     return heads, ext, ops_begin.astype("<u4")
 
 
-def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> PackedJoinBatch:
-    """Per-read bundles of long_spanning_reads (JoinSegmentsWorker rules, long_spanning_reads.cpp:2706-2785): contiguous segment
-    hits followed by the junction-index hits mapped back to the genome (SplicedBAMHitFactory, bwt_map.cpp:1469-1770); a read is
-    kept when every segment has at least one hit."""
+def assemble_join_batch(side: SideData, spliced) -> PackedJoinBatch:
+    """Per-read bundles of long_spanning_reads (JoinSegmentsWorker rules, long_spanning_reads.cpp:2706-2785): per segment the contiguous
+    hits followed by the junction-index hits on the genome; a read is kept when every segment has at least one hit.
+    spliced: per segment (read_idx array, JHIT_FULL_DTYPE array) in stream order."""
     nseg = len(side.seg_hits)
     n, L = side.reads.shape
-    spl = spliced_placements(wl, side, junctions)
     counts = np.zeros((n, nseg), dtype=np.int64)
     for k in range(nseg):
-        counts[:, k] = np.bincount(side.seg_hits[k]["read_idx"], minlength=n) + np.bincount(spl[k]["read_idx"], minlength=n)
+        counts[:, k] = np.bincount(side.seg_hits[k]["read_idx"], minlength=n) + np.bincount(spliced[k][0], minlength=n)
     visit = (counts > 0).all(axis=1)
     sel = np.nonzero(visit)[0]
     nb = sel.shape[0]
@@ -1158,17 +1157,9 @@ def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> Packe
         jh["ref_id"] = hm["ref_id"]; jh["left"] = hm["left"]; jh["n_ops"] = 1; jh["flags"] = hm["flags"]; jh["mismatches"] = hm["edit_dist"]
         jh["ops"][:, 0] = (hm["read_len"].astype(np.uint32) << 4) | OP_MATCH
         parts.append(jh); keys.append(b[m] * (2 * nseg) + 2 * k)
-        d = spl[k]
-        b = remap[d["read_idx"]]; m = b >= 0
-        js = np.zeros(int(m.sum()), dtype=JHIT_FULL_DTYPE)
-        x = d["x"][m]; ln = d["ln"]
-        js["ref_id"] = d["ref_id"][m]; js["left"] = d["jl"][m] - x + 1; js["n_ops"] = 3
-        js["flags"] = np.where(d["anti"][m], HIT_ANTISENSE, 0) | (HIT_END if k == nseg - 1 else 0) | np.where(d["asplice"][m] > 0, JHIT_ANTISENSE_SPLICE, 0)
-        js["mismatches"] = d["nm"][m]; js["splice_mms"] = d["smm"][m]
-        js["ops"][:, 0] = (x.astype(np.uint32) << 4) | OP_MATCH
-        js["ops"][:, 1] = ((d["jr"][m] - d["jl"][m] - 1).astype(np.uint32) << 4) | OP_REF_SKIP
-        js["ops"][:, 2] = ((ln - x).astype(np.uint32) << 4) | OP_MATCH
-        parts.append(js); keys.append(b[m] * (2 * nseg) + 2 * k + 1)
+        ridx, js = spliced[k]
+        b = remap[ridx]; m = b >= 0
+        parts.append(js[m]); keys.append(b[m] * (2 * nseg) + 2 * k + 1)
     allh = np.concatenate(parts); key = np.concatenate(keys)
     allh = allh[np.argsort(key, kind="stable")]
     bundles = np.zeros(nb, dtype=JBUNDLE_DTYPE)
@@ -1179,6 +1170,26 @@ def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> Packe
     bundles["ops_begin"] = ops_begin
     rw = (L + 63) // 64
     return PackedJoinBatch(nseg, rw, bundles, np.ascontiguousarray(counts[sel].astype("<u2")), pack_reads(side.reads[sel], rw), heads, ext)
+
+
+def pack_join_side(wl: Workload, side: SideData, junctions: np.ndarray) -> PackedJoinBatch:
+    """assemble_join_batch with the junction-index hits placed analytically (spliced_placements) and mapped back to the genome
+    as SplicedBAMHitFactory does (bwt_map.cpp:1469-1770)."""
+    nseg = len(side.seg_hits)
+    spl = spliced_placements(wl, side, junctions)
+    spliced = []
+    for k in range(nseg):
+        d = spl[k]
+        js = np.zeros(int(d["read_idx"].shape[0]), dtype=JHIT_FULL_DTYPE)
+        x = d["x"]; ln = d["ln"]
+        js["ref_id"] = d["ref_id"]; js["left"] = d["jl"] - x + 1; js["n_ops"] = 3
+        js["flags"] = np.where(d["anti"], HIT_ANTISENSE, 0) | (HIT_END if k == nseg - 1 else 0) | np.where(d["asplice"] > 0, JHIT_ANTISENSE_SPLICE, 0)
+        js["mismatches"] = d["nm"]; js["splice_mms"] = d["smm"]
+        js["ops"][:, 0] = (x.astype(np.uint32) << 4) | OP_MATCH
+        js["ops"][:, 1] = ((d["jr"] - d["jl"] - 1).astype(np.uint32) << 4) | OP_REF_SKIP
+        js["ops"][:, 2] = ((ln - x).astype(np.uint32) << 4) | OP_MATCH
+        spliced.append((d["read_idx"], js))
+    return assemble_join_batch(side, spliced)
 
 
 def spliced_hits_for_sam(wl: Workload, side: SideData, junctions: np.ndarray, contigs):
