@@ -353,6 +353,70 @@ def parity_check(ctx, wl, P, rank: int, world: int, dist, total_pairs: int):
 # GPU arm
 
 
+def flank_join_inputs(ctx, wl, res0, P, peaks_for_flank=None, steps: int = 3):
+    """Stage-2 inputs through the junction-flank matcher (thb_flank_*: the device replacement of juncs_db + bowtie-build + bowtie of the
+    segments, tophat.py:2546-2600, 3686-3741) instead of placing the spliced segments analytically: index over the sets of the
+    set-up pass, every segment of every unmapped read searched, placements mapped back to the genome on the device, then the
+    per-read bundles of long_spanning_reads.  Returns the two join batches and the matcher's own measurements (CUDA events)."""
+    import torch
+    from tophat_b200 import capi, synth
+    offs, lens = synth.segment_layout(wl.cfg.read_len, wl.cfg.segment_length)
+    bounds = [int(o) for o in offs] + [int(offs[-1] + lens[-1])]
+    nseg = len(lens); rw = (wl.cfg.read_len + 63) // 64
+    FP = capi.FlankParams(int(P.segment_mismatches), int(P.max_seg_multihits), int(lens.min()), int(lens.max()), 3, 1)
+    t0 = time.time()
+    ctx.flank_begin(FP, res0.junctions, res0.deletions, res0.insertions, res0.fusions)
+    begin_wall = time.time() - t0
+    ft = ctx.flank_timing()
+    info = {"replaces": "juncs_db <3> <max_seg_len> + bowtie-build + bowtie -v %d -k %d -m %d of every segment of the unmapped reads "
+                        "(tophat.py:2546-2600, 3686-3741); outside the timed step, like the reference arm's own set-up" % (FP.max_mismatches, FP.max_multihits, FP.max_multihits),
+            "index": {"contigs": int(ft.n_contigs), "entries": int(ft.n_index_entries), "device_ms": float(ft.index_ms), "wall_ms": begin_wall * 1e3},
+            "sides": []}
+    batches = []
+    for side in (wl.left, wl.right):
+        idx = np.nonzero(side.unmapped)[0]
+        pin = torch.from_numpy(synth.pack_reads(side.reads[idx], rw)).pin_memory()
+        dev = pin.cuda(); torch.cuda.synchronize()
+        ms, vs = [], []
+        for k in range(steps + 1):                                  # one warm-up
+            ctx.flank_submit(len(idx), rw, bounds, device_ptr=dev.data_ptr(), copy=False)
+            t = ctx.flank_timing()
+            if k:
+                ms.append((t.match_ms, t.post_ms)); vs.append(int(t.n_verified))
+        w0 = time.time()
+        hits = ctx.flank_submit(pin.numpy(), rw, bounds)            # the call a host makes: pinned host reads in, placements out
+        host_ms = (time.time() - w0) * 1e3
+        t = ctx.flank_timing()
+        jh = ctx.flank_spliced_hits(int(P.min_anchor_len))
+        keep = jh["n_ops"] > 0
+        spliced = []
+        for k in range(nseg):
+            m = (hits["seg"] == k) & keep
+            spliced.append((idx[hits["read"][m]], jh[m]))
+        # the analytically placed spliced segments (the previous stage-2 input) must all be among the matcher's
+        ana = synth.spliced_placements(wl, side, res0.junctions)
+        def keyof(read, seg, x, left):
+            return (read.astype(np.uint64) << np.uint64(40)) | (np.uint64(seg) << np.uint64(37)) | (x.astype(np.uint64) << np.uint64(32)) | (left.astype(np.int64).astype(np.uint64) & np.uint64(0xffffffff))
+        got = np.concatenate([keyof(r, k, (j["ops"][:, 0] >> 4), j["left"]) for k, (r, j) in enumerate(spliced)]) if spliced else np.zeros(0, np.uint64)
+        want = np.concatenate([keyof(d["read_idx"], k, d["x"], d["jl"] - d["x"] + 1) for k, d in enumerate(ana)])
+        missing = int((~np.isin(want, got)).sum())
+        subset = missing == 0
+        match_ms = float(np.mean([a for a, _ in ms])); post_ms = float(np.mean([b for _, b in ms]))
+        info["sides"].append({"reads": int(len(idx)), "segments": int(len(idx)) * nseg, "placements": int(len(hits)), "spliced_hits": int(keep.sum()),
+                              "analytic_placements": int(want.shape[0]), "analytic_subset_of_matcher": subset, "analytic_missing": missing, "verified_candidates": int(np.mean(vs)),
+                              "match_ms": match_ms, "post_ms": post_ms, "host_call_ms": host_ms, "h2d_bytes": int(pin.numel() * 8), "d2h_bytes": int(hits.nbytes),
+                              "algorithmic_bytes": int(t.algorithmic_bytes)})
+        if not subset:
+            log("[bench] WARNING: %d analytically placed spliced segments are not among the matcher's placements" % missing)
+        batches.append(synth.assemble_join_batch(side, spliced))
+        del dev, pin
+    tot_ms = sum(x["match_ms"] + x["post_ms"] for x in info["sides"])
+    info["segments_per_s"] = sum(x["segments"] for x in info["sides"]) / (tot_ms * 1e-3) if tot_ms > 0 else 0.0
+    info["reads_per_s"] = sum(x["reads"] for x in info["sides"]) / (tot_ms * 1e-3) if tot_ms > 0 else 0.0
+    info["achieved_gbs"] = sum(x["algorithmic_bytes"] for x in info["sides"]) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    return batches, info
+
+
 def bind_to_gpu_numa(local_rank: int):
     """Pins this rank (and the threads / worker processes it starts) to the CPUs of the NUMA node its GPU hangs off, so the page-locked
     batch buffers it allocates are node-local to the GPU's PCIe root (first-touch policy).  Returns what it did for the JSON line."""
@@ -446,7 +510,11 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     # page-locked copies of the junction / insertion sets (stage-2 inputs that thb_join_begin uploads every step)
     _jpin = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory() for a in jsets]
     jsets = tuple(t.numpy().view(a.dtype) for t, a in zip(_jpin, jsets))
-    jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
+    if args.analytic_join_inputs:
+        jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
+        flank = None
+    else:
+        jbatches, flank = flank_join_inputs(ctx, wl, res0, P, peaks_for_flank=None)
     log("[bench] rank %d: join batches %d + %d reads, %d segment hits (%.1f s)" % (
         rank, jbatches[0].n_bundles, jbatches[1].n_bundles, sum(int(b.hits.shape[0]) for b in jbatches), time.time() - t0))
     j_fields = ("bundles", "seg_count", "reads", "hits", "ops_ext")
@@ -636,7 +704,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                              "all_kernels": {"ms_per_step": tot_ms, "algorithmic_bytes_per_step": tot_bytes,
                                              "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
                                              "frac": (tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks) if tot_ms > 0 else 0.0}},
-                "clocks": clocks, "numa": numa, "parity_checked": parity, "host_wall_ms_per_call_kind": wall_dev if args.breakdown else None,
+                "clocks": clocks, "numa": numa, "flank_match": flank, "parity_checked": parity, "host_wall_ms_per_call_kind": wall_dev if args.breakdown else None,
                 "host": {"cpu_count": os.cpu_count()},
                 "results": {"junctions": int(len(res.junctions)), "deletions": int(len(res.deletions)),
                             "insertions": int(len(res.insertions)), "windows": int(tm.n_windows),
@@ -727,6 +795,8 @@ def main():
                     help="hg38 = BASELINE configs[2] (the configuration the metric is quoted on: hg38-sized reference at 1/2/4/8 GPUs, sharded by read); "
                          "chr20 = configs[1]; indel = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--analytic-join-inputs", action="store_true",
+                    help="place the spliced segments of stage 2 analytically (round 1) instead of through the junction-flank matcher")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank on all CPUs instead of its GPU's NUMA node")
     ap.add_argument("--breakdown", action="store_true", help="also report the host wall clock of every C-ABI call kind (device-resident pass)")
     args = ap.parse_args()
