@@ -130,22 +130,26 @@ def tophat_common_opts(inner_mean: int = 50, inner_sd: int = 20, extra: Optional
 
 
 def make_bams(files: Dict[str, str], outdir: str, nseg: int) -> Dict[str, str]:
-    """FASTQ/SAM text -> BAM via the reference's prep_reads / fix_map_ordering (oracle/_ref)."""
+    """FASTQ/SAM text -> BAM via the reference's prep_reads / fix_map_ordering (oracle/_ref); the conversions are independent
+    processes and run side by side."""
+    from concurrent.futures import ThreadPoolExecutor
     hdr = files["header"]
     out = {}
+    cmds = []
     for side in ("left", "right"):
         kept = os.path.join(outdir, side + "_kept_reads.bam")
-        subprocess.run([os.path.join(REF_DIR, "prep_reads"), "--sam-header", hdr, "--outfile", kept,
-                        "--index-outfile", kept + ".index", "--aux-outfile", os.path.join(outdir, side + ".info"),
-                        files[side + "_fq"]], check=True, stderr=subprocess.DEVNULL)
+        cmds.append([os.path.join(REF_DIR, "prep_reads"), "--sam-header", hdr, "--outfile", kept,
+                     "--index-outfile", kept + ".index", "--aux-outfile", os.path.join(outdir, side + ".info"), files[side + "_fq"]])
         out[side + "_reads"] = kept
         for key, name in [("mapped", side + "_kept_reads.mapped.bam")] + \
                          [("seg%d" % (k + 1), "%s_kept_reads_seg%d.bam" % (side, k + 1)) for k in range(nseg)]:
             bam = os.path.join(outdir, name)
-            subprocess.run([os.path.join(REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile",
-                            bam + ".index", files["%s_%s_sam" % (side, key)], bam], check=True,
-                           stderr=subprocess.DEVNULL)
+            cmds.append([os.path.join(REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile",
+                         bam + ".index", files["%s_%s_sam" % (side, key)], bam])
             out["%s_%s" % (side, key)] = bam
+    with ThreadPoolExecutor(max_workers=max(1, min(len(cmds), os.cpu_count() or 1))) as ex:
+        for r in ex.map(lambda c: subprocess.run(c, check=True, stderr=subprocess.DEVNULL), cmds):
+            pass
     return out
 
 

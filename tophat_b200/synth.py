@@ -846,19 +846,50 @@ def write_hits_sam(path: str, wl: Workload, side: SideData, hits: np.ndarray, se
 
 
 def write_pipeline_files(wl: Workload, outdir: str) -> Dict[str, str]:
+    """FASTA, SAM header, FASTQ and the SAM text of every hit stream; large workloads write the files in forked workers."""
     os.makedirs(outdir, exist_ok=True)
     p = {}
     p["fasta"] = os.path.join(outdir, "ref.fa"); write_fasta(p["fasta"], wl.ref)
     p["header"] = os.path.join(outdir, "hdr.sam"); write_sam_header(p["header"], wl.ref)
     nseg = len(wl.left.seg_hits)
+    jobs = []
     for sname, side in (("left", wl.left), ("right", wl.right)):
-        p[sname + "_fq"] = os.path.join(outdir, sname + ".fq"); write_fastq(p[sname + "_fq"], side)
-        p[sname + "_mapped_sam"] = os.path.join(outdir, sname + "_mapped.sam")
-        write_hits_sam(p[sname + "_mapped_sam"], wl, side, side.mapped_hits, None)
+        p[sname + "_fq"] = os.path.join(outdir, sname + ".fq"); jobs.append(("fq", p[sname + "_fq"], sname, None))
+        p[sname + "_mapped_sam"] = os.path.join(outdir, sname + "_mapped.sam"); jobs.append(("sam", p[sname + "_mapped_sam"], sname, None))
         for k in range(nseg):
             key = "%s_seg%d_sam" % (sname, k + 1)
-            p[key] = os.path.join(outdir, "%s_seg%d.sam" % (sname, k + 1))
-            write_hits_sam(p[key], wl, side, side.seg_hits[k], k)
+            p[key] = os.path.join(outdir, "%s_seg%d.sam" % (sname, k + 1)); jobs.append(("sam", p[key], sname, k))
+
+    def run(job):
+        kind, path, sname, k = job
+        side = wl.left if sname == "left" else wl.right
+        if kind == "fq":
+            write_fastq(path, side)
+        else:
+            write_hits_sam(path, wl, side, side.mapped_hits if k is None else side.seg_hits[k], k)
+
+    if wl.cfg.n_pairs < 50_000 or (os.cpu_count() or 1) < 2:
+        for j in jobs:
+            run(j)
+        return p
+    pids = []
+    limit = max(1, min(len(jobs), os.cpu_count() or 1))
+    for j in jobs:                                           # fork per file: the workload arrays are shared copy-on-write
+        while len(pids) >= limit:
+            _, st = os.wait(); pids.pop()
+            if st != 0:
+                raise RuntimeError("a writer process failed")
+        pid = os.fork()
+        if pid == 0:
+            try:
+                run(j); os._exit(0)
+            except BaseException:
+                os._exit(1)
+        pids.append(pid)
+    while pids:
+        _, st = os.wait(); pids.pop()
+        if st != 0:
+            raise RuntimeError("a writer process failed")
     return p
 
 
