@@ -678,7 +678,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                traffic = next((v for k, v in tj.get(WORKLOAD, tj).items() if k.startswith(dom + "_kernel")), None)
+                ent = tj.get(WORKLOAD, tj)
+                traffic = next((v for k, v in ent.items() if k.startswith(dom + "_kernel")), None)
+                if traffic is not None and ent.get("pairs_per_launch"):
+                    traffic = traffic * args.pairs / ent["pairs_per_launch"]       # captured at another launch size: linear in the reads
             except Exception:
                 traffic = None
         non_kernel = {"segjuncs_finish (set compaction, CUB sorts, decode, D2H of the sets)": A["finish_ms"] / steps,
@@ -693,7 +696,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                                "once outside the timed region (in the executables that is BAM decoding: see drop_in_cli)"},
                 "gpu_launches": int(A["launches"]),
                 "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peaks, "unit": "GB/s",
-                             "frac": achieved / peaks, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, per launch)" if traffic else None,
+                             "frac": achieved / peaks, "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, DRAM read + write bytes per launch, scaled linearly to this launch size)" if traffic else None,
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
                              "launches_per_step": klaunch[dom],

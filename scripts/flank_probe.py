@@ -91,7 +91,7 @@ def main():
         jn = np.stack([res.junctions[n].astype(np.int64) for n in ("ref_id", "left", "right", "antisense")], axis=1)
         dl = np.stack([res.deletions[n].astype(np.int64) for n in ("ref_id", "left", "right", "antisense")], axis=1) if len(res.deletions) else np.zeros((0, 4), np.int64)
         ins = [(int(r["ref_id"]), int(r["left"]), r["seq"].decode()) for r in res.insertions]
-        allc = flank_oracle.contigs(wl.ref.names, wl.ref.codes, int(lens.max()), 3, jn, dl, ins, np.zeros((0, 5), np.int64)) if len(contigs) <= 400_000 else None
+        allc = flank_oracle.contigs(wl.ref.names, wl.ref.codes, int(lens.max()), 3, jn, dl, ins, np.zeros((0, 5), np.int64)) if len(contigs) <= 3_000_000 else None
         if allc is not None:
             assert len(allc) == len(contigs)
             sub = [allc[int(c)]["codes"] for c in cset]
