@@ -32,3 +32,10 @@ for kw, over in [
 for name in helpers.join_golden_cases():
     helpers.check_join_golden(name)
 print("tiny caps ok: join goldens")
+import numpy as np  # noqa: E402
+import test_flank  # noqa: E402
+for nm in ("v2_101bp", "v3_two_word_contigs"):
+    seed, v, bounds, n_reads, max_hits, npol, kw = test_flank.FLANK_CASES[nm]
+    n, _ = test_flank.check_flank(test_flank.flank_case(seed, v, np.asarray(bounds), n_reads, **kw), v, max_hits, npol)
+    assert n > 40
+print("tiny caps ok: flank matcher (append buffer growth, grid-stride rounds)")

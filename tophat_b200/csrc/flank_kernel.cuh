@@ -148,50 +148,90 @@ __device__ __forceinline__ uint64_t flank_hit_key(uint32_t read, int seg, uint32
   return ((uint64_t)read << 37) | ((uint64_t)seg << 33) | ((uint64_t)contig << 8) | ((uint64_t)pos << 1) | (uint64_t)anti;
 }
 
-// thread = (read, segment, strand, piece pair)
+// lane = (read, segment, strand, piece pair) for the seed lookup; the proposed placements of the warp's 32 lookups are then
+// verified as ONE flattened list, 32 per round (buckets differ in size by orders of magnitude: a lane that walked its own bucket
+// left the other 31 idle -- 7 of 32 lanes active in the first version, profiles/r2m_ncu_table.md).
+struct FlankTask { uint64_t p0, p1, pn; uint32_t read; uint32_t info; };     // info: seg | anti << 4 | a << 5 | b << 8 | s << 11
+
 template <int CW>
-__global__ void flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
-                                   FlankIndexParams ip, FlankBatchView bv, FlankOut o)
+__global__ void __launch_bounds__(256)
+flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+                   FlankIndexParams ip, FlankBatchView bv, FlankOut o)
 {
+  __shared__ FlankTask tasks[8][32];
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const uint64_t total = (uint64_t)bv.n_reads * bv.n_segs * 2u * (uint32_t)ip.npairs;
+  const int pl = ip.piece_len; const uint64_t pm = maskn(pl);
   unsigned long long verified = 0;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-    const int pr = (int)(t % (uint32_t)ip.npairs); uint64_t r = t / (uint32_t)ip.npairs;
-    const int anti = (int)(r & 1u); r >>= 1;
-    const int seg = (int)(r % bv.n_segs); const uint32_t read = (uint32_t)(r / bv.n_segs);
-    const int s0 = bv.seg_bounds[seg], s = bv.seg_bounds[seg + 1] - s0;
-    P3 q = read_slice(bv.reads + (uint64_t)read * 3u * bv.read_words, (int)bv.read_words, s0, s);
-    if (anti) q = revcomp(q, s);
-    int a = 0, rem = pr;
-    while (rem >= ip.npieces - 1 - a) { rem -= ip.npieces - 1 - a; ++a; }
-    const int b = a + 1 + rem;
-    const int pl = ip.piece_len; const uint64_t pm = maskn(pl);
-    if ((((q.pn >> (a * pl)) | (q.pn >> (b * pl))) & pm) != 0ull) continue;       // an N in the read never matches
-    const uint32_t key = ((uint32_t)pr << ip.bbits) | flank_bucket(ip, q.p0, q.p1, a, b);
-    const uint32_t lo = __ldg(start + key), hi = __ldg(start + key + 1);
-    uint32_t* cnt = o.per_seg + (uint64_t)read * bv.n_segs + seg;
-    const uint64_t sm = maskn(s);
-    for (uint32_t e = lo; e < hi; ++e) {
-      if (((e - lo) & 63u) == 63u && *(volatile uint32_t*)cnt > (uint32_t)ip.max_hits) break;    // already suppressed by -m
-      const uint32_t v = __ldg(vals + e);
+  // task t = ((read * n_segs + seg) * 2 + anti) * npairs + pair.  64-bit divisions cost ~100 instructions each: the warp keeps
+  // (read, remainder) of its tile's first task incrementally and the lanes finish with 32-bit arithmetic on small numbers.
+  const uint32_t per_read = bv.n_segs * 2u * (uint32_t)ip.npairs;
+  const uint64_t stride = (uint64_t)gridDim.x * 256u;
+  const uint32_t stride_reads = (uint32_t)(stride / per_read), stride_rem = (uint32_t)(stride % per_read);
+  uint64_t tile = ((uint64_t)blockIdx.x * 8u + w) * 32u;
+  uint32_t read0 = (uint32_t)(tile / per_read), rem0 = (uint32_t)(tile % per_read);
+  for (; tile < total; tile += stride, read0 += stride_reads, rem0 += stride_rem) {
+    if (rem0 >= per_read) { rem0 -= per_read; ++read0; }
+    const uint64_t t = tile + lane;
+    uint32_t lo = 0, hi = 0;
+    if (t < total) {
+      const uint32_t off = rem0 + lane, dr = off / per_read, x = off - dr * per_read;
+      const uint32_t read = read0 + dr;
+      const uint32_t y = x / (uint32_t)ip.npairs;                 // (seg * 2 + anti)
+      const int pr = (int)(x - y * (uint32_t)ip.npairs), anti = (int)(y & 1u), seg = (int)(y >> 1);
+      const int s0 = bv.seg_bounds[seg], s = bv.seg_bounds[seg + 1] - s0;
+      P3 q = read_slice(bv.reads + (uint64_t)read * 3u * bv.read_words, (int)bv.read_words, s0, s);
+      if (anti) q = revcomp(q, s);
+      int a = 0, rem = pr;
+      while (rem >= ip.npieces - 1 - a) { rem -= ip.npieces - 1 - a; ++a; }
+      const int b = a + 1 + rem;
+      if ((((q.pn >> (a * pl)) | (q.pn >> (b * pl))) & pm) == 0ull) {              // an N in a seed piece of the read never matches
+        const uint32_t key = ((uint32_t)pr << ip.bbits) | flank_bucket(ip, q.p0, q.p1, a, b);
+        lo = __ldg(start + key); hi = __ldg(start + key + 1);
+      }
+      FlankTask tk; tk.p0 = q.p0; tk.p1 = q.p1; tk.pn = q.pn; tk.read = read;
+      tk.info = (uint32_t)seg | ((uint32_t)anti << 4) | ((uint32_t)a << 5) | ((uint32_t)b << 8) | ((uint32_t)s << 11);
+      tasks[w][lane] = tk;
+    }
+    const uint32_t cnt = hi - lo;
+    uint32_t incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += up; }
+    const uint32_t excl = incl - cnt;
+    const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (uint32_t j0 = 0; j0 < all; j0 += 32u) {
+      const uint32_t j = j0 + lane;
+      int owner = 0;                                                               // the last lane whose list starts at or before j
+      for (int step = 16; step; step >>= 1) {
+        const int cand = owner + step;
+        const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+        if (cand < 32 && e <= j) owner = cand;
+      }
+      const uint32_t olo = __shfl_sync(0xffffffffu, lo, owner), oex = __shfl_sync(0xffffffffu, excl, owner), ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+      if (j >= all) continue;
+      const FlankTask tk = tasks[w][owner];
+      const int seg = (int)(tk.info & 15u), anti = (int)((tk.info >> 4) & 1u), a = (int)((tk.info >> 5) & 7u), b = (int)((tk.info >> 8) & 7u), s = (int)(tk.info >> 11);
+      uint32_t* pcnt = o.per_seg + (uint64_t)tk.read * bv.n_segs + seg;
+      if (ocnt > 64u && *(volatile uint32_t*)pcnt > (uint32_t)ip.max_hits) continue;     // a big bucket of a segment already suppressed by -m
+      const uint32_t v = __ldg(vals + olo + (j - oex));
       const uint32_t c = v >> FLANK_POS_BITS; const int pos = (int)(v & ((1u << FLANK_POS_BITS) - 1u));
       const FlankSeq<CW>& cs = seq[c];
       if (pos + s > (int)cs.len) continue;
       ++verified;
       const uint64_t w0 = flank_get<CW>(cs.p0, pos, s), w1 = flank_get<CW>(cs.p1, pos, s), wn = flank_get<CW>(cs.pn, pos, s);
       if (wn != 0ull && !ip.ref_n_mismatch) continue;                              // bowtie 1: no placement over an ambiguous reference base
-      const uint64_t mism = ((w0 ^ q.p0) | (w1 ^ q.p1) | q.pn | wn) & sm;
+      const uint64_t mism = ((w0 ^ tk.p0) | (w1 ^ tk.p1) | tk.pn | wn) & maskn(s);
       const int nm = __popcll(mism);
       if (nm > ip.max_mm) continue;
-      // reported from the pair of its two first exact pieces only
-      int first = -1, second = -1;
+      int first = -1, second = -1;                                                 // reported from the pair of its two first exact pieces only
       for (int i = 0; i < ip.npieces; ++i)
         if (((mism >> (i * pl)) & pm) == 0ull) { if (first < 0) first = i; else if (second < 0) second = i; }
       if (first != a || second != b) continue;
-      atomicAdd(cnt, 1u);
+      atomicAdd(pcnt, 1u);
       const unsigned long long slot = atomicAdd(o.count, 1ull);
-      if (slot < o.cap) { o.keys[slot] = flank_hit_key(read, seg, c, pos, anti); o.mm[slot] = (uint32_t)nm; }
+      if (slot < o.cap) { o.keys[slot] = flank_hit_key(tk.read, seg, c, pos, anti); o.mm[slot] = (uint32_t)nm; }
     }
+    __syncwarp();
   }
   if (verified) atomicAdd(o.n_verified, verified);
 }

@@ -1226,6 +1226,37 @@ bool flank_fusion(uint64_t n1, uint64_t n2, uint64_t left, uint64_t right, uint3
   return g.ls < g.le && g.le <= n1 && g.rs < g.re && g.re <= n2;
 }
 
+// Pins a buffer that is gathered at random (the contig planes of the flank matcher) in the L2 for the kernels that follow on the
+// stream, while the tables that are streamed past it are marked evict-first.  bytes == 0 lifts the window again.
+void l2_persist(thb_ctx* ctx, const void* base, size_t bytes)
+{
+#ifndef THB_EMU
+  static const bool off = getenv("THB_NO_L2_PERSIST") != nullptr;
+  if (off) return;
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+  if (max_persist <= 0 || max_window <= 0) return;
+  cudaStreamAttrValue a; memset(&a, 0, sizeof a);
+  if (bytes) {
+    const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    a.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    a.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+    a.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)carve / (float)bytes;
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    a.accessPolicyWindow.num_bytes = 0;
+  }
+  cudaStreamSetAttribute(ctx->compute, cudaStreamAttributeAccessPolicyWindow, &a);
+  if (!bytes) cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+#else
+  (void)ctx; (void)base; (void)bytes;
+#endif
+}
+
 template <int CW>
 int flank_build_index(thb_ctx* ctx, uint64_t n_contigs, uint64_t n_entries, int sort_bits, uint32_t n_keys)
 {
@@ -1396,19 +1427,22 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
   unsigned long long* sc = (unsigned long long*)f.scalars.p;      // [0] appended, [1] kept, [2] verified
   unsigned long long counts[3] = {0, 0, 0};
   const uint64_t threads = nsegs_total * 2u * (uint64_t)f.ip.npairs;
+  l2_persist(ctx, f.seq.p, (size_t)f.n_contigs * (f.cw == 2 ? sizeof(FlankSeq<2>) : sizeof(FlankSeq<1>)));
   for (;;) {
     CU(f.hkeys.reserve(f.cap_hits * 8)); CU(f.hmm.reserve(f.cap_hits * 4));
     CU(cudaMemsetAsync(f.per_seg.p, 0, nsegs_total * 4, ctx->compute));
     CU(cudaMemsetAsync(sc, 0, 24, ctx->compute));
     FlankOut o{}; o.keys = (uint64_t*)f.hkeys.p; o.mm = (uint32_t*)f.hmm.p; o.count = sc; o.cap = f.cap_hits; o.per_seg = (uint32_t*)f.per_seg.p; o.n_verified = sc + 2;
-    if (f.cw == 2) flank_match_kernel<2><<<grid_for(threads, 256), 256, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
-    else           flank_match_kernel<1><<<grid_for(threads, 256), 256, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
+    const int mgrid = tiny_caps() ? 3 : grid_for(threads, 256);      // THB_TINY_CAPS: many grid-stride rounds per warp on small inputs
+    if (f.cw == 2) flank_match_kernel<2><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
+    else           flank_match_kernel<1><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
     CU(cudaGetLastError()); f.timing.launches++;
     CU(cudaMemcpyAsync(counts, sc, 24, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     if (counts[0] <= f.cap_hits) break;
     while (f.cap_hits < counts[0]) f.cap_hits *= 2;               // the append buffer was too small: repeat the batch with a larger one
   }
+  l2_persist(ctx, nullptr, 0);
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
   const uint64_t n_app = counts[0];
   uint64_t n_keep = 0;
