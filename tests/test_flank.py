@@ -216,7 +216,7 @@ FLANK_CASES = {
     "v0_exact": (14, 0, [0, 25, 50, 76], 80, 40, 0, {}),
     "v1": (15, 1, [0, 25, 50, 75, 101], 80, 40, 0, {}),
     "v3_two_word_contigs": (16, 3, [0, 30, 60, 94], 60, 40, 0, {}),
-    "v3_direct_buckets": (17, 3, [0, 20, 40], 40, 40, 0, dict(lens=(60000, 20000, 5000, 90), n_j=1500, n_d=100, n_i=100, n_f=100)),
+    "v3_direct_buckets": (17, 3, [0, 20, 40], 40, 40, 0, dict(lens=(300000, 100000, 5000, 90), n_j=7000, n_d=100, n_i=100, n_f=100)),
 }
 
 

@@ -36,7 +36,34 @@ struct FlankIndexParams {
   int bbits;                                 // bucket bits per pair
   int hashed;                                // seed code wider than bbits: bucket = mix(code) >> (64 - bbits)
   int max_mm, max_hits, ref_n_mismatch;
+  int fp_bases;                              // bases of every NON-seed piece kept in an index entry (2 bits each, <= 32 bits in all)
 };
+
+constexpr int FLANK_INLINE = 7;              // entries held in the 64-byte bucket record itself
+struct FlankBucket { uint32_t count, overflow; uint64_t e[FLANK_INLINE]; };      // overflow: index of entry #7 in the sorted entry array
+
+// The bases of the v pieces that are NOT the seed pair (a, b), fp_bases of each: piece i of them at bits [2*i*fb, 2*i*fb + fb) (plane 0)
+// and the next fb bits (plane 1).  An index entry carries this fingerprint of its contig window, so a proposed placement whose
+// non-seed pieces alone already differ from the read in more than v bases is rejected without touching the contig's planes.
+__device__ __forceinline__ uint32_t flank_fingerprint(const FlankIndexParams& ip, uint64_t p0, uint64_t p1, int a, int b)
+{
+  const int fb = ip.fp_bases, pl = ip.piece_len; const uint64_t m = maskn(fb);
+  uint32_t fp = 0; int k = 0;
+  for (int i = 0; i < ip.npieces; ++i) {
+    if (i == a || i == b) continue;
+    fp |= (uint32_t)(((p0 >> (i * pl)) & m) | (((p1 >> (i * pl)) & m) << fb)) << (2 * k * fb);
+    ++k;
+  }
+  return fp;
+}
+// mismatching bases between two fingerprints (+ the read's N bits of the same bases, gathered the same way into plane-0 positions)
+__device__ __forceinline__ int flank_fp_mismatches(const FlankIndexParams& ip, uint32_t x, uint32_t nbits)
+{
+  const int fb = ip.fp_bases; const uint32_t m = (uint32_t)maskn(fb);
+  int n = 0;
+  for (int k = 0; k < ip.npieces - 2; ++k) n += __popc((((x >> (2 * k * fb)) | (x >> (2 * k * fb + fb))) & m) | ((nbits >> (2 * k * fb)) & m));
+  return n;
+}
 
 __device__ __forceinline__ uint64_t flank_mix(uint64_t x)
 {
@@ -99,7 +126,7 @@ __global__ void flank_build_kernel(RefView ref, const FlankDesc* __restrict__ de
 // Entries whose seed pieces touch an 'N' of the contig get the key `npairs << bbits` (sorted to the end, never looked up).
 template <int CW>
 __global__ void flank_seed_kernel(const FlankSeq<CW>* __restrict__ seq, const uint64_t* __restrict__ entry_base, uint32_t n_contigs,
-                                  FlankIndexParams ip, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                                  FlankIndexParams ip, uint32_t* __restrict__ keys, uint64_t* __restrict__ vals)
 {
   for (uint32_t c = blockIdx.x; c < n_contigs; c += gridDim.x) {
     const int len = (int)seq[c].len;
@@ -116,7 +143,7 @@ __global__ void flank_seed_kernel(const FlankSeq<CW>* __restrict__ seq, const ui
       const uint64_t pm = maskn(ip.piece_len);
       const bool has_n = (((wn >> (a * ip.piece_len)) | (wn >> (b * ip.piece_len))) & pm) != 0ull;
       keys[base + t] = has_n ? ((uint32_t)ip.npairs << ip.bbits) : (((uint32_t)pr << ip.bbits) | flank_bucket(ip, w0, w1, a, b));
-      vals[base + t] = (c << FLANK_POS_BITS) | (uint32_t)o;
+      vals[base + t] = ((uint64_t)flank_fingerprint(ip, w0, w1, a, b) << 32) | (uint64_t)((c << FLANK_POS_BITS) | (uint32_t)o);
     }
   }
 }
@@ -128,6 +155,19 @@ __global__ void flank_bucket_kernel(const uint32_t* __restrict__ keys, uint64_t 
     const uint32_t hi = (i < n) ? min(keys[i], n_keys) : n_keys;
     const int64_t lo = (i == 0) ? -1 : (int64_t)min(keys[i - 1], n_keys);
     for (int64_t k = lo + 1; k <= (int64_t)hi; ++k) start[k] = (uint32_t)i;
+  }
+}
+
+// bucket records: the first FLANK_INLINE entries of a key inline, so that a lookup is ONE 64-byte gather (count + entries with their
+// fingerprints) instead of three dependent ones (range, entries, contig planes)
+__global__ void flank_fill_kernel(const uint32_t* __restrict__ start, const uint64_t* __restrict__ vals, uint32_t n_keys, FlankBucket* __restrict__ buckets)
+{
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_keys; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t lo = start[k], hi = start[k + 1];
+    FlankBucket b;
+    b.count = hi - lo; b.overflow = lo + FLANK_INLINE;
+    for (int i = 0; i < FLANK_INLINE; ++i) b.e[i] = (lo + i < hi) ? vals[lo + i] : 0ull;
+    buckets[k] = b;
   }
 }
 
@@ -148,17 +188,20 @@ __device__ __forceinline__ uint64_t flank_hit_key(uint32_t read, int seg, uint32
   return ((uint64_t)read << 37) | ((uint64_t)seg << 33) | ((uint64_t)contig << 8) | ((uint64_t)pos << 1) | (uint64_t)anti;
 }
 
-// lane = (read, segment, strand, piece pair) for the seed lookup; the proposed placements of the warp's 32 lookups are then
-// verified as ONE flattened list, 32 per round (buckets differ in size by orders of magnitude: a lane that walked its own bucket
-// left the other 31 idle -- 7 of 32 lanes active in the first version, profiles/r2m_ncu_table.md).
-struct FlankTask { uint64_t p0, p1, pn; uint32_t read; uint32_t info; };     // info: seg | anti << 4 | a << 5 | b << 8 | s << 11
+// lane = (read, segment, strand, piece pair) for the seed lookup: one 64-byte bucket record.  The proposed placements of the warp's
+// 32 lookups are then checked as ONE flattened list, 32 per round (buckets differ in size by orders of magnitude: a lane that walked
+// its own bucket left the other 31 idle -- 7 of 32 lanes active in the first version, profiles/r2m_ncu_table.md): fingerprint first,
+// the contig's planes only for the survivors.
+struct FlankTask { uint64_t p0, p1, pn; uint32_t read; uint32_t info; uint32_t fp, fpn; uint32_t overflow, pad; };
+// info: seg | anti << 4 | a << 5 | b << 8 | s << 11
 
 template <int CW>
 __global__ void __launch_bounds__(256)
-flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const FlankBucket* __restrict__ buckets, const uint64_t* __restrict__ vals,
                    FlankIndexParams ip, FlankBatchView bv, FlankOut o)
 {
   __shared__ FlankTask tasks[8][32];
+  __shared__ uint64_t inl[8][32][FLANK_INLINE];
   const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const uint64_t total = (uint64_t)bv.n_reads * bv.n_segs * 2u * (uint32_t)ip.npairs;
   const int pl = ip.piece_len; const uint64_t pm = maskn(pl);
@@ -173,7 +216,7 @@ flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restr
   for (; tile < total; tile += stride, read0 += stride_reads, rem0 += stride_rem) {
     if (rem0 >= per_read) { rem0 -= per_read; ++read0; }
     const uint64_t t = tile + lane;
-    uint32_t lo = 0, hi = 0;
+    uint32_t cnt = 0;
     if (t < total) {
       const uint32_t off = rem0 + lane, dr = off / per_read, x = off - dr * per_read;
       const uint32_t read = read0 + dr;
@@ -185,15 +228,19 @@ flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restr
       int a = 0, rem = pr;
       while (rem >= ip.npieces - 1 - a) { rem -= ip.npieces - 1 - a; ++a; }
       const int b = a + 1 + rem;
+      FlankTask tk; tk.p0 = q.p0; tk.p1 = q.p1; tk.pn = q.pn; tk.read = read; tk.overflow = 0; tk.pad = 0;
+      tk.info = (uint32_t)seg | ((uint32_t)anti << 4) | ((uint32_t)a << 5) | ((uint32_t)b << 8) | ((uint32_t)s << 11);
+      tk.fp = flank_fingerprint(ip, q.p0, q.p1, a, b); tk.fpn = flank_fingerprint(ip, q.pn, 0ull, a, b);
       if ((((q.pn >> (a * pl)) | (q.pn >> (b * pl))) & pm) == 0ull) {              // an N in a seed piece of the read never matches
         const uint32_t key = ((uint32_t)pr << ip.bbits) | flank_bucket(ip, q.p0, q.p1, a, b);
-        lo = __ldg(start + key); hi = __ldg(start + key + 1);
+        const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(buckets + key);
+        const ulonglong2 h0 = __ldg(bp), h1 = __ldg(bp + 1), h2 = __ldg(bp + 2), h3 = __ldg(bp + 3);
+        cnt = (uint32_t)h0.x; tk.overflow = (uint32_t)(h0.x >> 32);
+        uint64_t* dst = inl[w][lane];
+        dst[0] = h0.y; dst[1] = h1.x; dst[2] = h1.y; dst[3] = h2.x; dst[4] = h2.y; dst[5] = h3.x; dst[6] = h3.y;
       }
-      FlankTask tk; tk.p0 = q.p0; tk.p1 = q.p1; tk.pn = q.pn; tk.read = read;
-      tk.info = (uint32_t)seg | ((uint32_t)anti << 4) | ((uint32_t)a << 5) | ((uint32_t)b << 8) | ((uint32_t)s << 11);
       tasks[w][lane] = tk;
     }
-    const uint32_t cnt = hi - lo;
     uint32_t incl = cnt;
     for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += up; }
     const uint32_t excl = incl - cnt;
@@ -207,13 +254,16 @@ flank_match_kernel(const FlankSeq<CW>* __restrict__ seq, const uint32_t* __restr
         const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
         if (cand < 32 && e <= j) owner = cand;
       }
-      const uint32_t olo = __shfl_sync(0xffffffffu, lo, owner), oex = __shfl_sync(0xffffffffu, excl, owner), ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+      const uint32_t oex = __shfl_sync(0xffffffffu, excl, owner), ocnt = __shfl_sync(0xffffffffu, cnt, owner);
       if (j >= all) continue;
-      const FlankTask tk = tasks[w][owner];
+      const FlankTask& tk = tasks[w][owner];
       const int seg = (int)(tk.info & 15u), anti = (int)((tk.info >> 4) & 1u), a = (int)((tk.info >> 5) & 7u), b = (int)((tk.info >> 8) & 7u), s = (int)(tk.info >> 11);
       uint32_t* pcnt = o.per_seg + (uint64_t)tk.read * bv.n_segs + seg;
       if (ocnt > 64u && *(volatile uint32_t*)pcnt > (uint32_t)ip.max_hits) continue;     // a big bucket of a segment already suppressed by -m
-      const uint32_t v = __ldg(vals + olo + (j - oex));
+      const uint32_t idx = j - oex;
+      const uint64_t ent = idx < (uint32_t)FLANK_INLINE ? inl[w][owner][idx] : __ldg(vals + tk.overflow + (idx - FLANK_INLINE));
+      if (flank_fp_mismatches(ip, (uint32_t)(ent >> 32) ^ tk.fp, tk.fpn) > ip.max_mm) continue;
+      const uint32_t v = (uint32_t)ent;
       const uint32_t c = v >> FLANK_POS_BITS; const int pos = (int)(v & ((1u << FLANK_POS_BITS) - 1u));
       const FlankSeq<CW>& cs = seq[c];
       if (pos + s > (int)cs.len) continue;

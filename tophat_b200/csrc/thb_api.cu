@@ -83,12 +83,12 @@ struct Nccl {
 
 // junction-flank matcher (thb_flank_*)
 struct FlankState {
-  DevBuf desc, seq, base, keys, vals, keys2, vals2, start, reads, hkeys, hmm, hkeys2, hmm2, per_seg, out, scalars, cdesc, jout;
+  DevBuf desc, seq, base, keys, vals, keys2, vals2, start, buckets, reads, hkeys, hmm, hkeys2, hmm2, per_seg, out, scalars, cdesc, jout;
   std::vector<thb_flank_contig> contigs; PinnedVec<thb_flank_hit> hits; PinnedVec<thb_jhit_full> jhits;
   FlankBatchView last_bv{}; uint64_t last_n = 0; bool have_last = false;
   FlankIndexParams ip{}; int cw = 1; bool begun = false; uint64_t n_contigs = 0, n_entries = 0, cap_hits = 0;
   int min_seg_len = 0, max_seg_len = 0; thb_flank_timing timing{};
-  void release() { for (DevBuf* b : { &desc, &seq, &base, &keys, &vals, &keys2, &vals2, &start, &reads, &hkeys, &hmm, &hkeys2, &hmm2, &per_seg, &out, &scalars, &cdesc, &jout }) b->release(); hits.release(); jhits.release(); }
+  void release() { for (DevBuf* b : { &desc, &seq, &base, &keys, &vals, &keys2, &vals2, &start, &buckets, &reads, &hkeys, &hmm, &hkeys2, &hmm2, &per_seg, &out, &scalars, &cdesc, &jout }) b->release(); hits.release(); jhits.release(); }
 };
 
 }  // namespace
@@ -1249,8 +1249,11 @@ void l2_persist(thb_ctx* ctx, const void* base, size_t bytes)
   } else {
     a.accessPolicyWindow.num_bytes = 0;
   }
-  cudaStreamSetAttribute(ctx->compute, cudaStreamAttributeAccessPolicyWindow, &a);
+  const cudaError_t e1 = cudaStreamSetAttribute(ctx->compute, cudaStreamAttributeAccessPolicyWindow, &a);
   if (!bytes) cudaCtxResetPersistingL2Cache();
+  static const bool trace = getenv("THB_TRACE") != nullptr;
+  if (trace && bytes) fprintf(stderr, "[thb trace] L2 window: %zu bytes, max persisting %d, max window %d, hit ratio %.2f, set: %s\n", bytes, max_persist, max_window,
+                              a.accessPolicyWindow.hitRatio, cudaGetErrorString(e1));
   cudaGetLastError();
 #else
   (void)ctx; (void)base; (void)bytes;
@@ -1264,15 +1267,17 @@ int flank_build_index(thb_ctx* ctx, uint64_t n_contigs, uint64_t n_entries, int 
   flank_build_kernel<CW><<<grid_for(n_contigs, 128), 128, 0, ctx->compute>>>(ctx->ref, (const FlankDesc*)f.desc.p, (FlankSeq<CW>*)f.seq.p, (uint32_t)n_contigs);
   CU(cudaGetLastError());
   flank_seed_kernel<CW><<<(unsigned)std::min<uint64_t>(n_contigs, (uint64_t)ctx->sms * 64), 64, 0, ctx->compute>>>(
-      (const FlankSeq<CW>*)f.seq.p, (const uint64_t*)f.base.p, (uint32_t)n_contigs, f.ip, (uint32_t*)f.keys.p, (uint32_t*)f.vals.p);
+      (const FlankSeq<CW>*)f.seq.p, (const uint64_t*)f.base.p, (uint32_t)n_contigs, f.ip, (uint32_t*)f.keys.p, (uint64_t*)f.vals.p);
   CU(cudaGetLastError());
   size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint32_t*)f.vals.p, (uint32_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint64_t*)f.vals.p, (uint64_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute);
   CU(ctx->d_cub_tmp.reserve(tmp + 16));
-  CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint32_t*)f.vals.p, (uint32_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute));
+  CU(cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, tmp, (const uint32_t*)f.keys.p, (uint32_t*)f.keys2.p, (const uint64_t*)f.vals.p, (uint64_t*)f.vals2.p, (int)n_entries, 0, sort_bits, ctx->compute));
   flank_bucket_kernel<<<grid_for(n_entries + 1, 256), 256, 0, ctx->compute>>>((const uint32_t*)f.keys2.p, n_entries, n_keys, (uint32_t*)f.start.p);
   CU(cudaGetLastError());
-  f.timing.launches = 4;
+  flank_fill_kernel<<<grid_for(n_keys, 256), 256, 0, ctx->compute>>>((const uint32_t*)f.start.p, (const uint64_t*)f.vals2.p, n_keys, (FlankBucket*)f.buckets.p);
+  CU(cudaGetLastError());
+  f.timing.launches = 5;
   return THB_OK;
 }
 
@@ -1353,8 +1358,10 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   ip.npieces = npieces; ip.piece_len = P->min_seg_len / npieces; if (ip.piece_len > 16) ip.piece_len = 16;
   ip.npairs = npieces * (npieces - 1) / 2; ip.smin = P->min_seg_len;
   ip.max_mm = P->max_mismatches; ip.max_hits = P->max_multihits; ip.ref_n_mismatch = P->ref_n_is_mismatch ? 1 : 0;
-  int bb = 10; while (bb < 24 && (1ull << bb) < 2 * n_off) ++bb;
+  // ~4 entries per 64-byte bucket record on average (7 fit inline); 2^23 buckets per pair at most (0.5 GB of records per pair)
+  int bb = 8; while (bb < 23 && (4ull << bb) < n_off) ++bb;
   if (4 * ip.piece_len <= bb) { ip.bbits = 4 * ip.piece_len; ip.hashed = 0; } else { ip.bbits = bb; ip.hashed = 1; }
+  ip.fp_bases = P->max_mismatches ? std::min(ip.piece_len, 16 / P->max_mismatches) : 0;
   f.ip = ip; f.cw = max_len > 64 ? 2 : 1; f.n_contigs = nc;
   const uint64_t n_entries = n_off * (uint64_t)ip.npairs;
   if (n_entries >= 0x7fffffffull) return fail(ctx, THB_EUNSUPPORTED, "thb_flank_begin: %llu index entries (limit 2^31)", (unsigned long long)n_entries);
@@ -1366,8 +1373,8 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   int sort_bits = ip.bbits; while ((1u << (sort_bits - ip.bbits)) <= (uint32_t)ip.npairs) ++sort_bits;
   CU(f.desc.reserve(nc * sizeof(FlankDesc))); CU(f.base.reserve((nc + 1) * 8));
   CU(f.seq.reserve(nc * (f.cw == 2 ? sizeof(FlankSeq<2>) : sizeof(FlankSeq<1>))));
-  CU(f.keys.reserve(n_entries * 4)); CU(f.vals.reserve(n_entries * 4)); CU(f.keys2.reserve(n_entries * 4)); CU(f.vals2.reserve(n_entries * 4));
-  CU(f.start.reserve(((uint64_t)n_keys + 2) * 4));
+  CU(f.keys.reserve(n_entries * 4)); CU(f.vals.reserve(n_entries * 8)); CU(f.keys2.reserve(n_entries * 4)); CU(f.vals2.reserve(n_entries * 8));
+  CU(f.start.reserve(((uint64_t)n_keys + 2) * 4)); CU(f.buckets.reserve((uint64_t)n_keys * sizeof(FlankBucket)));
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   CU(cudaMemcpyAsync(f.desc.p, desc.data(), nc * sizeof(FlankDesc), cudaMemcpyHostToDevice, ctx->compute));
   CU(cudaMemcpyAsync(f.base.p, base.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->compute));
@@ -1378,7 +1385,7 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   CU(cudaEventRecord(ctx->ev_b, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));      // desc / base are host vectors of this call
   CU(cudaEventElapsedTime(&f.timing.index_ms, ctx->ev_a, ctx->ev_b));
-  f.keys.release(); f.vals.release(); f.keys2.release(); f.desc.release(); f.base.release();      // the search needs seq, start and the sorted values
+  f.keys.release(); f.vals.release(); f.keys2.release(); f.desc.release(); f.base.release(); f.start.release();      // the search needs seq, the bucket records and the sorted entries (overflow)
   f.begun = true;
   return THB_OK;
 }
@@ -1434,8 +1441,8 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
     CU(cudaMemsetAsync(sc, 0, 24, ctx->compute));
     FlankOut o{}; o.keys = (uint64_t*)f.hkeys.p; o.mm = (uint32_t*)f.hmm.p; o.count = sc; o.cap = f.cap_hits; o.per_seg = (uint32_t*)f.per_seg.p; o.n_verified = sc + 2;
     const int mgrid = tiny_caps() ? 3 : grid_for(threads, 256);      // THB_TINY_CAPS: many grid-stride rounds per warp on small inputs
-    if (f.cw == 2) flank_match_kernel<2><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
-    else           flank_match_kernel<1><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const uint32_t*)f.start.p, (const uint32_t*)f.vals2.p, f.ip, bv, o);
+    if (f.cw == 2) flank_match_kernel<2><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<2>*)f.seq.p, (const FlankBucket*)f.buckets.p, (const uint64_t*)f.vals2.p, f.ip, bv, o);
+    else           flank_match_kernel<1><<<mgrid, 256, 0, ctx->compute>>>((const FlankSeq<1>*)f.seq.p, (const FlankBucket*)f.buckets.p, (const uint64_t*)f.vals2.p, f.ip, bv, o);
     CU(cudaGetLastError()); f.timing.launches++;
     CU(cudaMemcpyAsync(counts, sc, 24, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
