@@ -1226,40 +1226,6 @@ bool flank_fusion(uint64_t n1, uint64_t n2, uint64_t left, uint64_t right, uint3
   return g.ls < g.le && g.le <= n1 && g.rs < g.re && g.re <= n2;
 }
 
-// Pins a buffer that is gathered at random (the contig planes of the flank matcher) in the L2 for the kernels that follow on the
-// stream, while the tables that are streamed past it are marked evict-first.  bytes == 0 lifts the window again.
-void l2_persist(thb_ctx* ctx, const void* base, size_t bytes)
-{
-#ifndef THB_EMU
-  static const bool off = getenv("THB_NO_L2_PERSIST") != nullptr;
-  if (off) return;
-  int max_persist = 0, max_window = 0;
-  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-  if (max_persist <= 0 || max_window <= 0) return;
-  cudaStreamAttrValue a; memset(&a, 0, sizeof a);
-  if (bytes) {
-    const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-    a.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    a.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
-    a.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)carve / (float)bytes;
-    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  } else {
-    a.accessPolicyWindow.num_bytes = 0;
-  }
-  const cudaError_t e1 = cudaStreamSetAttribute(ctx->compute, cudaStreamAttributeAccessPolicyWindow, &a);
-  if (!bytes) cudaCtxResetPersistingL2Cache();
-  static const bool trace = getenv("THB_TRACE") != nullptr;
-  if (trace && bytes) fprintf(stderr, "[thb trace] L2 window: %zu bytes, max persisting %d, max window %d, hit ratio %.2f, set: %s\n", bytes, max_persist, max_window,
-                              a.accessPolicyWindow.hitRatio, cudaGetErrorString(e1));
-  cudaGetLastError();
-#else
-  (void)ctx; (void)base; (void)bytes;
-#endif
-}
-
 template <int CW>
 int flank_build_index(thb_ctx* ctx, uint64_t n_contigs, uint64_t n_entries, int sort_bits, uint32_t n_keys)
 {
@@ -1359,7 +1325,8 @@ int thb_flank_begin(thb_ctx* ctx, const thb_flank_params* P,
   ip.npairs = npieces * (npieces - 1) / 2; ip.smin = P->min_seg_len;
   ip.max_mm = P->max_mismatches; ip.max_hits = P->max_multihits; ip.ref_n_mismatch = P->ref_n_is_mismatch ? 1 : 0;
   // ~4 entries per 64-byte bucket record on average (7 fit inline); 2^23 buckets per pair at most (0.5 GB of records per pair)
-  int bb = 8; while (bb < 23 && (4ull << bb) < n_off) ++bb;
+  static const int bb_max = getenv("THB_FLANK_BBITS") ? atoi(getenv("THB_FLANK_BBITS")) : 23;      // measurement knob
+  int bb = 8; while (bb < bb_max && (4ull << bb) < n_off) ++bb;
   if (4 * ip.piece_len <= bb) { ip.bbits = 4 * ip.piece_len; ip.hashed = 0; } else { ip.bbits = bb; ip.hashed = 1; }
   ip.fp_bases = P->max_mismatches ? std::min(ip.piece_len, 16 / P->max_mismatches) : 0;
   f.ip = ip; f.cw = max_len > 64 ? 2 : 1; f.n_contigs = nc;
@@ -1434,7 +1401,6 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
   unsigned long long* sc = (unsigned long long*)f.scalars.p;      // [0] appended, [1] kept, [2] verified
   unsigned long long counts[3] = {0, 0, 0};
   const uint64_t threads = nsegs_total * 2u * (uint64_t)f.ip.npairs;
-  l2_persist(ctx, f.seq.p, (size_t)f.n_contigs * (f.cw == 2 ? sizeof(FlankSeq<2>) : sizeof(FlankSeq<1>)));
   for (;;) {
     CU(f.hkeys.reserve(f.cap_hits * 8)); CU(f.hmm.reserve(f.cap_hits * 4));
     CU(cudaMemsetAsync(f.per_seg.p, 0, nsegs_total * 4, ctx->compute));
@@ -1449,7 +1415,6 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
     if (counts[0] <= f.cap_hits) break;
     while (f.cap_hits < counts[0]) f.cap_hits *= 2;               // the append buffer was too small: repeat the batch with a larger one
   }
-  l2_persist(ctx, nullptr, 0);
   CU(cudaEventRecord(ctx->ev_c, ctx->compute));
   const uint64_t n_app = counts[0];
   uint64_t n_keep = 0;
