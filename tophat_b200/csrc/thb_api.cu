@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include "../../include/tophat_b200.h"
 #include "segjuncs_kernel.cuh"
 #include "scan_tile_kernel.cuh"
@@ -117,6 +118,7 @@ struct thb_ctx {
   DevBuf d_keys, d_keys_sorted, d_cub_tmp, d_decoded, d_count;
   // task queues of the scan phase
   DevBuf ag_send, ag_recv;
+  const uint64_t* ag_keys[2] = {nullptr, nullptr}; uint64_t ag_n[2] = {0, 0};     // after the all-gather: every rank's junction / deletion keys (HS_EMPTY padded)
   DevBuf q_win, q_indel, q_rescue, q_rescue_out, q_rbundle, q_bstate, q_owner;
   uint64_t cap_win = 0, cap_indel = 0;
   unsigned long long* d_qcounts = nullptr; unsigned int* d_qovf = nullptr;
@@ -304,6 +306,7 @@ int validate_batch(thb_ctx* ctx, const thb_segjuncs_batch* b)
 {
   if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
   if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  if (ctx->ag_keys[0]) return fail(ctx, THB_ESTATE, "batch submitted after thb_segjuncs_allgather (the exchange closes the pass)");
   if (b->n_segs < 1 || b->n_segs > (uint32_t)THB_MAX_SEGS) return fail(ctx, THB_EUNSUPPORTED, "n_segs %u outside [1,%d]", b->n_segs, THB_MAX_SEGS);
   if (b->n_bundles >= (1u << 28)) return fail(ctx, THB_EUNSUPPORTED, "more than 2^28 bundles in one batch");
   if (b->read_words < 1 || b->read_words > 4) return fail(ctx, THB_EUNSUPPORTED, "read_words %u outside [1,4] (reads up to 255 bp)", b->read_words);
@@ -647,6 +650,7 @@ int thb_segjuncs_begin(thb_ctx* ctx, const thb_params* p)
   ctx->own_launches = 2;            // the two hs_clear launches above
   ctx->h_ins_count = 0; ctx->h_fus_count = 0;
   ctx->n_bundles_total = ctx->n_hits_total = ctx->n_partner_total = 0; ctx->n_ins_out = ctx->n_del_out = 0;
+  ctx->ag_keys[0] = ctx->ag_keys[1] = nullptr; ctx->ag_n[0] = ctx->ag_n[1] = 0;
   ctx->begun = true;
   return THB_OK;
 }
@@ -769,25 +773,52 @@ struct Trace {
   ~Trace() { if (on && !line.empty()) fprintf(stderr, "[thb trace ms]%s\n", line.c_str()); }
 };
 
-static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit, Trace* tr = nullptr)
+static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit, Trace* tr = nullptr,
+                      const uint64_t* gathered = nullptr, uint64_t n_gathered = 0)
 {
-  CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8)); CU(ctx->d_count.reserve(64));
-  CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
-  hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, (unsigned long long*)ctx->d_count.p);
-  CU(cudaGetLastError()); ctx->own_launches++;
+  CU(ctx->d_count.reserve(64));
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
-  if (tr) tr->mark("compact");
-  out.clear();
-  if (n == 0) return THB_OK;
+  const uint64_t* sorted = nullptr;
   size_t tmp = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute);
-  CU(ctx->d_cub_tmp.reserve(tmp + 16));
-  CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute));
+  if (gathered) {
+    // after thb_segjuncs_allgather: the union is the sorted, de-duplicated concatenation of every rank's keys -- one radix sort and
+    // one unique pass instead of world x keys random inserts into a hash set sized for all of them
+    out.clear();
+    if (n_gathered == 0) return THB_OK;
+    CU(ctx->d_keys.reserve(n_gathered * 8)); CU(ctx->d_keys_sorted.reserve(n_gathered * 8));
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, gathered, (uint64_t*)ctx->d_keys.p, (int)n_gathered, 0, 64, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, gathered, (uint64_t*)ctx->d_keys.p, (int)n_gathered, 0, 64, ctx->compute));
+    tmp = 0;
+    cub::DeviceSelect::Unique(nullptr, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (unsigned long long*)ctx->d_count.p, (int)n_gathered, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceSelect::Unique(ctx->d_cub_tmp.p, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (unsigned long long*)ctx->d_count.p, (int)n_gathered, ctx->compute));
+    uint64_t last = 0;
+    CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (n) { CU(cudaMemcpy(&last, (const uint64_t*)ctx->d_keys_sorted.p + (n - 1), 8, cudaMemcpyDeviceToHost)); if (last == HS_EMPTY) --n; }    // the padding
+    ctx->own_launches += 2;
+    if (tr) tr->mark("sort+unique(gathered)");
+    if (n == 0) return THB_OK;
+    sorted = (const uint64_t*)ctx->d_keys_sorted.p;
+  } else {
+    CU(ctx->d_keys.reserve(cap * 8)); CU(ctx->d_keys_sorted.reserve(cap * 8));
+    CU(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->compute));
+    hs_compact_kernel<<<grid_for(cap, 256), 256, 0, ctx->compute>>>((const uint64_t*)set.p, cap, (uint64_t*)ctx->d_keys.p, (unsigned long long*)ctx->d_count.p);
+    CU(cudaGetLastError()); ctx->own_launches++;
+    CU(cudaMemcpyAsync(&n, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (tr) tr->mark("compact");
+    out.clear();
+    if (n == 0) return THB_OK;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, (const uint64_t*)ctx->d_keys.p, (uint64_t*)ctx->d_keys_sorted.p, (int)n, 0, 64, ctx->compute));
+    sorted = (const uint64_t*)ctx->d_keys_sorted.p;
+  }
   if (n > limit) n = limit;       // std::set capped at max_seg_juncs by erasing the largest (1692-1693)
   CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
-  decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_keys_sorted.p, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
+  decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>(sorted, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
   CU(cudaGetLastError()); ctx->own_launches++;
   if (tr) tr->mark("sort+decode(enqueue)");
   CU(out.resize(n));
@@ -806,8 +837,8 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   Trace tr;
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   int rc;
-  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull, &tr))) return rc;
-  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull, &tr))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull, &tr, ctx->ag_keys[0], ctx->ag_n[0]))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull, &tr, ctx->ag_keys[1], ctx->ag_n[1]))) return rc;
   // insertions: first inserted wins among equal (ref, left, length) -- insertions.h:52-67
   unsigned long long nins = 0;
   CU(cudaMemcpyAsync(&nins, ctx->d_ins_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -1570,11 +1601,11 @@ int thb_segjuncs_allgather(thb_ctx* ctx)
   if (mx[3]) e |= ctx->nccl.AllGather(send + sj + sd + si, rf, mx[3] * 4, 5, ctx->comm, ctx->compute);
   if (ctx->nccl.GroupEnd) e |= ctx->nccl.GroupEnd();
   if (e != 0) return fail(ctx, THB_ENCCL, "ncclAllGather(payload)");
-  int rc;
-  while (ctx->cap_juncs < 2 * tot[0]) { if ((rc = grow_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs))) return rc; }
-  while (ctx->cap_dels < 2 * tot[1]) { if ((rc = grow_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels))) return rc; }
-  if (mx[0]) { hs_insert_list_kernel<<<grid_for(mx[0] * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)rj, mx[0] * W, make_set(ctx->d_juncs, ctx->cap_juncs, ctx->d_ovf_juncs)); ctx->own_launches++; }
-  if (mx[1]) { hs_insert_list_kernel<<<grid_for(mx[1] * W, 256), 256, 0, ctx->compute>>>((const uint64_t*)rd, mx[1] * W, make_set(ctx->d_dels, ctx->cap_dels, ctx->d_ovf_dels)); ctx->own_launches++; }
+  // the key sets are NOT re-inserted into the hash sets: thb_segjuncs_finish sorts and de-duplicates the gathered lists (which
+  // contain this rank's own keys as well)
+  ctx->ag_keys[0] = (const uint64_t*)rj; ctx->ag_n[0] = mx[0] * W; ctx->ag_keys[1] = (const uint64_t*)rd; ctx->ag_n[1] = mx[1] * W;
+  if (!mx[0]) ctx->ag_keys[0] = (const uint64_t*)recv;       // empty everywhere: still "gathered" (n = 0)
+  if (!mx[1]) ctx->ag_keys[1] = (const uint64_t*)recv;
   if (mx[2]) {
     if (tot[2] > ctx->cap_ins) {                                   // the gathered records replace the local buffer
       ctx->d_ins.release(); ctx->cap_ins = tot[2] + 1024; CU(ctx->d_ins.reserve(ctx->cap_ins * sizeof(InsRec)));
