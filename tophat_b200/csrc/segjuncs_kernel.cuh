@@ -28,6 +28,7 @@ namespace thb {
 
 // ---------------------------------------------------------------------------------------------
 constexpr uint64_t HS_EMPTY = ~0ull;
+constexpr int HS_MAX_PROBES = 24;
 constexpr int      MAX_SEGS = 16;
 constexpr int      RES_MAX  = 64;       // rescued mate-anchor hits kept per read (bowtie2 guard is 40)
 
@@ -53,7 +54,9 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 __device__ __forceinline__ void hs_insert(const HashSet& hs, uint64_t key)
 {
   uint64_t h = mix64(key) & hs.mask;
-  for (int probe = 0; probe < 256; ++probe) {
+  // a probe run this long means the table is too full to be fast (linear probing: ~0.5 load): report overflow, the host doubles the
+  // table and repeats the scan of the batch -- the larger table stays for the following batches and passes
+  for (int probe = 0; probe < HS_MAX_PROBES; ++probe) {
     uint64_t cur = __ldcg(hs.slots + h);
     if (cur == key) return;
     if (cur == HS_EMPTY) {
