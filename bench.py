@@ -229,13 +229,16 @@ def run_reference_arm(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+HOST_HANDOFF = False
+
+
 def workload_config(pairs: int, world: int, note: str = ""):
     what = {"chr20": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, ",
             "hg38": "BASELINE configs[2] sharded by read (50 M pairs over 8 GPUs = 6.25 M per GPU): synthetic 2x101 bp pairs, hg38-sized reference "
                     "(24 contigs, 3.09 Gbp, 0.5% N; 1.2 GB image, not L2-resident), ",
             "indel": "BASELINE configs[3]: indel-heavy synthetic 2x101 bp pairs (1-3 bp indel in half of the mates), chr20-sized reference, "}[WORKLOAD]
     c = {"workload": what + "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
-         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)",
+         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)", "handoff": "host" if HOST_HANDOFF else "device-resident sets (value arm); host arrays (e2e arm)",
          "l2": "inputs (>1 GB per step at the default size) exceed the 126 MB L2; no explicit flush",
          "parallelism": "read-shard x%d%s" % (world, " + NCCL all-gather of the junction/indel sets" if world > 1 else "")}
     if note:
@@ -499,7 +502,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             ctx.segjuncs_allgather()
         # copy=False (every step but the last): the C call alone -- the result sets land in the library's page-locked arrays either way,
         # building numpy views of them is the harness's business, not the path's
-        res = ctx.segjuncs_finish(True) if copy else ctx.segjuncs_finish_raw()
+        if device_resident and not args.host_handoff:
+            res = ctx.segjuncs_finish_resident()      # sets stay on the device for thb_join_begin_resident; their download runs behind stage 2
+        else:
+            res = ctx.segjuncs_finish(True) if copy else ctx.segjuncs_finish_raw()
         return res, ctx.timing()
 
     # stage 2 inputs: the junction-index segment hits depend on the junction set stage 1 finds (tophat.py:3686-3741 runs
@@ -536,16 +542,26 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 clock("segjuncs_submit", lambda: ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit"))
         if world > 1:
             clock("allgather", ctx.segjuncs_allgather)
-        res = clock("segjuncs_finish", ctx.segjuncs_finish, True) if copy else clock("segjuncs_finish", ctx.segjuncs_finish_raw)
+        if device_resident and not args.host_handoff:
+            res = clock("segjuncs_finish", ctx.segjuncs_finish_resident)
+        else:
+            res = clock("segjuncs_finish", ctx.segjuncs_finish, True) if copy else clock("segjuncs_finish", ctx.segjuncs_finish_raw)
         return res, ctx.timing()
 
     def step(device_resident: bool, copy: bool = False):
+        resident = device_resident and not args.host_handoff
         if args.breakdown:
             res, tm = segjuncs_pass_timed(device_resident, copy)
-            clock("join_begin", ctx.join_begin, P, jsets[0], jsets[1])
+            if resident:
+                clock("join_begin", ctx.join_begin_resident, P)
+            else:
+                clock("join_begin", ctx.join_begin, P, jsets[0], jsets[1])
         else:
             res, tm = segjuncs_pass(device_resident, copy)
-            ctx.join_begin(P, jsets[0], jsets[1])
+            if resident:
+                ctx.join_begin_resident(P)
+            else:
+                ctx.join_begin(P, jsets[0], jsets[1])
         n_joined, d2h = 0, 0
         for i in range(len(jbatches)):
             if device_resident:
@@ -554,6 +570,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 out = C.c_void_p(); n = C.c_uint64()
                 ctx._check(ctx.lib.thb_join_submit(ctx.h, C.byref(j_host[i]), C.byref(out), C.byref(n)), "thb_join_submit")
                 n_joined += int(n.value); d2h += int(n.value) * 128
+        if resident:
+            clock("segjuncs_fetch", ctx.segjuncs_fetch) if args.breakdown else ctx.segjuncs_fetch()      # the sets are on the host when the step ends
         return res, tm, ctx.join_timing(), n_joined, d2h
 
     def timed(device_resident: bool, steps: int, warmup: int):
@@ -684,9 +702,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                     traffic = traffic * args.pairs / ent["pairs_per_launch"]       # captured at another launch size: linear in the reads
             except Exception:
                 traffic = None
-        non_kernel = {"segjuncs_finish (set compaction, CUB sorts, decode, D2H of the sets)": A["finish_ms"] / steps,
-                      "join_begin (set upload, validation, bucket index build)": A["begin_ms"] / steps}
-        non_kernel["other (queue counters read back, launch gaps, Python between calls)"] = max(0.0, per_step - tot_ms - sum(non_kernel.values()))
+        if args.host_handoff:
+            non_kernel = {"segjuncs_finish (set compaction, CUB sorts, decode, D2H of the sets)": A["finish_ms"] / steps,
+                          "join_begin (set upload, validation, bucket index build)": A["begin_ms"] / steps}
+        else:
+            non_kernel = {"segjuncs_finish_resident (set compaction, CUB sorts, decode; the D2H of the sets runs behind stage 2)": A["finish_ms"] / steps,
+                          "join_begin_resident (device-to-device hand-off of the sets, validation, bucket index build)": A["begin_ms"] / steps}
+        non_kernel["other (queue counters read back, launch gaps, wait for the sets' download, Python between calls)"] = max(0.0, per_step - tot_ms - sum(non_kernel.values()))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(args.pairs, world),
@@ -800,11 +822,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--analytic-join-inputs", action="store_true",
                     help="place the spliced segments of stage 2 analytically (round 1) instead of through the junction-flank matcher")
+    ap.add_argument("--host-handoff", action="store_true",
+                    help="device-resident arm: hand the sets from stage 1 to stage 2 through the host (thb_segjuncs_finish + thb_join_begin) "
+                         "instead of thb_segjuncs_finish_resident + thb_join_begin_resident")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank on all CPUs instead of its GPU's NUMA node")
     ap.add_argument("--breakdown", action="store_true", help="also report the host wall clock of every C-ABI call kind (device-resident pass)")
     args = ap.parse_args()
-    global WORKLOAD
+    global WORKLOAD, HOST_HANDOFF
     WORKLOAD = args.workload
+    HOST_HANDOFF = bool(args.host_handoff)
     if args.pairs <= 0:
         args.pairs = default_pairs(WORKLOAD)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -209,6 +209,11 @@ int thb_segjuncs_submit_device(thb_ctx* ctx, const thb_segjuncs_batch* device_ba
  * first-wins, the max_seg_juncs cap of 58/1692-1693) and returns host pointers owned by ctx,
  * valid until the next thb_segjuncs_begin / thb_destroy.                                       */
 int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out);
+/* thb_segjuncs_finish in two halves, for a caller that goes on with the device-resident sets (thb_join_begin_resident, thb_flank_begin
+ * on the host arrays later): _finish_resident builds the sets on the device, fills the counts and the pointers of `out` and queues
+ * the download of the arrays on a copy stream WITHOUT waiting for it; the arrays are valid once thb_segjuncs_fetch has returned. */
+int thb_segjuncs_finish_resident(thb_ctx* ctx, thb_segjuncs_results* out);
+int thb_segjuncs_fetch(thb_ctx* ctx);
 
 /* Multi-GPU exchange (replaces the per-thread set union at 4911-4922): all-gathers the
  * de-duplicated junction/deletion/insertion/fusion sets of every rank over NCCL and merges them,
@@ -304,6 +309,9 @@ typedef struct thb_joined {        /* the BowtieHit merge_chain returns         
  * insertion set (2952-2980).  Arrays must be sorted and unique in the reference's set orders.                */
 int thb_join_begin(thb_ctx* ctx, const thb_params* params, const thb_junction* juncs, uint64_t n_juncs,
                    const thb_insertion* insertions, uint64_t n_insertions);
+/* Same with the sets of the segment_juncs pass this context has just finished (thb_segjuncs_finish or _finish_resident), taken where they
+ * lie in device memory: junctions and deletions merged into one Junction-ordered set (deletions with antisense = false), insertions. */
+int thb_join_begin_resident(thb_ctx* ctx, const thb_params* params);
 /* --fusion-search (params->fusion_search != 0 in thb_join_begin): the fusion set of long_spanning_reads.cpp:2996-3040, sorted and
  * unique in Fusion order (refid1, refid2, left, right, dir; fusions.h:40-70); count / edit_dist of the records are ignored.
  * Call after thb_join_begin; thb_join_begin resets the set to empty.                                                          */

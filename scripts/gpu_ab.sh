@@ -19,7 +19,7 @@ i=0
 for v in "${VS[@]}"; do
   i=$((i+1))
   ( if [ "$v" != "none" ]; then for kv in $v; do export "$kv"; done; fi
-    timeout 900 python bench.py --workload $WL --pairs $PAIRS --steps 5 --no-cpu-baseline --parity-pairs 50000 --breakdown > gpurun_out/bench_${TAG}_v$i.json 2> gpurun_out/bench_${TAG}_v$i.err; echo "variant $i [$v] exit $?" )
+    timeout 900 python bench.py --workload $WL --pairs $PAIRS --steps 5 --no-cpu-baseline --parity-pairs 50000 --breakdown $THB_BENCH_EXTRA > gpurun_out/bench_${TAG}_v$i.json 2> gpurun_out/bench_${TAG}_v$i.err; echo "variant $i [$v] exit $?" )
   show gpurun_out/bench_${TAG}_v$i.json
 done
 if [ -n "$KRE" ]; then

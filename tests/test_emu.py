@@ -264,3 +264,8 @@ def test_emu_flank_pipeline_matches_reference_binaries(emu_lib):
     """stage 1 -> junction-flank matcher -> join, against segment_juncs -> juncs_db -> long_spanning_reads of the reference"""
     import test_flank
     assert test_flank.flank_pipeline_check() > 500
+
+
+def test_emu_resident_handoff_equals_host_handoff(emu_lib):
+    import test_gpu_join
+    assert test_gpu_join.resident_handoff_check() > 1000

@@ -226,3 +226,48 @@ def test_join_guards_and_budget():
 @pytest.mark.parametrize("name", helpers.join_golden_cases())
 def test_join_matches_reference_golden(name):
     helpers.check_join_golden(name)
+
+
+def resident_handoff_check(n_pairs=1500, seed=353):
+    """thb_segjuncs_finish_resident + thb_join_begin_resident (sets never leave the device) against thb_segjuncs_finish +
+    thb_join_begin with the host arrays: same sets after thb_segjuncs_fetch, same joined records; with deletions and insertions
+    in the sets (the junction / deletion merge) and without."""
+    total = 0
+    for indel_prob in (0.4, 0.0):
+        wl = synth.generate(synth.SynthConfig(keep_candidates=True, contig_lens=(200_000, 80_000), n_pairs=n_pairs, seed=seed, indel_prob=indel_prob))
+        P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+        ctx = capi.Context(0); ctx.ref_upload(wl.ref)
+        batches = helpers.pack_both(wl)
+        ctx.segjuncs_begin(P)
+        for b in batches:
+            ctx.segjuncs_submit(b)
+        want = ctx.segjuncs_finish(True)
+        juncs, ins = capi.join_sets_from_results(want)
+        jb = [synth.pack_join_side(wl, s, want.junctions) for s in (wl.left, wl.right)]
+        ctx.join_begin(P, juncs, ins)
+        ref = [joined_to_keys(ctx.join_submit(b), b, P) for b in jb]
+        if indel_prob:
+            assert len(want.deletions) > 20 and len(want.insertions) > 20
+        # second pass over the same batches, resident hand-off
+        ctx.segjuncs_begin(P)
+        for b in batches:
+            ctx.segjuncs_submit(b)
+        raw = ctx.segjuncs_finish_resident()
+        assert (raw.n_junctions, raw.n_deletions, raw.n_insertions) == (len(want.junctions), len(want.deletions), len(want.insertions))
+        ctx.join_begin_resident(P)
+        got = [joined_to_keys(ctx.join_submit(b), b, P) for b in jb]
+        ctx.segjuncs_fetch()
+        res = capi.SegJuncsResults.from_c(raw, copy=True)
+        helpers.assert_same_results(res, want, "resident finish")
+        for g, r in zip(got, ref):
+            assert g == r
+            total += len(g)
+        with pytest.raises(capi.ThbError):
+            capi.Context(0).join_begin_resident(P)          # no finished pass in that context
+        ctx.close()
+    return total
+
+
+@pytest.mark.gpu
+def test_resident_handoff_equals_host_handoff():
+    assert resident_handoff_check() > 1000

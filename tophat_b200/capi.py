@@ -207,6 +207,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.thb_segjuncs_submit_device.argtypes = [C.c_void_p, C.POINTER(BatchC)]
     lib.thb_segjuncs_finish.argtypes = [C.c_void_p, C.POINTER(ResultsC)]
     lib.thb_last_timing.argtypes = [C.c_void_p, C.POINTER(TimingC)]
+    lib.thb_segjuncs_finish_resident.argtypes = [C.c_void_p, C.POINTER(ResultsC)]
+    lib.thb_segjuncs_fetch.argtypes = [C.c_void_p]
+    lib.thb_join_begin_resident.argtypes = [C.c_void_p, C.POINTER(Params)]
     lib.thb_stream.argtypes = [C.c_void_p]
     lib.thb_stream.restype = C.c_void_p
     lib.thb_pack_bases.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -295,6 +298,19 @@ class Context:
         r = ResultsC()
         self._check(self.lib.thb_segjuncs_finish(self.h, C.byref(r)), "thb_segjuncs_finish")
         return r
+
+    def segjuncs_finish_resident(self) -> ResultsC:
+        """Sets built and kept on the device, counts filled, arrays downloading in the background: valid after segjuncs_fetch()."""
+        r = ResultsC()
+        self._check(self.lib.thb_segjuncs_finish_resident(self.h, C.byref(r)), "thb_segjuncs_finish_resident")
+        return r
+
+    def segjuncs_fetch(self) -> None:
+        self._check(self.lib.thb_segjuncs_fetch(self.h), "thb_segjuncs_fetch")
+
+    def join_begin_resident(self, params: Params) -> None:
+        """thb_join_begin with the device-resident sets of the segment_juncs pass this context has just finished."""
+        self._check(self.lib.thb_join_begin_resident(self.h, C.byref(params)), "thb_join_begin_resident")
 
     def timing(self) -> TimingC:
         t = TimingC()

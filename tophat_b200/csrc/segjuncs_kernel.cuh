@@ -844,4 +844,10 @@ __global__ void decode_keys_kernel(const uint64_t* keys, uint64_t n, RefView ref
   }
 }
 
+// deletion keys as Junction(ref, left, right, antisense = false) keys (long_spanning_reads.cpp:2916-2944)
+__global__ void clear_bit0_kernel(const uint64_t* in, uint64_t n, uint64_t* out)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i] & ~1ull;
+}
+
 }  // namespace thb

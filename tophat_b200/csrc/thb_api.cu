@@ -116,6 +116,9 @@ struct thb_ctx {
   unsigned long long* d_counters = nullptr; unsigned long long* d_ins_count = nullptr;
   unsigned int* d_ovf_juncs = nullptr; unsigned int* d_ovf_dels = nullptr; unsigned int* d_err = nullptr;
   DevBuf d_keys, d_keys_sorted, d_cub_tmp, d_decoded, d_count;
+  // device-resident results of the last finish (thb_join_begin_resident, asynchronous download of thb_segjuncs_finish_resident)
+  DevBuf d_decoded_dels, d_skeys_j, d_skeys_d; uint64_t res_n[3] = {0, 0, 0}; bool have_resident = false, fetch_pending = false;
+  cudaEvent_t ev_sets = nullptr;
   // task queues of the scan phase
   DevBuf ag_send, ag_recv;
   const uint64_t* ag_keys[2] = {nullptr, nullptr}; uint64_t ag_n[2] = {0, 0};     // after the all-gather: every rank's junction / deletion keys (HS_EMPTY padded)
@@ -493,6 +496,7 @@ int thb_create(int device, thb_ctx** out)
   ctx->d_qcounts = ctx->d_counters + 12;
   ctx->d_fus_count = ctx->d_counters + 16; ctx->d_fustask_count = ctx->d_counters + 17;
   for (auto& e : ctx->kev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&ctx->ev_sets, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
   cudaMemset(ctx->d_scalars.p, 0, 256);
   thb_params_default(&ctx->params);
@@ -511,6 +515,8 @@ void thb_destroy(thb_ctx* ctx)
                      &ctx->q_win, &ctx->q_indel, &ctx->q_rescue, &ctx->q_rescue_out, &ctx->q_rbundle, &ctx->q_bstate, &ctx->q_owner, &ctx->ag_send, &ctx->ag_recv,
                      &ctx->d_fus, &ctx->q_fus, &ctx->d_fus_ignore, &ctx->j_juncs, &ctx->j_ins, &ctx->j_bundles, &ctx->j_segc, &ctx->j_reads, &ctx->j_hits, &ctx->j_out, &ctx->j_chain, &ctx->j_idx, &ctx->j_iidx, &ctx->j_fus }) b->release();
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
+  if (ctx->ev_sets) cudaEventDestroy(ctx->ev_sets);
+  for (DevBuf* b : { &ctx->d_decoded_dels, &ctx->d_skeys_j, &ctx->d_skeys_d }) b->release();
   for (auto& s : ctx->stage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.partner }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.consumed); }
   cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_c); cudaEventDestroy(ctx->ev_d);
   for (auto& s : ctx->jstage) { for (DevBuf* b : { &s.bundles, &s.seg_count, &s.reads, &s.hits, &s.ops, &s.out }) b->release(); cudaEventDestroy(s.copied); cudaEventDestroy(s.out_free); }
@@ -773,8 +779,10 @@ struct Trace {
   ~Trace() { if (on && !line.empty()) fprintf(stderr, "[thb trace ms]%s\n", line.c_str()); }
 };
 
-static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit, Trace* tr = nullptr,
-                      const uint64_t* gathered = nullptr, uint64_t n_gathered = 0)
+// decoded: device buffer that keeps the records (resident sets); skeys: keeps the sorted keys; async: the download is queued on the
+// d2h stream behind the decode and NOT waited for (thb_segjuncs_fetch does)
+static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_junction>& out, uint64_t limit, Trace* tr,
+                      const uint64_t* gathered, uint64_t n_gathered, DevBuf& decoded, DevBuf& skeys, bool async)
 {
   CU(ctx->d_count.reserve(64));
   unsigned long long n = 0;
@@ -817,28 +825,38 @@ static int finish_set(thb_ctx* ctx, DevBuf& set, uint64_t cap, PinnedVec<thb_jun
     sorted = (const uint64_t*)ctx->d_keys_sorted.p;
   }
   if (n > limit) n = limit;       // std::set capped at max_seg_juncs by erasing the largest (1692-1693)
-  CU(ctx->d_decoded.reserve(n * sizeof(thb_junction)));
-  decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>(sorted, n, ctx->ref, (thb_junction*)ctx->d_decoded.p);
+  CU(decoded.reserve(n * sizeof(thb_junction))); CU(skeys.reserve(n * 8));
+  CU(cudaMemcpyAsync(skeys.p, sorted, n * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+  decode_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->compute>>>(sorted, n, ctx->ref, (thb_junction*)decoded.p);
   CU(cudaGetLastError()); ctx->own_launches++;
   if (tr) tr->mark("sort+decode(enqueue)");
   CU(out.resize(n));
   if (tr) tr->mark("host_resize");
-  CU(cudaMemcpyAsync(out.data(), ctx->d_decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
+  if (async) {
+    CU(cudaEventRecord(ctx->ev_sets, ctx->compute));
+    CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_sets, 0));
+    CU(cudaMemcpyAsync(out.data(), decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->d2h));
+    ctx->fetch_pending = true;
+  } else {
+    CU(cudaMemcpyAsync(out.data(), decoded.p, n * sizeof(thb_junction), cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+  }
   if (tr) tr->mark("d2h+sync");
   return THB_OK;
 }
 
-int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
+static int finish_impl(thb_ctx* ctx, thb_segjuncs_results* out, bool async)
 {
   if (!ctx || !out) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
   if (!ctx->begun) return fail(ctx, THB_ESTATE, "thb_segjuncs_begin not called");
+  if (ctx->fetch_pending) { CU(cudaStreamSynchronize(ctx->d2h)); ctx->fetch_pending = false; }
+  ctx->have_resident = false;
   Trace tr;
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   int rc;
-  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull, &tr, ctx->ag_keys[0], ctx->ag_n[0]))) return rc;
-  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull, &tr, ctx->ag_keys[1], ctx->ag_n[1]))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_juncs, ctx->cap_juncs, ctx->h_juncs, 10000000ull, &tr, ctx->ag_keys[0], ctx->ag_n[0], ctx->d_decoded, ctx->d_skeys_j, async))) return rc;
+  if ((rc = finish_set(ctx, ctx->d_dels, ctx->cap_dels, ctx->h_dels, ~0ull, &tr, ctx->ag_keys[1], ctx->ag_n[1], ctx->d_decoded_dels, ctx->d_skeys_d, async))) return rc;
   // insertions: first inserted wins among equal (ref, left, length) -- insertions.h:52-67
   unsigned long long nins = 0;
   CU(cudaMemcpyAsync(&nins, ctx->d_ins_count, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -869,8 +887,15 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
     ins_decode_kernel<<<grid_for(nw, 256), 256, 0, ctx->compute>>>(kb, vb, nw, ctx->ref, (thb_insertion*)ctx->d_ins_out.p);
     CU(cudaGetLastError()); ctx->own_launches += 4;
     CU(ctx->h_ins.resize(nw));
-    CU(cudaMemcpyAsync(ctx->h_ins.data(), ctx->d_ins_out.p, nw * sizeof(thb_insertion), cudaMemcpyDeviceToHost, ctx->compute));
-    CU(cudaStreamSynchronize(ctx->compute));
+    if (async) {
+      CU(cudaEventRecord(ctx->ev_sets, ctx->compute));
+      CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_sets, 0));
+      CU(cudaMemcpyAsync(ctx->h_ins.data(), ctx->d_ins_out.p, nw * sizeof(thb_insertion), cudaMemcpyDeviceToHost, ctx->d2h));
+      ctx->fetch_pending = true;
+    } else {
+      CU(cudaMemcpyAsync(ctx->h_ins.data(), ctx->d_ins_out.p, nw * sizeof(thb_insertion), cudaMemcpyDeviceToHost, ctx->compute));
+      CU(cudaStreamSynchronize(ctx->compute));
+    }
   }
   // fusions: reduce the appended records by key -- count, minimum edit distance (2787-2803, fusions.h:87-101)
   ctx->h_fus.clear();
@@ -912,6 +937,17 @@ int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out)
   out->n_deletions = ctx->h_dels.size(); out->deletions = ctx->h_dels.data();
   out->n_insertions = ctx->h_ins.size(); out->insertions = ctx->h_ins.data();
   out->n_fusions = ctx->h_fus.size(); out->fusions = ctx->h_fus.data();
+  ctx->res_n[0] = ctx->h_juncs.size(); ctx->res_n[1] = ctx->h_dels.size(); ctx->res_n[2] = ctx->h_ins.size(); ctx->have_resident = true;
+  return THB_OK;
+}
+
+int thb_segjuncs_finish(thb_ctx* ctx, thb_segjuncs_results* out) { return finish_impl(ctx, out, false); }
+int thb_segjuncs_finish_resident(thb_ctx* ctx, thb_segjuncs_results* out) { return finish_impl(ctx, out, true); }
+int thb_segjuncs_fetch(thb_ctx* ctx)
+{
+  if (!ctx) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->fetch_pending) { CU(cudaStreamSynchronize(ctx->d2h)); ctx->fetch_pending = false; }
   return THB_OK;
 }
 
@@ -924,18 +960,69 @@ int thb_last_timing(thb_ctx* ctx, thb_timing* out)
 
 
 // ---- long_spanning_reads join -------------------------------------------------------------------------
+static int join_begin_checks(thb_ctx* ctx, const thb_params* p)
+{
+  if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
+  if (p->segment_length < 4 || p->segment_length > 255) return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside [4,255]", p->segment_length);
+  if (p->max_insertion_length > 19) return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 not supported");
+  return THB_OK;
+}
+static int join_index_sets(thb_ctx* ctx, const thb_params* p, uint64_t n_juncs, uint64_t n_ins);     // validation + bucket index + parameters (ev_a recorded by the caller)
+
 int thb_join_begin(thb_ctx* ctx, const thb_params* p, const thb_junction* juncs, uint64_t n_juncs, const thb_insertion* ins, uint64_t n_ins)
 {
   if (!ctx || !p) return THB_EINVAL;
   CU(cudaSetDevice(ctx->device));
-  if (!ctx->have_ref) return fail(ctx, THB_ESTATE, "no reference image uploaded");
-  if (p->segment_length < 4 || p->segment_length > 255) return fail(ctx, THB_EUNSUPPORTED, "--segment-length %d outside [4,255]", p->segment_length);
-  if (p->max_insertion_length > 19) return fail(ctx, THB_EUNSUPPORTED, "--max-insertion-length > 19 not supported");
+  int rc = join_begin_checks(ctx, p); if (rc) return rc;
   if ((n_juncs && !juncs) || (n_ins && !ins) || n_juncs >= (1ull << 31) || n_ins >= (1ull << 31)) return fail(ctx, THB_EINVAL, "bad junction / insertion set");
   CU(ctx->j_juncs.reserve((n_juncs + 1) * sizeof(thb_junction))); CU(ctx->j_ins.reserve((n_ins + 1) * sizeof(thb_insertion)));
   CU(cudaEventRecord(ctx->ev_a, ctx->compute));
   if (n_juncs) CU(cudaMemcpyAsync(ctx->j_juncs.p, juncs, n_juncs * sizeof(thb_junction), cudaMemcpyHostToDevice, ctx->compute));
   if (n_ins) CU(cudaMemcpyAsync(ctx->j_ins.p, ins, n_ins * sizeof(thb_insertion), cudaMemcpyHostToDevice, ctx->compute));
+  return join_index_sets(ctx, p, n_juncs, n_ins);
+}
+
+// The sets of the finished segment_juncs pass, still on the device, become the join's sets: junctions and deletions (as
+// Junction(ref, left, right, antisense = false)) merged in Junction order without duplicates, as long_spanning_reads builds its set from
+// the two files (2895-2944); the insertions as they are.  No host round trip.
+int thb_join_begin_resident(thb_ctx* ctx, const thb_params* p)
+{
+  if (!ctx || !p) return THB_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = join_begin_checks(ctx, p); if (rc) return rc;
+  if (!ctx->have_resident) return fail(ctx, THB_ESTATE, "thb_join_begin_resident without a finished segment_juncs pass in this context");
+  const uint64_t nj = ctx->res_n[0], nd = ctx->res_n[1], ni = ctx->res_n[2];
+  uint64_t n_juncs = nj;
+  CU(ctx->j_juncs.reserve((nj + nd + 1) * sizeof(thb_junction))); CU(ctx->j_ins.reserve((ni + 1) * sizeof(thb_insertion)));
+  CU(cudaEventRecord(ctx->ev_a, ctx->compute));
+  if (nd == 0) {
+    if (nj) CU(cudaMemcpyAsync(ctx->j_juncs.p, ctx->d_decoded.p, nj * sizeof(thb_junction), cudaMemcpyDeviceToDevice, ctx->compute));
+  } else {
+    CU(ctx->d_keys.reserve((nj + nd) * 8)); CU(ctx->d_keys_sorted.reserve((nj + nd) * 8)); CU(ctx->d_count.reserve(64));
+    uint64_t* cat = (uint64_t*)ctx->d_keys.p;
+    if (nj) CU(cudaMemcpyAsync(cat, ctx->d_skeys_j.p, nj * 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    clear_bit0_kernel<<<grid_for(nd, 256), 256, 0, ctx->compute>>>((const uint64_t*)ctx->d_skeys_d.p, nd, cat + nj);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const uint64_t*)cat, (uint64_t*)ctx->d_keys_sorted.p, (int)(nj + nd), 0, 64, ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, (const uint64_t*)cat, (uint64_t*)ctx->d_keys_sorted.p, (int)(nj + nd), 0, 64, ctx->compute));
+    tmp = 0;
+    cub::DeviceSelect::Unique(nullptr, tmp, (const uint64_t*)ctx->d_keys_sorted.p, cat, (unsigned long long*)ctx->d_count.p, (int)(nj + nd), ctx->compute);
+    CU(ctx->d_cub_tmp.reserve(tmp + 16));
+    CU(cub::DeviceSelect::Unique(ctx->d_cub_tmp.p, tmp, (const uint64_t*)ctx->d_keys_sorted.p, cat, (unsigned long long*)ctx->d_count.p, (int)(nj + nd), ctx->compute));
+    unsigned long long nu = 0;
+    CU(cudaMemcpyAsync(&nu, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    n_juncs = nu;
+    decode_keys_kernel<<<grid_for(nu, 256), 256, 0, ctx->compute>>>((const uint64_t*)cat, nu, ctx->ref, (thb_junction*)ctx->j_juncs.p);
+    CU(cudaGetLastError());
+  }
+  if (ni) CU(cudaMemcpyAsync(ctx->j_ins.p, ctx->d_ins_out.p, ni * sizeof(thb_insertion), cudaMemcpyDeviceToDevice, ctx->compute));
+  return join_index_sets(ctx, p, n_juncs, ni);
+}
+
+static int join_index_sets(thb_ctx* ctx, const thb_params* p, uint64_t n_juncs, uint64_t n_ins)
+{
   // The sets are validated where they now live (a pass over 1.4 M junctions of an hg38-sized run on the host cost more than
   // the join kernels): strictly increasing in Junction / Insertion order; and, for the bucket index, monotone global lefts
   // (every junction inside its contig's slot of the image -- otherwise the kernels binary-search).
