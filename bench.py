@@ -502,7 +502,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             ctx.segjuncs_allgather()
         # copy=False (every step but the last): the C call alone -- the result sets land in the library's page-locked arrays either way,
         # building numpy views of them is the harness's business, not the path's
-        if device_resident and not args.host_handoff:
+        if device_resident and not args.host_handoff and not copy:
             res = ctx.segjuncs_finish_resident()      # sets stay on the device for thb_join_begin_resident; their download runs behind stage 2
         else:
             res = ctx.segjuncs_finish(True) if copy else ctx.segjuncs_finish_raw()
@@ -542,14 +542,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 clock("segjuncs_submit", lambda: ctx._check(ctx.lib.thb_segjuncs_submit(ctx.h, C.byref(sj_host[i])), "thb_segjuncs_submit"))
         if world > 1:
             clock("allgather", ctx.segjuncs_allgather)
-        if device_resident and not args.host_handoff:
+        if device_resident and not args.host_handoff and not copy:
             res = clock("segjuncs_finish", ctx.segjuncs_finish_resident)
         else:
             res = clock("segjuncs_finish", ctx.segjuncs_finish, True) if copy else clock("segjuncs_finish", ctx.segjuncs_finish_raw)
         return res, ctx.timing()
 
     def step(device_resident: bool, copy: bool = False):
-        resident = device_resident and not args.host_handoff
+        resident = device_resident and not args.host_handoff and not copy
         if args.breakdown:
             res, tm = segjuncs_pass_timed(device_resident, copy)
             if resident:
