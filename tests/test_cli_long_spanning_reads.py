@@ -165,3 +165,41 @@ def test_cli_fusion_test_sets_through_both_stages(name):
         assert len(recs) > 200 and jin["left_n_spliced"] > 100
         if "fusion" in name or "total" in name:
             assert jin["n_fus_contigs"] > 10 and sum(1 for r in recs if "XF" in r[11]) > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+@pytest.mark.parametrize("gz", [False, True])
+def test_cli_reads_as_fastq_text(gz):
+    """The reads argument may be FASTQ text (plain or gzip-ed) instead of the BAM prep_reads writes (ReadStream::init, reads.cpp:528-560):
+    same records as the reference's binary given the same file."""
+    import gzip
+    OUR_BIN = helpers.our_bin("long_spanning_reads")
+    with tempfile.TemporaryDirectory() as td:
+        wl = synth.generate(synth.SynthConfig(keep_truth=True, contig_lens=(250_000,), n_pairs=1500, seed=407, indel_prob=0.3))
+        files = synth.write_pipeline_files(wl, td)
+        nseg = len(wl.left.seg_hits)
+        bams = pyoracle.make_bams(files, td, nseg)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, nseg)
+        jin = pyoracle.make_join_inputs(wl, files, outs, td, nseg)
+        # the kept reads as text: numeric names, as prep_reads numbers them
+        fq = os.path.join(td, "left_kept_reads.fq" + (".gz" if gz else ""))
+        with (gzip.open(fq, "wb") if gz else open(fq, "wb")) as f:
+            for i in range(wl.left.reads.shape[0]):
+                f.write(b"@%d some comment\n" % int(wl.left.ids[i])); f.write(synth.CODE2CHAR[wl.left.reads[i]].tobytes())
+                f.write(b"\n+\n"); f.write(bytes(33 + (i + k) % 40 for k in range(wl.left.reads.shape[1]))); f.write(b"\n")
+        tb = dict(bams); tb["left_reads"] = fq
+        if gz:
+            our_bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, tb, jin, outs, td, nseg, side="left", tag=".b200gz")
+            plain = dict(bams); plain["left_reads"] = fq[:-3]
+            with open(plain["left_reads"], "wb") as f:
+                f.write(gzip.open(fq, "rb").read())
+            ref_bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, plain, jin, outs, td, nseg, side="left", tag=".b200plain")
+        else:
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, tb, jin, outs, td, nseg, side="left", tag=".ref")
+            our_bam = pyoracle.run_long_spanning_reads(OUR_BIN, files, tb, jin, outs, td, nseg, side="left", tag=".b200")
+        _, a = pyoracle.read_bam(our_bam)
+        _, b = pyoracle.read_bam(ref_bam)
+        assert len(a) == len(b) > 100
+        for x, y in zip(a, b):
+            assert x == y, "record differs:\n ours %r\n ref  %r" % (x, y)

@@ -269,3 +269,11 @@ def test_emu_flank_pipeline_matches_reference_binaries(emu_lib):
 def test_emu_resident_handoff_equals_host_handoff(emu_lib):
     import test_gpu_join
     assert test_gpu_join.resident_handoff_check() > 1000
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_emu_cli_reads_as_fastq_text(monkeypatch):
+    """long_spanning_reads with the reads argument as FASTQ text instead of BAM (tests/test_cli_long_spanning_reads.py), emulated library"""
+    import test_cli_long_spanning_reads as t
+    monkeypatch.setenv("THB_TEST_EMU", "1")
+    t.test_cli_reads_as_fastq_text(False)

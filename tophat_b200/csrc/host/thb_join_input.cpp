@@ -4,6 +4,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <zlib.h>
 
 namespace thbhost {
 
@@ -282,7 +283,12 @@ void JoinHitStream::skip_group()
 { const uint32_t id = next_group_id(); if (!id) return; while (ensure() && cur_[pos_].id == id) ++pos_; }
 
 // ---- FullReadStream ---------------------------------------------------------------------------------------
-FullReadStream::FullReadStream(const std::string& path, StreamRange range) : path_(path), range_(range), q_(4) { th_ = std::thread([this] { produce(); }); }
+FullReadStream::FullReadStream(const std::string& path, StreamRange range) : path_(path), range_(range), q_(4)
+{
+  // a reads file that is not BAM is FASTQ / FASTA text, possibly gzip-ed (ReadStream::init, reads.cpp:528-560; next_fastx_read 94-190)
+  const bool bam = path.size() >= 4 && path.compare(path.size() - 4, 4, ".bam") == 0;
+  th_ = std::thread([this, bam] { if (bam) produce(); else produce_fastx(); });
+}
 FullReadStream::~FullReadStream() { q_.stop(); if (th_.joinable()) th_.join(); }
 
 void FullReadStream::produce()
@@ -306,6 +312,38 @@ void FullReadStream::produce()
     if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<FullRead>(); chunk.reserve(CH); }
   }
   if (!br.error().empty()) err_ = br.error();
+  if (!chunk.empty()) q_.push(std::move(chunk));
+  q_.finish();
+}
+void FullReadStream::produce_fastx()
+{
+  gzFile f = gzopen(path_.c_str(), "rb");
+  if (!f) { err_ = "cannot open " + path_ + " for reading"; q_.finish(); return; }
+  gzbuffer(f, 1 << 20);
+  const size_t CH = 1 << 14;
+  std::vector<FullRead> chunk; chunk.reserve(CH);
+  std::vector<char> line(1 << 16);
+  auto getl = [&](std::string& s) -> bool { s.clear(); if (!gzgets(f, line.data(), (int)line.size())) return false; s = line.data();
+    while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); return true; };
+  std::string l, seq, plus, qual;
+  while (getl(l)) {
+    if (l.empty()) continue;
+    const bool fq = l[0] == '@';
+    if (!fq && l[0] != '>') continue;
+    if (!getl(seq)) break;
+    if (fq) { getl(plus); getl(qual); }
+    FullRead fr; fr.name = l.substr(1);
+    const size_t sp = fr.name.find_first_of(" \t");          // the name ends at the first blank (reads.cpp:114-118)
+    if (sp != std::string::npos) fr.name.resize(sp);
+    fr.id = (uint32_t)atol(fr.name.c_str());
+    if (fr.id < range_.begin_id) continue;                    // text read files have no index: a range scans from the start
+    if (fr.id >= range_.end_id) break;
+    for (char& c : seq) if (c == '.') c = 'N';                // reads.cpp:125
+    fr.seq = seq; fr.qual = fq ? qual : std::string();
+    chunk.push_back(std::move(fr));
+    if (chunk.size() >= CH) { q_.push(std::move(chunk)); chunk = std::vector<FullRead>(); chunk.reserve(CH); }
+  }
+  gzclose(f);
   if (!chunk.empty()) q_.push(std::move(chunk));
   q_.finish();
 }

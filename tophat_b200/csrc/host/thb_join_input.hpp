@@ -39,7 +39,7 @@ class FullReadStream {
   const std::string& error() const { return err_; }
   const FullRead* get(uint32_t id);        // increasing ids; NULL if absent
  private:
-  void produce();
+  void produce(); void produce_fastx();
   bool ensure();
   std::string path_, err_; StreamRange range_;
   ChunkQueue<FullRead> q_; std::thread th_;
