@@ -516,7 +516,11 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     # page-locked copies of the junction / insertion sets (stage-2 inputs that thb_join_begin uploads every step)
     _jpin = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory() for a in jsets]
     jsets = tuple(t.numpy().view(a.dtype) for t, a in zip(_jpin, jsets))
-    if args.analytic_join_inputs:
+    # The indel-heavy configuration keeps the analytically placed junction-index hits by default: its segment_juncs pass reports 2 M
+    # insertion / deletion candidates per 10 M pairs, the matcher (like bowtie would) places 120 M segments per side on their contigs
+    # and the join enumerates 1.3 G chains -- 2.2 s per step, measured once (profiles/r2y_bench_indel_matcher_inputs.json); it is a
+    # different workload from round 1's, so it is opt-in there (--matcher-join-inputs).
+    if args.analytic_join_inputs or (WORKLOAD == "indel" and not args.matcher_join_inputs):
         jbatches = [synth.pack_join_side(wl, wl.left, res0.junctions), synth.pack_join_side(wl, wl.right, res0.junctions)]
         flank = None
     else:
@@ -710,7 +714,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                           "join_begin_resident (device-to-device hand-off of the sets, validation, bucket index build)": A["begin_ms"] / steps}
         non_kernel["other (queue counters read back, launch gaps, wait for the sets' download, Python between calls)"] = max(0.0, per_step - tot_ms - sum(non_kernel.values()))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong" if args.total_pairs > 0 else "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(args.pairs, world),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": E["ms"] / args.steps,
@@ -822,6 +826,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--analytic-join-inputs", action="store_true",
                     help="place the spliced segments of stage 2 analytically (round 1) instead of through the junction-flank matcher")
+    ap.add_argument("--matcher-join-inputs", action="store_true", help="--workload indel: stage-2 inputs through the junction-flank matcher as well")
+    ap.add_argument("--total-pairs", type=int, default=0,
+                    help="strong scaling: this many read pairs divided over the GPUs (default: --pairs per GPU, weak scaling)")
     ap.add_argument("--host-handoff", action="store_true",
                     help="device-resident arm: hand the sets from stage 1 to stage 2 through the host (thb_segjuncs_finish + thb_join_begin) "
                          "instead of thb_segjuncs_finish_resident + thb_join_begin_resident")
@@ -831,6 +838,9 @@ def main():
     global WORKLOAD, HOST_HANDOFF
     WORKLOAD = args.workload
     HOST_HANDOFF = bool(args.host_handoff)
+    if args.total_pairs > 0:
+        # strong scaling: a fixed job divided over the GPUs (BASELINE configs[2] as a whole is --total-pairs 50000000)
+        args.pairs = max(1, args.total_pairs // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
     if args.pairs <= 0:
         args.pairs = default_pairs(WORKLOAD)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
