@@ -378,8 +378,10 @@ typedef struct thb_flank_contig {        /* what juncs_db encodes in the FASTA n
 typedef struct thb_flank_params {
   int32_t max_mismatches;                /* bowtie -v: --segment-mismatches (0..3)                                              */
   int32_t max_multihits;                 /* bowtie -k / -m: --max-seg-multihits                                                 */
-  int32_t min_seg_len, max_seg_len;      /* shortest / longest segment that will be submitted; max_seg_len is juncs_db's
-                                            <read_length> (flank length); 4*(max_mismatches+2) <= min_seg_len, max_seg_len <= 56 */
+  int32_t min_seg_len, max_seg_len;      /* min_seg_len: shortest segment that will be submitted (the seeds cover its bases),
+                                            4*(max_mismatches+2) <= min_seg_len; max_seg_len: juncs_db's <read_length>, the flank
+                                            length on either side of an event (tophat.py:3483-3492), <= 56.  Segments of up to 64
+                                            bases may be submitted; one longer than a contig has no placement on it.             */
   int32_t min_anchor;                    /* juncs_db's <min_anchor>: tophat.py passes 3                                          */
   int32_t ref_n_is_mismatch;             /* 0: bowtie 1 (placement over a contig N invalid); 1: the N counts as a mismatch       */
 } thb_flank_params;

@@ -248,7 +248,7 @@ def test_emu_fusion_test_sets_join_matches_reference(name):
         assert a == b and sum(1 for r in b if "XF" in r[11]) > 200
 
 
-@pytest.mark.parametrize("name", ["v2_101bp", "v2_m2_suppression", "v3_two_word_contigs", "v3_direct_buckets", "v0_exact"])
+@pytest.mark.parametrize("name", ["v2_101bp", "v2_m2_suppression", "v3_two_word_contigs", "v3_direct_buckets", "v0_exact", "v2_long_last_segment"])
 def test_emu_flank_matcher_equals_oracle(emu_lib, name):
     """junction-flank matcher kernels (flank_kernel.cuh) under emulation against oracle/flank_oracle.py"""
     import numpy as np
@@ -277,3 +277,10 @@ def test_emu_cli_reads_as_fastq_text(monkeypatch):
     import test_cli_long_spanning_reads as t
     monkeypatch.setenv("THB_TEST_EMU", "1")
     t.test_cli_reads_as_fastq_text(False)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_emu_cli_long_spanning_reads_searches_the_junction_index_itself(emu_lib, monkeypatch):
+    import test_flank
+    monkeypatch.setenv("THB_TEST_EMU", "1")
+    assert test_flank.flank_pipeline_check(cli_bin=helpers.our_bin("long_spanning_reads")) > 500

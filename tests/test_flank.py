@@ -93,7 +93,7 @@ def test_contigs_equal_reference_juncs_db(tmp_path, seed, max_seg_len):
 # ----------------------------------------------------------------------------------------------------------------------------
 # the device matcher against the oracle (through the C ABI)
 
-def flank_case(seed, max_mm, seg_bounds, n_reads, lens=(3000, 1200, 500, 90), n_j=60, n_d=12, n_i=12, n_f=16, min_anchor=3):
+def flank_case(seed, max_mm, seg_bounds, n_reads, lens=(3000, 1200, 500, 90), n_j=60, n_d=12, n_i=12, n_f=16, min_anchor=3, flank=None):
     """Reference + sets + reads: segments cut out of contigs (either strand, 0..max_mm+1 substitutions, now and then an N),
     segments cut out of the genome, and random ones."""
     from tophat_b200 import synth
@@ -101,7 +101,7 @@ def flank_case(seed, max_mm, seg_bounds, n_reads, lens=(3000, 1200, 500, 90), n_
     names, codes = random_reference(rng, list(lens))
     j, d, ins, f = random_sets(rng, list(lens), n_j, n_d, n_i, n_f)
     seg_lens = np.diff(seg_bounds)
-    max_seg_len = int(seg_lens.max())
+    max_seg_len = int(flank or seg_lens.max())          # flank: juncs_db's <read_length> when it is not the longest segment
     cs = flank_oracle.contigs(names, codes, max_seg_len, min_anchor, j, d, ins, f)
     L = int(seg_bounds[-1])
     reads = rng.integers(0, 4, (n_reads, L)).astype(np.uint8)
@@ -214,6 +214,7 @@ FLANK_CASES = {
     "v2_bowtie2_n": (12, 2, [0, 25, 50, 75, 101], 80, 40, 1, {}),
     "v2_m2_suppression": (13, 2, [0, 25, 50, 75], 100, 2, 0, {}),
     "v0_exact": (14, 0, [0, 25, 50, 76], 80, 40, 0, {}),
+    "v2_long_last_segment": (18, 2, [0, 25, 50, 94], 80, 40, 0, dict(flank=26)),
     "v1": (15, 1, [0, 25, 50, 75, 101], 80, 40, 0, {}),
     "v3_two_word_contigs": (16, 3, [0, 30, 60, 94], 60, 40, 0, {}),
     "v3_direct_buckets": (17, 3, [0, 20, 40], 40, 40, 0, dict(lens=(300000, 100000, 5000, 90), n_j=7000, n_d=100, n_i=100, n_f=100)),
@@ -248,7 +249,7 @@ def test_flank_argument_errors():
             ctx.flank_begin(bad, *sets_as_records(case))
     ctx.flank_begin(capi.FlankParams(2, 40, 25, 25, 3, 0), *sets_as_records(case))
     with pytest.raises(capi.ThbError):
-        ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, [0, 25, 51])                  # 26-base segment, index built for 25
+        ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, [0, 24, 50])                  # 24-base segment, seeds built for 25
     with pytest.raises(capi.ThbError):
         ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, [0, 25, 50, 75])              # past the read words
     # empty sets: an index without contigs answers with no placements
@@ -262,7 +263,7 @@ def test_flank_argument_errors():
 # ----------------------------------------------------------------------------------------------------------------------------
 # both stages with the matcher in between, against the reference's own binaries fed the same placements
 
-def flank_pipeline_check(n_pairs=1200, seed=511, indel_prob=0.4):
+def flank_pipeline_check(n_pairs=1200, seed=511, indel_prob=0.4, cli_bin=None):
     """stage 1 (ours) -> thb_flank_* -> join (ours)   versus   segment_juncs -> juncs_db -> [the matcher's placements written as bowtie
     would: SAM records on the contig names of the reference's juncs_db] -> fix_map_ordering -> long_spanning_reads, all reference
     binaries.  Checks (1) our contigs are juncs_db's, name for name; (2) the join over thb_flank_spliced_hits gives the records the
@@ -355,6 +356,15 @@ def flank_pipeline_check(n_pairs=1200, seed=511, indel_prob=0.4):
             _, recs = pyoracle.read_bam(ref_bam)
             want = set((int(r[0]), names.index(r[2]) + 1, r[3], r[5], r[1], r[11]["NM"]) for r in recs)
             assert got == want, "%s: only ours %r; only reference %r" % (sname, sorted(got - want)[:3], sorted(want - got)[:3])
+            if cli_bin:
+                # our executable searching the junction index itself (TOPHAT_GPU_FLANK_SEARCH=1, no spliced segment files), -p1 and -p3
+                for thr in (1, 3):
+                    our_bam = pyoracle.run_long_spanning_reads(cli_bin, files, bams, jin, outs, td, nseg, side=sname, tag=".flank%d" % thr, with_spliced=False,
+                                                               threads=thr, env=dict(os.environ, TOPHAT_GPU_FLANK_SEARCH="1"))
+                    _, ours = pyoracle.read_bam(our_bam)
+                    assert len(ours) == len(recs), "%s -p%d: %d records vs %d in the reference output" % (sname, thr, len(ours), len(recs))
+                    for x, y in zip(ours, recs):
+                        assert x == y, "record differs:\n ours %r\n ref  %r" % (x, y)
             spl = [r for r in want if "N" in r[3] or "D" in r[3] or "I" in r[3]]
             assert len(spl) > 50, len(spl)
             total += len(want)
@@ -366,3 +376,12 @@ def flank_pipeline_check(n_pairs=1200, seed=511, indel_prob=0.4):
 @pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
 def test_flank_pipeline_matches_reference_binaries():
     assert flank_pipeline_check() > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_cli_long_spanning_reads_searches_the_junction_index_itself():
+    """long_spanning_reads with TOPHAT_GPU_FLANK_SEARCH=1 and no spliced segment files: the records of the reference's binary that was
+    given the placements as to_spliced.bam files, in the same order."""
+    import helpers
+    assert flank_pipeline_check(cli_bin=helpers.our_bin("long_spanning_reads")) > 500

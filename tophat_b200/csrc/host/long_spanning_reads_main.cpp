@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -158,13 +159,14 @@ int main(int argc, char** argv)
   struct IL { bool operator()(const thb_insertion& x, const thb_insertion& y) const {
     if (x.ref_id != y.ref_id) return x.ref_id < y.ref_id; if (x.left != y.left) return x.left < y.left; return x.len < y.len; } };
   std::set<thb_junction, JL> jset; std::set<thb_insertion, IL> iset;
+  std::set<thb_junction, JL> jonly, donly;      // the junction / deletion files on their own: what juncs_db reads (TOPHAT_GPU_FLANK_SEARCH)
   fprintf(stderr, "Loading junctions...");
   for (const std::string& f : juncs_files) {
     FILE* fp = fopen(f.c_str(), "r"); if (!fp) die("Error: cannot open %s for reading", f);
     char buf[2048];
     while (fgets(buf, sizeof buf, fp)) { char name[256]; int l, r; char orient;
       if (sscanf(buf, "%255s %d %d %c", name, &l, &r, &orient) != 4) continue;
-      thb_junction j; j.ref_id = rt.get_id(name); j.left = (uint32_t)l; j.right = (uint32_t)r; j.antisense = orient == '-'; jset.insert(j); }
+      thb_junction j; j.ref_id = rt.get_id(name); j.left = (uint32_t)l; j.right = (uint32_t)r; j.antisense = orient == '-'; jset.insert(j); jonly.insert(j); }
     fclose(fp);
   }
   fprintf(stderr, "done\nLoading deletions...");
@@ -175,7 +177,7 @@ int main(int argc, char** argv)
       char* t1 = strchr(buf, '\t'); if (!t1) die("Error: malformed deletion coordinate record"); *t1++ = 0;
       char* t2 = strchr(t1, '\t'); if (!t2) die("Error: malformed deletion coordinate record"); *t2++ = 0;
       char* t3 = strchr(t2, '\t'); if (t3) *t3 = 0;
-      thb_junction j; j.ref_id = rt.get_id(buf); j.left = (uint32_t)atoi(t1) - 1u; j.right = (uint32_t)atoi(t2); j.antisense = 0; jset.insert(j); }
+      thb_junction j; j.ref_id = rt.get_id(buf); j.left = (uint32_t)atoi(t1) - 1u; j.right = (uint32_t)atoi(t2); j.antisense = 0; jset.insert(j); donly.insert(j); }
     fclose(fp);
   }
   fprintf(stderr, "done\nLoading insertions...");
@@ -229,6 +231,40 @@ int main(int argc, char** argv)
   if (thb_join_begin(ctx, &o.p, jv.data(), jv.size(), iv.data(), iv.size()) != THB_OK) die("Error: thb_join_begin: %s", thb_last_error(ctx));
   if (o.p.fusion_search) { std::vector<thb_fusion> fv(fset.begin(), fset.end());
     if (thb_join_set_fusions(ctx, fv.data(), fv.size()) != THB_OK) die("Error: thb_join_set_fusions: %s", thb_last_error(ctx)); }
+  // TOPHAT_GPU_FLANK_SEARCH=1: the junction index is searched in this process (thb_flank_*) instead of reading the segment hits that
+  // juncs_db + bowtie-build + bowtie + fix_map_ordering would have left in <spliced_segK.bwtout> (tophat.py:2546-2600, 3686-3741);
+  // a spliced argument, if given, is ignored.  The flank length is tophat.py's max_seg_len (3483-3492) for the longest read.
+  const bool flank_search = getenv("TOPHAT_GPU_FLANK_SEARCH") != nullptr && atoi(getenv("TOPHAT_GPU_FLANK_SEARCH")) != 0;
+  const int seglen = o.p.segment_length;
+  auto segment_bounds = [seglen](int L, std::vector<uint16_t>& b) {       // split_reads, tophat.py:2975-2990
+    b.clear(); int n = L / seglen;
+    for (int i = 0; i <= n; ++i) b.push_back((uint16_t)(seglen * i));
+    if (L % seglen >= std::min(seglen - 2, 20)) { b.push_back((uint16_t)L); ++n; } else b.back() = (uint16_t)L;
+    if (n <= 1) { b.clear(); b.push_back(0); b.push_back((uint16_t)L); }
+  };
+  if (flank_search) {
+    if (!spl_files.empty()) { fprintf(stderr, "TOPHAT_GPU_FLANK_SEARCH: ignoring the spliced segment files\n"); spl_files.clear(); }
+    int max_len = 0, min_seg = 1 << 30;
+    { FullReadStream all(reads_fname);                       // lengths only: the flank length follows the longest read
+      std::vector<uint16_t> b; std::vector<char> seen(256, 0);
+      while (const FullRead* r = all.next()) {
+        const int L = (int)r->seq.size(); if (L > 255) die("Error: reads longer than 255 bases are not supported");
+        if (L < seglen || seen[(size_t)L]) continue; seen[(size_t)L] = 1; max_len = std::max(max_len, L);
+        segment_bounds(L, b); for (size_t k = 0; k + 1 < b.size(); ++k) min_seg = std::min(min_seg, (int)b[k + 1] - (int)b[k]); }
+      if (!all.ok()) die("Error: %s", all.error()); }
+    if (max_len == 0) { max_len = seglen; min_seg = seglen; }
+    int max_seg_len = seglen;
+    { int n = max_len / seglen; if (!(max_len % seglen >= std::min(seglen - 2, 20)) && n > 1) max_seg_len += max_len % seglen; }
+    thb_flank_params fp; memset(&fp, 0, sizeof fp);
+    fp.max_mismatches = std::min(o.p.segment_mismatches, 3); fp.max_multihits = o.p.max_seg_multihits; fp.min_seg_len = std::min(min_seg, max_seg_len);
+    fp.max_seg_len = max_seg_len; fp.min_anchor = 3; fp.ref_n_is_mismatch = o.p.bowtie2 ? 1 : 0;
+    std::vector<thb_junction> jo(jonly.begin(), jonly.end()), dn(donly.begin(), donly.end());
+    std::vector<thb_fusion> fv(fset.begin(), fset.end());
+    if (thb_flank_begin(ctx, &fp, jo.data(), jo.size(), dn.data(), dn.size(), iv.data(), iv.size(), fv.data(), fv.size()) != THB_OK)
+      die("Error: thb_flank_begin: %s", thb_last_error(ctx));
+    thb_flank_timing ft; thb_flank_last_timing(ctx, &ft);
+    fprintf(stderr, "Junction index: %llu contigs, %llu seed entries, built in %.1f ms\n", (unsigned long long)ft.n_contigs, (unsigned long long)ft.n_index_entries, ft.index_ms);
+  }
   auto t1 = std::chrono::steady_clock::now();
 
   // Read-id ranges, one output BAM per range -- the reference's own -p N layout (<out minus .bam><i>.bam, 3056-3064, which
@@ -258,6 +294,48 @@ int main(int argc, char** argv)
   for (auto& f : spl_files) spliced.emplace_back(new JoinHitStream(f, rt, rtm, true, o.p.max_report_intron_length, o.p.min_anchor_len, range_for(f, begin_id, end_id)));
   FullReadStream reads(reads_fname, range_for(reads_fname, begin_id, end_id));
   uint64_t r_reads = 0, r_out = 0; double r_submit = 0, r_post = 0;
+  // in-process junction index search: the placements of this range's reads, per segment, in id order
+  std::vector<std::vector<JHitRec>> mem_spl(flank_search ? nseg : 0); std::vector<size_t> mem_pos(mem_spl.size(), 0);
+  if (flank_search) {
+    FullReadStream pre(reads_fname, range_for(reads_fname, begin_id, end_id));
+    std::map<int, std::pair<std::vector<uint32_t>, std::vector<uint64_t>>> by_len;        // read length -> ids, bit planes (read_words = 4)
+    auto search = [&](int L, std::vector<uint32_t>& ids, std::vector<uint64_t>& planes) {
+      if (ids.empty()) return;
+      std::vector<uint16_t> b; segment_bounds(L, b);
+      thb_flank_batch fb; memset(&fb, 0, sizeof fb);
+      fb.n_reads = (uint32_t)ids.size(); fb.read_words = 4; fb.n_segs = (uint32_t)b.size() - 1; fb.reads = planes.data();
+      if (fb.n_segs > nseg) die("Error: a read of %s bases has more segments than segment files were given", std::to_string(L));
+      for (size_t k = 0; k < b.size(); ++k) fb.seg_bounds[k] = b[k];
+      std::lock_guard<std::mutex> cl(ctx_mutex);
+      const thb_flank_hit* fh = nullptr; const thb_jhit_full* jh = nullptr; uint64_t n = 0, n2 = 0;
+      if (thb_flank_submit(ctx, &fb, &fh, &n) != THB_OK) die("Error: thb_flank_submit: %s", thb_last_error(ctx));
+      if (thb_flank_spliced_hits(ctx, o.p.min_anchor_len, &jh, &n2) != THB_OK || n2 != n) die("Error: thb_flank_spliced_hits: %s", thb_last_error(ctx));
+      for (uint64_t i = 0; i < n; ++i) if (jh[i].n_ops) { JHitRec r; r.id = ids[fh[i].read]; r.h = jh[i]; mem_spl[fh[i].seg].push_back(r); }
+      ids.clear(); planes.clear();
+    };
+    while (const FullRead* r = pre.next()) {
+      const int L = (int)r->seq.size();
+      if (L < seglen || L > 255) continue;
+      auto& slot = by_len[L];
+      ReadRec rr; pack_read_ascii(r->seq.data(), (uint32_t)L, rr);
+      slot.first.push_back(r->id); slot.second.insert(slot.second.end(), rr.planes, rr.planes + 12);
+      if (slot.first.size() >= (1u << 20)) search(L, slot.first, slot.second);
+    }
+    if (!pre.ok()) die("Error: %s", pre.error());
+    for (auto& kv : by_len) search(kv.first, kv.second.first, kv.second.second);
+    for (auto& v : mem_spl) std::stable_sort(v.begin(), v.end(), [](const JHitRec& x, const JHitRec& y) { return x.id < y.id; });
+  }
+  const size_t n_spl = flank_search ? nseg : spliced.size();
+  auto spl_next_id = [&](size_t s) -> uint32_t {
+    if (!flank_search) return spliced[s]->next_group_id();
+    return mem_pos[s] < mem_spl[s].size() ? mem_spl[s][mem_pos[s]].id : 0u; };
+  auto spl_next_group = [&](size_t s, std::vector<thb_jhit_full>& out) {
+    if (!flank_search) { spliced[s]->next_group(out); return; }
+    const uint32_t id = spl_next_id(s); if (!id) return;
+    while (mem_pos[s] < mem_spl[s].size() && mem_spl[s][mem_pos[s]].id == id) out.push_back(mem_spl[s][mem_pos[s]++].h); };
+  auto spl_skip = [&](size_t s) {
+    if (!flank_search) { spliced[s]->skip_group(); return; }
+    const uint32_t id = spl_next_id(s); while (mem_pos[s] < mem_spl[s].size() && mem_spl[s][mem_pos[s]].id == id) ++mem_pos[s]; };
   BamWriter bw;
   if (!bw.open(out_path, o.sam_header, out_path + ".index", &err)) die("Error: %s", err);
   std::vector<int> ref2tid;
@@ -392,18 +470,18 @@ int main(int argc, char** argv)
   std::vector<std::vector<thb_jhit_full>> seg_hits(nseg);
   for (;;) {
     const uint32_t cid = contig[0]->next_group_id();
-    const uint32_t sid = spliced.empty() ? 0 : spliced[0]->next_group_id();
+    const uint32_t sid = n_spl == 0 ? 0 : spl_next_id(0);
     if (!cid && !sid) break;
     const uint32_t id = (cid && (!sid || cid <= sid)) ? cid : sid;
     for (auto& v : seg_hits) v.clear();
     if (cid == id) contig[0]->next_group(seg_hits[0]);
-    if (sid == id) spliced[0]->next_group(seg_hits[0]);
+    if (sid == id) spl_next_group(0, seg_hits[0]);
     // look_right_for_hit_group (87-163): stop at the first segment without contiguous or spliced hits
     for (size_t s = 1; s < nseg; ++s) {
       uint32_t gidc; while ((gidc = contig[s]->next_group_id()) != 0 && gidc < id) contig[s]->skip_group();
       if (gidc == id) contig[s]->next_group(seg_hits[s]);
-      if (s < spliced.size()) { uint32_t gids; while ((gids = spliced[s]->next_group_id()) != 0 && gids < id) spliced[s]->skip_group();
-                                if (gids == id) spliced[s]->next_group(seg_hits[s]); }
+      if (s < n_spl) { uint32_t gids; while ((gids = spl_next_id(s)) != 0 && gids < id) spl_skip(s);
+                       if (gids == id) spl_next_group(s, seg_hits[s]); }
       if (seg_hits[s].empty()) break;
     }
     int last_non_empty = (int)nseg - 1;

@@ -356,6 +356,7 @@ bool FullReadStream::ensure()
   }
   return true;
 }
+const FullRead* FullReadStream::next() { if (!ensure()) return nullptr; return &cur_[pos_++]; }
 const FullRead* FullReadStream::get(uint32_t id)
 {
   while (ensure()) { const FullRead& r = cur_[pos_]; if (r.id == id) return &r; if (r.id > id) return nullptr; ++pos_; }

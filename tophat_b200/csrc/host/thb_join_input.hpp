@@ -38,6 +38,7 @@ class FullReadStream {
   bool ok() const { return err_.empty(); }
   const std::string& error() const { return err_; }
   const FullRead* get(uint32_t id);        // increasing ids; NULL if absent
+  const FullRead* next();                  // sequential access: the next read of the stream, NULL at its end
  private:
   void produce(); void produce_fastx();
   bool ensure();

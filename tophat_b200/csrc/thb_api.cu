@@ -1494,8 +1494,8 @@ static int flank_submit(thb_ctx* ctx, const thb_flank_batch* b, bool on_device, 
   if (b->n_reads && !b->reads) return fail(ctx, THB_EINVAL, "thb_flank_submit: null reads");
   for (uint32_t k = 0; k < b->n_segs; ++k) {
     const int s = (int)b->seg_bounds[k + 1] - (int)b->seg_bounds[k];
-    if (s < f.min_seg_len || s > f.max_seg_len || b->seg_bounds[k + 1] > 64u * b->read_words)
-      return fail(ctx, THB_EINVAL, "thb_flank_submit: segment %u has %d bases (index built for %d..%d) or ends past the read", k, s, f.min_seg_len, f.max_seg_len);
+    if (s < f.min_seg_len || s > 64 || b->seg_bounds[k + 1] > 64u * b->read_words)
+      return fail(ctx, THB_EINVAL, "thb_flank_submit: segment %u has %d bases (index seeds need >= %d, a segment is at most 64) or ends past the read", k, s, f.min_seg_len);
   }
   CU(cudaSetDevice(ctx->device));
   const uint32_t launches0 = f.timing.launches;
