@@ -129,8 +129,9 @@ def test_emu_cli_fusions_match_reference_binary(extra):
 
 
 def test_emu_allgather_world1():
-    """thb_segjuncs_allgather's staging / padding / re-insertion of all four record kinds, in a fresh process with a
-    single-rank stand-in for libnccl (tests/emu/fake_nccl.c)."""
+    """thb_segjuncs_allgather's staging / padding / union of all four record kinds, in a fresh process with a stand-in for libnccl
+    (tests/emu/fake_nccl.c): world size 1, and a replicating "world size 3" (sort + unique union, first-wins insertions, fusion
+    counts, the refused late submit, the resident hand-off of the gathered union)."""
     import subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "emu", "allgather_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "allgather ok" in r.stdout, r.stdout + r.stderr
