@@ -713,6 +713,12 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             non_kernel = {"segjuncs_finish_resident (set compaction, CUB sorts, decode; the D2H of the sets runs behind stage 2)": A["finish_ms"] / steps,
                           "join_begin_resident (device-to-device hand-off of the sets, validation, bucket index build)": A["begin_ms"] / steps}
         non_kernel["other (queue counters read back, launch gaps, wait for the sets' download, Python between calls)"] = max(0.0, per_step - tot_ms - sum(non_kernel.values()))
+        if flank is not None:
+            # what one pass costs when the junction index is rebuilt and searched every step as well (sum of the measured parts; the
+            # reference spends juncs_db + bowtie-build + 2 x nseg bowtie runs here, outside both arms' timed region)
+            extra = flank["index"]["device_ms"] + sum(x["match_ms"] + x["post_ms"] for x in flank["sides"])
+            flank["step_plus_junction_index"] = {"ms": per_step + extra, "reads_per_s": n_reads / ((per_step + extra) * 1e-3),
+                                                 "note": "per GPU: ms_per_step + index build + search of both sides, device times"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong" if args.total_pairs > 0 else "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config(args.pairs, world),
