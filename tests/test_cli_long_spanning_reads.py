@@ -163,6 +163,10 @@ def test_cli_fusion_test_sets_through_both_stages(name):
         our_bam = pyoracle.run_long_spanning_reads(LSR, files, bams, jin, ours1, td, nseg, side="left", tag=".b200", opts=opts, fusions=ours1["fusions"])
         recs = _compare_bams(our_bam, ref_bam, name)
         assert len(recs) > 200 and jin["left_n_spliced"] > 100
+        # the same without any junction-index BAM: long_spanning_reads builds and searches the index itself (fusion contigs included)
+        flank_bam = pyoracle.run_long_spanning_reads(LSR, files, bams, jin, ours1, td, nseg, side="left", tag=".b200flank", opts=opts, fusions=ours1["fusions"],
+                                                     with_spliced=False, env=dict(os.environ, TOPHAT_GPU_FLANK_SEARCH="1", TOPHAT_GPU_FLANK_LENGTH="26"))     # the pipeline above ran juncs_db 3 26
+        _compare_bams(flank_bam, ref_bam, name + " (in-process junction index)")
         if "fusion" in name or "total" in name:
             assert jin["n_fus_contigs"] > 10 and sum(1 for r in recs if "XF" in r[11]) > 500
 

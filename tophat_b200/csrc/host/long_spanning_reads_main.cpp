@@ -255,6 +255,7 @@ int main(int argc, char** argv)
     if (max_len == 0) { max_len = seglen; min_seg = seglen; }
     int max_seg_len = seglen;
     { int n = max_len / seglen; if (!(max_len % seglen >= std::min(seglen - 2, 20)) && n > 1) max_seg_len += max_len % seglen; }
+    if (const char* e = getenv("TOPHAT_GPU_FLANK_LENGTH")) if (atoi(e) >= seglen) max_seg_len = atoi(e);      // juncs_db's <read_length> given explicitly
     thb_flank_params fp; memset(&fp, 0, sizeof fp);
     fp.max_mismatches = std::min(o.p.segment_mismatches, 3); fp.max_multihits = o.p.max_seg_multihits; fp.min_seg_len = std::min(min_seg, max_seg_len);
     fp.max_seg_len = max_seg_len; fp.min_anchor = 3; fp.ref_n_is_mismatch = o.p.bowtie2 ? 1 : 0;
