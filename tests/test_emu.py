@@ -247,6 +247,11 @@ def test_emu_fusion_test_sets_join_matches_reference(name):
         our_bam = pyoracle.run_long_spanning_reads(exe, files, bams, jin, outs, td, nseg, side="left", tag=".emu", opts=opts, fusions=outs["fusions"])
         _, a = pyoracle.read_bam(our_bam); _, b = pyoracle.read_bam(ref_bam)
         assert a == b and sum(1 for r in b if "XF" in r[11]) > 200
+        # and with the junction index (fusion contigs included) built and searched inside the executable
+        flank_bam = pyoracle.run_long_spanning_reads(exe, files, bams, jin, outs, td, nseg, side="left", tag=".emuflank", opts=opts, fusions=outs["fusions"],
+                                                     with_spliced=False, env=dict(os.environ, TOPHAT_GPU_FLANK_SEARCH="1", TOPHAT_GPU_FLANK_LENGTH="26"))
+        _, c = pyoracle.read_bam(flank_bam)
+        assert c == b
 
 
 @pytest.mark.parametrize("name", ["v2_101bp", "v2_m2_suppression", "v3_two_word_contigs", "v3_direct_buckets", "v0_exact", "v2_long_last_segment"])
