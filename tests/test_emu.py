@@ -290,3 +290,11 @@ def test_emu_cli_long_spanning_reads_searches_the_junction_index_itself(emu_lib,
     import test_flank
     monkeypatch.setenv("THB_TEST_EMU", "1")
     assert test_flank.flank_pipeline_check(cli_bin=helpers.our_bin("long_spanning_reads")) > 500
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_emu_cli_in_process_junction_index_with_two_read_lengths(emu_lib, monkeypatch):
+    """101-bp and 75-bp reads in one run: per-length segment layouts in the in-process junction index search (tests/test_flank.py)"""
+    import test_flank
+    monkeypatch.setenv("THB_TEST_EMU", "1")
+    assert test_flank.mixed_length_cli_check(helpers.our_bin("long_spanning_reads")) > 400

@@ -385,3 +385,133 @@ def test_cli_long_spanning_reads_searches_the_junction_index_itself():
     given the placements as to_spliced.bam files, in the same order."""
     import helpers
     assert flank_pipeline_check(cli_bin=helpers.our_bin("long_spanning_reads")) > 500
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# reads of two lengths in one run (101 bp = 4 segments with a 26-base last one, 75 bp = 3 segments)
+
+def mixed_length_cli_check(cli_bin, n_pairs=600):
+    """One reads file with 101-bp and 75-bp reads: the reference chain (segment_juncs, juncs_db 3 26, long_spanning_reads fed the
+    placements as BAM files) against our long_spanning_reads searching the index itself -- per read length its own segment layout,
+    segment count and end-of-read flag."""
+    import tempfile
+    from tophat_b200 import capi, synth
+    base = dict(contig_lens=(200_000, 80_000), keep_truth=True, indel_prob=0.3)
+    cfgs = [synth.SynthConfig(n_pairs=n_pairs, seed=611, read_len=101, **base), synth.SynthConfig(n_pairs=n_pairs, seed=611, read_len=75, **base)]
+    rd = synth.make_reference(cfgs[0])
+    wls = [synth.generate(c, refdata=rd) for c in cfgs]
+    names = wls[0].ref.names
+    NSEG = 4
+    with tempfile.TemporaryDirectory() as td:
+        parts = []
+        for k, wl in enumerate(wls):
+            d = os.path.join(td, "part%d" % k)
+            parts.append(synth.write_pipeline_files(wl, d))
+        files = {"fasta": parts[0]["fasta"], "header": parts[0]["header"]}
+        offset = [0, wls[0].left.reads.shape[0]]
+        for side in ("left", "right"):
+            files[side + "_fq"] = os.path.join(td, side + ".fq")
+            with open(files[side + "_fq"], "wb") as out:
+                for p in parts:
+                    out.write(open(p[side + "_fq"], "rb").read())
+            for key in ["mapped"] + ["seg%d" % (s + 1) for s in range(NSEG)]:
+                fk = "%s_%s_sam" % (side, key)
+                files[fk] = os.path.join(td, "%s_%s.sam" % (side, key))
+                with open(files[fk], "w") as out:
+                    for k, p in enumerate(parts):
+                        if fk not in p:
+                            continue                                     # the 75-bp reads have no fourth segment
+                        for line in open(p[fk]):
+                            q, rest = line.split("\t", 1)
+                            head, sep, tail = q.partition("|")
+                            out.write("%d%s%s\t%s" % (int(head) + offset[k], sep, tail, rest))
+        bams = pyoracle.make_bams(files, td, NSEG)
+        outs = pyoracle.run_segment_juncs(os.path.join(pyoracle.REF_DIR, "segment_juncs"), files, bams, td, NSEG)
+        fa = os.path.join(td, "segment_juncs.fa")
+        with open(fa, "w") as f:
+            subprocess.run([os.path.join(pyoracle.REF_DIR, "juncs_db"), "3", "26", outs["juncs"], outs["insertions"], outs["deletions"], "/dev/null",
+                            files["fasta"]], check=True, stdout=f, stderr=subprocess.DEVNULL)
+        cnames, cseqs = [], []
+        for line in open(fa):
+            (cnames if line.startswith(">") else cseqs).append(line[1:].rstrip("\n") if line.startswith(">") else line.rstrip("\n"))
+        hdr = os.path.join(td, "segment_juncs.hdr.sam")
+        with open(hdr, "w") as f:
+            f.write("@HD\tVN:1.0\tSO:unsorted\n")
+            for n, sq in zip(cnames, cseqs):
+                f.write("@SQ\tSN:%s\tLN:%d\n" % (n, len(sq)))
+        ccodes = [synth.codes_from_ascii(sq.encode()) for sq in cseqs]
+        # the sets as the reference wrote them -> the index (flank 26, bowtie2's N policy as the executable will use)
+        P = capi.default_params(inner_dist_mean=50, inner_dist_std_dev=20)
+        jn = pyoracle.parse_juncs(outs["juncs"], names)
+        dl = np.zeros(0, synth.JUNCTION_DTYPE); ins = np.zeros(0, synth.INSERTION_DTYPE)
+        dlines = [l.split("\t") for l in open(outs["deletions"]).read().splitlines()]
+        if dlines:
+            dl = np.zeros(len(dlines), synth.JUNCTION_DTYPE)
+            for i, t in enumerate(dlines):
+                dl[i] = (names.index(t[0]) + 1, int(t[1]) - 1, int(t[2]), 0)
+        ilines = [l.split("\t") for l in open(outs["insertions"]).read().splitlines()]
+        if ilines:
+            ins = np.zeros(len(ilines), synth.INSERTION_DTYPE)
+            for i, t in enumerate(ilines):
+                ins[i] = (names.index(t[0]) + 1, int(t[1]), len(t[3]), t[3].encode())
+        ctx = capi.Context(0); ctx.ref_upload(wls[0].ref)
+        ctx.flank_begin(capi.FlankParams(2, 40, 25, 26, 3, 1), jn, dl, ins, np.zeros(0, synth.FUSION_DTYPE))
+        assert len(ctx.flank_contigs()) == len(cnames) > 100
+        total = 0
+        for sname in ("left", "right"):
+            sams = [open(os.path.join(td, "%s_seg%d.to_spliced.sam" % (sname, s + 1)), "w") for s in range(NSEG)]
+            n_hits = 0
+            for k, wl in enumerate(wls):
+                side = wl.left if sname == "left" else wl.right
+                offs, lens = synth.segment_layout(wl.cfg.read_len, wl.cfg.segment_length)
+                bounds = [int(o) for o in offs] + [int(offs[-1] + lens[-1])]
+                rw = (wl.cfg.read_len + 63) // 64
+                idx = np.nonzero(side.unmapped)[0]
+                hits = ctx.flank_submit(synth.pack_reads(side.reads[idx], rw), rw, bounds)
+                n_hits += len(hits)
+                for h in hits:
+                    s = int(h["seg"]); ri = int(idx[int(h["read"])]); ln = int(lens[s])
+                    q = side.reads[ri, bounds[s]:bounds[s + 1]]
+                    if h["antisense"]:
+                        q = flank_oracle._rc(q)
+                    cw = ccodes[int(h["contig"])][int(h["pos"]):int(h["pos"]) + ln]
+                    mm = (q != cw) | (q > 3) | (cw > 3)
+                    md, run = [], 0
+                    for x in range(ln):
+                        if mm[x]:
+                            md.append(str(run)); md.append(chr(synth.CODE2CHAR[min(int(cw[x]), 4)])); run = 0
+                        else:
+                            run += 1
+                    md.append(str(run)); nm = int(mm.sum())
+                    sams[s].write("%d|%d:%d:%d\t%d\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:UU\n" % (
+                        ri + 1 + offset[k], bounds[s], s, len(lens), 16 if h["antisense"] else 0, cnames[int(h["contig"])], int(h["pos"]) + 1, ln,
+                        synth.CODE2CHAR[q].tobytes().decode(), "I" * ln, -6 * nm, nm, nm, "".join(md)))
+            jin = {"juncs_fa": fa, "juncs_header": hdr, "n_contigs": len(cnames)}
+            for s, f in enumerate(sams):
+                f.close()
+                bam = os.path.join(td, "%s_kept_reads_seg%d.to_spliced.bam" % (sname, s + 1))
+                subprocess.run([os.path.join(pyoracle.REF_DIR, "fix_map_ordering"), "--sam-header", hdr, "--index-outfile", bam + ".index", f.name, bam],
+                               check=True, stderr=subprocess.DEVNULL)
+                jin["%s_spl%d" % (sname, s + 1)] = bam
+            ref_bam = pyoracle.run_long_spanning_reads(os.path.join(pyoracle.REF_DIR, "long_spanning_reads"), files, bams, jin, outs, td, NSEG, side=sname, tag=".ref")
+            _, want = pyoracle.read_bam(ref_bam)
+            lens_seen = {len(r[6]) for r in want}
+            assert lens_seen == {101, 75}, lens_seen
+            assert n_hits > 200 and sum(1 for r in want if "N" in r[5]) > 60
+            for thr in (1, 2):
+                our_bam = pyoracle.run_long_spanning_reads(cli_bin, files, bams, jin, outs, td, NSEG, side=sname, tag=".flank%d" % thr, with_spliced=False, threads=thr,
+                                                           env=dict(os.environ, TOPHAT_GPU_FLANK_SEARCH="1", TOPHAT_GPU_FLANK_LENGTH="26"))
+                _, got = pyoracle.read_bam(our_bam)
+                assert len(got) == len(want), "%s -p%d: %d records vs %d" % (sname, thr, len(got), len(want))
+                for x, y in zip(got, want):
+                    assert x == y, "record differs:\n ours %r\n ref  %r" % (x, y)
+            total += len(want)
+        ctx.close()
+    return total
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref (reference binaries) not present")
+def test_cli_in_process_junction_index_with_two_read_lengths():
+    import helpers
+    assert mixed_length_cli_check(helpers.our_bin("long_spanning_reads")) > 400
