@@ -232,13 +232,14 @@ def run_reference_arm(args, rank: int, world: int):
 HOST_HANDOFF = False
 
 
-def workload_config(pairs: int, world: int, note: str = ""):
+def workload_config(pairs: int, world: int, note: str = "", join_inputs: str = ""):
     what = {"chr20": "BASELINE configs[1]: synthetic 2x101 bp pairs, chr20-sized (64,444,167 bp) reference, ",
             "hg38": "BASELINE configs[2] sharded by read (50 M pairs over 8 GPUs = 6.25 M per GPU): synthetic 2x101 bp pairs, hg38-sized reference "
                     "(24 contigs, 3.09 Gbp, 0.5% N; 1.2 GB image, not L2-resident), ",
             "indel": "BASELINE configs[3]: indel-heavy synthetic 2x101 bp pairs (1-3 bp indel in half of the mates), chr20-sized reference, "}[WORKLOAD]
-    c = {"workload": what + "4 segments/mate (25/25/25/26), segment hits placed analytically (SURVEY.md 8d)",
-         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)", "handoff": "host" if HOST_HANDOFF else "device-resident sets (value arm); host arrays (e2e arm)",
+    c = {"workload": what + "4 segments/mate (25/25/25/26), genome segment hits placed analytically (SURVEY.md 8d)",
+         "join_inputs": join_inputs or "junction-index segment hits placed analytically",
+         "pairs_per_gpu": pairs, "reads_per_gpu": 2 * pairs, "stages": "segment_juncs (junction / indel discovery) + long_spanning_reads (segment-chain join)",
          "l2": "inputs (>1 GB per step at the default size) exceed the 126 MB L2; no explicit flush",
          "parallelism": "read-shard x%d%s" % (world, " + NCCL all-gather of the junction/indel sets" if world > 1 else "")}
     if note:
@@ -721,7 +722,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                                                  "note": "per GPU: ms_per_step + index build + search of both sides, device times"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong" if args.total_pairs > 0 else "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": workload_config(args.pairs, world),
+                "data": "synthetic", "config": dict(workload_config(args.pairs, world, join_inputs=(
+                    "junction-index segment hits from the junction-flank matcher (thb_flank_*) over the sets of the set-up pass" if flank is not None
+                    else "junction-index segment hits placed analytically")),
+                    handoff="host" if HOST_HANDOFF else "device-resident sets (value arm); host arrays (e2e arm)"),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": E["ms"] / args.steps,
                         "api": "thb_segjuncs_begin/submit(host, pinned)/finish + thb_join_begin/submit(host, pinned); the packed batches are built "
