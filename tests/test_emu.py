@@ -298,3 +298,10 @@ def test_emu_cli_in_process_junction_index_with_two_read_lengths(emu_lib, monkey
     import test_flank
     monkeypatch.setenv("THB_TEST_EMU", "1")
     assert test_flank.mixed_length_cli_check(helpers.our_bin("long_spanning_reads")) > 400
+
+
+@pytest.mark.parametrize("name", ["flank_v2_101bp", "flank_v3_two_word", "flank_v2_m2"])
+def test_emu_flank_matcher_equals_golden(emu_lib, name):
+    """the matcher against the committed golden vectors (FASTA of the reference's juncs_db, placements over it)"""
+    import test_flank
+    assert test_flank.flank_golden_check(name) > 40

@@ -515,3 +515,57 @@ def mixed_length_cli_check(cli_bin, n_pairs=600):
 def test_cli_in_process_junction_index_with_two_read_lengths():
     import helpers
     assert mixed_length_cli_check(helpers.our_bin("long_spanning_reads")) > 400
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# committed golden vectors (scripts/make_flank_golden.py: FASTA of the reference's juncs_db, placements by exhaustion over it)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FLANK_GOLDENS = sorted(d for d in os.listdir(GOLDEN_DIR) if d.startswith("flank_"))
+
+
+def _load_flank_golden(name):
+    import json
+    d = os.path.join(GOLDEN_DIR, name)
+    cfg = json.load(open(os.path.join(d, "config.json")))
+    case = flank_case(cfg["seed"], cfg["max_mismatches"], np.asarray(cfg["seg_bounds"]), cfg["n_reads"], **cfg["kwargs"])
+    fasta = open(os.path.join(d, "juncs_db.fa")).read()
+    want = np.loadtxt(os.path.join(d, "placements.tsv"), dtype=np.int64, ndmin=2).reshape(-1, 6)
+    return cfg, case, fasta, want
+
+
+@pytest.mark.parametrize("name", FLANK_GOLDENS)
+def test_flank_oracle_equals_golden(name):
+    """no reference binary needed: the restated juncs_db and the exhaustive search reproduce the committed outputs"""
+    cfg, case, fasta, want = _load_flank_golden(name)
+    assert flank_oracle.fasta(case["contigs"]) == fasta
+    got = flank_oracle.search([c["codes"] for c in case["contigs"]], case["reads"], case["seg_bounds"], cfg["max_mismatches"], cfg["max_multihits"],
+                              bool(cfg["ref_n_is_mismatch"]))
+    assert got.shape == want.shape and (got == want).all()
+
+
+def flank_golden_check(name):
+    from tophat_b200 import capi, synth
+    cfg, case, fasta, want = _load_flank_golden(name)
+    ctx = capi.Context(0); ctx.ref_upload(case["ref"])
+    ctx.flank_begin(capi.FlankParams(cfg["max_mismatches"], cfg["max_multihits"], case["min_seg_len"], case["max_seg_len"], case["min_anchor"], cfg["ref_n_is_mismatch"]),
+                    *sets_as_records(case))
+    names = [l[1:] for l in fasta.splitlines() if l.startswith(">")]
+    seqs = [l for l in fasta.splitlines() if not l.startswith(">")]
+    contigs = ctx.flank_contigs()
+    assert len(contigs) == len(names)
+    for c, nme, sq in zip(contigs, names, seqs):
+        t = nme.split("|")
+        assert int(c["left_start"]) == int(t[1]) and int(c["length"]) == len(sq), nme
+    rw = (case["reads"].shape[1] + 63) // 64
+    hits = ctx.flank_submit(synth.pack_reads(case["reads"], rw), rw, case["seg_bounds"])
+    got = np.stack([hits[n].astype(np.int64) for n in ("read", "seg", "contig", "pos", "antisense", "mismatches")], axis=1).reshape(-1, 6)
+    assert got.shape == want.shape and (got == want).all()
+    ctx.close()
+    return len(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FLANK_GOLDENS)
+def test_flank_matcher_equals_golden(name):
+    assert flank_golden_check(name) > 40
